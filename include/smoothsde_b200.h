@@ -1,0 +1,160 @@
+/* smoothsde_b200 -- C ABI of the B200-native likelihood engine for smoothSDE's hot path.
+ *
+ * Drop-in boundary.  In the reference, R reaches the objective through TMB's registered .Call
+ * routines (src/init.c:6-15): MakeADFunObject(data, parameters, reportenv, control) deep-copies
+ * the data list into a C++ objective_function and tapes src/smoothSDE.cpp:9-28; EvalADFunObject
+ * (ptr, theta, control) replays the tape for value / gradient; REPORT(aest_all)
+ * (src/nllk/nllk_ctcrw.hpp:249) is read back through the report environment.  This header is
+ * what an R (or any other) host binds instead:
+ *
+ *   reference (.Call, src/init.c)      this library
+ *   -------------------------------    ------------------------------------------------------
+ *   MakeADFunObject        :6          ssde_create        (copies the data list to the GPU once)
+ *   EvalADFunObject        :8          ssde_eval          (order 0: nllk, order 1: + gradient)
+ *   MakeADGradObject       :12         ssde_eval(order = 1)
+ *   MakeADHessObject2      :13         ssde_eval(order = 2)   [reserved, not built yet]
+ *   REPORT(aest_all)                   ssde_report
+ *   getParameterOrder      :11         ssde_n_par / ssde_par_layout
+ *   (external pointer finalizer)       ssde_destroy
+ *   Rf_error                           non-zero return + ssde_last_error / ssde_create_error
+ *
+ * All entry points are extern "C", take plain pointers and sizes, never throw and never call
+ * back into the host.  Everything is fp64.  A handle must not be used concurrently from two
+ * threads.  There is no CPU fallback: every call fails with SSDE_ERR_CUDA if no device exists.
+ */
+#ifndef SMOOTHSDE_B200_H
+#define SMOOTHSDE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ssde_handle ssde_handle;
+
+/* DATA_STRING(type) of src/smoothSDE.cpp:11-25.  BM_t, CIR, BM_SSM, OU_SSM, ESEAL_SSM are not
+ * built (ssde_create returns SSDE_ERR_UNSUPPORTED; the reference says error("Unknown SDE type")
+ * only for names outside its list, smoothSDE.cpp:25 -> SSDE_ERR_UNKNOWN_TYPE here). */
+enum ssde_model { SSDE_BM = 0, SSDE_OU = 1, SSDE_CTCRW = 2 };
+
+enum ssde_status {
+    SSDE_OK = 0,
+    SSDE_ERR_UNKNOWN_TYPE = 1,
+    SSDE_ERR_BAD_ARG = 2,
+    SSDE_ERR_UNSUPPORTED = 3,
+    SSDE_ERR_CUDA = 4,
+    SSDE_ERR_NUMERIC = 5      /* F <= 0 in the filter, scan time-out, ... */
+};
+
+/* dgTMatrix triplets as produced by as_sparse(), R/utility.R:204-213: 0-based i, j; duplicate
+ * (i, j) entries are summed. */
+typedef struct {
+    int64_t nrow, ncol, nnz;
+    const int32_t* i;
+    const int32_t* j;
+    const double* x;
+} ssde_triplet;
+
+enum ssde_shard_flags {
+    SSDE_SHARD_CONT_PREV = 1,  /* first row continues a track that started on the previous shard */
+    SSDE_SHARD_CONT_NEXT = 2,  /* the track of the last row continues on the next shard */
+    SSDE_SHARD_NO_PENALTY = 4  /* smoothing penalty is added by another shard (rank != 0) */
+};
+
+/* The data list that SDE$setup() hands to MakeADFun (R/sde.R:528-536, :569-598), for the rows
+ * of one shard (a whole problem is one shard with shard_flags = 0). */
+typedef struct {
+    int32_t model;            /* enum ssde_model */
+    int32_t n_dim;            /* ncol(obs) = length(response) */
+    int64_t n;                /* rows */
+    const double* ID;         /* [n]  factor codes; only equality of neighbours is used */
+    const double* times;      /* [n] */
+    const double* obs;        /* [n x n_dim] column-major (R matrix); NaN/NA = missing */
+    ssde_triplet X_fe;        /* [(n_par*n) x p_fe]; rows j*n..(j+1)*n-1 belong to parameter j */
+    ssde_triplet X_re;        /* [(n_par*n) x p_re] */
+    ssde_triplet S;           /* [p_re x p_re] block-diagonal penalty */
+    int32_t n_smooth;         /* length(ncol_re) (1 with ncol_re[0] = 0 when there are no smooths) */
+    const int32_t* ncol_re;   /* [n_smooth] */
+    int32_t include_penalty;  /* only honoured for BM/OU, as in the reference (nllk_sde.hpp:91) */
+    int32_t n_ID;             /* CTCRW: rows of a0 (tracks starting on this shard) */
+    const double* a0;         /* CTCRW: [n_ID x 2*n_dim] column-major, (x, 0, y, 0, ...) R/sde.R:574-580 */
+    const double* P0;         /* CTCRW: [2*n_dim x 2*n_dim] column-major, R/sde.R:582-588 */
+    const double* H_array;    /* CTCRW: NULL or array(0) for H = sigma_obs^2 I; user H not built yet */
+    int64_t H_len;
+    int32_t device;           /* CUDA device ordinal */
+    int32_t shard_flags;      /* enum ssde_shard_flags */
+    double t_next;            /* time of the next shard's first row (only with CONT_NEXT) */
+} ssde_desc;
+
+/* Zero-copy variant for data that already lives on the GPU in the engine's native layout
+ * (see smoothsde_b200/csrc/kernels_linpred.cuh).  All d_* pointers are device pointers that must
+ * stay valid for the life of the handle; the rest is host memory and is copied. */
+typedef struct {
+    int32_t model, n_dim, n_par;
+    int64_t n;
+    int64_t nnz;
+    const uint32_t* d_rowptr; /* [n+1] */
+    const uint32_t* d_cnt;    /* [n]   byte p = nonzeros of parameter p in the row */
+    const uint32_t* d_col;    /* [nnz] column in theta = [coeff_fe | coeff_re] */
+    const double* d_val;      /* [nnz] */
+    const double* d_obs;      /* [n x n_dim] ROW-major, missing entries hold any finite value */
+    const double* d_dt;       /* [n] dt_i = t_{i+1} - t_i; 1 on rows flagged LAST */
+    const uint8_t* d_flags;   /* [n] bit0 track start, bit1 track last, bit2 obs present (CTCRW),
+                                 bit(3+d) dimension d missing (BM/OU) */
+    int32_t p_fe, p_re;
+    ssde_triplet S;
+    int32_t n_smooth;
+    const int32_t* ncol_re;
+    int32_t include_penalty;
+    int32_t n_ID;
+    const int64_t* track_starts; /* [n_ID] host, sorted rows flagged as track start */
+    const double* a0;            /* [n_ID x 2*n_dim] host, ROW-major */
+    double P0[3];                /* shared 2x2 block (p11, p12, p22) */
+    int32_t device;
+    int32_t shard_flags;
+} ssde_packed_desc;
+
+int ssde_create(const ssde_desc* desc, ssde_handle** out);
+int ssde_create_packed(const ssde_packed_desc* desc, ssde_handle** out);
+void ssde_destroy(ssde_handle* h);
+
+/* Length of the joint parameter vector and its layout (PARAMETER order of the templates):
+ *   CTCRW : log_sigma_obs, coeff_fe[p_fe], log_lambda[n_smooth], coeff_re[p_re]
+ *           (nllk_ctcrw.hpp:135-140)
+ *   BM/OU : coeff_fe[p_fe], log_lambda[n_smooth], coeff_re[p_re]
+ *           (nllk_sde.hpp:42-45; log_decay is mapped off without decay terms, R/sde.R:648)
+ * offsets[4] = {log_sigma_obs (or -1), coeff_fe, log_lambda, coeff_re}. */
+int ssde_n_par(const ssde_handle* h);
+int ssde_par_layout(const ssde_handle* h, int32_t offsets[4], int32_t sizes[4]);
+
+/* One objective evaluation with HOST buffers (what obj$fn / obj$gr do through EvalADFunObject).
+ *   order 0: *nllk;  order 1: *nllk and grad[ssde_n_par];  order 2: reserved.
+ * Copies `par` to the device, runs the kernels, copies the result back, synchronises. */
+int ssde_eval(ssde_handle* h, const double* par, int order, double* nllk, double* grad, double* hess);
+
+/* Same evaluation with DEVICE buffers and no synchronisation: d_out[0] = nllk (this shard's
+ * part), d_out[1 .. n_par] = gradient.  `stream` is a cudaStream_t (NULL = the handle's own
+ * stream).  Used by the multi-GPU host, which all-reduces d_out over NCCL. */
+int ssde_eval_device(ssde_handle* h, const double* d_par, int order, double* d_out, void* stream);
+/* Check the device-side status word of the last evaluation (synchronises the stream). */
+int ssde_check(ssde_handle* h);
+
+/* REPORT(aest_all): [n x 2*n_dim] column-major predicted-state means after each row
+ * (nllk_ctcrw.hpp:192-194, :246-249) at the parameters of the last ssde_eval. */
+int ssde_report(ssde_handle* h, double* aest_all);
+
+/* Device time in milliseconds of the kernels of the last ssde_eval / ssde_eval_device on the
+ * handle's own stream (CUDA events around the launches). */
+double ssde_last_eval_ms(ssde_handle* h);
+/* Number of kernels the last evaluation launched. */
+int ssde_last_eval_launches(const ssde_handle* h);
+
+const char* ssde_last_error(const ssde_handle* h);
+const char* ssde_create_error(void);
+const char* ssde_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMOOTHSDE_B200_H */

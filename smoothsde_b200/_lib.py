@@ -1,0 +1,105 @@
+"""ctypes binding of the C ABI (include/smoothsde_b200.h).  Fails loudly if the library is
+missing: there is no CPU fallback in the product path."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libsmoothsde_b200.so")
+
+c_double_p = C.POINTER(C.c_double)
+c_int32_p = C.POINTER(C.c_int32)
+c_int64_p = C.POINTER(C.c_int64)
+
+SSDE_BM, SSDE_OU, SSDE_CTCRW = 0, 1, 2
+MODEL_CODES = {"BM": SSDE_BM, "OU": SSDE_OU, "CTCRW": SSDE_CTCRW}
+KNOWN_UNBUILT = ("BM_t", "CIR", "BM_SSM", "OU_SSM", "ESEAL_SSM")
+
+SHARD_CONT_PREV, SHARD_CONT_NEXT, SHARD_NO_PENALTY = 1, 2, 4
+
+STATUS = {0: "OK", 1: "UNKNOWN_TYPE", 2: "BAD_ARG", 3: "UNSUPPORTED", 4: "CUDA", 5: "NUMERIC"}
+
+
+class Triplet(C.Structure):
+    _fields_ = [("nrow", C.c_int64), ("ncol", C.c_int64), ("nnz", C.c_int64),
+                ("i", c_int32_p), ("j", c_int32_p), ("x", c_double_p)]
+
+
+class Desc(C.Structure):
+    _fields_ = [("model", C.c_int32), ("n_dim", C.c_int32), ("n", C.c_int64),
+                ("ID", c_double_p), ("times", c_double_p), ("obs", c_double_p),
+                ("X_fe", Triplet), ("X_re", Triplet), ("S", Triplet),
+                ("n_smooth", C.c_int32), ("ncol_re", c_int32_p), ("include_penalty", C.c_int32),
+                ("n_ID", C.c_int32), ("a0", c_double_p), ("P0", c_double_p),
+                ("H_array", c_double_p), ("H_len", C.c_int64),
+                ("device", C.c_int32), ("shard_flags", C.c_int32), ("t_next", C.c_double)]
+
+
+class PackedDesc(C.Structure):
+    _fields_ = [("model", C.c_int32), ("n_dim", C.c_int32), ("n_par", C.c_int32),
+                ("n", C.c_int64), ("nnz", C.c_int64),
+                ("d_rowptr", C.c_void_p), ("d_cnt", C.c_void_p), ("d_col", C.c_void_p),
+                ("d_val", C.c_void_p), ("d_obs", C.c_void_p), ("d_dt", C.c_void_p),
+                ("d_flags", C.c_void_p),
+                ("p_fe", C.c_int32), ("p_re", C.c_int32), ("S", Triplet),
+                ("n_smooth", C.c_int32), ("ncol_re", c_int32_p), ("include_penalty", C.c_int32),
+                ("n_ID", C.c_int32), ("track_starts", c_int64_p), ("a0", c_double_p),
+                ("P0", C.c_double * 3), ("device", C.c_int32), ("shard_flags", C.c_int32)]
+
+
+class EngineError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"smoothsde_b200 error {code} ({STATUS.get(code, '?')}): {msg}")
+        self.code = code
+
+
+_lib = None
+
+# every symbol include/smoothsde_b200.h declares
+EXPORTS = ["ssde_create", "ssde_create_packed", "ssde_destroy", "ssde_n_par", "ssde_par_layout",
+           "ssde_eval", "ssde_eval_device", "ssde_check", "ssde_report", "ssde_last_eval_ms",
+           "ssde_last_eval_launches", "ssde_last_error", "ssde_create_error", "ssde_version"]
+
+
+def load():
+    """Load libsmoothsde_b200.so (raises if it has not been built)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `python -m smoothsde_b200.build` "
+            "(the engine has no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    lib.ssde_create.argtypes = [C.POINTER(Desc), C.POINTER(vp)]
+    lib.ssde_create.restype = C.c_int
+    lib.ssde_create_packed.argtypes = [C.POINTER(PackedDesc), C.POINTER(vp)]
+    lib.ssde_create_packed.restype = C.c_int
+    lib.ssde_destroy.argtypes = [vp]
+    lib.ssde_destroy.restype = None
+    lib.ssde_n_par.argtypes = [vp]
+    lib.ssde_n_par.restype = C.c_int
+    lib.ssde_par_layout.argtypes = [vp, c_int32_p, c_int32_p]
+    lib.ssde_par_layout.restype = C.c_int
+    lib.ssde_eval.argtypes = [vp, c_double_p, C.c_int, c_double_p, c_double_p, c_double_p]
+    lib.ssde_eval.restype = C.c_int
+    lib.ssde_eval_device.argtypes = [vp, vp, C.c_int, vp, vp]
+    lib.ssde_eval_device.restype = C.c_int
+    lib.ssde_check.argtypes = [vp]
+    lib.ssde_check.restype = C.c_int
+    lib.ssde_report.argtypes = [vp, c_double_p]
+    lib.ssde_report.restype = C.c_int
+    lib.ssde_last_eval_ms.argtypes = [vp]
+    lib.ssde_last_eval_ms.restype = C.c_double
+    lib.ssde_last_eval_launches.argtypes = [vp]
+    lib.ssde_last_eval_launches.restype = C.c_int
+    lib.ssde_last_error.argtypes = [vp]
+    lib.ssde_last_error.restype = C.c_char_p
+    lib.ssde_create_error.argtypes = []
+    lib.ssde_create_error.restype = C.c_char_p
+    lib.ssde_version.argtypes = []
+    lib.ssde_version.restype = C.c_char_p
+    _lib = lib
+    return lib

@@ -1,0 +1,259 @@
+// Shared device utilities: warp shuffles of multi-double elements, coalesced tile staging with a
+// conflict-free transposed shared-memory layout, block reductions, and the chained
+// ("decoupled look-back") tile-prefix protocol used by the forward and adjoint scans.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ctcrw_math.cuh"
+
+namespace ssde {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+// row flags (uint8 per row)
+enum : uint8_t {
+    ROW_START = 1,     // first row of a track (ID(i) != ID(i-1)); never set for a continued shard
+    ROW_LAST = 2,      // last row of a track: its prediction / outgoing transition is discarded
+    ROW_OBS = 4,       // CTCRW: obs(i,0) is not NA (nllk_ctcrw.hpp:214 tests column 0 only)
+    ROW_NA0 = 8,       // BM/OU: dimension d of this row is NA  -> bit (3 + d)
+};
+
+// ---------------------------------------------------------------------------------------------
+// elements as arrays of doubles
+// ---------------------------------------------------------------------------------------------
+template <class E>
+__device__ __forceinline__ E shfl_down_elem(const E& e, int delta) {
+    E r;
+    const double* s = reinterpret_cast<const double*>(&e);
+    double* d = reinterpret_cast<double*>(&r);
+#pragma unroll
+    for (int i = 0; i < E::NDBL; ++i) d[i] = __shfl_down_sync(FULL, s[i], delta);
+    return r;
+}
+template <class E>
+__device__ __forceinline__ E shfl_up_elem(const E& e, int delta) {
+    E r;
+    const double* s = reinterpret_cast<const double*>(&e);
+    double* d = reinterpret_cast<double*>(&r);
+#pragma unroll
+    for (int i = 0; i < E::NDBL; ++i) d[i] = __shfl_up_sync(FULL, s[i], delta);
+    return r;
+}
+template <class E>
+__device__ __forceinline__ E shfl_idx_elem(const E& e, int src) {
+    E r;
+    const double* s = reinterpret_cast<const double*>(&e);
+    double* d = reinterpret_cast<double*>(&r);
+#pragma unroll
+    for (int i = 0; i < E::NDBL; ++i) d[i] = __shfl_sync(FULL, s[i], src);
+    return r;
+}
+template <class E>
+__device__ __forceinline__ void store_elem(double* dst, const E& e) {
+    const double* s = reinterpret_cast<const double*>(&e);
+#pragma unroll
+    for (int i = 0; i < E::NDBL; ++i) dst[i] = s[i];
+}
+template <class E>
+__device__ __forceinline__ E load_elem(const double* src) {
+    E r;
+    double* d = reinterpret_cast<double*>(&r);
+#pragma unroll
+    for (int i = 0; i < E::NDBL; ++i) d[i] = src[i];
+    return r;
+}
+// L2-coherent (L1-bypassing) load of an element published by another CTA
+template <class E>
+__device__ __forceinline__ E load_elem_cg(const double* src) {
+    E r;
+    double* d = reinterpret_cast<double*>(&r);
+#pragma unroll
+    for (int i = 0; i < E::NDBL; ++i) d[i] = __ldcg(src + i);
+    return r;
+}
+
+// Time-ordered composition traits.  join(far, near): `near` covers tiles closer (in processing
+// order) to the current one.  Forward scan processes tiles in time order, so far = earlier in
+// time; the adjoint scan processes tiles in reverse time, so far = later in time.
+template <int ND>
+struct FwdOps {
+    using Elem = FwdElem<ND>;
+    static __device__ __forceinline__ Elem identity() { return fwd_identity<ND>(); }
+    static __device__ __forceinline__ Elem join(const Elem& far, const Elem& near) {
+        return fwd_combine<ND>(far, near);
+    }
+};
+template <int ND>
+struct BwdOps {
+    using Elem = BwdElem<ND>;
+    static __device__ __forceinline__ Elem identity() { return bwd_identity<ND>(); }
+    static __device__ __forceinline__ Elem join(const Elem& far, const Elem& near) {
+        return bwd_combine<ND>(near, far);     // near = earlier rows (E1), far = later rows (E2)
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// reductions
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+
+// Sum over a block of NT threads; result valid in thread 0.  `red` has NT/32 doubles.
+template <int NT>
+__device__ __forceinline__ double block_sum(double v, double* red) {
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < NT / 32; ++i) t += red[i];
+    }
+    return t;
+}
+
+// ---------------------------------------------------------------------------------------------
+// tile staging: rows [r0, r0 + NT*LC) x NC doubles (row-major in global memory) are loaded with
+// coalesced 16-byte loads and stored transposed so that thread t reads component c of its k-th
+// row at  s[(k*NC + c)*(NT + 1) + t]  without bank conflicts.
+// ---------------------------------------------------------------------------------------------
+template <int NC, int NT, int LC>
+struct Staged {
+    static constexpr int STRIDE = NT + 1;
+    static constexpr int SIZE = LC * NC * STRIDE;       // doubles
+    static __device__ __forceinline__ int at(int k, int c, int t) { return (k * NC + c) * STRIDE + t; }
+};
+
+template <int NC, int NT, int LC>
+__device__ __forceinline__ void stage_rows(double* s, const double* __restrict__ g, int64_t r0,
+                                           int64_t n) {
+    using L = Staged<NC, NT, LC>;
+    constexpr int TOTAL = NT * LC * NC;                 // doubles in a full tile
+    const double* base = g + r0 * NC;
+    int64_t valid = (n - r0) * NC;
+    if (valid > TOTAL) valid = TOTAL;
+    if ((TOTAL % 2 == 0) && ((reinterpret_cast<uintptr_t>(base) & 15) == 0)) {
+        const double2* b2 = reinterpret_cast<const double2*>(base);
+        for (int i = threadIdx.x; i < TOTAL / 2; i += NT) {
+            double2 v = make_double2(0.0, 0.0);
+            const int e0 = 2 * i;
+            if (e0 + 1 < valid) v = __ldg(b2 + i);
+            else if (e0 < valid) v.x = __ldg(base + e0);
+            int r = e0 / NC, c = e0 % NC;
+            s[L::at(r % LC, c, r / LC)] = v.x;
+            r = (e0 + 1) / NC; c = (e0 + 1) % NC;
+            s[L::at(r % LC, c, r / LC)] = v.y;
+        }
+    } else {
+        for (int i = threadIdx.x; i < TOTAL; i += NT) {
+            const double v = (i < valid) ? __ldg(base + i) : 0.0;
+            const int r = i / NC, c = i % NC;
+            s[L::at(r % LC, c, r / LC)] = v;
+        }
+    }
+}
+
+// uint8 flags of a tile: s[k*(NT+4) + t]   (row = t*LC + k)
+template <int NT, int LC>
+__device__ __forceinline__ void stage_flags(uint8_t* s, const uint8_t* __restrict__ g, int64_t r0,
+                                            int64_t n) {
+    constexpr int TOTAL = NT * LC;
+    for (int i = threadIdx.x; i < TOTAL; i += NT) {
+        const uint8_t v = (r0 + i < n) ? g[r0 + i] : (uint8_t)0xff;   // 0xff = row beyond the end
+        s[(i % LC) * (NT + 4) + (i / LC)] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// chained tile prefix (decoupled look-back, Merrill & Garland) with multi-double payloads.
+//   status word = (epoch << 2) | code,  code: 1 = aggregate available, 2 = inclusive prefix
+//   available.  A word whose epoch differs from the current launch's counts as "not ready", so
+//   the descriptor arrays never need clearing between evaluations.
+// ---------------------------------------------------------------------------------------------
+struct ScanDesc {
+    unsigned* status;      // [ntiles]
+    double* agg;           // [ntiles * NDBL]
+    double* incl;          // [ntiles * NDBL]
+    unsigned* ticket;      // dynamic tile counter (zeroed by the host before every launch)
+    unsigned* error;       // set to non-zero if a spin-wait times out
+    unsigned epoch;
+};
+
+__device__ __forceinline__ unsigned ld_status(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_status(unsigned* p, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Publish the aggregate of tile `t` (one thread).
+template <class Ops>
+__device__ __forceinline__ void publish_agg(const ScanDesc& d, int t, const typename Ops::Elem& e) {
+    store_elem(d.agg + (size_t)t * Ops::Elem::NDBL, e);
+    __threadfence();
+    st_status(d.status + t, (d.epoch << 2) | 1u);
+}
+template <class Ops>
+__device__ __forceinline__ void publish_incl(const ScanDesc& d, int t, const typename Ops::Elem& e) {
+    store_elem(d.incl + (size_t)t * Ops::Elem::NDBL, e);
+    __threadfence();
+    st_status(d.status + t, (d.epoch << 2) | 2u);
+}
+
+// Executed by one full warp.  Returns (in every lane) the composite of all tiles processed
+// before ticket `t` (identity for t == 0).
+template <class Ops>
+__device__ __forceinline__ typename Ops::Elem lookback(const ScanDesc& d, int t) {
+    using Elem = typename Ops::Elem;
+    const int lane = threadIdx.x & 31;
+    Elem acc = Ops::identity();
+    int base = t - 1;
+    while (base >= 0) {
+        const int idx = base - lane;
+        unsigned st = 2u;                                  // virtual tile -1: identity prefix
+        unsigned spins = 0;
+        while (true) {
+            bool ready = true;
+            if (idx >= 0) {
+                st = ld_status(d.status + idx);
+                ready = (st >> 2) == d.epoch;
+            }
+            if (__all_sync(FULL, ready)) break;
+            if (++spins > (1u << 22)) {                    // ~seconds: give up instead of hanging
+                if (lane == 0) atomicExch(d.error, 1u);
+                return acc;
+            }
+            __nanosleep(40);
+        }
+        const unsigned code = (idx >= 0) ? (st & 3u) : 2u;
+        const unsigned pmask = __ballot_sync(FULL, code == 2u);
+        const int first = pmask ? (__ffs(pmask) - 1) : 32;
+        Elem e = Ops::identity();
+        if (idx >= 0) {
+            if (lane < first) e = load_elem_cg<Elem>(d.agg + (size_t)idx * Elem::NDBL);
+            else if (lane == first) e = load_elem_cg<Elem>(d.incl + (size_t)idx * Elem::NDBL);
+        }
+        // ordered tree reduction: higher lanes are farther away
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            Elem f = shfl_down_elem(e, o);
+            if (lane + o < 32) e = Ops::join(f, e);
+        }
+        e = shfl_idx_elem(e, 0);
+        acc = Ops::join(e, acc);
+        if (pmask) break;
+        base -= 32;
+    }
+    return acc;
+}
+
+}  // namespace ssde

@@ -1,0 +1,525 @@
+// CTCRW Kalman filter algebra for the time-parallel (associative-scan) likelihood engine.
+//
+// Everything in this header is a small inline function usable from device code (the CUDA
+// kernels in kernels_ctcrw.cuh) and from host code (tests/harness/math_harness.cpp compiles it
+// with g++ to check the algebra against the oracle without a GPU -- test infrastructure only,
+// the product path always runs these functions on the device).
+//
+// What is being computed (reference: src/nllk/nllk_ctcrw.hpp:195-247, helpers :30-91):
+//   state at row i = predicted (a, P) for row i;  row i (same track, obs present) does
+//     u = y - Z a;  F = Z P Z' + H;  llk -= (log|F| + u'F^-1 u)/2;
+//     K = T P Z' F^-1;  a <- T a + K u + B mu;  P <- T P L' + Q,  L = T - K Z
+//   with T, Q, B built from (beta_i, sigma_i, dt_i = t_{i+1} - t_i).
+//
+// Decoupled representation.  With H = sigma_obs^2 I (makeH_ctcrw, :30-38) and a block-diagonal
+// P0 with identical 2x2 blocks (the default diag(1,10,1,10), R/sde.R:584) the 2d-state filter
+// is d independent 2-state (position, velocity) filters that share one covariance recursion:
+//   P = [[p11,p12],[p12,p22]] (3 doubles),  a_d = (z_d, v_d) per dimension,
+//   F = p11 + h,  log|F| = d log F,  u'F^-1u = sum_d u_d^2 / F.
+//
+// Time-parallel formulation (Sarkka & Garcia-Fernandez 2021, prediction form).  Row i is the map
+//   s_i -> s_{i+1}:  "update with y_i, then predict with (T_i, Q_i, c_i)",
+// which is the element (A, b, C, eta, J) = (T_i, c_i, Q_i, Z'y_i/h, Z'Z/h); a missing row has
+// eta = J = 0 and a track-start row is the constant map (A = 0, b = a0, C = P0).  Elements
+// compose associatively (fwd_combine); a thread composes its consecutive rows with the cheap
+// fwd_append (one Kalman step on (b, C) plus the A/eta/J bookkeeping).
+//
+// The hand-derived adjoint (gradient) is again a scan, in reverse time, over elements
+// (L, z, D):  (abar, Pbar) <- (L'abar+ - z,  L'Pbar+ L + sum_d sym(L'abar+_d z_d') + D).
+#pragma once
+
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define SSDE_HD __host__ __device__ __forceinline__
+#else
+#define SSDE_HD inline
+#endif
+
+namespace ssde {
+
+// ---------------------------------------------------------------------------------------------
+// small types
+// ---------------------------------------------------------------------------------------------
+struct Sym2 {            // symmetric 2x2: [[a, b], [b, c]]
+    double a, b, c;
+};
+struct Mat2 {            // general 2x2: [[m11, m12], [m21, m22]]
+    double m11, m12, m21, m22;
+};
+struct Vec2 {
+    double x, y;
+};
+
+template <int ND>
+struct State {           // predicted state: per-dimension mean (z, v) + shared covariance
+    Vec2 a[ND];
+    Sym2 P;
+};
+
+// Per-row step quantities derived from the transformed parameters (tau, e = exp(-dt/tau),
+// s2 = sigma^2) and dt.  makeT/makeQ/makeB_ctcrw, nllk_ctcrw.hpp:45-91, written in tau = 1/beta
+// so that no division is needed:  (1-e)/beta = (1-e) tau, (sigma/beta)^2 = s2 tau^2, ...
+struct StepPar {
+    double T12, e;       // T = [[1, T12], [0, e]]
+    Sym2 Q;
+    double B1, B2;       // B mu = (B1 mu, B2 mu)
+};
+
+SSDE_HD StepPar make_step(double tau, double e, double s2, double dt) {
+    StepPar s;
+    const double om = 1.0 - e;
+    const double ome2 = 1.0 - e * e;
+    s.T12 = om * tau;
+    s.e = e;
+    const double st2 = s2 * tau * tau;
+    s.Q.a = st2 * (dt - 2.0 * tau * om + 0.5 * tau * ome2);   // :68-69
+    s.Q.b = 0.5 * st2 * om * om;                              // :70
+    s.Q.c = 0.5 * s2 * tau * ome2;                            // :72
+    s.B1 = dt - om * tau;                                     // :87
+    s.B2 = om;                                                // :88
+    return s;
+}
+
+// Natural-scale transform of one linear-predictor row, nllk_ctcrw.hpp:152-156:
+//   tau = exp(eta_tau), nu = exp(eta_nu), sigma = 2 nu / sqrt(pi tau)  =>  s2 = 4 nu^2/(pi tau)
+SSDE_HD void transform_row(double eta_tau, double eta_nu, double dt, double& tau, double& e,
+                           double& s2) {
+    tau = exp(eta_tau);
+    const double nu = exp(eta_nu);
+    s2 = (4.0 / 3.14159265358979323846) * nu * nu / tau;
+    e = exp(-dt / tau);
+}
+
+// ---------------------------------------------------------------------------------------------
+// sequential filter step (prediction form), one row
+// ---------------------------------------------------------------------------------------------
+// Intermediate quantities of a step that the adjoint needs.
+template <int ND>
+struct StepAux {
+    double F, iF, g1, g2;        // F = p11 + h, gain G = (g1, g2) = P e1 / F
+    double w[ND];                // w_d = u_d / F
+    double afv[ND];              // filtered velocity a_f,d,v
+    double tp12, tp22;           // (T P_f)_12, (T P_f)_22
+};
+
+// Advances `s` (predicted state of row i) to the predicted state of row i+1 and returns the
+// row's log-likelihood contribution  -(d log F + sum u^2/F)/2  (0 if the row is missing).
+// `has_obs` false reproduces the missing branch (:214-217).
+template <int ND, bool WITH_AUX>
+SSDE_HD double fwd_step(State<ND>& s, const StepPar& sp, const double* y, const double* mu,
+                        bool has_obs, double h, StepAux<ND>* aux) {
+    double llk = 0.0;
+    Sym2 Pf = s.P;
+    Vec2 af[ND];
+#pragma unroll
+    for (int d = 0; d < ND; ++d) af[d] = s.a[d];
+    if (has_obs) {
+        const double F = s.P.a + h;                     // :223
+        const double iF = 1.0 / F;
+        const double g1 = s.P.a * iF, g2 = s.P.b * iF;
+        double quad = 0.0;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+            const double u = y[d] - s.a[d].x;           // :221
+            const double w = u * iF;
+            quad += u * w;
+            af[d].x = s.a[d].x + g1 * u;
+            af[d].y = s.a[d].y + g2 * u;
+            if (WITH_AUX) aux->w[d] = w;
+        }
+        llk = -0.5 * ((double)ND * log(F) + quad);      // :231-234 (no d*log(2 pi))
+        Pf.a = s.P.a - g1 * s.P.a;                      // P - F G G'
+        Pf.b = s.P.b - g1 * s.P.b;
+        Pf.c = s.P.c - g2 * s.P.b;
+        if (WITH_AUX) { aux->F = F; aux->iF = iF; aux->g1 = g1; aux->g2 = g2; }
+    } else if (WITH_AUX) {
+        aux->F = 1.0; aux->iF = 0.0; aux->g1 = 0.0; aux->g2 = 0.0;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) aux->w[d] = 0.0;
+    }
+    // predict: a+ = T a_f + B mu,  P+ = T P_f T' + Q      (:238-241 / :216-217)
+    const double tp11 = Pf.a + sp.T12 * Pf.b;
+    const double tp12 = Pf.b + sp.T12 * Pf.c;
+    const double tp22 = sp.e * Pf.c;
+    if (WITH_AUX) { aux->tp12 = tp12; aux->tp22 = tp22; }
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+        if (WITH_AUX) aux->afv[d] = af[d].y;
+        s.a[d].x = af[d].x + sp.T12 * af[d].y + sp.B1 * mu[d];
+        s.a[d].y = sp.e * af[d].y + sp.B2 * mu[d];
+    }
+    s.P.a = tp11 + sp.T12 * tp12 + sp.Q.a;
+    s.P.b = sp.e * tp12 + sp.Q.b;
+    s.P.c = sp.e * tp22 + sp.Q.c;
+    return llk;
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward scan elements
+// ---------------------------------------------------------------------------------------------
+template <int ND>
+struct FwdElem {
+    Mat2 A;
+    Vec2 b[ND];
+    Sym2 C;
+    Vec2 eta[ND];
+    Sym2 J;
+    static constexpr int NDBL = 4 + 2 * ND + 3 + 2 * ND + 3;
+};
+
+template <int ND>
+SSDE_HD FwdElem<ND> fwd_identity() {
+    FwdElem<ND> E;
+    E.A = {1.0, 0.0, 0.0, 1.0};
+    E.C = {0.0, 0.0, 0.0};
+    E.J = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int d = 0; d < ND; ++d) { E.b[d] = {0.0, 0.0}; E.eta[d] = {0.0, 0.0}; }
+    return E;
+}
+
+// Constant map to a known state (track start, or the incoming state of a time shard).
+template <int ND>
+SSDE_HD FwdElem<ND> fwd_const(const State<ND>& s) {
+    FwdElem<ND> E = fwd_identity<ND>();
+    E.A = {0.0, 0.0, 0.0, 0.0};
+    E.C = s.P;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) E.b[d] = s.a[d];
+    return E;
+}
+
+// E <- (element of one ordinary row) o E.   Equivalent to fwd_combine(E, elem_row) but uses the
+// structure J_row = e1 e1'/h, eta_row = e1 y/h:  (b, C) advance by one Kalman step, A <- L A,
+// eta += A_row1' w, J += A_row1' A_row1 / F.
+template <int ND>
+SSDE_HD void fwd_append(FwdElem<ND>& E, const StepPar& sp, const double* y, const double* mu,
+                        bool has_obs, double h) {
+    double L11 = 1.0, L21 = 0.0;           // L = T (I - G e1')
+    if (has_obs) {
+        const double F = E.C.a + h;
+        const double iF = 1.0 / F;
+        const double g1 = E.C.a * iF, g2 = E.C.b * iF;
+        const double a11 = E.A.m11, a12 = E.A.m12;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+            const double u = y[d] - E.b[d].x;
+            const double w = u * iF;
+            E.eta[d].x += a11 * w;
+            E.eta[d].y += a12 * w;
+            E.b[d].x += g1 * u;
+            E.b[d].y += g2 * u;
+        }
+        E.J.a += a11 * a11 * iF;
+        E.J.b += a11 * a12 * iF;
+        E.J.c += a12 * a12 * iF;
+        const double c11 = E.C.a, c12 = E.C.b;
+        E.C.a = c11 - g1 * c11;
+        E.C.b = c12 - g1 * c12;
+        E.C.c = E.C.c - g2 * c12;
+        L11 = 1.0 - g1 - sp.T12 * g2;
+        L21 = -sp.e * g2;
+    }
+    // A <- L A with L = [[L11, T12], [L21, e]]
+    const Mat2 A = E.A;
+    E.A.m11 = L11 * A.m11 + sp.T12 * A.m21;
+    E.A.m12 = L11 * A.m12 + sp.T12 * A.m22;
+    E.A.m21 = L21 * A.m11 + sp.e * A.m21;
+    E.A.m22 = L21 * A.m12 + sp.e * A.m22;
+    // predict (b, C)
+    const double tp11 = E.C.a + sp.T12 * E.C.b;
+    const double tp12 = E.C.b + sp.T12 * E.C.c;
+    const double tp22 = sp.e * E.C.c;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+        const double bx = E.b[d].x, by = E.b[d].y;
+        E.b[d].x = bx + sp.T12 * by + sp.B1 * mu[d];
+        E.b[d].y = sp.e * by + sp.B2 * mu[d];
+    }
+    E.C.a = tp11 + sp.T12 * tp12 + sp.Q.a;
+    E.C.b = sp.e * tp12 + sp.Q.b;
+    E.C.c = sp.e * tp22 + sp.Q.c;
+}
+
+// E <- (track-start element with state s0) o E : the constant map wins; eta, J keep describing
+// the dependence of everything *before* the start on the incoming state.
+template <int ND>
+SSDE_HD void fwd_append_start(FwdElem<ND>& E, const State<ND>& s0) {
+    E.A = {0.0, 0.0, 0.0, 0.0};
+    E.C = s0.P;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) E.b[d] = s0.a[d];
+}
+
+// General composition: `Ei` covers earlier rows, `Ej` later rows.
+//   M = (I + C_i J_j)^-1
+//   A = A_j M A_i;  b = A_j M (b_i + C_i eta_j) + b_j;  C = A_j M C_i A_j' + C_j
+//   eta = A_i' M' (eta_j - J_j b_i) + eta_i;  J = A_i' M' J_j A_i + J_i
+template <int ND>
+SSDE_HD FwdElem<ND> fwd_combine(const FwdElem<ND>& Ei, const FwdElem<ND>& Ej) {
+    FwdElem<ND> R;
+    const Sym2 C = Ei.C, J = Ej.J;
+    const double x11 = 1.0 + C.a * J.a + C.b * J.b;
+    const double x12 = C.a * J.b + C.b * J.c;
+    const double x21 = C.b * J.a + C.c * J.b;
+    const double x22 = 1.0 + C.b * J.b + C.c * J.c;
+    const double idet = 1.0 / (x11 * x22 - x12 * x21);
+    const Mat2 M = {x22 * idet, -x12 * idet, -x21 * idet, x11 * idet};
+    // AM = A_j M
+    const Mat2 Aj = Ej.A;
+    const Mat2 AM = {Aj.m11 * M.m11 + Aj.m12 * M.m21, Aj.m11 * M.m12 + Aj.m12 * M.m22,
+                     Aj.m21 * M.m11 + Aj.m22 * M.m21, Aj.m21 * M.m12 + Aj.m22 * M.m22};
+    const Mat2 Ai = Ei.A;
+    R.A = {AM.m11 * Ai.m11 + AM.m12 * Ai.m21, AM.m11 * Ai.m12 + AM.m12 * Ai.m22,
+           AM.m21 * Ai.m11 + AM.m22 * Ai.m21, AM.m21 * Ai.m12 + AM.m22 * Ai.m22};
+    // AMC = A_j M C_i  (2x2), then C = AMC A_j' + C_j
+    const Mat2 AMC = {AM.m11 * C.a + AM.m12 * C.b, AM.m11 * C.b + AM.m12 * C.c,
+                      AM.m21 * C.a + AM.m22 * C.b, AM.m21 * C.b + AM.m22 * C.c};
+    R.C.a = AMC.m11 * Aj.m11 + AMC.m12 * Aj.m12 + Ej.C.a;
+    R.C.b = 0.5 * ((AMC.m11 * Aj.m21 + AMC.m12 * Aj.m22) + (AMC.m21 * Aj.m11 + AMC.m22 * Aj.m12))
+            + Ej.C.b;
+    R.C.c = AMC.m21 * Aj.m21 + AMC.m22 * Aj.m22 + Ej.C.c;
+    // MtJ = M' J_j ;  J = A_i' MtJ A_i + J_i
+    const Mat2 MtJ = {M.m11 * J.a + M.m21 * J.b, M.m11 * J.b + M.m21 * J.c,
+                      M.m12 * J.a + M.m22 * J.b, M.m12 * J.b + M.m22 * J.c};
+    // AtN = A_i' M'  (2x2)
+    const Mat2 AtN = {Ai.m11 * M.m11 + Ai.m21 * M.m12, Ai.m11 * M.m21 + Ai.m21 * M.m22,
+                      Ai.m12 * M.m11 + Ai.m22 * M.m12, Ai.m12 * M.m21 + Ai.m22 * M.m22};
+    // W = A_i' (M' J_j)  then J = W A_i + J_i
+    const Mat2 W = {Ai.m11 * MtJ.m11 + Ai.m21 * MtJ.m21, Ai.m11 * MtJ.m12 + Ai.m21 * MtJ.m22,
+                    Ai.m12 * MtJ.m11 + Ai.m22 * MtJ.m21, Ai.m12 * MtJ.m12 + Ai.m22 * MtJ.m22};
+    R.J.a = W.m11 * Ai.m11 + W.m12 * Ai.m21 + Ei.J.a;
+    R.J.b = 0.5 * ((W.m11 * Ai.m12 + W.m12 * Ai.m22) + (W.m21 * Ai.m11 + W.m22 * Ai.m21)) + Ei.J.b;
+    R.J.c = W.m21 * Ai.m12 + W.m22 * Ai.m22 + Ei.J.c;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+        const Vec2 bi = Ei.b[d], ej = Ej.eta[d];
+        // t = b_i + C_i eta_j
+        const double t1 = bi.x + C.a * ej.x + C.b * ej.y;
+        const double t2 = bi.y + C.b * ej.x + C.c * ej.y;
+        R.b[d].x = AM.m11 * t1 + AM.m12 * t2 + Ej.b[d].x;
+        R.b[d].y = AM.m21 * t1 + AM.m22 * t2 + Ej.b[d].y;
+        // r = eta_j - J_j b_i
+        const double r1 = ej.x - (J.a * bi.x + J.b * bi.y);
+        const double r2 = ej.y - (J.b * bi.x + J.c * bi.y);
+        R.eta[d].x = AtN.m11 * r1 + AtN.m12 * r2 + Ei.eta[d].x;
+        R.eta[d].y = AtN.m21 * r1 + AtN.m22 * r2 + Ei.eta[d].y;
+    }
+    return R;
+}
+
+// State after pushing state `s` through element E:  the (b, C) part of fwd_combine(const(s), E).
+template <int ND>
+SSDE_HD State<ND> fwd_apply(const FwdElem<ND>& E, const State<ND>& s) {
+    State<ND> r;
+    const Sym2 C = s.P, J = E.J;
+    const double x11 = 1.0 + C.a * J.a + C.b * J.b;
+    const double x12 = C.a * J.b + C.b * J.c;
+    const double x21 = C.b * J.a + C.c * J.b;
+    const double x22 = 1.0 + C.b * J.b + C.c * J.c;
+    const double idet = 1.0 / (x11 * x22 - x12 * x21);
+    const Mat2 M = {x22 * idet, -x12 * idet, -x21 * idet, x11 * idet};
+    const Mat2 Aj = E.A;
+    const Mat2 AM = {Aj.m11 * M.m11 + Aj.m12 * M.m21, Aj.m11 * M.m12 + Aj.m12 * M.m22,
+                     Aj.m21 * M.m11 + Aj.m22 * M.m21, Aj.m21 * M.m12 + Aj.m22 * M.m22};
+    const Mat2 AMC = {AM.m11 * C.a + AM.m12 * C.b, AM.m11 * C.b + AM.m12 * C.c,
+                      AM.m21 * C.a + AM.m22 * C.b, AM.m21 * C.b + AM.m22 * C.c};
+    r.P.a = AMC.m11 * Aj.m11 + AMC.m12 * Aj.m12 + E.C.a;
+    r.P.b = 0.5 * ((AMC.m11 * Aj.m21 + AMC.m12 * Aj.m22) + (AMC.m21 * Aj.m11 + AMC.m22 * Aj.m12))
+            + E.C.b;
+    r.P.c = AMC.m21 * Aj.m21 + AMC.m22 * Aj.m22 + E.C.c;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+        const double t1 = s.a[d].x + C.a * E.eta[d].x + C.b * E.eta[d].y;
+        const double t2 = s.a[d].y + C.b * E.eta[d].x + C.c * E.eta[d].y;
+        r.a[d].x = AM.m11 * t1 + AM.m12 * t2 + E.b[d].x;
+        r.a[d].y = AM.m21 * t1 + AM.m22 * t2 + E.b[d].y;
+    }
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// adjoint (reverse-time) elements
+// ---------------------------------------------------------------------------------------------
+// Adjoint of a predicted state: abar_d (2 per dim) and the symmetric FULL-matrix adjoint Pbar
+// (inner product <Pbar, dP> = Pbar.a dp11 + 2 Pbar.b dp12 + Pbar.c dp22).
+template <int ND>
+struct Adj {
+    Vec2 a[ND];
+    Sym2 P;
+};
+
+template <int ND>
+SSDE_HD Adj<ND> adj_zero() {
+    Adj<ND> r;
+    r.P = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int d = 0; d < ND; ++d) r.a[d] = {0.0, 0.0};
+    return r;
+}
+
+// Backward element:  abar_d = L' abar+_d - z_d ;
+//                    Pbar   = L' Pbar+ L + sum_d sym(L' abar+_d z_d') + D
+template <int ND>
+struct BwdElem {
+    Mat2 L;
+    Vec2 z[ND];
+    Sym2 D;
+    static constexpr int NDBL = 4 + 2 * ND + 3;
+};
+
+template <int ND>
+SSDE_HD BwdElem<ND> bwd_identity() {
+    BwdElem<ND> E;
+    E.L = {1.0, 0.0, 0.0, 1.0};
+    E.D = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int d = 0; d < ND; ++d) E.z[d] = {0.0, 0.0};
+    return E;
+}
+
+// Constant map to a known adjoint (end of a track: zero; or the incoming adjoint of a shard).
+template <int ND>
+SSDE_HD BwdElem<ND> bwd_const(const Adj<ND>& g) {
+    BwdElem<ND> E;
+    E.L = {0.0, 0.0, 0.0, 0.0};
+    E.D = g.P;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) E.z[d] = {-g.a[d].x, -g.a[d].y};
+    return E;
+}
+
+// Elementary backward element of one ordinary row from its forward intermediates.
+//   obs:      L = T (I - G e1'),  z_d = w_d e1,  D = Fl e1 e1',  Fl = (d/F - sum w^2)/2
+//   missing:  L = T, z = 0, D = 0
+//   `cut`:    the row is the last of its track: its prediction is discarded, i.e. the incoming
+//             adjoint is replaced by zero before the row's own update terms are applied (L = 0).
+template <int ND>
+SSDE_HD BwdElem<ND> bwd_row_elem(const StepPar& sp, const StepAux<ND>& ax, bool has_obs, bool cut) {
+    BwdElem<ND> E;
+    double sw2 = 0.0;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+        E.z[d] = {has_obs ? ax.w[d] : 0.0, 0.0};
+        sw2 += ax.w[d] * ax.w[d];
+    }
+    E.D = {has_obs ? 0.5 * ((double)ND * ax.iF - sw2) : 0.0, 0.0, 0.0};
+    if (cut) {
+        E.L = {0.0, 0.0, 0.0, 0.0};
+    } else {
+        E.L = {1.0 - ax.g1 - sp.T12 * ax.g2, sp.T12, -sp.e * ax.g2, sp.e};
+    }
+    return E;
+}
+
+// Composition: E1 covers EARLIER rows (applied last in reverse time), E2 later rows.
+//   L = L2 L1;  z = L1' z2 + z1;  D = L1' D2 L1 + D1 - sum_d sym(L1' z2_d z1_d')
+template <int ND>
+SSDE_HD BwdElem<ND> bwd_combine(const BwdElem<ND>& E1, const BwdElem<ND>& E2) {
+    BwdElem<ND> R;
+    const Mat2 L1 = E1.L, L2 = E2.L;
+    R.L = {L2.m11 * L1.m11 + L2.m12 * L1.m21, L2.m11 * L1.m12 + L2.m12 * L1.m22,
+           L2.m21 * L1.m11 + L2.m22 * L1.m21, L2.m21 * L1.m12 + L2.m22 * L1.m22};
+    // L1' D2 L1
+    const Sym2 D2 = E2.D;
+    const double q11 = D2.a * L1.m11 + D2.b * L1.m21, q12 = D2.a * L1.m12 + D2.b * L1.m22;
+    const double q21 = D2.b * L1.m11 + D2.c * L1.m21, q22 = D2.b * L1.m12 + D2.c * L1.m22;
+    R.D.a = L1.m11 * q11 + L1.m21 * q21 + E1.D.a;
+    R.D.b = 0.5 * ((L1.m11 * q12 + L1.m21 * q22) + (L1.m12 * q11 + L1.m22 * q21)) + E1.D.b;
+    R.D.c = L1.m12 * q12 + L1.m22 * q22 + E1.D.c;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+        const double t1 = L1.m11 * E2.z[d].x + L1.m21 * E2.z[d].y;   // L1' z2
+        const double t2 = L1.m12 * E2.z[d].x + L1.m22 * E2.z[d].y;
+        const Vec2 z1 = E1.z[d];
+        R.z[d] = {t1 + z1.x, t2 + z1.y};
+        R.D.a -= t1 * z1.x;
+        R.D.b -= 0.5 * (t1 * z1.y + t2 * z1.x);
+        R.D.c -= t2 * z1.y;
+    }
+    return R;
+}
+
+// Adjoint at the start of E's range given the adjoint `g` flowing in at its end.
+template <int ND>
+SSDE_HD Adj<ND> bwd_apply(const BwdElem<ND>& E, const Adj<ND>& g) {
+    Adj<ND> r;
+    const Mat2 L = E.L;
+    const Sym2 P = g.P;
+    const double q11 = P.a * L.m11 + P.b * L.m21, q12 = P.a * L.m12 + P.b * L.m22;
+    const double q21 = P.b * L.m11 + P.c * L.m21, q22 = P.b * L.m12 + P.c * L.m22;
+    r.P.a = L.m11 * q11 + L.m21 * q21 + E.D.a;
+    r.P.b = 0.5 * ((L.m11 * q12 + L.m21 * q22) + (L.m12 * q11 + L.m22 * q21)) + E.D.b;
+    r.P.c = L.m12 * q12 + L.m22 * q22 + E.D.c;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+        const double t1 = L.m11 * g.a[d].x + L.m21 * g.a[d].y;       // L' abar+
+        const double t2 = L.m12 * g.a[d].x + L.m22 * g.a[d].y;
+        r.a[d] = {t1 - E.z[d].x, t2 - E.z[d].y};
+        r.P.a += t1 * E.z[d].x;
+        r.P.b += 0.5 * (t1 * E.z[d].y + t2 * E.z[d].x);
+        r.P.c += t2 * E.z[d].y;
+    }
+    return r;
+}
+
+// Gradient of one row w.r.t. its linear predictors, given the adjoint `g` of the state this row
+// PREDICTS (row i+1's predicted state), the row's transformed parameters and its forward
+// intermediates.  Outputs: gmu[d] = d nllk / d eta_mu_d,  g_tau = d/d eta_tau,  g_nu = d/d eta_nu,
+// and the contribution to d nllk / d h  (h = sigma_obs^2), which also needs the update part.
+template <int ND>
+SSDE_HD void row_param_grad(const Adj<ND>& g, const StepPar& sp, const StepAux<ND>& ax,
+                            const double* mu, double tau, double e, double s2, double dt,
+                            bool has_obs, double* gmu, double& g_tau, double& g_nu, double& g_h) {
+    // predict part: c_d = B mu_d, Q, T
+    double B1b = 0.0, B2b = 0.0, T12b = 0.0, T22b = 0.0;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+        gmu[d] = sp.B1 * g.a[d].x + sp.B2 * g.a[d].y;
+        B1b += g.a[d].x * mu[d];
+        B2b += g.a[d].y * mu[d];
+        T12b += g.a[d].x * ax.afv[d];
+        T22b += g.a[d].y * ax.afv[d];
+    }
+    T12b += 2.0 * (g.P.a * ax.tp12 + g.P.b * ax.tp22);
+    T22b += 2.0 * (g.P.b * ax.tp12 + g.P.c * ax.tp22);
+    const double om = 1.0 - e, ome2 = 1.0 - e * e;
+    const double q1 = dt - 2.0 * tau * om + 0.5 * tau * ome2;
+    const double Q11b = g.P.a, Q12b = 2.0 * g.P.b, Q22b = g.P.c;
+    const double st = s2 * tau;
+    const double taub = (T12b - B1b) * om
+                        + Q11b * (2.0 * st * q1 + st * tau * (0.5 * ome2 - 2.0 * om))
+                        + Q12b * (st * om * om)
+                        + Q22b * (0.5 * s2 * ome2);
+    const double eb = (B1b - T12b) * tau + T22b - B2b
+                      + Q11b * (st * tau * tau * (2.0 - e))
+                      - Q12b * (st * tau * om)
+                      - Q22b * (st * e);
+    const double s2b = Q11b * (tau * tau * q1) + Q12b * (0.5 * tau * tau * om * om)
+                       + Q22b * (0.5 * tau * ome2);
+    g_tau = taub * tau + eb * e * dt / tau - s2b * s2;
+    g_nu = 2.0 * s2b * s2;
+    // update part (only h): hbar = G' Pf_bar G - sum_d w_d (af_bar_d' G) + Fl,
+    // with af_bar_d = T' abar+_d and Pf_bar = T' Pbar+ T.
+    g_h = 0.0;
+    if (has_obs) {
+        // T' Pbar T, T = [[1, T12], [0, e]]
+        const double r11 = g.P.a;
+        const double r12 = g.P.a * sp.T12 + g.P.b * sp.e;
+        const double r22 = sp.T12 * (g.P.a * sp.T12 + g.P.b * sp.e)
+                           + sp.e * (g.P.b * sp.T12 + g.P.c * sp.e);
+        double sw2 = 0.0, acc = 0.0;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+            const double f1 = g.a[d].x;                              // T' abar+
+            const double f2 = sp.T12 * g.a[d].x + sp.e * g.a[d].y;
+            acc += ax.w[d] * (f1 * ax.g1 + f2 * ax.g2);
+            sw2 += ax.w[d] * ax.w[d];
+        }
+        g_h = ax.g1 * (r11 * ax.g1 + r12 * ax.g2) + ax.g2 * (r12 * ax.g1 + r22 * ax.g2) - acc
+              + 0.5 * ((double)ND * ax.iF - sw2);
+    }
+}
+
+}  // namespace ssde

@@ -1,0 +1,761 @@
+// C ABI of the engine (include/smoothsde_b200.h): handle life-cycle, conversion of the
+// reference's data list to the device layout, and the per-evaluation kernel pipeline.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/smoothsde_b200.h"
+#include "kernels_ctcrw.cuh"
+#include "kernels_linpred.cuh"
+
+using namespace ssde;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+constexpr int FWD_NT = 128, FWD_LC = 8;
+constexpr int BWD_NT = 64, BWD_LC = 8;
+static_assert(FWD_LC == BWD_LC, "checkpoints are per LC-row chunk");
+
+#define CUDA_TRY(expr)                                                                       \
+    do {                                                                                     \
+        cudaError_t e__ = (expr);                                                            \
+        if (e__ != cudaSuccess) {                                                            \
+            err = std::string(#expr) + ": " + cudaGetErrorString(e__);                       \
+            return SSDE_ERR_CUDA;                                                            \
+        }                                                                                    \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    bool owned = false;
+    ~DevBuf() { if (owned && p) cudaFree(p); }
+    template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+}  // namespace
+
+struct ssde_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int model = 0, n_dim = 0, n_par = 0;
+    int64_t n = 0, nnz = 0;
+    int n_tracks = 0;
+    int p_fe = 0, p_re = 0, n_s = 0, npar = 0;
+    int o_sig = -1, o_fe = 0, o_ll = 0, o_re = 0;
+    bool has_smooth = false, add_penalty = true, penalty_consts = false;
+    int include_penalty = 1;
+    int shard_flags = 0;
+    int num_sms = 148;
+    Sym2 P0{1.0, 0.0, 10.0};
+    // design + data
+    DevBuf rowptr, cnt, col, val, obs, dt, flags, track_starts, a0;
+    // penalty (CSR of S, per-smooth offsets, constants)
+    DevBuf S_rowptr, S_col, S_val, sm_off;
+    double pen_const = 0.0;
+    // work buffers
+    DevBuf par, theta, grad_theta, W, eta_bar, ckpt, tile_llk, tile_gh, block_llk, out, sb;
+    DevBuf f_status, f_agg, f_incl, b_status, b_agg, b_incl, counters;   // counters: ticket_f, ticket_b, error
+    DevBuf aest;
+    double* h_pinned = nullptr;      // pinned host staging: par in, out back
+    unsigned epoch = 0;
+    int ntiles_f = 0, ntiles_b = 0, grid_lp = 0, grid_f = 0, grid_b = 0;
+    int64_t nchunks = 0;
+    int last_launches = 0;
+    bool timed = false;
+    std::string err;
+
+    ~ssde_handle() {
+        if (h_pinned) cudaFreeHost(h_pinned);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+namespace {
+
+template <class T>
+int dev_alloc(DevBuf& b, size_t count, std::string& err) {
+    b.owned = true;
+    CUDA_TRY(cudaMalloc(&b.p, std::max<size_t>(count, 1) * sizeof(T)));
+    return SSDE_OK;
+}
+template <class T>
+int dev_upload(DevBuf& b, const std::vector<T>& v, std::string& err) {
+    int rc = dev_alloc<T>(b, v.size(), err);
+    if (rc) return rc;
+    if (!v.empty()) CUDA_TRY(cudaMemcpy(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return SSDE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// small kernels: theta gather, finalisation (reductions over tiles, penalty, packing)
+// ---------------------------------------------------------------------------------------------
+__global__ void gather_theta_kernel(const double* __restrict__ par, double* __restrict__ theta,
+                                    int p_fe, int p_re, int o_fe, int o_re) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < p_fe) theta[i] = par[o_fe + i];
+    else if (i < p_fe + p_re) theta[i] = par[o_re + (i - p_fe)];
+}
+
+struct FinArgs {
+    const double* par;
+    const double* grad_theta;
+    const double* part_llk;   // per-tile / per-block log-likelihood partial sums
+    int n_part;
+    const double* tile_gh;    // CTCRW: per-tile d nllk / d h partial sums (or nullptr)
+    int n_gh;
+    const uint32_t* S_rowptr;
+    const uint32_t* S_col;
+    const double* S_val;
+    const int32_t* sm_off;    // [n_s + 1] offsets of the smooth blocks in coeff_re
+    double* sb;               // [p_re] scratch: S b
+    int p_fe, p_re, n_s, npar, o_sig, o_fe, o_ll, o_re;
+    int penalty;              // 0 none, 1 Kalman form (nllk_ctcrw.hpp:254-280), 2 nllk_sde form
+    double pen_const;         // sum_i [Sn_i/2 log(2 pi) - 1/2 log det S_i]  (nllk_sde.hpp:114-116)
+    int want_grad;
+    const unsigned* error;
+    double* out;              // [1 + npar + 1]: nllk, gradient, status
+};
+
+// deterministic sum of a strided array by one block
+__device__ double block_reduce_array(const double* x, int n, double* red) {
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s += x[i];
+    // tree over the block (blockDim = 256)
+    __syncthreads();
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    return red[0];
+}
+
+__global__ void __launch_bounds__(256) finalize_kernel(FinArgs a) {
+    __shared__ double red[256];
+    __shared__ double s_quad[64];
+    const int tid = threadIdx.x;
+    double nllk = -block_reduce_array(a.part_llk, a.n_part, red);
+    __syncthreads();
+    if (a.want_grad) {
+        for (int i = tid; i < a.npar; i += blockDim.x) a.out[1 + i] = 0.0;
+        __syncthreads();
+        if (a.tile_gh) {
+            const double gh = block_reduce_array(a.tile_gh, a.n_gh, red);
+            __syncthreads();
+            if (tid == 0) { const double h = exp(2.0 * a.par[a.o_sig]); a.out[1 + a.o_sig] = 2.0 * h * gh; }
+        }
+        for (int i = tid; i < a.p_fe; i += blockDim.x) a.out[1 + a.o_fe + i] = a.grad_theta[i];
+        for (int i = tid; i < a.p_re; i += blockDim.x) a.out[1 + a.o_re + i] = a.grad_theta[a.p_fe + i];
+    }
+    __syncthreads();
+    if (a.penalty) {
+        const double* b = a.par + a.o_re;
+        for (int r = tid; r < a.p_re; r += blockDim.x) {
+            double acc = 0.0;
+            for (uint32_t k = a.S_rowptr[r]; k < a.S_rowptr[r + 1]; ++k) acc += a.S_val[k] * b[a.S_col[k]];
+            a.sb[r] = acc;
+        }
+        __syncthreads();
+        for (int i0 = 0; i0 < a.n_s; i0 += 64) {
+            // quadratic forms of up to 64 smooths at a time: one warp-strided pass each
+            for (int i = i0; i < a.n_s && i < i0 + 64; ++i) {
+                double q = 0.0;
+                for (int r = a.sm_off[i] + tid; r < a.sm_off[i + 1]; r += blockDim.x) q += b[r] * a.sb[r];
+                __syncthreads();
+                red[tid] = q;
+                __syncthreads();
+                for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+                    if (tid < o) red[tid] += red[tid + o];
+                    __syncthreads();
+                }
+                if (tid == 0) s_quad[i - i0] = red[0];
+                __syncthreads();
+            }
+            if (tid == 0) {
+                for (int i = i0; i < a.n_s && i < i0 + 64; ++i) {
+                    const double Sn = (double)(a.sm_off[i + 1] - a.sm_off[i]);
+                    const double ll = a.par[a.o_ll + i], lam = exp(ll);
+                    nllk += -0.5 * Sn * ll + 0.5 * lam * s_quad[i - i0];
+                    if (a.want_grad) a.out[1 + a.o_ll + i] = -0.5 * Sn + 0.5 * lam * s_quad[i - i0];
+                }
+            }
+            __syncthreads();
+            if (a.want_grad) {
+                for (int i = i0; i < a.n_s && i < i0 + 64; ++i) {
+                    const double lam = exp(a.par[a.o_ll + i]);
+                    for (int r = a.sm_off[i] + tid; r < a.sm_off[i + 1]; r += blockDim.x)
+                        a.out[1 + a.o_re + r] += lam * a.sb[r];
+                }
+            }
+            __syncthreads();
+        }
+        if (tid == 0 && a.penalty == 2) nllk += a.pen_const;
+    }
+    if (tid == 0) {
+        a.out[0] = nllk;
+        a.out[1 + a.npar] = (double)(*a.error);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-side helpers
+// ---------------------------------------------------------------------------------------------
+struct Packed {
+    std::vector<uint32_t> rowptr, cnt, col;
+    std::vector<double> val;
+};
+
+int pack_design(const ssde_desc& d, int n_par, Packed& out, std::string& err) {
+    const int64_t n = d.n;
+    const ssde_triplet* mats[2] = {&d.X_fe, &d.X_re};
+    const int64_t total = d.X_fe.nnz + d.X_re.nnz;
+    struct Ent { uint64_t key; uint32_t col; double x; };
+    std::vector<Ent> ents;
+    ents.reserve(total);
+    for (int m = 0; m < 2; ++m) {
+        const ssde_triplet& T = *mats[m];
+        const uint32_t coff = (m == 0) ? 0u : (uint32_t)d.X_fe.ncol;
+        for (int64_t k = 0; k < T.nnz; ++k) {
+            const int64_t r = T.i[k], c = T.j[k];
+            if (r < 0 || r >= T.nrow || c < 0 || c >= T.ncol) { err = "design triplet index out of range"; return SSDE_ERR_BAD_ARG; }
+            if (T.x[k] == 0.0) continue;
+            const int64_t p = r / n, i = r % n;
+            ents.push_back({(uint64_t)(i * n_par + p), coff + (uint32_t)c, T.x[k]});
+        }
+    }
+    std::sort(ents.begin(), ents.end(), [](const Ent& a, const Ent& b) {
+        return a.key != b.key ? a.key < b.key : a.col < b.col;
+    });
+    out.rowptr.assign(n + 1, 0);
+    out.cnt.assign(n, 0);
+    out.col.clear(); out.val.clear();
+    out.col.reserve(ents.size()); out.val.reserve(ents.size());
+    std::vector<uint32_t> pc(n_par);
+    size_t k = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        out.rowptr[i] = (uint32_t)out.col.size();
+        std::fill(pc.begin(), pc.end(), 0u);
+        while (k < ents.size() && (int64_t)(ents[k].key / n_par) == i) {
+            const int p = (int)(ents[k].key % n_par);
+            const uint32_t c = ents[k].col;
+            double x = ents[k].x;
+            ++k;
+            while (k < ents.size() && ents[k].key == ents[k - 1].key && ents[k].col == c) { x += ents[k].x; ++k; }
+            out.col.push_back(c); out.val.push_back(x);
+            if (++pc[p] > 255u) { err = "more than 255 nonzeros for one (row, parameter)"; return SSDE_ERR_UNSUPPORTED; }
+        }
+        uint32_t w = 0;
+        for (int p = 0; p < n_par; ++p) w |= pc[p] << (8 * p);
+        out.cnt[i] = w;
+        if (out.col.size() > 0xfffffff0ull) { err = "more than 2^32 nonzeros in one shard"; return SSDE_ERR_UNSUPPORTED; }
+    }
+    out.rowptr[n] = (uint32_t)out.col.size();
+    return SSDE_OK;
+}
+
+// log det of a dense SPD block by Cholesky; NaN if not positive definite (the reference's
+// atomic::matinvpd gives garbage there too, nllk_sde.hpp:109-111)
+double logdet_spd(std::vector<double>& A, int m) {
+    double ld = 0.0;
+    for (int j = 0; j < m; ++j) {
+        double s = A[(size_t)j * m + j];
+        for (int k = 0; k < j; ++k) s -= A[(size_t)j * m + k] * A[(size_t)j * m + k];
+        if (!(s > 0.0)) return NAN;
+        const double l = std::sqrt(s);
+        A[(size_t)j * m + j] = l;
+        ld += 2.0 * std::log(l);
+        for (int i = j + 1; i < m; ++i) {
+            double t = A[(size_t)i * m + j];
+            for (int k = 0; k < j; ++k) t -= A[(size_t)i * m + k] * A[(size_t)j * m + k];
+            A[(size_t)i * m + j] = t / l;
+        }
+    }
+    return ld;
+}
+
+int setup_penalty(ssde_handle* h, const ssde_triplet& S, int n_smooth, const int32_t* ncol_re,
+                  std::string& err) {
+    h->n_s = n_smooth;
+    h->has_smooth = n_smooth > 0 && ncol_re[0] > 0;       // `if(ncol_re(0) > 0)`, nllk_ctcrw.hpp:256
+    std::vector<int32_t> off(n_smooth + 1, 0);
+    if (h->has_smooth) {
+        for (int i = 0; i < n_smooth; ++i) off[i + 1] = off[i] + ncol_re[i];
+        if (off[n_smooth] != h->p_re) { err = "sum(ncol_re) != ncol(X_re)"; return SSDE_ERR_BAD_ARG; }
+        if (S.nrow != h->p_re || S.ncol != h->p_re) { err = "S must be p_re x p_re"; return SSDE_ERR_BAD_ARG; }
+    }
+    // CSR of S with duplicates summed
+    std::vector<uint32_t> rp(h->p_re + 1, 0), cols;
+    std::vector<double> vals;
+    if (h->has_smooth) {
+        struct E { int32_t r, c; double x; };
+        std::vector<E> es;
+        for (int64_t k = 0; k < S.nnz; ++k) {
+            if (S.i[k] < 0 || S.i[k] >= S.nrow || S.j[k] < 0 || S.j[k] >= S.ncol) { err = "S triplet index out of range"; return SSDE_ERR_BAD_ARG; }
+            es.push_back({S.i[k], S.j[k], S.x[k]});
+        }
+        std::sort(es.begin(), es.end(), [](const E& a, const E& b) { return a.r != b.r ? a.r < b.r : a.c < b.c; });
+        size_t k = 0;
+        for (int r = 0; r < h->p_re; ++r) {
+            rp[r] = (uint32_t)cols.size();
+            while (k < es.size() && es[k].r == r) {
+                int c = es[k].c; double x = es[k].x; ++k;
+                while (k < es.size() && es[k].r == r && es[k].c == c) { x += es[k].x; ++k; }
+                cols.push_back((uint32_t)c); vals.push_back(x);
+            }
+        }
+        rp[h->p_re] = (uint32_t)cols.size();
+        // additive constants of nllk_sde's penalty (nllk_sde.hpp:109-116)
+        if (h->model != SSDE_CTCRW) {
+            double cst = 0.0;
+            for (int i = 0; i < n_smooth; ++i) {
+                const int m = ncol_re[i], o = off[i];
+                bool diag = true;
+                double ld = 0.0;
+                for (int r = o; r < o + m && diag; ++r)
+                    for (uint32_t q = rp[r]; q < rp[r + 1]; ++q)
+                        if ((int)cols[q] != r && vals[q] != 0.0) { diag = false; break; }
+                if (diag) {
+                    for (int r = o; r < o + m; ++r) {
+                        double dd = 0.0;
+                        for (uint32_t q = rp[r]; q < rp[r + 1]; ++q) if ((int)cols[q] == r) dd += vals[q];
+                        ld += std::log(dd);
+                    }
+                } else {
+                    std::vector<double> A((size_t)m * m, 0.0);
+                    for (int r = o; r < o + m; ++r)
+                        for (uint32_t q = rp[r]; q < rp[r + 1]; ++q) {
+                            const int c = (int)cols[q] - o;
+                            if (c >= 0 && c < m) A[(size_t)(r - o) * m + c] = vals[q];
+                        }
+                    ld = logdet_spd(A, m);
+                }
+                cst += 0.5 * m * std::log(2.0 * M_PI) - 0.5 * ld;
+            }
+            h->pen_const = cst;
+        }
+    }
+    int rc;
+    if ((rc = dev_upload(h->S_rowptr, rp, err))) return rc;
+    if ((rc = dev_upload(h->S_col, cols, err))) return rc;
+    if ((rc = dev_upload(h->S_val, vals, err))) return rc;
+    if ((rc = dev_upload(h->sm_off, off, err))) return rc;
+    if ((rc = dev_alloc<double>(h->sb, h->p_re, err))) return rc;
+    return SSDE_OK;
+}
+
+template <class K>
+int max_grid(K kernel, int nt, size_t smem, int num_sms, std::string& err, int& grid) {
+    int occ = 0;
+    if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, nt, smem));
+    if (occ < 1) { err = "kernel does not fit on an SM"; return SSDE_ERR_CUDA; }
+    grid = occ * num_sms;
+    return SSDE_OK;
+}
+
+template <int ND>
+int ctcrw_grids(ssde_handle* h) {
+    std::string& err = h->err;
+    int rc;
+    using SMF = CtcrwSmem<ND, FWD_NT, FWD_LC>;
+    using SMB = CtcrwSmem<ND, BWD_NT, BWD_LC>;
+    if ((rc = max_grid(ctcrw_fwd_kernel<ND, FWD_NT, FWD_LC>, FWD_NT, SMF::BYTES_FWD, h->num_sms, err, h->grid_f))) return rc;
+    if ((rc = max_grid(ctcrw_bwd_kernel<ND, BWD_NT, BWD_LC>, BWD_NT, SMB::BYTES_BWD, h->num_sms, err, h->grid_b))) return rc;
+    return SSDE_OK;
+}
+
+// allocate the per-evaluation work buffers once the data are on the device
+int finish_setup(ssde_handle* h) {
+    std::string& err = h->err;
+    int rc;
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, h->device));
+    h->num_sms = prop.multiProcessorCount;
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreate(&h->ev0));
+    CUDA_TRY(cudaEventCreate(&h->ev1));
+    const int p = h->p_fe + h->p_re;
+    h->o_sig = (h->model == SSDE_CTCRW) ? 0 : -1;
+    h->o_fe = (h->model == SSDE_CTCRW) ? 1 : 0;
+    h->o_ll = h->o_fe + h->p_fe;
+    h->o_re = h->o_ll + h->n_s;
+    h->npar = h->o_re + h->p_re;
+    if ((rc = dev_alloc<double>(h->par, h->npar, err))) return rc;
+    if ((rc = dev_alloc<double>(h->theta, p, err))) return rc;
+    if ((rc = dev_alloc<double>(h->grad_theta, p, err))) return rc;
+    if ((rc = dev_alloc<double>(h->out, h->npar + 2, err))) return rc;
+    if ((rc = dev_alloc<unsigned>(h->counters, 4, err))) return rc;
+    CUDA_TRY(cudaMemset(h->counters.p, 0, 4 * sizeof(unsigned)));
+    CUDA_TRY(cudaMallocHost(&h->h_pinned, sizeof(double) * (2 * (size_t)h->npar + 4)));
+    h->grid_lp = 4 * h->num_sms;
+    {
+        const int64_t nt = (h->n + LP_NT - 1) / LP_NT;
+        if (nt < h->grid_lp) h->grid_lp = (int)std::max<int64_t>(nt, 1);
+    }
+    if (h->model == SSDE_CTCRW) {
+        const int nd = h->n_dim;
+        const int64_t tile_f = (int64_t)FWD_NT * FWD_LC, tile_b = (int64_t)BWD_NT * BWD_LC;
+        h->ntiles_f = (int)((h->n + tile_f - 1) / tile_f);
+        h->ntiles_b = (int)((h->n + tile_b - 1) / tile_b);
+        h->nchunks = (h->n + FWD_LC - 1) / FWD_LC;
+        // chunk index = tile * NT + tid must stay inside the buffer for partially filled tiles
+        const int64_t nch_alloc = std::max<int64_t>((int64_t)h->ntiles_f * FWD_NT, (int64_t)h->ntiles_b * BWD_NT);
+        h->nchunks = nch_alloc;
+        if ((rc = dev_alloc<double>(h->W, (size_t)h->n * (nd + 3), err))) return rc;
+        if ((rc = dev_alloc<double>(h->eta_bar, (size_t)h->n * (nd + 2), err))) return rc;
+        if ((rc = dev_alloc<double>(h->ckpt, (size_t)nch_alloc * (2 * nd + 3), err))) return rc;
+        if ((rc = dev_alloc<double>(h->tile_llk, h->ntiles_f, err))) return rc;
+        if ((rc = dev_alloc<double>(h->tile_gh, h->ntiles_b, err))) return rc;
+        if ((rc = dev_alloc<unsigned>(h->f_status, h->ntiles_f, err))) return rc;
+        if ((rc = dev_alloc<unsigned>(h->b_status, h->ntiles_b, err))) return rc;
+        CUDA_TRY(cudaMemset(h->f_status.p, 0, sizeof(unsigned) * std::max(h->ntiles_f, 1)));
+        CUDA_TRY(cudaMemset(h->b_status.p, 0, sizeof(unsigned) * std::max(h->ntiles_b, 1)));
+        const size_t fe = (nd == 1) ? FwdElem<1>::NDBL : FwdElem<2>::NDBL;
+        const size_t be = (nd == 1) ? BwdElem<1>::NDBL : BwdElem<2>::NDBL;
+        if ((rc = dev_alloc<double>(h->f_agg, (size_t)h->ntiles_f * fe, err))) return rc;
+        if ((rc = dev_alloc<double>(h->f_incl, (size_t)h->ntiles_f * fe, err))) return rc;
+        if ((rc = dev_alloc<double>(h->b_agg, (size_t)h->ntiles_b * be, err))) return rc;
+        if ((rc = dev_alloc<double>(h->b_incl, (size_t)h->ntiles_b * be, err))) return rc;
+        if (nd == 1) rc = ctcrw_grids<1>(h); else rc = ctcrw_grids<2>(h);
+        if (rc) return rc;
+        h->grid_f = std::min(h->grid_f, std::max(h->ntiles_f, 1));
+        h->grid_b = std::min(h->grid_b, std::max(h->ntiles_b, 1));
+    } else {
+        if ((rc = dev_alloc<double>(h->block_llk, h->grid_lp, err))) return rc;
+    }
+    return SSDE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// evaluation pipeline
+// ---------------------------------------------------------------------------------------------
+template <int ND>
+int launch_ctcrw(ssde_handle* h, const double* d_par, int order, cudaStream_t st, double* aest) {
+    std::string& err = h->err;
+    Design X{h->n, ND + 2, h->rowptr.as<uint32_t>(), h->cnt.as<uint32_t>(), h->col.as<uint32_t>(), h->val.as<double>()};
+    ctcrw_linpred_kernel<ND><<<h->grid_lp, LP_NT, 0, st>>>(X, h->theta.as<double>(), h->dt.as<double>(), h->W.as<double>());
+    ++h->last_launches;
+    CtcrwArgs<ND> a;
+    a.n = h->n;
+    a.W = h->W.as<double>(); a.obs = h->obs.as<double>(); a.dt = h->dt.as<double>(); a.flags = h->flags.as<uint8_t>();
+    a.track_starts = h->track_starts.as<int64_t>(); a.a0 = h->a0.as<double>(); a.n_tracks = h->n_tracks;
+    a.P0 = h->P0; a.par = d_par; a.s_in = nullptr; a.g_in = nullptr;
+    a.ckpt = h->ckpt.as<double>(); a.nchunks = h->nchunks;
+    a.tile_llk = h->tile_llk.as<double>(); a.tile_gh = h->tile_gh.as<double>(); a.eta_bar = h->eta_bar.as<double>();
+    a.aest = aest;
+    unsigned* cnt = h->counters.as<unsigned>();
+    a.fdesc = {h->f_status.as<unsigned>(), h->f_agg.as<double>(), h->f_incl.as<double>(), cnt + 0, cnt + 2, h->epoch};
+    a.bdesc = {h->b_status.as<unsigned>(), h->b_agg.as<double>(), h->b_incl.as<double>(), cnt + 1, cnt + 2, h->epoch};
+    a.ntiles = h->ntiles_f;
+    ctcrw_fwd_kernel<ND, FWD_NT, FWD_LC><<<h->grid_f, FWD_NT, CtcrwSmem<ND, FWD_NT, FWD_LC>::BYTES_FWD, st>>>(a);
+    ++h->last_launches;
+    if (order >= 1) {
+        a.ntiles = h->ntiles_b;
+        ctcrw_bwd_kernel<ND, BWD_NT, BWD_LC><<<h->grid_b, BWD_NT, CtcrwSmem<ND, BWD_NT, BWD_LC>::BYTES_BWD, st>>>(a);
+        linpred_T_kernel<ND + 2><<<h->grid_lp, LP_NT, 0, st>>>(X, h->eta_bar.as<double>(), h->grad_theta.as<double>());
+        h->last_launches += 2;
+    }
+    CUDA_TRY(cudaGetLastError());
+    return SSDE_OK;
+}
+
+template <int MODEL, int ND>
+int launch_sde(ssde_handle* h, int order, cudaStream_t st) {
+    std::string& err = h->err;
+    constexpr int NP = (MODEL == MODEL_BM) ? ND + 1 : ND + 2;
+    Design X{h->n, NP, h->rowptr.as<uint32_t>(), h->cnt.as<uint32_t>(), h->col.as<uint32_t>(), h->val.as<double>()};
+    sde_fused_kernel<MODEL, ND><<<h->grid_lp, LP_NT, 0, st>>>(X, h->theta.as<double>(), h->obs.as<double>(), h->dt.as<double>(),
+                                                             h->flags.as<uint8_t>(), order >= 1, h->grad_theta.as<double>(),
+                                                             h->block_llk.as<double>());
+    ++h->last_launches;
+    CUDA_TRY(cudaGetLastError());
+    return SSDE_OK;
+}
+
+int run_eval(ssde_handle* h, const double* d_par, int order, double* d_out, cudaStream_t st, double* aest) {
+    std::string& err = h->err;
+    if (order < 0 || order > 1) { err = "order must be 0 or 1 (Hessian not built yet)"; return SSDE_ERR_UNSUPPORTED; }
+    h->last_launches = 0;
+    ++h->epoch;
+    if (h->epoch >= (1u << 30)) h->epoch = 1;     // status arrays were zeroed at creation; 0 is never a live epoch
+    const int p = h->p_fe + h->p_re;
+    CUDA_TRY(cudaMemsetAsync(h->counters.p, 0, 3 * sizeof(unsigned), st));
+    if (order >= 1) CUDA_TRY(cudaMemsetAsync(h->grad_theta.p, 0, sizeof(double) * std::max(p, 1), st));
+    gather_theta_kernel<<<(p + 255) / 256, 256, 0, st>>>(d_par, h->theta.as<double>(), h->p_fe, h->p_re, h->o_fe, h->o_re);
+    ++h->last_launches;
+    int rc = SSDE_OK;
+    FinArgs f{};
+    if (h->model == SSDE_CTCRW) {
+        rc = (h->n_dim == 1) ? launch_ctcrw<1>(h, d_par, order, st, aest) : launch_ctcrw<2>(h, d_par, order, st, aest);
+        f.part_llk = h->tile_llk.as<double>(); f.n_part = h->ntiles_f;
+        f.tile_gh = (order >= 1) ? h->tile_gh.as<double>() : nullptr; f.n_gh = h->ntiles_b;
+    } else {
+        if (h->model == SSDE_BM) {
+            if (h->n_dim == 1) rc = launch_sde<MODEL_BM, 1>(h, order, st);
+            else if (h->n_dim == 2) rc = launch_sde<MODEL_BM, 2>(h, order, st);
+            else rc = launch_sde<MODEL_BM, 3>(h, order, st);
+        } else {
+            rc = (h->n_dim == 1) ? launch_sde<MODEL_OU, 1>(h, order, st) : launch_sde<MODEL_OU, 2>(h, order, st);
+        }
+        f.part_llk = h->block_llk.as<double>(); f.n_part = h->grid_lp;
+        f.tile_gh = nullptr; f.n_gh = 0;
+    }
+    if (rc) return rc;
+    f.par = d_par; f.grad_theta = h->grad_theta.as<double>();
+    f.S_rowptr = h->S_rowptr.as<uint32_t>(); f.S_col = h->S_col.as<uint32_t>(); f.S_val = h->S_val.as<double>();
+    f.sm_off = h->sm_off.as<int32_t>(); f.sb = h->sb.as<double>();
+    f.p_fe = h->p_fe; f.p_re = h->p_re; f.n_s = h->n_s; f.npar = h->npar;
+    f.o_sig = h->o_sig; f.o_fe = h->o_fe; f.o_ll = h->o_ll; f.o_re = h->o_re;
+    f.penalty = 0;
+    if (h->has_smooth && h->add_penalty) {
+        if (h->model == SSDE_CTCRW) f.penalty = 1;                       // ignores include_penalty
+        else if (h->include_penalty) f.penalty = 2;
+    }
+    f.pen_const = h->pen_const;
+    f.want_grad = order >= 1;
+    f.error = h->counters.as<unsigned>() + 2;
+    f.out = d_out;
+    finalize_kernel<<<1, 256, 0, st>>>(f);
+    ++h->last_launches;
+    CUDA_TRY(cudaGetLastError());
+    return SSDE_OK;
+}
+
+int check_common(int model, int n_dim, std::string& err) {
+    if (model < 0 || model > 2) { err = "Unknown SDE type"; return SSDE_ERR_UNKNOWN_TYPE; }
+    const int n_par = (model == SSDE_BM) ? n_dim + 1 : n_dim + 2;
+    if (n_dim < 1 || n_par > 4 || (model == SSDE_CTCRW && n_dim > 2)) {
+        err = "n_dim not supported for this model (n_par <= 4; CTCRW n_dim <= 2)";
+        return SSDE_ERR_UNSUPPORTED;
+    }
+    return SSDE_OK;
+}
+
+}  // namespace
+
+// =============================================================================================
+// extern "C"
+// =============================================================================================
+extern "C" {
+
+const char* ssde_version(void) { return "smoothsde_b200 0.1 (sm_100a)"; }
+const char* ssde_create_error(void) { return g_create_error.c_str(); }
+const char* ssde_last_error(const ssde_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+void ssde_destroy(ssde_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    delete h;
+}
+
+int ssde_n_par(const ssde_handle* h) { return h ? h->npar : -1; }
+
+int ssde_par_layout(const ssde_handle* h, int32_t offsets[4], int32_t sizes[4]) {
+    if (!h) return SSDE_ERR_BAD_ARG;
+    offsets[0] = h->o_sig; offsets[1] = h->o_fe; offsets[2] = h->o_ll; offsets[3] = h->o_re;
+    sizes[0] = (h->o_sig >= 0) ? 1 : 0; sizes[1] = h->p_fe; sizes[2] = h->n_s; sizes[3] = h->p_re;
+    return SSDE_OK;
+}
+
+int ssde_create(const ssde_desc* d, ssde_handle** out) {
+    std::string& err = g_create_error;
+    err.clear();
+    if (!d || !out) { err = "null argument"; return SSDE_ERR_BAD_ARG; }
+    *out = nullptr;
+    int rc = check_common(d->model, d->n_dim, err);
+    if (rc) return rc;
+    const int nd = d->n_dim;
+    const int n_par = (d->model == SSDE_BM) ? nd + 1 : nd + 2;
+    const int64_t n = d->n;
+    if (n < 1 || !d->ID || !d->times || !d->obs) { err = "ID, times and obs are required"; return SSDE_ERR_BAD_ARG; }
+    if (d->X_fe.nrow != n_par * n || d->X_re.nrow != n_par * n) { err = "X_fe / X_re must have n_par * n rows"; return SSDE_ERR_BAD_ARG; }
+    if (d->H_array && d->H_len > 1) { err = "user-supplied H_array (coupled filter) is not built yet"; return SSDE_ERR_UNSUPPORTED; }
+    if (cudaSetDevice(d->device) != cudaSuccess) { err = "cudaSetDevice failed: no usable CUDA device (there is no CPU fallback)"; return SSDE_ERR_CUDA; }
+
+    ssde_handle* h = new (std::nothrow) ssde_handle();
+    if (!h) { err = "out of memory"; return SSDE_ERR_BAD_ARG; }
+    h->device = d->device; h->model = d->model; h->n_dim = nd; h->n_par = n_par; h->n = n;
+    h->p_fe = (int)d->X_fe.ncol; h->p_re = (int)d->X_re.ncol;
+    h->include_penalty = d->include_penalty; h->shard_flags = d->shard_flags;
+    h->add_penalty = !(d->shard_flags & SSDE_SHARD_NO_PENALTY);
+    auto fail = [&](int code) { err = h->err.empty() ? err : h->err; delete h; return code; };
+
+    // rows: flags, dt, obs (row-major), track starts
+    std::vector<uint8_t> flags(n, 0);
+    std::vector<double> dt(n, 1.0), obs((size_t)n * nd, 0.0);
+    std::vector<int64_t> starts;
+    for (int64_t i = 0; i < n; ++i) {
+        const bool start = (i == 0) ? !(d->shard_flags & SSDE_SHARD_CONT_PREV) : (d->ID[i] != d->ID[i - 1]);
+        const bool last = (i == n - 1) ? !(d->shard_flags & SSDE_SHARD_CONT_NEXT) : (d->ID[i + 1] != d->ID[i]);
+        uint8_t f = (start ? ROW_START : 0) | (last ? ROW_LAST : 0);
+        for (int k = 0; k < nd; ++k) {
+            const double y = d->obs[(size_t)k * n + i];
+            if (std::isnan(y)) f |= (uint8_t)(ROW_NA0 << k);
+            else obs[(size_t)i * nd + k] = y;
+        }
+        if (!std::isnan(d->obs[i])) f |= ROW_OBS;             // column 0 only, nllk_ctcrw.hpp:214
+        if (d->model != SSDE_CTCRW) f &= (uint8_t)~ROW_OBS;
+        flags[i] = f;
+        if (start) starts.push_back(i);
+        if (!last) dt[i] = ((i == n - 1) ? d->t_next : d->times[i + 1]) - d->times[i];
+    }
+    if (d->model == SSDE_CTCRW) {
+        for (int64_t i = 0; i < n; ++i) flags[i] &= (uint8_t)~(0xf8);      // NA bits unused
+        if (!d->a0 || !d->P0) { err = "CTCRW needs a0 and P0"; return fail(SSDE_ERR_BAD_ARG); }
+        if (d->n_ID != (int)starts.size()) { err = "nrow(a0) != number of tracks starting on this shard"; return fail(SSDE_ERR_BAD_ARG); }
+        const int m = 2 * nd;
+        const double p11 = d->P0[0], p12 = d->P0[(size_t)1 * m + 0], p22 = d->P0[(size_t)1 * m + 1];
+        for (int r = 0; r < m; ++r)
+            for (int c = 0; c < m; ++c) {
+                double want = 0.0;
+                if (r / 2 == c / 2) want = (r % 2 == 0 && c % 2 == 0) ? p11 : ((r % 2 == 1 && c % 2 == 1) ? p22 : p12);
+                if (d->P0[(size_t)c * m + r] != want) {
+                    err = "P0 must be block-diagonal with identical 2x2 blocks (coupled filter not built yet)";
+                    return fail(SSDE_ERR_UNSUPPORTED);
+                }
+            }
+        h->P0 = {p11, p12, p22};
+        std::vector<double> a0((size_t)starts.size() * m);
+        for (size_t k = 0; k < starts.size(); ++k)
+            for (int c = 0; c < m; ++c) a0[k * m + c] = d->a0[(size_t)c * starts.size() + k];
+        if ((rc = dev_upload(h->a0, a0, h->err))) return fail(rc);
+    }
+    h->n_tracks = (int)starts.size();
+    Packed pk;
+    if ((rc = pack_design(*d, n_par, pk, h->err))) return fail(rc);
+    h->nnz = (int64_t)pk.col.size();
+    if ((rc = dev_upload(h->rowptr, pk.rowptr, h->err))) return fail(rc);
+    if ((rc = dev_upload(h->cnt, pk.cnt, h->err))) return fail(rc);
+    if ((rc = dev_upload(h->col, pk.col, h->err))) return fail(rc);
+    if ((rc = dev_upload(h->val, pk.val, h->err))) return fail(rc);
+    if ((rc = dev_upload(h->obs, obs, h->err))) return fail(rc);
+    if ((rc = dev_upload(h->dt, dt, h->err))) return fail(rc);
+    if ((rc = dev_upload(h->flags, flags, h->err))) return fail(rc);
+    if ((rc = dev_upload(h->track_starts, starts, h->err))) return fail(rc);
+    if ((rc = setup_penalty(h, d->S, d->n_smooth, d->ncol_re, h->err))) return fail(rc);
+    if ((rc = finish_setup(h))) return fail(rc);
+    *out = h;
+    return SSDE_OK;
+}
+
+int ssde_create_packed(const ssde_packed_desc* d, ssde_handle** out) {
+    std::string& err = g_create_error;
+    err.clear();
+    if (!d || !out) { err = "null argument"; return SSDE_ERR_BAD_ARG; }
+    *out = nullptr;
+    int rc = check_common(d->model, d->n_dim, err);
+    if (rc) return rc;
+    const int n_par = (d->model == SSDE_BM) ? d->n_dim + 1 : d->n_dim + 2;
+    if (d->n_par != n_par) { err = "n_par does not match model / n_dim"; return SSDE_ERR_BAD_ARG; }
+    if (cudaSetDevice(d->device) != cudaSuccess) { err = "cudaSetDevice failed: no usable CUDA device (there is no CPU fallback)"; return SSDE_ERR_CUDA; }
+    ssde_handle* h = new (std::nothrow) ssde_handle();
+    if (!h) { err = "out of memory"; return SSDE_ERR_BAD_ARG; }
+    auto fail = [&](int code) { err = h->err.empty() ? err : h->err; delete h; return code; };
+    h->device = d->device; h->model = d->model; h->n_dim = d->n_dim; h->n_par = n_par; h->n = d->n; h->nnz = d->nnz;
+    h->p_fe = d->p_fe; h->p_re = d->p_re; h->include_penalty = d->include_penalty; h->shard_flags = d->shard_flags;
+    h->add_penalty = !(d->shard_flags & SSDE_SHARD_NO_PENALTY);
+    h->rowptr.p = (void*)d->d_rowptr; h->cnt.p = (void*)d->d_cnt; h->col.p = (void*)d->d_col; h->val.p = (void*)d->d_val;
+    h->obs.p = (void*)d->d_obs; h->dt.p = (void*)d->d_dt; h->flags.p = (void*)d->d_flags;
+    h->n_tracks = d->n_ID;
+    h->P0 = {d->P0[0], d->P0[1], d->P0[2]};
+    std::vector<int64_t> starts(d->track_starts, d->track_starts + d->n_ID);
+    if ((rc = dev_upload(h->track_starts, starts, h->err))) return fail(rc);
+    if (d->model == SSDE_CTCRW) {
+        if (!d->a0) { err = "CTCRW needs a0"; return fail(SSDE_ERR_BAD_ARG); }
+        std::vector<double> a0(d->a0, d->a0 + (size_t)d->n_ID * 2 * d->n_dim);
+        if ((rc = dev_upload(h->a0, a0, h->err))) return fail(rc);
+    }
+    if ((rc = setup_penalty(h, d->S, d->n_smooth, d->ncol_re, h->err))) return fail(rc);
+    if ((rc = finish_setup(h))) return fail(rc);
+    *out = h;
+    return SSDE_OK;
+}
+
+int ssde_eval_device(ssde_handle* h, const double* d_par, int order, double* d_out, void* stream) {
+    if (!h || !d_par || !d_out) return SSDE_ERR_BAD_ARG;
+    std::string& err = h->err;
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    h->timed = (st == h->stream);
+    if (h->timed) CUDA_TRY(cudaEventRecord(h->ev0, st));
+    int rc = run_eval(h, d_par, order, d_out, st, nullptr);
+    if (rc) return rc;
+    if (h->timed) CUDA_TRY(cudaEventRecord(h->ev1, st));
+    return SSDE_OK;
+}
+
+int ssde_check(ssde_handle* h) {
+    if (!h) return SSDE_ERR_BAD_ARG;
+    std::string& err = h->err;
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    unsigned e = 0;
+    CUDA_TRY(cudaMemcpy(&e, h->counters.as<unsigned>() + 2, sizeof(unsigned), cudaMemcpyDeviceToHost));
+    if (e) { err = "device-side failure (scan look-back timed out)"; return SSDE_ERR_NUMERIC; }
+    return SSDE_OK;
+}
+
+int ssde_eval(ssde_handle* h, const double* par, int order, double* nllk, double* grad, double* hess) {
+    if (!h || !par || !nllk) return SSDE_ERR_BAD_ARG;
+    std::string& err = h->err;
+    (void)hess;
+    if (order >= 1 && !grad) { err = "grad buffer required for order >= 1"; return SSDE_ERR_BAD_ARG; }
+    CUDA_TRY(cudaSetDevice(h->device));
+    double* hp = h->h_pinned;
+    double* ho = h->h_pinned + h->npar;
+    std::memcpy(hp, par, sizeof(double) * h->npar);
+    cudaStream_t st = h->stream;
+    CUDA_TRY(cudaMemcpyAsync(h->par.p, hp, sizeof(double) * h->npar, cudaMemcpyHostToDevice, st));
+    h->timed = true;
+    CUDA_TRY(cudaEventRecord(h->ev0, st));
+    int rc = run_eval(h, h->par.as<double>(), order, h->out.as<double>(), st, nullptr);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(h->ev1, st));
+    const size_t nout = (order >= 1) ? (size_t)h->npar + 2 : 1;
+    CUDA_TRY(cudaMemcpyAsync(ho, h->out.p, sizeof(double) * nout, cudaMemcpyDeviceToHost, st));
+    if (order == 0) CUDA_TRY(cudaMemcpyAsync(ho + 1 + h->npar, h->out.as<double>() + 1 + h->npar, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    *nllk = ho[0];
+    if (order >= 1) std::memcpy(grad, ho + 1, sizeof(double) * h->npar);
+    if (ho[1 + h->npar] != 0.0) { err = "device-side failure (scan look-back timed out)"; return SSDE_ERR_NUMERIC; }
+    return SSDE_OK;
+}
+
+int ssde_report(ssde_handle* h, double* aest_all) {
+    if (!h || !aest_all) return SSDE_ERR_BAD_ARG;
+    std::string& err = h->err;
+    if (h->model != SSDE_CTCRW) { err = "REPORT(aest_all) exists for CTCRW only"; return SSDE_ERR_UNSUPPORTED; }
+    CUDA_TRY(cudaSetDevice(h->device));
+    const int m = 2 * h->n_dim;
+    if (!h->aest.p) { int rc = dev_alloc<double>(h->aest, (size_t)h->n * m, err); if (rc) return rc; }
+    int rc = run_eval(h, h->par.as<double>(), 0, h->out.as<double>(), h->stream, h->aest.as<double>());
+    if (rc) return rc;
+    std::vector<double> tmp((size_t)h->n * m);
+    CUDA_TRY(cudaMemcpyAsync(tmp.data(), h->aest.p, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    for (int64_t i = 0; i < h->n; ++i)
+        for (int c = 0; c < m; ++c) aest_all[(size_t)c * h->n + i] = tmp[(size_t)i * m + c];
+    return SSDE_OK;
+}
+
+double ssde_last_eval_ms(ssde_handle* h) {
+    if (!h || !h->timed) return -1.0;
+    if (cudaEventSynchronize(h->ev1) != cudaSuccess) return -1.0;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) != cudaSuccess) return -1.0;
+    return (double)ms;
+}
+
+int ssde_last_eval_launches(const ssde_handle* h) { return h ? h->last_launches : 0; }
+
+}  // extern "C"

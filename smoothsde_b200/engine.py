@@ -1,0 +1,168 @@
+"""Host-side handle of the CUDA likelihood engine.
+
+`Engine` wraps one ``ssde_handle`` of the C ABI (include/smoothsde_b200.h): it takes the data
+list that SDE$setup() builds for TMB::MakeADFun (R/sde.R:528-598), ships it to the GPU once and
+then evaluates the joint penalised negative log-likelihood and its gradient for full parameter
+vectors in the templates' PARAMETER order.  `map` / `random` handling
+lives one level up, in :mod:`smoothsde_b200.adfun`, exactly as TMB's R layer sits above
+EvalADFunObject.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import scipy.sparse as sp
+
+from . import _lib as L
+
+
+def _as_triplet(M, keep):
+    """scipy sparse / dense -> (Triplet struct, arrays kept alive).  dgTMatrix convention."""
+    if M is None:
+        M = sp.coo_matrix((1, 1))
+    M = sp.coo_matrix(M)
+    i = np.ascontiguousarray(M.row, dtype=np.int32)
+    j = np.ascontiguousarray(M.col, dtype=np.int32)
+    x = np.ascontiguousarray(M.data, dtype=np.float64)
+    keep += [i, j, x]
+    t = L.Triplet()
+    t.nrow, t.ncol, t.nnz = M.shape[0], M.shape[1], x.size
+    t.i = i.ctypes.data_as(L.c_int32_p)
+    t.j = j.ctypes.data_as(L.c_int32_p)
+    t.x = x.ctypes.data_as(L.c_double_p)
+    return t
+
+
+def model_code(type_):
+    if type_ in L.MODEL_CODES:
+        return L.MODEL_CODES[type_]
+    if type_ in L.KNOWN_UNBUILT:
+        raise L.EngineError(3, f"SDE type '{type_}' exists in the reference but is not built here")
+    raise L.EngineError(1, "Unknown SDE type")          # src/smoothSDE.cpp:25
+
+
+class Engine:
+    """One shard of one model on one GPU."""
+
+    def __init__(self, handle, lib, keep=None):
+        self._h = handle
+        self._lib = lib
+        self._keep = keep or []
+        self.n_par = lib.ssde_n_par(handle)
+        off = (C.c_int32 * 4)()
+        siz = (C.c_int32 * 4)()
+        lib.ssde_par_layout(handle, off, siz)
+        names = ("log_sigma_obs", "coeff_fe", "log_lambda", "coeff_re")
+        self.layout = {nm: (int(off[k]), int(siz[k])) for k, nm in enumerate(names) if siz[k] > 0 or k > 0}
+        self._grad = np.zeros(self.n_par)
+        self._nllk = C.c_double()
+
+    # ------------------------------------------------------------------------------------
+    @classmethod
+    def from_data(cls, dat, device=0, shard_flags=0, t_next=0.0):
+        lib = L.load()
+        keep = []
+        d = L.Desc()
+        d.model = model_code(dat["type"])
+        obs = np.asarray(dat["obs"], dtype=np.float64)
+        if obs.ndim == 1:
+            obs = obs[:, None]
+        n, nd = obs.shape
+        d.n_dim, d.n = nd, n
+        ID = np.ascontiguousarray(dat["ID"], dtype=np.float64)
+        times = np.ascontiguousarray(dat["times"], dtype=np.float64)
+        obs_cm = np.asfortranarray(obs)
+        keep += [ID, times, obs_cm]
+        d.ID = ID.ctypes.data_as(L.c_double_p)
+        d.times = times.ctypes.data_as(L.c_double_p)
+        d.obs = obs_cm.ctypes.data_as(L.c_double_p)
+        d.X_fe = _as_triplet(dat["X_fe"], keep)
+        d.X_re = _as_triplet(dat["X_re"], keep)
+        d.S = _as_triplet(dat.get("S"), keep)
+        ncol_re = np.ascontiguousarray(np.atleast_1d(dat["ncol_re"]), dtype=np.int32)
+        keep.append(ncol_re)
+        d.n_smooth = ncol_re.size
+        d.ncol_re = ncol_re.ctypes.data_as(L.c_int32_p)
+        d.include_penalty = int(dat.get("include_penalty", 1))
+        if dat["type"] == "CTCRW":
+            a0 = np.asfortranarray(np.asarray(dat["a0"], dtype=np.float64).reshape(-1, 2 * nd))
+            P0 = np.asfortranarray(np.asarray(dat["P0"], dtype=np.float64))
+            keep += [a0, P0]
+            d.n_ID = a0.shape[0]
+            d.a0 = a0.ctypes.data_as(L.c_double_p)
+            d.P0 = P0.ctypes.data_as(L.c_double_p)
+            H = dat.get("H_array")
+            if H is not None and np.size(H) > 1:
+                H = np.asfortranarray(np.asarray(H, dtype=np.float64))
+                keep.append(H)
+                d.H_array = H.ctypes.data_as(L.c_double_p)
+                d.H_len = H.size
+        d.device = device
+        d.shard_flags = shard_flags
+        d.t_next = float(t_next)
+        h = C.c_void_p()
+        rc = lib.ssde_create(C.byref(d), C.byref(h))
+        if rc != 0:
+            raise L.EngineError(rc, lib.ssde_create_error().decode())
+        return cls(h, lib)       # the library copied everything it needs
+
+    @classmethod
+    def from_packed(cls, pd: "L.PackedDesc", keep):
+        """Adopt device-resident arrays (see ssde_create_packed); `keep` holds their owners."""
+        lib = L.load()
+        h = C.c_void_p()
+        rc = lib.ssde_create_packed(C.byref(pd), C.byref(h))
+        if rc != 0:
+            raise L.EngineError(rc, lib.ssde_create_error().decode())
+        return cls(h, lib, keep)
+
+    # ------------------------------------------------------------------------------------
+    def _check(self, rc):
+        if rc != 0:
+            raise L.EngineError(rc, self._lib.ssde_last_error(self._h).decode())
+
+    def eval(self, par, order=1):
+        """(nllk, grad) for the full parameter vector; host buffers in and out (obj$fn / obj$gr)."""
+        par = np.ascontiguousarray(par, dtype=np.float64)
+        if par.size != self.n_par:
+            raise ValueError(f"parameter vector has length {par.size}, expected {self.n_par}")
+        g = self._grad
+        rc = self._lib.ssde_eval(self._h, par.ctypes.data_as(L.c_double_p), int(order),
+                                 C.byref(self._nllk), g.ctypes.data_as(L.c_double_p), None)
+        self._check(rc)
+        return self._nllk.value, (g.copy() if order >= 1 else None)
+
+    def eval_device(self, d_par_ptr, d_out_ptr, order=1, stream_ptr=None):
+        """Asynchronous evaluation on device buffers (raw pointers, e.g. tensor.data_ptr())."""
+        rc = self._lib.ssde_eval_device(self._h, C.c_void_p(d_par_ptr), int(order),
+                                        C.c_void_p(d_out_ptr), C.c_void_p(stream_ptr or 0))
+        self._check(rc)
+
+    def check(self):
+        self._check(self._lib.ssde_check(self._h))
+
+    def report(self, n, n_dim):
+        """REPORT(aest_all) at the parameters of the last eval()."""
+        out = np.zeros((n, 2 * n_dim), order="F")
+        self._check(self._lib.ssde_report(self._h, out.ctypes.data_as(L.c_double_p)))
+        return np.ascontiguousarray(out)
+
+    @property
+    def last_eval_ms(self):
+        return self._lib.ssde_last_eval_ms(self._h)
+
+    @property
+    def last_eval_launches(self):
+        return self._lib.ssde_last_eval_launches(self._h)
+
+    def close(self):
+        if self._h is not None:
+            self._lib.ssde_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

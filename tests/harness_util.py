@@ -1,0 +1,67 @@
+"""Helpers shared by the CPU-side tests: row flags / dt conventions and the ctypes binding of the
+host-compiled math harness (tests/harness/math_harness.cpp).  TEST INFRASTRUCTURE ONLY."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+_c_dp = ctypes.POINTER(ctypes.c_double)
+
+
+def _P(a):
+    return a.ctypes.data_as(_c_dp)
+
+
+def build_harness():
+    src = os.path.join(HERE, "harness", "math_harness.cpp")
+    out_dir = os.path.join(HERE, "harness", "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    out = os.path.join(out_dir, "libmath_harness.so")
+    hdr = os.path.join(ROOT, "smoothsde_b200", "csrc", "ctcrw_math.cuh")
+    if (not os.path.exists(out)) or os.path.getmtime(out) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-x", "c++", "-o", out, src])
+    return ctypes.CDLL(out)
+
+
+def row_flags(ID, obs):
+    ID = np.asarray(ID)
+    start = np.r_[True, ID[1:] != ID[:-1]]
+    last = np.r_[ID[1:] != ID[:-1], True]
+    has = ~np.isnan(obs[:, 0])
+    return (start * 1 + last * 2 + has * 4).astype(np.uint8)
+
+
+def ctcrw_dt(times, flags):
+    """dt_i = t_{i+1} - t_i (nllk_ctcrw.hpp:126-129); rows whose prediction is discarded (last
+    row of a track) get dt = 1 like the reference's final row."""
+    t = np.asarray(times, dtype=float)
+    dt = np.r_[t[1:] - t[:-1], 1.0]
+    dt[(flags & 2) != 0] = 1.0
+    return dt
+
+
+def harness_ctcrw(lib, dat, eta, log_sigma_obs, mode, lc=8, nt=128, want_grad=True, want_aest=False):
+    obs = np.asarray(dat["obs"], dtype=float)
+    n, nd = obs.shape
+    flags = row_flags(dat["ID"], obs)
+    dt = ctcrw_dt(dat["times"], flags)
+    eta = np.ascontiguousarray(eta, dtype=float)
+    y = np.ascontiguousarray(np.nan_to_num(obs))
+    a0 = np.ascontiguousarray(dat["a0"], dtype=float)
+    P0 = np.asarray(dat["P0"], dtype=float)
+    P0s = np.array([P0[0, 0], P0[0, 1], P0[1, 1]])
+    h = float(np.exp(2 * log_sigma_obs))
+    llk = ctypes.c_double()
+    gh = ctypes.c_double()
+    eb = np.zeros((n, nd + 2)) if want_grad else None
+    aest = np.zeros((n, 2 * nd)) if want_aest else None
+    rc = lib.harness_ctcrw(nd, mode, ctypes.c_int64(n),
+                           flags.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), _P(y), _P(dt),
+                           _P(eta), _P(a0), _P(P0s), ctypes.c_double(h), lc, nt,
+                           ctypes.byref(llk), _P(eb) if want_grad else None, ctypes.byref(gh),
+                           _P(aest) if want_aest else None)
+    assert rc == 0
+    return llk.value, eb, gh.value * 2 * h, aest
