@@ -150,6 +150,12 @@ double ssde_last_eval_ms(ssde_handle* h);
 /* Number of kernels the last evaluation launched. */
 int ssde_last_eval_launches(const ssde_handle* h);
 
+/* Per-kernel device times: with profiling on, every evaluation records a CUDA event in front of
+ * each kernel on the launching stream; ssde_last_kernel_times returns how many kernels the last
+ * evaluation ran and fills ms[] / names[] (static strings) for up to `cap` of them. */
+int ssde_set_profile(ssde_handle* h, int on);
+int ssde_last_kernel_times(ssde_handle* h, int cap, float* ms, const char** names);
+
 const char* ssde_last_error(const ssde_handle* h);
 const char* ssde_create_error(void);
 const char* ssde_version(void);

@@ -59,7 +59,7 @@ _lib = None
 # every symbol include/smoothsde_b200.h declares
 EXPORTS = ["ssde_create", "ssde_create_packed", "ssde_destroy", "ssde_n_par", "ssde_par_layout",
            "ssde_eval", "ssde_eval_device", "ssde_check", "ssde_report", "ssde_last_eval_ms",
-           "ssde_last_eval_launches", "ssde_last_error", "ssde_create_error", "ssde_version"]
+           "ssde_last_eval_launches", "ssde_set_profile", "ssde_last_kernel_times", "ssde_last_error", "ssde_create_error", "ssde_version"]
 
 
 def load():
@@ -95,6 +95,10 @@ def load():
     lib.ssde_last_eval_ms.restype = C.c_double
     lib.ssde_last_eval_launches.argtypes = [vp]
     lib.ssde_last_eval_launches.restype = C.c_int
+    lib.ssde_set_profile.argtypes = [vp, C.c_int]
+    lib.ssde_set_profile.restype = C.c_int
+    lib.ssde_last_kernel_times.argtypes = [vp, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_char_p)]
+    lib.ssde_last_kernel_times.restype = C.c_int
     lib.ssde_last_error.argtypes = [vp]
     lib.ssde_last_error.restype = C.c_char_p
     lib.ssde_create_error.argtypes = []

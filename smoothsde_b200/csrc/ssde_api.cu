@@ -69,10 +69,16 @@ struct ssde_handle {
     int64_t nchunks = 0;
     int last_launches = 0;
     bool timed = false;
+    // optional per-kernel timing (ssde_set_profile): event k is recorded before kernel k
+    bool profile = false;
+    std::vector<cudaEvent_t> pev;
+    std::vector<const char*> pnames;
+    int pcount = 0;
     std::string err;
 
     ~ssde_handle() {
         if (h_pinned) cudaFreeHost(h_pinned);
+        for (cudaEvent_t e : pev) cudaEventDestroy(e);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (stream) cudaStreamDestroy(stream);
@@ -439,12 +445,27 @@ int finish_setup(ssde_handle* h) {
 // ---------------------------------------------------------------------------------------------
 // evaluation pipeline
 // ---------------------------------------------------------------------------------------------
+// counts a kernel launch and, in profiling mode, records an event in front of it
+void mark(ssde_handle* h, cudaStream_t st, const char* name) {
+    if (name) ++h->last_launches;
+    if (!h->profile) return;
+    if ((int)h->pev.size() <= h->pcount) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        h->pev.push_back(e);
+        h->pnames.push_back(name);
+    }
+    h->pnames[h->pcount] = name;
+    cudaEventRecord(h->pev[h->pcount], st);
+    ++h->pcount;
+}
+
 template <int ND>
 int launch_ctcrw(ssde_handle* h, const double* d_par, int order, cudaStream_t st, double* aest) {
     std::string& err = h->err;
     Design X{h->n, ND + 2, h->rowptr.as<uint32_t>(), h->cnt.as<uint32_t>(), h->col.as<uint32_t>(), h->val.as<double>()};
+    mark(h, st, "ctcrw_linpred");
     ctcrw_linpred_kernel<ND><<<h->grid_lp, LP_NT, 0, st>>>(X, h->theta.as<double>(), h->dt.as<double>(), h->W.as<double>());
-    ++h->last_launches;
     CtcrwArgs<ND> a;
     a.n = h->n;
     a.W = h->W.as<double>(); a.obs = h->obs.as<double>(); a.dt = h->dt.as<double>(); a.flags = h->flags.as<uint8_t>();
@@ -457,13 +478,14 @@ int launch_ctcrw(ssde_handle* h, const double* d_par, int order, cudaStream_t st
     a.fdesc = {h->f_status.as<unsigned>(), h->f_agg.as<double>(), h->f_incl.as<double>(), cnt + 0, cnt + 2, h->epoch};
     a.bdesc = {h->b_status.as<unsigned>(), h->b_agg.as<double>(), h->b_incl.as<double>(), cnt + 1, cnt + 2, h->epoch};
     a.ntiles = h->ntiles_f;
+    mark(h, st, "ctcrw_fwd_scan");
     ctcrw_fwd_kernel<ND, FWD_NT, FWD_LC><<<h->grid_f, FWD_NT, CtcrwSmem<ND, FWD_NT, FWD_LC>::BYTES_FWD, st>>>(a);
-    ++h->last_launches;
     if (order >= 1) {
         a.ntiles = h->ntiles_b;
+        mark(h, st, "ctcrw_bwd_scan");
         ctcrw_bwd_kernel<ND, BWD_NT, BWD_LC><<<h->grid_b, BWD_NT, CtcrwSmem<ND, BWD_NT, BWD_LC>::BYTES_BWD, st>>>(a);
+        mark(h, st, "linpred_T");
         linpred_T_kernel<ND + 2><<<h->grid_lp, LP_NT, 0, st>>>(X, h->eta_bar.as<double>(), h->grad_theta.as<double>());
-        h->last_launches += 2;
     }
     CUDA_TRY(cudaGetLastError());
     return SSDE_OK;
@@ -474,10 +496,10 @@ int launch_sde(ssde_handle* h, int order, cudaStream_t st) {
     std::string& err = h->err;
     constexpr int NP = (MODEL == MODEL_BM) ? ND + 1 : ND + 2;
     Design X{h->n, NP, h->rowptr.as<uint32_t>(), h->cnt.as<uint32_t>(), h->col.as<uint32_t>(), h->val.as<double>()};
+    mark(h, st, "sde_fused");
     sde_fused_kernel<MODEL, ND><<<h->grid_lp, LP_NT, 0, st>>>(X, h->theta.as<double>(), h->obs.as<double>(), h->dt.as<double>(),
                                                              h->flags.as<uint8_t>(), order >= 1, h->grad_theta.as<double>(),
                                                              h->block_llk.as<double>());
-    ++h->last_launches;
     CUDA_TRY(cudaGetLastError());
     return SSDE_OK;
 }
@@ -486,13 +508,14 @@ int run_eval(ssde_handle* h, const double* d_par, int order, double* d_out, cuda
     std::string& err = h->err;
     if (order < 0 || order > 1) { err = "order must be 0 or 1 (Hessian not built yet)"; return SSDE_ERR_UNSUPPORTED; }
     h->last_launches = 0;
+    h->pcount = 0;
     ++h->epoch;
     if (h->epoch >= (1u << 30)) h->epoch = 1;     // status arrays were zeroed at creation; 0 is never a live epoch
     const int p = h->p_fe + h->p_re;
     CUDA_TRY(cudaMemsetAsync(h->counters.p, 0, 3 * sizeof(unsigned), st));
     if (order >= 1) CUDA_TRY(cudaMemsetAsync(h->grad_theta.p, 0, sizeof(double) * std::max(p, 1), st));
+    mark(h, st, "gather_theta");
     gather_theta_kernel<<<(p + 255) / 256, 256, 0, st>>>(d_par, h->theta.as<double>(), h->p_fe, h->p_re, h->o_fe, h->o_re);
-    ++h->last_launches;
     int rc = SSDE_OK;
     FinArgs f{};
     if (h->model == SSDE_CTCRW) {
@@ -525,8 +548,9 @@ int run_eval(ssde_handle* h, const double* d_par, int order, double* d_out, cuda
     f.want_grad = order >= 1;
     f.error = h->counters.as<unsigned>() + 2;
     f.out = d_out;
+    mark(h, st, "finalize");
     finalize_kernel<<<1, 256, 0, st>>>(f);
-    ++h->last_launches;
+    mark(h, st, nullptr);
     CUDA_TRY(cudaGetLastError());
     return SSDE_OK;
 }
@@ -757,5 +781,25 @@ double ssde_last_eval_ms(ssde_handle* h) {
 }
 
 int ssde_last_eval_launches(const ssde_handle* h) { return h ? h->last_launches : 0; }
+
+int ssde_set_profile(ssde_handle* h, int on) {
+    if (!h) return SSDE_ERR_BAD_ARG;
+    h->profile = on != 0;
+    h->pcount = 0;
+    return SSDE_OK;
+}
+
+int ssde_last_kernel_times(ssde_handle* h, int cap, float* ms, const char** names) {
+    if (!h || !h->profile || h->pcount < 2) return 0;
+    if (cudaEventSynchronize(h->pev[h->pcount - 1]) != cudaSuccess) return 0;
+    int k = 0;
+    for (; k + 1 < h->pcount && k < cap; ++k) {
+        float t = 0.f;
+        cudaEventElapsedTime(&t, h->pev[k], h->pev[k + 1]);
+        ms[k] = t;
+        if (names) names[k] = h->pnames[k];
+    }
+    return k;
+}
 
 }  // extern "C"

@@ -1,0 +1,223 @@
+"""Device-side synthetic problems at BASELINE.json's full sizes (10^8 rows do not fit a host
+triplet list), built with torch directly in the engine's packed layout and handed to
+``ssde_create_packed`` without a copy.  torch is plumbing here (device memory + RNG); the
+likelihood itself is computed by the CUDA library.
+
+Shapes follow SURVEY.md section 8(d): CTCRW, d = 2, ``tau, nu ~ s(time, k = 10)``, mu fixed at 0
+(C3: 1024 x 1e5 irregular steps; C4: one 1e8-step track; C5: 4096 x 2.5e4).  Every row has the
+same 22 nonzeros: mu1.(Intercept), mu2.(Intercept), tau.(Intercept) + 9 spline columns,
+nu.(Intercept) + 9 spline columns.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import scipy.sparse as sp
+
+from . import _lib as L
+from . import design as _design
+from .engine import Engine, _as_triplet
+
+
+def _bspline_torch(x, k, lo, hi):
+    import torch
+    nseg = k - 3
+    h = (hi - lo) / nseg
+    t = (x - lo) / h
+    seg = torch.clamp(torch.floor(t), 0, nseg - 1)
+    u = t - seg
+    seg = seg.to(torch.int64)
+    w = torch.stack([(1 - u) ** 3 / 6.0,
+                     (3 * u ** 3 - 6 * u ** 2 + 4) / 6.0,
+                     (-3 * u ** 3 + 3 * u ** 2 + 3 * u + 1) / 6.0,
+                     u ** 3 / 6.0], dim=1)
+    B = torch.zeros((x.numel(), k), dtype=torch.float64, device=x.device)
+    idx = seg[:, None] + torch.arange(4, device=x.device)[None, :]
+    B.scatter_(1, idx, w)
+    return B
+
+
+def simulate_ctcrw_torch(times, tau, nu, gen, seg_len=None):
+    """Exact-transition CTCRW simulation (R/sde.R:1448-1478) vectorised over tracks on the GPU.
+    times/tau/nu: [T, m].  Returns z [T, m] for one dimension (mu = 0)."""
+    import torch
+    T, m = times.shape
+    dt = times[:, 1:] - times[:, :-1]
+    beta = 1.0 / tau[:, :-1]
+    sigma = 2.0 * nu[:, :-1] / torch.sqrt(math.pi * tau[:, :-1])
+    p = torch.exp(-beta * dt)
+    p2 = p * p
+    qvv = sigma ** 2 / (2 * beta) * (1 - p2)
+    qzz = (sigma / beta) ** 2 * (dt + (1 - p2) / (2 * beta) - 2 * (1 - p) / beta)
+    qvz = sigma ** 2 / (2 * beta ** 2) * (1 - 2 * p + p2)
+    l11 = torch.sqrt(qvv)
+    l21 = qvz / l11
+    l22 = torch.sqrt(torch.clamp(qzz - l21 * l21, min=0.0))
+    e1 = torch.randn((T, m - 1), dtype=torch.float64, device=times.device, generator=gen)
+    e2 = torch.randn((T, m - 1), dtype=torch.float64, device=times.device, generator=gen)
+    nv = l11 * e1                      # velocity noise
+    nz = l21 * e1 + l22 * e2           # position noise
+    cz = (1 - p) / beta                # position gain from velocity
+    del e1, e2, l11, l21, l22, qvv, qzz, qvz, sigma, beta, p2
+    # time-major copies so that the sequential loop reads contiguous [T] slices
+    p_t, nv_t, nz_t, cz_t = (a.t().contiguous() for a in (p, nv, nz, cz))
+    del p, nv, nz, cz
+    z = torch.empty((m, T), dtype=torch.float64, device=times.device)
+    v = torch.zeros(T, dtype=torch.float64, device=times.device)
+    zc = torch.zeros(T, dtype=torch.float64, device=times.device)
+    z[0] = zc
+    for i in range(1, m):
+        zc = zc + cz_t[i - 1] * v + nz_t[i - 1]
+        v = p_t[i - 1] * v + nv_t[i - 1]
+        z[i] = zc
+    return z.t().contiguous()
+
+
+def make_ctcrw_device(n_tracks, n_steps, seed=20260103, device=0, k=10, sigma_obs=0.1,
+                      irregular=True, rank=0, world=1, sim_tracks=None, dist_reduce=None,
+                      shard_flags=0):
+    """Build the rows of `n_tracks` tracks x `n_steps` steps on `device` (this rank's shard).
+
+    sim_tracks: simulate only this many distinct tracks x (n_tracks*n_steps/sim_tracks) ... used
+    for the single-long-track configuration, where the track is simulated as `sim_tracks`
+    segments that are stitched together (positions made continuous).
+    dist_reduce(tensor, op) -> tensor: optional all-reduce across ranks so that every shard uses
+    the same knots and sum-to-zero constraint.
+    Returns (engine, par, info)."""
+    import torch
+    dev = torch.device("cuda", device)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(seed + 1000 * rank)
+    nd = 2
+    T, m = n_tracks, n_steps
+    single = sim_tracks is not None
+    if single:
+        assert n_tracks == 1
+        T, m = sim_tracks, n_steps // sim_tracks
+        assert T * m == n_steps
+    n = T * m
+    if irregular:
+        inc = 0.2 + 1.8 * torch.rand((T, m), dtype=torch.float64, device=dev, generator=gen)
+        inc[:, 0] = 0.0
+        times = torch.cumsum(inc, dim=1)
+        del inc
+    else:
+        times = torch.arange(m, dtype=torch.float64, device=dev).repeat(T, 1)
+    if single:      # consecutive segments of one track: shift times so they increase overall
+        ends = times[:, -1] + 1.0
+        off = torch.cumsum(ends, 0) - ends
+        times = times + off[:, None]
+    s = (times - times.min()) / (times.max() - times.min()) if single else times / times[:, -1:]
+    tau = torch.exp(0.5 * torch.sin(2 * math.pi * s))
+    nu = torch.exp(0.3 * torch.cos(2 * math.pi * s))
+    del s
+    obs = torch.empty((n, nd), dtype=torch.float64, device=dev)
+    for d in range(nd):
+        z = simulate_ctcrw_torch(times, tau, nu, gen)
+        if single:
+            ends = z[:, -1]
+            z = z + (torch.cumsum(ends, 0) - ends)[:, None]
+        z = z + sigma_obs * torch.randn(z.shape, dtype=torch.float64, device=dev, generator=gen)
+        obs[:, d] = z.reshape(-1)
+        del z
+    del tau, nu
+    tflat = times.reshape(-1)
+    # dt_i = t_{i+1} - t_i; 1 on the last row of each track
+    dt = torch.ones(n, dtype=torch.float64, device=dev)
+    dt[:-1] = tflat[1:] - tflat[:-1]
+    flags = torch.full((n,), 4, dtype=torch.uint8, device=dev)
+    if single:
+        track_starts = np.array([0], dtype=np.int64)
+        flags[0] |= 1
+        flags[-1] |= 2
+        dt[-1] = 1.0
+        n_id = 1
+    else:
+        first = torch.arange(0, n, m, device=dev)
+        flags[first] |= 1
+        flags[first + (m - 1)] |= 2
+        dt[first + (m - 1)] = 1.0
+        track_starts = np.arange(0, n, m, dtype=np.int64)
+        n_id = T
+    a0 = np.zeros((n_id, 2 * nd))
+    first_obs = obs[torch.as_tensor(track_starts, device=dev)].cpu().numpy()
+    for d in range(nd):
+        a0[:, 2 * d] = first_obs[:, d]
+
+    # spline design: knots over the global time range, sum-to-zero constraint from global means
+    lo, hi = tflat.min().reshape(1), tflat.max().reshape(1)
+    if dist_reduce is not None:
+        lo, hi = dist_reduce(lo, "min"), dist_reduce(hi, "max")
+    lo, hi = float(lo), float(hi)
+    colsum = torch.zeros(k + 1, dtype=torch.float64, device=dev)
+    CH = 1 << 22
+    for c0 in range(0, n, CH):
+        B = _bspline_torch(tflat[c0:c0 + CH], k, lo, hi)
+        colsum[:k] += B.sum(0)
+        colsum[k] += B.shape[0]
+        del B
+    if dist_reduce is not None:
+        colsum = dist_reduce(colsum, "sum")
+    means = (colsum[:k] / colsum[k]).cpu().numpy()
+    Zc = _design.sum_to_zero_transform(means)
+    S1 = Zc.T @ _design.second_diff_penalty(k) @ Zc + 1e-2 * np.eye(k - 1)
+    S1 = 0.5 * (S1 + S1.T)
+    Zt = torch.as_tensor(Zc, device=dev)
+    nnz_row = 2 + 2 * k            # 2 mu intercepts + 2 x (intercept + k-1 spline columns)
+    val = torch.empty((n, nnz_row), dtype=torch.float64, device=dev)
+    val[:, 0] = 1.0
+    val[:, 1] = 1.0
+    val[:, 2] = 1.0
+    val[:, 2 + k] = 1.0
+    for c0 in range(0, n, CH):
+        Bz = _bspline_torch(tflat[c0:c0 + CH], k, lo, hi) @ Zt
+        val[c0:c0 + CH, 3:2 + k] = Bz
+        val[c0:c0 + CH, 3 + k:2 + 2 * k] = Bz
+        del Bz
+    p_fe, p_re = nd + 2, 2 * (k - 1)
+    # theta = [coeff_fe (mu1, mu2, tau, nu intercepts) | coeff_re (tau spline, nu spline)]
+    pat = [0, 1, 2] + [p_fe + j for j in range(k - 1)] + [3] + [p_fe + (k - 1) + j for j in range(k - 1)]
+    col = torch.as_tensor(np.asarray(pat, dtype=np.int32), device=dev).repeat(n, 1).contiguous()
+    rowptr = (torch.arange(n + 1, dtype=torch.int64, device=dev) * nnz_row).to(torch.int32)
+    cntw = 1 | (1 << 8) | (k << 16) | (k << 24)
+    cnt = torch.full((n,), cntw, dtype=torch.int32, device=dev)
+
+    keep = [rowptr, cnt, col, val, obs, dt, flags]
+    pd = L.PackedDesc()
+    pd.model, pd.n_dim, pd.n_par = L.SSDE_CTCRW, nd, nd + 2
+    pd.n, pd.nnz = n, n * nnz_row
+    pd.d_rowptr, pd.d_cnt, pd.d_col, pd.d_val = rowptr.data_ptr(), cnt.data_ptr(), col.data_ptr(), val.data_ptr()
+    pd.d_obs, pd.d_dt, pd.d_flags = obs.data_ptr(), dt.data_ptr(), flags.data_ptr()
+    pd.p_fe, pd.p_re = p_fe, p_re
+    S = sp.block_diag([S1, S1], format="csr")
+    pd.S = _as_triplet(S, keep)
+    ncol_re = np.array([k - 1, k - 1], dtype=np.int32)
+    keep.append(ncol_re)
+    pd.n_smooth = 2
+    pd.ncol_re = ncol_re.ctypes.data_as(L.c_int32_p)
+    pd.include_penalty = 1
+    pd.n_ID = n_id
+    ts = np.ascontiguousarray(track_starts)
+    a0c = np.ascontiguousarray(a0)
+    keep += [ts, a0c]
+    pd.track_starts = ts.ctypes.data_as(L.c_int64_p)
+    pd.a0 = a0c.ctypes.data_as(L.c_double_p)
+    pd.P0[0], pd.P0[1], pd.P0[2] = 1.0, 0.0, 10.0
+    pd.device = device
+    pd.shard_flags = shard_flags
+    torch.cuda.synchronize(dev)
+    eng = Engine.from_packed(pd, keep)
+
+    prng = np.random.default_rng(seed + 1)
+    par = np.concatenate([[math.log(sigma_obs)], np.zeros(p_fe), np.zeros(2), 0.1 * prng.standard_normal(p_re)])
+    info = {"n": n, "n_dim": nd, "nnz": n * nnz_row, "p_fe": p_fe, "p_re": p_re, "n_s": 2,
+            "n_par": nd + 2, "n_tracks": n_id, "tensors": dict(val=val, col=col, obs=obs, dt=dt, flags=flags, times=tflat),
+            "S": S, "a0": a0, "track_starts": track_starts, "knots": (lo, hi), "Zc": Zc}
+    return eng, par, info
+
+
+def alg_bytes_per_obs(n_dim, n_par, nnz_per_obs):
+    """B_alg/n = (8 d + 8 + 4) + 2 [12 nnz/n + 4*2*n_par]."""
+    return (8 * n_dim + 8 + 4) + 2 * (12 * nnz_per_obs + 8 * n_par)

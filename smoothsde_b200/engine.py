@@ -156,6 +156,16 @@ class Engine:
     def last_eval_launches(self):
         return self._lib.ssde_last_eval_launches(self._h)
 
+    def set_profile(self, on=True):
+        self._lib.ssde_set_profile(self._h, int(bool(on)))
+
+    def last_kernel_times(self):
+        """[(kernel name, device ms)] of the last evaluation (profiling mode only)."""
+        ms = (C.c_float * 16)()
+        names = (C.c_char_p * 16)()
+        k = self._lib.ssde_last_kernel_times(self._h, 16, ms, names)
+        return [(names[i].decode(), float(ms[i])) for i in range(k)]
+
     def close(self):
         if self._h is not None:
             self._lib.ssde_destroy(self._h)
