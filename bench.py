@@ -177,7 +177,12 @@ def main():
     out_dev = torch.zeros(npar + 2, dtype=torch.float64, device=dev)
     par_host = torch.as_tensor(par).pin_memory()
     out_host = torch.zeros(npar + 2, dtype=torch.float64).pin_memory()
-    stream = torch.cuda.current_stream().cuda_stream
+    # a non-default torch stream: the C ABI treats a NULL stream as "the handle's own stream",
+    # and torch.cuda.Event only sees work on torch's current stream
+    tstream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
 
     def step_device():
         eng.eval_device(par_dev.data_ptr(), out_dev.data_ptr(), 1, stream)

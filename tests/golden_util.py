@@ -1,0 +1,29 @@
+"""Loader for the committed golden fixtures (tests/golden/*.npz, made by make_golden.py)."""
+import glob
+import os
+
+import numpy as np
+import scipy.sparse as sp
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def names():
+    return sorted(os.path.splitext(os.path.basename(f))[0] for f in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+
+
+def load(name):
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    dat = {"type": str(z["type"]), "ID": z["ID"], "times": z["times"], "obs": z["obs"],
+           "ncol_re": z["ncol_re"], "include_penalty": int(z["include_penalty"])}
+    for nm in ("X_fe", "X_re", "S"):
+        dat[nm] = sp.csr_matrix((z[nm + "_x"], (z[nm + "_i"], z[nm + "_j"])), shape=tuple(z[nm + "_shape"]))
+    if dat["type"] == "CTCRW":
+        dat["a0"], dat["P0"] = z["a0"], z["P0"]
+    out = {"par": z["par"], "nllk": float(z["nllk"]), "grad": z["grad"],
+           "known_answer": float(z["known_answer"])}
+    if "nllk_mpmath" in z:
+        out["nllk_mpmath"] = float(z["nllk_mpmath"])
+    if "aest_all" in z:
+        out["aest_all"] = z["aest_all"]
+    return dat, out
