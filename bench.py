@@ -282,6 +282,7 @@ def main():
         "gpu_launches": launches_per_step * args.steps,
         "roofline": roofline,
         "nllk": float(first[0]),
+        "launch_info": eng.launch_info(),
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         val, cores, sample, ms = cpu_time_evals(args, 5, 1)

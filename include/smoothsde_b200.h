@@ -87,21 +87,33 @@ typedef struct {
     double t_next;            /* time of the next shard's first row (only with CONT_NEXT) */
 } ssde_desc;
 
-/* Zero-copy variant for data that already lives on the GPU in the engine's native layout
- * (see smoothsde_b200/csrc/kernels_linpred.cuh).  All d_* pointers are device pointers that must
- * stay valid for the life of the handle; the rest is host memory and is copied. */
+/* Zero-copy variant for data that already lives on the GPU in the engine's native "warp-tile
+ * transposed" layout (smoothsde_b200/csrc/design.cuh): rows are grouped in warp-tiles of
+ * WT = 32 * LC rows, row i = q*WT + l*LC + k lives at position q*WT + k*32 + l of every per-row
+ * array, and the design is a sliced-ELL structure with one 24-byte descriptor per warp-tile.
+ * ssde_layout_info reports {LC, WT, padding unit, sizeof(descriptor)}; ssde_padded_rows(n) is the
+ * length every per-row array must have.  All d_* pointers are device pointers that must stay
+ * valid for the life of the handle; the rest is host memory and is copied. */
+typedef struct {
+    int64_t val_off;          /* first value of the warp-tile in d_val */
+    int64_t col_off;          /* first column index of the warp-tile in d_col */
+    uint32_t kmax;            /* byte p = slots of SDE parameter p; S = sum of the bytes */
+    uint32_t flags;           /* bit0: one column list col[col_off + j] for the whole warp-tile,
+                                 else per nonzero, indexed like the values */
+} ssde_wt_desc;               /* value of slot j, row (k, l): d_val[val_off + (k*S + j)*32 + l] */
+
 typedef struct {
     int32_t model, n_dim, n_par;
-    int64_t n;
-    int64_t nnz;
-    const uint32_t* d_rowptr; /* [n+1] */
-    const uint32_t* d_cnt;    /* [n]   byte p = nonzeros of parameter p in the row */
-    const uint32_t* d_col;    /* [nnz] column in theta = [coeff_fe | coeff_re] */
-    const double* d_val;      /* [nnz] */
-    const double* d_obs;      /* [n x n_dim] ROW-major, missing entries hold any finite value */
-    const double* d_dt;       /* [n] dt_i = t_{i+1} - t_i; 1 on rows flagged LAST */
-    const uint8_t* d_flags;   /* [n] bit0 track start, bit1 track last, bit2 obs present (CTCRW),
-                                 bit(3+d) dimension d missing (BM/OU) */
+    int64_t n, n_pad;
+    int64_t nnz;              /* informational */
+    const ssde_wt_desc* d_desc; /* [n_pad / WT] */
+    const double* d_val;
+    const uint32_t* d_col;    /* columns in theta = [coeff_fe | coeff_re] */
+    const double* d_obs;      /* n_dim planes of n_pad doubles, permuted; missing entries hold any finite value */
+    const double* d_dt;       /* [n_pad] permuted; dt_i = t_{i+1} - t_i; 1 on rows flagged LAST; CTCRW: on
+                                 track-start rows the 0-based track index (row of a0) instead */
+    const uint8_t* d_flags;   /* [n_pad] permuted; bit0 track start, bit1 track last, bit2 obs present
+                                 (CTCRW), bit(3+d) dimension d missing (BM/OU); 0xff = beyond row n */
     int32_t p_fe, p_re;
     ssde_triplet S;
     int32_t n_smooth;
@@ -114,6 +126,20 @@ typedef struct {
     int32_t device;
     int32_t shard_flags;
 } ssde_packed_desc;
+
+int64_t ssde_padded_rows(int64_t n);
+int ssde_layout_info(int32_t info[4]);
+
+/* Host-side packing of the design of `desc` into the device layout (no GPU needed); free the
+ * arrays with ssde_pack_free. */
+typedef struct {
+    int64_t n_pad, n_desc, n_val, n_col;
+    ssde_wt_desc* desc;
+    double* val;
+    uint32_t* col;
+} ssde_host_pack;
+int ssde_pack_host(const ssde_desc* desc, ssde_host_pack* out);
+void ssde_pack_free(ssde_host_pack* p);
 
 int ssde_create(const ssde_desc* desc, ssde_handle** out);
 int ssde_create_packed(const ssde_packed_desc* desc, ssde_handle** out);
@@ -150,11 +176,23 @@ double ssde_last_eval_ms(ssde_handle* h);
 /* Number of kernels the last evaluation launched. */
 int ssde_last_eval_launches(const ssde_handle* h);
 
+/* Launch geometry of the handle's kernels: {SMs, forward grid, adjoint grid, BM/OU grid, forward
+ * tiles, adjoint tiles, BM/OU tiles, tracks}.  Grids are (resident CTAs per SM) x SMs. */
+int ssde_launch_info(const ssde_handle* h, int32_t info[8]);
+
 /* Per-kernel device times: with profiling on, every evaluation records a CUDA event in front of
  * each kernel on the launching stream; ssde_last_kernel_times returns how many kernels the last
  * evaluation ran and fills ms[] / names[] (static strings) for up to `cap` of them. */
 int ssde_set_profile(ssde_handle* h, int on);
 int ssde_last_kernel_times(ssde_handle* h, int cap, float* ms, const char** names);
+
+/* Exact-transition CTCRW simulator on the device (SDE$simulate, R/sde.R:1448-1478; CTCRW_cov,
+ * R/utility.R:188-196), one dimension: all arrays are [n_tracks x n_steps] track-major device
+ * arrays; d_z[track][0] holds the start position on entry; d_e1, d_e2 are standard normal draws;
+ * d_mu may be NULL (mu = 0).  Asynchronous on `stream`. */
+int ssde_simulate_ctcrw(int device, int64_t n_tracks, int64_t n_steps, const double* d_times,
+                        const double* d_tau, const double* d_nu, const double* d_mu,
+                        const double* d_e1, const double* d_e2, double* d_z, void* stream);
 
 const char* ssde_last_error(const ssde_handle* h);
 const char* ssde_create_error(void);

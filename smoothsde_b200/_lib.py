@@ -36,16 +36,24 @@ class Desc(C.Structure):
                 ("device", C.c_int32), ("shard_flags", C.c_int32), ("t_next", C.c_double)]
 
 
+class WtDesc(C.Structure):
+    _fields_ = [("val_off", C.c_int64), ("col_off", C.c_int64), ("kmax", C.c_uint32), ("flags", C.c_uint32)]
+
+
 class PackedDesc(C.Structure):
     _fields_ = [("model", C.c_int32), ("n_dim", C.c_int32), ("n_par", C.c_int32),
-                ("n", C.c_int64), ("nnz", C.c_int64),
-                ("d_rowptr", C.c_void_p), ("d_cnt", C.c_void_p), ("d_col", C.c_void_p),
-                ("d_val", C.c_void_p), ("d_obs", C.c_void_p), ("d_dt", C.c_void_p),
-                ("d_flags", C.c_void_p),
+                ("n", C.c_int64), ("n_pad", C.c_int64), ("nnz", C.c_int64),
+                ("d_desc", C.c_void_p), ("d_val", C.c_void_p), ("d_col", C.c_void_p),
+                ("d_obs", C.c_void_p), ("d_dt", C.c_void_p), ("d_flags", C.c_void_p),
                 ("p_fe", C.c_int32), ("p_re", C.c_int32), ("S", Triplet),
                 ("n_smooth", C.c_int32), ("ncol_re", c_int32_p), ("include_penalty", C.c_int32),
                 ("n_ID", C.c_int32), ("track_starts", c_int64_p), ("a0", c_double_p),
                 ("P0", C.c_double * 3), ("device", C.c_int32), ("shard_flags", C.c_int32)]
+
+
+class HostPack(C.Structure):
+    _fields_ = [("n_pad", C.c_int64), ("n_desc", C.c_int64), ("n_val", C.c_int64), ("n_col", C.c_int64),
+                ("desc", C.POINTER(WtDesc)), ("val", c_double_p), ("col", C.POINTER(C.c_uint32))]
 
 
 class EngineError(RuntimeError):
@@ -59,7 +67,9 @@ _lib = None
 # every symbol include/smoothsde_b200.h declares
 EXPORTS = ["ssde_create", "ssde_create_packed", "ssde_destroy", "ssde_n_par", "ssde_par_layout",
            "ssde_eval", "ssde_eval_device", "ssde_check", "ssde_report", "ssde_last_eval_ms",
-           "ssde_last_eval_launches", "ssde_set_profile", "ssde_last_kernel_times", "ssde_last_error", "ssde_create_error", "ssde_version"]
+           "ssde_last_eval_launches", "ssde_set_profile", "ssde_last_kernel_times", "ssde_last_error", "ssde_create_error", "ssde_version",
+           "ssde_padded_rows", "ssde_layout_info", "ssde_pack_host", "ssde_pack_free",
+           "ssde_simulate_ctcrw", "ssde_launch_info"]
 
 
 def load():
@@ -103,6 +113,18 @@ def load():
     lib.ssde_last_error.restype = C.c_char_p
     lib.ssde_create_error.argtypes = []
     lib.ssde_create_error.restype = C.c_char_p
+    lib.ssde_padded_rows.argtypes = [C.c_int64]
+    lib.ssde_padded_rows.restype = C.c_int64
+    lib.ssde_layout_info.argtypes = [c_int32_p]
+    lib.ssde_layout_info.restype = C.c_int
+    lib.ssde_pack_host.argtypes = [C.POINTER(Desc), C.POINTER(HostPack)]
+    lib.ssde_pack_host.restype = C.c_int
+    lib.ssde_pack_free.argtypes = [C.POINTER(HostPack)]
+    lib.ssde_pack_free.restype = None
+    lib.ssde_simulate_ctcrw.argtypes = [C.c_int, C.c_int64, C.c_int64] + [vp] * 8
+    lib.ssde_simulate_ctcrw.restype = C.c_int
+    lib.ssde_launch_info.argtypes = [vp, c_int32_p]
+    lib.ssde_launch_info.restype = C.c_int
     lib.ssde_version.argtypes = []
     lib.ssde_version.restype = C.c_char_p
     _lib = lib

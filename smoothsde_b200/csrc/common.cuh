@@ -242,9 +242,10 @@ __device__ __forceinline__ typename Ops::Elem lookback(const ScanDesc& d, int t)
             if (lane < first) e = load_elem_cg<Elem>(d.agg + (size_t)idx * Elem::NDBL);
             else if (lane == first) e = load_elem_cg<Elem>(d.incl + (size_t)idx * Elem::NDBL);
         }
-        // ordered tree reduction: higher lanes are farther away
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
+        // ordered tree reduction: higher lanes are farther away; lanes beyond `first` hold the
+        // identity, so only ceil(log2(first + 1)) levels are needed
+#pragma unroll 1
+        for (int o = 1; o < 32 && o <= first; o <<= 1) {
             Elem f = shfl_down_elem(e, o);
             if (lane + o < 32) e = Ops::join(f, e);
         }
@@ -254,6 +255,44 @@ __device__ __forceinline__ typename Ops::Elem lookback(const ScanDesc& d, int t)
         base -= 32;
     }
     return acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// TMA bulk copies (cp.async.bulk, global -> shared, completion on an mbarrier): one lane of a warp
+// fetches the next contiguous block of its warp-tile while the warp computes on the current one.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// arrive (count 1) and announce `bytes` of asynchronous traffic for the current phase
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+// order this thread's earlier generic-proxy accesses to shared memory before later async-proxy
+// (TMA) writes to the same locations
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
 }  // namespace ssde

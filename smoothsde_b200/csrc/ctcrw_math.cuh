@@ -103,17 +103,19 @@ struct StepAux {
     double tp12, tp22;           // (T P_f)_12, (T P_f)_22
 };
 
-// Advances `s` (predicted state of row i) to the predicted state of row i+1 and returns the
-// row's log-likelihood contribution  -(d log F + sum u^2/F)/2  (0 if the row is missing).
+// Advances `s` (predicted state of row i) to the predicted state of row i+1.  Outputs the
+// innovation variance F (1 if the row is missing) and quad = sum_d u_d^2 / F (0 if missing); the
+// row's log-likelihood contribution is  -(d log F + quad)/2  (:231-234, no d*log(2 pi)).
 // `has_obs` false reproduces the missing branch (:214-217).
 template <int ND, bool WITH_AUX>
-SSDE_HD double fwd_step(State<ND>& s, const StepPar& sp, const double* y, const double* mu,
-                        bool has_obs, double h, StepAux<ND>* aux) {
-    double llk = 0.0;
+SSDE_HD void fwd_step_q(State<ND>& s, const StepPar& sp, const double* y, const double* mu,
+                        bool has_obs, double h, StepAux<ND>* aux, double& F_out, double& quad_out) {
     Sym2 Pf = s.P;
     Vec2 af[ND];
 #pragma unroll
     for (int d = 0; d < ND; ++d) af[d] = s.a[d];
+    F_out = 1.0;
+    quad_out = 0.0;
     if (has_obs) {
         const double F = s.P.a + h;                     // :223
         const double iF = 1.0 / F;
@@ -128,7 +130,8 @@ SSDE_HD double fwd_step(State<ND>& s, const StepPar& sp, const double* y, const 
             af[d].y = s.a[d].y + g2 * u;
             if (WITH_AUX) aux->w[d] = w;
         }
-        llk = -0.5 * ((double)ND * log(F) + quad);      // :231-234 (no d*log(2 pi))
+        F_out = F;
+        quad_out = quad;
         Pf.a = s.P.a - g1 * s.P.a;                      // P - F G G'
         Pf.b = s.P.b - g1 * s.P.b;
         Pf.c = s.P.c - g2 * s.P.b;
@@ -152,7 +155,15 @@ SSDE_HD double fwd_step(State<ND>& s, const StepPar& sp, const double* y, const 
     s.P.a = tp11 + sp.T12 * tp12 + sp.Q.a;
     s.P.b = sp.e * tp12 + sp.Q.b;
     s.P.c = sp.e * tp22 + sp.Q.c;
-    return llk;
+}
+
+// Same step, returning the row's log-likelihood contribution.
+template <int ND, bool WITH_AUX>
+SSDE_HD double fwd_step(State<ND>& s, const StepPar& sp, const double* y, const double* mu,
+                        bool has_obs, double h, StepAux<ND>* aux) {
+    double F, quad;
+    fwd_step_q<ND, WITH_AUX>(s, sp, y, mu, has_obs, h, aux, F, quad);
+    return has_obs ? -0.5 * ((double)ND * log(F) + quad) : 0.0;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -1,0 +1,268 @@
+// Device layout of the data list and of the sparse spline design matrices, and the two design
+// products every kernel fuses in: the linear predictor eta_i = X_i theta (replaces
+// par_vec = X_fe*coeff_fe + X_re*coeff_re and its reshape, nllk_ctcrw.hpp:143-149,
+// nllk_sde.hpp:61-67) and the transposed product grad_theta += X' eta_bar (TMB's reverse sweep of
+// the same line).
+//
+// "Warp-tile transposed" layout, built once in ssde_create:
+//   * rows are grouped in warp-tiles of WT = 32 * LC consecutive rows; lane l of the warp that
+//     processes a warp-tile owns the LC consecutive rows  q*WT + l*LC + k, k = 0..LC-1 (a
+//     contiguous piece of the time series, which is what the scan kernels need);
+//   * every per-row array (flags, dt, obs planes) is stored at  pos = q*WT + k*32 + l, so the
+//     k-th row of all 32 lanes is one coalesced 256-byte (doubles) request straight into
+//     registers -- no shared-memory staging;
+//   * the design is stored per warp-tile in a sliced-ELL form: X_fe and X_re are block-diagonal
+//     by parameter (rows j*n..(j+1)*n-1 belong to parameter j, R/sde.R:443-447), so row i has a
+//     short list of nonzeros per parameter.  A warp-tile has kmax_p slots for parameter p
+//     (S = sum_p kmax_p), value slot j of row (k, l) sits at  val[val_off + (k*S + j)*32 + l];
+//   * mgcv smooth blocks are dense in their rows and `bs = "re"` blocks are constant along a
+//     track, so almost every warp-tile uses the same columns in all of its rows: then
+//     (WT_UNIFORM) the column of slot j is stored once per warp-tile, col[col_off + j], instead
+//     of once per nonzero (zeros are filled in for rows that lack a column of the union).
+//     Otherwise columns are stored per nonzero with the same indexing as val.
+#pragma once
+
+#include "common.cuh"
+
+namespace ssde {
+
+constexpr int LC = 8;              // rows per thread chunk
+constexpr int WT = 32 * LC;        // rows per warp-tile
+constexpr int MAX_NP = 4;          // SDE parameters per row (n_dim + 2 <= 4)
+constexpr int TH_CACHE = 64;       // per-warp cache of theta[col[j]] for uniform warp-tiles
+constexpr int STAGE_SLOTS = 24;    // slots of one row-step that a warp stages in shared memory by TMA
+constexpr int STAGE_DBL = STAGE_SLOTS * 32;
+
+enum : uint32_t { WT_UNIFORM = 1u };
+
+struct WtDesc {
+    int64_t val_off;
+    int64_t col_off;
+    uint32_t kmax;                 // byte p = slots of parameter p
+    uint32_t flags;
+};
+static_assert(sizeof(WtDesc) == 24, "descriptor layout is part of the C ABI (ssde_create_packed)");
+
+struct DesignV2 {
+    int64_t n;                     // real rows
+    int64_t n_pad;                 // rows rounded up to a multiple of WT
+    const WtDesc* desc;            // [n_pad / WT]
+    const double* val;
+    const uint32_t* col;
+};
+
+__host__ __device__ __forceinline__ int64_t row_pos(int64_t row) {
+    const int64_t q = row / WT;
+    const int r = (int)(row - q * WT);
+    return q * WT + (int64_t)(r % LC) * 32 + r / LC;
+}
+
+__device__ __forceinline__ int slots_of(uint32_t kmax) {
+    return (int)((kmax & 255u) + ((kmax >> 8) & 255u) + ((kmax >> 16) & 255u) + (kmax >> 24));
+}
+
+// Per-warp view of one warp-tile's design.
+struct WtView {
+    const double* blk;             // val + val_off
+    const double* v;               // val + val_off + lane
+    const uint32_t* c;             // col + col_off (+ lane if not uniform)
+    const double* th;              // per-warp theta cache (shared memory) or nullptr
+    uint32_t kmax;
+    int S;
+    bool uniform;
+    bool staged;                   // row-steps are fetched with TMA bulk copies (uniform, 0 < S <= STAGE_SLOTS)
+};
+
+// Per-warp staging buffer for the values of one row-step (S x 32 doubles, slot-major) and the
+// mbarrier its TMA copies complete on.
+struct WarpStage {
+    double* buf;
+    uint64_t* bar;
+    unsigned phase;
+};
+
+__device__ __forceinline__ void stage_init(WarpStage& st, double* buf, uint64_t* bar) {
+    st.buf = buf; st.bar = bar; st.phase = 0;
+    if ((threadIdx.x & 31) == 0) mbar_init(bar, 1);
+}
+
+// Called by all lanes of a warp.  `th_cache` is this warp's TH_CACHE doubles of shared memory.
+__device__ __forceinline__ WtView open_warptile(const DesignV2& X, int64_t q, const double* __restrict__ theta,
+                                                double* th_cache) {
+    const int lane = threadIdx.x & 31;
+    const WtDesc d = X.desc[q];
+    WtView w;
+    w.kmax = d.kmax;
+    w.S = slots_of(d.kmax);
+    w.uniform = (d.flags & WT_UNIFORM) != 0;
+    w.blk = X.val + d.val_off;
+    w.v = w.blk + lane;
+    w.c = X.col + d.col_off + (w.uniform ? 0 : lane);
+    w.th = nullptr;
+    if (w.uniform && w.S <= TH_CACHE) {
+        __syncwarp();
+        for (int j = lane; j < w.S; j += 32) th_cache[j] = __ldg(theta + __ldg(w.c + j));
+        __syncwarp();
+        w.th = th_cache;
+    }
+    w.staged = w.th != nullptr && w.S > 0 && w.S <= STAGE_SLOTS;
+    return w;
+}
+
+// lane 0: start the copy of row-step k of the warp-tile into the staging buffer.  The caller has
+// made sure (with __syncwarp) that no lane still reads the buffer.
+__device__ __forceinline__ void stage_issue(const WtView& w, const WarpStage& st, int k) {
+    const unsigned bytes = (unsigned)w.S * 32u * 8u;
+    fence_proxy_async();
+    mbar_expect_tx(st.bar, bytes);
+    tma_load_1d(st.buf, w.blk + (size_t)k * w.S * 32, bytes, st.bar);
+}
+__device__ __forceinline__ void stage_wait(WarpStage& st) {
+    mbar_wait(st.bar, st.phase);
+    st.phase ^= 1u;
+}
+
+// eta[p] of this lane's row from the staged row-step
+template <int NP>
+__device__ __forceinline__ void row_eta_staged(const WtView& w, const WarpStage& st, double* eta) {
+    const double* v = st.buf + (threadIdx.x & 31);
+    const double* th = w.th;
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+        const int kp = (int)((w.kmax >> (8 * p)) & 255u);
+        double acc = 0.0;
+#pragma unroll 2
+        for (int i = 0; i < kp; ++i) { acc = fma(v[0], th[0], acc); v += 32; ++th; }
+        eta[p] = acc;
+    }
+}
+
+// eta[p] for the first NPRE parameters only, straight from global memory (row k of this lane)
+template <int NPRE>
+__device__ __forceinline__ void row_eta_prefix(const WtView& w, int k, const double* __restrict__ theta, double* eta) {
+    const double* v = w.v + (size_t)k * w.S * 32;
+    const uint32_t* c = w.c + (w.uniform ? 0 : (size_t)k * w.S * 32);
+    const int cs = w.uniform ? 1 : 32;
+    int j = 0;
+#pragma unroll
+    for (int p = 0; p < NPRE; ++p) {
+        const int kp = (int)((w.kmax >> (8 * p)) & 255u);
+        double acc = 0.0;
+        for (int i = 0; i < kp; ++i, ++j) {
+            const double t = w.th ? w.th[j] : __ldg(theta + __ldg(c + j * cs));
+            acc = fma(__ldg(v + j * 32), t, acc);
+        }
+        eta[p] = acc;
+    }
+}
+
+// eta[p] = sum over parameter p's slots of row k of this lane.
+template <int NP>
+__device__ __forceinline__ void row_eta(const WtView& w, int k, const double* __restrict__ theta, double* eta) {
+    const double* v = w.v + (size_t)k * w.S * 32;
+    int j = 0;
+    if (w.th) {
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            const int kp = (int)((w.kmax >> (8 * p)) & 255u);
+            double acc = 0.0;
+#pragma unroll 4
+            for (int i = 0; i < kp; ++i, ++j) acc = fma(__ldg(v + j * 32), w.th[j], acc);
+            eta[p] = acc;
+        }
+    } else {
+        const uint32_t* c = w.c + (w.uniform ? 0 : (size_t)k * w.S * 32);
+        const int cs = w.uniform ? 1 : 32;
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            const int kp = (int)((w.kmax >> (8 * p)) & 255u);
+            double acc = 0.0;
+            for (int i = 0; i < kp; ++i, ++j) acc = fma(__ldg(v + j * 32), __ldg(theta + __ldg(c + j * cs)), acc);
+            eta[p] = acc;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// transposed product for one warp-tile.  eb(k, p) returns d nllk / d eta of this lane's row k,
+// parameter p.  Per-CTA accumulators `sgrad` (shared memory, npc doubles, flushed by the caller)
+// are used when the parameter vector fits, global atomics otherwise.
+// ---------------------------------------------------------------------------------------------
+struct GradAcc {
+    double* sgrad;                 // shared-memory accumulators or nullptr
+    double* ggrad;                 // global gradient w.r.t. theta
+};
+
+__device__ __forceinline__ void grad_add(const GradAcc& g, uint32_t c, double v) {
+    if (g.sgrad) atomicAdd(g.sgrad + c, v);
+    else atomicAdd(g.ggrad + c, v);
+}
+
+// Uniform warp-tile with at most STAGE_SLOTS slots: per-lane partial sums over the LC rows go to
+// the warp's scratch T[j][lane] (the staging buffer, idle by now), then lane j adds up row j of
+// T -- no shuffles, one atomic per slot.
+template <int NP, class EB>
+__device__ __forceinline__ void scatter_warptile_staged(const WtView& w, double* T, const GradAcc& g, EB eb) {
+    const int lane = threadIdx.x & 31;
+    const size_t ks = (size_t)w.S * 32;
+    const double* vj = w.v;
+    double* tj = T + lane;
+    __syncwarp();
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+        const int kp = (int)((w.kmax >> (8 * p)) & 255u);
+        double e[LC];
+#pragma unroll
+        for (int k = 0; k < LC; ++k) e[k] = eb(k, p);
+        for (int i = 0; i < kp; ++i) {
+            double acc = 0.0;
+#pragma unroll
+            for (int k = 0; k < LC; ++k) acc = fma(__ldg(vj + k * ks), e[k], acc);
+            *tj = acc;
+            vj += 32; tj += 32;
+        }
+    }
+    __syncwarp();
+    if (lane < w.S) {
+        const double* t = T + lane * 32;
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+            s0 += t[(i + lane) & 31];
+            s1 += t[(i + 1 + lane) & 31];
+        }
+        grad_add(g, __ldg(w.c + lane), s0 + s1);
+    }
+    __syncwarp();
+}
+
+template <int NP, class EB>
+__device__ __forceinline__ void scatter_warptile(const WtView& w, const GradAcc& g, EB eb) {
+    const int lane = threadIdx.x & 31;
+    int j = 0;
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+        const int kp = (int)((w.kmax >> (8 * p)) & 255u);
+        double e[LC];
+#pragma unroll
+        for (int k = 0; k < LC; ++k) e[k] = eb(k, p);
+        for (int i = 0; i < kp; ++i, ++j) {
+            if (w.uniform) {
+                double acc = 0.0;
+#pragma unroll
+                for (int k = 0; k < LC; ++k) acc = fma(__ldg(w.v + ((size_t)k * w.S + j) * 32), e[k], acc);
+                acc = warp_sum(acc);
+                if (lane == 0) grad_add(g, __ldg(w.c + j), acc);
+            } else {
+#pragma unroll
+                for (int k = 0; k < LC; ++k) {
+                    const size_t o = ((size_t)k * w.S + j) * 32;
+                    const double t = __ldg(w.v + o) * e[k];
+                    if (t != 0.0) grad_add(g, __ldg(w.c + o), t);
+                }
+            }
+        }
+    }
+}
+
+}  // namespace ssde

@@ -1,29 +1,32 @@
-// CTCRW Kalman filter as a time-parallel scan: forward (likelihood) and adjoint (gradient)
-// kernels.  Replaces the sequential loop nllk_ctcrw.hpp:195-247 and TMB's reverse sweep of it.
+// CTCRW Kalman filter as a time-parallel scan, fused with the spline linear predictor and (in
+// the adjoint kernel) with the transposed design product.  Replaces the sequential loop
+// nllk_ctcrw.hpp:195-247 (+ :143-156 in front of it) and TMB's reverse sweep of both.
 //
 // Rows of all tracks are stacked exactly as in the reference's data list; a track start is a
-// "constant map" element, so the whole stack is ONE segmented scan and the same kernels serve
-// many short tracks, few long tracks and a single 1e8-row track.  Work decomposition:
-//   tile = NT threads x LC consecutive rows per thread, tiles taken from a dynamic ticket,
-//   (1) each thread composes its LC rows into one element (fwd_append),
+// "constant map" element, so the whole stack is ONE segmented scan and the same two kernels serve
+// many short tracks, few long tracks and a single 1e8-row track.  Work decomposition (layout in
+// design.cuh): tile = NT/32 warp-tiles, tiles taken from a dynamic ticket,
+//   (1) each thread walks its LC rows: coalesced loads of the design slots -> eta -> natural
+//       scale step matrices (kept in shared memory, never in HBM) -> composes the rows into one
+//       scan element (fwd_append),
 //   (2) warp shuffle scan + cross-warp scan of the thread elements,
 //   (3) chained look-back across tiles gives the state at the tile start,
 //   (4) each thread re-runs the plain filter over its rows from its exact start state.
-// The adjoint kernel walks the tiles in reverse with elements (L, z, D).
+// The adjoint kernel walks the tiles in reverse with elements (L, z, D), recomputes the forward
+// states of its rows from one checkpoint per thread chunk and ends with X' eta_bar.
 #pragma once
 
-#include "common.cuh"
+#include "design.cuh"
 
 namespace ssde {
 
 template <int ND>
 struct CtcrwArgs {
-    int64_t n;                 // rows in this shard
-    int ntiles;
-    const double* W;           // [n, ND+3]: mu_1..mu_ND, tau, e, s2   (written by linpred kernel)
-    const double* obs;         // [n, ND] row-major, NA replaced by 0
-    const double* dt;          // [n]
-    const uint8_t* flags;      // [n]
+    DesignV2 X;
+    const double* theta;       // [coeff_fe | coeff_re]
+    const double* obs;         // ND planes of n_pad doubles, permuted (design.cuh), NA replaced by 0
+    const double* dt;          // [n_pad] permuted
+    const uint8_t* flags;      // [n_pad] permuted, 0xff beyond the end
     const int64_t* track_starts;   // [n_tracks] sorted rows flagged ROW_START
     const double* a0;          // [n_tracks, 2*ND]
     int n_tracks;
@@ -32,24 +35,22 @@ struct CtcrwArgs {
     const double* s_in;        // optional incoming state (2*ND + 3 doubles) for a continued shard
     const double* g_in;        // optional incoming adjoint (2*ND + 3 doubles)
     double* ckpt;              // [(2*ND+3), nchunks] start state of every thread chunk
-    int64_t nchunks;
-    double* tile_llk;          // [ntiles]
-    double* tile_gh;           // [ntiles]
-    double* eta_bar;           // [n, ND+2] adjoint of the linear predictors
+    int64_t nchunks;           // n_pad / LC
+    double* tile_llk;          // [ntiles_f]
+    double* tile_gh;           // [ntiles_b]
+    double* grad_theta;        // [p_theta], accumulated with atomics
+    int p_theta;
     double* aest;              // optional [n, 2*ND]: REPORT(aest_all), nllk_ctcrw.hpp:246-249
     ScanDesc fdesc, bdesc;
+    int ntiles;
 };
 
+// Start state of the track whose first row carries track index `idx` (stored, as a double, in
+// the otherwise unused dt slot of track-start rows).
 template <int ND>
-__device__ __forceinline__ State<ND> track_start_state(const CtcrwArgs<ND>& a, int64_t row) {
-    // binary search: index of `row` in track_starts
-    int lo = 0, hi = a.n_tracks - 1;
-    while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (a.track_starts[mid] <= row) lo = mid; else hi = mid - 1;
-    }
+__device__ __forceinline__ State<ND> track_start_state(const CtcrwArgs<ND>& a, double idx) {
     State<ND> s;
-    const double* p = a.a0 + (size_t)lo * 2 * ND;
+    const double* p = a.a0 + (size_t)idx * 2 * ND;
 #pragma unroll
     for (int d = 0; d < ND; ++d) s.a[d] = {p[2 * d], p[2 * d + 1]};
     s.P = a.P0;
@@ -65,80 +66,89 @@ __device__ __forceinline__ State<ND> load_state(const double* p) {
     return s;
 }
 
-template <int ND, int NT, int LC>
-struct CtcrwSmem {
-    static constexpr int NW = ND + 3;
-    using SW = Staged<NW, NT, LC>;
-    using SY = Staged<ND, NT, LC>;
-    using SD = Staged<1, NT, LC>;
-    static constexpr int FS = 2 * ND + 3;               // doubles of a forward state
-    using SF = Staged<FS, NT, LC>;
-    static constexpr int OFF_W = 0;
-    static constexpr int OFF_Y = OFF_W + SW::SIZE;
-    static constexpr int OFF_DT = OFF_Y + SY::SIZE;
-    static constexpr int OFF_WAGG = OFF_DT + SD::SIZE;   // NT/32 elements (<= 24 doubles each)
-    static constexpr int OFF_MISC = OFF_WAGG + (NT / 32) * 24;
-    static constexpr int OFF_FS = OFF_MISC + 32;          // backward only
-    static constexpr int DBL_FWD = OFF_FS;
-    static constexpr int DBL_BWD = OFF_FS + SF::SIZE;
-    static constexpr size_t BYTES_FWD = (size_t)DBL_FWD * 8 + (size_t)LC * (NT + 4);
-    static constexpr size_t BYTES_BWD = (size_t)DBL_BWD * 8 + (size_t)LC * (NT + 4);
-};
+// the 8 row flags of this lane's chunk, packed (0xff = row beyond the end)
+__device__ __forceinline__ unsigned long long load_flags8(const uint8_t* __restrict__ flags, int64_t base) {
+    unsigned long long fl = 0;
+#pragma unroll
+    for (int k = 0; k < LC; ++k) fl |= (unsigned long long)flags[base + k * 32] << (8 * k);
+    return fl;
+}
 
 // ---------------------------------------------------------------------------------------------
 // forward kernel
 // ---------------------------------------------------------------------------------------------
-template <int ND, int NT, int LC>
-__global__ void __launch_bounds__(NT) ctcrw_fwd_kernel(CtcrwArgs<ND> a) {
-    using SM = CtcrwSmem<ND, NT, LC>;
+template <int ND, int NT>
+struct FwdSmem {
+    static constexpr int NC = 5;                 // T12, e, Qa, Qb, Qc
+    double W[LC][NC][NT];
+    double stage[NT / 32][STAGE_DBL];
+    double wagg[NT / 32][24];
+    double misc[32];
+    double th[NT / 32][TH_CACHE];
+    uint64_t bar[NT / 32];
+    int ticket;
+};
+
+template <int ND, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(CtcrwArgs<ND> a) {
+    using SM = FwdSmem<ND, NT>;
     using Ops = FwdOps<ND>;
     using Elem = FwdElem<ND>;
     constexpr int NWARP = NT / 32;
+    constexpr int NP = ND + 2;
     static_assert(Elem::NDBL <= 24, "element too large for the shared staging area");
-    extern __shared__ __align__(16) double smem[];
-    double* sW = smem + SM::OFF_W;
-    double* sY = smem + SM::OFF_Y;
-    double* sDt = smem + SM::OFF_DT;
-    double* sWagg = smem + SM::OFF_WAGG;
-    double* sMisc = smem + SM::OFF_MISC;
-    uint8_t* sFl = reinterpret_cast<uint8_t*>(smem + SM::DBL_FWD);
-    __shared__ int s_ticket;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    SM& sm = *reinterpret_cast<SM*>(smem_raw);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double h = exp(2.0 * a.par[0]);               // H = sigma_obs^2 I, nllk_ctcrw.hpp:136,167
+    WarpStage st;
+    stage_init(st, sm.stage[warp], &sm.bar[warp]);
+    mbar_fence_init();
 
     while (true) {
         __syncthreads();
-        if (tid == 0) s_ticket = (int)atomicAdd(a.fdesc.ticket, 1u);
+        if (tid == 0) sm.ticket = (int)atomicAdd(a.fdesc.ticket, 1u);
         __syncthreads();
-        const int tile = s_ticket;
+        const int tile = sm.ticket;
         if (tile >= a.ntiles) break;
-        const int64_t r0 = (int64_t)tile * (NT * LC);
-        stage_rows<SM::NW, NT, LC>(sW, a.W, r0, a.n);
-        stage_rows<ND, NT, LC>(sY, a.obs, r0, a.n);
-        stage_rows<1, NT, LC>(sDt, a.dt, r0, a.n);
-        stage_flags<NT, LC>(sFl, a.flags, r0, a.n);
-        __syncthreads();
+        const int64_t q = (int64_t)tile * NWARP + warp;
+        const int64_t base = q * WT + lane;
+        const int64_t row0 = q * WT + (int64_t)lane * LC;
+        const WtView w = open_warptile(a.X, q, a.theta, sm.th[warp]);
+        if (w.staged && lane == 0) stage_issue(w, st, 0);
+        const unsigned long long fl = load_flags8(a.flags, base);
 
         // (1) thread element over its LC rows
-        const int64_t row0 = r0 + (int64_t)tid * LC;
         Elem E = fwd_identity<ND>();
 #pragma unroll 1
         for (int k = 0; k < LC; ++k) {
-            const uint8_t f = sFl[k * (NT + 4) + tid];
-            if (f == 0xff) break;
-            if (f & ROW_START) {
-                fwd_append_start<ND>(E, track_start_state<ND>(a, row0 + k));
-            } else {
-                double mu[ND], y[ND];
+            const int64_t pos = base + k * 32;
+            const uint8_t f = (uint8_t)(fl >> (8 * k));
+            const bool live = f != 0xff;
+            const bool step = live && !(f & ROW_START);
+            const double dtv = live ? a.dt[pos] : 1.0;
+            double y[ND];
 #pragma unroll
-                for (int d = 0; d < ND; ++d) {
-                    mu[d] = sW[SM::SW::at(k, d, tid)];
-                    y[d] = sY[SM::SY::at(k, d, tid)];
-                }
-                const StepPar sp = make_step(sW[SM::SW::at(k, ND, tid)], sW[SM::SW::at(k, ND + 1, tid)],
-                                             sW[SM::SW::at(k, ND + 2, tid)], sDt[SM::SD::at(k, 0, tid)]);
-                fwd_append<ND>(E, sp, y, mu, (f & ROW_OBS) != 0, h);
+            for (int d = 0; d < ND; ++d) y[d] = step ? a.obs[(size_t)d * a.X.n_pad + pos] : 0.0;
+            double eta[NP];
+            if (w.staged) {
+                stage_wait(st);
+                row_eta_staged<NP>(w, st, eta);
+                __syncwarp();
+                if (lane == 0 && k + 1 < LC) stage_issue(w, st, k + 1);
+            } else if (step) {
+                row_eta<NP>(w, k, a.theta, eta);
+            }
+            if (step) {
+                double tau, e, s2;
+                transform_row(eta[ND], eta[ND + 1], dtv, tau, e, s2);
+                const StepPar sp = make_step(tau, e, s2, dtv);
+                sm.W[k][0][tid] = sp.T12; sm.W[k][1][tid] = sp.e;
+                sm.W[k][2][tid] = sp.Q.a; sm.W[k][3][tid] = sp.Q.b; sm.W[k][4][tid] = sp.Q.c;
+                fwd_append<ND>(E, sp, y, eta, (f & ROW_OBS) != 0, h);
+            } else if (live) {
+                fwd_append_start<ND>(E, track_start_state<ND>(a, dtv));
             }
         }
         // (2) warp inclusive scan (lower lanes = earlier rows)
@@ -148,15 +158,15 @@ __global__ void __launch_bounds__(NT) ctcrw_fwd_kernel(CtcrwArgs<ND> a) {
             Elem f = shfl_up_elem(inc, o);
             if (lane >= o) inc = fwd_combine<ND>(f, inc);
         }
-        if (lane == 31) store_elem(sWagg + warp * 24, inc);
+        if (lane == 31) store_elem(sm.wagg[warp], inc);
         Elem exc = shfl_up_elem(inc, 1);
         if (lane == 0) exc = fwd_identity<ND>();
         __syncthreads();
         // (3) tile aggregate, chained look-back (warp 0), tile start state
         if (warp == 0) {
-            Elem tagg = load_elem<Elem>(sWagg);
+            Elem tagg = load_elem<Elem>(sm.wagg[0]);
 #pragma unroll
-            for (int w = 1; w < NWARP; ++w) tagg = fwd_combine<ND>(tagg, load_elem<Elem>(sWagg + w * 24));
+            for (int ww = 1; ww < NWARP; ++ww) tagg = fwd_combine<ND>(tagg, load_elem<Elem>(sm.wagg[ww]));
             if (lane == 0) publish_agg<Ops>(a.fdesc, tile, tagg);
             const Elem pre = lookback<Ops>(a.fdesc, tile);
             if (lane == 0) {
@@ -167,20 +177,20 @@ __global__ void __launch_bounds__(NT) ctcrw_fwd_kernel(CtcrwArgs<ND> a) {
                 else { s0.P = a.P0;
 #pragma unroll
                     for (int d = 0; d < ND; ++d) s0.a[d] = {0.0, 0.0}; }
-                const State<ND> st = fwd_apply<ND>(pre, s0);
+                const State<ND> st0 = fwd_apply<ND>(pre, s0);
 #pragma unroll
-                for (int d = 0; d < ND; ++d) { sMisc[2 * d] = st.a[d].x; sMisc[2 * d + 1] = st.a[d].y; }
-                sMisc[2 * ND] = st.P.a; sMisc[2 * ND + 1] = st.P.b; sMisc[2 * ND + 2] = st.P.c;
+                for (int d = 0; d < ND; ++d) { sm.misc[2 * d] = st0.a[d].x; sm.misc[2 * d + 1] = st0.a[d].y; }
+                sm.misc[2 * ND] = st0.P.a; sm.misc[2 * ND + 1] = st0.P.b; sm.misc[2 * ND + 2] = st0.P.c;
             }
         }
         __syncthreads();
         // (4) exact start state of this thread, checkpoint, plain filter re-run
-        State<ND> s = load_state<ND>(sMisc);
+        State<ND> s = load_state<ND>(sm.misc);
 #pragma unroll 1
-        for (int w = 0; w < warp; ++w) s = fwd_apply<ND>(load_elem<Elem>(sWagg + w * 24), s);
+        for (int ww = 0; ww < warp; ++ww) s = fwd_apply<ND>(load_elem<Elem>(sm.wagg[ww]), s);
         s = fwd_apply<ND>(exc, s);
-        const int64_t chunk = (int64_t)tile * NT + tid;
-        if (row0 < a.n) {
+        const int64_t chunk = q * 32 + lane;
+        {
 #pragma unroll
             for (int d = 0; d < ND; ++d) {
                 a.ckpt[(size_t)(2 * d) * a.nchunks + chunk] = s.a[d].x;
@@ -190,23 +200,31 @@ __global__ void __launch_bounds__(NT) ctcrw_fwd_kernel(CtcrwArgs<ND> a) {
             a.ckpt[(size_t)(2 * ND + 1) * a.nchunks + chunk] = s.P.b;
             a.ckpt[(size_t)(2 * ND + 2) * a.nchunks + chunk] = s.P.c;
         }
-        double llk = 0.0;
+        // sum_i log F_i is taken as the log of a running product (one log per chunk instead of
+        // one per row); the product is folded into `slog` whenever it leaves a safe range.
+        double quad = 0.0, fprod = 1.0, slog = 0.0;
 #pragma unroll 1
         for (int k = 0; k < LC; ++k) {
-            const uint8_t f = sFl[k * (NT + 4) + tid];
+            const uint8_t f = (uint8_t)(fl >> (8 * k));
             if (f == 0xff) break;
+            const int64_t pos = base + k * 32;
+            const double dtv = a.dt[pos];
             if (f & ROW_START) {
-                s = track_start_state<ND>(a, row0 + k);
+                s = track_start_state<ND>(a, dtv);
             } else {
                 double mu[ND], y[ND];
+                row_eta_prefix<ND>(w, k, a.theta, mu);
 #pragma unroll
-                for (int d = 0; d < ND; ++d) {
-                    mu[d] = sW[SM::SW::at(k, d, tid)];
-                    y[d] = sY[SM::SY::at(k, d, tid)];
-                }
-                const StepPar sp = make_step(sW[SM::SW::at(k, ND, tid)], sW[SM::SW::at(k, ND + 1, tid)],
-                                             sW[SM::SW::at(k, ND + 2, tid)], sDt[SM::SD::at(k, 0, tid)]);
-                llk += fwd_step<ND, false>(s, sp, y, mu, (f & ROW_OBS) != 0, h, nullptr);
+                for (int d = 0; d < ND; ++d) y[d] = a.obs[(size_t)d * a.X.n_pad + pos];
+                StepPar sp;
+                sp.T12 = sm.W[k][0][tid]; sp.e = sm.W[k][1][tid];
+                sp.Q.a = sm.W[k][2][tid]; sp.Q.b = sm.W[k][3][tid]; sp.Q.c = sm.W[k][4][tid];
+                sp.B1 = dtv - sp.T12; sp.B2 = 1.0 - sp.e;      // makeB_ctcrw, :87-88
+                double F, qd;
+                fwd_step_q<ND, false>(s, sp, y, mu, (f & ROW_OBS) != 0, h, nullptr, F, qd);
+                quad += qd;
+                fprod *= F;
+                if (!(fprod > 1e-150 && fprod < 1e150)) { slog += log(fprod); fprod = 1.0; }
             }
             if (a.aest) {
                 double* o = a.aest + (size_t)(row0 + k) * (2 * ND);
@@ -214,7 +232,8 @@ __global__ void __launch_bounds__(NT) ctcrw_fwd_kernel(CtcrwArgs<ND> a) {
                 for (int d = 0; d < ND; ++d) { o[2 * d] = s.a[d].x; o[2 * d + 1] = s.a[d].y; }
             }
         }
-        const double tl = block_sum<NT>(llk, sMisc + 16);
+        const double llk = -0.5 * ((double)ND * (slog + log(fprod)) + quad);
+        const double tl = block_sum<NT>(llk, sm.misc + 16);
         if (tid == 0) a.tile_llk[tile] = tl;
     }
 }
@@ -231,88 +250,109 @@ __device__ __forceinline__ Adj<ND> load_adj(const double* p) {
     return g;
 }
 
-template <int ND, int NT, int LC>
-__global__ void __launch_bounds__(NT) ctcrw_bwd_kernel(CtcrwArgs<ND> a) {
-    using SM = CtcrwSmem<ND, NT, LC>;
+constexpr int SGRAD = 256;         // per-CTA gradient accumulators (doubles) when p_theta fits
+
+template <int ND, int NT>
+struct BwdSmem {
+    static constexpr int FS = 2 * ND + 3;        // forward state before the row
+    static constexpr int NC = FS + 3;            // + tau, e, s2
+    double R[LC][NC][NT];
+    double stage[NT / 32][STAGE_DBL];
+    double wagg[NT / 32][16];
+    double misc[32];
+    double th[NT / 32][TH_CACHE];
+    double sgrad[SGRAD];
+    uint64_t bar[NT / 32];
+    int ticket;
+};
+
+template <int ND, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) ctcrw_bwd_kernel(CtcrwArgs<ND> a) {
+    using SM = BwdSmem<ND, NT>;
     using Ops = BwdOps<ND>;
     using Elem = BwdElem<ND>;
     constexpr int NWARP = NT / 32;
     constexpr int NP = ND + 2;
-    extern __shared__ __align__(16) double smem[];
-    double* sW = smem + SM::OFF_W;
-    double* sY = smem + SM::OFF_Y;
-    double* sDt = smem + SM::OFF_DT;
-    double* sWagg = smem + SM::OFF_WAGG;
-    double* sMisc = smem + SM::OFF_MISC;
-    double* sFs = smem + SM::OFF_FS;
-    uint8_t* sFl = reinterpret_cast<uint8_t*>(smem + SM::DBL_BWD);
-    __shared__ int s_ticket;
+    constexpr int FS = SM::FS;
+    static_assert(Elem::NDBL <= 16, "element too large for the shared staging area");
+    static_assert(SM::NC >= NP, "eta_bar reuses the state slots");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    SM& sm = *reinterpret_cast<SM*>(smem_raw);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double h = exp(2.0 * a.par[0]);
+    GradAcc gacc{(a.p_theta <= SGRAD) ? sm.sgrad : nullptr, a.grad_theta};
+    if (gacc.sgrad) for (int i = tid; i < SGRAD; i += NT) sm.sgrad[i] = 0.0;
+    WarpStage st;
+    stage_init(st, sm.stage[warp], &sm.bar[warp]);
+    mbar_fence_init();
 
     while (true) {
         __syncthreads();
-        if (tid == 0) s_ticket = (int)atomicAdd(a.bdesc.ticket, 1u);
+        if (tid == 0) sm.ticket = (int)atomicAdd(a.bdesc.ticket, 1u);
         __syncthreads();
-        const int ticket = s_ticket;
+        const int ticket = sm.ticket;
         if (ticket >= a.ntiles) break;
         const int tile = a.ntiles - 1 - ticket;           // reverse time order
-        const int64_t r0 = (int64_t)tile * (NT * LC);
-        stage_rows<SM::NW, NT, LC>(sW, a.W, r0, a.n);
-        stage_rows<ND, NT, LC>(sY, a.obs, r0, a.n);
-        stage_rows<1, NT, LC>(sDt, a.dt, r0, a.n);
-        stage_flags<NT, LC>(sFl, a.flags, r0, a.n);
-        __syncthreads();
+        const int64_t q = (int64_t)tile * NWARP + warp;
+        const int64_t base = q * WT + lane;
+        const int64_t chunk = q * 32 + lane;
+        const WtView w = open_warptile(a.X, q, a.theta, sm.th[warp]);
+        if (w.staged && lane == 0) stage_issue(w, st, 0);
+        const unsigned long long fl = load_flags8(a.flags, base);
 
         // (1) recompute the forward states of this thread's rows from its checkpoint and compose
         //     the rows' adjoint elements (in time order)
-        const int64_t row0 = r0 + (int64_t)tid * LC;
-        const int64_t chunk = (int64_t)tile * NT + tid;
         State<ND> s;
-        if (row0 < a.n) {
 #pragma unroll
-            for (int d = 0; d < ND; ++d) {
-                s.a[d].x = a.ckpt[(size_t)(2 * d) * a.nchunks + chunk];
-                s.a[d].y = a.ckpt[(size_t)(2 * d + 1) * a.nchunks + chunk];
-            }
-            s.P.a = a.ckpt[(size_t)(2 * ND) * a.nchunks + chunk];
-            s.P.b = a.ckpt[(size_t)(2 * ND + 1) * a.nchunks + chunk];
-            s.P.c = a.ckpt[(size_t)(2 * ND + 2) * a.nchunks + chunk];
-        } else {
-            s.P = a.P0;
-#pragma unroll
-            for (int d = 0; d < ND; ++d) s.a[d] = {0.0, 0.0};
+        for (int d = 0; d < ND; ++d) {
+            s.a[d].x = a.ckpt[(size_t)(2 * d) * a.nchunks + chunk];
+            s.a[d].y = a.ckpt[(size_t)(2 * d + 1) * a.nchunks + chunk];
         }
+        s.P.a = a.ckpt[(size_t)(2 * ND) * a.nchunks + chunk];
+        s.P.b = a.ckpt[(size_t)(2 * ND + 1) * a.nchunks + chunk];
+        s.P.c = a.ckpt[(size_t)(2 * ND + 2) * a.nchunks + chunk];
         Elem E = bwd_identity<ND>();
 #pragma unroll 1
         for (int k = 0; k < LC; ++k) {
-            const uint8_t f = sFl[k * (NT + 4) + tid];
-            if (f == 0xff) break;
+            const int64_t pos = base + k * 32;
+            const uint8_t f = (uint8_t)(fl >> (8 * k));
+            const bool live = f != 0xff;
+            const bool step = live && !(f & ROW_START);
+            const double dtv = live ? a.dt[pos] : 1.0;
+            double y[ND];
+#pragma unroll
+            for (int d = 0; d < ND; ++d) y[d] = step ? a.obs[(size_t)d * a.X.n_pad + pos] : 0.0;
+            double eta[NP];
+            if (w.staged) {
+                stage_wait(st);
+                row_eta_staged<NP>(w, st, eta);
+                __syncwarp();
+                if (lane == 0 && k + 1 < LC) stage_issue(w, st, k + 1);
+            } else if (step) {
+                row_eta<NP>(w, k, a.theta, eta);
+            }
             // state BEFORE row k
 #pragma unroll
             for (int d = 0; d < ND; ++d) {
-                sFs[SM::SF::at(k, 2 * d, tid)] = s.a[d].x;
-                sFs[SM::SF::at(k, 2 * d + 1, tid)] = s.a[d].y;
+                sm.R[k][2 * d][tid] = s.a[d].x;
+                sm.R[k][2 * d + 1][tid] = s.a[d].y;
             }
-            sFs[SM::SF::at(k, 2 * ND, tid)] = s.P.a;
-            sFs[SM::SF::at(k, 2 * ND + 1, tid)] = s.P.b;
-            sFs[SM::SF::at(k, 2 * ND + 2, tid)] = s.P.c;
-            if (f & ROW_START) {
-                s = track_start_state<ND>(a, row0 + k);
-                E = bwd_combine<ND>(E, bwd_const<ND>(adj_zero<ND>()));
-            } else {
-                double mu[ND], y[ND];
-#pragma unroll
-                for (int d = 0; d < ND; ++d) {
-                    mu[d] = sW[SM::SW::at(k, d, tid)];
-                    y[d] = sY[SM::SY::at(k, d, tid)];
-                }
-                const StepPar sp = make_step(sW[SM::SW::at(k, ND, tid)], sW[SM::SW::at(k, ND + 1, tid)],
-                                             sW[SM::SW::at(k, ND + 2, tid)], sDt[SM::SD::at(k, 0, tid)]);
+            sm.R[k][2 * ND][tid] = s.P.a;
+            sm.R[k][2 * ND + 1][tid] = s.P.b;
+            sm.R[k][2 * ND + 2][tid] = s.P.c;
+            if (step) {
+                double tau, e, s2;
+                transform_row(eta[ND], eta[ND + 1], dtv, tau, e, s2);
+                sm.R[k][FS][tid] = tau; sm.R[k][FS + 1][tid] = e; sm.R[k][FS + 2][tid] = s2;
+                const StepPar sp = make_step(tau, e, s2, dtv);
                 StepAux<ND> ax;
-                fwd_step<ND, true>(s, sp, y, mu, (f & ROW_OBS) != 0, h, &ax);
+                double F, qd;
+                fwd_step_q<ND, true>(s, sp, y, eta, (f & ROW_OBS) != 0, h, &ax, F, qd);
                 E = bwd_combine<ND>(E, bwd_row_elem<ND>(sp, ax, (f & ROW_OBS) != 0, (f & ROW_LAST) != 0));
+            } else if (live) {
+                s = track_start_state<ND>(a, dtv);
+                E = bwd_combine<ND>(E, bwd_const<ND>(adj_zero<ND>()));
             }
         }
         // (2) warp inclusive SUFFIX scan (higher lanes = later rows)
@@ -322,15 +362,15 @@ __global__ void __launch_bounds__(NT) ctcrw_bwd_kernel(CtcrwArgs<ND> a) {
             Elem f = shfl_down_elem(inc, o);
             if (lane + o < 32) inc = bwd_combine<ND>(inc, f);
         }
-        if (lane == 0) store_elem(sWagg + warp * 24, inc);
+        if (lane == 0) store_elem(sm.wagg[warp], inc);
         Elem exc = shfl_down_elem(inc, 1);
         if (lane == 31) exc = bwd_identity<ND>();
         __syncthreads();
         // (3) tile aggregate, chained look-back over LATER tiles, adjoint entering the tile end
         if (warp == 0) {
-            Elem tagg = load_elem<Elem>(sWagg + (NWARP - 1) * 24);
+            Elem tagg = load_elem<Elem>(sm.wagg[NWARP - 1]);
 #pragma unroll
-            for (int w = NWARP - 2; w >= 0; --w) tagg = bwd_combine<ND>(load_elem<Elem>(sWagg + w * 24), tagg);
+            for (int ww = NWARP - 2; ww >= 0; --ww) tagg = bwd_combine<ND>(load_elem<Elem>(sm.wagg[ww]), tagg);
             if (lane == 0) publish_agg<Ops>(a.bdesc, ticket, tagg);
             const Elem suf = lookback<Ops>(a.bdesc, ticket);
             if (lane == 0) {
@@ -338,60 +378,71 @@ __global__ void __launch_bounds__(NT) ctcrw_bwd_kernel(CtcrwArgs<ND> a) {
                 Adj<ND> g0 = a.g_in ? load_adj<ND>(a.g_in) : adj_zero<ND>();
                 const Adj<ND> gt = bwd_apply<ND>(suf, g0);
 #pragma unroll
-                for (int d = 0; d < ND; ++d) { sMisc[2 * d] = gt.a[d].x; sMisc[2 * d + 1] = gt.a[d].y; }
-                sMisc[2 * ND] = gt.P.a; sMisc[2 * ND + 1] = gt.P.b; sMisc[2 * ND + 2] = gt.P.c;
+                for (int d = 0; d < ND; ++d) { sm.misc[2 * d] = gt.a[d].x; sm.misc[2 * d + 1] = gt.a[d].y; }
+                sm.misc[2 * ND] = gt.P.a; sm.misc[2 * ND + 1] = gt.P.b; sm.misc[2 * ND + 2] = gt.P.c;
             }
         }
         __syncthreads();
         // (4) adjoint entering this thread's last row, then the reverse sweep over its rows
-        Adj<ND> g = load_adj<ND>(sMisc);
+        Adj<ND> g = load_adj<ND>(sm.misc);
 #pragma unroll 1
-        for (int w = NWARP - 1; w > warp; --w) g = bwd_apply<ND>(load_elem<Elem>(sWagg + w * 24), g);
+        for (int ww = NWARP - 1; ww > warp; --ww) g = bwd_apply<ND>(load_elem<Elem>(sm.wagg[ww]), g);
         g = bwd_apply<ND>(exc, g);
         double gh = 0.0;
 #pragma unroll 1
         for (int k = LC - 1; k >= 0; --k) {
-            const uint8_t f = sFl[k * (NT + 4) + tid];
-            if (f == 0xff) continue;
+            const uint8_t f = (uint8_t)(fl >> (8 * k));
             double gp[NP];
 #pragma unroll
             for (int j = 0; j < NP; ++j) gp[j] = 0.0;
-            if (f & ROW_START) {
-                g = adj_zero<ND>();
-            } else {
-                State<ND> sk;
+            if (f != 0xff) {
+                if (f & ROW_START) {
+                    g = adj_zero<ND>();
+                } else {
+                    const int64_t pos = base + k * 32;
+                    const double dtv = a.dt[pos];
+                    double mu[ND], y[ND];
+                    row_eta_prefix<ND>(w, k, a.theta, mu);
 #pragma unroll
-                for (int d = 0; d < ND; ++d) {
-                    sk.a[d].x = sFs[SM::SF::at(k, 2 * d, tid)];
-                    sk.a[d].y = sFs[SM::SF::at(k, 2 * d + 1, tid)];
-                }
-                sk.P.a = sFs[SM::SF::at(k, 2 * ND, tid)];
-                sk.P.b = sFs[SM::SF::at(k, 2 * ND + 1, tid)];
-                sk.P.c = sFs[SM::SF::at(k, 2 * ND + 2, tid)];
-                double mu[ND], y[ND];
+                    for (int d = 0; d < ND; ++d) y[d] = a.obs[(size_t)d * a.X.n_pad + pos];
+                    State<ND> sk;
 #pragma unroll
-                for (int d = 0; d < ND; ++d) {
-                    mu[d] = sW[SM::SW::at(k, d, tid)];
-                    y[d] = sY[SM::SY::at(k, d, tid)];
+                    for (int d = 0; d < ND; ++d) {
+                        sk.a[d].x = sm.R[k][2 * d][tid];
+                        sk.a[d].y = sm.R[k][2 * d + 1][tid];
+                    }
+                    sk.P.a = sm.R[k][2 * ND][tid];
+                    sk.P.b = sm.R[k][2 * ND + 1][tid];
+                    sk.P.c = sm.R[k][2 * ND + 2][tid];
+                    const double tau = sm.R[k][FS][tid], e = sm.R[k][FS + 1][tid], s2 = sm.R[k][FS + 2][tid];
+                    const StepPar sp = make_step(tau, e, s2, dtv);
+                    const bool has = (f & ROW_OBS) != 0, cut = (f & ROW_LAST) != 0;
+                    StepAux<ND> ax;
+                    double F, qd;
+                    fwd_step_q<ND, true>(sk, sp, y, mu, has, h, &ax, F, qd);
+                    const Adj<ND> gin = cut ? adj_zero<ND>() : g;
+                    double g_h;
+                    row_param_grad<ND>(gin, sp, ax, mu, tau, e, s2, dtv, has, gp, gp[ND], gp[ND + 1], g_h);
+                    gh += g_h;
+                    g = bwd_apply<ND>(bwd_row_elem<ND>(sp, ax, has, cut), g);
                 }
-                const double tau = sW[SM::SW::at(k, ND, tid)], e = sW[SM::SW::at(k, ND + 1, tid)],
-                             s2 = sW[SM::SW::at(k, ND + 2, tid)], dt = sDt[SM::SD::at(k, 0, tid)];
-                const StepPar sp = make_step(tau, e, s2, dt);
-                const bool has = (f & ROW_OBS) != 0, cut = (f & ROW_LAST) != 0;
-                StepAux<ND> ax;
-                fwd_step<ND, true>(sk, sp, y, mu, has, h, &ax);
-                const Adj<ND> gin = cut ? adj_zero<ND>() : g;
-                double g_h;
-                row_param_grad<ND>(gin, sp, ax, mu, tau, e, s2, dt, has, gp, gp[ND], gp[ND + 1], g_h);
-                gh += g_h;
-                g = bwd_apply<ND>(bwd_row_elem<ND>(sp, ax, has, cut), g);
             }
-            double* out = a.eta_bar + (size_t)(row0 + k) * NP;
+            // eta_bar of this row replaces its (consumed) forward state
 #pragma unroll
-            for (int j = 0; j < NP; ++j) out[j] = gp[j];
+            for (int j = 0; j < NP; ++j) sm.R[k][j][tid] = gp[j];
         }
-        const double tg = block_sum<NT>(gh, sMisc + 16);
+        // (5) grad_theta += X' eta_bar for this warp-tile
+        if (w.staged) scatter_warptile_staged<NP>(w, st.buf, gacc, [&](int k, int p) { return sm.R[k][p][tid]; });
+        else scatter_warptile<NP>(w, gacc, [&](int k, int p) { return sm.R[k][p][tid]; });
+        const double tg = block_sum<NT>(gh, sm.misc + 16);
         if (tid == 0) a.tile_gh[tile] = tg;
+    }
+    if (gacc.sgrad) {
+        __syncthreads();
+        for (int i = tid; i < a.p_theta; i += NT) {
+            const double v = sm.sgrad[i];
+            if (v != 0.0) atomicAdd(a.grad_theta + i, v);
+        }
     }
 }
 

@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -10,7 +11,8 @@
 
 #include "../../include/smoothsde_b200.h"
 #include "kernels_ctcrw.cuh"
-#include "kernels_linpred.cuh"
+#include "kernels_sde.cuh"
+#include "kernels_sim.cuh"
 
 using namespace ssde;
 
@@ -18,9 +20,11 @@ namespace {
 
 thread_local std::string g_create_error;
 
-constexpr int FWD_NT = 128, FWD_LC = 8;
-constexpr int BWD_NT = 64, BWD_LC = 8;
-static_assert(FWD_LC == BWD_LC, "checkpoints are per LC-row chunk");
+constexpr int FWD_NT = 128, FWD_MINB = 3;
+constexpr int BWD_NT = 128, BWD_MINB = 2;
+constexpr int PAD_ROWS = 1024;          // n_pad is a multiple of the largest tile (FWD_NT * LC)
+static_assert(PAD_ROWS % (FWD_NT * LC) == 0 && PAD_ROWS % (BWD_NT * LC) == 0 && PAD_ROWS % (SDE_NT * LC) == 0, "tiles must divide the padding unit");
+constexpr int RED_BLOCKS = 64;          // partial sums of the per-tile outputs
 
 #define CUDA_TRY(expr)                                                                       \
     do {                                                                                     \
@@ -45,7 +49,7 @@ struct ssde_handle {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int model = 0, n_dim = 0, n_par = 0;
-    int64_t n = 0, nnz = 0;
+    int64_t n = 0, n_pad = 0, nnz = 0;
     int n_tracks = 0;
     int p_fe = 0, p_re = 0, n_s = 0, npar = 0;
     int o_sig = -1, o_fe = 0, o_ll = 0, o_re = 0;
@@ -55,17 +59,18 @@ struct ssde_handle {
     int num_sms = 148;
     Sym2 P0{1.0, 0.0, 10.0};
     // design + data
-    DevBuf rowptr, cnt, col, val, obs, dt, flags, track_starts, a0;
+    DevBuf desc, col, val, obs, dt, flags, track_starts, a0;
     // penalty (CSR of S, per-smooth offsets, constants)
     DevBuf S_rowptr, S_col, S_val, sm_off;
     double pen_const = 0.0;
     // work buffers
-    DevBuf par, theta, grad_theta, W, eta_bar, ckpt, tile_llk, tile_gh, block_llk, out, sb;
+    DevBuf par, theta, grad_theta, ckpt, tile_llk, tile_gh, block_llk, part, out, sb;
     DevBuf f_status, f_agg, f_incl, b_status, b_agg, b_incl, counters;   // counters: ticket_f, ticket_b, error
     DevBuf aest;
     double* h_pinned = nullptr;      // pinned host staging: par in, out back
     unsigned epoch = 0;
     int ntiles_f = 0, ntiles_b = 0, grid_lp = 0, grid_f = 0, grid_b = 0;
+    int64_t ntiles_lp = 0;
     int64_t nchunks = 0;
     int last_launches = 0;
     bool timed = false;
@@ -144,6 +149,28 @@ __device__ double block_reduce_array(const double* x, int n, double* red) {
         __syncthreads();
     }
     return red[0];
+}
+
+// Fixed-shape partial sums of the per-tile outputs (deterministic: block b always sums the same
+// slice in the same order).  part[b] = sum of x[slice b], part[RED_BLOCKS + b] likewise for y.
+__global__ void __launch_bounds__(256) reduce_tiles_kernel(const double* __restrict__ x, int nx,
+                                                           const double* __restrict__ y, int ny,
+                                                           double* __restrict__ part) {
+    __shared__ double red[256];
+    const int b = blockIdx.x, nb = gridDim.x;
+    {
+        const int per = (nx + nb - 1) / nb;
+        const int lo = min(b * per, nx), hi = min(lo + per, nx);
+        const double s = block_reduce_array(x + lo, hi - lo, red);
+        if (threadIdx.x == 0) part[b] = s;
+    }
+    if (y) {
+        __syncthreads();
+        const int per = (ny + nb - 1) / nb;
+        const int lo = min(b * per, ny), hi = min(lo + per, ny);
+        const double s = block_reduce_array(y + lo, hi - lo, red);
+        if (threadIdx.x == 0) part[nb + b] = s;
+    }
 }
 
 __global__ void __launch_bounds__(256) finalize_kernel(FinArgs a) {
@@ -269,6 +296,98 @@ int pack_design(const ssde_desc& d, int n_par, Packed& out, std::string& err) {
     return SSDE_OK;
 }
 
+// Warp-tile transposed layout (design.cuh) from the row-major packed form.
+struct V2Host {
+    std::vector<WtDesc> desc;
+    std::vector<double> val;
+    std::vector<uint32_t> col;
+};
+
+int build_v2(const Packed& pk, int64_t n, int64_t n_pad, int n_par, V2Host& out, std::string& err) {
+    const int64_t nwt = n_pad / WT;
+    out.desc.assign(nwt, WtDesc{0, 0, 0u, WT_UNIFORM});
+    out.val.clear(); out.col.clear();
+    std::vector<uint32_t> prev_cols;         // column list of the previous uniform warp-tile
+    int64_t prev_col_off = -1;
+    std::vector<std::vector<uint32_t>> U(n_par);
+    for (int64_t q = 0; q < nwt; ++q) {
+        const int64_t r0 = q * WT, r1 = std::min<int64_t>(n, r0 + WT);
+        WtDesc& d = out.desc[q];
+        d.val_off = (int64_t)out.val.size();
+        d.col_off = 0;
+        if (r0 >= r1) continue;              // padding warp-tile: no slots
+        // union of columns and max count per parameter
+        uint32_t kmax_row[MAX_NP] = {0, 0, 0, 0};
+        for (int p = 0; p < n_par; ++p) U[p].clear();
+        for (int64_t r = r0; r < r1; ++r) {
+            uint32_t rp = pk.rowptr[r];
+            for (int p = 0; p < n_par; ++p) {
+                const uint32_t k = (pk.cnt[r] >> (8 * p)) & 255u;
+                kmax_row[p] = std::max(kmax_row[p], k);
+                for (uint32_t j = 0; j < k; ++j) U[p].push_back(pk.col[rp + j]);
+                rp += k;
+            }
+        }
+        size_t s_union = 0, s_max = 0;
+        bool fits = true;
+        for (int p = 0; p < n_par; ++p) {
+            std::sort(U[p].begin(), U[p].end());
+            U[p].erase(std::unique(U[p].begin(), U[p].end()), U[p].end());
+            s_union += U[p].size(); s_max += kmax_row[p];
+            if (U[p].size() > 255) fits = false;
+        }
+        const bool uniform = fits && s_union <= std::max(s_max + 4, 2 * s_max);
+        uint32_t kw = 0;
+        size_t S = 0;
+        for (int p = 0; p < n_par; ++p) {
+            const uint32_t k = uniform ? (uint32_t)U[p].size() : kmax_row[p];
+            kw |= k << (8 * p);
+            S += k;
+        }
+        d.kmax = kw;
+        d.flags = uniform ? WT_UNIFORM : 0u;
+        out.val.resize(out.val.size() + S * WT, 0.0);
+        double* v = out.val.data() + d.val_off;
+        uint32_t* c = nullptr;
+        if (uniform) {
+            std::vector<uint32_t> cols;
+            cols.reserve(S);
+            for (int p = 0; p < n_par; ++p) cols.insert(cols.end(), U[p].begin(), U[p].end());
+            if (prev_col_off >= 0 && cols == prev_cols) {
+                d.col_off = prev_col_off;
+            } else {
+                d.col_off = (int64_t)out.col.size();
+                out.col.insert(out.col.end(), cols.begin(), cols.end());
+                prev_cols = cols; prev_col_off = d.col_off;
+            }
+        } else {
+            d.col_off = (int64_t)out.col.size();
+            out.col.resize(out.col.size() + S * WT, 0u);
+            c = out.col.data() + d.col_off;
+        }
+        for (int64_t r = r0; r < r1; ++r) {
+            const int rr = (int)(r - r0), k = rr % LC, lane = rr / LC;
+            uint32_t rp = pk.rowptr[r];
+            size_t slot0 = 0;
+            for (int p = 0; p < n_par; ++p) {
+                const uint32_t cntp = (pk.cnt[r] >> (8 * p)) & 255u;
+                for (uint32_t j = 0; j < cntp; ++j) {
+                    size_t slot;
+                    if (uniform) slot = slot0 + (std::lower_bound(U[p].begin(), U[p].end(), pk.col[rp + j]) - U[p].begin());
+                    else slot = slot0 + j;
+                    v[((size_t)k * S + slot) * 32 + lane] = pk.val[rp + j];
+                    if (c) c[((size_t)k * S + slot) * 32 + lane] = pk.col[rp + j];
+                }
+                rp += cntp;
+                slot0 += (kw >> (8 * p)) & 255u;
+            }
+        }
+    }
+    if (out.col.empty()) out.col.push_back(0u);
+    (void)err;
+    return SSDE_OK;
+}
+
 // log det of a dense SPD block by Cholesky; NaN if not positive definite (the reference's
 // atomic::matinvpd gives garbage there too, nllk_sde.hpp:109-111)
 double logdet_spd(std::vector<double>& A, int m) {
@@ -373,11 +492,15 @@ template <int ND>
 int ctcrw_grids(ssde_handle* h) {
     std::string& err = h->err;
     int rc;
-    using SMF = CtcrwSmem<ND, FWD_NT, FWD_LC>;
-    using SMB = CtcrwSmem<ND, BWD_NT, BWD_LC>;
-    if ((rc = max_grid(ctcrw_fwd_kernel<ND, FWD_NT, FWD_LC>, FWD_NT, SMF::BYTES_FWD, h->num_sms, err, h->grid_f))) return rc;
-    if ((rc = max_grid(ctcrw_bwd_kernel<ND, BWD_NT, BWD_LC>, BWD_NT, SMB::BYTES_BWD, h->num_sms, err, h->grid_b))) return rc;
+    if ((rc = max_grid(ctcrw_fwd_kernel<ND, FWD_NT, FWD_MINB>, FWD_NT, sizeof(FwdSmem<ND, FWD_NT>), h->num_sms, err, h->grid_f))) return rc;
+    if ((rc = max_grid(ctcrw_bwd_kernel<ND, BWD_NT, BWD_MINB>, BWD_NT, sizeof(BwdSmem<ND, BWD_NT>), h->num_sms, err, h->grid_b))) return rc;
     return SSDE_OK;
+}
+
+template <int MODEL, int ND>
+int sde_grid(ssde_handle* h) {
+    constexpr int NP = (MODEL == MODEL_BM) ? ND + 1 : ND + 2;
+    return max_grid(sde_fused_kernel<MODEL, ND>, SDE_NT, sizeof(SdeSmem<NP>), h->num_sms, h->err, h->grid_lp);
 }
 
 // allocate the per-evaluation work buffers once the data are on the device
@@ -400,26 +523,16 @@ int finish_setup(ssde_handle* h) {
     if ((rc = dev_alloc<double>(h->theta, p, err))) return rc;
     if ((rc = dev_alloc<double>(h->grad_theta, p, err))) return rc;
     if ((rc = dev_alloc<double>(h->out, h->npar + 2, err))) return rc;
+    if ((rc = dev_alloc<double>(h->part, 2 * RED_BLOCKS, err))) return rc;
     if ((rc = dev_alloc<unsigned>(h->counters, 4, err))) return rc;
     CUDA_TRY(cudaMemset(h->counters.p, 0, 4 * sizeof(unsigned)));
     CUDA_TRY(cudaMallocHost(&h->h_pinned, sizeof(double) * (2 * (size_t)h->npar + 4)));
-    h->grid_lp = 4 * h->num_sms;
-    {
-        const int64_t nt = (h->n + LP_NT - 1) / LP_NT;
-        if (nt < h->grid_lp) h->grid_lp = (int)std::max<int64_t>(nt, 1);
-    }
     if (h->model == SSDE_CTCRW) {
         const int nd = h->n_dim;
-        const int64_t tile_f = (int64_t)FWD_NT * FWD_LC, tile_b = (int64_t)BWD_NT * BWD_LC;
-        h->ntiles_f = (int)((h->n + tile_f - 1) / tile_f);
-        h->ntiles_b = (int)((h->n + tile_b - 1) / tile_b);
-        h->nchunks = (h->n + FWD_LC - 1) / FWD_LC;
-        // chunk index = tile * NT + tid must stay inside the buffer for partially filled tiles
-        const int64_t nch_alloc = std::max<int64_t>((int64_t)h->ntiles_f * FWD_NT, (int64_t)h->ntiles_b * BWD_NT);
-        h->nchunks = nch_alloc;
-        if ((rc = dev_alloc<double>(h->W, (size_t)h->n * (nd + 3), err))) return rc;
-        if ((rc = dev_alloc<double>(h->eta_bar, (size_t)h->n * (nd + 2), err))) return rc;
-        if ((rc = dev_alloc<double>(h->ckpt, (size_t)nch_alloc * (2 * nd + 3), err))) return rc;
+        h->ntiles_f = (int)(h->n_pad / (FWD_NT * LC));
+        h->ntiles_b = (int)(h->n_pad / (BWD_NT * LC));
+        h->nchunks = h->n_pad / LC;
+        if ((rc = dev_alloc<double>(h->ckpt, (size_t)h->nchunks * (2 * nd + 3), err))) return rc;
         if ((rc = dev_alloc<double>(h->tile_llk, h->ntiles_f, err))) return rc;
         if ((rc = dev_alloc<double>(h->tile_gh, h->ntiles_b, err))) return rc;
         if ((rc = dev_alloc<unsigned>(h->f_status, h->ntiles_f, err))) return rc;
@@ -437,6 +550,16 @@ int finish_setup(ssde_handle* h) {
         h->grid_f = std::min(h->grid_f, std::max(h->ntiles_f, 1));
         h->grid_b = std::min(h->grid_b, std::max(h->ntiles_b, 1));
     } else {
+        h->ntiles_lp = h->n_pad / (SDE_NT * LC);
+        if (h->model == SSDE_BM) {
+            if (h->n_dim == 1) rc = sde_grid<MODEL_BM, 1>(h);
+            else if (h->n_dim == 2) rc = sde_grid<MODEL_BM, 2>(h);
+            else rc = sde_grid<MODEL_BM, 3>(h);
+        } else {
+            rc = (h->n_dim == 1) ? sde_grid<MODEL_OU, 1>(h) : sde_grid<MODEL_OU, 2>(h);
+        }
+        if (rc) return rc;
+        h->grid_lp = (int)std::max<int64_t>(1, std::min<int64_t>(h->grid_lp, h->ntiles_lp));
         if ((rc = dev_alloc<double>(h->block_llk, h->grid_lp, err))) return rc;
     }
     return SSDE_OK;
@@ -460,33 +583,38 @@ void mark(ssde_handle* h, cudaStream_t st, const char* name) {
     ++h->pcount;
 }
 
+DesignV2 design_of(const ssde_handle* h) {
+    return DesignV2{h->n, h->n_pad, h->desc.as<WtDesc>(), h->val.as<double>(), h->col.as<uint32_t>()};
+}
+
 template <int ND>
 int launch_ctcrw(ssde_handle* h, const double* d_par, int order, cudaStream_t st, double* aest) {
     std::string& err = h->err;
-    Design X{h->n, ND + 2, h->rowptr.as<uint32_t>(), h->cnt.as<uint32_t>(), h->col.as<uint32_t>(), h->val.as<double>()};
-    mark(h, st, "ctcrw_linpred");
-    ctcrw_linpred_kernel<ND><<<h->grid_lp, LP_NT, 0, st>>>(X, h->theta.as<double>(), h->dt.as<double>(), h->W.as<double>());
     CtcrwArgs<ND> a;
-    a.n = h->n;
-    a.W = h->W.as<double>(); a.obs = h->obs.as<double>(); a.dt = h->dt.as<double>(); a.flags = h->flags.as<uint8_t>();
+    a.X = design_of(h);
+    a.theta = h->theta.as<double>();
+    a.obs = h->obs.as<double>(); a.dt = h->dt.as<double>(); a.flags = h->flags.as<uint8_t>();
     a.track_starts = h->track_starts.as<int64_t>(); a.a0 = h->a0.as<double>(); a.n_tracks = h->n_tracks;
     a.P0 = h->P0; a.par = d_par; a.s_in = nullptr; a.g_in = nullptr;
     a.ckpt = h->ckpt.as<double>(); a.nchunks = h->nchunks;
-    a.tile_llk = h->tile_llk.as<double>(); a.tile_gh = h->tile_gh.as<double>(); a.eta_bar = h->eta_bar.as<double>();
+    a.tile_llk = h->tile_llk.as<double>(); a.tile_gh = h->tile_gh.as<double>();
+    a.grad_theta = h->grad_theta.as<double>(); a.p_theta = h->p_fe + h->p_re;
     a.aest = aest;
     unsigned* cnt = h->counters.as<unsigned>();
     a.fdesc = {h->f_status.as<unsigned>(), h->f_agg.as<double>(), h->f_incl.as<double>(), cnt + 0, cnt + 2, h->epoch};
     a.bdesc = {h->b_status.as<unsigned>(), h->b_agg.as<double>(), h->b_incl.as<double>(), cnt + 1, cnt + 2, h->epoch};
     a.ntiles = h->ntiles_f;
-    mark(h, st, "ctcrw_fwd_scan");
-    ctcrw_fwd_kernel<ND, FWD_NT, FWD_LC><<<h->grid_f, FWD_NT, CtcrwSmem<ND, FWD_NT, FWD_LC>::BYTES_FWD, st>>>(a);
+    mark(h, st, "ctcrw_fwd");
+    ctcrw_fwd_kernel<ND, FWD_NT, FWD_MINB><<<h->grid_f, FWD_NT, sizeof(FwdSmem<ND, FWD_NT>), st>>>(a);
     if (order >= 1) {
         a.ntiles = h->ntiles_b;
-        mark(h, st, "ctcrw_bwd_scan");
-        ctcrw_bwd_kernel<ND, BWD_NT, BWD_LC><<<h->grid_b, BWD_NT, CtcrwSmem<ND, BWD_NT, BWD_LC>::BYTES_BWD, st>>>(a);
-        mark(h, st, "linpred_T");
-        linpred_T_kernel<ND + 2><<<h->grid_lp, LP_NT, 0, st>>>(X, h->eta_bar.as<double>(), h->grad_theta.as<double>());
+        mark(h, st, "ctcrw_bwd");
+        ctcrw_bwd_kernel<ND, BWD_NT, BWD_MINB><<<h->grid_b, BWD_NT, sizeof(BwdSmem<ND, BWD_NT>), st>>>(a);
     }
+    mark(h, st, "reduce_tiles");
+    reduce_tiles_kernel<<<RED_BLOCKS, 256, 0, st>>>(h->tile_llk.as<double>(), h->ntiles_f,
+                                                     order >= 1 ? h->tile_gh.as<double>() : nullptr, h->ntiles_b,
+                                                     h->part.as<double>());
     CUDA_TRY(cudaGetLastError());
     return SSDE_OK;
 }
@@ -495,11 +623,16 @@ template <int MODEL, int ND>
 int launch_sde(ssde_handle* h, int order, cudaStream_t st) {
     std::string& err = h->err;
     constexpr int NP = (MODEL == MODEL_BM) ? ND + 1 : ND + 2;
-    Design X{h->n, NP, h->rowptr.as<uint32_t>(), h->cnt.as<uint32_t>(), h->col.as<uint32_t>(), h->val.as<double>()};
+    SdeArgs a;
+    a.X = design_of(h);
+    a.theta = h->theta.as<double>();
+    a.obs = h->obs.as<double>(); a.dt = h->dt.as<double>(); a.flags = h->flags.as<uint8_t>();
+    a.want_grad = order >= 1;
+    a.grad_theta = h->grad_theta.as<double>(); a.p_theta = h->p_fe + h->p_re;
+    a.block_llk = h->block_llk.as<double>();
+    a.ntiles = h->ntiles_lp;
     mark(h, st, "sde_fused");
-    sde_fused_kernel<MODEL, ND><<<h->grid_lp, LP_NT, 0, st>>>(X, h->theta.as<double>(), h->obs.as<double>(), h->dt.as<double>(),
-                                                             h->flags.as<uint8_t>(), order >= 1, h->grad_theta.as<double>(),
-                                                             h->block_llk.as<double>());
+    sde_fused_kernel<MODEL, ND><<<h->grid_lp, SDE_NT, sizeof(SdeSmem<NP>), st>>>(a);
     CUDA_TRY(cudaGetLastError());
     return SSDE_OK;
 }
@@ -520,8 +653,8 @@ int run_eval(ssde_handle* h, const double* d_par, int order, double* d_out, cuda
     FinArgs f{};
     if (h->model == SSDE_CTCRW) {
         rc = (h->n_dim == 1) ? launch_ctcrw<1>(h, d_par, order, st, aest) : launch_ctcrw<2>(h, d_par, order, st, aest);
-        f.part_llk = h->tile_llk.as<double>(); f.n_part = h->ntiles_f;
-        f.tile_gh = (order >= 1) ? h->tile_gh.as<double>() : nullptr; f.n_gh = h->ntiles_b;
+        f.part_llk = h->part.as<double>(); f.n_part = RED_BLOCKS;
+        f.tile_gh = (order >= 1) ? h->part.as<double>() + RED_BLOCKS : nullptr; f.n_gh = RED_BLOCKS;
     } else {
         if (h->model == SSDE_BM) {
             if (h->n_dim == 1) rc = launch_sde<MODEL_BM, 1>(h, order, st);
@@ -572,7 +705,7 @@ int check_common(int model, int n_dim, std::string& err) {
 // =============================================================================================
 extern "C" {
 
-const char* ssde_version(void) { return "smoothsde_b200 0.1 (sm_100a)"; }
+const char* ssde_version(void) { return "smoothsde_b200 0.2 (sm_100a)"; }
 const char* ssde_create_error(void) { return g_create_error.c_str(); }
 const char* ssde_last_error(const ssde_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
@@ -591,6 +724,47 @@ int ssde_par_layout(const ssde_handle* h, int32_t offsets[4], int32_t sizes[4]) 
     return SSDE_OK;
 }
 
+int64_t ssde_padded_rows(int64_t n) { return (n + PAD_ROWS - 1) / PAD_ROWS * PAD_ROWS; }
+int ssde_layout_info(int32_t info[4]) {
+    if (!info) return SSDE_ERR_BAD_ARG;
+    info[0] = LC; info[1] = WT; info[2] = PAD_ROWS; info[3] = (int32_t)sizeof(WtDesc);
+    return SSDE_OK;
+}
+
+// Host-only: the design of `d` in the device layout (no GPU needed).  Used by hosts that want to
+// build an ssde_packed_desc themselves and by the CPU tests of the layout.
+int ssde_pack_host(const ssde_desc* d, ssde_host_pack* out) {
+    std::string& err = g_create_error;
+    err.clear();
+    if (!d || !out) { err = "null argument"; return SSDE_ERR_BAD_ARG; }
+    std::memset(out, 0, sizeof(*out));
+    int rc = check_common(d->model, d->n_dim, err);
+    if (rc) return rc;
+    const int n_par = (d->model == SSDE_BM) ? d->n_dim + 1 : d->n_dim + 2;
+    if (d->n < 1 || d->X_fe.nrow != n_par * d->n || d->X_re.nrow != n_par * d->n) { err = "X_fe / X_re must have n_par * n rows"; return SSDE_ERR_BAD_ARG; }
+    Packed pk;
+    if ((rc = pack_design(*d, n_par, pk, err))) return rc;
+    V2Host v2;
+    const int64_t n_pad = ssde_padded_rows(d->n);
+    if ((rc = build_v2(pk, d->n, n_pad, n_par, v2, err))) return rc;
+    out->n_pad = n_pad;
+    out->n_desc = (int64_t)v2.desc.size(); out->n_val = (int64_t)v2.val.size(); out->n_col = (int64_t)v2.col.size();
+    out->desc = (ssde_wt_desc*)std::malloc(sizeof(WtDesc) * std::max<size_t>(v2.desc.size(), 1));
+    out->val = (double*)std::malloc(sizeof(double) * std::max<size_t>(v2.val.size(), 1));
+    out->col = (uint32_t*)std::malloc(sizeof(uint32_t) * std::max<size_t>(v2.col.size(), 1));
+    if (!out->desc || !out->val || !out->col) { ssde_pack_free(out); err = "out of memory"; return SSDE_ERR_BAD_ARG; }
+    std::memcpy(out->desc, v2.desc.data(), sizeof(WtDesc) * v2.desc.size());
+    std::memcpy(out->val, v2.val.data(), sizeof(double) * v2.val.size());
+    std::memcpy(out->col, v2.col.data(), sizeof(uint32_t) * v2.col.size());
+    return SSDE_OK;
+}
+
+void ssde_pack_free(ssde_host_pack* p) {
+    if (!p) return;
+    std::free(p->desc); std::free(p->val); std::free(p->col);
+    std::memset(p, 0, sizeof(*p));
+}
+
 int ssde_create(const ssde_desc* d, ssde_handle** out) {
     std::string& err = g_create_error;
     err.clear();
@@ -604,37 +778,47 @@ int ssde_create(const ssde_desc* d, ssde_handle** out) {
     if (n < 1 || !d->ID || !d->times || !d->obs) { err = "ID, times and obs are required"; return SSDE_ERR_BAD_ARG; }
     if (d->X_fe.nrow != n_par * n || d->X_re.nrow != n_par * n) { err = "X_fe / X_re must have n_par * n rows"; return SSDE_ERR_BAD_ARG; }
     if (d->H_array && d->H_len > 1) { err = "user-supplied H_array (coupled filter) is not built yet"; return SSDE_ERR_UNSUPPORTED; }
+    if (d->model != SSDE_CTCRW && (d->shard_flags & (SSDE_SHARD_CONT_PREV | SSDE_SHARD_CONT_NEXT))) {
+        err = "BM / OU shards must hold whole tracks (time-sharding exists for CTCRW only)";
+        return SSDE_ERR_UNSUPPORTED;
+    }
     if (cudaSetDevice(d->device) != cudaSuccess) { err = "cudaSetDevice failed: no usable CUDA device (there is no CPU fallback)"; return SSDE_ERR_CUDA; }
 
     ssde_handle* h = new (std::nothrow) ssde_handle();
     if (!h) { err = "out of memory"; return SSDE_ERR_BAD_ARG; }
     h->device = d->device; h->model = d->model; h->n_dim = nd; h->n_par = n_par; h->n = n;
+    h->n_pad = ssde_padded_rows(n);
     h->p_fe = (int)d->X_fe.ncol; h->p_re = (int)d->X_re.ncol;
     h->include_penalty = d->include_penalty; h->shard_flags = d->shard_flags;
     h->add_penalty = !(d->shard_flags & SSDE_SHARD_NO_PENALTY);
     auto fail = [&](int code) { err = h->err.empty() ? err : h->err; delete h; return code; };
 
-    // rows: flags, dt, obs (row-major), track starts
-    std::vector<uint8_t> flags(n, 0);
-    std::vector<double> dt(n, 1.0), obs((size_t)n * nd, 0.0);
+    // rows in the permuted order of design.cuh: flags, dt, obs planes; track starts
+    const int64_t n_pad = h->n_pad;
+    std::vector<uint8_t> flags(n_pad, 0xff);
+    std::vector<double> dt(n_pad, 1.0), obs((size_t)n_pad * nd, 0.0);
     std::vector<int64_t> starts;
     for (int64_t i = 0; i < n; ++i) {
+        const int64_t pos = row_pos(i);
         const bool start = (i == 0) ? !(d->shard_flags & SSDE_SHARD_CONT_PREV) : (d->ID[i] != d->ID[i - 1]);
         const bool last = (i == n - 1) ? !(d->shard_flags & SSDE_SHARD_CONT_NEXT) : (d->ID[i + 1] != d->ID[i]);
         uint8_t f = (start ? ROW_START : 0) | (last ? ROW_LAST : 0);
         for (int k = 0; k < nd; ++k) {
             const double y = d->obs[(size_t)k * n + i];
             if (std::isnan(y)) f |= (uint8_t)(ROW_NA0 << k);
-            else obs[(size_t)i * nd + k] = y;
+            else obs[(size_t)k * n_pad + pos] = y;
         }
-        if (!std::isnan(d->obs[i])) f |= ROW_OBS;             // column 0 only, nllk_ctcrw.hpp:214
-        if (d->model != SSDE_CTCRW) f &= (uint8_t)~ROW_OBS;
-        flags[i] = f;
+        if (d->model == SSDE_CTCRW) {
+            f &= (uint8_t)0x07;                                    // NA bits unused
+            if (!std::isnan(d->obs[i])) f |= ROW_OBS;              // column 0 only, nllk_ctcrw.hpp:214
+        }
+        flags[pos] = f;
+        if (!last) dt[pos] = ((i == n - 1) ? d->t_next : d->times[i + 1]) - d->times[i];
+        // CTCRW never uses the dt of a track-start row: it carries the track index instead
+        if (start && d->model == SSDE_CTCRW) dt[pos] = (double)starts.size();
         if (start) starts.push_back(i);
-        if (!last) dt[i] = ((i == n - 1) ? d->t_next : d->times[i + 1]) - d->times[i];
     }
     if (d->model == SSDE_CTCRW) {
-        for (int64_t i = 0; i < n; ++i) flags[i] &= (uint8_t)~(0xf8);      // NA bits unused
         if (!d->a0 || !d->P0) { err = "CTCRW needs a0 and P0"; return fail(SSDE_ERR_BAD_ARG); }
         if (d->n_ID != (int)starts.size()) { err = "nrow(a0) != number of tracks starting on this shard"; return fail(SSDE_ERR_BAD_ARG); }
         const int m = 2 * nd;
@@ -658,10 +842,11 @@ int ssde_create(const ssde_desc* d, ssde_handle** out) {
     Packed pk;
     if ((rc = pack_design(*d, n_par, pk, h->err))) return fail(rc);
     h->nnz = (int64_t)pk.col.size();
-    if ((rc = dev_upload(h->rowptr, pk.rowptr, h->err))) return fail(rc);
-    if ((rc = dev_upload(h->cnt, pk.cnt, h->err))) return fail(rc);
-    if ((rc = dev_upload(h->col, pk.col, h->err))) return fail(rc);
-    if ((rc = dev_upload(h->val, pk.val, h->err))) return fail(rc);
+    V2Host v2;
+    if ((rc = build_v2(pk, n, n_pad, n_par, v2, h->err))) return fail(rc);
+    if ((rc = dev_upload(h->desc, v2.desc, h->err))) return fail(rc);
+    if ((rc = dev_upload(h->col, v2.col, h->err))) return fail(rc);
+    if ((rc = dev_upload(h->val, v2.val, h->err))) return fail(rc);
     if ((rc = dev_upload(h->obs, obs, h->err))) return fail(rc);
     if ((rc = dev_upload(h->dt, dt, h->err))) return fail(rc);
     if ((rc = dev_upload(h->flags, flags, h->err))) return fail(rc);
@@ -681,14 +866,16 @@ int ssde_create_packed(const ssde_packed_desc* d, ssde_handle** out) {
     if (rc) return rc;
     const int n_par = (d->model == SSDE_BM) ? d->n_dim + 1 : d->n_dim + 2;
     if (d->n_par != n_par) { err = "n_par does not match model / n_dim"; return SSDE_ERR_BAD_ARG; }
+    if (d->n < 1 || d->n_pad != ssde_padded_rows(d->n)) { err = "n_pad must be ssde_padded_rows(n)"; return SSDE_ERR_BAD_ARG; }
+    if (!d->d_desc || !d->d_val || !d->d_col || !d->d_obs || !d->d_dt || !d->d_flags) { err = "null device array"; return SSDE_ERR_BAD_ARG; }
     if (cudaSetDevice(d->device) != cudaSuccess) { err = "cudaSetDevice failed: no usable CUDA device (there is no CPU fallback)"; return SSDE_ERR_CUDA; }
     ssde_handle* h = new (std::nothrow) ssde_handle();
     if (!h) { err = "out of memory"; return SSDE_ERR_BAD_ARG; }
     auto fail = [&](int code) { err = h->err.empty() ? err : h->err; delete h; return code; };
-    h->device = d->device; h->model = d->model; h->n_dim = d->n_dim; h->n_par = n_par; h->n = d->n; h->nnz = d->nnz;
+    h->device = d->device; h->model = d->model; h->n_dim = d->n_dim; h->n_par = n_par; h->n = d->n; h->n_pad = d->n_pad; h->nnz = d->nnz;
     h->p_fe = d->p_fe; h->p_re = d->p_re; h->include_penalty = d->include_penalty; h->shard_flags = d->shard_flags;
     h->add_penalty = !(d->shard_flags & SSDE_SHARD_NO_PENALTY);
-    h->rowptr.p = (void*)d->d_rowptr; h->cnt.p = (void*)d->d_cnt; h->col.p = (void*)d->d_col; h->val.p = (void*)d->d_val;
+    h->desc.p = (void*)d->d_desc; h->col.p = (void*)d->d_col; h->val.p = (void*)d->d_val;
     h->obs.p = (void*)d->d_obs; h->dt.p = (void*)d->d_dt; h->flags.p = (void*)d->d_flags;
     h->n_tracks = d->n_ID;
     h->P0 = {d->P0[0], d->P0[1], d->P0[2]};
@@ -722,7 +909,7 @@ int ssde_check(ssde_handle* h) {
     if (!h) return SSDE_ERR_BAD_ARG;
     std::string& err = h->err;
     CUDA_TRY(cudaSetDevice(h->device));
-    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaDeviceSynchronize());
     unsigned e = 0;
     CUDA_TRY(cudaMemcpy(&e, h->counters.as<unsigned>() + 2, sizeof(unsigned), cudaMemcpyDeviceToHost));
     if (e) { err = "device-side failure (scan look-back timed out)"; return SSDE_ERR_NUMERIC; }
@@ -761,7 +948,7 @@ int ssde_report(ssde_handle* h, double* aest_all) {
     if (h->model != SSDE_CTCRW) { err = "REPORT(aest_all) exists for CTCRW only"; return SSDE_ERR_UNSUPPORTED; }
     CUDA_TRY(cudaSetDevice(h->device));
     const int m = 2 * h->n_dim;
-    if (!h->aest.p) { int rc = dev_alloc<double>(h->aest, (size_t)h->n * m, err); if (rc) return rc; }
+    if (!h->aest.p) { int rc = dev_alloc<double>(h->aest, (size_t)h->n_pad * m, err); if (rc) return rc; }
     int rc = run_eval(h, h->par.as<double>(), 0, h->out.as<double>(), h->stream, h->aest.as<double>());
     if (rc) return rc;
     std::vector<double> tmp((size_t)h->n * m);
@@ -769,6 +956,20 @@ int ssde_report(ssde_handle* h, double* aest_all) {
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     for (int64_t i = 0; i < h->n; ++i)
         for (int c = 0; c < m; ++c) aest_all[(size_t)c * h->n + i] = tmp[(size_t)i * m + c];
+    return SSDE_OK;
+}
+
+int ssde_simulate_ctcrw(int device, int64_t n_tracks, int64_t n_steps, const double* d_times,
+                        const double* d_tau, const double* d_nu, const double* d_mu,
+                        const double* d_e1, const double* d_e2, double* d_z, void* stream) {
+    std::string& err = g_create_error;
+    err.clear();
+    if (n_tracks < 1 || n_steps < 1 || !d_times || !d_tau || !d_nu || !d_e1 || !d_e2 || !d_z) { err = "bad argument"; return SSDE_ERR_BAD_ARG; }
+    CUDA_TRY(cudaSetDevice(device));
+    const int nt = 32;
+    ctcrw_sim_kernel<<<(unsigned)((n_tracks + nt - 1) / nt), nt, 0, (cudaStream_t)stream>>>(
+        n_tracks, n_steps, d_times, d_tau, d_nu, d_mu, d_e1, d_e2, d_z);
+    CUDA_TRY(cudaGetLastError());
     return SSDE_OK;
 }
 
@@ -781,6 +982,13 @@ double ssde_last_eval_ms(ssde_handle* h) {
 }
 
 int ssde_last_eval_launches(const ssde_handle* h) { return h ? h->last_launches : 0; }
+
+int ssde_launch_info(const ssde_handle* h, int32_t info[8]) {
+    if (!h || !info) return SSDE_ERR_BAD_ARG;
+    info[0] = h->num_sms; info[1] = h->grid_f; info[2] = h->grid_b; info[3] = h->grid_lp;
+    info[4] = h->ntiles_f; info[5] = h->ntiles_b; info[6] = (int32_t)h->ntiles_lp; info[7] = h->n_tracks;
+    return SSDE_OK;
+}
 
 int ssde_set_profile(ssde_handle* h, int on) {
     if (!h) return SSDE_ERR_BAD_ARG;

@@ -39,40 +39,36 @@ def _bspline_torch(x, k, lo, hi):
     return B
 
 
-def simulate_ctcrw_torch(times, tau, nu, gen, seg_len=None):
-    """Exact-transition CTCRW simulation (R/sde.R:1448-1478) vectorised over tracks on the GPU.
-    times/tau/nu: [T, m].  Returns z [T, m] for one dimension (mu = 0)."""
+def simulate_ctcrw_device(times, tau, nu, gen, device):
+    """Exact-transition CTCRW simulation (R/sde.R:1448-1478), one thread per track, by the
+    library's own simulator kernel (ssde_simulate_ctcrw).  times/tau/nu: [T, m] contiguous.
+    Returns z [T, m] for one dimension (mu = 0, start at 0)."""
     import torch
     T, m = times.shape
-    dt = times[:, 1:] - times[:, :-1]
-    beta = 1.0 / tau[:, :-1]
-    sigma = 2.0 * nu[:, :-1] / torch.sqrt(math.pi * tau[:, :-1])
-    p = torch.exp(-beta * dt)
-    p2 = p * p
-    qvv = sigma ** 2 / (2 * beta) * (1 - p2)
-    qzz = (sigma / beta) ** 2 * (dt + (1 - p2) / (2 * beta) - 2 * (1 - p) / beta)
-    qvz = sigma ** 2 / (2 * beta ** 2) * (1 - 2 * p + p2)
-    l11 = torch.sqrt(qvv)
-    l21 = qvz / l11
-    l22 = torch.sqrt(torch.clamp(qzz - l21 * l21, min=0.0))
-    e1 = torch.randn((T, m - 1), dtype=torch.float64, device=times.device, generator=gen)
-    e2 = torch.randn((T, m - 1), dtype=torch.float64, device=times.device, generator=gen)
-    nv = l11 * e1                      # velocity noise
-    nz = l21 * e1 + l22 * e2           # position noise
-    cz = (1 - p) / beta                # position gain from velocity
-    del e1, e2, l11, l21, l22, qvv, qzz, qvz, sigma, beta, p2
-    # time-major copies so that the sequential loop reads contiguous [T] slices
-    p_t, nv_t, nz_t, cz_t = (a.t().contiguous() for a in (p, nv, nz, cz))
-    del p, nv, nz, cz
-    z = torch.empty((m, T), dtype=torch.float64, device=times.device)
-    v = torch.zeros(T, dtype=torch.float64, device=times.device)
-    zc = torch.zeros(T, dtype=torch.float64, device=times.device)
-    z[0] = zc
-    for i in range(1, m):
-        zc = zc + cz_t[i - 1] * v + nz_t[i - 1]
-        v = p_t[i - 1] * v + nv_t[i - 1]
-        z[i] = zc
-    return z.t().contiguous()
+    e1 = torch.randn((T, m), dtype=torch.float64, device=times.device, generator=gen)
+    e2 = torch.randn((T, m), dtype=torch.float64, device=times.device, generator=gen)
+    z = torch.zeros((T, m), dtype=torch.float64, device=times.device)
+    lib = L.load()
+    torch.cuda.synchronize(times.device)
+    rc = lib.ssde_simulate_ctcrw(device, T, m, times.data_ptr(), tau.data_ptr(), nu.data_ptr(), None,
+                                 e1.data_ptr(), e2.data_ptr(), z.data_ptr(), None)
+    if rc != 0:
+        raise L.EngineError(rc, lib.ssde_create_error().decode())
+    torch.cuda.synchronize(times.device)
+    return z
+
+
+def permute_rows(x, n_pad, lc, fill):
+    """[n, ...] natural row order -> [n_pad, ...] in the engine's warp-tile order
+    (row q*WT + l*LC + k  ->  position q*WT + k*32 + l)."""
+    import torch
+    n = x.shape[0]
+    if n_pad > n:
+        pad = torch.full((n_pad - n,) + tuple(x.shape[1:]), fill, dtype=x.dtype, device=x.device)
+        x = torch.cat([x, pad], dim=0)
+    rest = tuple(x.shape[1:])
+    x = x.reshape((n_pad // (32 * lc), 32, lc) + rest).transpose(1, 2)
+    return x.contiguous().reshape((n_pad,) + rest)
 
 
 def make_ctcrw_device(n_tracks, n_steps, seed=20260103, device=0, k=10, sigma_obs=0.1,
@@ -115,7 +111,7 @@ def make_ctcrw_device(n_tracks, n_steps, seed=20260103, device=0, k=10, sigma_ob
     del s
     obs = torch.empty((n, nd), dtype=torch.float64, device=dev)
     for d in range(nd):
-        z = simulate_ctcrw_torch(times, tau, nu, gen)
+        z = simulate_ctcrw_device(times.contiguous(), tau.contiguous(), nu.contiguous(), gen, device)
         if single:
             ends = z[:, -1]
             z = z + (torch.cumsum(ends, 0) - ends)[:, None]
@@ -141,6 +137,8 @@ def make_ctcrw_device(n_tracks, n_steps, seed=20260103, device=0, k=10, sigma_ob
         dt[first + (m - 1)] = 1.0
         track_starts = np.arange(0, n, m, dtype=np.int64)
         n_id = T
+    # CTCRW never uses the dt of a track-start row: it carries the track index (row of a0)
+    dt[torch.as_tensor(track_starts, device=dev)] = torch.arange(n_id, dtype=torch.float64, device=dev)
     a0 = np.zeros((n_id, 2 * nd))
     first_obs = obs[torch.as_tensor(track_starts, device=dev)].cpu().numpy()
     for d in range(nd):
@@ -166,30 +164,44 @@ def make_ctcrw_device(n_tracks, n_steps, seed=20260103, device=0, k=10, sigma_ob
     S1 = 0.5 * (S1 + S1.T)
     Zt = torch.as_tensor(Zc, device=dev)
     nnz_row = 2 + 2 * k            # 2 mu intercepts + 2 x (intercept + k-1 spline columns)
-    val = torch.empty((n, nnz_row), dtype=torch.float64, device=dev)
-    val[:, 0] = 1.0
-    val[:, 1] = 1.0
-    val[:, 2] = 1.0
-    val[:, 2 + k] = 1.0
+    info4 = (C.c_int32 * 4)()
+    L.load().ssde_layout_info(info4)
+    lc, wt = int(info4[0]), int(info4[1])
+    n_pad = int(L.load().ssde_padded_rows(n))
+    nq = n_pad // wt
+    # values: [n, nnz_row] natural -> [q][k][slot][lane]
+    val = torch.zeros((n_pad, nnz_row), dtype=torch.float64, device=dev)
+    val[:n, 0] = 1.0
+    val[:n, 1] = 1.0
+    val[:n, 2] = 1.0
+    val[:n, 2 + k] = 1.0
     for c0 in range(0, n, CH):
         Bz = _bspline_torch(tflat[c0:c0 + CH], k, lo, hi) @ Zt
-        val[c0:c0 + CH, 3:2 + k] = Bz
-        val[c0:c0 + CH, 3 + k:2 + 2 * k] = Bz
+        c1 = min(c0 + CH, n)
+        val[c0:c1, 3:2 + k] = Bz
+        val[c0:c1, 3 + k:2 + 2 * k] = Bz
         del Bz
+    val = val.reshape(nq, 32, lc, nnz_row).permute(0, 2, 3, 1).contiguous().reshape(-1)
     p_fe, p_re = nd + 2, 2 * (k - 1)
-    # theta = [coeff_fe (mu1, mu2, tau, nu intercepts) | coeff_re (tau spline, nu spline)]
+    # theta = [coeff_fe (mu1, mu2, tau, nu intercepts) | coeff_re (tau spline, nu spline)];
+    # every warp-tile uses the same 22 columns -> one shared column list
     pat = [0, 1, 2] + [p_fe + j for j in range(k - 1)] + [3] + [p_fe + (k - 1) + j for j in range(k - 1)]
-    col = torch.as_tensor(np.asarray(pat, dtype=np.int32), device=dev).repeat(n, 1).contiguous()
-    rowptr = (torch.arange(n + 1, dtype=torch.int64, device=dev) * nnz_row).to(torch.int32)
-    cntw = 1 | (1 << 8) | (k << 16) | (k << 24)
-    cnt = torch.full((n,), cntw, dtype=torch.int32, device=dev)
+    col = torch.as_tensor(np.asarray(pat, dtype=np.int32), device=dev)
+    kmax = 1 | (1 << 8) | (k << 16) | (k << 24)
+    desc = torch.empty((nq, 3), dtype=torch.int64, device=dev)
+    desc[:, 0] = torch.arange(nq, dtype=torch.int64, device=dev) * (wt * nnz_row)
+    desc[:, 1] = 0
+    desc[:, 2] = kmax | (1 << 32)                    # flags = WT_UNIFORM
+    obs_p = torch.stack([permute_rows(obs[:, d].contiguous(), n_pad, lc, 0.0) for d in range(nd)]).contiguous()
+    dt_p = permute_rows(dt, n_pad, lc, 1.0)
+    flags_p = permute_rows(flags, n_pad, lc, 255)
 
-    keep = [rowptr, cnt, col, val, obs, dt, flags]
+    keep = [desc, col, val, obs_p, dt_p, flags_p]
     pd = L.PackedDesc()
     pd.model, pd.n_dim, pd.n_par = L.SSDE_CTCRW, nd, nd + 2
-    pd.n, pd.nnz = n, n * nnz_row
-    pd.d_rowptr, pd.d_cnt, pd.d_col, pd.d_val = rowptr.data_ptr(), cnt.data_ptr(), col.data_ptr(), val.data_ptr()
-    pd.d_obs, pd.d_dt, pd.d_flags = obs.data_ptr(), dt.data_ptr(), flags.data_ptr()
+    pd.n, pd.n_pad, pd.nnz = n, n_pad, n * nnz_row
+    pd.d_desc, pd.d_col, pd.d_val = desc.data_ptr(), col.data_ptr(), val.data_ptr()
+    pd.d_obs, pd.d_dt, pd.d_flags = obs_p.data_ptr(), dt_p.data_ptr(), flags_p.data_ptr()
     pd.p_fe, pd.p_re = p_fe, p_re
     S = sp.block_diag([S1, S1], format="csr")
     pd.S = _as_triplet(S, keep)
@@ -213,7 +225,7 @@ def make_ctcrw_device(n_tracks, n_steps, seed=20260103, device=0, k=10, sigma_ob
     prng = np.random.default_rng(seed + 1)
     par = np.concatenate([[math.log(sigma_obs)], np.zeros(p_fe), np.zeros(2), 0.1 * prng.standard_normal(p_re)])
     info = {"n": n, "n_dim": nd, "nnz": n * nnz_row, "p_fe": p_fe, "p_re": p_re, "n_s": 2,
-            "n_par": nd + 2, "n_tracks": n_id, "tensors": dict(val=val, col=col, obs=obs, dt=dt, flags=flags, times=tflat),
+            "n_par": nd + 2, "n_tracks": n_id, "n_pad": n_pad, "tensors": dict(obs=obs, dt=dt, flags=flags, times=tflat),
             "S": S, "a0": a0, "track_starts": track_starts, "knots": (lo, hi), "Zc": Zc}
     return eng, par, info
 

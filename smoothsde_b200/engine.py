@@ -42,6 +42,69 @@ def model_code(type_):
     raise L.EngineError(1, "Unknown SDE type")          # src/smoothSDE.cpp:25
 
 
+def make_desc(dat, device=0, shard_flags=0, t_next=0.0):
+    """The reference's data list (R/sde.R:528-598) as an ``ssde_desc``; returns (desc, keep-alive)."""
+    keep = []
+    d = L.Desc()
+    d.model = model_code(dat["type"])
+    obs = np.asarray(dat["obs"], dtype=np.float64)
+    if obs.ndim == 1:
+        obs = obs[:, None]
+    n, nd = obs.shape
+    d.n_dim, d.n = nd, n
+    ID = np.ascontiguousarray(dat["ID"], dtype=np.float64)
+    times = np.ascontiguousarray(dat["times"], dtype=np.float64)
+    obs_cm = np.asfortranarray(obs)
+    keep += [ID, times, obs_cm]
+    d.ID = ID.ctypes.data_as(L.c_double_p)
+    d.times = times.ctypes.data_as(L.c_double_p)
+    d.obs = obs_cm.ctypes.data_as(L.c_double_p)
+    d.X_fe = _as_triplet(dat["X_fe"], keep)
+    d.X_re = _as_triplet(dat["X_re"], keep)
+    d.S = _as_triplet(dat.get("S"), keep)
+    ncol_re = np.ascontiguousarray(np.atleast_1d(dat["ncol_re"]), dtype=np.int32)
+    keep.append(ncol_re)
+    d.n_smooth = ncol_re.size
+    d.ncol_re = ncol_re.ctypes.data_as(L.c_int32_p)
+    d.include_penalty = int(dat.get("include_penalty", 1))
+    if dat["type"] == "CTCRW":
+        a0 = np.asfortranarray(np.asarray(dat["a0"], dtype=np.float64).reshape(-1, 2 * nd))
+        P0 = np.asfortranarray(np.asarray(dat["P0"], dtype=np.float64))
+        keep += [a0, P0]
+        d.n_ID = a0.shape[0]
+        d.a0 = a0.ctypes.data_as(L.c_double_p)
+        d.P0 = P0.ctypes.data_as(L.c_double_p)
+        H = dat.get("H_array")
+        if H is not None and np.size(H) > 1:
+            H = np.asfortranarray(np.asarray(H, dtype=np.float64))
+            keep.append(H)
+            d.H_array = H.ctypes.data_as(L.c_double_p)
+            d.H_len = H.size
+    d.device = device
+    d.shard_flags = shard_flags
+    d.t_next = float(t_next)
+    return d, keep
+
+
+def pack_host(dat):
+    """Design of `dat` in the device layout, packed on the host (no GPU needed).
+    Returns dict(n_pad, desc [structured array], val, col)."""
+    lib = L.load()
+    d, keep = make_desc(dat)
+    hp = L.HostPack()
+    rc = lib.ssde_pack_host(C.byref(d), C.byref(hp))
+    if rc != 0:
+        raise L.EngineError(rc, lib.ssde_create_error().decode())
+    try:
+        dt = np.dtype([("val_off", "<i8"), ("col_off", "<i8"), ("kmax", "<u4"), ("flags", "<u4")])
+        desc = np.frombuffer(C.string_at(hp.desc, hp.n_desc * 24), dtype=dt).copy()
+        val = np.ctypeslib.as_array(hp.val, shape=(max(hp.n_val, 1),))[:hp.n_val].copy()
+        col = np.ctypeslib.as_array(hp.col, shape=(max(hp.n_col, 1),))[:hp.n_col].copy()
+        return {"n_pad": int(hp.n_pad), "desc": desc, "val": val, "col": col}
+    finally:
+        lib.ssde_pack_free(C.byref(hp))
+
+
 class Engine:
     """One shard of one model on one GPU."""
 
@@ -62,45 +125,7 @@ class Engine:
     @classmethod
     def from_data(cls, dat, device=0, shard_flags=0, t_next=0.0):
         lib = L.load()
-        keep = []
-        d = L.Desc()
-        d.model = model_code(dat["type"])
-        obs = np.asarray(dat["obs"], dtype=np.float64)
-        if obs.ndim == 1:
-            obs = obs[:, None]
-        n, nd = obs.shape
-        d.n_dim, d.n = nd, n
-        ID = np.ascontiguousarray(dat["ID"], dtype=np.float64)
-        times = np.ascontiguousarray(dat["times"], dtype=np.float64)
-        obs_cm = np.asfortranarray(obs)
-        keep += [ID, times, obs_cm]
-        d.ID = ID.ctypes.data_as(L.c_double_p)
-        d.times = times.ctypes.data_as(L.c_double_p)
-        d.obs = obs_cm.ctypes.data_as(L.c_double_p)
-        d.X_fe = _as_triplet(dat["X_fe"], keep)
-        d.X_re = _as_triplet(dat["X_re"], keep)
-        d.S = _as_triplet(dat.get("S"), keep)
-        ncol_re = np.ascontiguousarray(np.atleast_1d(dat["ncol_re"]), dtype=np.int32)
-        keep.append(ncol_re)
-        d.n_smooth = ncol_re.size
-        d.ncol_re = ncol_re.ctypes.data_as(L.c_int32_p)
-        d.include_penalty = int(dat.get("include_penalty", 1))
-        if dat["type"] == "CTCRW":
-            a0 = np.asfortranarray(np.asarray(dat["a0"], dtype=np.float64).reshape(-1, 2 * nd))
-            P0 = np.asfortranarray(np.asarray(dat["P0"], dtype=np.float64))
-            keep += [a0, P0]
-            d.n_ID = a0.shape[0]
-            d.a0 = a0.ctypes.data_as(L.c_double_p)
-            d.P0 = P0.ctypes.data_as(L.c_double_p)
-            H = dat.get("H_array")
-            if H is not None and np.size(H) > 1:
-                H = np.asfortranarray(np.asarray(H, dtype=np.float64))
-                keep.append(H)
-                d.H_array = H.ctypes.data_as(L.c_double_p)
-                d.H_len = H.size
-        d.device = device
-        d.shard_flags = shard_flags
-        d.t_next = float(t_next)
+        d, keep = make_desc(dat, device, shard_flags, t_next)
         h = C.c_void_p()
         rc = lib.ssde_create(C.byref(d), C.byref(h))
         if rc != 0:
@@ -155,6 +180,12 @@ class Engine:
     @property
     def last_eval_launches(self):
         return self._lib.ssde_last_eval_launches(self._h)
+
+    def launch_info(self):
+        info = (C.c_int32 * 8)()
+        self._lib.ssde_launch_info(self._h, info)
+        keys = ("sms", "grid_fwd", "grid_bwd", "grid_sde", "tiles_fwd", "tiles_bwd", "tiles_sde", "tracks")
+        return dict(zip(keys, (int(x) for x in info)))
 
     def set_profile(self, on=True):
         self._lib.ssde_set_profile(self._h, int(bool(on)))

@@ -64,3 +64,102 @@ def test_report_aest_matches_oracle():
     last = np.r_[ID[1:] != ID[:-1], True]     # the reference predicts across tracks there (garbage)
     assert np.max(np.abs(aest[~last] - aest_ref[~last])) < 1e-9
     eng.close()
+
+
+@pytest.mark.parametrize("name", __import__("golden_util").names())
+def test_engine_reproduces_golden_fixtures(name):
+    import golden_util as G
+    dat, gold = G.load(name)
+    eng = Engine.from_data(dat)
+    v, g = eng.eval(gold["par"], order=1)
+    assert abs(v - gold["nllk"]) <= NLLK_RTOL * abs(gold["nllk"]), (v, gold["nllk"])
+    assert grad_err(g, gold["grad"]) <= GRAD_RTOL
+    eng.close()
+
+
+EDGE_CASES = [
+    ("CTCRW", 40, 3, 0.0, 2),        # many tiny tracks: several track starts inside one thread chunk
+    ("CTCRW", 1, 2, 0.0, 1),         # a single transition-free track (two rows)
+    ("CTCRW", 7, 301, 0.5, 2),       # half of the rows missing
+    ("CTCRW", 3, 1024, 0.02, 2),     # track boundaries exactly on tile boundaries
+    ("CTCRW", 1, 5000, 0.01, 2),     # one long track across several tiles of both kernels
+    ("OU", 30, 4, 0.2, 2),
+    ("BM", 1, 2, 0.0, 1),
+    ("BM", 2, 1300, 0.05, 3),
+]
+
+
+@pytest.mark.parametrize("model,T,m,miss,nd", EDGE_CASES)
+def test_edge_shapes_match_c_oracle(model, T, m, miss, nd):
+    from oracle import oracle_c
+    dat, par, info = synth.make_problem(model, T, m, missing_frac=miss, n_dim=nd, seed=1000 + T + m, k=5 if m < 20 else 10)
+    if model == "CTCRW":
+        par = par.copy()
+        par[1:1 + nd] = [0.3, -0.2][:nd]
+    ref_v, ref_g = oracle_c.COracle(dat).eval(par, True)
+    eng = Engine.from_data(dat)
+    v, g = eng.eval(par, order=1)
+    assert abs(v - ref_v) <= NLLK_RTOL * max(abs(ref_v), 1.0), (v, ref_v)
+    assert grad_err(g, ref_g) <= GRAD_RTOL
+    eng.close()
+
+
+def test_ragged_track_lengths_and_irregular_design():
+    """Tracks of different lengths and a design whose rows do not share their columns (the
+    per-nonzero column path of the layout)."""
+    import scipy.sparse as sp
+    from oracle import oracle_c
+    rng = np.random.default_rng(5)
+    lens = [3, 700, 41, 1, 260, 2]
+    dat, par, info = synth.make_problem("CTCRW", 1, sum(lens), missing_frac=0.1, n_dim=2, seed=31)
+    n = sum(lens)
+    ID = np.repeat(np.arange(len(lens)), lens).astype(float)
+    i0 = np.r_[0, np.cumsum(lens)[:-1]]
+    obs = dat["obs"].copy()
+    obs[i0] = np.nan_to_num(obs[i0])
+    a0 = np.zeros((len(lens), 4))
+    a0[:, 0], a0[:, 2] = obs[i0, 0], obs[i0, 1]
+    p_re = 40
+    Xre = sp.random(4 * n, p_re, density=0.04, random_state=9, format="csr") * 0.3
+    Xre = sp.vstack([sp.csr_matrix((2 * n, p_re)),
+                     sp.hstack([Xre[2 * n:3 * n, :20], sp.csr_matrix((n, 20))]),
+                     sp.hstack([sp.csr_matrix((n, 20)), Xre[3 * n:, 20:]])], format="csr")
+    dat = dict(dat, ID=ID, obs=obs, a0=a0, X_re=Xre, S=sp.identity(p_re, format="csr") * 2.0,
+               ncol_re=np.array([20, 20]))
+    par = np.r_[np.log(0.1), [0.1, -0.1, 0.0, 0.0], [0.3, -0.4], 0.2 * rng.standard_normal(p_re)]
+    ref_v, ref_g = oracle_c.COracle(dat).eval(par, True)
+    eng = Engine.from_data(dat)
+    v, g = eng.eval(par, order=1)
+    assert abs(v - ref_v) <= NLLK_RTOL * abs(ref_v), (v, ref_v)
+    assert grad_err(g, ref_g) <= GRAD_RTOL
+    eng.close()
+
+
+def test_device_built_problem_matches_host_built_problem():
+    """smoothsde_b200.devgen builds the packed layout with torch on the GPU (used by bench.py at
+    1e8 rows); the same rows passed through ssde_create must give the same objective."""
+    import scipy.sparse as sp
+    import torch
+    from smoothsde_b200 import design as D
+    from smoothsde_b200 import devgen
+    eng, par, info = devgen.make_ctcrw_device(5, 700, seed=3, device=0)
+    v, g = eng.eval(par, order=1)
+    n, k = info["n"], 10
+    t = info["tensors"]
+    times = t["times"].cpu().numpy()
+    lo, hi = info["knots"]
+    Bz = D.bspline_basis(times, k, lo, hi) @ info["Zc"]
+    one = sp.csr_matrix(np.ones((n, 1)))
+    X_fe = sp.block_diag([one, one, one, one], format="csr")
+    X_re = sp.block_diag([sp.csr_matrix((n, 0)), sp.csr_matrix((n, 0)), sp.csr_matrix(Bz), sp.csr_matrix(Bz)], format="csr")
+    dat = {"type": "CTCRW", "ID": np.repeat(np.arange(5), 700).astype(float), "times": times,
+           "obs": t["obs"].cpu().numpy(), "X_fe": X_fe, "X_re": X_re, "S": info["S"],
+           "ncol_re": np.array([9, 9]), "include_penalty": 1, "a0": info["a0"],
+           "P0": np.diag([1.0, 10.0, 1.0, 10.0])}
+    eng2 = Engine.from_data(dat)
+    v2, g2 = eng2.eval(par, order=1)
+    assert abs(v - v2) <= 1e-12 * abs(v2), (v, v2)
+    assert grad_err(g, g2) <= 1e-10
+    eng.close(); eng2.close()
+    del t
+    torch.cuda.empty_cache()
