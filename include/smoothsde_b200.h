@@ -125,6 +125,8 @@ typedef struct {
     double P0[3];                /* shared 2x2 block (p11, p12, p22) */
     int32_t device;
     int32_t shard_flags;
+    const int32_t* mu_cols;      /* CTCRW, optional (host): every column of theta that some mu_d predictor uses; */
+    int32_t n_mu_cols;           /* lets the kernels skip B*mu when all those entries are exactly 0.  NULL: unknown */
 } ssde_packed_desc;
 
 int64_t ssde_padded_rows(int64_t n);

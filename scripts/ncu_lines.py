@@ -16,13 +16,10 @@ import tempfile
 from collections import defaultdict
 
 
-def main():
-    rep, kre, lib = sys.argv[1:4]
-    rows = float(sys.argv[4]) if len(sys.argv) > 4 else None
+def _collect(rep, kre, lib):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass",
                           "--kernel-name", "regex:" + kre], capture_output=True, text=True).stdout
     lines = raw.splitlines()
-    # first kernel block only
     start = next(i for i, l in enumerate(lines) if l.startswith('"Address"'))
     end = next((i for i in range(start + 1, len(lines)) if lines[i].startswith('"Kernel Name"')), len(lines))
     kname = lines[start - 1]
@@ -30,14 +27,12 @@ def main():
     hdr = rd[0]
     ix = {h: i for i, h in enumerate(hdr)}
     sass = rd[1:]
-    mangled = None
     tmp = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, capture_output=True)
     cubin = [os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")][0]
     dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout.splitlines()
-    # find the function whose instruction count matches
     funcs = {}
-    cur, curline, inl = None, None, []
+    cur, curline = None, None
     for l in dis:
         m = re.match(r"\s*\.section\s+\.text\.(\S+),", l)
         if m:
@@ -55,20 +50,32 @@ def main():
     if not cands:
         cands = [f for f, v in funcs.items() if len(v) == len(sass)]
     if not cands:
-        print("no function with", len(sass), "instructions; candidates:", {f: len(v) for f, v in funcs.items() if re.search(kre, f)})
-        return
+        raise SystemExit(f"no function with {len(sass)} instructions in {lib} (library rebuilt since the capture?); "
+                         f"candidates: { {f: len(v) for f, v in funcs.items() if re.search(kre, f)} }")
     lineinfo = funcs[cands[0]]
-    inst = defaultdict(float)
-    stall = defaultdict(float)
-    longsb = defaultdict(float)
+    inst, stall, longsb = defaultdict(float), defaultdict(float), defaultdict(float)
     for k, r in enumerate(sass):
         key = lineinfo[k]
         inst[key] += float(r[ix["Instructions Executed"]] or 0)
         stall[key] += float(r[ix["Warp Stall Sampling (All Samples)"]] or 0)
         longsb[key] += float(r[ix["stall_long_sb"]] or 0)
+    return inst, stall, longsb, kname
+
+
+def collect(rep, kre, lib):
+    """-> (instructions executed, stall samples) keyed by (file, line)."""
+    r = _collect(rep, kre, lib)
+    return r[0], r[1]
+
+
+def main():
+    rep, kre, lib = sys.argv[1:4]
+    rows = float(sys.argv[4]) if len(sys.argv) > 4 else None
+    inst, stall, longsb, kname = _collect(rep, kre, lib)
     tot_i, tot_s = sum(inst.values()), sum(stall.values())
     print(kname[:120])
-    print(f"total warp instructions {tot_i:.0f}" + (f" = {tot_i * 32 / rows:.0f} thread-instr/row" if rows else "") + f", stall samples {tot_s:.0f}")
+    print(f"total warp instructions {tot_i:.0f}" + (f" = {tot_i * 32 / rows:.0f} thread-instr/row" if rows else "")
+          + f", stall samples {tot_s:.0f}")
     print("top lines by stall samples:")
     for key, v in sorted(stall.items(), key=lambda kv: -kv[1])[:25]:
         print(f"  {str(key):40s} stalls {100 * v / tot_s:5.1f}% (long_sb {100 * longsb[key] / tot_s:5.1f}%)  instr {100 * inst[key] / tot_i:5.1f}%")

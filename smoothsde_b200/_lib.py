@@ -48,7 +48,8 @@ class PackedDesc(C.Structure):
                 ("p_fe", C.c_int32), ("p_re", C.c_int32), ("S", Triplet),
                 ("n_smooth", C.c_int32), ("ncol_re", c_int32_p), ("include_penalty", C.c_int32),
                 ("n_ID", C.c_int32), ("track_starts", c_int64_p), ("a0", c_double_p),
-                ("P0", C.c_double * 3), ("device", C.c_int32), ("shard_flags", C.c_int32)]
+                ("P0", C.c_double * 3), ("device", C.c_int32), ("shard_flags", C.c_int32),
+                ("mu_cols", c_int32_p), ("n_mu_cols", C.c_int32)]
 
 
 class HostPack(C.Structure):

@@ -199,18 +199,18 @@ __device__ __forceinline__ void st_status(unsigned* p, unsigned v) {
 template <class Ops>
 __device__ __forceinline__ void publish_agg(const ScanDesc& d, int t, const typename Ops::Elem& e) {
     store_elem(d.agg + (size_t)t * Ops::Elem::NDBL, e);
-    __threadfence();
-    st_status(d.status + t, (d.epoch << 2) | 1u);
+    st_status(d.status + t, (d.epoch << 2) | 1u);          // release: orders the element stores before it
 }
 template <class Ops>
 __device__ __forceinline__ void publish_incl(const ScanDesc& d, int t, const typename Ops::Elem& e) {
     store_elem(d.incl + (size_t)t * Ops::Elem::NDBL, e);
-    __threadfence();
     st_status(d.status + t, (d.epoch << 2) | 2u);
 }
 
 // Executed by one full warp.  Returns (in every lane) the composite of all tiles processed
-// before ticket `t` (identity for t == 0).
+// before ticket `t` (identity for t == 0).  Lane l inspects tile base - l; the window is consumed
+// as soon as every tile up to the nearest one that already knows its inclusive prefix has at
+// least published its aggregate -- tiles farther away are never waited for.
 template <class Ops>
 __device__ __forceinline__ typename Ops::Elem lookback(const ScanDesc& d, int t) {
     using Elem = typename Ops::Elem;
@@ -219,24 +219,25 @@ __device__ __forceinline__ typename Ops::Elem lookback(const ScanDesc& d, int t)
     int base = t - 1;
     while (base >= 0) {
         const int idx = base - lane;
-        unsigned st = 2u;                                  // virtual tile -1: identity prefix
         unsigned spins = 0;
+        int first;                                         // nearest lane holding an inclusive prefix
         while (true) {
-            bool ready = true;
+            unsigned code = 2u;                            // virtual tile -1: identity prefix
             if (idx >= 0) {
-                st = ld_status(d.status + idx);
-                ready = (st >> 2) == d.epoch;
+                const unsigned st = ld_status(d.status + idx);
+                code = ((st >> 2) == d.epoch) ? (st & 3u) : 0u;
             }
-            if (__all_sync(FULL, ready)) break;
+            const unsigned incl = __ballot_sync(FULL, code == 2u);
+            const unsigned none = __ballot_sync(FULL, code == 0u);
+            first = incl ? (__ffs(incl) - 1) : 32;
+            const unsigned need = (first >= 31) ? FULL : ((2u << first) - 1u);
+            if ((none & need) == 0u) break;
             if (++spins > (1u << 22)) {                    // ~seconds: give up instead of hanging
                 if (lane == 0) atomicExch(d.error, 1u);
                 return acc;
             }
-            __nanosleep(40);
+            __nanosleep(20);
         }
-        const unsigned code = (idx >= 0) ? (st & 3u) : 2u;
-        const unsigned pmask = __ballot_sync(FULL, code == 2u);
-        const int first = pmask ? (__ffs(pmask) - 1) : 32;
         Elem e = Ops::identity();
         if (idx >= 0) {
             if (lane < first) e = load_elem_cg<Elem>(d.agg + (size_t)idx * Elem::NDBL);
@@ -251,7 +252,7 @@ __device__ __forceinline__ typename Ops::Elem lookback(const ScanDesc& d, int t)
         }
         e = shfl_idx_elem(e, 0);
         acc = Ops::join(e, acc);
-        if (pmask) break;
+        if (first < 32) break;
         base -= 32;
     }
     return acc;

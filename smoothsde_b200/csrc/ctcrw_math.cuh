@@ -87,8 +87,9 @@ SSDE_HD void transform_row(double eta_tau, double eta_nu, double dt, double& tau
                            double& s2) {
     tau = exp(eta_tau);
     const double nu = exp(eta_nu);
-    s2 = (4.0 / 3.14159265358979323846) * nu * nu / tau;
-    e = exp(-dt / tau);
+    const double itau = 1.0 / tau;
+    s2 = (4.0 / 3.14159265358979323846) * nu * nu * itau;
+    e = exp(-dt * itau);
 }
 
 // ---------------------------------------------------------------------------------------------

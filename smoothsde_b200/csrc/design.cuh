@@ -67,6 +67,7 @@ struct WtView {
     const double* v;               // val + val_off + lane
     const uint32_t* c;             // col + col_off (+ lane if not uniform)
     const double* th;              // per-warp theta cache (shared memory) or nullptr
+    int th_pad;                    // 16: parameter p's cached thetas start at th[16 p]; 0: contiguous
     uint32_t kmax;
     int S;
     bool uniform;
@@ -99,13 +100,30 @@ __device__ __forceinline__ WtView open_warptile(const DesignV2& X, int64_t q, co
     w.v = w.blk + lane;
     w.c = X.col + d.col_off + (w.uniform ? 0 : lane);
     w.th = nullptr;
-    if (w.uniform && w.S <= TH_CACHE) {
+    w.th_pad = 0;
+    // every parameter has at most 16 slots -> 16-aligned per-parameter segments (vector loads)
+    bool le16 = true;
+#pragma unroll
+    for (int p = 0; p < MAX_NP; ++p) le16 = le16 && (((d.kmax >> (8 * p)) & 255u) <= 16u);
+    if (w.uniform && w.S > 0 && w.S <= STAGE_SLOTS && le16) {
+        __syncwarp();
+        int j0 = 0;
+#pragma unroll
+        for (int p = 0; p < MAX_NP; ++p) {
+            const int kp = (int)((d.kmax >> (8 * p)) & 255u);
+            if (lane < kp) th_cache[16 * p + lane] = __ldg(theta + __ldg(w.c + j0 + lane));
+            j0 += kp;
+        }
+        __syncwarp();
+        w.th = th_cache;
+        w.th_pad = 16;
+    } else if (w.uniform && w.S <= TH_CACHE) {
         __syncwarp();
         for (int j = lane; j < w.S; j += 32) th_cache[j] = __ldg(theta + __ldg(w.c + j));
         __syncwarp();
         w.th = th_cache;
     }
-    w.staged = w.th != nullptr && w.S > 0 && w.S <= STAGE_SLOTS;
+    w.staged = w.th_pad != 0;
     return w;
 }
 
@@ -126,14 +144,30 @@ __device__ __forceinline__ void stage_wait(WarpStage& st) {
 template <int NP>
 __device__ __forceinline__ void row_eta_staged(const WtView& w, const WarpStage& st, double* eta) {
     const double* v = st.buf + (threadIdx.x & 31);
-    const double* th = w.th;
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
         const int kp = (int)((w.kmax >> (8 * p)) & 255u);
-        double acc = 0.0;
-#pragma unroll 2
-        for (int i = 0; i < kp; ++i) { acc = fma(v[0], th[0], acc); v += 32; ++th; }
-        eta[p] = acc;
+        const double* th = w.th + 16 * p;
+        double acc0 = 0.0, acc1 = 0.0;
+        int i = 0;
+#pragma unroll 1
+        for (; i + 4 <= kp; i += 4) {
+            const double2 ta = *reinterpret_cast<const double2*>(th + i);
+            const double2 tb = *reinterpret_cast<const double2*>(th + i + 2);
+            acc0 = fma(v[0], ta.x, acc0);
+            acc1 = fma(v[32], ta.y, acc1);
+            acc0 = fma(v[64], tb.x, acc0);
+            acc1 = fma(v[96], tb.y, acc1);
+            v += 128;
+        }
+        if (kp - i >= 2) {
+            const double2 ta = *reinterpret_cast<const double2*>(th + i);
+            acc0 = fma(v[0], ta.x, acc0);
+            acc1 = fma(v[32], ta.y, acc1);
+            v += 64; i += 2;
+        }
+        if (i < kp) { acc0 = fma(v[0], th[i], acc0); v += 32; }
+        eta[p] = acc0 + acc1;
     }
 }
 
@@ -149,7 +183,7 @@ __device__ __forceinline__ void row_eta_prefix(const WtView& w, int k, const dou
         const int kp = (int)((w.kmax >> (8 * p)) & 255u);
         double acc = 0.0;
         for (int i = 0; i < kp; ++i, ++j) {
-            const double t = w.th ? w.th[j] : __ldg(theta + __ldg(c + j * cs));
+            const double t = w.th ? w.th[w.th_pad ? 16 * p + i : j] : __ldg(theta + __ldg(c + j * cs));
             acc = fma(__ldg(v + j * 32), t, acc);
         }
         eta[p] = acc;
@@ -167,7 +201,7 @@ __device__ __forceinline__ void row_eta(const WtView& w, int k, const double* __
             const int kp = (int)((w.kmax >> (8 * p)) & 255u);
             double acc = 0.0;
 #pragma unroll 4
-            for (int i = 0; i < kp; ++i, ++j) acc = fma(__ldg(v + j * 32), w.th[j], acc);
+            for (int i = 0; i < kp; ++i, ++j) acc = fma(__ldg(v + j * 32), w.th[w.th_pad ? 16 * p + i : j], acc);
             eta[p] = acc;
         }
     } else {

@@ -34,6 +34,7 @@ struct CtcrwArgs {
     const double* par;         // device parameter vector; par[0] = log_sigma_obs
     const double* s_in;        // optional incoming state (2*ND + 3 doubles) for a continued shard
     const double* g_in;        // optional incoming adjoint (2*ND + 3 doubles)
+    const int* mu_zero;        // device flag: every mu_d predictor is exactly 0 at these parameters
     double* ckpt;              // [(2*ND+3), nchunks] start state of every thread chunk
     int64_t nchunks;           // n_pad / LC
     double* tile_llk;          // [ntiles_f]
@@ -83,6 +84,7 @@ struct FwdSmem {
     double W[LC][NC][NT];
     double stage[NT / 32][STAGE_DBL];
     double wagg[NT / 32][24];
+    double tagg[24];
     double misc[32];
     double th[NT / 32][TH_CACHE];
     uint64_t bar[NT / 32];
@@ -102,6 +104,7 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(CtcrwArgs<ND> a) {
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double h = exp(2.0 * a.par[0]);               // H = sigma_obs^2 I, nllk_ctcrw.hpp:136,167
+    const bool mu0 = *a.mu_zero != 0;
     WarpStage st;
     stage_init(st, sm.stage[warp], &sm.bar[warp]);
     mbar_fence_init();
@@ -153,7 +156,7 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(CtcrwArgs<ND> a) {
         }
         // (2) warp inclusive scan (lower lanes = earlier rows)
         Elem inc = E;
-#pragma unroll
+#pragma unroll 1
         for (int o = 1; o < 32; o <<= 1) {
             Elem f = shfl_up_elem(inc, o);
             if (lane >= o) inc = fwd_combine<ND>(f, inc);
@@ -162,28 +165,31 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(CtcrwArgs<ND> a) {
         Elem exc = shfl_up_elem(inc, 1);
         if (lane == 0) exc = fwd_identity<ND>();
         __syncthreads();
-        // (3) tile aggregate, chained look-back (warp 0), tile start state
-        if (warp == 0) {
+        // (3) the last warp composes and publishes the tile aggregate while warp 0 looks back over
+        //     the earlier tiles; warp 0 then publishes the inclusive prefix and the tile start state
+        if (warp == NWARP - 1) {
             Elem tagg = load_elem<Elem>(sm.wagg[0]);
-#pragma unroll
+#pragma unroll 1
             for (int ww = 1; ww < NWARP; ++ww) tagg = fwd_combine<ND>(tagg, load_elem<Elem>(sm.wagg[ww]));
-            if (lane == 0) publish_agg<Ops>(a.fdesc, tile, tagg);
-            const Elem pre = lookback<Ops>(a.fdesc, tile);
-            if (lane == 0) {
-                publish_incl<Ops>(a.fdesc, tile, fwd_combine<ND>(pre, tagg));
-                // state at the first row of the tile
-                State<ND> s0;
-                if (a.s_in) s0 = load_state<ND>(a.s_in);
-                else { s0.P = a.P0;
+            if (lane == 0) { publish_agg<Ops>(a.fdesc, tile, tagg); store_elem(sm.tagg, tagg); }
+        }
+        Elem pre;
+        if (warp == 0) pre = lookback<Ops>(a.fdesc, tile);
+        __syncthreads();
+        if (warp == 0 && lane == 0) {
+            // state at the first row of the tile
+            State<ND> s0;
+            if (a.s_in) s0 = load_state<ND>(a.s_in);
+            else { s0.P = a.P0;
 #pragma unroll
-                    for (int d = 0; d < ND; ++d) s0.a[d] = {0.0, 0.0}; }
-                const State<ND> st0 = fwd_apply<ND>(pre, s0);
+                for (int d = 0; d < ND; ++d) s0.a[d] = {0.0, 0.0}; }
+            const State<ND> st0 = fwd_apply<ND>(pre, s0);
 #pragma unroll
-                for (int d = 0; d < ND; ++d) { sm.misc[2 * d] = st0.a[d].x; sm.misc[2 * d + 1] = st0.a[d].y; }
-                sm.misc[2 * ND] = st0.P.a; sm.misc[2 * ND + 1] = st0.P.b; sm.misc[2 * ND + 2] = st0.P.c;
-            }
+            for (int d = 0; d < ND; ++d) { sm.misc[2 * d] = st0.a[d].x; sm.misc[2 * d + 1] = st0.a[d].y; }
+            sm.misc[2 * ND] = st0.P.a; sm.misc[2 * ND + 1] = st0.P.b; sm.misc[2 * ND + 2] = st0.P.c;
         }
         __syncthreads();
+        if (warp == 0 && lane == 0) publish_incl<Ops>(a.fdesc, tile, fwd_combine<ND>(pre, load_elem<Elem>(sm.tagg)));
         // (4) exact start state of this thread, checkpoint, plain filter re-run
         State<ND> s = load_state<ND>(sm.misc);
 #pragma unroll 1
@@ -213,7 +219,9 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(CtcrwArgs<ND> a) {
                 s = track_start_state<ND>(a, dtv);
             } else {
                 double mu[ND], y[ND];
-                row_eta_prefix<ND>(w, k, a.theta, mu);
+#pragma unroll
+                for (int d = 0; d < ND; ++d) mu[d] = 0.0;
+                if (!mu0) row_eta_prefix<ND>(w, k, a.theta, mu);
 #pragma unroll
                 for (int d = 0; d < ND; ++d) y[d] = a.obs[(size_t)d * a.X.n_pad + pos];
                 StepPar sp;
@@ -259,6 +267,7 @@ struct BwdSmem {
     double R[LC][NC][NT];
     double stage[NT / 32][STAGE_DBL];
     double wagg[NT / 32][16];
+    double tagg[16];
     double misc[32];
     double th[NT / 32][TH_CACHE];
     double sgrad[SGRAD];
@@ -281,6 +290,7 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_bwd_kernel(CtcrwArgs<ND> a) {
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double h = exp(2.0 * a.par[0]);
+    const bool mu0 = *a.mu_zero != 0;
     GradAcc gacc{(a.p_theta <= SGRAD) ? sm.sgrad : nullptr, a.grad_theta};
     if (gacc.sgrad) for (int i = tid; i < SGRAD; i += NT) sm.sgrad[i] = 0.0;
     WarpStage st;
@@ -357,7 +367,7 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_bwd_kernel(CtcrwArgs<ND> a) {
         }
         // (2) warp inclusive SUFFIX scan (higher lanes = later rows)
         Elem inc = E;
-#pragma unroll
+#pragma unroll 1
         for (int o = 1; o < 32; o <<= 1) {
             Elem f = shfl_down_elem(inc, o);
             if (lane + o < 32) inc = bwd_combine<ND>(inc, f);
@@ -366,23 +376,27 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_bwd_kernel(CtcrwArgs<ND> a) {
         Elem exc = shfl_down_elem(inc, 1);
         if (lane == 31) exc = bwd_identity<ND>();
         __syncthreads();
-        // (3) tile aggregate, chained look-back over LATER tiles, adjoint entering the tile end
-        if (warp == 0) {
+        // (3) the last warp composes and publishes the tile aggregate while warp 0 looks back over
+        //     the LATER tiles; warp 0 then publishes the inclusive suffix and the adjoint entering
+        //     the tile end
+        if (warp == NWARP - 1) {
             Elem tagg = load_elem<Elem>(sm.wagg[NWARP - 1]);
-#pragma unroll
+#pragma unroll 1
             for (int ww = NWARP - 2; ww >= 0; --ww) tagg = bwd_combine<ND>(load_elem<Elem>(sm.wagg[ww]), tagg);
-            if (lane == 0) publish_agg<Ops>(a.bdesc, ticket, tagg);
-            const Elem suf = lookback<Ops>(a.bdesc, ticket);
-            if (lane == 0) {
-                publish_incl<Ops>(a.bdesc, ticket, bwd_combine<ND>(tagg, suf));
-                Adj<ND> g0 = a.g_in ? load_adj<ND>(a.g_in) : adj_zero<ND>();
-                const Adj<ND> gt = bwd_apply<ND>(suf, g0);
+            if (lane == 0) { publish_agg<Ops>(a.bdesc, ticket, tagg); store_elem(sm.tagg, tagg); }
+        }
+        Elem suf;
+        if (warp == 0) suf = lookback<Ops>(a.bdesc, ticket);
+        __syncthreads();
+        if (warp == 0 && lane == 0) {
+            Adj<ND> g0 = a.g_in ? load_adj<ND>(a.g_in) : adj_zero<ND>();
+            const Adj<ND> gt = bwd_apply<ND>(suf, g0);
 #pragma unroll
-                for (int d = 0; d < ND; ++d) { sm.misc[2 * d] = gt.a[d].x; sm.misc[2 * d + 1] = gt.a[d].y; }
-                sm.misc[2 * ND] = gt.P.a; sm.misc[2 * ND + 1] = gt.P.b; sm.misc[2 * ND + 2] = gt.P.c;
-            }
+            for (int d = 0; d < ND; ++d) { sm.misc[2 * d] = gt.a[d].x; sm.misc[2 * d + 1] = gt.a[d].y; }
+            sm.misc[2 * ND] = gt.P.a; sm.misc[2 * ND + 1] = gt.P.b; sm.misc[2 * ND + 2] = gt.P.c;
         }
         __syncthreads();
+        if (warp == 0 && lane == 0) publish_incl<Ops>(a.bdesc, ticket, bwd_combine<ND>(load_elem<Elem>(sm.tagg), suf));
         // (4) adjoint entering this thread's last row, then the reverse sweep over its rows
         Adj<ND> g = load_adj<ND>(sm.misc);
 #pragma unroll 1
@@ -402,7 +416,9 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_bwd_kernel(CtcrwArgs<ND> a) {
                     const int64_t pos = base + k * 32;
                     const double dtv = a.dt[pos];
                     double mu[ND], y[ND];
-                    row_eta_prefix<ND>(w, k, a.theta, mu);
+#pragma unroll
+                    for (int d = 0; d < ND; ++d) mu[d] = 0.0;
+                    if (!mu0) row_eta_prefix<ND>(w, k, a.theta, mu);
 #pragma unroll
                     for (int d = 0; d < ND; ++d) y[d] = a.obs[(size_t)d * a.X.n_pad + pos];
                     State<ND> sk;

@@ -60,6 +60,8 @@ struct ssde_handle {
     Sym2 P0{1.0, 0.0, 10.0};
     // design + data
     DevBuf desc, col, val, obs, dt, flags, track_starts, a0;
+    DevBuf mu_cols, mu_zero;         // theta entries that feed the mu_d predictors; device flag "all of them are 0"
+    int n_mu_cols = -1;              // -1: unknown (flag stays 0)
     // penalty (CSR of S, per-smooth offsets, constants)
     DevBuf S_rowptr, S_col, S_val, sm_off;
     double pen_const = 0.0;
@@ -110,10 +112,22 @@ int dev_upload(DevBuf& b, const std::vector<T>& v, std::string& err) {
 // small kernels: theta gather, finalisation (reductions over tiles, penalty, packing)
 // ---------------------------------------------------------------------------------------------
 __global__ void gather_theta_kernel(const double* __restrict__ par, double* __restrict__ theta,
-                                    int p_fe, int p_re, int o_fe, int o_re) {
+                                    int p_fe, int p_re, int o_fe, int o_re,
+                                    const int32_t* __restrict__ mu_cols, int n_mu_cols, int* __restrict__ mu_zero) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < p_fe) theta[i] = par[o_fe + i];
     else if (i < p_fe + p_re) theta[i] = par[o_re + (i - p_fe)];
+    if (blockIdx.x == 0 && mu_zero) {
+        // mu_d == 0 on every row iff every theta entry its design columns touch is exactly 0
+        int nz = (n_mu_cols < 0) ? 1 : 0;
+        for (int k = threadIdx.x; k < n_mu_cols; k += blockDim.x) {
+            const int c = mu_cols[k];
+            const double v = (c < p_fe) ? par[o_fe + c] : par[o_re + (c - p_fe)];
+            if (v != 0.0) nz = 1;
+        }
+        nz = __syncthreads_or(nz);
+        if (threadIdx.x == 0) *mu_zero = nz ? 0 : 1;
+    }
 }
 
 struct FinArgs {
@@ -524,6 +538,9 @@ int finish_setup(ssde_handle* h) {
     if ((rc = dev_alloc<double>(h->grad_theta, p, err))) return rc;
     if ((rc = dev_alloc<double>(h->out, h->npar + 2, err))) return rc;
     if ((rc = dev_alloc<double>(h->part, 2 * RED_BLOCKS, err))) return rc;
+    if ((rc = dev_alloc<int>(h->mu_zero, 1, err))) return rc;
+    CUDA_TRY(cudaMemset(h->mu_zero.p, 0, sizeof(int)));
+    if (!h->mu_cols.p && (rc = dev_alloc<int32_t>(h->mu_cols, 1, err))) return rc;
     if ((rc = dev_alloc<unsigned>(h->counters, 4, err))) return rc;
     CUDA_TRY(cudaMemset(h->counters.p, 0, 4 * sizeof(unsigned)));
     CUDA_TRY(cudaMallocHost(&h->h_pinned, sizeof(double) * (2 * (size_t)h->npar + 4)));
@@ -596,6 +613,7 @@ int launch_ctcrw(ssde_handle* h, const double* d_par, int order, cudaStream_t st
     a.obs = h->obs.as<double>(); a.dt = h->dt.as<double>(); a.flags = h->flags.as<uint8_t>();
     a.track_starts = h->track_starts.as<int64_t>(); a.a0 = h->a0.as<double>(); a.n_tracks = h->n_tracks;
     a.P0 = h->P0; a.par = d_par; a.s_in = nullptr; a.g_in = nullptr;
+    a.mu_zero = h->mu_zero.as<int>();
     a.ckpt = h->ckpt.as<double>(); a.nchunks = h->nchunks;
     a.tile_llk = h->tile_llk.as<double>(); a.tile_gh = h->tile_gh.as<double>();
     a.grad_theta = h->grad_theta.as<double>(); a.p_theta = h->p_fe + h->p_re;
@@ -648,7 +666,8 @@ int run_eval(ssde_handle* h, const double* d_par, int order, double* d_out, cuda
     CUDA_TRY(cudaMemsetAsync(h->counters.p, 0, 3 * sizeof(unsigned), st));
     if (order >= 1) CUDA_TRY(cudaMemsetAsync(h->grad_theta.p, 0, sizeof(double) * std::max(p, 1), st));
     mark(h, st, "gather_theta");
-    gather_theta_kernel<<<(p + 255) / 256, 256, 0, st>>>(d_par, h->theta.as<double>(), h->p_fe, h->p_re, h->o_fe, h->o_re);
+    gather_theta_kernel<<<std::max((p + 255) / 256, 1), 256, 0, st>>>(d_par, h->theta.as<double>(), h->p_fe, h->p_re, h->o_fe, h->o_re,
+                                                                     h->mu_cols.as<int32_t>(), h->n_mu_cols, h->mu_zero.as<int>());
     int rc = SSDE_OK;
     FinArgs f{};
     if (h->model == SSDE_CTCRW) {
@@ -842,6 +861,22 @@ int ssde_create(const ssde_desc* d, ssde_handle** out) {
     Packed pk;
     if ((rc = pack_design(*d, n_par, pk, h->err))) return fail(rc);
     h->nnz = (int64_t)pk.col.size();
+    if (d->model == SSDE_CTCRW) {
+        std::vector<int32_t> mc;
+        for (int64_t r = 0; r < n; ++r) {
+            uint32_t rp = pk.rowptr[r];
+            for (int p = 0; p < nd; ++p) {
+                const uint32_t k = (pk.cnt[r] >> (8 * p)) & 255u;
+                for (uint32_t j = 0; j < k; ++j) mc.push_back((int32_t)pk.col[rp + j]);
+                rp += k;
+            }
+            if (mc.size() > (1u << 20)) { std::sort(mc.begin(), mc.end()); mc.erase(std::unique(mc.begin(), mc.end()), mc.end()); }
+        }
+        std::sort(mc.begin(), mc.end());
+        mc.erase(std::unique(mc.begin(), mc.end()), mc.end());
+        h->n_mu_cols = (int)mc.size();
+        if ((rc = dev_upload(h->mu_cols, mc, h->err))) return fail(rc);
+    }
     V2Host v2;
     if ((rc = build_v2(pk, n, n_pad, n_par, v2, h->err))) return fail(rc);
     if ((rc = dev_upload(h->desc, v2.desc, h->err))) return fail(rc);
@@ -879,6 +914,11 @@ int ssde_create_packed(const ssde_packed_desc* d, ssde_handle** out) {
     h->obs.p = (void*)d->d_obs; h->dt.p = (void*)d->d_dt; h->flags.p = (void*)d->d_flags;
     h->n_tracks = d->n_ID;
     h->P0 = {d->P0[0], d->P0[1], d->P0[2]};
+    if (d->mu_cols && d->n_mu_cols >= 0) {
+        std::vector<int32_t> mc(d->mu_cols, d->mu_cols + d->n_mu_cols);
+        h->n_mu_cols = d->n_mu_cols;
+        if ((rc = dev_upload(h->mu_cols, mc, h->err))) return fail(rc);
+    }
     std::vector<int64_t> starts(d->track_starts, d->track_starts + d->n_ID);
     if ((rc = dev_upload(h->track_starts, starts, h->err))) return fail(rc);
     if (d->model == SSDE_CTCRW) {

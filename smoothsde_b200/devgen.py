@@ -219,6 +219,10 @@ def make_ctcrw_device(n_tracks, n_steps, seed=20260103, device=0, k=10, sigma_ob
     pd.P0[0], pd.P0[1], pd.P0[2] = 1.0, 0.0, 10.0
     pd.device = device
     pd.shard_flags = shard_flags
+    mu_cols = np.array([0, 1], dtype=np.int32)       # mu1.(Intercept), mu2.(Intercept)
+    keep.append(mu_cols)
+    pd.mu_cols = mu_cols.ctypes.data_as(L.c_int32_p)
+    pd.n_mu_cols = 2
     torch.cuda.synchronize(dev)
     eng = Engine.from_packed(pd, keep)
 

@@ -182,3 +182,4 @@ extern "C" int harness_ctcrw(int nd, int mode, int64_t n, const uint8_t* flags, 
     }
     return 1;
 }
+

@@ -156,3 +156,4 @@ def test_scan_algebra_matches_oracle(harness, T, m, miss, nd, lc, nt):
         assert abs((-llk + pen) - v) <= 1e-12 * abs(v)
         assert abs(gsig - g[0]) <= 1e-9 * max(abs(g[0]), 1e-3)
         assert np.max(np.abs(eb - pb_ref)) <= 1e-9 * max(np.max(np.abs(pb_ref)), 1.0)
+
