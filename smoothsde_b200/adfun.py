@@ -1,0 +1,164 @@
+"""`MakeADFun`-shaped objective on top of the CUDA engine.
+
+In the reference, ``SDE$setup()`` calls ``TMB::MakeADFun(data, parameters, map, random)`` twice
+(R/sde.R:656-669) and then only uses the returned closures: ``obj$par``, ``obj$fn``, ``obj$gr``
+(R/sde.R:694-697), ``obj$report()`` (R/sde.R:1324) and ``obj$env$last.par.best`` (sdreport).
+:class:`ADFun` provides the same members for the parameter lists the hot path knows:
+
+    CTCRW : log_sigma_obs, coeff_fe, log_lambda, coeff_re      (nllk_ctcrw.hpp:135-140)
+    BM/OU : coeff_fe, log_lambda, [log_decay], coeff_re        (nllk_sde.hpp:42-45)
+
+``map`` follows TMB: per parameter a vector of factor codes, ``None``/NaN fixes an entry at its
+initial value, equal codes tie entries together (``fixpar`` becomes ``map$coeff_fe`` with NA at
+the fixed positions, R/sde.R:621-632).  ``random="coeff_re"`` asks for the Laplace-marginal
+objective; it is provided by :mod:`smoothsde_b200.laplace`.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .engine import Engine
+
+PAR_ORDER = ("log_sigma_obs", "coeff_fe", "log_lambda", "log_decay", "coeff_re")
+
+
+class Env:
+    """The part of TMB's ``obj$env`` that R/sde.R and sdreport read."""
+
+    def __init__(self, last_par):
+        self.last_par = last_par.copy()
+        self.last_par_best = last_par.copy()
+        self.value_best = np.inf
+        self.random = None
+
+
+class ADFun:
+    def __init__(self, data, parameters, map=None, random=None, device=0, engine=None):
+        self.data = data
+        self.engine = engine if engine is not None else Engine.from_data(data, device=device)
+        layout = self.engine.layout                      # name -> (offset, size) in the full vector
+        map = dict(map or {})
+        # ---- full parameter vector in the templates' PARAMETER order
+        full = np.zeros(self.engine.n_par)
+        names = np.empty(self.engine.n_par, dtype=object)
+        for nm in PAR_ORDER:
+            if nm == "log_decay":
+                # exists in the list for BM/OU (R/sde.R:504-507) but is mapped off without decay
+                # terms (R/sde.R:648); decay models are out of scope
+                if nm in parameters and nm in map and not _all_na(map[nm]):
+                    raise NotImplementedError("decay terms (log_decay) are not built")
+                continue
+            if nm not in layout:
+                continue
+            off, size = layout[nm]
+            val = np.atleast_1d(np.asarray(parameters.get(nm, np.zeros(size)), dtype=float))
+            if val.size != size:
+                raise ValueError(f"parameter '{nm}' has length {val.size}, the data imply {size}")
+            full[off:off + size] = val
+            names[off:off + size] = nm
+        # ---- map: group id per entry (-1 = fixed)
+        group = np.arange(full.size)
+        for nm, codes in map.items():
+            if nm == "log_decay" or nm not in layout:
+                continue
+            off, size = layout[nm]
+            codes = np.atleast_1d(np.asarray(codes, dtype=object))
+            if codes.size != size:
+                raise ValueError(f"map${nm} has length {codes.size}, expected {size}")
+            first = {}
+            for i, c in enumerate(codes):
+                if c is None or (isinstance(c, float) and np.isnan(c)):
+                    group[off + i] = -1
+                else:
+                    group[off + i] = first.setdefault(c, off + i)
+        self._full0 = full
+        self._group = group
+        self.names_full = names
+        self.random = random
+        if random is not None:
+            if random != "coeff_re":
+                raise ValueError("only random = 'coeff_re' exists in smoothSDE (R/sde.R:522-524)")
+            off, size = layout["coeff_re"]
+            self._is_random = np.zeros(full.size, dtype=bool)
+            self._is_random[off:off + size] = True
+        else:
+            self._is_random = np.zeros(full.size, dtype=bool)
+        free = np.unique(group[group >= 0])
+        self._free = free                                   # representative index of every free group
+        self._active = free[~self._is_random[free]]         # what optim sees (obj$par)
+        self._rand = free[self._is_random[free]]
+        self.par = full[self._active].copy()
+        self.names = names[self._active]
+        self.env = Env(full)
+        self.env.random = self._rand
+        self._laplace = None
+        if random is not None and self._rand.size:
+            from .laplace import Laplace
+            self._laplace = Laplace(self)
+
+    # ------------------------------------------------------------------------------------
+    def full_from(self, x, b=None):
+        """Scatter active (and optionally random) values into the full parameter vector."""
+        p = self._full0.copy()
+        vals = np.empty(p.size)
+        vals[:] = np.nan
+        vals[self._active] = np.asarray(x, dtype=float)
+        if self._rand.size:
+            vals[self._rand] = self.env.last_par[self._rand] if b is None else np.asarray(b, dtype=float)
+        ok = self._group >= 0
+        p[ok] = vals[self._group[ok]]
+        return p
+
+    def reduce_grad(self, g_full, idx):
+        """Sum the full-vector gradient over tied entries and pick the groups in `idx`."""
+        out = np.zeros(self._full0.size)
+        ok = self._group >= 0
+        np.add.at(out, self._group[ok], g_full[ok])
+        return out[idx]
+
+    def joint(self, p_full, order=1):
+        v, g = self.engine.eval(p_full, order=order)
+        self.env.last_par = p_full.copy()
+        return v, g
+
+    def _remember(self, v, p_full):
+        if np.isfinite(v) and v < self.env.value_best:
+            self.env.value_best = v
+            self.env.last_par_best = p_full.copy()
+
+    # ------------------------------------------------------------------------------------
+    def fn(self, x=None):
+        x = self.par if x is None else x
+        if self._laplace is not None:
+            return self._laplace.fn(np.asarray(x, dtype=float))
+        p = self.full_from(x)
+        v, _ = self.joint(p, order=0)
+        self._remember(v, p)
+        return v
+
+    def gr(self, x=None):
+        x = self.par if x is None else x
+        if self._laplace is not None:
+            return self._laplace.gr(np.asarray(x, dtype=float))
+        p = self.full_from(x)
+        v, g = self.joint(p, order=1)
+        self._remember(v, p)
+        return self.reduce_grad(g, self._active)
+
+    def report(self, par_full=None):
+        """REPORT()ed quantities at `par_full` (default: the last evaluated parameters)."""
+        if self.data["type"] != "CTCRW":
+            return {}
+        if par_full is not None:
+            self.joint(np.asarray(par_full, dtype=float), order=0)
+        obs = np.asarray(self.data["obs"])
+        n, d = (obs.shape[0], 1) if obs.ndim == 1 else obs.shape
+        return {"aest_all": self.engine.report(n, d)}
+
+    def close(self):
+        self.engine.close()
+
+
+def _all_na(codes):
+    codes = np.atleast_1d(np.asarray(codes, dtype=object))
+    return all(c is None or (isinstance(c, float) and np.isnan(c)) for c in codes)

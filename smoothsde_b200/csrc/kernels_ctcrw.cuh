@@ -37,8 +37,8 @@ struct CtcrwArgs {
     const int* mu_zero;        // device flag: every mu_d predictor is exactly 0 at these parameters
     double* ckpt;              // [(2*ND+3), nchunks] start state of every thread chunk
     int64_t nchunks;           // n_pad / LC
-    double* tile_llk;          // [ntiles_f]
-    double* tile_gh;           // [ntiles_b]
+    double* tile_llk;          // [n_pad / WT] one partial log-likelihood per warp-tile
+    double* tile_gh;           // [n_pad / WT] one partial d nllk / d h per warp-tile
     double* grad_theta;        // [p_theta], accumulated with atomics
     int p_theta;
     double* aest;              // optional [n, 2*ND]: REPORT(aest_all), nllk_ctcrw.hpp:246-249
@@ -83,12 +83,12 @@ struct FwdSmem {
     static constexpr int NC = 5;                 // T12, e, Qa, Qb, Qc
     double W[LC][NC][NT];
     double stage[NT / 32][STAGE_DBL];
-    double wagg[NT / 32][24];
-    double tagg[24];
-    double misc[32];
+    double wagg[2][NT / 32][24];     // shared scratch is double-buffered by tile parity: the only
+    double tagg[2][24];              // barrier between two tiles is the one that hands out the ticket
+    double misc[2][16];
     double th[NT / 32][TH_CACHE];
     uint64_t bar[NT / 32];
-    int ticket;
+    int ticket[2];
 };
 
 template <int ND, int NT, int MINB>
@@ -109,11 +109,13 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(CtcrwArgs<ND> a) {
     stage_init(st, sm.stage[warp], &sm.bar[warp]);
     mbar_fence_init();
 
-    while (true) {
+    // Tickets are taken just in time (a tile reserved ahead of time by a busy CTA would stall the
+    // look-back of every later tile).
+    for (int it = 0;; ++it) {
+        const int par = it & 1;
+        if (tid == 0) sm.ticket[par] = (int)atomicAdd(a.fdesc.ticket, 1u);
         __syncthreads();
-        if (tid == 0) sm.ticket = (int)atomicAdd(a.fdesc.ticket, 1u);
-        __syncthreads();
-        const int tile = sm.ticket;
+        const int tile = sm.ticket[par];
         if (tile >= a.ntiles) break;
         const int64_t q = (int64_t)tile * NWARP + warp;
         const int64_t base = q * WT + lane;
@@ -161,39 +163,40 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(CtcrwArgs<ND> a) {
             Elem f = shfl_up_elem(inc, o);
             if (lane >= o) inc = fwd_combine<ND>(f, inc);
         }
-        if (lane == 31) store_elem(sm.wagg[warp], inc);
+        if (lane == 31) store_elem(sm.wagg[par][warp], inc);
         Elem exc = shfl_up_elem(inc, 1);
         if (lane == 0) exc = fwd_identity<ND>();
         __syncthreads();
         // (3) the last warp composes and publishes the tile aggregate while warp 0 looks back over
         //     the earlier tiles; warp 0 then publishes the inclusive prefix and the tile start state
         if (warp == NWARP - 1) {
-            Elem tagg = load_elem<Elem>(sm.wagg[0]);
+            Elem tagg = load_elem<Elem>(sm.wagg[par][0]);
 #pragma unroll 1
-            for (int ww = 1; ww < NWARP; ++ww) tagg = fwd_combine<ND>(tagg, load_elem<Elem>(sm.wagg[ww]));
-            if (lane == 0) { publish_agg<Ops>(a.fdesc, tile, tagg); store_elem(sm.tagg, tagg); }
+            for (int ww = 1; ww < NWARP; ++ww) tagg = fwd_combine<ND>(tagg, load_elem<Elem>(sm.wagg[par][ww]));
+            if (lane == 0) { publish_agg<Ops>(a.fdesc, tile, tagg); store_elem(sm.tagg[par], tagg); }
         }
         Elem pre;
-        if (warp == 0) pre = lookback<Ops>(a.fdesc, tile);
-        __syncthreads();
-        if (warp == 0 && lane == 0) {
-            // state at the first row of the tile
-            State<ND> s0;
-            if (a.s_in) s0 = load_state<ND>(a.s_in);
-            else { s0.P = a.P0;
+        if (warp == 0) {
+            pre = lookback<Ops>(a.fdesc, tile);
+            if (lane == 0) {
+                // state at the first row of the tile
+                State<ND> s0;
+                if (a.s_in) s0 = load_state<ND>(a.s_in);
+                else { s0.P = a.P0;
 #pragma unroll
-                for (int d = 0; d < ND; ++d) s0.a[d] = {0.0, 0.0}; }
-            const State<ND> st0 = fwd_apply<ND>(pre, s0);
+                    for (int d = 0; d < ND; ++d) s0.a[d] = {0.0, 0.0}; }
+                const State<ND> st0 = fwd_apply<ND>(pre, s0);
 #pragma unroll
-            for (int d = 0; d < ND; ++d) { sm.misc[2 * d] = st0.a[d].x; sm.misc[2 * d + 1] = st0.a[d].y; }
-            sm.misc[2 * ND] = st0.P.a; sm.misc[2 * ND + 1] = st0.P.b; sm.misc[2 * ND + 2] = st0.P.c;
+                for (int d = 0; d < ND; ++d) { sm.misc[par][2 * d] = st0.a[d].x; sm.misc[par][2 * d + 1] = st0.a[d].y; }
+                sm.misc[par][2 * ND] = st0.P.a; sm.misc[par][2 * ND + 1] = st0.P.b; sm.misc[par][2 * ND + 2] = st0.P.c;
+            }
         }
         __syncthreads();
-        if (warp == 0 && lane == 0) publish_incl<Ops>(a.fdesc, tile, fwd_combine<ND>(pre, load_elem<Elem>(sm.tagg)));
+        if (warp == 0 && lane == 0) publish_incl<Ops>(a.fdesc, tile, fwd_combine<ND>(pre, load_elem<Elem>(sm.tagg[par])));
         // (4) exact start state of this thread, checkpoint, plain filter re-run
-        State<ND> s = load_state<ND>(sm.misc);
+        State<ND> s = load_state<ND>(sm.misc[par]);
 #pragma unroll 1
-        for (int ww = 0; ww < warp; ++ww) s = fwd_apply<ND>(load_elem<Elem>(sm.wagg[ww]), s);
+        for (int ww = 0; ww < warp; ++ww) s = fwd_apply<ND>(load_elem<Elem>(sm.wagg[par][ww]), s);
         s = fwd_apply<ND>(exc, s);
         const int64_t chunk = q * 32 + lane;
         {
@@ -240,9 +243,8 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(CtcrwArgs<ND> a) {
                 for (int d = 0; d < ND; ++d) { o[2 * d] = s.a[d].x; o[2 * d + 1] = s.a[d].y; }
             }
         }
-        const double llk = -0.5 * ((double)ND * (slog + log(fprod)) + quad);
-        const double tl = block_sum<NT>(llk, sm.misc + 16);
-        if (tid == 0) a.tile_llk[tile] = tl;
+        const double llk = warp_sum(-0.5 * ((double)ND * (slog + log(fprod)) + quad));
+        if (lane == 0) a.tile_llk[q] = llk;              // one partial per warp-tile
     }
 }
 
@@ -266,13 +268,13 @@ struct BwdSmem {
     static constexpr int NC = FS + 3;            // + tau, e, s2
     double R[LC][NC][NT];
     double stage[NT / 32][STAGE_DBL];
-    double wagg[NT / 32][16];
-    double tagg[16];
-    double misc[32];
+    double wagg[2][NT / 32][16];
+    double tagg[2][16];
+    double misc[2][16];
     double th[NT / 32][TH_CACHE];
     double sgrad[SGRAD];
     uint64_t bar[NT / 32];
-    int ticket;
+    int ticket[2];
 };
 
 template <int ND, int NT, int MINB>
@@ -297,11 +299,11 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_bwd_kernel(CtcrwArgs<ND> a) {
     stage_init(st, sm.stage[warp], &sm.bar[warp]);
     mbar_fence_init();
 
-    while (true) {
+    for (int it = 0;; ++it) {
+        const int par = it & 1;
+        if (tid == 0) sm.ticket[par] = (int)atomicAdd(a.bdesc.ticket, 1u);
         __syncthreads();
-        if (tid == 0) sm.ticket = (int)atomicAdd(a.bdesc.ticket, 1u);
-        __syncthreads();
-        const int ticket = sm.ticket;
+        const int ticket = sm.ticket[par];
         if (ticket >= a.ntiles) break;
         const int tile = a.ntiles - 1 - ticket;           // reverse time order
         const int64_t q = (int64_t)tile * NWARP + warp;
@@ -372,7 +374,7 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_bwd_kernel(CtcrwArgs<ND> a) {
             Elem f = shfl_down_elem(inc, o);
             if (lane + o < 32) inc = bwd_combine<ND>(inc, f);
         }
-        if (lane == 0) store_elem(sm.wagg[warp], inc);
+        if (lane == 0) store_elem(sm.wagg[par][warp], inc);
         Elem exc = shfl_down_elem(inc, 1);
         if (lane == 31) exc = bwd_identity<ND>();
         __syncthreads();
@@ -380,27 +382,28 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_bwd_kernel(CtcrwArgs<ND> a) {
         //     the LATER tiles; warp 0 then publishes the inclusive suffix and the adjoint entering
         //     the tile end
         if (warp == NWARP - 1) {
-            Elem tagg = load_elem<Elem>(sm.wagg[NWARP - 1]);
+            Elem tagg = load_elem<Elem>(sm.wagg[par][NWARP - 1]);
 #pragma unroll 1
-            for (int ww = NWARP - 2; ww >= 0; --ww) tagg = bwd_combine<ND>(load_elem<Elem>(sm.wagg[ww]), tagg);
-            if (lane == 0) { publish_agg<Ops>(a.bdesc, ticket, tagg); store_elem(sm.tagg, tagg); }
+            for (int ww = NWARP - 2; ww >= 0; --ww) tagg = bwd_combine<ND>(load_elem<Elem>(sm.wagg[par][ww]), tagg);
+            if (lane == 0) { publish_agg<Ops>(a.bdesc, ticket, tagg); store_elem(sm.tagg[par], tagg); }
         }
         Elem suf;
-        if (warp == 0) suf = lookback<Ops>(a.bdesc, ticket);
-        __syncthreads();
-        if (warp == 0 && lane == 0) {
-            Adj<ND> g0 = a.g_in ? load_adj<ND>(a.g_in) : adj_zero<ND>();
-            const Adj<ND> gt = bwd_apply<ND>(suf, g0);
+        if (warp == 0) {
+            suf = lookback<Ops>(a.bdesc, ticket);
+            if (lane == 0) {
+                Adj<ND> g0 = a.g_in ? load_adj<ND>(a.g_in) : adj_zero<ND>();
+                const Adj<ND> gt = bwd_apply<ND>(suf, g0);
 #pragma unroll
-            for (int d = 0; d < ND; ++d) { sm.misc[2 * d] = gt.a[d].x; sm.misc[2 * d + 1] = gt.a[d].y; }
-            sm.misc[2 * ND] = gt.P.a; sm.misc[2 * ND + 1] = gt.P.b; sm.misc[2 * ND + 2] = gt.P.c;
+                for (int d = 0; d < ND; ++d) { sm.misc[par][2 * d] = gt.a[d].x; sm.misc[par][2 * d + 1] = gt.a[d].y; }
+                sm.misc[par][2 * ND] = gt.P.a; sm.misc[par][2 * ND + 1] = gt.P.b; sm.misc[par][2 * ND + 2] = gt.P.c;
+            }
         }
         __syncthreads();
-        if (warp == 0 && lane == 0) publish_incl<Ops>(a.bdesc, ticket, bwd_combine<ND>(load_elem<Elem>(sm.tagg), suf));
+        if (warp == 0 && lane == 0) publish_incl<Ops>(a.bdesc, ticket, bwd_combine<ND>(load_elem<Elem>(sm.tagg[par]), suf));
         // (4) adjoint entering this thread's last row, then the reverse sweep over its rows
-        Adj<ND> g = load_adj<ND>(sm.misc);
+        Adj<ND> g = load_adj<ND>(sm.misc[par]);
 #pragma unroll 1
-        for (int ww = NWARP - 1; ww > warp; --ww) g = bwd_apply<ND>(load_elem<Elem>(sm.wagg[ww]), g);
+        for (int ww = NWARP - 1; ww > warp; --ww) g = bwd_apply<ND>(load_elem<Elem>(sm.wagg[par][ww]), g);
         g = bwd_apply<ND>(exc, g);
         double gh = 0.0;
 #pragma unroll 1
@@ -450,8 +453,8 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_bwd_kernel(CtcrwArgs<ND> a) {
         // (5) grad_theta += X' eta_bar for this warp-tile
         if (w.staged) scatter_warptile_staged<NP>(w, st.buf, gacc, [&](int k, int p) { return sm.R[k][p][tid]; });
         else scatter_warptile<NP>(w, gacc, [&](int k, int p) { return sm.R[k][p][tid]; });
-        const double tg = block_sum<NT>(gh, sm.misc + 16);
-        if (tid == 0) a.tile_gh[tile] = tg;
+        gh = warp_sum(gh);
+        if (lane == 0) a.tile_gh[q] = gh;                // one partial per warp-tile
     }
     if (gacc.sgrad) {
         __syncthreads();

@@ -550,8 +550,8 @@ int finish_setup(ssde_handle* h) {
         h->ntiles_b = (int)(h->n_pad / (BWD_NT * LC));
         h->nchunks = h->n_pad / LC;
         if ((rc = dev_alloc<double>(h->ckpt, (size_t)h->nchunks * (2 * nd + 3), err))) return rc;
-        if ((rc = dev_alloc<double>(h->tile_llk, h->ntiles_f, err))) return rc;
-        if ((rc = dev_alloc<double>(h->tile_gh, h->ntiles_b, err))) return rc;
+        if ((rc = dev_alloc<double>(h->tile_llk, h->n_pad / WT, err))) return rc;
+        if ((rc = dev_alloc<double>(h->tile_gh, h->n_pad / WT, err))) return rc;
         if ((rc = dev_alloc<unsigned>(h->f_status, h->ntiles_f, err))) return rc;
         if ((rc = dev_alloc<unsigned>(h->b_status, h->ntiles_b, err))) return rc;
         CUDA_TRY(cudaMemset(h->f_status.p, 0, sizeof(unsigned) * std::max(h->ntiles_f, 1)));
@@ -630,8 +630,8 @@ int launch_ctcrw(ssde_handle* h, const double* d_par, int order, cudaStream_t st
         ctcrw_bwd_kernel<ND, BWD_NT, BWD_MINB><<<h->grid_b, BWD_NT, sizeof(BwdSmem<ND, BWD_NT>), st>>>(a);
     }
     mark(h, st, "reduce_tiles");
-    reduce_tiles_kernel<<<RED_BLOCKS, 256, 0, st>>>(h->tile_llk.as<double>(), h->ntiles_f,
-                                                     order >= 1 ? h->tile_gh.as<double>() : nullptr, h->ntiles_b,
+    reduce_tiles_kernel<<<RED_BLOCKS, 256, 0, st>>>(h->tile_llk.as<double>(), (int)(h->n_pad / WT),
+                                                     order >= 1 ? h->tile_gh.as<double>() : nullptr, (int)(h->n_pad / WT),
                                                      h->part.as<double>());
     CUDA_TRY(cudaGetLastError());
     return SSDE_OK;
