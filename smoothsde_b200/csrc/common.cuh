@@ -290,6 +290,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
             "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     } while (!done);
 }
+// hint: bring [p, p + bytes) into L2 (bytes a multiple of 16)
+__device__ __forceinline__ void prefetch_l2(const void* p, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 // order this thread's earlier generic-proxy accesses to shared memory before later async-proxy
 // (TMA) writes to the same locations
 __device__ __forceinline__ void fence_proxy_async() {

@@ -89,7 +89,7 @@ __device__ __forceinline__ void stage_init(WarpStage& st, double* buf, uint64_t*
 
 // Called by all lanes of a warp.  `th_cache` is this warp's TH_CACHE doubles of shared memory.
 __device__ __forceinline__ WtView open_warptile(const DesignV2& X, int64_t q, const double* __restrict__ theta,
-                                                double* th_cache) {
+                                                double* th_cache, bool want_theta = true) {
     const int lane = threadIdx.x & 31;
     const WtDesc d = X.desc[q];
     WtView w;
@@ -105,7 +105,9 @@ __device__ __forceinline__ WtView open_warptile(const DesignV2& X, int64_t q, co
     bool le16 = true;
 #pragma unroll
     for (int p = 0; p < MAX_NP; ++p) le16 = le16 && (((d.kmax >> (8 * p)) & 255u) <= 16u);
-    if (w.uniform && w.S > 0 && w.S <= STAGE_SLOTS && le16) {
+    if (!want_theta) {
+        // caller only walks the values / columns (transposed product)
+    } else if (w.uniform && w.S > 0 && w.S <= STAGE_SLOTS && le16) {
         __syncwarp();
         int j0 = 0;
 #pragma unroll
@@ -232,15 +234,15 @@ __device__ __forceinline__ void grad_add(const GradAcc& g, uint32_t c, double v)
     else atomicAdd(g.ggrad + c, v);
 }
 
-// Uniform warp-tile with at most STAGE_SLOTS slots: per-lane partial sums over the LC rows go to
-// the warp's scratch T[j][lane] (the staging buffer, idle by now), then lane j adds up row j of
-// T -- no shuffles, one atomic per slot.
-template <int NP, class EB>
-__device__ __forceinline__ void scatter_warptile_staged(const WtView& w, double* T, const GradAcc& g, EB eb) {
+// Uniform warp-tile: per-lane partial sums over the LC rows go to a per-warp scratch T(j, lane)
+// in shared memory (accessor `T`), then lane j adds up row j of T -- no shuffles, one atomic per
+// slot.  The caller guarantees that T has room for w.S slots.
+template <int NP, class EB, class TA>
+__device__ __forceinline__ void scatter_warptile_transposed(const WtView& w, const GradAcc& g, EB eb, TA T) {
     const int lane = threadIdx.x & 31;
     const size_t ks = (size_t)w.S * 32;
     const double* vj = w.v;
-    double* tj = T + lane;
+    int j = 0;
     __syncwarp();
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
@@ -248,24 +250,24 @@ __device__ __forceinline__ void scatter_warptile_staged(const WtView& w, double*
         double e[LC];
 #pragma unroll
         for (int k = 0; k < LC; ++k) e[k] = eb(k, p);
-        for (int i = 0; i < kp; ++i) {
+#pragma unroll 1
+        for (int i = 0; i < kp; ++i, ++j) {
             double acc = 0.0;
 #pragma unroll
             for (int k = 0; k < LC; ++k) acc = fma(__ldg(vj + k * ks), e[k], acc);
-            *tj = acc;
-            vj += 32; tj += 32;
+            T(j, lane) = acc;
+            vj += 32;
         }
     }
     __syncwarp();
-    if (lane < w.S) {
-        const double* t = T + lane * 32;
+    for (int jj = lane; jj < w.S; jj += 32) {
         double s0 = 0.0, s1 = 0.0;
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-            s0 += t[(i + lane) & 31];
-            s1 += t[(i + 1 + lane) & 31];
+            s0 += T(jj, (i + lane) & 31);
+            s1 += T(jj, (i + 1 + lane) & 31);
         }
-        grad_add(g, __ldg(w.c + lane), s0 + s1);
+        grad_add(g, __ldg(w.c + jj), s0 + s1);
     }
     __syncwarp();
 }

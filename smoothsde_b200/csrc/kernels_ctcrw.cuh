@@ -35,6 +35,7 @@ struct CtcrwArgs {
     const double* s_in;        // optional incoming state (2*ND + 3 doubles) for a continued shard
     const double* g_in;        // optional incoming adjoint (2*ND + 3 doubles)
     const int* mu_zero;        // device flag: every mu_d predictor is exactly 0 at these parameters
+    double* wg;                // [3, n_pad] permuted: tau, e = exp(-dt/tau), s2 of every row (forward -> adjoint)
     double* ckpt;              // [(2*ND+3), nchunks] start state of every thread chunk
     int64_t nchunks;           // n_pad / LC
     double* tile_llk;          // [n_pad / WT] one partial log-likelihood per warp-tile
@@ -120,7 +121,7 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(CtcrwArgs<ND> a) {
         const int64_t q = (int64_t)tile * NWARP + warp;
         const int64_t base = q * WT + lane;
         const int64_t row0 = q * WT + (int64_t)lane * LC;
-        const WtView w = open_warptile(a.X, q, a.theta, sm.th[warp]);
+        const WtView w = open_warptile(a.X, q, a.theta, sm.th[warp], true);
         if (w.staged && lane == 0) stage_issue(w, st, 0);
         const unsigned long long fl = load_flags8(a.flags, base);
 
@@ -148,6 +149,7 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(CtcrwArgs<ND> a) {
             if (step) {
                 double tau, e, s2;
                 transform_row(eta[ND], eta[ND + 1], dtv, tau, e, s2);
+                a.wg[pos] = tau; a.wg[a.X.n_pad + pos] = e; a.wg[2 * a.X.n_pad + pos] = s2;
                 const StepPar sp = make_step(tau, e, s2, dtv);
                 sm.W[k][0][tid] = sp.T12; sm.W[k][1][tid] = sp.e;
                 sm.W[k][2][tid] = sp.Q.a; sm.W[k][3][tid] = sp.Q.b; sm.W[k][4][tid] = sp.Q.c;
@@ -265,17 +267,33 @@ constexpr int SGRAD = 256;         // per-CTA gradient accumulators (doubles) wh
 template <int ND, int NT>
 struct BwdSmem {
     static constexpr int FS = 2 * ND + 3;        // forward state before the row
-    static constexpr int NC = FS + 3;            // + tau, e, s2
-    double R[LC][NC][NT];
-    double stage[NT / 32][STAGE_DBL];
+    double R[LC][FS][NT];            // states; overwritten by eta_bar (slots 0..NP-1) and by the
+                                     // transposed-product scratch (slots NP..FS-1) once consumed
     double wagg[2][NT / 32][16];
     double tagg[2][16];
     double misc[2][16];
     double th[NT / 32][TH_CACHE];
     double sgrad[SGRAD];
-    uint64_t bar[NT / 32];
     int ticket[2];
 };
+
+// per-row inputs of the adjoint sweep, fetched one row ahead
+template <int ND>
+struct RowIn {
+    double tau, e, s2, dt, y[ND];
+};
+template <int ND>
+__device__ __forceinline__ RowIn<ND> load_row(const CtcrwArgs<ND>& a, int64_t pos, bool live) {
+    RowIn<ND> r;
+    const int64_t np = a.X.n_pad;
+    r.dt = live ? a.dt[pos] : 1.0;
+    r.tau = live ? a.wg[pos] : 1.0;
+    r.e = live ? a.wg[np + pos] : 0.0;
+    r.s2 = live ? a.wg[2 * np + pos] : 0.0;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) r.y[d] = live ? a.obs[(size_t)d * np + pos] : 0.0;
+    return r;
+}
 
 template <int ND, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) ctcrw_bwd_kernel(CtcrwArgs<ND> a) {
@@ -285,8 +303,9 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_bwd_kernel(CtcrwArgs<ND> a) {
     constexpr int NWARP = NT / 32;
     constexpr int NP = ND + 2;
     constexpr int FS = SM::FS;
+    constexpr int TCAP = (FS - NP) * LC;          // slots whose scratch fits in the freed state slots
     static_assert(Elem::NDBL <= 16, "element too large for the shared staging area");
-    static_assert(SM::NC >= NP, "eta_bar reuses the state slots");
+    static_assert(FS >= NP, "eta_bar reuses the state slots");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SM& sm = *reinterpret_cast<SM*>(smem_raw);
 
@@ -295,9 +314,6 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_bwd_kernel(CtcrwArgs<ND> a) {
     const bool mu0 = *a.mu_zero != 0;
     GradAcc gacc{(a.p_theta <= SGRAD) ? sm.sgrad : nullptr, a.grad_theta};
     if (gacc.sgrad) for (int i = tid; i < SGRAD; i += NT) sm.sgrad[i] = 0.0;
-    WarpStage st;
-    stage_init(st, sm.stage[warp], &sm.bar[warp]);
-    mbar_fence_init();
 
     for (int it = 0;; ++it) {
         const int par = it & 1;
@@ -309,8 +325,10 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_bwd_kernel(CtcrwArgs<ND> a) {
         const int64_t q = (int64_t)tile * NWARP + warp;
         const int64_t base = q * WT + lane;
         const int64_t chunk = q * 32 + lane;
-        const WtView w = open_warptile(a.X, q, a.theta, sm.th[warp]);
-        if (w.staged && lane == 0) stage_issue(w, st, 0);
+        const WtView w = open_warptile(a.X, q, a.theta, sm.th[warp], !mu0);
+        // the design values of this warp-tile are only needed at the very end (X' eta_bar):
+        // ask for them in L2 now
+        if (lane == 0 && w.S > 0) prefetch_l2(w.blk, (unsigned)w.S * WT * 8u);
         const unsigned long long fl = load_flags8(a.flags, base);
 
         // (1) recompute the forward states of this thread's rows from its checkpoint and compose
@@ -325,25 +343,14 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_bwd_kernel(CtcrwArgs<ND> a) {
         s.P.b = a.ckpt[(size_t)(2 * ND + 1) * a.nchunks + chunk];
         s.P.c = a.ckpt[(size_t)(2 * ND + 2) * a.nchunks + chunk];
         Elem E = bwd_identity<ND>();
+        RowIn<ND> nx = load_row<ND>(a, base, (uint8_t)fl != 0xff);
 #pragma unroll 1
         for (int k = 0; k < LC; ++k) {
-            const int64_t pos = base + k * 32;
             const uint8_t f = (uint8_t)(fl >> (8 * k));
             const bool live = f != 0xff;
             const bool step = live && !(f & ROW_START);
-            const double dtv = live ? a.dt[pos] : 1.0;
-            double y[ND];
-#pragma unroll
-            for (int d = 0; d < ND; ++d) y[d] = step ? a.obs[(size_t)d * a.X.n_pad + pos] : 0.0;
-            double eta[NP];
-            if (w.staged) {
-                stage_wait(st);
-                row_eta_staged<NP>(w, st, eta);
-                __syncwarp();
-                if (lane == 0 && k + 1 < LC) stage_issue(w, st, k + 1);
-            } else if (step) {
-                row_eta<NP>(w, k, a.theta, eta);
-            }
+            const RowIn<ND> r = nx;
+            if (k + 1 < LC) nx = load_row<ND>(a, base + (k + 1) * 32, (uint8_t)(fl >> (8 * (k + 1))) != 0xff);
             // state BEFORE row k
 #pragma unroll
             for (int d = 0; d < ND; ++d) {
@@ -354,16 +361,17 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_bwd_kernel(CtcrwArgs<ND> a) {
             sm.R[k][2 * ND + 1][tid] = s.P.b;
             sm.R[k][2 * ND + 2][tid] = s.P.c;
             if (step) {
-                double tau, e, s2;
-                transform_row(eta[ND], eta[ND + 1], dtv, tau, e, s2);
-                sm.R[k][FS][tid] = tau; sm.R[k][FS + 1][tid] = e; sm.R[k][FS + 2][tid] = s2;
-                const StepPar sp = make_step(tau, e, s2, dtv);
+                double mu[ND];
+#pragma unroll
+                for (int d = 0; d < ND; ++d) mu[d] = 0.0;
+                if (!mu0) row_eta_prefix<ND>(w, k, a.theta, mu);
+                const StepPar sp = make_step(r.tau, r.e, r.s2, r.dt);
                 StepAux<ND> ax;
                 double F, qd;
-                fwd_step_q<ND, true>(s, sp, y, eta, (f & ROW_OBS) != 0, h, &ax, F, qd);
+                fwd_step_q<ND, true>(s, sp, r.y, mu, (f & ROW_OBS) != 0, h, &ax, F, qd);
                 E = bwd_combine<ND>(E, bwd_row_elem<ND>(sp, ax, (f & ROW_OBS) != 0, (f & ROW_LAST) != 0));
             } else if (live) {
-                s = track_start_state<ND>(a, dtv);
+                s = track_start_state<ND>(a, r.dt);
                 E = bwd_combine<ND>(E, bwd_const<ND>(adj_zero<ND>()));
             }
         }
@@ -406,9 +414,12 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_bwd_kernel(CtcrwArgs<ND> a) {
         for (int ww = NWARP - 1; ww > warp; --ww) g = bwd_apply<ND>(load_elem<Elem>(sm.wagg[par][ww]), g);
         g = bwd_apply<ND>(exc, g);
         double gh = 0.0;
+        nx = load_row<ND>(a, base + (LC - 1) * 32, (uint8_t)(fl >> (8 * (LC - 1))) != 0xff);
 #pragma unroll 1
         for (int k = LC - 1; k >= 0; --k) {
             const uint8_t f = (uint8_t)(fl >> (8 * k));
+            const RowIn<ND> r = nx;
+            if (k > 0) nx = load_row<ND>(a, base + (k - 1) * 32, (uint8_t)(fl >> (8 * (k - 1))) != 0xff);
             double gp[NP];
 #pragma unroll
             for (int j = 0; j < NP; ++j) gp[j] = 0.0;
@@ -416,14 +427,10 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_bwd_kernel(CtcrwArgs<ND> a) {
                 if (f & ROW_START) {
                     g = adj_zero<ND>();
                 } else {
-                    const int64_t pos = base + k * 32;
-                    const double dtv = a.dt[pos];
-                    double mu[ND], y[ND];
+                    double mu[ND];
 #pragma unroll
                     for (int d = 0; d < ND; ++d) mu[d] = 0.0;
                     if (!mu0) row_eta_prefix<ND>(w, k, a.theta, mu);
-#pragma unroll
-                    for (int d = 0; d < ND; ++d) y[d] = a.obs[(size_t)d * a.X.n_pad + pos];
                     State<ND> sk;
 #pragma unroll
                     for (int d = 0; d < ND; ++d) {
@@ -433,15 +440,14 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_bwd_kernel(CtcrwArgs<ND> a) {
                     sk.P.a = sm.R[k][2 * ND][tid];
                     sk.P.b = sm.R[k][2 * ND + 1][tid];
                     sk.P.c = sm.R[k][2 * ND + 2][tid];
-                    const double tau = sm.R[k][FS][tid], e = sm.R[k][FS + 1][tid], s2 = sm.R[k][FS + 2][tid];
-                    const StepPar sp = make_step(tau, e, s2, dtv);
+                    const StepPar sp = make_step(r.tau, r.e, r.s2, r.dt);
                     const bool has = (f & ROW_OBS) != 0, cut = (f & ROW_LAST) != 0;
                     StepAux<ND> ax;
                     double F, qd;
-                    fwd_step_q<ND, true>(sk, sp, y, mu, has, h, &ax, F, qd);
+                    fwd_step_q<ND, true>(sk, sp, r.y, mu, has, h, &ax, F, qd);
                     const Adj<ND> gin = cut ? adj_zero<ND>() : g;
                     double g_h;
-                    row_param_grad<ND>(gin, sp, ax, mu, tau, e, s2, dtv, has, gp, gp[ND], gp[ND + 1], g_h);
+                    row_param_grad<ND>(gin, sp, ax, mu, r.tau, r.e, r.s2, r.dt, has, gp, gp[ND], gp[ND + 1], g_h);
                     gh += g_h;
                     g = bwd_apply<ND>(bwd_row_elem<ND>(sp, ax, has, cut), g);
                 }
@@ -451,8 +457,12 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_bwd_kernel(CtcrwArgs<ND> a) {
             for (int j = 0; j < NP; ++j) sm.R[k][j][tid] = gp[j];
         }
         // (5) grad_theta += X' eta_bar for this warp-tile
-        if (w.staged) scatter_warptile_staged<NP>(w, st.buf, gacc, [&](int k, int p) { return sm.R[k][p][tid]; });
-        else scatter_warptile<NP>(w, gacc, [&](int k, int p) { return sm.R[k][p][tid]; });
+        if (w.uniform && w.S <= TCAP) {
+            scatter_warptile_transposed<NP>(w, gacc, [&](int k, int p) { return sm.R[k][p][tid]; },
+                                            [&](int j, int l) -> double& { return sm.R[j / (FS - NP)][NP + j % (FS - NP)][(tid & ~31) + l]; });
+        } else {
+            scatter_warptile<NP>(w, gacc, [&](int k, int p) { return sm.R[k][p][tid]; });
+        }
         gh = warp_sum(gh);
         if (lane == 0) a.tile_gh[q] = gh;                // one partial per warp-tile
     }

@@ -21,7 +21,7 @@ namespace {
 thread_local std::string g_create_error;
 
 constexpr int FWD_NT = 128, FWD_MINB = 3;
-constexpr int BWD_NT = 128, BWD_MINB = 2;
+constexpr int BWD_NT = 128, BWD_MINB = 3;
 constexpr int PAD_ROWS = 1024;          // n_pad is a multiple of the largest tile (FWD_NT * LC)
 static_assert(PAD_ROWS % (FWD_NT * LC) == 0 && PAD_ROWS % (BWD_NT * LC) == 0 && PAD_ROWS % (SDE_NT * LC) == 0, "tiles must divide the padding unit");
 constexpr int RED_BLOCKS = 64;          // partial sums of the per-tile outputs
@@ -66,7 +66,7 @@ struct ssde_handle {
     DevBuf S_rowptr, S_col, S_val, sm_off;
     double pen_const = 0.0;
     // work buffers
-    DevBuf par, theta, grad_theta, ckpt, tile_llk, tile_gh, block_llk, part, out, sb;
+    DevBuf par, theta, grad_theta, wg, ckpt, tile_llk, tile_gh, block_llk, part, out, sb;
     DevBuf f_status, f_agg, f_incl, b_status, b_agg, b_incl, counters;   // counters: ticket_f, ticket_b, error
     DevBuf aest;
     double* h_pinned = nullptr;      // pinned host staging: par in, out back
@@ -550,6 +550,7 @@ int finish_setup(ssde_handle* h) {
         h->ntiles_b = (int)(h->n_pad / (BWD_NT * LC));
         h->nchunks = h->n_pad / LC;
         if ((rc = dev_alloc<double>(h->ckpt, (size_t)h->nchunks * (2 * nd + 3), err))) return rc;
+        if ((rc = dev_alloc<double>(h->wg, (size_t)h->n_pad * 3, err))) return rc;
         if ((rc = dev_alloc<double>(h->tile_llk, h->n_pad / WT, err))) return rc;
         if ((rc = dev_alloc<double>(h->tile_gh, h->n_pad / WT, err))) return rc;
         if ((rc = dev_alloc<unsigned>(h->f_status, h->ntiles_f, err))) return rc;
@@ -614,7 +615,7 @@ int launch_ctcrw(ssde_handle* h, const double* d_par, int order, cudaStream_t st
     a.track_starts = h->track_starts.as<int64_t>(); a.a0 = h->a0.as<double>(); a.n_tracks = h->n_tracks;
     a.P0 = h->P0; a.par = d_par; a.s_in = nullptr; a.g_in = nullptr;
     a.mu_zero = h->mu_zero.as<int>();
-    a.ckpt = h->ckpt.as<double>(); a.nchunks = h->nchunks;
+    a.ckpt = h->ckpt.as<double>(); a.nchunks = h->nchunks; a.wg = h->wg.as<double>();
     a.tile_llk = h->tile_llk.as<double>(); a.tile_gh = h->tile_gh.as<double>();
     a.grad_theta = h->grad_theta.as<double>(); a.p_theta = h->p_fe + h->p_re;
     a.aest = aest;
