@@ -165,6 +165,22 @@ int ssde_eval(ssde_handle* h, const double* par, int order, double* nllk, double
  * part), d_out[1 .. n_par] = gradient.  `stream` is a cudaStream_t (NULL = the handle's own
  * stream).  Used by the multi-GPU host, which all-reduces d_out over NCCL. */
 int ssde_eval_device(ssde_handle* h, const double* d_par, int order, double* d_out, void* stream);
+/* Time-sharded evaluation of ONE long CTCRW track whose rows are split along time over several
+ * handles / ranks (shard_flags SSDE_SHARD_CONT_PREV / CONT_NEXT).  The filter and its adjoint are
+ * associative scans, so each shard is summarised by one composite element; the host gathers the
+ * elements of all shards between the stages (two all-gathers of < 1 KB and the final all-reduce
+ * per evaluation).  Everything is asynchronous on `stream`, all pointers are device pointers:
+ *   stage 0: forward summary pass;             d_out[ssde_shard_elem_doubles(h, 0)] = this shard's element
+ *   stage 1: d_elems = forward elements of all n_shards shards (shard-major); computes the incoming
+ *            state, runs the forward pass and the adjoint summary pass;
+ *            d_out[ssde_shard_elem_doubles(h, 1)] = this shard's adjoint element
+ *   stage 2: d_elems = adjoint elements of all shards; computes the incoming adjoint, runs the
+ *            adjoint pass;  d_out[1 + n_par + 1] = partial nllk, gradient, status (as ssde_eval_device)
+ */
+int ssde_shard_elem_doubles(const ssde_handle* h, int which);
+int ssde_eval_stage(ssde_handle* h, const double* d_par, int stage, const double* d_elems, int n_shards,
+                    int my_shard, double* d_out, void* stream);
+
 /* Check the device-side status word of the last evaluation (synchronises the stream). */
 int ssde_check(ssde_handle* h);
 

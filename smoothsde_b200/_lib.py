@@ -70,7 +70,8 @@ EXPORTS = ["ssde_create", "ssde_create_packed", "ssde_destroy", "ssde_n_par", "s
            "ssde_eval", "ssde_eval_device", "ssde_check", "ssde_report", "ssde_last_eval_ms",
            "ssde_last_eval_launches", "ssde_set_profile", "ssde_last_kernel_times", "ssde_last_error", "ssde_create_error", "ssde_version",
            "ssde_padded_rows", "ssde_layout_info", "ssde_pack_host", "ssde_pack_free",
-           "ssde_simulate_ctcrw", "ssde_launch_info"]
+           "ssde_simulate_ctcrw", "ssde_launch_info",
+           "ssde_shard_elem_doubles", "ssde_eval_stage"]
 
 
 def load():
@@ -126,6 +127,10 @@ def load():
     lib.ssde_simulate_ctcrw.restype = C.c_int
     lib.ssde_launch_info.argtypes = [vp, c_int32_p]
     lib.ssde_launch_info.restype = C.c_int
+    lib.ssde_shard_elem_doubles.argtypes = [vp, C.c_int]
+    lib.ssde_shard_elem_doubles.restype = C.c_int
+    lib.ssde_eval_stage.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.c_int, vp, vp]
+    lib.ssde_eval_stage.restype = C.c_int
     lib.ssde_version.argtypes = []
     lib.ssde_version.restype = C.c_char_p
     _lib = lib

@@ -250,13 +250,29 @@ __device__ __forceinline__ void scatter_warptile_transposed(const WtView& w, con
         double e[LC];
 #pragma unroll
         for (int k = 0; k < LC; ++k) e[k] = eb(k, p);
+        // 4 slots x LC rows = 32 independent loads in flight per batch
 #pragma unroll 1
-        for (int i = 0; i < kp; ++i, ++j) {
-            double acc = 0.0;
+        for (int i = 0; i < kp; i += 4) {
+            double v[4][LC];
 #pragma unroll
-            for (int k = 0; k < LC; ++k) acc = fma(__ldg(vj + k * ks), e[k], acc);
-            T(j, lane) = acc;
-            vj += 32;
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int k = 0; k < LC; ++k) v[u][k] = (i + u < kp) ? __ldg(vj + u * 32 + k * ks) : 0.0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                double acc = 0.0;
+#pragma unroll
+                for (int k = 0; k < LC; ++k) acc = fma(v[u][k], e[k], acc);
+                if (i + u < kp) T(j + u, lane) = acc;
+            }
+            vj += 128;
+            j += 4;
+        }
+        // slots were advanced in steps of 4: step back to the first slot of the next parameter
+        {
+            const int over = (4 - (kp & 3)) & 3;
+            vj -= over * 32;
+            j -= over;
         }
     }
     __syncwarp();

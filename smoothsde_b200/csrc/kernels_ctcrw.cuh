@@ -45,6 +45,8 @@ struct CtcrwArgs {
     double* aest;              // optional [n, 2*ND]: REPORT(aest_all), nllk_ctcrw.hpp:246-249
     ScanDesc fdesc, bdesc;
     int ntiles;
+    int summary;               // 1: stop after the tile prefixes are published (time-sharded runs only
+                               // need the composite element of the whole shard = last inclusive prefix)
 };
 
 // Start state of the track whose first row carries track index `idx` (stored, as a double, in
@@ -195,6 +197,7 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(CtcrwArgs<ND> a) {
         }
         __syncthreads();
         if (warp == 0 && lane == 0) publish_incl<Ops>(a.fdesc, tile, fwd_combine<ND>(pre, load_elem<Elem>(sm.tagg[par])));
+        if (a.summary) continue;
         // (4) exact start state of this thread, checkpoint, plain filter re-run
         State<ND> s = load_state<ND>(sm.misc[par]);
 #pragma unroll 1
@@ -326,9 +329,6 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_bwd_kernel(CtcrwArgs<ND> a) {
         const int64_t base = q * WT + lane;
         const int64_t chunk = q * 32 + lane;
         const WtView w = open_warptile(a.X, q, a.theta, sm.th[warp], !mu0);
-        // the design values of this warp-tile are only needed at the very end (X' eta_bar):
-        // ask for them in L2 now
-        if (lane == 0 && w.S > 0) prefetch_l2(w.blk, (unsigned)w.S * WT * 8u);
         const unsigned long long fl = load_flags8(a.flags, base);
 
         // (1) recompute the forward states of this thread's rows from its checkpoint and compose
@@ -408,6 +408,7 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_bwd_kernel(CtcrwArgs<ND> a) {
         }
         __syncthreads();
         if (warp == 0 && lane == 0) publish_incl<Ops>(a.bdesc, ticket, bwd_combine<ND>(load_elem<Elem>(sm.tagg[par]), suf));
+        if (a.summary) continue;
         // (4) adjoint entering this thread's last row, then the reverse sweep over its rows
         Adj<ND> g = load_adj<ND>(sm.misc[par]);
 #pragma unroll 1
@@ -473,6 +474,40 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_bwd_kernel(CtcrwArgs<ND> a) {
             if (v != 0.0) atomicAdd(a.grad_theta + i, v);
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// time-sharded runs: composite elements of the shards (gathered from all ranks) -> incoming
+// state / adjoint of shard `me`.  One thread.
+// ---------------------------------------------------------------------------------------------
+template <int ND>
+__global__ void shard_state_kernel(const double* __restrict__ elems, int n_shards, int me, Sym2 P0,
+                                   double* __restrict__ s_out) {
+    using Elem = FwdElem<ND>;
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    Elem acc = fwd_identity<ND>();
+    for (int i = 0; i < me && i < n_shards; ++i) acc = fwd_combine<ND>(acc, load_elem<Elem>(elems + (size_t)i * Elem::NDBL));
+    State<ND> s0;
+    s0.P = P0;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) s0.a[d] = {0.0, 0.0};
+    const State<ND> s = fwd_apply<ND>(acc, s0);       // shard 0 begins with a track start: s0 is irrelevant
+#pragma unroll
+    for (int d = 0; d < ND; ++d) { s_out[2 * d] = s.a[d].x; s_out[2 * d + 1] = s.a[d].y; }
+    s_out[2 * ND] = s.P.a; s_out[2 * ND + 1] = s.P.b; s_out[2 * ND + 2] = s.P.c;
+}
+
+template <int ND>
+__global__ void shard_adjoint_kernel(const double* __restrict__ elems, int n_shards, int me,
+                                     double* __restrict__ g_out) {
+    using Elem = BwdElem<ND>;
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    Elem acc = bwd_identity<ND>();
+    for (int i = n_shards - 1; i > me; --i) acc = bwd_combine<ND>(load_elem<Elem>(elems + (size_t)i * Elem::NDBL), acc);
+    const Adj<ND> g = bwd_apply<ND>(acc, adj_zero<ND>());
+#pragma unroll
+    for (int d = 0; d < ND; ++d) { g_out[2 * d] = g.a[d].x; g_out[2 * d + 1] = g.a[d].y; }
+    g_out[2 * ND] = g.P.a; g_out[2 * ND + 1] = g.P.b; g_out[2 * ND + 2] = g.P.c;
 }
 
 }  // namespace ssde

@@ -69,6 +69,8 @@ struct ssde_handle {
     DevBuf par, theta, grad_theta, wg, ckpt, tile_llk, tile_gh, block_llk, part, out, sb;
     DevBuf f_status, f_agg, f_incl, b_status, b_agg, b_incl, counters;   // counters: ticket_f, ticket_b, error
     DevBuf aest;
+    DevBuf s_in, g_in;               // incoming state / adjoint of a time shard (2 n_dim + 3 doubles each)
+    bool have_s_in = false, have_g_in = false;
     double* h_pinned = nullptr;      // pinned host staging: par in, out back
     unsigned epoch = 0;
     int ntiles_f = 0, ntiles_b = 0, grid_lp = 0, grid_f = 0, grid_b = 0;
@@ -551,6 +553,8 @@ int finish_setup(ssde_handle* h) {
         h->nchunks = h->n_pad / LC;
         if ((rc = dev_alloc<double>(h->ckpt, (size_t)h->nchunks * (2 * nd + 3), err))) return rc;
         if ((rc = dev_alloc<double>(h->wg, (size_t)h->n_pad * 3, err))) return rc;
+        if ((rc = dev_alloc<double>(h->s_in, 2 * nd + 3, err))) return rc;
+        if ((rc = dev_alloc<double>(h->g_in, 2 * nd + 3, err))) return rc;
         if ((rc = dev_alloc<double>(h->tile_llk, h->n_pad / WT, err))) return rc;
         if ((rc = dev_alloc<double>(h->tile_gh, h->n_pad / WT, err))) return rc;
         if ((rc = dev_alloc<unsigned>(h->f_status, h->ntiles_f, err))) return rc;
@@ -606,14 +610,15 @@ DesignV2 design_of(const ssde_handle* h) {
 }
 
 template <int ND>
-int launch_ctcrw(ssde_handle* h, const double* d_par, int order, cudaStream_t st, double* aest) {
-    std::string& err = h->err;
+CtcrwArgs<ND> ctcrw_args(ssde_handle* h, const double* d_par, double* aest) {
     CtcrwArgs<ND> a;
     a.X = design_of(h);
     a.theta = h->theta.as<double>();
     a.obs = h->obs.as<double>(); a.dt = h->dt.as<double>(); a.flags = h->flags.as<uint8_t>();
     a.track_starts = h->track_starts.as<int64_t>(); a.a0 = h->a0.as<double>(); a.n_tracks = h->n_tracks;
-    a.P0 = h->P0; a.par = d_par; a.s_in = nullptr; a.g_in = nullptr;
+    a.P0 = h->P0; a.par = d_par;
+    a.s_in = h->have_s_in ? h->s_in.as<double>() : nullptr;
+    a.g_in = h->have_g_in ? h->g_in.as<double>() : nullptr;
     a.mu_zero = h->mu_zero.as<int>();
     a.ckpt = h->ckpt.as<double>(); a.nchunks = h->nchunks; a.wg = h->wg.as<double>();
     a.tile_llk = h->tile_llk.as<double>(); a.tile_gh = h->tile_gh.as<double>();
@@ -623,19 +628,63 @@ int launch_ctcrw(ssde_handle* h, const double* d_par, int order, cudaStream_t st
     a.fdesc = {h->f_status.as<unsigned>(), h->f_agg.as<double>(), h->f_incl.as<double>(), cnt + 0, cnt + 2, h->epoch};
     a.bdesc = {h->b_status.as<unsigned>(), h->b_agg.as<double>(), h->b_incl.as<double>(), cnt + 1, cnt + 2, h->epoch};
     a.ntiles = h->ntiles_f;
-    mark(h, st, "ctcrw_fwd");
+    a.summary = 0;
+    return a;
+}
+
+// the scan descriptors are keyed by an epoch so that they never need clearing; every kernel that
+// walks the tiles (full pass or summary pass) gets a fresh epoch and fresh tickets
+int new_scan_epoch(ssde_handle* h, cudaStream_t st) {
+    std::string& err = h->err;
+    ++h->epoch;
+    if (h->epoch >= (1u << 30)) h->epoch = 1;     // status arrays were zeroed at creation; 0 is never a live epoch
+    CUDA_TRY(cudaMemsetAsync(h->counters.p, 0, 2 * sizeof(unsigned), st));
+    return SSDE_OK;
+}
+
+template <int ND>
+int launch_ctcrw_fwd(ssde_handle* h, const double* d_par, cudaStream_t st, double* aest, bool summary) {
+    std::string& err = h->err;
+    int rc = new_scan_epoch(h, st);
+    if (rc) return rc;
+    CtcrwArgs<ND> a = ctcrw_args<ND>(h, d_par, aest);
+    a.summary = summary ? 1 : 0;
+    mark(h, st, summary ? "ctcrw_fwd_summary" : "ctcrw_fwd");
     ctcrw_fwd_kernel<ND, FWD_NT, FWD_MINB><<<h->grid_f, FWD_NT, sizeof(FwdSmem<ND, FWD_NT>), st>>>(a);
-    if (order >= 1) {
-        a.ntiles = h->ntiles_b;
-        mark(h, st, "ctcrw_bwd");
-        ctcrw_bwd_kernel<ND, BWD_NT, BWD_MINB><<<h->grid_b, BWD_NT, sizeof(BwdSmem<ND, BWD_NT>), st>>>(a);
-    }
+    CUDA_TRY(cudaGetLastError());
+    return SSDE_OK;
+}
+
+template <int ND>
+int launch_ctcrw_bwd(ssde_handle* h, const double* d_par, cudaStream_t st, bool summary) {
+    std::string& err = h->err;
+    int rc = new_scan_epoch(h, st);
+    if (rc) return rc;
+    CtcrwArgs<ND> a = ctcrw_args<ND>(h, d_par, nullptr);
+    a.ntiles = h->ntiles_b;
+    a.summary = summary ? 1 : 0;
+    mark(h, st, summary ? "ctcrw_bwd_summary" : "ctcrw_bwd");
+    ctcrw_bwd_kernel<ND, BWD_NT, BWD_MINB><<<h->grid_b, BWD_NT, sizeof(BwdSmem<ND, BWD_NT>), st>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    return SSDE_OK;
+}
+
+int launch_reduce(ssde_handle* h, int order, cudaStream_t st) {
+    std::string& err = h->err;
     mark(h, st, "reduce_tiles");
     reduce_tiles_kernel<<<RED_BLOCKS, 256, 0, st>>>(h->tile_llk.as<double>(), (int)(h->n_pad / WT),
                                                      order >= 1 ? h->tile_gh.as<double>() : nullptr, (int)(h->n_pad / WT),
                                                      h->part.as<double>());
     CUDA_TRY(cudaGetLastError());
     return SSDE_OK;
+}
+
+template <int ND>
+int launch_ctcrw(ssde_handle* h, const double* d_par, int order, cudaStream_t st, double* aest) {
+    int rc;
+    if ((rc = launch_ctcrw_fwd<ND>(h, d_par, st, aest, false))) return rc;
+    if (order >= 1 && (rc = launch_ctcrw_bwd<ND>(h, d_par, st, false))) return rc;
+    return launch_reduce(h, order, st);
 }
 
 template <int MODEL, int ND>
@@ -656,37 +705,28 @@ int launch_sde(ssde_handle* h, int order, cudaStream_t st) {
     return SSDE_OK;
 }
 
-int run_eval(ssde_handle* h, const double* d_par, int order, double* d_out, cudaStream_t st, double* aest) {
+int eval_prologue(ssde_handle* h, const double* d_par, int order, cudaStream_t st) {
     std::string& err = h->err;
-    if (order < 0 || order > 1) { err = "order must be 0 or 1 (Hessian not built yet)"; return SSDE_ERR_UNSUPPORTED; }
-    h->last_launches = 0;
-    h->pcount = 0;
-    ++h->epoch;
-    if (h->epoch >= (1u << 30)) h->epoch = 1;     // status arrays were zeroed at creation; 0 is never a live epoch
     const int p = h->p_fe + h->p_re;
-    CUDA_TRY(cudaMemsetAsync(h->counters.p, 0, 3 * sizeof(unsigned), st));
+    CUDA_TRY(cudaMemsetAsync(h->counters.as<unsigned>() + 2, 0, sizeof(unsigned), st));
     if (order >= 1) CUDA_TRY(cudaMemsetAsync(h->grad_theta.p, 0, sizeof(double) * std::max(p, 1), st));
     mark(h, st, "gather_theta");
     gather_theta_kernel<<<std::max((p + 255) / 256, 1), 256, 0, st>>>(d_par, h->theta.as<double>(), h->p_fe, h->p_re, h->o_fe, h->o_re,
                                                                      h->mu_cols.as<int32_t>(), h->n_mu_cols, h->mu_zero.as<int>());
-    int rc = SSDE_OK;
+    CUDA_TRY(cudaGetLastError());
+    return SSDE_OK;
+}
+
+int eval_epilogue(ssde_handle* h, const double* d_par, int order, double* d_out, cudaStream_t st) {
+    std::string& err = h->err;
     FinArgs f{};
     if (h->model == SSDE_CTCRW) {
-        rc = (h->n_dim == 1) ? launch_ctcrw<1>(h, d_par, order, st, aest) : launch_ctcrw<2>(h, d_par, order, st, aest);
         f.part_llk = h->part.as<double>(); f.n_part = RED_BLOCKS;
         f.tile_gh = (order >= 1) ? h->part.as<double>() + RED_BLOCKS : nullptr; f.n_gh = RED_BLOCKS;
     } else {
-        if (h->model == SSDE_BM) {
-            if (h->n_dim == 1) rc = launch_sde<MODEL_BM, 1>(h, order, st);
-            else if (h->n_dim == 2) rc = launch_sde<MODEL_BM, 2>(h, order, st);
-            else rc = launch_sde<MODEL_BM, 3>(h, order, st);
-        } else {
-            rc = (h->n_dim == 1) ? launch_sde<MODEL_OU, 1>(h, order, st) : launch_sde<MODEL_OU, 2>(h, order, st);
-        }
         f.part_llk = h->block_llk.as<double>(); f.n_part = h->grid_lp;
         f.tile_gh = nullptr; f.n_gh = 0;
     }
-    if (rc) return rc;
     f.par = d_par; f.grad_theta = h->grad_theta.as<double>();
     f.S_rowptr = h->S_rowptr.as<uint32_t>(); f.S_col = h->S_col.as<uint32_t>(); f.S_val = h->S_val.as<double>();
     f.sm_off = h->sm_off.as<int32_t>(); f.sb = h->sb.as<double>();
@@ -706,6 +746,33 @@ int run_eval(ssde_handle* h, const double* d_par, int order, double* d_out, cuda
     mark(h, st, nullptr);
     CUDA_TRY(cudaGetLastError());
     return SSDE_OK;
+}
+
+int run_eval(ssde_handle* h, const double* d_par, int order, double* d_out, cudaStream_t st, double* aest) {
+    std::string& err = h->err;
+    if (order < 0 || order > 1) { err = "order must be 0 or 1 (Hessian not built yet)"; return SSDE_ERR_UNSUPPORTED; }
+    if ((h->shard_flags & (SSDE_SHARD_CONT_PREV | SSDE_SHARD_CONT_NEXT)) &&
+        !((h->shard_flags & SSDE_SHARD_CONT_PREV) ? h->have_s_in : true)) {
+        err = "time shard: use ssde_eval_stage (the incoming state is unknown)";
+        return SSDE_ERR_BAD_ARG;
+    }
+    h->last_launches = 0;
+    h->pcount = 0;
+    int rc = eval_prologue(h, d_par, order, st);
+    if (rc) return rc;
+    if (h->model == SSDE_CTCRW) {
+        rc = (h->n_dim == 1) ? launch_ctcrw<1>(h, d_par, order, st, aest) : launch_ctcrw<2>(h, d_par, order, st, aest);
+    } else {
+        if (h->model == SSDE_BM) {
+            if (h->n_dim == 1) rc = launch_sde<MODEL_BM, 1>(h, order, st);
+            else if (h->n_dim == 2) rc = launch_sde<MODEL_BM, 2>(h, order, st);
+            else rc = launch_sde<MODEL_BM, 3>(h, order, st);
+        } else {
+            rc = (h->n_dim == 1) ? launch_sde<MODEL_OU, 1>(h, order, st) : launch_sde<MODEL_OU, 2>(h, order, st);
+        }
+    }
+    if (rc) return rc;
+    return eval_epilogue(h, d_par, order, d_out, st);
 }
 
 int check_common(int model, int n_dim, std::string& err) {
@@ -943,6 +1010,64 @@ int ssde_eval_device(ssde_handle* h, const double* d_par, int order, double* d_o
     int rc = run_eval(h, d_par, order, d_out, st, nullptr);
     if (rc) return rc;
     if (h->timed) CUDA_TRY(cudaEventRecord(h->ev1, st));
+    return SSDE_OK;
+}
+
+int ssde_shard_elem_doubles(const ssde_handle* h, int which) {
+    if (!h || h->model != SSDE_CTCRW) return -1;
+    if (which == 0) return h->n_dim == 1 ? FwdElem<1>::NDBL : FwdElem<2>::NDBL;
+    return h->n_dim == 1 ? BwdElem<1>::NDBL : BwdElem<2>::NDBL;
+}
+
+int ssde_eval_stage(ssde_handle* h, const double* d_par, int stage, const double* d_elems, int n_shards,
+                    int my_shard, double* d_out, void* stream) {
+    if (!h || !d_par) return SSDE_ERR_BAD_ARG;
+    std::string& err = h->err;
+    if (h->model != SSDE_CTCRW) { err = "time-sharded evaluation exists for CTCRW only"; return SSDE_ERR_UNSUPPORTED; }
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    const int nd = h->n_dim;
+    const size_t fe = (size_t)ssde_shard_elem_doubles(h, 0), be = (size_t)ssde_shard_elem_doubles(h, 1);
+    int rc = SSDE_OK;
+    if (stage == 0) {
+        // parameters -> theta; forward summary; composite element of the shard -> d_out[fe]
+        if (!d_out) return SSDE_ERR_BAD_ARG;
+        h->last_launches = 0; h->pcount = 0;
+        h->have_s_in = h->have_g_in = false;
+        if ((rc = eval_prologue(h, d_par, 1, st))) return rc;
+        rc = (nd == 1) ? launch_ctcrw_fwd<1>(h, d_par, st, nullptr, true) : launch_ctcrw_fwd<2>(h, d_par, st, nullptr, true);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync(d_out, h->f_incl.as<double>() + (size_t)(h->ntiles_f - 1) * fe, fe * sizeof(double),
+                                 cudaMemcpyDeviceToDevice, st));
+    } else if (stage == 1) {
+        // gathered forward elements -> incoming state; forward pass; adjoint summary -> d_out[be]
+        if (!d_elems || !d_out || my_shard < 0 || my_shard >= n_shards) return SSDE_ERR_BAD_ARG;
+        if (nd == 1) shard_state_kernel<1><<<1, 32, 0, st>>>(d_elems, n_shards, my_shard, h->P0, h->s_in.as<double>());
+        else shard_state_kernel<2><<<1, 32, 0, st>>>(d_elems, n_shards, my_shard, h->P0, h->s_in.as<double>());
+        ++h->last_launches;
+        h->have_s_in = true;
+        rc = (nd == 1) ? launch_ctcrw_fwd<1>(h, d_par, st, nullptr, false) : launch_ctcrw_fwd<2>(h, d_par, st, nullptr, false);
+        if (rc) return rc;
+        rc = (nd == 1) ? launch_ctcrw_bwd<1>(h, d_par, st, true) : launch_ctcrw_bwd<2>(h, d_par, st, true);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync(d_out, h->b_incl.as<double>() + (size_t)(h->ntiles_b - 1) * be, be * sizeof(double),
+                                 cudaMemcpyDeviceToDevice, st));
+    } else if (stage == 2) {
+        // gathered adjoint elements -> incoming adjoint; adjoint pass; finalize -> d_out[1 + n_par + 1]
+        if (!d_elems || !d_out || my_shard < 0 || my_shard >= n_shards) return SSDE_ERR_BAD_ARG;
+        if (nd == 1) shard_adjoint_kernel<1><<<1, 32, 0, st>>>(d_elems, n_shards, my_shard, h->g_in.as<double>());
+        else shard_adjoint_kernel<2><<<1, 32, 0, st>>>(d_elems, n_shards, my_shard, h->g_in.as<double>());
+        ++h->last_launches;
+        h->have_g_in = true;
+        rc = (nd == 1) ? launch_ctcrw_bwd<1>(h, d_par, st, false) : launch_ctcrw_bwd<2>(h, d_par, st, false);
+        if (rc) return rc;
+        if ((rc = launch_reduce(h, 1, st))) return rc;
+        if ((rc = eval_epilogue(h, d_par, 1, d_out, st))) return rc;
+    } else {
+        err = "stage must be 0, 1 or 2";
+        return SSDE_ERR_BAD_ARG;
+    }
+    CUDA_TRY(cudaGetLastError());
     return SSDE_OK;
 }
 

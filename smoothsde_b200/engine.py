@@ -164,6 +164,15 @@ class Engine:
                                         C.c_void_p(d_out_ptr), C.c_void_p(stream_ptr or 0))
         self._check(rc)
 
+    def shard_elem_doubles(self, which):
+        return int(self._lib.ssde_shard_elem_doubles(self._h, int(which)))
+
+    def eval_stage(self, stage, d_par_ptr, d_out_ptr, d_elems_ptr=0, n_shards=1, my_shard=0, stream_ptr=None):
+        """One stage of a time-sharded evaluation (see ssde_eval_stage); raw device pointers."""
+        rc = self._lib.ssde_eval_stage(self._h, C.c_void_p(d_par_ptr), int(stage), C.c_void_p(d_elems_ptr or 0),
+                                       int(n_shards), int(my_shard), C.c_void_p(d_out_ptr), C.c_void_p(stream_ptr or 0))
+        self._check(rc)
+
     def check(self):
         self._check(self._lib.ssde_check(self._h))
 
