@@ -12,7 +12,7 @@
  *   MakeADFunObject        :6          ssde_create        (copies the data list to the GPU once)
  *   EvalADFunObject        :8          ssde_eval          (order 0: nllk, order 1: + gradient)
  *   MakeADGradObject       :12         ssde_eval(order = 1)
- *   MakeADHessObject2      :13         ssde_eval(order = 2)   [reserved, not built yet]
+ *   MakeADHessObject2      :13         ssde_eval(order = 2), ssde_hvp, ssde_hess_cols_device
  *   REPORT(aest_all)                   ssde_report
  *   getParameterOrder      :11         ssde_n_par / ssde_par_layout
  *   (external pointer finalizer)       ssde_destroy
@@ -156,8 +156,11 @@ void ssde_destroy(ssde_handle* h);
 int ssde_n_par(const ssde_handle* h);
 int ssde_par_layout(const ssde_handle* h, int32_t offsets[4], int32_t sizes[4]);
 
-/* One objective evaluation with HOST buffers (what obj$fn / obj$gr do through EvalADFunObject).
- *   order 0: *nllk;  order 1: *nllk and grad[ssde_n_par];  order 2: reserved.
+/* One objective evaluation with HOST buffers (what obj$fn / obj$gr / obj$he do through
+ * EvalADFunObject and the MakeADHessObject2 tape).
+ *   order 0: *nllk;  order 1: *nllk and grad[ssde_n_par];
+ *   order 2: also hess[ssde_n_par x ssde_n_par] (column-major, symmetric): the exact joint Hessian
+ *            of the penalised objective, one tangent pass per column (see ssde_hvp).
  * Copies `par` to the device, runs the kernels, copies the result back, synchronises. */
 int ssde_eval(ssde_handle* h, const double* par, int order, double* nllk, double* grad, double* hess);
 
@@ -165,6 +168,23 @@ int ssde_eval(ssde_handle* h, const double* par, int order, double* nllk, double
  * part), d_out[1 .. n_par] = gradient.  `stream` is a cudaStream_t (NULL = the handle's own
  * stream).  Used by the multi-GPU host, which all-reduces d_out over NCCL. */
 int ssde_eval_device(ssde_handle* h, const double* d_par, int order, double* d_out, void* stream);
+/* Exact Hessian-vector products (second-order adjoint).  The kernels are templates over their
+ * scalar type; instantiated with (value, tangent) pairs, one forward + adjoint pass along a
+ * direction v of the parameter vector returns nllk, the gradient and H v, H the Hessian of the
+ * joint penalised objective -- what TMB obtains by taping the gradient tape again
+ * (MakeADHessObject2, src/init.c:13) and needs for the Laplace approximation over coeff_re
+ * (R/sde.R:522-524) and for obj$he (R/sde.R:1363).
+ *   ssde_hvp: HOST buffers; dirs = [n_par x n_dir] column-major directions; hv likewise = H dirs;
+ *             nllk / grad may be NULL.
+ *   ssde_hvp_device: DEVICE buffers, asynchronous on `stream`; d_out[1 + n_par + 1] as in
+ *             ssde_eval_device, d_hv[n_par] = H d_dir (this shard's part: sum over shards).
+ *   ssde_hess_cols_device: columns first .. first+count-1 of H into d_hess[n_par x count]
+ *             (column-major), e.g. the coeff_re block for the Laplace inner problem.
+ * Not available for time shards (SSDE_SHARD_CONT_*) yet: SSDE_ERR_UNSUPPORTED. */
+int ssde_hvp(ssde_handle* h, const double* par, int n_dir, const double* dirs, double* nllk, double* grad, double* hv);
+int ssde_hvp_device(ssde_handle* h, const double* d_par, const double* d_dir, double* d_out, double* d_hv, void* stream);
+int ssde_hess_cols_device(ssde_handle* h, const double* d_par, int first, int count, double* d_out, double* d_hess, void* stream);
+
 /* Time-sharded evaluation of ONE long CTCRW track whose rows are split along time over several
  * handles / ranks (shard_flags SSDE_SHARD_CONT_PREV / CONT_NEXT).  The filter and its adjoint are
  * associative scans, so each shard is summarised by one composite element; the host gathers the

@@ -115,6 +115,20 @@ class COracle:
         pieces = ([np.array([gsig.value])] if self.type == "CTCRW" else []) + [g_fe, g_ll, g_re]
         return nllk, np.concatenate(pieces)
 
+    def hessian(self, par, k=1e-3):
+        """Joint Hessian of the penalised objective: Richardson-extrapolated central differences
+        (error O(k^4)) of the analytic gradient above.  TMB gets it by AD-of-AD."""
+        par = np.asarray(par, dtype=float)
+        n = par.size
+        H = np.empty((n, n))
+        for j in range(n):
+            e = np.zeros(n)
+            e[j] = 1.0
+            d1 = (self.eval(par + k * e)[1] - self.eval(par - k * e)[1]) / (2 * k)
+            d2 = (self.eval(par + 0.5 * k * e)[1] - self.eval(par - 0.5 * k * e)[1]) / k
+            H[:, j] = (4 * d2 - d1) / 3
+        return 0.5 * (H + H.T)
+
     def aest(self, par):
         L = lib()
         p = O.split_par(self.dat, np.asarray(par, dtype=float))

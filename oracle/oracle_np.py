@@ -315,3 +315,22 @@ def grad_complex_step(dat, par, h=1e-30):
         z[j] += 1j * h
         g[j] = np.imag(nllk(dat, z)) / h
     return g
+
+
+def hess_complex_fd(dat, par, k=1e-3, h=1e-30):
+    """Hessian of nllk(dat, .): complex-step first derivative (exact to rounding), Richardson-
+    extrapolated central difference of it in the second direction (error O(k^4))."""
+    par = np.asarray(par, dtype=float)
+    n = par.size
+    H = np.empty((n, n))
+
+    def g(p):
+        return grad_complex_step(dat, p, h)
+
+    for j in range(n):
+        e = np.zeros(n)
+        e[j] = 1.0
+        d1 = (g(par + k * e) - g(par - k * e)) / (2 * k)
+        d2 = (g(par + 0.5 * k * e) - g(par - 0.5 * k * e)) / k
+        H[:, j] = (4 * d2 - d1) / 3
+    return 0.5 * (H + H.T)

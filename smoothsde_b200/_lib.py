@@ -71,7 +71,8 @@ EXPORTS = ["ssde_create", "ssde_create_packed", "ssde_destroy", "ssde_n_par", "s
            "ssde_last_eval_launches", "ssde_set_profile", "ssde_last_kernel_times", "ssde_last_error", "ssde_create_error", "ssde_version",
            "ssde_padded_rows", "ssde_layout_info", "ssde_pack_host", "ssde_pack_free",
            "ssde_simulate_ctcrw", "ssde_launch_info",
-           "ssde_shard_elem_doubles", "ssde_eval_stage"]
+           "ssde_shard_elem_doubles", "ssde_eval_stage",
+           "ssde_hvp", "ssde_hvp_device", "ssde_hess_cols_device"]
 
 
 def load():
@@ -131,6 +132,12 @@ def load():
     lib.ssde_shard_elem_doubles.restype = C.c_int
     lib.ssde_eval_stage.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.c_int, vp, vp]
     lib.ssde_eval_stage.restype = C.c_int
+    lib.ssde_hvp.argtypes = [vp, c_double_p, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p]
+    lib.ssde_hvp.restype = C.c_int
+    lib.ssde_hvp_device.argtypes = [vp, vp, vp, vp, vp, vp]
+    lib.ssde_hvp_device.restype = C.c_int
+    lib.ssde_hess_cols_device.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp, vp]
+    lib.ssde_hess_cols_device.restype = C.c_int
     lib.ssde_version.argtypes = []
     lib.ssde_version.restype = C.c_char_p
     _lib = lib

@@ -77,20 +77,20 @@ __device__ __forceinline__ E load_elem_cg(const double* src) {
 // Time-ordered composition traits.  join(far, near): `near` covers tiles closer (in processing
 // order) to the current one.  Forward scan processes tiles in time order, so far = earlier in
 // time; the adjoint scan processes tiles in reverse time, so far = later in time.
-template <int ND>
+template <int ND, class R = double>
 struct FwdOps {
-    using Elem = FwdElem<ND>;
-    static __device__ __forceinline__ Elem identity() { return fwd_identity<ND>(); }
+    using Elem = FwdElem<ND, R>;
+    static __device__ __forceinline__ Elem identity() { return fwd_identity<ND, R>(); }
     static __device__ __forceinline__ Elem join(const Elem& far, const Elem& near) {
-        return fwd_combine<ND>(far, near);
+        return fwd_combine<ND, R>(far, near);
     }
 };
-template <int ND>
+template <int ND, class R = double>
 struct BwdOps {
-    using Elem = BwdElem<ND>;
-    static __device__ __forceinline__ Elem identity() { return bwd_identity<ND>(); }
+    using Elem = BwdElem<ND, R>;
+    static __device__ __forceinline__ Elem identity() { return bwd_identity<ND, R>(); }
     static __device__ __forceinline__ Elem join(const Elem& far, const Elem& near) {
-        return bwd_combine<ND>(near, far);     // near = earlier rows (E1), far = later rows (E2)
+        return bwd_combine<ND, R>(near, far);  // near = earlier rows (E1), far = later rows (E2)
     }
 };
 
@@ -101,6 +101,10 @@ __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
     return v;
+}
+
+__device__ __forceinline__ Dual warp_sum(Dual v) {
+    return Dual(warp_sum(v.v), warp_sum(v.d));
 }
 
 // Sum over a block of NT threads; result valid in thread 0.  `red` has NT/32 doubles.

@@ -22,6 +22,8 @@
 //     Otherwise columns are stored per nonzero with the same indexing as val.
 #pragma once
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace ssde {
@@ -61,18 +63,32 @@ __device__ __forceinline__ int slots_of(uint32_t kmax) {
     return (int)((kmax & 255u) + ((kmax >> 8) & 255u) + ((kmax >> 16) & 255u) + (kmax >> 24));
 }
 
+// The coefficient vector theta = [coeff_fe | coeff_re] and, for the tangent pass (R = Dual), the
+// direction it is differentiated along.
+struct Theta {
+    const double* v;
+    const double* d;               // nullptr unless R = Dual
+};
+template <class R>
+__device__ __forceinline__ R theta_at(const Theta& t, uint32_t c) {
+    if constexpr (std::is_same<R, double>::value) return __ldg(t.v + c);
+    else return Dual(__ldg(t.v + c), __ldg(t.d + c));
+}
+
 // Per-warp view of one warp-tile's design.
-struct WtView {
+template <class R>
+struct WtViewT {
     const double* blk;             // val + val_off
     const double* v;               // val + val_off + lane
     const uint32_t* c;             // col + col_off (+ lane if not uniform)
-    const double* th;              // per-warp theta cache (shared memory) or nullptr
+    const R* th;                   // per-warp theta cache (shared memory) or nullptr
     int th_pad;                    // 16: parameter p's cached thetas start at th[16 p]; 0: contiguous
     uint32_t kmax;
     int S;
     bool uniform;
     bool staged;                   // row-steps are fetched with TMA bulk copies (uniform, 0 < S <= STAGE_SLOTS)
 };
+using WtView = WtViewT<double>;
 
 // Per-warp staging buffer for the values of one row-step (S x 32 doubles, slot-major) and the
 // mbarrier its TMA copies complete on.
@@ -88,11 +104,12 @@ __device__ __forceinline__ void stage_init(WarpStage& st, double* buf, uint64_t*
 }
 
 // Called by all lanes of a warp.  `th_cache` is this warp's TH_CACHE doubles of shared memory.
-__device__ __forceinline__ WtView open_warptile(const DesignV2& X, int64_t q, const double* __restrict__ theta,
-                                                double* th_cache, bool want_theta = true) {
+template <class R>
+__device__ __forceinline__ WtViewT<R> open_warptile(const DesignV2& X, int64_t q, const Theta& theta,
+                                                   R* th_cache, bool want_theta = true) {
     const int lane = threadIdx.x & 31;
     const WtDesc d = X.desc[q];
-    WtView w;
+    WtViewT<R> w;
     w.kmax = d.kmax;
     w.S = slots_of(d.kmax);
     w.uniform = (d.flags & WT_UNIFORM) != 0;
@@ -113,7 +130,7 @@ __device__ __forceinline__ WtView open_warptile(const DesignV2& X, int64_t q, co
 #pragma unroll
         for (int p = 0; p < MAX_NP; ++p) {
             const int kp = (int)((d.kmax >> (8 * p)) & 255u);
-            if (lane < kp) th_cache[16 * p + lane] = __ldg(theta + __ldg(w.c + j0 + lane));
+            if (lane < kp) th_cache[16 * p + lane] = theta_at<R>(theta, __ldg(w.c + j0 + lane));
             j0 += kp;
         }
         __syncwarp();
@@ -121,7 +138,7 @@ __device__ __forceinline__ WtView open_warptile(const DesignV2& X, int64_t q, co
         w.th_pad = 16;
     } else if (w.uniform && w.S <= TH_CACHE) {
         __syncwarp();
-        for (int j = lane; j < w.S; j += 32) th_cache[j] = __ldg(theta + __ldg(w.c + j));
+        for (int j = lane; j < w.S; j += 32) th_cache[j] = theta_at<R>(theta, __ldg(w.c + j));
         __syncwarp();
         w.th = th_cache;
     }
@@ -131,7 +148,8 @@ __device__ __forceinline__ WtView open_warptile(const DesignV2& X, int64_t q, co
 
 // lane 0: start the copy of row-step k of the warp-tile into the staging buffer.  The caller has
 // made sure (with __syncwarp) that no lane still reads the buffer.
-__device__ __forceinline__ void stage_issue(const WtView& w, const WarpStage& st, int k) {
+template <class R>
+__device__ __forceinline__ void stage_issue(const WtViewT<R>& w, const WarpStage& st, int k) {
     const unsigned bytes = (unsigned)w.S * 32u * 8u;
     fence_proxy_async();
     mbar_expect_tx(st.bar, bytes);
@@ -143,6 +161,25 @@ __device__ __forceinline__ void stage_wait(WarpStage& st) {
 }
 
 // eta[p] of this lane's row from the staged row-step
+template <int NP>
+__device__ __forceinline__ void row_eta_staged(const WtViewT<Dual>& w, const WarpStage& st, Dual* eta) {
+    const double* v = st.buf + (threadIdx.x & 31);
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+        const int kp = (int)((w.kmax >> (8 * p)) & 255u);
+        const Dual* th = w.th + 16 * p;
+        Dual acc0 = 0.0, acc1 = 0.0;
+        int i = 0;
+#pragma unroll 1
+        for (; i + 2 <= kp; i += 2) {
+            acc0 = fmad(v[0], th[i], acc0);
+            acc1 = fmad(v[32], th[i + 1], acc1);
+            v += 64;
+        }
+        if (i < kp) { acc0 = fmad(v[0], th[i], acc0); v += 32; }
+        eta[p] = acc0 + acc1;
+    }
+}
 template <int NP>
 __device__ __forceinline__ void row_eta_staged(const WtView& w, const WarpStage& st, double* eta) {
     const double* v = st.buf + (threadIdx.x & 31);
@@ -174,8 +211,8 @@ __device__ __forceinline__ void row_eta_staged(const WtView& w, const WarpStage&
 }
 
 // eta[p] for the first NPRE parameters only, straight from global memory (row k of this lane)
-template <int NPRE>
-__device__ __forceinline__ void row_eta_prefix(const WtView& w, int k, const double* __restrict__ theta, double* eta) {
+template <int NPRE, class R>
+__device__ __forceinline__ void row_eta_prefix(const WtViewT<R>& w, int k, const Theta& theta, R* eta) {
     const double* v = w.v + (size_t)k * w.S * 32;
     const uint32_t* c = w.c + (w.uniform ? 0 : (size_t)k * w.S * 32);
     const int cs = w.uniform ? 1 : 32;
@@ -183,27 +220,27 @@ __device__ __forceinline__ void row_eta_prefix(const WtView& w, int k, const dou
 #pragma unroll
     for (int p = 0; p < NPRE; ++p) {
         const int kp = (int)((w.kmax >> (8 * p)) & 255u);
-        double acc = 0.0;
+        R acc = 0.0;
         for (int i = 0; i < kp; ++i, ++j) {
-            const double t = w.th ? w.th[w.th_pad ? 16 * p + i : j] : __ldg(theta + __ldg(c + j * cs));
-            acc = fma(__ldg(v + j * 32), t, acc);
+            const R t = w.th ? w.th[w.th_pad ? 16 * p + i : j] : theta_at<R>(theta, __ldg(c + j * cs));
+            acc = fmad(__ldg(v + j * 32), t, acc);
         }
         eta[p] = acc;
     }
 }
 
 // eta[p] = sum over parameter p's slots of row k of this lane.
-template <int NP>
-__device__ __forceinline__ void row_eta(const WtView& w, int k, const double* __restrict__ theta, double* eta) {
+template <int NP, class R>
+__device__ __forceinline__ void row_eta(const WtViewT<R>& w, int k, const Theta& theta, R* eta) {
     const double* v = w.v + (size_t)k * w.S * 32;
     int j = 0;
     if (w.th) {
 #pragma unroll
         for (int p = 0; p < NP; ++p) {
             const int kp = (int)((w.kmax >> (8 * p)) & 255u);
-            double acc = 0.0;
+            R acc = 0.0;
 #pragma unroll 4
-            for (int i = 0; i < kp; ++i, ++j) acc = fma(__ldg(v + j * 32), w.th[w.th_pad ? 16 * p + i : j], acc);
+            for (int i = 0; i < kp; ++i, ++j) acc = fmad(__ldg(v + j * 32), w.th[w.th_pad ? 16 * p + i : j], acc);
             eta[p] = acc;
         }
     } else {
@@ -212,8 +249,8 @@ __device__ __forceinline__ void row_eta(const WtView& w, int k, const double* __
 #pragma unroll
         for (int p = 0; p < NP; ++p) {
             const int kp = (int)((w.kmax >> (8 * p)) & 255u);
-            double acc = 0.0;
-            for (int i = 0; i < kp; ++i, ++j) acc = fma(__ldg(v + j * 32), __ldg(theta + __ldg(c + j * cs)), acc);
+            R acc = 0.0;
+            for (int i = 0; i < kp; ++i, ++j) acc = fmad(__ldg(v + j * 32), theta_at<R>(theta, __ldg(c + j * cs)), acc);
             eta[p] = acc;
         }
     }
@@ -224,21 +261,40 @@ __device__ __forceinline__ void row_eta(const WtView& w, int k, const double* __
 // parameter p.  Per-CTA accumulators `sgrad` (shared memory, npc doubles, flushed by the caller)
 // are used when the parameter vector fits, global atomics otherwise.
 // ---------------------------------------------------------------------------------------------
-struct GradAcc {
-    double* sgrad;                 // shared-memory accumulators or nullptr
-    double* ggrad;                 // global gradient w.r.t. theta
+template <class R>
+struct GradAccT {
+    R* sgrad;                      // shared-memory accumulators or nullptr
+    double* ggrad;                 // global gradient w.r.t. theta; R = Dual: tangents at ggrad[p_theta + c]
+    int p_theta;
 };
+using GradAcc = GradAccT<double>;
 
 __device__ __forceinline__ void grad_add(const GradAcc& g, uint32_t c, double v) {
     if (g.sgrad) atomicAdd(g.sgrad + c, v);
     else atomicAdd(g.ggrad + c, v);
 }
+__device__ __forceinline__ void grad_add(const GradAccT<Dual>& g, uint32_t c, const Dual& v) {
+    if (g.sgrad) { atomicAdd(&g.sgrad[c].v, v.v); atomicAdd(&g.sgrad[c].d, v.d); }
+    else { atomicAdd(g.ggrad + c, v.v); atomicAdd(g.ggrad + g.p_theta + c, v.d); }
+}
+// flush the per-CTA accumulators (all threads of the CTA, after a __syncthreads)
+template <class R>
+__device__ __forceinline__ void grad_flush(const GradAccT<R>& g, int nthreads) {
+    if (!g.sgrad) return;
+    for (int i = threadIdx.x; i < g.p_theta; i += nthreads) {
+        const R v = g.sgrad[i];
+        if (value(v) != 0.0) atomicAdd(g.ggrad + i, value(v));
+        if constexpr (!std::is_same<R, double>::value) { if (v.d != 0.0) atomicAdd(g.ggrad + g.p_theta + i, v.d); }
+    }
+}
+__device__ __forceinline__ bool nonzero(double x) { return x != 0.0; }
+__device__ __forceinline__ bool nonzero(const Dual& x) { return x.v != 0.0 || x.d != 0.0; }
 
 // Uniform warp-tile: per-lane partial sums over the LC rows go to a per-warp scratch T(j, lane)
 // in shared memory (accessor `T`), then lane j adds up row j of T -- no shuffles, one atomic per
 // slot.  The caller guarantees that T has room for w.S slots.
-template <int NP, class EB, class TA>
-__device__ __forceinline__ void scatter_warptile_transposed(const WtView& w, const GradAcc& g, EB eb, TA T) {
+template <int NP, class R, class EB, class TA>
+__device__ __forceinline__ void scatter_warptile_transposed(const WtViewT<R>& w, const GradAccT<R>& g, EB eb, TA T) {
     const int lane = threadIdx.x & 31;
     const size_t ks = (size_t)w.S * 32;
     const double* vj = w.v;
@@ -247,7 +303,7 @@ __device__ __forceinline__ void scatter_warptile_transposed(const WtView& w, con
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
         const int kp = (int)((w.kmax >> (8 * p)) & 255u);
-        double e[LC];
+        R e[LC];
 #pragma unroll
         for (int k = 0; k < LC; ++k) e[k] = eb(k, p);
         // 4 slots x LC rows = 32 independent loads in flight per batch
@@ -260,9 +316,9 @@ __device__ __forceinline__ void scatter_warptile_transposed(const WtView& w, con
                 for (int k = 0; k < LC; ++k) v[u][k] = (i + u < kp) ? __ldg(vj + u * 32 + k * ks) : 0.0;
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                double acc = 0.0;
+                R acc = 0.0;
 #pragma unroll
-                for (int k = 0; k < LC; ++k) acc = fma(v[u][k], e[k], acc);
+                for (int k = 0; k < LC; ++k) acc = fmad(v[u][k], e[k], acc);
                 if (i + u < kp) T(j + u, lane) = acc;
             }
             vj += 128;
@@ -277,7 +333,7 @@ __device__ __forceinline__ void scatter_warptile_transposed(const WtView& w, con
     }
     __syncwarp();
     for (int jj = lane; jj < w.S; jj += 32) {
-        double s0 = 0.0, s1 = 0.0;
+        R s0 = 0.0, s1 = 0.0;
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
             s0 += T(jj, (i + lane) & 31);
@@ -288,29 +344,29 @@ __device__ __forceinline__ void scatter_warptile_transposed(const WtView& w, con
     __syncwarp();
 }
 
-template <int NP, class EB>
-__device__ __forceinline__ void scatter_warptile(const WtView& w, const GradAcc& g, EB eb) {
+template <int NP, class R, class EB>
+__device__ __forceinline__ void scatter_warptile(const WtViewT<R>& w, const GradAccT<R>& g, EB eb) {
     const int lane = threadIdx.x & 31;
     int j = 0;
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
         const int kp = (int)((w.kmax >> (8 * p)) & 255u);
-        double e[LC];
+        R e[LC];
 #pragma unroll
         for (int k = 0; k < LC; ++k) e[k] = eb(k, p);
         for (int i = 0; i < kp; ++i, ++j) {
             if (w.uniform) {
-                double acc = 0.0;
+                R acc = 0.0;
 #pragma unroll
-                for (int k = 0; k < LC; ++k) acc = fma(__ldg(w.v + ((size_t)k * w.S + j) * 32), e[k], acc);
+                for (int k = 0; k < LC; ++k) acc = fmad(__ldg(w.v + ((size_t)k * w.S + j) * 32), e[k], acc);
                 acc = warp_sum(acc);
                 if (lane == 0) grad_add(g, __ldg(w.c + j), acc);
             } else {
 #pragma unroll
                 for (int k = 0; k < LC; ++k) {
                     const size_t o = ((size_t)k * w.S + j) * 32;
-                    const double t = __ldg(w.v + o) * e[k];
-                    if (t != 0.0) grad_add(g, __ldg(w.c + o), t);
+                    const R t = __ldg(w.v + o) * e[k];
+                    if (nonzero(t)) grad_add(g, __ldg(w.c + o), t);
                 }
             }
         }

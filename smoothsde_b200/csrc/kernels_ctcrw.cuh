@@ -20,10 +20,10 @@
 
 namespace ssde {
 
-template <int ND>
+template <int ND, class R = double>
 struct CtcrwArgs {
     DesignV2 X;
-    const double* theta;       // [coeff_fe | coeff_re]
+    Theta theta;               // [coeff_fe | coeff_re] (+ direction for the tangent pass)
     const double* obs;         // ND planes of n_pad doubles, permuted (design.cuh), NA replaced by 0
     const double* dt;          // [n_pad] permuted
     const uint8_t* flags;      // [n_pad] permuted, 0xff beyond the end
@@ -32,15 +32,17 @@ struct CtcrwArgs {
     int n_tracks;
     Sym2 P0;
     const double* par;         // device parameter vector; par[0] = log_sigma_obs
-    const double* s_in;        // optional incoming state (2*ND + 3 doubles) for a continued shard
-    const double* g_in;        // optional incoming adjoint (2*ND + 3 doubles)
+    const double* par_dot;     // R = Dual: direction in the parameter vector (else nullptr)
+    const R* s_in;             // optional incoming state (2*ND + 3 scalars) for a continued shard
+    const R* g_in;             // optional incoming adjoint (2*ND + 3 scalars)
     const int* mu_zero;        // device flag: every mu_d predictor is exactly 0 at these parameters
-    double* wg;                // [3, n_pad] permuted: tau, e = exp(-dt/tau), s2 of every row (forward -> adjoint)
-    double* ckpt;              // [(2*ND+3), nchunks] start state of every thread chunk
+    R* wg;                     // [3, n_pad] permuted: tau, e = exp(-dt/tau), s2 of every row (forward -> adjoint)
+    R* ckpt;                   // [(2*ND+3), nchunks] start state of every thread chunk
     int64_t nchunks;           // n_pad / LC
     double* tile_llk;          // [n_pad / WT] one partial log-likelihood per warp-tile
-    double* tile_gh;           // [n_pad / WT] one partial d nllk / d h per warp-tile
-    double* grad_theta;        // [p_theta], accumulated with atomics
+    double* tile_gh;           // [n_pad / WT] one partial d nllk / d h per warp-tile; R = Dual: the
+                               // tangents follow at tile_gh[n_pad / WT + q]
+    double* grad_theta;        // [p_theta] (R = Dual: [2 p_theta], tangents second), accumulated with atomics
     int p_theta;
     double* aest;              // optional [n, 2*ND]: REPORT(aest_all), nllk_ctcrw.hpp:246-249
     ScanDesc fdesc, bdesc;
@@ -51,19 +53,25 @@ struct CtcrwArgs {
 
 // Start state of the track whose first row carries track index `idx` (stored, as a double, in
 // the otherwise unused dt slot of track-start rows).
-template <int ND>
-__device__ __forceinline__ State<ND> track_start_state(const CtcrwArgs<ND>& a, double idx) {
-    State<ND> s;
+template <int ND, class R>
+__device__ __forceinline__ State<ND, R> track_start_state(const CtcrwArgs<ND, R>& a, double idx) {
+    State<ND, R> s;
     const double* p = a.a0 + (size_t)idx * 2 * ND;
 #pragma unroll
     for (int d = 0; d < ND; ++d) s.a[d] = {p[2 * d], p[2 * d + 1]};
-    s.P = a.P0;
+    s.P = {a.P0.a, a.P0.b, a.P0.c};
     return s;
 }
 
-template <int ND>
-__device__ __forceinline__ State<ND> load_state(const double* p) {
-    State<ND> s;
+// h = sigma_obs^2 = exp(2 log_sigma_obs), nllk_ctcrw.hpp:136,167
+template <int ND, class R>
+__device__ __forceinline__ R obs_variance(const CtcrwArgs<ND, R>& a) {
+    return exp(2.0 * ScalarOf<R>::make(a.par[0], a.par_dot ? a.par_dot[0] : 0.0));
+}
+
+template <int ND, class R>
+__device__ __forceinline__ State<ND, R> load_state(const R* p) {
+    State<ND, R> s;
 #pragma unroll
     for (int d = 0; d < ND; ++d) s.a[d] = {p[2 * d], p[2 * d + 1]};
     s.P = {p[2 * ND], p[2 * ND + 1], p[2 * ND + 2]};
@@ -81,32 +89,34 @@ __device__ __forceinline__ unsigned long long load_flags8(const uint8_t* __restr
 // ---------------------------------------------------------------------------------------------
 // forward kernel
 // ---------------------------------------------------------------------------------------------
-template <int ND, int NT>
+template <int ND, int NT, class R = double>
 struct FwdSmem {
     static constexpr int NC = 5;                 // T12, e, Qa, Qb, Qc
-    double W[LC][NC][NT];
+    static constexpr int ES = 24 * ScalarOf<R>::NDBL;
+    R W[LC][NC][NT];
     double stage[NT / 32][STAGE_DBL];
-    double wagg[2][NT / 32][24];     // shared scratch is double-buffered by tile parity: the only
-    double tagg[2][24];              // barrier between two tiles is the one that hands out the ticket
-    double misc[2][16];
-    double th[NT / 32][TH_CACHE];
+    double wagg[2][NT / 32][ES];     // shared scratch is double-buffered by tile parity: the only
+    double tagg[2][ES];              // barrier between two tiles is the one that hands out the ticket
+    R misc[2][16];
+    R th[NT / 32][TH_CACHE];
     uint64_t bar[NT / 32];
     int ticket[2];
 };
 
-template <int ND, int NT, int MINB>
-__global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(CtcrwArgs<ND> a) {
-    using SM = FwdSmem<ND, NT>;
-    using Ops = FwdOps<ND>;
-    using Elem = FwdElem<ND>;
+template <int ND, int NT, int MINB, class R = double>
+__global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(CtcrwArgs<ND, R> a) {
+    using SM = FwdSmem<ND, NT, R>;
+    using Ops = FwdOps<ND, R>;
+    using Elem = FwdElem<ND, R>;
+    using St = State<ND, R>;
     constexpr int NWARP = NT / 32;
     constexpr int NP = ND + 2;
-    static_assert(Elem::NDBL <= 24, "element too large for the shared staging area");
+    static_assert(Elem::NDBL <= SM::ES, "element too large for the shared staging area");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SM& sm = *reinterpret_cast<SM*>(smem_raw);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const double h = exp(2.0 * a.par[0]);               // H = sigma_obs^2 I, nllk_ctcrw.hpp:136,167
+    const R h = obs_variance(a);                        // H = sigma_obs^2 I, nllk_ctcrw.hpp:136,167
     const bool mu0 = *a.mu_zero != 0;
     WarpStage st;
     stage_init(st, sm.stage[warp], &sm.bar[warp]);
@@ -123,12 +133,12 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(CtcrwArgs<ND> a) {
         const int64_t q = (int64_t)tile * NWARP + warp;
         const int64_t base = q * WT + lane;
         const int64_t row0 = q * WT + (int64_t)lane * LC;
-        const WtView w = open_warptile(a.X, q, a.theta, sm.th[warp], true);
+        const WtViewT<R> w = open_warptile<R>(a.X, q, a.theta, sm.th[warp], true);
         if (w.staged && lane == 0) stage_issue(w, st, 0);
         const unsigned long long fl = load_flags8(a.flags, base);
 
         // (1) thread element over its LC rows
-        Elem E = fwd_identity<ND>();
+        Elem E = fwd_identity<ND, R>();
 #pragma unroll 1
         for (int k = 0; k < LC; ++k) {
             const int64_t pos = base + k * 32;
@@ -139,7 +149,7 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(CtcrwArgs<ND> a) {
             double y[ND];
 #pragma unroll
             for (int d = 0; d < ND; ++d) y[d] = step ? a.obs[(size_t)d * a.X.n_pad + pos] : 0.0;
-            double eta[NP];
+            R eta[NP];
             if (w.staged) {
                 stage_wait(st);
                 row_eta_staged<NP>(w, st, eta);
@@ -149,10 +159,10 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(CtcrwArgs<ND> a) {
                 row_eta<NP>(w, k, a.theta, eta);
             }
             if (step) {
-                double tau, e, s2;
+                R tau, e, s2;
                 transform_row(eta[ND], eta[ND + 1], dtv, tau, e, s2);
                 a.wg[pos] = tau; a.wg[a.X.n_pad + pos] = e; a.wg[2 * a.X.n_pad + pos] = s2;
-                const StepPar sp = make_step(tau, e, s2, dtv);
+                const StepParT<R> sp = make_step(tau, e, s2, dtv);
                 sm.W[k][0][tid] = sp.T12; sm.W[k][1][tid] = sp.e;
                 sm.W[k][2][tid] = sp.Q.a; sm.W[k][3][tid] = sp.Q.b; sm.W[k][4][tid] = sp.Q.c;
                 fwd_append<ND>(E, sp, y, eta, (f & ROW_OBS) != 0, h);
@@ -169,7 +179,7 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(CtcrwArgs<ND> a) {
         }
         if (lane == 31) store_elem(sm.wagg[par][warp], inc);
         Elem exc = shfl_up_elem(inc, 1);
-        if (lane == 0) exc = fwd_identity<ND>();
+        if (lane == 0) exc = fwd_identity<ND, R>();
         __syncthreads();
         // (3) the last warp composes and publishes the tile aggregate while warp 0 looks back over
         //     the earlier tiles; warp 0 then publishes the inclusive prefix and the tile start state
@@ -184,12 +194,12 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(CtcrwArgs<ND> a) {
             pre = lookback<Ops>(a.fdesc, tile);
             if (lane == 0) {
                 // state at the first row of the tile
-                State<ND> s0;
-                if (a.s_in) s0 = load_state<ND>(a.s_in);
-                else { s0.P = a.P0;
+                St s0;
+                if (a.s_in) s0 = load_state<ND, R>(a.s_in);
+                else { s0.P = {a.P0.a, a.P0.b, a.P0.c};
 #pragma unroll
                     for (int d = 0; d < ND; ++d) s0.a[d] = {0.0, 0.0}; }
-                const State<ND> st0 = fwd_apply<ND>(pre, s0);
+                const St st0 = fwd_apply<ND>(pre, s0);
 #pragma unroll
                 for (int d = 0; d < ND; ++d) { sm.misc[par][2 * d] = st0.a[d].x; sm.misc[par][2 * d + 1] = st0.a[d].y; }
                 sm.misc[par][2 * ND] = st0.P.a; sm.misc[par][2 * ND + 1] = st0.P.b; sm.misc[par][2 * ND + 2] = st0.P.c;
@@ -199,7 +209,7 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(CtcrwArgs<ND> a) {
         if (warp == 0 && lane == 0) publish_incl<Ops>(a.fdesc, tile, fwd_combine<ND>(pre, load_elem<Elem>(sm.tagg[par])));
         if (a.summary) continue;
         // (4) exact start state of this thread, checkpoint, plain filter re-run
-        State<ND> s = load_state<ND>(sm.misc[par]);
+        St s = load_state<ND, R>(sm.misc[par]);
 #pragma unroll 1
         for (int ww = 0; ww < warp; ++ww) s = fwd_apply<ND>(load_elem<Elem>(sm.wagg[par][ww]), s);
         s = fwd_apply<ND>(exc, s);
@@ -216,7 +226,7 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(CtcrwArgs<ND> a) {
         }
         // sum_i log F_i is taken as the log of a running product (one log per chunk instead of
         // one per row); the product is folded into `slog` whenever it leaves a safe range.
-        double quad = 0.0, fprod = 1.0, slog = 0.0;
+        R quad = 0.0, fprod = 1.0, slog = 0.0;
 #pragma unroll 1
         for (int k = 0; k < LC; ++k) {
             const uint8_t f = (uint8_t)(fl >> (8 * k));
@@ -226,29 +236,30 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(CtcrwArgs<ND> a) {
             if (f & ROW_START) {
                 s = track_start_state<ND>(a, dtv);
             } else {
-                double mu[ND], y[ND];
+                R mu[ND];
+                double y[ND];
 #pragma unroll
                 for (int d = 0; d < ND; ++d) mu[d] = 0.0;
                 if (!mu0) row_eta_prefix<ND>(w, k, a.theta, mu);
 #pragma unroll
                 for (int d = 0; d < ND; ++d) y[d] = a.obs[(size_t)d * a.X.n_pad + pos];
-                StepPar sp;
+                StepParT<R> sp;
                 sp.T12 = sm.W[k][0][tid]; sp.e = sm.W[k][1][tid];
                 sp.Q.a = sm.W[k][2][tid]; sp.Q.b = sm.W[k][3][tid]; sp.Q.c = sm.W[k][4][tid];
                 sp.B1 = dtv - sp.T12; sp.B2 = 1.0 - sp.e;      // makeB_ctcrw, :87-88
-                double F, qd;
+                R F, qd;
                 fwd_step_q<ND, false>(s, sp, y, mu, (f & ROW_OBS) != 0, h, nullptr, F, qd);
                 quad += qd;
                 fprod *= F;
-                if (!(fprod > 1e-150 && fprod < 1e150)) { slog += log(fprod); fprod = 1.0; }
+                if (!(value(fprod) > 1e-150 && value(fprod) < 1e150)) { slog += log(fprod); fprod = 1.0; }
             }
             if (a.aest) {
                 double* o = a.aest + (size_t)(row0 + k) * (2 * ND);
 #pragma unroll
-                for (int d = 0; d < ND; ++d) { o[2 * d] = s.a[d].x; o[2 * d + 1] = s.a[d].y; }
+                for (int d = 0; d < ND; ++d) { o[2 * d] = value(s.a[d].x); o[2 * d + 1] = value(s.a[d].y); }
             }
         }
-        const double llk = warp_sum(-0.5 * ((double)ND * (slog + log(fprod)) + quad));
+        const double llk = warp_sum(value(-0.5 * ((double)ND * (slog + log(fprod)) + quad)));
         if (lane == 0) a.tile_llk[q] = llk;              // one partial per warp-tile
     }
 }
@@ -256,9 +267,9 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(CtcrwArgs<ND> a) {
 // ---------------------------------------------------------------------------------------------
 // adjoint kernel
 // ---------------------------------------------------------------------------------------------
-template <int ND>
-__device__ __forceinline__ Adj<ND> load_adj(const double* p) {
-    Adj<ND> g;
+template <int ND, class R>
+__device__ __forceinline__ Adj<ND, R> load_adj(const R* p) {
+    Adj<ND, R> g;
 #pragma unroll
     for (int d = 0; d < ND; ++d) g.a[d] = {p[2 * d], p[2 * d + 1]};
     g.P = {p[2 * ND], p[2 * ND + 1], p[2 * ND + 2]};
@@ -267,55 +278,59 @@ __device__ __forceinline__ Adj<ND> load_adj(const double* p) {
 
 constexpr int SGRAD = 256;         // per-CTA gradient accumulators (doubles) when p_theta fits
 
-template <int ND, int NT>
+template <int ND, int NT, class R = double>
 struct BwdSmem {
     static constexpr int FS = 2 * ND + 3;        // forward state before the row
-    double R[LC][FS][NT];            // states; overwritten by eta_bar (slots 0..NP-1) and by the
+    static constexpr int ES = 16 * ScalarOf<R>::NDBL;
+    R Rs[LC][FS][NT];                // states; overwritten by eta_bar (slots 0..NP-1) and by the
                                      // transposed-product scratch (slots NP..FS-1) once consumed
-    double wagg[2][NT / 32][16];
-    double tagg[2][16];
-    double misc[2][16];
-    double th[NT / 32][TH_CACHE];
-    double sgrad[SGRAD];
+    double wagg[2][NT / 32][ES];
+    double tagg[2][ES];
+    R misc[2][16];
+    R th[NT / 32][TH_CACHE];
+    R sgrad[SGRAD];
     int ticket[2];
 };
 
 // per-row inputs of the adjoint sweep, fetched one row ahead
-template <int ND>
+template <int ND, class R>
 struct RowIn {
-    double tau, e, s2, dt, y[ND];
+    R tau, e, s2;
+    double dt, y[ND];
 };
-template <int ND>
-__device__ __forceinline__ RowIn<ND> load_row(const CtcrwArgs<ND>& a, int64_t pos, bool live) {
-    RowIn<ND> r;
+template <int ND, class R>
+__device__ __forceinline__ RowIn<ND, R> load_row(const CtcrwArgs<ND, R>& a, int64_t pos, bool live) {
+    RowIn<ND, R> r;
     const int64_t np = a.X.n_pad;
     r.dt = live ? a.dt[pos] : 1.0;
-    r.tau = live ? a.wg[pos] : 1.0;
-    r.e = live ? a.wg[np + pos] : 0.0;
-    r.s2 = live ? a.wg[2 * np + pos] : 0.0;
+    r.tau = live ? a.wg[pos] : R(1.0);
+    r.e = live ? a.wg[np + pos] : R(0.0);
+    r.s2 = live ? a.wg[2 * np + pos] : R(0.0);
 #pragma unroll
     for (int d = 0; d < ND; ++d) r.y[d] = live ? a.obs[(size_t)d * np + pos] : 0.0;
     return r;
 }
 
-template <int ND, int NT, int MINB>
-__global__ void __launch_bounds__(NT, MINB) ctcrw_bwd_kernel(CtcrwArgs<ND> a) {
-    using SM = BwdSmem<ND, NT>;
-    using Ops = BwdOps<ND>;
-    using Elem = BwdElem<ND>;
+template <int ND, int NT, int MINB, class R = double>
+__global__ void __launch_bounds__(NT, MINB) ctcrw_bwd_kernel(CtcrwArgs<ND, R> a) {
+    using SM = BwdSmem<ND, NT, R>;
+    using Ops = BwdOps<ND, R>;
+    using Elem = BwdElem<ND, R>;
+    using St = State<ND, R>;
+    using Ad = Adj<ND, R>;
     constexpr int NWARP = NT / 32;
     constexpr int NP = ND + 2;
     constexpr int FS = SM::FS;
     constexpr int TCAP = (FS - NP) * LC;          // slots whose scratch fits in the freed state slots
-    static_assert(Elem::NDBL <= 16, "element too large for the shared staging area");
+    static_assert(Elem::NDBL <= SM::ES, "element too large for the shared staging area");
     static_assert(FS >= NP, "eta_bar reuses the state slots");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SM& sm = *reinterpret_cast<SM*>(smem_raw);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const double h = exp(2.0 * a.par[0]);
+    const R h = obs_variance(a);
     const bool mu0 = *a.mu_zero != 0;
-    GradAcc gacc{(a.p_theta <= SGRAD) ? sm.sgrad : nullptr, a.grad_theta};
+    GradAccT<R> gacc{(a.p_theta <= SGRAD) ? sm.sgrad : nullptr, a.grad_theta, a.p_theta};
     if (gacc.sgrad) for (int i = tid; i < SGRAD; i += NT) sm.sgrad[i] = 0.0;
 
     for (int it = 0;; ++it) {
@@ -328,12 +343,12 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_bwd_kernel(CtcrwArgs<ND> a) {
         const int64_t q = (int64_t)tile * NWARP + warp;
         const int64_t base = q * WT + lane;
         const int64_t chunk = q * 32 + lane;
-        const WtView w = open_warptile(a.X, q, a.theta, sm.th[warp], !mu0);
+        const WtViewT<R> w = open_warptile<R>(a.X, q, a.theta, sm.th[warp], !mu0);
         const unsigned long long fl = load_flags8(a.flags, base);
 
         // (1) recompute the forward states of this thread's rows from its checkpoint and compose
         //     the rows' adjoint elements (in time order)
-        State<ND> s;
+        St s;
 #pragma unroll
         for (int d = 0; d < ND; ++d) {
             s.a[d].x = a.ckpt[(size_t)(2 * d) * a.nchunks + chunk];
@@ -342,37 +357,37 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_bwd_kernel(CtcrwArgs<ND> a) {
         s.P.a = a.ckpt[(size_t)(2 * ND) * a.nchunks + chunk];
         s.P.b = a.ckpt[(size_t)(2 * ND + 1) * a.nchunks + chunk];
         s.P.c = a.ckpt[(size_t)(2 * ND + 2) * a.nchunks + chunk];
-        Elem E = bwd_identity<ND>();
-        RowIn<ND> nx = load_row<ND>(a, base, (uint8_t)fl != 0xff);
+        Elem E = bwd_identity<ND, R>();
+        RowIn<ND, R> nx = load_row<ND, R>(a, base, (uint8_t)fl != 0xff);
 #pragma unroll 1
         for (int k = 0; k < LC; ++k) {
             const uint8_t f = (uint8_t)(fl >> (8 * k));
             const bool live = f != 0xff;
             const bool step = live && !(f & ROW_START);
-            const RowIn<ND> r = nx;
-            if (k + 1 < LC) nx = load_row<ND>(a, base + (k + 1) * 32, (uint8_t)(fl >> (8 * (k + 1))) != 0xff);
+            const RowIn<ND, R> r = nx;
+            if (k + 1 < LC) nx = load_row<ND, R>(a, base + (k + 1) * 32, (uint8_t)(fl >> (8 * (k + 1))) != 0xff);
             // state BEFORE row k
 #pragma unroll
             for (int d = 0; d < ND; ++d) {
-                sm.R[k][2 * d][tid] = s.a[d].x;
-                sm.R[k][2 * d + 1][tid] = s.a[d].y;
+                sm.Rs[k][2 * d][tid] = s.a[d].x;
+                sm.Rs[k][2 * d + 1][tid] = s.a[d].y;
             }
-            sm.R[k][2 * ND][tid] = s.P.a;
-            sm.R[k][2 * ND + 1][tid] = s.P.b;
-            sm.R[k][2 * ND + 2][tid] = s.P.c;
+            sm.Rs[k][2 * ND][tid] = s.P.a;
+            sm.Rs[k][2 * ND + 1][tid] = s.P.b;
+            sm.Rs[k][2 * ND + 2][tid] = s.P.c;
             if (step) {
-                double mu[ND];
+                R mu[ND];
 #pragma unroll
                 for (int d = 0; d < ND; ++d) mu[d] = 0.0;
                 if (!mu0) row_eta_prefix<ND>(w, k, a.theta, mu);
-                const StepPar sp = make_step(r.tau, r.e, r.s2, r.dt);
-                StepAux<ND> ax;
-                double F, qd;
+                const StepParT<R> sp = make_step(r.tau, r.e, r.s2, r.dt);
+                StepAux<ND, R> ax;
+                R F, qd;
                 fwd_step_q<ND, true>(s, sp, r.y, mu, (f & ROW_OBS) != 0, h, &ax, F, qd);
                 E = bwd_combine<ND>(E, bwd_row_elem<ND>(sp, ax, (f & ROW_OBS) != 0, (f & ROW_LAST) != 0));
             } else if (live) {
                 s = track_start_state<ND>(a, r.dt);
-                E = bwd_combine<ND>(E, bwd_const<ND>(adj_zero<ND>()));
+                E = bwd_combine<ND>(E, bwd_const<ND>(adj_zero<ND, R>()));
             }
         }
         // (2) warp inclusive SUFFIX scan (higher lanes = later rows)
@@ -384,7 +399,7 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_bwd_kernel(CtcrwArgs<ND> a) {
         }
         if (lane == 0) store_elem(sm.wagg[par][warp], inc);
         Elem exc = shfl_down_elem(inc, 1);
-        if (lane == 31) exc = bwd_identity<ND>();
+        if (lane == 31) exc = bwd_identity<ND, R>();
         __syncthreads();
         // (3) the last warp composes and publishes the tile aggregate while warp 0 looks back over
         //     the LATER tiles; warp 0 then publishes the inclusive suffix and the adjoint entering
@@ -399,8 +414,8 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_bwd_kernel(CtcrwArgs<ND> a) {
         if (warp == 0) {
             suf = lookback<Ops>(a.bdesc, ticket);
             if (lane == 0) {
-                Adj<ND> g0 = a.g_in ? load_adj<ND>(a.g_in) : adj_zero<ND>();
-                const Adj<ND> gt = bwd_apply<ND>(suf, g0);
+                Ad g0 = a.g_in ? load_adj<ND, R>(a.g_in) : adj_zero<ND, R>();
+                const Ad gt = bwd_apply<ND>(suf, g0);
 #pragma unroll
                 for (int d = 0; d < ND; ++d) { sm.misc[par][2 * d] = gt.a[d].x; sm.misc[par][2 * d + 1] = gt.a[d].y; }
                 sm.misc[par][2 * ND] = gt.P.a; sm.misc[par][2 * ND + 1] = gt.P.b; sm.misc[par][2 * ND + 2] = gt.P.c;
@@ -410,44 +425,44 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_bwd_kernel(CtcrwArgs<ND> a) {
         if (warp == 0 && lane == 0) publish_incl<Ops>(a.bdesc, ticket, bwd_combine<ND>(load_elem<Elem>(sm.tagg[par]), suf));
         if (a.summary) continue;
         // (4) adjoint entering this thread's last row, then the reverse sweep over its rows
-        Adj<ND> g = load_adj<ND>(sm.misc[par]);
+        Ad g = load_adj<ND, R>(sm.misc[par]);
 #pragma unroll 1
         for (int ww = NWARP - 1; ww > warp; --ww) g = bwd_apply<ND>(load_elem<Elem>(sm.wagg[par][ww]), g);
         g = bwd_apply<ND>(exc, g);
-        double gh = 0.0;
-        nx = load_row<ND>(a, base + (LC - 1) * 32, (uint8_t)(fl >> (8 * (LC - 1))) != 0xff);
+        R gh = 0.0;
+        nx = load_row<ND, R>(a, base + (LC - 1) * 32, (uint8_t)(fl >> (8 * (LC - 1))) != 0xff);
 #pragma unroll 1
         for (int k = LC - 1; k >= 0; --k) {
             const uint8_t f = (uint8_t)(fl >> (8 * k));
-            const RowIn<ND> r = nx;
-            if (k > 0) nx = load_row<ND>(a, base + (k - 1) * 32, (uint8_t)(fl >> (8 * (k - 1))) != 0xff);
-            double gp[NP];
+            const RowIn<ND, R> r = nx;
+            if (k > 0) nx = load_row<ND, R>(a, base + (k - 1) * 32, (uint8_t)(fl >> (8 * (k - 1))) != 0xff);
+            R gp[NP];
 #pragma unroll
             for (int j = 0; j < NP; ++j) gp[j] = 0.0;
             if (f != 0xff) {
                 if (f & ROW_START) {
-                    g = adj_zero<ND>();
+                    g = adj_zero<ND, R>();
                 } else {
-                    double mu[ND];
+                    R mu[ND];
 #pragma unroll
                     for (int d = 0; d < ND; ++d) mu[d] = 0.0;
                     if (!mu0) row_eta_prefix<ND>(w, k, a.theta, mu);
-                    State<ND> sk;
+                    St sk;
 #pragma unroll
                     for (int d = 0; d < ND; ++d) {
-                        sk.a[d].x = sm.R[k][2 * d][tid];
-                        sk.a[d].y = sm.R[k][2 * d + 1][tid];
+                        sk.a[d].x = sm.Rs[k][2 * d][tid];
+                        sk.a[d].y = sm.Rs[k][2 * d + 1][tid];
                     }
-                    sk.P.a = sm.R[k][2 * ND][tid];
-                    sk.P.b = sm.R[k][2 * ND + 1][tid];
-                    sk.P.c = sm.R[k][2 * ND + 2][tid];
-                    const StepPar sp = make_step(r.tau, r.e, r.s2, r.dt);
+                    sk.P.a = sm.Rs[k][2 * ND][tid];
+                    sk.P.b = sm.Rs[k][2 * ND + 1][tid];
+                    sk.P.c = sm.Rs[k][2 * ND + 2][tid];
+                    const StepParT<R> sp = make_step(r.tau, r.e, r.s2, r.dt);
                     const bool has = (f & ROW_OBS) != 0, cut = (f & ROW_LAST) != 0;
-                    StepAux<ND> ax;
-                    double F, qd;
+                    StepAux<ND, R> ax;
+                    R F, qd;
                     fwd_step_q<ND, true>(sk, sp, r.y, mu, has, h, &ax, F, qd);
-                    const Adj<ND> gin = cut ? adj_zero<ND>() : g;
-                    double g_h;
+                    const Ad gin = cut ? adj_zero<ND, R>() : g;
+                    R g_h;
                     row_param_grad<ND>(gin, sp, ax, mu, r.tau, r.e, r.s2, r.dt, has, gp, gp[ND], gp[ND + 1], g_h);
                     gh += g_h;
                     g = bwd_apply<ND>(bwd_row_elem<ND>(sp, ax, has, cut), g);
@@ -455,24 +470,24 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_bwd_kernel(CtcrwArgs<ND> a) {
             }
             // eta_bar of this row replaces its (consumed) forward state
 #pragma unroll
-            for (int j = 0; j < NP; ++j) sm.R[k][j][tid] = gp[j];
+            for (int j = 0; j < NP; ++j) sm.Rs[k][j][tid] = gp[j];
         }
         // (5) grad_theta += X' eta_bar for this warp-tile
         if (w.uniform && w.S <= TCAP) {
-            scatter_warptile_transposed<NP>(w, gacc, [&](int k, int p) { return sm.R[k][p][tid]; },
-                                            [&](int j, int l) -> double& { return sm.R[j / (FS - NP)][NP + j % (FS - NP)][(tid & ~31) + l]; });
+            scatter_warptile_transposed<NP, R>(w, gacc, [&](int k, int p) { return sm.Rs[k][p][tid]; },
+                                               [&](int j, int l) -> R& { return sm.Rs[j / (FS - NP)][NP + j % (FS - NP)][(tid & ~31) + l]; });
         } else {
-            scatter_warptile<NP>(w, gacc, [&](int k, int p) { return sm.R[k][p][tid]; });
+            scatter_warptile<NP, R>(w, gacc, [&](int k, int p) { return sm.Rs[k][p][tid]; });
         }
         gh = warp_sum(gh);
-        if (lane == 0) a.tile_gh[q] = gh;                // one partial per warp-tile
+        if (lane == 0) {                                 // one partial per warp-tile
+            a.tile_gh[q] = value(gh);
+            if constexpr (!std::is_same<R, double>::value) a.tile_gh[a.X.n_pad / WT + q] = gh.d;
+        }
     }
     if (gacc.sgrad) {
         __syncthreads();
-        for (int i = tid; i < a.p_theta; i += NT) {
-            const double v = sm.sgrad[i];
-            if (v != 0.0) atomicAdd(a.grad_theta + i, v);
-        }
+        grad_flush(gacc, NT);
     }
 }
 
@@ -480,31 +495,31 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_bwd_kernel(CtcrwArgs<ND> a) {
 // time-sharded runs: composite elements of the shards (gathered from all ranks) -> incoming
 // state / adjoint of shard `me`.  One thread.
 // ---------------------------------------------------------------------------------------------
-template <int ND>
+template <int ND, class R = double>
 __global__ void shard_state_kernel(const double* __restrict__ elems, int n_shards, int me, Sym2 P0,
-                                   double* __restrict__ s_out) {
-    using Elem = FwdElem<ND>;
+                                   R* __restrict__ s_out) {
+    using Elem = FwdElem<ND, R>;
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    Elem acc = fwd_identity<ND>();
+    Elem acc = fwd_identity<ND, R>();
     for (int i = 0; i < me && i < n_shards; ++i) acc = fwd_combine<ND>(acc, load_elem<Elem>(elems + (size_t)i * Elem::NDBL));
-    State<ND> s0;
-    s0.P = P0;
+    State<ND, R> s0;
+    s0.P = {P0.a, P0.b, P0.c};
 #pragma unroll
     for (int d = 0; d < ND; ++d) s0.a[d] = {0.0, 0.0};
-    const State<ND> s = fwd_apply<ND>(acc, s0);       // shard 0 begins with a track start: s0 is irrelevant
+    const State<ND, R> s = fwd_apply<ND>(acc, s0);    // shard 0 begins with a track start: s0 is irrelevant
 #pragma unroll
     for (int d = 0; d < ND; ++d) { s_out[2 * d] = s.a[d].x; s_out[2 * d + 1] = s.a[d].y; }
     s_out[2 * ND] = s.P.a; s_out[2 * ND + 1] = s.P.b; s_out[2 * ND + 2] = s.P.c;
 }
 
-template <int ND>
+template <int ND, class R = double>
 __global__ void shard_adjoint_kernel(const double* __restrict__ elems, int n_shards, int me,
-                                     double* __restrict__ g_out) {
-    using Elem = BwdElem<ND>;
+                                     R* __restrict__ g_out) {
+    using Elem = BwdElem<ND, R>;
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    Elem acc = bwd_identity<ND>();
+    Elem acc = bwd_identity<ND, R>();
     for (int i = n_shards - 1; i > me; --i) acc = bwd_combine<ND>(load_elem<Elem>(elems + (size_t)i * Elem::NDBL), acc);
-    const Adj<ND> g = bwd_apply<ND>(acc, adj_zero<ND>());
+    const Adj<ND, R> g = bwd_apply<ND>(acc, adj_zero<ND, R>());
 #pragma unroll
     for (int d = 0; d < ND; ++d) { g_out[2 * d] = g.a[d].x; g_out[2 * d + 1] = g.a[d].y; }
     g_out[2 * ND] = g.P.a; g_out[2 * ND + 1] = g.P.b; g_out[2 * ND + 2] = g.P.c;

@@ -71,6 +71,10 @@ struct ssde_handle {
     DevBuf aest;
     DevBuf s_in, g_in;               // incoming state / adjoint of a time shard (2 n_dim + 3 doubles each)
     bool have_s_in = false, have_g_in = false;
+    // tangent (Hessian-vector) pass: Dual-sized copies of the work buffers, allocated on first use
+    bool tan_ready = false;
+    DevBuf t_dir, t_theta_dot, t_grad_theta, t_wg, t_ckpt, t_tile_gh, t_f_agg, t_f_incl, t_b_agg, t_b_incl, t_out, t_hess;
+    int grid_f2 = 0, grid_b2 = 0, grid_lp2 = 0;
     double* h_pinned = nullptr;      // pinned host staging: par in, out back
     unsigned epoch = 0;
     int ntiles_f = 0, ntiles_b = 0, grid_lp = 0, grid_f = 0, grid_b = 0;
@@ -113,19 +117,22 @@ int dev_upload(DevBuf& b, const std::vector<T>& v, std::string& err) {
 // ---------------------------------------------------------------------------------------------
 // small kernels: theta gather, finalisation (reductions over tiles, penalty, packing)
 // ---------------------------------------------------------------------------------------------
+// `dir` / `theta_dot` (both or neither): direction of the tangent pass, gathered like theta.
 __global__ void gather_theta_kernel(const double* __restrict__ par, double* __restrict__ theta,
+                                    const double* __restrict__ dir, double* __restrict__ theta_dot,
                                     int p_fe, int p_re, int o_fe, int o_re,
                                     const int32_t* __restrict__ mu_cols, int n_mu_cols, int* __restrict__ mu_zero) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < p_fe) theta[i] = par[o_fe + i];
-    else if (i < p_fe + p_re) theta[i] = par[o_re + (i - p_fe)];
+    if (i < p_fe) { theta[i] = par[o_fe + i]; if (dir) theta_dot[i] = dir[o_fe + i]; }
+    else if (i < p_fe + p_re) { theta[i] = par[o_re + (i - p_fe)]; if (dir) theta_dot[i] = dir[o_re + (i - p_fe)]; }
     if (blockIdx.x == 0 && mu_zero) {
         // mu_d == 0 on every row iff every theta entry its design columns touch is exactly 0
+        // (and, in a tangent pass, so is the direction)
         int nz = (n_mu_cols < 0) ? 1 : 0;
         for (int k = threadIdx.x; k < n_mu_cols; k += blockDim.x) {
             const int c = mu_cols[k];
-            const double v = (c < p_fe) ? par[o_fe + c] : par[o_re + (c - p_fe)];
-            if (v != 0.0) nz = 1;
+            const int o = (c < p_fe) ? o_fe + c : o_re + (c - p_fe);
+            if (par[o] != 0.0 || (dir && dir[o] != 0.0)) nz = 1;
         }
         nz = __syncthreads_or(nz);
         if (threadIdx.x == 0) *mu_zero = nz ? 0 : 1;
@@ -134,22 +141,25 @@ __global__ void gather_theta_kernel(const double* __restrict__ par, double* __re
 
 struct FinArgs {
     const double* par;
-    const double* grad_theta;
+    const double* par_dot;    // tangent pass: direction in the parameter vector (else nullptr)
+    const double* grad_theta; // [p] (tangent pass: [2 p], tangents second)
     const double* part_llk;   // per-tile / per-block log-likelihood partial sums
     int n_part;
     const double* tile_gh;    // CTCRW: per-tile d nllk / d h partial sums (or nullptr)
+    const double* tile_gh_dot;
     int n_gh;
     const uint32_t* S_rowptr;
     const uint32_t* S_col;
     const double* S_val;
     const int32_t* sm_off;    // [n_s + 1] offsets of the smooth blocks in coeff_re
-    double* sb;               // [p_re] scratch: S b
+    double* sb;               // [2 p_re] scratch: S b (as R)
     int p_fe, p_re, n_s, npar, o_sig, o_fe, o_ll, o_re;
     int penalty;              // 0 none, 1 Kalman form (nllk_ctcrw.hpp:254-280), 2 nllk_sde form
     double pen_const;         // sum_i [Sn_i/2 log(2 pi) - 1/2 log det S_i]  (nllk_sde.hpp:114-116)
     int want_grad;
     const unsigned* error;
     double* out;              // [1 + npar + 1]: nllk, gradient, status
+    double* hv;               // tangent pass: [npar] Hessian-vector product
 };
 
 // deterministic sum of a strided array by one block
@@ -168,9 +178,11 @@ __device__ double block_reduce_array(const double* x, int n, double* red) {
 }
 
 // Fixed-shape partial sums of the per-tile outputs (deterministic: block b always sums the same
-// slice in the same order).  part[b] = sum of x[slice b], part[RED_BLOCKS + b] likewise for y.
+// slice in the same order).  part[b] = sum of x[slice b], part[RED_BLOCKS + b] likewise for y,
+// part[2 RED_BLOCKS + b] for z.
 __global__ void __launch_bounds__(256) reduce_tiles_kernel(const double* __restrict__ x, int nx,
-                                                           const double* __restrict__ y, int ny,
+                                                           const double* __restrict__ y,
+                                                           const double* __restrict__ z, int ny,
                                                            double* __restrict__ part) {
     __shared__ double red[256];
     const int b = blockIdx.x, nb = gridDim.x;
@@ -180,70 +192,94 @@ __global__ void __launch_bounds__(256) reduce_tiles_kernel(const double* __restr
         const double s = block_reduce_array(x + lo, hi - lo, red);
         if (threadIdx.x == 0) part[b] = s;
     }
-    if (y) {
+    const double* more[2] = {y, z};
+    for (int m = 0; m < 2; ++m) {
+        if (!more[m]) continue;
         __syncthreads();
         const int per = (ny + nb - 1) / nb;
         const int lo = min(b * per, ny), hi = min(lo + per, ny);
-        const double s = block_reduce_array(y + lo, hi - lo, red);
-        if (threadIdx.x == 0) part[nb + b] = s;
+        const double s = block_reduce_array(more[m] + lo, hi - lo, red);
+        if (threadIdx.x == 0) part[(m + 1) * nb + b] = s;
     }
 }
 
+// Reductions over tiles, chain rule for log_sigma_obs, smoothing penalty (nllk_ctcrw.hpp:254-280 /
+// nllk_sde.hpp:89-124) and packing.  R = Dual: the same arithmetic on (value, tangent) pairs
+// also yields the Hessian-vector product of the penalised objective in a.hv.
+template <class R>
 __global__ void __launch_bounds__(256) finalize_kernel(FinArgs a) {
+    constexpr bool TAN = !std::is_same<R, double>::value;
     __shared__ double red[256];
-    __shared__ double s_quad[64];
+    __shared__ R s_quad[64];
     const int tid = threadIdx.x;
-    double nllk = -block_reduce_array(a.part_llk, a.n_part, red);
+    const int p = a.p_fe + a.p_re;
+    auto P = [&](int i) -> R { return ScalarOf<R>::make(a.par[i], TAN ? a.par_dot[i] : 0.0); };
+    auto put = [&](int i, const R& g) {            // gradient entry i (and its tangent)
+        a.out[1 + i] = value(g);
+        if (TAN) a.hv[i] = tangent(g);
+    };
+    R nllk = -block_reduce_array(a.part_llk, a.n_part, red);
     __syncthreads();
     if (a.want_grad) {
-        for (int i = tid; i < a.npar; i += blockDim.x) a.out[1 + i] = 0.0;
+        for (int i = tid; i < a.npar; i += blockDim.x) put(i, R(0.0));
         __syncthreads();
         if (a.tile_gh) {
-            const double gh = block_reduce_array(a.tile_gh, a.n_gh, red);
+            const double ghv = block_reduce_array(a.tile_gh, a.n_gh, red);
             __syncthreads();
-            if (tid == 0) { const double h = exp(2.0 * a.par[a.o_sig]); a.out[1 + a.o_sig] = 2.0 * h * gh; }
+            double ghd = 0.0;
+            if (TAN) { ghd = block_reduce_array(a.tile_gh_dot, a.n_gh, red); __syncthreads(); }
+            if (tid == 0) { const R h = exp(2.0 * P(a.o_sig)); put(a.o_sig, 2.0 * h * ScalarOf<R>::make(ghv, ghd)); }
         }
-        for (int i = tid; i < a.p_fe; i += blockDim.x) a.out[1 + a.o_fe + i] = a.grad_theta[i];
-        for (int i = tid; i < a.p_re; i += blockDim.x) a.out[1 + a.o_re + i] = a.grad_theta[a.p_fe + i];
+        for (int i = tid; i < p; i += blockDim.x) {
+            const R g = ScalarOf<R>::make(a.grad_theta[i], TAN ? a.grad_theta[p + i] : 0.0);
+            put(i < a.p_fe ? a.o_fe + i : a.o_re + (i - a.p_fe), g);
+        }
     }
     __syncthreads();
     if (a.penalty) {
-        const double* b = a.par + a.o_re;
+        R* sb = reinterpret_cast<R*>(a.sb);
         for (int r = tid; r < a.p_re; r += blockDim.x) {
-            double acc = 0.0;
-            for (uint32_t k = a.S_rowptr[r]; k < a.S_rowptr[r + 1]; ++k) acc += a.S_val[k] * b[a.S_col[k]];
-            a.sb[r] = acc;
+            R acc = 0.0;
+            for (uint32_t k = a.S_rowptr[r]; k < a.S_rowptr[r + 1]; ++k) acc = fmad(a.S_val[k], P(a.o_re + (int)a.S_col[k]), acc);
+            sb[r] = acc;
         }
         __syncthreads();
         for (int i0 = 0; i0 < a.n_s; i0 += 64) {
-            // quadratic forms of up to 64 smooths at a time: one warp-strided pass each
+            // quadratic forms of up to 64 smooths at a time: one block-strided pass each
             for (int i = i0; i < a.n_s && i < i0 + 64; ++i) {
-                double q = 0.0;
-                for (int r = a.sm_off[i] + tid; r < a.sm_off[i + 1]; r += blockDim.x) q += b[r] * a.sb[r];
-                __syncthreads();
-                red[tid] = q;
-                __syncthreads();
-                for (int o = blockDim.x / 2; o > 0; o >>= 1) {
-                    if (tid < o) red[tid] += red[tid + o];
+                R q = 0.0;
+                for (int r = a.sm_off[i] + tid; r < a.sm_off[i + 1]; r += blockDim.x) q += P(a.o_re + r) * sb[r];
+                double part[2] = {value(q), tangent(q)};
+                for (int c = 0; c < (TAN ? 2 : 1); ++c) {
                     __syncthreads();
+                    red[tid] = part[c];
+                    __syncthreads();
+                    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+                        if (tid < o) red[tid] += red[tid + o];
+                        __syncthreads();
+                    }
+                    part[c] = red[0];
                 }
-                if (tid == 0) s_quad[i - i0] = red[0];
+                if (tid == 0) s_quad[i - i0] = ScalarOf<R>::make(part[0], part[1]);
                 __syncthreads();
             }
             if (tid == 0) {
                 for (int i = i0; i < a.n_s && i < i0 + 64; ++i) {
                     const double Sn = (double)(a.sm_off[i + 1] - a.sm_off[i]);
-                    const double ll = a.par[a.o_ll + i], lam = exp(ll);
+                    const R ll = P(a.o_ll + i), lam = exp(ll);
                     nllk += -0.5 * Sn * ll + 0.5 * lam * s_quad[i - i0];
-                    if (a.want_grad) a.out[1 + a.o_ll + i] = -0.5 * Sn + 0.5 * lam * s_quad[i - i0];
+                    if (a.want_grad) put(a.o_ll + i, -0.5 * Sn + 0.5 * lam * s_quad[i - i0]);
                 }
             }
             __syncthreads();
             if (a.want_grad) {
                 for (int i = i0; i < a.n_s && i < i0 + 64; ++i) {
-                    const double lam = exp(a.par[a.o_ll + i]);
-                    for (int r = a.sm_off[i] + tid; r < a.sm_off[i + 1]; r += blockDim.x)
-                        a.out[1 + a.o_re + r] += lam * a.sb[r];
+                    const R lam = exp(P(a.o_ll + i));
+                    for (int r = a.sm_off[i] + tid; r < a.sm_off[i + 1]; r += blockDim.x) {
+                        const R g = lam * sb[r];
+                        a.out[1 + a.o_re + r] += value(g);
+                        if (TAN) a.hv[a.o_re + r] += tangent(g);
+                    }
                 }
             }
             __syncthreads();
@@ -251,9 +287,15 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinArgs a) {
         if (tid == 0 && a.penalty == 2) nllk += a.pen_const;
     }
     if (tid == 0) {
-        a.out[0] = nllk;
+        a.out[0] = value(nllk);
         a.out[1 + a.npar] = (double)(*a.error);
     }
+}
+
+// dir = e_j
+__global__ void unit_vector_kernel(double* __restrict__ dir, int n, int j) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dir[i] = (i == j) ? 1.0 : 0.0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -490,7 +532,7 @@ int setup_penalty(ssde_handle* h, const ssde_triplet& S, int n_smooth, const int
     if ((rc = dev_upload(h->S_col, cols, err))) return rc;
     if ((rc = dev_upload(h->S_val, vals, err))) return rc;
     if ((rc = dev_upload(h->sm_off, off, err))) return rc;
-    if ((rc = dev_alloc<double>(h->sb, h->p_re, err))) return rc;
+    if ((rc = dev_alloc<double>(h->sb, 2 * (size_t)h->p_re, err))) return rc;
     return SSDE_OK;
 }
 
@@ -539,7 +581,7 @@ int finish_setup(ssde_handle* h) {
     if ((rc = dev_alloc<double>(h->theta, p, err))) return rc;
     if ((rc = dev_alloc<double>(h->grad_theta, p, err))) return rc;
     if ((rc = dev_alloc<double>(h->out, h->npar + 2, err))) return rc;
-    if ((rc = dev_alloc<double>(h->part, 2 * RED_BLOCKS, err))) return rc;
+    if ((rc = dev_alloc<double>(h->part, 3 * RED_BLOCKS, err))) return rc;
     if ((rc = dev_alloc<int>(h->mu_zero, 1, err))) return rc;
     CUDA_TRY(cudaMemset(h->mu_zero.p, 0, sizeof(int)));
     if (!h->mu_cols.p && (rc = dev_alloc<int32_t>(h->mu_cols, 1, err))) return rc;
@@ -609,24 +651,31 @@ DesignV2 design_of(const ssde_handle* h) {
     return DesignV2{h->n, h->n_pad, h->desc.as<WtDesc>(), h->val.as<double>(), h->col.as<uint32_t>()};
 }
 
-template <int ND>
-CtcrwArgs<ND> ctcrw_args(ssde_handle* h, const double* d_par, double* aest) {
-    CtcrwArgs<ND> a;
+constexpr int TAN_MINB = 1;             // resident CTAs per SM the tangent kernels are compiled for
+
+template <int ND, class R>
+CtcrwArgs<ND, R> ctcrw_args(ssde_handle* h, const double* d_par, const double* d_dir, double* aest) {
+    constexpr bool TAN = !std::is_same<R, double>::value;
+    CtcrwArgs<ND, R> a;
     a.X = design_of(h);
-    a.theta = h->theta.as<double>();
+    a.theta = Theta{h->theta.as<double>(), TAN ? h->t_theta_dot.as<double>() : nullptr};
     a.obs = h->obs.as<double>(); a.dt = h->dt.as<double>(); a.flags = h->flags.as<uint8_t>();
     a.track_starts = h->track_starts.as<int64_t>(); a.a0 = h->a0.as<double>(); a.n_tracks = h->n_tracks;
-    a.P0 = h->P0; a.par = d_par;
-    a.s_in = h->have_s_in ? h->s_in.as<double>() : nullptr;
-    a.g_in = h->have_g_in ? h->g_in.as<double>() : nullptr;
+    a.P0 = h->P0; a.par = d_par; a.par_dot = TAN ? d_dir : nullptr;
+    a.s_in = h->have_s_in ? h->s_in.as<R>() : nullptr;
+    a.g_in = h->have_g_in ? h->g_in.as<R>() : nullptr;
     a.mu_zero = h->mu_zero.as<int>();
-    a.ckpt = h->ckpt.as<double>(); a.nchunks = h->nchunks; a.wg = h->wg.as<double>();
-    a.tile_llk = h->tile_llk.as<double>(); a.tile_gh = h->tile_gh.as<double>();
-    a.grad_theta = h->grad_theta.as<double>(); a.p_theta = h->p_fe + h->p_re;
+    a.nchunks = h->nchunks;
+    a.ckpt = TAN ? h->t_ckpt.as<R>() : h->ckpt.as<R>();
+    a.wg = TAN ? h->t_wg.as<R>() : h->wg.as<R>();
+    a.tile_llk = h->tile_llk.as<double>();
+    a.tile_gh = TAN ? h->t_tile_gh.as<double>() : h->tile_gh.as<double>();
+    a.grad_theta = TAN ? h->t_grad_theta.as<double>() : h->grad_theta.as<double>();
+    a.p_theta = h->p_fe + h->p_re;
     a.aest = aest;
     unsigned* cnt = h->counters.as<unsigned>();
-    a.fdesc = {h->f_status.as<unsigned>(), h->f_agg.as<double>(), h->f_incl.as<double>(), cnt + 0, cnt + 2, h->epoch};
-    a.bdesc = {h->b_status.as<unsigned>(), h->b_agg.as<double>(), h->b_incl.as<double>(), cnt + 1, cnt + 2, h->epoch};
+    a.fdesc = {h->f_status.as<unsigned>(), (TAN ? h->t_f_agg : h->f_agg).as<double>(), (TAN ? h->t_f_incl : h->f_incl).as<double>(), cnt + 0, cnt + 2, h->epoch};
+    a.bdesc = {h->b_status.as<unsigned>(), (TAN ? h->t_b_agg : h->b_agg).as<double>(), (TAN ? h->t_b_incl : h->b_incl).as<double>(), cnt + 1, cnt + 2, h->epoch};
     a.ntiles = h->ntiles_f;
     a.summary = 0;
     return a;
@@ -642,92 +691,106 @@ int new_scan_epoch(ssde_handle* h, cudaStream_t st) {
     return SSDE_OK;
 }
 
-template <int ND>
-int launch_ctcrw_fwd(ssde_handle* h, const double* d_par, cudaStream_t st, double* aest, bool summary) {
+template <int ND, class R>
+int launch_ctcrw_fwd(ssde_handle* h, const double* d_par, const double* d_dir, cudaStream_t st, double* aest, bool summary) {
+    constexpr bool TAN = !std::is_same<R, double>::value;
     std::string& err = h->err;
     int rc = new_scan_epoch(h, st);
     if (rc) return rc;
-    CtcrwArgs<ND> a = ctcrw_args<ND>(h, d_par, aest);
+    CtcrwArgs<ND, R> a = ctcrw_args<ND, R>(h, d_par, d_dir, aest);
     a.summary = summary ? 1 : 0;
-    mark(h, st, summary ? "ctcrw_fwd_summary" : "ctcrw_fwd");
-    ctcrw_fwd_kernel<ND, FWD_NT, FWD_MINB><<<h->grid_f, FWD_NT, sizeof(FwdSmem<ND, FWD_NT>), st>>>(a);
+    mark(h, st, TAN ? "ctcrw_fwd_tangent" : (summary ? "ctcrw_fwd_summary" : "ctcrw_fwd"));
+    if constexpr (TAN) ctcrw_fwd_kernel<ND, FWD_NT, TAN_MINB, R><<<h->grid_f2, FWD_NT, sizeof(FwdSmem<ND, FWD_NT, R>), st>>>(a);
+    else ctcrw_fwd_kernel<ND, FWD_NT, FWD_MINB, R><<<h->grid_f, FWD_NT, sizeof(FwdSmem<ND, FWD_NT, R>), st>>>(a);
     CUDA_TRY(cudaGetLastError());
     return SSDE_OK;
 }
 
-template <int ND>
-int launch_ctcrw_bwd(ssde_handle* h, const double* d_par, cudaStream_t st, bool summary) {
+template <int ND, class R>
+int launch_ctcrw_bwd(ssde_handle* h, const double* d_par, const double* d_dir, cudaStream_t st, bool summary) {
+    constexpr bool TAN = !std::is_same<R, double>::value;
     std::string& err = h->err;
     int rc = new_scan_epoch(h, st);
     if (rc) return rc;
-    CtcrwArgs<ND> a = ctcrw_args<ND>(h, d_par, nullptr);
+    CtcrwArgs<ND, R> a = ctcrw_args<ND, R>(h, d_par, d_dir, nullptr);
     a.ntiles = h->ntiles_b;
     a.summary = summary ? 1 : 0;
-    mark(h, st, summary ? "ctcrw_bwd_summary" : "ctcrw_bwd");
-    ctcrw_bwd_kernel<ND, BWD_NT, BWD_MINB><<<h->grid_b, BWD_NT, sizeof(BwdSmem<ND, BWD_NT>), st>>>(a);
+    mark(h, st, TAN ? "ctcrw_bwd_tangent" : (summary ? "ctcrw_bwd_summary" : "ctcrw_bwd"));
+    if constexpr (TAN) ctcrw_bwd_kernel<ND, BWD_NT, TAN_MINB, R><<<h->grid_b2, BWD_NT, sizeof(BwdSmem<ND, BWD_NT, R>), st>>>(a);
+    else ctcrw_bwd_kernel<ND, BWD_NT, BWD_MINB, R><<<h->grid_b, BWD_NT, sizeof(BwdSmem<ND, BWD_NT, R>), st>>>(a);
     CUDA_TRY(cudaGetLastError());
     return SSDE_OK;
 }
 
-int launch_reduce(ssde_handle* h, int order, cudaStream_t st) {
+int launch_reduce(ssde_handle* h, int order, bool tan, cudaStream_t st) {
     std::string& err = h->err;
+    const int nwt = (int)(h->n_pad / WT);
+    const double* gh = tan ? h->t_tile_gh.as<double>() : h->tile_gh.as<double>();
     mark(h, st, "reduce_tiles");
-    reduce_tiles_kernel<<<RED_BLOCKS, 256, 0, st>>>(h->tile_llk.as<double>(), (int)(h->n_pad / WT),
-                                                     order >= 1 ? h->tile_gh.as<double>() : nullptr, (int)(h->n_pad / WT),
-                                                     h->part.as<double>());
+    reduce_tiles_kernel<<<RED_BLOCKS, 256, 0, st>>>(h->tile_llk.as<double>(), nwt, order >= 1 ? gh : nullptr,
+                                                     tan ? gh + nwt : nullptr, nwt, h->part.as<double>());
     CUDA_TRY(cudaGetLastError());
     return SSDE_OK;
 }
 
-template <int ND>
-int launch_ctcrw(ssde_handle* h, const double* d_par, int order, cudaStream_t st, double* aest) {
+template <int ND, class R>
+int launch_ctcrw(ssde_handle* h, const double* d_par, const double* d_dir, int order, cudaStream_t st, double* aest) {
     int rc;
-    if ((rc = launch_ctcrw_fwd<ND>(h, d_par, st, aest, false))) return rc;
-    if (order >= 1 && (rc = launch_ctcrw_bwd<ND>(h, d_par, st, false))) return rc;
-    return launch_reduce(h, order, st);
+    if ((rc = launch_ctcrw_fwd<ND, R>(h, d_par, d_dir, st, aest, false))) return rc;
+    if (order >= 1 && (rc = launch_ctcrw_bwd<ND, R>(h, d_par, d_dir, st, false))) return rc;
+    return launch_reduce(h, order, !std::is_same<R, double>::value, st);
 }
 
-template <int MODEL, int ND>
+template <int MODEL, int ND, class R>
 int launch_sde(ssde_handle* h, int order, cudaStream_t st) {
+    constexpr bool TAN = !std::is_same<R, double>::value;
     std::string& err = h->err;
     constexpr int NP = (MODEL == MODEL_BM) ? ND + 1 : ND + 2;
     SdeArgs a;
     a.X = design_of(h);
-    a.theta = h->theta.as<double>();
+    a.theta = Theta{h->theta.as<double>(), TAN ? h->t_theta_dot.as<double>() : nullptr};
     a.obs = h->obs.as<double>(); a.dt = h->dt.as<double>(); a.flags = h->flags.as<uint8_t>();
     a.want_grad = order >= 1;
-    a.grad_theta = h->grad_theta.as<double>(); a.p_theta = h->p_fe + h->p_re;
+    a.grad_theta = TAN ? h->t_grad_theta.as<double>() : h->grad_theta.as<double>(); a.p_theta = h->p_fe + h->p_re;
     a.block_llk = h->block_llk.as<double>();
     a.ntiles = h->ntiles_lp;
-    mark(h, st, "sde_fused");
-    sde_fused_kernel<MODEL, ND><<<h->grid_lp, SDE_NT, sizeof(SdeSmem<NP>), st>>>(a);
+    mark(h, st, TAN ? "sde_fused_tangent" : "sde_fused");
+    sde_fused_kernel<MODEL, ND, R><<<TAN ? h->grid_lp2 : h->grid_lp, SDE_NT, sizeof(SdeSmem<NP, R>), st>>>(a);
     CUDA_TRY(cudaGetLastError());
     return SSDE_OK;
 }
 
-int eval_prologue(ssde_handle* h, const double* d_par, int order, cudaStream_t st) {
+// d_dir != nullptr: tangent pass along that direction of the parameter vector
+int eval_prologue(ssde_handle* h, const double* d_par, const double* d_dir, int order, cudaStream_t st) {
     std::string& err = h->err;
     const int p = h->p_fe + h->p_re;
     CUDA_TRY(cudaMemsetAsync(h->counters.as<unsigned>() + 2, 0, sizeof(unsigned), st));
-    if (order >= 1) CUDA_TRY(cudaMemsetAsync(h->grad_theta.p, 0, sizeof(double) * std::max(p, 1), st));
+    if (order >= 1) {
+        if (d_dir) CUDA_TRY(cudaMemsetAsync(h->t_grad_theta.p, 0, sizeof(double) * 2 * std::max(p, 1), st));
+        else CUDA_TRY(cudaMemsetAsync(h->grad_theta.p, 0, sizeof(double) * std::max(p, 1), st));
+    }
     mark(h, st, "gather_theta");
-    gather_theta_kernel<<<std::max((p + 255) / 256, 1), 256, 0, st>>>(d_par, h->theta.as<double>(), h->p_fe, h->p_re, h->o_fe, h->o_re,
+    gather_theta_kernel<<<std::max((p + 255) / 256, 1), 256, 0, st>>>(d_par, h->theta.as<double>(), d_dir,
+                                                                     d_dir ? h->t_theta_dot.as<double>() : nullptr,
+                                                                     h->p_fe, h->p_re, h->o_fe, h->o_re,
                                                                      h->mu_cols.as<int32_t>(), h->n_mu_cols, h->mu_zero.as<int>());
     CUDA_TRY(cudaGetLastError());
     return SSDE_OK;
 }
 
-int eval_epilogue(ssde_handle* h, const double* d_par, int order, double* d_out, cudaStream_t st) {
+int eval_epilogue(ssde_handle* h, const double* d_par, const double* d_dir, int order, double* d_out, double* d_hv, cudaStream_t st) {
     std::string& err = h->err;
     FinArgs f{};
     if (h->model == SSDE_CTCRW) {
         f.part_llk = h->part.as<double>(); f.n_part = RED_BLOCKS;
         f.tile_gh = (order >= 1) ? h->part.as<double>() + RED_BLOCKS : nullptr; f.n_gh = RED_BLOCKS;
+        f.tile_gh_dot = h->part.as<double>() + 2 * RED_BLOCKS;
     } else {
-        f.part_llk = h->block_llk.as<double>(); f.n_part = h->grid_lp;
-        f.tile_gh = nullptr; f.n_gh = 0;
+        f.part_llk = h->block_llk.as<double>(); f.n_part = d_dir ? h->grid_lp2 : h->grid_lp;
+        f.tile_gh = nullptr; f.tile_gh_dot = nullptr; f.n_gh = 0;
     }
-    f.par = d_par; f.grad_theta = h->grad_theta.as<double>();
+    f.par = d_par; f.par_dot = d_dir;
+    f.grad_theta = d_dir ? h->t_grad_theta.as<double>() : h->grad_theta.as<double>();
     f.S_rowptr = h->S_rowptr.as<uint32_t>(); f.S_col = h->S_col.as<uint32_t>(); f.S_val = h->S_val.as<double>();
     f.sm_off = h->sm_off.as<int32_t>(); f.sb = h->sb.as<double>();
     f.p_fe = h->p_fe; f.p_re = h->p_re; f.n_s = h->n_s; f.npar = h->npar;
@@ -741,16 +804,30 @@ int eval_epilogue(ssde_handle* h, const double* d_par, int order, double* d_out,
     f.want_grad = order >= 1;
     f.error = h->counters.as<unsigned>() + 2;
     f.out = d_out;
+    f.hv = d_hv;
     mark(h, st, "finalize");
-    finalize_kernel<<<1, 256, 0, st>>>(f);
+    if (d_dir) finalize_kernel<Dual><<<1, 256, 0, st>>>(f);
+    else finalize_kernel<double><<<1, 256, 0, st>>>(f);
     mark(h, st, nullptr);
     CUDA_TRY(cudaGetLastError());
     return SSDE_OK;
 }
 
+template <class R>
+int launch_model(ssde_handle* h, const double* d_par, const double* d_dir, int order, cudaStream_t st, double* aest) {
+    if (h->model == SSDE_CTCRW)
+        return (h->n_dim == 1) ? launch_ctcrw<1, R>(h, d_par, d_dir, order, st, aest) : launch_ctcrw<2, R>(h, d_par, d_dir, order, st, aest);
+    if (h->model == SSDE_BM) {
+        if (h->n_dim == 1) return launch_sde<MODEL_BM, 1, R>(h, order, st);
+        if (h->n_dim == 2) return launch_sde<MODEL_BM, 2, R>(h, order, st);
+        return launch_sde<MODEL_BM, 3, R>(h, order, st);
+    }
+    return (h->n_dim == 1) ? launch_sde<MODEL_OU, 1, R>(h, order, st) : launch_sde<MODEL_OU, 2, R>(h, order, st);
+}
+
 int run_eval(ssde_handle* h, const double* d_par, int order, double* d_out, cudaStream_t st, double* aest) {
     std::string& err = h->err;
-    if (order < 0 || order > 1) { err = "order must be 0 or 1 (Hessian not built yet)"; return SSDE_ERR_UNSUPPORTED; }
+    if (order < 0 || order > 1) { err = "order must be 0 or 1 here"; return SSDE_ERR_BAD_ARG; }
     if ((h->shard_flags & (SSDE_SHARD_CONT_PREV | SSDE_SHARD_CONT_NEXT)) &&
         !((h->shard_flags & SSDE_SHARD_CONT_PREV) ? h->have_s_in : true)) {
         err = "time shard: use ssde_eval_stage (the incoming state is unknown)";
@@ -758,21 +835,81 @@ int run_eval(ssde_handle* h, const double* d_par, int order, double* d_out, cuda
     }
     h->last_launches = 0;
     h->pcount = 0;
-    int rc = eval_prologue(h, d_par, order, st);
+    int rc = eval_prologue(h, d_par, nullptr, order, st);
     if (rc) return rc;
+    if ((rc = launch_model<double>(h, d_par, nullptr, order, st, aest))) return rc;
+    return eval_epilogue(h, d_par, nullptr, order, d_out, nullptr, st);
+}
+
+// ---- tangent pass -------------------------------------------------------------------------------
+template <int ND>
+int ctcrw_tan_grids(ssde_handle* h) {
+    std::string& err = h->err;
+    int rc;
+    if ((rc = max_grid(ctcrw_fwd_kernel<ND, FWD_NT, TAN_MINB, Dual>, FWD_NT, sizeof(FwdSmem<ND, FWD_NT, Dual>), h->num_sms, err, h->grid_f2))) return rc;
+    if ((rc = max_grid(ctcrw_bwd_kernel<ND, BWD_NT, TAN_MINB, Dual>, BWD_NT, sizeof(BwdSmem<ND, BWD_NT, Dual>), h->num_sms, err, h->grid_b2))) return rc;
+    return SSDE_OK;
+}
+template <int MODEL, int ND>
+int sde_tan_grid(ssde_handle* h) {
+    constexpr int NP = (MODEL == MODEL_BM) ? ND + 1 : ND + 2;
+    return max_grid(sde_fused_kernel<MODEL, ND, Dual>, SDE_NT, sizeof(SdeSmem<NP, Dual>), h->num_sms, h->err, h->grid_lp2);
+}
+
+// Dual-sized work buffers and launch geometry of the tangent kernels (first use only)
+int tangent_setup(ssde_handle* h) {
+    if (h->tan_ready) return SSDE_OK;
+    std::string& err = h->err;
+    if (h->shard_flags & (SSDE_SHARD_CONT_PREV | SSDE_SHARD_CONT_NEXT)) {
+        err = "Hessian-vector products of a time-sharded track are not built yet";
+        return SSDE_ERR_UNSUPPORTED;
+    }
+    int rc;
+    const int p = h->p_fe + h->p_re;
+    if ((rc = dev_alloc<double>(h->t_dir, h->npar, err))) return rc;
+    if ((rc = dev_alloc<double>(h->t_theta_dot, p, err))) return rc;
+    if ((rc = dev_alloc<double>(h->t_grad_theta, 2 * (size_t)p, err))) return rc;
+    if ((rc = dev_alloc<double>(h->t_out, 2 * (size_t)h->npar + 2, err))) return rc;
     if (h->model == SSDE_CTCRW) {
-        rc = (h->n_dim == 1) ? launch_ctcrw<1>(h, d_par, order, st, aest) : launch_ctcrw<2>(h, d_par, order, st, aest);
+        const int nd = h->n_dim;
+        if ((rc = dev_alloc<double>(h->t_ckpt, 2 * (size_t)h->nchunks * (2 * nd + 3), err))) return rc;
+        if ((rc = dev_alloc<double>(h->t_wg, 2 * (size_t)h->n_pad * 3, err))) return rc;
+        if ((rc = dev_alloc<double>(h->t_tile_gh, 2 * (size_t)(h->n_pad / WT), err))) return rc;
+        const size_t fe = (nd == 1) ? FwdElem<1, Dual>::NDBL : FwdElem<2, Dual>::NDBL;
+        const size_t be = (nd == 1) ? BwdElem<1, Dual>::NDBL : BwdElem<2, Dual>::NDBL;
+        if ((rc = dev_alloc<double>(h->t_f_agg, (size_t)h->ntiles_f * fe, err))) return rc;
+        if ((rc = dev_alloc<double>(h->t_f_incl, (size_t)h->ntiles_f * fe, err))) return rc;
+        if ((rc = dev_alloc<double>(h->t_b_agg, (size_t)h->ntiles_b * be, err))) return rc;
+        if ((rc = dev_alloc<double>(h->t_b_incl, (size_t)h->ntiles_b * be, err))) return rc;
+        rc = (nd == 1) ? ctcrw_tan_grids<1>(h) : ctcrw_tan_grids<2>(h);
+        if (rc) return rc;
+        h->grid_f2 = std::min(h->grid_f2, std::max(h->ntiles_f, 1));
+        h->grid_b2 = std::min(h->grid_b2, std::max(h->ntiles_b, 1));
     } else {
         if (h->model == SSDE_BM) {
-            if (h->n_dim == 1) rc = launch_sde<MODEL_BM, 1>(h, order, st);
-            else if (h->n_dim == 2) rc = launch_sde<MODEL_BM, 2>(h, order, st);
-            else rc = launch_sde<MODEL_BM, 3>(h, order, st);
+            if (h->n_dim == 1) rc = sde_tan_grid<MODEL_BM, 1>(h);
+            else if (h->n_dim == 2) rc = sde_tan_grid<MODEL_BM, 2>(h);
+            else rc = sde_tan_grid<MODEL_BM, 3>(h);
         } else {
-            rc = (h->n_dim == 1) ? launch_sde<MODEL_OU, 1>(h, order, st) : launch_sde<MODEL_OU, 2>(h, order, st);
+            rc = (h->n_dim == 1) ? sde_tan_grid<MODEL_OU, 1>(h) : sde_tan_grid<MODEL_OU, 2>(h);
         }
+        if (rc) return rc;
+        // block_llk has grid_lp entries: never launch more tangent CTAs than that
+        h->grid_lp2 = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(h->grid_lp2, h->grid_lp), h->ntiles_lp));
     }
+    h->tan_ready = true;
+    return SSDE_OK;
+}
+
+// One tangent pass: d_out[1 + npar + 1] = nllk, gradient, status;  d_hv[npar] = H * dir.
+int run_hvp(ssde_handle* h, const double* d_par, const double* d_dir, double* d_out, double* d_hv, cudaStream_t st) {
+    int rc = tangent_setup(h);
     if (rc) return rc;
-    return eval_epilogue(h, d_par, order, d_out, st);
+    h->last_launches = 0;
+    h->pcount = 0;
+    if ((rc = eval_prologue(h, d_par, d_dir, 1, st))) return rc;
+    if ((rc = launch_model<Dual>(h, d_par, d_dir, 1, st, nullptr))) return rc;
+    return eval_epilogue(h, d_par, d_dir, 1, d_out, d_hv, st);
 }
 
 int check_common(int model, int n_dim, std::string& err) {
@@ -1034,8 +1171,8 @@ int ssde_eval_stage(ssde_handle* h, const double* d_par, int stage, const double
         if (!d_out) return SSDE_ERR_BAD_ARG;
         h->last_launches = 0; h->pcount = 0;
         h->have_s_in = h->have_g_in = false;
-        if ((rc = eval_prologue(h, d_par, 1, st))) return rc;
-        rc = (nd == 1) ? launch_ctcrw_fwd<1>(h, d_par, st, nullptr, true) : launch_ctcrw_fwd<2>(h, d_par, st, nullptr, true);
+        if ((rc = eval_prologue(h, d_par, nullptr, 1, st))) return rc;
+        rc = (nd == 1) ? launch_ctcrw_fwd<1, double>(h, d_par, nullptr, st, nullptr, true) : launch_ctcrw_fwd<2, double>(h, d_par, nullptr, st, nullptr, true);
         if (rc) return rc;
         CUDA_TRY(cudaMemcpyAsync(d_out, h->f_incl.as<double>() + (size_t)(h->ntiles_f - 1) * fe, fe * sizeof(double),
                                  cudaMemcpyDeviceToDevice, st));
@@ -1046,9 +1183,9 @@ int ssde_eval_stage(ssde_handle* h, const double* d_par, int stage, const double
         else shard_state_kernel<2><<<1, 32, 0, st>>>(d_elems, n_shards, my_shard, h->P0, h->s_in.as<double>());
         ++h->last_launches;
         h->have_s_in = true;
-        rc = (nd == 1) ? launch_ctcrw_fwd<1>(h, d_par, st, nullptr, false) : launch_ctcrw_fwd<2>(h, d_par, st, nullptr, false);
+        rc = (nd == 1) ? launch_ctcrw_fwd<1, double>(h, d_par, nullptr, st, nullptr, false) : launch_ctcrw_fwd<2, double>(h, d_par, nullptr, st, nullptr, false);
         if (rc) return rc;
-        rc = (nd == 1) ? launch_ctcrw_bwd<1>(h, d_par, st, true) : launch_ctcrw_bwd<2>(h, d_par, st, true);
+        rc = (nd == 1) ? launch_ctcrw_bwd<1, double>(h, d_par, nullptr, st, true) : launch_ctcrw_bwd<2, double>(h, d_par, nullptr, st, true);
         if (rc) return rc;
         CUDA_TRY(cudaMemcpyAsync(d_out, h->b_incl.as<double>() + (size_t)(h->ntiles_b - 1) * be, be * sizeof(double),
                                  cudaMemcpyDeviceToDevice, st));
@@ -1059,10 +1196,10 @@ int ssde_eval_stage(ssde_handle* h, const double* d_par, int stage, const double
         else shard_adjoint_kernel<2><<<1, 32, 0, st>>>(d_elems, n_shards, my_shard, h->g_in.as<double>());
         ++h->last_launches;
         h->have_g_in = true;
-        rc = (nd == 1) ? launch_ctcrw_bwd<1>(h, d_par, st, false) : launch_ctcrw_bwd<2>(h, d_par, st, false);
+        rc = (nd == 1) ? launch_ctcrw_bwd<1, double>(h, d_par, nullptr, st, false) : launch_ctcrw_bwd<2, double>(h, d_par, nullptr, st, false);
         if (rc) return rc;
-        if ((rc = launch_reduce(h, 1, st))) return rc;
-        if ((rc = eval_epilogue(h, d_par, 1, d_out, st))) return rc;
+        if ((rc = launch_reduce(h, 1, false, st))) return rc;
+        if ((rc = eval_epilogue(h, d_par, nullptr, 1, d_out, nullptr, st))) return rc;
     } else {
         err = "stage must be 0, 1 or 2";
         return SSDE_ERR_BAD_ARG;
@@ -1082,17 +1219,101 @@ int ssde_check(ssde_handle* h) {
     return SSDE_OK;
 }
 
+int ssde_hvp_device(ssde_handle* h, const double* d_par, const double* d_dir, double* d_out, double* d_hv, void* stream) {
+    if (!h || !d_par || !d_dir || !d_out || !d_hv) return SSDE_ERR_BAD_ARG;
+    std::string& err = h->err;
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    h->timed = (st == h->stream);
+    if (h->timed) CUDA_TRY(cudaEventRecord(h->ev0, st));
+    int rc = run_hvp(h, d_par, d_dir, d_out, d_hv, st);
+    if (rc) return rc;
+    if (h->timed) CUDA_TRY(cudaEventRecord(h->ev1, st));
+    return SSDE_OK;
+}
+
+int ssde_hess_cols_device(ssde_handle* h, const double* d_par, int first, int count, double* d_out, double* d_hess, void* stream) {
+    if (!h || !d_par || !d_out || !d_hess) return SSDE_ERR_BAD_ARG;
+    std::string& err = h->err;
+    if (first < 0 || count < 0 || first + count > h->npar) { err = "Hessian columns out of range"; return SSDE_ERR_BAD_ARG; }
+    CUDA_TRY(cudaSetDevice(h->device));
+    int rc = tangent_setup(h);
+    if (rc) return rc;
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    h->timed = (st == h->stream);
+    if (h->timed) CUDA_TRY(cudaEventRecord(h->ev0, st));
+    int launches = 0;
+    for (int j = 0; j < count; ++j) {
+        unit_vector_kernel<<<(h->npar + 255) / 256, 256, 0, st>>>(h->t_dir.as<double>(), h->npar, first + j);
+        if ((rc = run_hvp(h, d_par, h->t_dir.as<double>(), d_out, d_hess + (size_t)j * h->npar, st))) return rc;
+        launches += h->last_launches + 1;
+    }
+    h->last_launches = launches;
+    if (h->timed) CUDA_TRY(cudaEventRecord(h->ev1, st));
+    return SSDE_OK;
+}
+
+int ssde_hvp(ssde_handle* h, const double* par, int n_dir, const double* dirs, double* nllk, double* grad, double* hv) {
+    if (!h || !par || !dirs || !hv || n_dir < 1) return SSDE_ERR_BAD_ARG;
+    std::string& err = h->err;
+    CUDA_TRY(cudaSetDevice(h->device));
+    int rc = tangent_setup(h);
+    if (rc) return rc;
+    const int np = h->npar;
+    cudaStream_t st = h->stream;
+    CUDA_TRY(cudaMemcpyAsync(h->par.p, par, sizeof(double) * np, cudaMemcpyHostToDevice, st));
+    std::vector<double> out((size_t)np + 2);
+    h->timed = true;
+    CUDA_TRY(cudaEventRecord(h->ev0, st));
+    int launches = 0;
+    for (int j = 0; j < n_dir; ++j) {
+        CUDA_TRY(cudaMemcpyAsync(h->t_dir.p, dirs + (size_t)j * np, sizeof(double) * np, cudaMemcpyHostToDevice, st));
+        if ((rc = run_hvp(h, h->par.as<double>(), h->t_dir.as<double>(), h->t_out.as<double>(), h->t_out.as<double>() + np + 2, st))) return rc;
+        launches += h->last_launches;
+        CUDA_TRY(cudaMemcpyAsync(hv + (size_t)j * np, h->t_out.as<double>() + np + 2, sizeof(double) * np, cudaMemcpyDeviceToHost, st));
+    }
+    h->last_launches = launches;
+    CUDA_TRY(cudaEventRecord(h->ev1, st));
+    CUDA_TRY(cudaMemcpyAsync(out.data(), h->t_out.p, sizeof(double) * (np + 2), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (nllk) *nllk = out[0];
+    if (grad) std::memcpy(grad, out.data() + 1, sizeof(double) * np);
+    if (out[1 + np] != 0.0) { err = "device-side failure (scan look-back timed out)"; return SSDE_ERR_NUMERIC; }
+    return SSDE_OK;
+}
+
 int ssde_eval(ssde_handle* h, const double* par, int order, double* nllk, double* grad, double* hess) {
     if (!h || !par || !nllk) return SSDE_ERR_BAD_ARG;
     std::string& err = h->err;
-    (void)hess;
+    if (order < 0 || order > 2) { err = "order must be 0, 1 or 2"; return SSDE_ERR_BAD_ARG; }
     if (order >= 1 && !grad) { err = "grad buffer required for order >= 1"; return SSDE_ERR_BAD_ARG; }
+    if (order == 2 && !hess) { err = "hess buffer required for order 2"; return SSDE_ERR_BAD_ARG; }
     CUDA_TRY(cudaSetDevice(h->device));
     double* hp = h->h_pinned;
     double* ho = h->h_pinned + h->npar;
     std::memcpy(hp, par, sizeof(double) * h->npar);
     cudaStream_t st = h->stream;
     CUDA_TRY(cudaMemcpyAsync(h->par.p, hp, sizeof(double) * h->npar, cudaMemcpyHostToDevice, st));
+    if (order == 2) {
+        // joint Hessian (what obj$he returns, R/sde.R:1363): npar tangent passes, column j = H e_j
+        const int np = h->npar;
+        int rc = tangent_setup(h);
+        if (rc) return rc;
+        if (!h->t_hess.p && (rc = dev_alloc<double>(h->t_hess, (size_t)np * np, err))) return rc;
+        if ((rc = ssde_hess_cols_device(h, h->par.as<double>(), 0, np, h->t_out.as<double>(), h->t_hess.as<double>(), nullptr))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(ho, h->t_out.p, sizeof(double) * (np + 2), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(hess, h->t_hess.p, sizeof(double) * (size_t)np * np, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        *nllk = ho[0];
+        std::memcpy(grad, ho + 1, sizeof(double) * np);
+        for (int i = 0; i < np; ++i)                    // symmetrise (columns come from independent passes)
+            for (int j = i + 1; j < np; ++j) {
+                const double m = 0.5 * (hess[(size_t)j * np + i] + hess[(size_t)i * np + j]);
+                hess[(size_t)j * np + i] = hess[(size_t)i * np + j] = m;
+            }
+        if (ho[1 + np] != 0.0) { err = "device-side failure (scan look-back timed out)"; return SSDE_ERR_NUMERIC; }
+        return SSDE_OK;
+    }
     h->timed = true;
     CUDA_TRY(cudaEventRecord(h->ev0, st));
     int rc = run_eval(h, h->par.as<double>(), order, h->out.as<double>(), st, nullptr);

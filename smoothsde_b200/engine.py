@@ -158,6 +158,42 @@ class Engine:
         self._check(rc)
         return self._nllk.value, (g.copy() if order >= 1 else None)
 
+    def hessian(self, par):
+        """(nllk, grad, H): exact joint Hessian of the penalised objective (obj$he), order 2."""
+        par = np.ascontiguousarray(par, dtype=np.float64)
+        if par.size != self.n_par:
+            raise ValueError(f"parameter vector has length {par.size}, expected {self.n_par}")
+        g = self._grad
+        H = np.zeros((self.n_par, self.n_par), order="F")
+        rc = self._lib.ssde_eval(self._h, par.ctypes.data_as(L.c_double_p), 2, C.byref(self._nllk),
+                                 g.ctypes.data_as(L.c_double_p), H.ctypes.data_as(L.c_double_p))
+        self._check(rc)
+        return self._nllk.value, g.copy(), np.ascontiguousarray(H)
+
+    def hvp(self, par, dirs):
+        """(nllk, grad, H @ dirs) by tangent passes; dirs is [n_par] or [n_par, k]."""
+        par = np.ascontiguousarray(par, dtype=np.float64)
+        dirs = np.asarray(dirs, dtype=np.float64)
+        one = dirs.ndim == 1
+        D = np.asfortranarray(dirs.reshape(self.n_par, -1))
+        hv = np.zeros_like(D, order="F")
+        g = self._grad
+        rc = self._lib.ssde_hvp(self._h, par.ctypes.data_as(L.c_double_p), D.shape[1], D.ctypes.data_as(L.c_double_p),
+                                C.byref(self._nllk), g.ctypes.data_as(L.c_double_p), hv.ctypes.data_as(L.c_double_p))
+        self._check(rc)
+        hv = np.ascontiguousarray(hv)
+        return self._nllk.value, g.copy(), (hv[:, 0] if one else hv)
+
+    def hvp_device(self, d_par_ptr, d_dir_ptr, d_out_ptr, d_hv_ptr, stream_ptr=None):
+        rc = self._lib.ssde_hvp_device(self._h, C.c_void_p(d_par_ptr), C.c_void_p(d_dir_ptr), C.c_void_p(d_out_ptr),
+                                       C.c_void_p(d_hv_ptr), C.c_void_p(stream_ptr or 0))
+        self._check(rc)
+
+    def hess_cols_device(self, d_par_ptr, first, count, d_out_ptr, d_hess_ptr, stream_ptr=None):
+        rc = self._lib.ssde_hess_cols_device(self._h, C.c_void_p(d_par_ptr), int(first), int(count), C.c_void_p(d_out_ptr),
+                                             C.c_void_p(d_hess_ptr), C.c_void_p(stream_ptr or 0))
+        self._check(rc)
+
     def eval_device(self, d_par_ptr, d_out_ptr, order=1, stream_ptr=None):
         """Asynchronous evaluation on device buffers (raw pointers, e.g. tensor.data_ptr())."""
         rc = self._lib.ssde_eval_device(self._h, C.c_void_p(d_par_ptr), int(order),

@@ -24,6 +24,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 
 from oracle import oracle_np as O            # noqa: E402
 from oracle import known_answers as KA       # noqa: E402
+from oracle import oracle_c                  # noqa: E402
 from smoothsde_b200 import synth             # noqa: E402
 
 CASES = [
@@ -73,6 +74,13 @@ def main():
         if model == "CTCRW":
             p = O.split_par(dat, par)
             extra["aest_all"] = O.nllk_ctcrw(dat, **p, return_aest=True)[1]
+        # joint Hessian (obj$he): Richardson differences of the C oracle's analytic gradient; on the
+        # smallest cases cross-checked against complex-step + differences of the numpy restatement
+        Hc = oracle_c.COracle(dat).hessian(par)
+        if info["n"] <= 120:
+            Hn = O.hess_complex_fd(dat, par)
+            assert np.max(np.abs(Hn - Hc)) <= 1e-7 * np.max(np.abs(Hc)), (name, np.max(np.abs(Hn - Hc)))
+        extra["hess"] = Hc
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **pack(dat, par, v, g, extra))
         print(f"{name}: n={info['n']} npar={par.size} nllk={v:.15g} known={ka:.15g}"
               + (f" mpmath={mp:.15g}" if mp is not None else ""))

@@ -24,6 +24,8 @@ def load(name):
            "known_answer": float(z["known_answer"])}
     if "nllk_mpmath" in z:
         out["nllk_mpmath"] = float(z["nllk_mpmath"])
+    if "hess" in z:
+        out["hess"] = z["hess"]
     if "aest_all" in z:
         out["aest_all"] = z["aest_all"]
     return dat, out

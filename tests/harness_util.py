@@ -20,8 +20,8 @@ def build_harness():
     out_dir = os.path.join(HERE, "harness", "_build")
     os.makedirs(out_dir, exist_ok=True)
     out = os.path.join(out_dir, "libmath_harness.so")
-    hdr = os.path.join(ROOT, "smoothsde_b200", "csrc", "ctcrw_math.cuh")
-    if (not os.path.exists(out)) or os.path.getmtime(out) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+    hdrs = [os.path.join(ROOT, "smoothsde_b200", "csrc", f) for f in ("ctcrw_math.cuh", "dual.cuh")]
+    if (not os.path.exists(out)) or os.path.getmtime(out) < max([os.path.getmtime(src)] + [os.path.getmtime(f) for f in hdrs]):
         subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-x", "c++", "-o", out, src])
     return ctypes.CDLL(out)
 
@@ -65,3 +65,33 @@ def harness_ctcrw(lib, dat, eta, log_sigma_obs, mode, lc=8, nt=128, want_grad=Tr
                            _P(aest) if want_aest else None)
     assert rc == 0
     return llk.value, eb, gh.value * 2 * h, aest
+
+
+def harness_ctcrw_tangent(lib, dat, eta, eta_dot, log_sigma_obs, lso_dot, mode, lc=8, nt=128):
+    """Dual-number run of the scan algebra along (eta_dot, d log_sigma_obs = lso_dot).
+    Returns (llk, d llk), (eta_bar, d eta_bar), (d nllk/d log_sigma_obs, its tangent)."""
+    obs = np.asarray(dat["obs"], dtype=float)
+    n, nd = obs.shape
+    flags = row_flags(dat["ID"], obs)
+    dt = ctcrw_dt(dat["times"], flags)
+    eta = np.ascontiguousarray(eta, dtype=float)
+    eta_dot = np.ascontiguousarray(eta_dot, dtype=float)
+    y = np.ascontiguousarray(np.nan_to_num(obs))
+    a0 = np.ascontiguousarray(dat["a0"], dtype=float)
+    P0 = np.asarray(dat["P0"], dtype=float)
+    P0s = np.array([P0[0, 0], P0[0, 1], P0[1, 1]])
+    h = float(np.exp(2 * log_sigma_obs))
+    h_dot = 2 * h * lso_dot
+    llk2 = np.zeros(2)
+    gh2 = np.zeros(2)
+    eb = np.zeros((n, nd + 2))
+    ebd = np.zeros((n, nd + 2))
+    rc = lib.harness_ctcrw_tangent(nd, mode, ctypes.c_int64(n),
+                                   flags.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), _P(y), _P(dt),
+                                   _P(eta), _P(eta_dot), _P(a0), _P(P0s), ctypes.c_double(h),
+                                   ctypes.c_double(h_dot), lc, nt, _P(llk2), _P(eb), _P(ebd), _P(gh2))
+    assert rc == 0
+    # g_lso = 2 h gh  ->  d g_lso = 2 (h_dot gh + h gh_dot)
+    g_lso = 2 * h * gh2[0]
+    g_lso_dot = 2 * (h_dot * gh2[0] + h * gh2[1])
+    return llk2, (eb, ebd), (g_lso, g_lso_dot)

@@ -157,3 +157,43 @@ def test_scan_algebra_matches_oracle(harness, T, m, miss, nd, lc, nt):
         assert abs(gsig - g[0]) <= 1e-9 * max(abs(g[0]), 1e-3)
         assert np.max(np.abs(eb - pb_ref)) <= 1e-9 * max(np.max(np.abs(pb_ref)), 1.0)
 
+
+
+# ---------------------------------------------------------------------------------------------
+# tangent (Dual) instantiation of the same algebra = second-order adjoint: its directional
+# derivative of the adjoint must match a Richardson-extrapolated central difference of the
+# plain-double adjoint, sequentially (mode 0) and through the chunked scan (mode 1)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("T,m,miss,nd,lc,nt", [(3, 70, 0.15, 2, 8, 32), (2, 120, 0.1, 1, 4, 8), (5, 9, 0.0, 2, 8, 32)])
+def test_tangent_algebra_matches_finite_differences(harness, T, m, miss, nd, lc, nt):
+    dat, par, _ = synth.make_problem("CTCRW", T, m, missing_frac=miss, n_dim=nd, seed=5 + m)
+    par = par.copy()
+    par[1:1 + nd] = [0.3, -0.2][:nd]
+    p = O.split_par(dat, par)
+    eta = O.linear_predictor(dat, p["coeff_fe"], p["coeff_re"])
+    rng = np.random.default_rng(3)
+    eta_dot = rng.normal(size=eta.shape)
+    lso, lso_dot = float(p["log_sigma_obs"]), 0.7
+
+    def adjoint(t):
+        _, eb, gsig, _ = H.harness_ctcrw(harness, dat, eta + t * eta_dot, lso + t * lso_dot, 0, lc=lc, nt=nt)
+        return eb, gsig
+
+    def richardson(f, k):
+        d1 = (f(k) - f(-k)) / (2 * k)
+        d2 = (f(k / 2) - f(-k / 2)) / k
+        return (4 * d2 - d1) / 3
+
+    k = 2e-3
+    ebd_fd = richardson(lambda t: adjoint(t)[0], k)
+    gsd_fd = richardson(lambda t: adjoint(t)[1], k)
+    eb0, gs0 = adjoint(0.0)
+    for mode in (0, 1):
+        llk2, (eb, ebd), (g_lso, g_lso_dot) = H.harness_ctcrw_tangent(harness, dat, eta, eta_dot, lso, lso_dot, mode, lc=lc, nt=nt)
+        assert np.max(np.abs(eb - eb0)) <= 1e-11 * max(np.max(np.abs(eb0)), 1.0)
+        # d llk = -(grad . direction)
+        dd = -(np.sum(eb0 * eta_dot) + gs0 * lso_dot)
+        assert abs(llk2[1] - dd) <= 1e-9 * max(abs(dd), 1.0)
+        scale = max(np.max(np.abs(ebd_fd)), 1.0)
+        assert np.max(np.abs(ebd - ebd_fd)) <= 2e-7 * scale
+        assert abs(g_lso_dot - gsd_fd) <= 2e-7 * max(abs(gsd_fd), 1.0)
