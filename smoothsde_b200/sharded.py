@@ -1,0 +1,324 @@
+"""Multi-GPU host layer: one process per GPU (``torch.distributed``, NCCL over NVLink), or several
+shards driven by one process.
+
+The reference has no parallelism at all: one sequential loop over every row of every track
+(nllk_ctcrw.hpp:195-247, nllk_sde.hpp:77-84).  What makes the path shard is in the model:
+
+* tracks are independent given the parameters (the filter is re-initialised at every ID change,
+  nllk_ctcrw.hpp:196-200; nllk_sde.hpp:79 skips the transition across it), so ranks hold
+  disjoint groups of whole tracks -- their rows of ``ID / times / obs`` and the matching rows of
+  every parameter block of ``X_fe / X_re`` -- and the packed ``[nllk, gradient]`` (or a Hessian-
+  vector product) is summed with ONE all-reduce per evaluation.  The smoothing penalty is added
+  by rank 0 only (``SSDE_SHARD_NO_PENALTY`` elsewhere).  -> :class:`TrackShardedEngine`
+* the filter and its adjoint along ONE track are associative scans (csrc/ctcrw_math.cuh), so a
+  single long track is cut into contiguous time slabs; per evaluation every shard contributes one
+  composite element per sweep (17 + 11 doubles for d = 2), exchanged with two all-gathers, then
+  the same all-reduce.  -> :class:`TimeShardedEngine` (CTCRW)
+
+Collectives run on a dedicated torch stream that is also handed to the C ABI, so kernels and
+collectives are ordered on the device without host synchronisation.
+"""
+from __future__ import annotations
+
+import numpy as np
+import scipy.sparse as sp
+
+from . import _lib as L
+
+
+# --------------------------------------------------------------------------------------------
+# partitioning of the reference's data list
+# --------------------------------------------------------------------------------------------
+def n_sde_par(dat):
+    obs = np.asarray(dat["obs"])
+    nd = 1 if obs.ndim == 1 else obs.shape[1]
+    return nd + 1 if dat["type"] == "BM" else nd + 2
+
+
+def track_bounds(ID):
+    """Row index of the first row of every track, plus n (tracks = runs of equal ID)."""
+    ID = np.asarray(ID)
+    starts = np.flatnonzero(np.r_[True, ID[1:] != ID[:-1]])
+    return np.r_[starts, ID.size]
+
+
+def split_tracks(ID, world):
+    """Contiguous groups of whole tracks, balanced by row count: [(lo, hi)] * world (a group may
+    be empty when there are fewer tracks than ranks)."""
+    b = track_bounds(ID)
+    n = int(b[-1])
+    cuts = [0]
+    for r in range(1, world):
+        target = n * r / world
+        j = int(np.argmin(np.abs(b - target)))
+        cuts.append(max(int(b[j]), cuts[-1]))
+    cuts.append(n)
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+def split_time(n, world):
+    """Contiguous time slabs of one track: [(lo, hi)] * world."""
+    cuts = [int(round(n * r / world)) for r in range(world + 1)]
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+def shard_rows(dat, lo, hi):
+    """Rows lo..hi-1 of the data list (R/sde.R:528-598): rows of ID / times / obs, the matching
+    rows of every SDE-parameter block of X_fe / X_re, and a0 of the tracks that START in the
+    range.  Returns (sub_dat, cont_prev, cont_next, t_next)."""
+    ID = np.asarray(dat["ID"])
+    n = ID.size
+    n_par = n_sde_par(dat)
+    obs = np.asarray(dat["obs"], dtype=float)
+    if obs.ndim == 1:
+        obs = obs[:, None]
+    sub = {k: v for k, v in dat.items() if k not in ("ID", "times", "obs", "X_fe", "X_re", "a0", "H_array")}
+    sub["ID"], sub["times"], sub["obs"] = ID[lo:hi], np.asarray(dat["times"])[lo:hi], obs[lo:hi]
+    for nm in ("X_fe", "X_re"):
+        X = sp.csr_matrix(dat[nm])
+        sub[nm] = sp.vstack([X[j * n + lo:j * n + hi] for j in range(n_par)], format="csr")
+    cont_prev = lo > 0 and ID[lo - 1] == ID[lo]
+    cont_next = hi < n and ID[hi] == ID[hi - 1]
+    if dat["type"] == "CTCRW":
+        b = track_bounds(ID)[:-1]
+        a0 = np.asarray(dat["a0"], dtype=float).reshape(b.size, -1)
+        sub["a0"] = a0[(b >= lo) & (b < hi)]
+    t_next = float(np.asarray(dat["times"])[hi]) if cont_next else 0.0
+    return sub, bool(cont_prev), bool(cont_next), t_next
+
+
+# --------------------------------------------------------------------------------------------
+# communication: torch.distributed, or nothing (world = 1)
+# --------------------------------------------------------------------------------------------
+class DistComm:
+    """Thin wrapper over a torch.distributed process group (NCCL on GPUs, gloo in CPU tests)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+
+    def all_reduce_sum(self, t):
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def all_gather(self, t):
+        import torch
+        out = torch.empty((self.world * t.numel(),), dtype=t.dtype, device=t.device)
+        if self.world > 1:
+            self.dist.all_gather_into_tensor(out, t.contiguous(), group=self.group)
+        else:
+            out.copy_(t.reshape(-1))
+        return out
+
+
+class SoloComm:
+    rank, world = 0, 1
+
+    def all_reduce_sum(self, t):
+        return t
+
+    def all_gather(self, t):
+        return t.reshape(-1).clone()
+
+
+def _default_factory(dat, device, shard_flags, t_next):
+    from .engine import Engine
+    return Engine.from_data(dat, device=device, shard_flags=shard_flags, t_next=t_next)
+
+
+# --------------------------------------------------------------------------------------------
+# many tracks: shard by track ID
+# --------------------------------------------------------------------------------------------
+class TrackShardedEngine:
+    """This rank's group of tracks + one all-reduce per evaluation.  Same ``eval`` / ``hvp`` /
+    ``hessian`` interface as :class:`smoothsde_b200.engine.Engine`; every rank gets the full result."""
+
+    def __init__(self, dat, comm=None, device=None, engine_factory=None):
+        import torch
+        self.comm = comm if comm is not None else SoloComm()
+        rank, world = self.comm.rank, self.comm.world
+        self.lo, self.hi = split_tracks(dat["ID"], world)[rank]
+        if self.hi <= self.lo:
+            raise ValueError(f"rank {rank} of {world} got no track: use at most as many ranks as tracks")
+        sub, cp, cn, _ = shard_rows(dat, self.lo, self.hi)
+        assert not cp and not cn
+        flags = L.SHARD_NO_PENALTY if rank > 0 else 0
+        self.device = device
+        factory = engine_factory or _default_factory
+        self.engine = factory(sub, 0 if device is None else device, flags, 0.0)
+        self.n_par, self.layout = self.engine.n_par, self.engine.layout
+        self.on_device = device is not None and hasattr(self.engine, "eval_device")
+        if self.on_device:
+            self.dev = torch.device("cuda", device)
+            self.stream = torch.cuda.Stream(device=self.dev)
+            self._par = torch.zeros(self.n_par, dtype=torch.float64, device=self.dev)
+            self._dir = torch.zeros(self.n_par, dtype=torch.float64, device=self.dev)
+            self._out = torch.zeros(2 * self.n_par + 2, dtype=torch.float64, device=self.dev)
+            self._hpar = torch.zeros(self.n_par, dtype=torch.float64).pin_memory()
+            self._hout = torch.zeros(2 * self.n_par + 2, dtype=torch.float64).pin_memory()
+
+    # ---- host-buffer interface (what obj$fn / obj$gr see)
+    def eval(self, par, order=1):
+        import torch
+        par = np.ascontiguousarray(par, dtype=np.float64)
+        np_ = self.n_par
+        if not self.on_device:
+            v, g = self.engine.eval(par, order=order)
+            buf = torch.zeros(np_ + 1, dtype=torch.float64)
+            buf[0] = v
+            if order >= 1:
+                buf[1:] = torch.as_tensor(g)
+            self.comm.all_reduce_sum(buf)
+            out = buf.numpy()
+            return float(out[0]), (out[1:].copy() if order >= 1 else None)
+        with torch.cuda.stream(self.stream):
+            self._hpar.copy_(torch.as_tensor(par))
+            self._par.copy_(self._hpar, non_blocking=True)
+            self.engine.eval_device(self._par.data_ptr(), self._out.data_ptr(), order, self.stream.cuda_stream)
+            # [nllk, gradient, status]: the status word is summed too (non-zero on any rank = failure)
+            self.comm.all_reduce_sum(self._out[:np_ + 2])
+            self._hout[:np_ + 2].copy_(self._out[:np_ + 2], non_blocking=True)
+        self.stream.synchronize()
+        out = self._hout.numpy()
+        if out[np_ + 1] != 0.0:
+            raise L.EngineError(5, "device-side failure on some rank")
+        return float(out[0]), (out[1:np_ + 1].copy() if order >= 1 else None)
+
+    def hvp(self, par, dirs):
+        """(nllk, grad, H @ dirs): one tangent pass + one all-reduce per direction."""
+        import torch
+        par = np.ascontiguousarray(par, dtype=np.float64)
+        dirs = np.asarray(dirs, dtype=np.float64)
+        one = dirs.ndim == 1
+        D = dirs.reshape(self.n_par, -1)
+        np_ = self.n_par
+        hv = np.zeros_like(D)
+        v, g = None, None
+        if not self.on_device:
+            for j in range(D.shape[1]):
+                v, g, h = self.engine.hvp(par, D[:, j])
+                buf = torch.as_tensor(np.concatenate([[v], g, h]))
+                self.comm.all_reduce_sum(buf)
+                out = buf.numpy()
+                v, g, hv[:, j] = float(out[0]), out[1:np_ + 1].copy(), out[np_ + 1:]
+            return v, g, (hv[:, 0] if one else hv)
+        with torch.cuda.stream(self.stream):
+            self._par.copy_(torch.as_tensor(par), non_blocking=False)
+            for j in range(D.shape[1]):
+                self._dir.copy_(torch.as_tensor(np.ascontiguousarray(D[:, j])), non_blocking=False)
+                self.engine.hvp_device(self._par.data_ptr(), self._dir.data_ptr(), self._out.data_ptr(),
+                                       self._out.data_ptr() + 8 * (np_ + 2), self.stream.cuda_stream)
+                self.comm.all_reduce_sum(self._out)
+                out = self._out.cpu().numpy()
+                hv[:, j] = out[np_ + 2:]
+        if out[np_ + 1] != 0.0:
+            raise L.EngineError(5, "device-side failure on some rank")
+        return float(out[0]), out[1:np_ + 1].copy(), (hv[:, 0] if one else hv)
+
+    def hessian(self, par):
+        v, g, H = self.hvp(par, np.eye(self.n_par))
+        return v, g, 0.5 * (H + H.T)
+
+    def close(self):
+        self.engine.close()
+
+
+# --------------------------------------------------------------------------------------------
+# one long track: shard along time (CTCRW)
+# --------------------------------------------------------------------------------------------
+def _stage_driver(shards, par_tensors, gather, reduce_, streams):
+    """The three stages of ssde_eval_stage for a list of local shards (one per rank in the
+    distributed case).  gather(list of per-shard tensors) -> list of gathered tensors, one per
+    local shard; reduce_(list of out tensors) sums them in place across all shards."""
+    import torch
+    e0, e1, outs = [], [], []
+    for (eng, me, nsh), par, st in zip(shards, par_tensors, streams):
+        with torch.cuda.stream(st):
+            t = torch.empty(eng.shard_elem_doubles(0), dtype=torch.float64, device=par.device)
+            eng.eval_stage(0, par.data_ptr(), t.data_ptr(), stream_ptr=st.cuda_stream)
+        e0.append(t)
+    g0 = gather(e0)
+    for (eng, me, nsh), par, st, g in zip(shards, par_tensors, streams, g0):
+        with torch.cuda.stream(st):
+            t = torch.empty(eng.shard_elem_doubles(1), dtype=torch.float64, device=par.device)
+            eng.eval_stage(1, par.data_ptr(), t.data_ptr(), g.data_ptr(), nsh, me, stream_ptr=st.cuda_stream)
+        e1.append(t)
+    g1 = gather(e1)
+    for (eng, me, nsh), par, st, g in zip(shards, par_tensors, streams, g1):
+        with torch.cuda.stream(st):
+            t = torch.empty(eng.n_par + 2, dtype=torch.float64, device=par.device)
+            eng.eval_stage(2, par.data_ptr(), t.data_ptr(), g.data_ptr(), nsh, me, stream_ptr=st.cuda_stream)
+        outs.append(t)
+    return reduce_(outs)
+
+
+class TimeShardedEngine:
+    """One CTCRW track cut along time.  Distributed use: one slab per rank (``comm`` = DistComm).
+    Single-process use: ``devices`` = list of CUDA ordinals (repeats allowed), all slabs driven
+    from this process, elements exchanged with device-to-device copies."""
+
+    def __init__(self, dat, comm=None, device=0, devices=None, engine_factory=None):
+        import torch
+        if dat["type"] != "CTCRW":
+            raise L.EngineError(3, "time sharding exists for CTCRW only")
+        if track_bounds(dat["ID"]).size != 2:
+            raise ValueError("TimeShardedEngine takes ONE track; use TrackShardedEngine for many")
+        n = np.asarray(dat["ID"]).size
+        factory = engine_factory or _default_factory
+        self.local = devices is not None
+        if self.local:
+            world, ranks, devs = len(devices), list(range(len(devices))), list(devices)
+            self.comm = SoloComm()
+        else:
+            self.comm = comm if comm is not None else SoloComm()
+            world, ranks, devs = self.comm.world, [self.comm.rank], [device]
+        slabs = split_time(n, world)
+        self.shards, self.streams, self.devs = [], [], []
+        for r, dv in zip(ranks, devs):
+            lo, hi = slabs[r]
+            sub, cp, cn, t_next = shard_rows(dat, lo, hi)
+            flags = (L.SHARD_CONT_PREV if cp else 0) | (L.SHARD_CONT_NEXT if cn else 0) | (L.SHARD_NO_PENALTY if r > 0 else 0)
+            self.shards.append((factory(sub, dv, flags, t_next), r, world))
+            self.devs.append(torch.device("cuda", dv))
+            self.streams.append(torch.cuda.Stream(device=self.devs[-1]))
+        self.n_par, self.layout = self.shards[0][0].n_par, self.shards[0][0].layout
+        self.world = world
+
+    def _gather(self, ts):
+        import torch
+        if not self.local:
+            with torch.cuda.stream(self.streams[0]):
+                return [self.comm.all_gather(ts[0])]
+        for st in self.streams:
+            st.synchronize()
+        return [torch.cat([t.to(dv) for t in ts]) for dv in self.devs]
+
+    def _reduce(self, outs):
+        import torch
+        if not self.local:
+            with torch.cuda.stream(self.streams[0]):
+                self.comm.all_reduce_sum(outs[0])
+                res = outs[0].cpu()
+            return res.numpy()
+        for st in self.streams:
+            st.synchronize()
+        return sum(o.cpu() for o in outs).numpy()
+
+    def eval(self, par, order=1):
+        """(nllk, grad); the stage protocol always computes the gradient."""
+        import torch
+        par = np.ascontiguousarray(par, dtype=np.float64)
+        pts = []
+        for dv, st in zip(self.devs, self.streams):
+            with torch.cuda.stream(st):
+                pts.append(torch.as_tensor(par).to(dv))
+        out = _stage_driver(self.shards, pts, self._gather, self._reduce, self.streams)
+        if out[self.n_par + 1] != 0.0:
+            raise L.EngineError(5, "device-side failure on some shard")
+        return float(out[0]), (out[1:self.n_par + 1].copy() if order >= 1 else None)
+
+    def close(self):
+        for eng, _, _ in self.shards:
+            eng.close()
