@@ -185,6 +185,41 @@ int ssde_hvp(ssde_handle* h, const double* par, int n_dir, const double* dirs, d
 int ssde_hvp_device(ssde_handle* h, const double* d_par, const double* d_dir, double* d_out, double* d_hv, void* stream);
 int ssde_hess_cols_device(ssde_handle* h, const double* d_par, int first, int count, double* d_out, double* d_hess, void* stream);
 
+/* Laplace-marginal objective over coeff_re: what MakeADFun(..., random = "coeff_re") evaluates
+ * (R/sde.R:522-524, :656-658; TMB's inner newton() + sparse Cholesky):
+ *     f(theta) = g(theta, b_hat) + 1/2 log det H_bb(theta, b_hat) - n_b/2 log(2 pi),
+ *     b_hat = argmin_b g(theta, b),   g = the joint penalised nllk.
+ * The inner Newton iterations use the exact H_bb (tangent passes) and cuSOLVER's dense Cholesky
+ * (potrf / potrs) on the device; the gradient of f costs 2 n_b (4 n_b with Richardson
+ * extrapolation) further tangent passes, see csrc/ssde_laplace.cu.
+ *   ssde_laplace_eval: `par` [ssde_n_par] holds the outer parameters and the STARTING value of
+ *     coeff_re on entry, and coeff_re = b_hat on exit (TMB's env$last.par).  order 0: *value;
+ *     order 1: also grad[ssde_n_par], the gradient of f w.r.t. every non-random entry (0 in the
+ *     coeff_re slots).  The host adapter applies `map` on top, as for ssde_eval. */
+typedef struct ssde_laplace ssde_laplace;
+typedef struct {
+    int32_t max_newton;       /* inner Newton iterations (default 100) */
+    int32_t richardson;       /* 1 (default): O(eps^4) differences of the Hessian-vector products */
+    double grad_tol;          /* inner convergence: max |d g / d b| (default 1e-8) */
+    double fd_step;           /* eps of those differences, along unit directions (default 1e-3) */
+} ssde_laplace_opts;
+typedef struct {
+    double joint;             /* g(theta, b_hat) */
+    double logdet;            /* log det H_bb(theta, b_hat) */
+    double grad_max;          /* max |d g / d b| at exit */
+    int32_t converged, n_newton, n_hess, n_value, n_hvp;
+} ssde_laplace_info;
+int ssde_laplace_create(ssde_handle* h, const ssde_laplace_opts* opts, ssde_laplace** out);
+void ssde_laplace_destroy(ssde_laplace* w);
+int ssde_laplace_eval(ssde_laplace* w, double* par, int order, double* value, double* grad, ssde_laplace_info* info);
+/* H_bb [n_b x n_b, column-major] at the mode of the last ssde_laplace_eval */
+int ssde_laplace_hessian_bb(ssde_laplace* w, double* hess_bb);
+const char* ssde_laplace_error(const ssde_laplace* w);
+
+/* The handle's CUDA device ordinal and its own stream (a cudaStream_t). */
+int ssde_device(const ssde_handle* h);
+void* ssde_stream(const ssde_handle* h);
+
 /* Time-sharded evaluation of ONE long CTCRW track whose rows are split along time over several
  * handles / ranks (shard_flags SSDE_SHARD_CONT_PREV / CONT_NEXT).  The filter and its adjoint are
  * associative scans, so each shard is summarised by one composite element; the host gathers the

@@ -57,6 +57,16 @@ class HostPack(C.Structure):
                 ("desc", C.POINTER(WtDesc)), ("val", c_double_p), ("col", C.POINTER(C.c_uint32))]
 
 
+class LaplaceOpts(C.Structure):
+    _fields_ = [("max_newton", C.c_int32), ("richardson", C.c_int32), ("grad_tol", C.c_double), ("fd_step", C.c_double)]
+
+
+class LaplaceInfo(C.Structure):
+    _fields_ = [("joint", C.c_double), ("logdet", C.c_double), ("grad_max", C.c_double),
+                ("converged", C.c_int32), ("n_newton", C.c_int32), ("n_hess", C.c_int32),
+                ("n_value", C.c_int32), ("n_hvp", C.c_int32)]
+
+
 class EngineError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"smoothsde_b200 error {code} ({STATUS.get(code, '?')}): {msg}")
@@ -72,7 +82,9 @@ EXPORTS = ["ssde_create", "ssde_create_packed", "ssde_destroy", "ssde_n_par", "s
            "ssde_padded_rows", "ssde_layout_info", "ssde_pack_host", "ssde_pack_free",
            "ssde_simulate_ctcrw", "ssde_launch_info",
            "ssde_shard_elem_doubles", "ssde_eval_stage",
-           "ssde_hvp", "ssde_hvp_device", "ssde_hess_cols_device"]
+           "ssde_hvp", "ssde_hvp_device", "ssde_hess_cols_device",
+           "ssde_laplace_create", "ssde_laplace_destroy", "ssde_laplace_eval", "ssde_laplace_hessian_bb",
+           "ssde_laplace_error", "ssde_device", "ssde_stream"]
 
 
 def load():
@@ -138,6 +150,20 @@ def load():
     lib.ssde_hvp_device.restype = C.c_int
     lib.ssde_hess_cols_device.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp, vp]
     lib.ssde_hess_cols_device.restype = C.c_int
+    lib.ssde_laplace_create.argtypes = [vp, C.POINTER(LaplaceOpts), C.POINTER(vp)]
+    lib.ssde_laplace_create.restype = C.c_int
+    lib.ssde_laplace_destroy.argtypes = [vp]
+    lib.ssde_laplace_destroy.restype = None
+    lib.ssde_laplace_eval.argtypes = [vp, c_double_p, C.c_int, c_double_p, c_double_p, C.POINTER(LaplaceInfo)]
+    lib.ssde_laplace_eval.restype = C.c_int
+    lib.ssde_laplace_hessian_bb.argtypes = [vp, c_double_p]
+    lib.ssde_laplace_hessian_bb.restype = C.c_int
+    lib.ssde_laplace_error.argtypes = [vp]
+    lib.ssde_laplace_error.restype = C.c_char_p
+    lib.ssde_device.argtypes = [vp]
+    lib.ssde_device.restype = C.c_int
+    lib.ssde_stream.argtypes = [vp]
+    lib.ssde_stream.restype = vp
     lib.ssde_version.argtypes = []
     lib.ssde_version.restype = C.c_char_p
     _lib = lib

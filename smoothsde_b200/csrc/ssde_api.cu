@@ -940,6 +940,8 @@ void ssde_destroy(ssde_handle* h) {
 }
 
 int ssde_n_par(const ssde_handle* h) { return h ? h->npar : -1; }
+int ssde_device(const ssde_handle* h) { return h ? h->device : -1; }
+void* ssde_stream(const ssde_handle* h) { return h ? (void*)h->stream : nullptr; }
 
 int ssde_par_layout(const ssde_handle* h, int32_t offsets[4], int32_t sizes[4]) {
     if (!h) return SSDE_ERR_BAD_ARG;

@@ -41,12 +41,17 @@ class OracleEngine:
             g = g - pg if order >= 1 else None
         return v, g
 
-    def hvp(self, par, d, k=1e-3):
-        par, d = np.asarray(par, dtype=float), np.asarray(d, dtype=float)
+    def hvp(self, par, dirs, k=1e-3):
+        par, dirs = np.asarray(par, dtype=float), np.asarray(dirs, dtype=float)
         v, g = self.eval(par, 1)
-        d1 = (self.eval(par + k * d)[1] - self.eval(par - k * d)[1]) / (2 * k)
-        d2 = (self.eval(par + 0.5 * k * d)[1] - self.eval(par - 0.5 * k * d)[1]) / k
-        return v, g, (4 * d2 - d1) / 3
+        D = dirs.reshape(par.size, -1)
+        hv = np.zeros_like(D)
+        for j in range(D.shape[1]):
+            d = D[:, j]
+            d1 = (self.eval(par + k * d)[1] - self.eval(par - k * d)[1]) / (2 * k)
+            d2 = (self.eval(par + 0.5 * k * d)[1] - self.eval(par - 0.5 * k * d)[1]) / k
+            hv[:, j] = (4 * d2 - d1) / 3
+        return v, g, (hv[:, 0] if dirs.ndim == 1 else hv)
 
     def report(self, n, n_dim):
         return self.co.aest(self._last)

@@ -172,3 +172,22 @@ def test_laplace_marginal_matches_dense_gaussian_integral():
     exact = g0 + q @ bhat + 0.5 * bhat @ A @ bhat + 0.5 * np.linalg.slogdet(A)[1] - 0.5 * nb * np.log(2 * np.pi)
     assert abs(f - exact) < 1e-6 * max(1.0, abs(exact))
     assert np.allclose(obj._laplace.b, bhat, atol=1e-6)
+
+
+def test_laplace_gradient_matches_differences_of_the_marginal():
+    """grad f = g_theta + 1/2 (w_theta - H_theta,b H_bb^-1 w_b), w from third-derivative differences
+    of Hessian-vector products (laplace.py / csrc/ssde_laplace.cu), against central differences of
+    the Laplace value itself.  OU: the joint nllk is NOT quadratic in b (tau smooth)."""
+    from smoothsde_b200 import synth
+    dat, par, info = synth.make_problem("OU", 2, 60, n_dim=1, seed=12, k=5, re_id=False)
+    p_fe, n_s = info["p_fe"], info["n_s"]
+    pars = {"coeff_fe": par[:p_fe], "log_lambda": par[p_fe:p_fe + n_s], "coeff_re": par[p_fe + n_s:]}
+    obj = oracle_adfun(dat, pars, random="coeff_re")
+    x = obj.par + 0.05 * np.arange(obj.par.size)
+    f, g = obj._laplace.fn_gr(x)
+    assert obj._laplace.last["converged"] == 1
+    fd = np.empty(x.size)
+    for j in range(x.size):
+        e = np.zeros(x.size); e[j] = 1e-4
+        fd[j] = (obj.fn(x + e) - obj.fn(x - e)) / 2e-4
+    assert np.max(np.abs(g - fd)) <= 2e-5 * max(1.0, np.max(np.abs(fd))), (g, fd)
