@@ -13,14 +13,26 @@ MakeADFun_b200 <- function(data, parameters, map = list(), random = NULL, device
         f <- map[[nm]]
         group[idx] <- ifelse(is.na(f), NA, idx[match(f, f)])
     }
-    if(!is.null(random)) stop("random = 'coeff_re' needs the Laplace layer (see smoothsde_b200/laplace.py)")
-    active <- sort(unique(group[!is.na(group)]))
-    scatter <- function(x) { p <- full; ok <- !is.na(group); p[ok] <- x[match(group[ok], active)]; p }
+    is_random <- if(is.null(random)) rep(FALSE, length(full)) else names(full) %in% random
+    lap <- if(any(is_random)) .Call("ssde_laplace_new", ptr) else NULL
+    free <- sort(unique(group[!is.na(group)]))
+    active <- free[!is_random[free]]                  # what optim sees (obj$par); random effects are integrated out
     env <- new.env()
     env$last.par <- full; env$last.par.best <- full; env$value.best <- Inf
+    scatter <- function(x) {
+        p <- env$last.par                             # keeps coeff_re of the last inner optimum (warm start)
+        ok <- !is.na(group) & !is_random
+        p[ok] <- x[match(group[ok], active)]
+        p
+    }
     eval_full <- function(x, order) {
         p <- scatter(x)
-        out <- .Call("ssde_fn_gr", ptr, p, as.integer(order))
+        if(is.null(lap)) {
+            out <- .Call("ssde_fn_gr", ptr, p, as.integer(order))
+        } else {                                      # Laplace marginal: inner Newton + Cholesky on the device
+            out <- .Call("ssde_laplace_fn_gr", lap, p, as.integer(order))
+            p <- out$par
+        }
         env$last.par <- p
         if(is.finite(out$value) && out$value < env$value.best) { env$value.best <- out$value; env$last.par.best <- p }
         out
@@ -29,8 +41,14 @@ MakeADFun_b200 <- function(data, parameters, map = list(), random = NULL, device
          fn = function(x = full[active], ...) eval_full(x, 0L)$value,
          gr = function(x = full[active], ...) {
              g <- eval_full(x, 1L)$gradient
-             ok <- !is.na(group)
+             ok <- !is.na(group) & !is_random
              matrix(tapply(g[ok], match(group[ok], active), sum), nrow = 1)
+         },
+         he = function(x = full[active], ...) {       # joint object only (R/sde.R:1363)
+             H <- .Call("ssde_he", ptr, scatter(x))
+             ok <- which(!is.na(group)); k <- match(group[ok], active)
+             A <- matrix(0, length(active), length(ok)); A[cbind(k, seq_along(ok))] <- 1
+             A %*% H[ok, ok] %*% t(A)
          },
          report = function(...) list(aest_all = .Call("ssde_aest", ptr, nrow(data$obs), ncol(data$obs))),
          env = env, ptr = ptr)

@@ -9,6 +9,9 @@ extern SEXP ssde_make(SEXP, SEXP);
 extern SEXP ssde_fn_gr(SEXP, SEXP, SEXP);
 extern SEXP ssde_layout(SEXP);
 extern SEXP ssde_aest(SEXP, SEXP, SEXP);
+extern SEXP ssde_he(SEXP, SEXP);
+extern SEXP ssde_laplace_new(SEXP);
+extern SEXP ssde_laplace_fn_gr(SEXP, SEXP, SEXP);
 extern SEXP ssde_free(SEXP);
 
 static const R_CallMethodDef CallEntries[] = {
@@ -16,6 +19,9 @@ static const R_CallMethodDef CallEntries[] = {
     {"ssde_fn_gr",  (DL_FUNC) &ssde_fn_gr,  3},
     {"ssde_layout", (DL_FUNC) &ssde_layout, 1},
     {"ssde_aest",   (DL_FUNC) &ssde_aest,   3},
+    {"ssde_he",     (DL_FUNC) &ssde_he,     2},
+    {"ssde_laplace_new",   (DL_FUNC) &ssde_laplace_new,   1},
+    {"ssde_laplace_fn_gr", (DL_FUNC) &ssde_laplace_fn_gr, 3},
     {"ssde_free",   (DL_FUNC) &ssde_free,   1},
     {NULL, NULL, 0}
 };

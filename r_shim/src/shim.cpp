@@ -4,6 +4,8 @@
 //   MakeADFunObject(data, parameters, reportenv, control)  ->  ssde_make(data, device)
 //   EvalADFunObject(ptr, theta, control)                   ->  ssde_fn_gr(ptr, par, order)
 //   REPORT(aest_all) via the report environment            ->  ssde_aest(ptr)
+//   MakeADHessObject2 (obj$he, the Laplace inner problem)  ->  ssde_he(ptr, par), ssde_laplace_new /
+//                                                              ssde_laplace_fn_gr(lap, par, order)
 // `map` / `random` stay on the R side (r_shim/R/adfun.R), exactly as in TMB's own R layer.
 #include <R.h>
 #include <Rinternals.h>
@@ -127,6 +129,59 @@ SEXP ssde_aest(SEXP ptr, SEXP n, SEXP n_dim) {
     int rc = ssde_report(h, REAL(out));
     UNPROTECT(1);
     if (rc != SSDE_OK) Rf_error("smoothsde_b200: %s", ssde_last_error(h));
+    return out;
+}
+
+// obj$he(par): joint Hessian [n_par x n_par] of the penalised objective (R/sde.R:1363)
+SEXP ssde_he(SEXP ptr, SEXP par) {
+    ssde_handle* h = (ssde_handle*)R_ExternalPtrAddr(ptr);
+    if (!h) Rf_error("smoothsde_b200: handle was freed");
+    const int np = ssde_n_par(h);
+    if (Rf_xlength(par) != np) Rf_error("smoothsde_b200: parameter vector has length %d, expected %d", (int)Rf_xlength(par), np);
+    SEXP H = PROTECT(Rf_allocMatrix(REALSXP, np, np));
+    SEXP g = PROTECT(Rf_allocVector(REALSXP, np));
+    double v;
+    int rc = ssde_eval(h, REAL(par), 2, &v, REAL(g), REAL(H));
+    UNPROTECT(2);
+    if (rc != SSDE_OK) Rf_error("smoothsde_b200: %s", ssde_last_error(h));
+    return H;
+}
+
+// Laplace-marginal object (random = "coeff_re", R/sde.R:522-524): workspace tied to a handle
+static void lap_finalizer(SEXP ptr) {
+    ssde_laplace* w = (ssde_laplace*)R_ExternalPtrAddr(ptr);
+    if (w) { ssde_laplace_destroy(w); R_ClearExternalPtr(ptr); }
+}
+SEXP ssde_laplace_new(SEXP ptr) {
+    ssde_handle* h = (ssde_handle*)R_ExternalPtrAddr(ptr);
+    ssde_laplace* w = NULL;
+    if (ssde_laplace_create(h, NULL, &w) != SSDE_OK) Rf_error("smoothsde_b200: ssde_laplace_create failed");
+    SEXP out = PROTECT(R_MakeExternalPtr(w, R_NilValue, ptr));      // keeps the engine handle alive
+    R_RegisterCFinalizerEx(out, lap_finalizer, TRUE);
+    UNPROTECT(1);
+    return out;
+}
+// list(value = f(theta), gradient [full length, 0 in the coeff_re slots], par = full vector with
+// coeff_re at the inner optimum); `par` carries the starting value of coeff_re
+SEXP ssde_laplace_fn_gr(SEXP lap, SEXP par, SEXP order) {
+    ssde_laplace* w = (ssde_laplace*)R_ExternalPtrAddr(lap);
+    if (!w) Rf_error("smoothsde_b200: Laplace workspace was freed");
+    const int np = (int)Rf_xlength(par), ord = Rf_asInteger(order);
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 3));
+    SEXP val = PROTECT(Rf_allocVector(REALSXP, 1));
+    SEXP grad = PROTECT(Rf_allocVector(REALSXP, ord >= 1 ? np : 0));
+    SEXP p = PROTECT(Rf_duplicate(par));
+    int rc = ssde_laplace_eval(w, REAL(p), ord, REAL(val), ord >= 1 ? REAL(grad) : NULL, NULL);
+    if (rc != SSDE_OK && rc != SSDE_ERR_NUMERIC) { UNPROTECT(4); Rf_error("smoothsde_b200: %s", ssde_laplace_error(w)); }
+    SET_VECTOR_ELT(out, 0, val);
+    SET_VECTOR_ELT(out, 1, grad);
+    SET_VECTOR_ELT(out, 2, p);
+    SEXP nm = PROTECT(Rf_allocVector(STRSXP, 3));
+    SET_STRING_ELT(nm, 0, Rf_mkChar("value"));
+    SET_STRING_ELT(nm, 1, Rf_mkChar("gradient"));
+    SET_STRING_ELT(nm, 2, Rf_mkChar("par"));
+    Rf_setAttrib(out, R_NamesSymbol, nm);
+    UNPROTECT(5);
     return out;
 }
 
