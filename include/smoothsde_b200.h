@@ -216,6 +216,10 @@ int ssde_laplace_eval(ssde_laplace* w, double* par, int order, double* value, do
 int ssde_laplace_hessian_bb(ssde_laplace* w, double* hess_bb);
 const char* ssde_laplace_error(const ssde_laplace* w);
 
+/* Diagnostics (libraries built with -DSSDE_STATS only, else SSDE_ERR_UNSUPPORTED): look-back and
+ * per-phase cycle counters of the scan kernels, [0..15] forward, [16..31] adjoint. */
+int ssde_debug_stats(ssde_handle* h, uint64_t out[32], int reset);
+
 /* The handle's CUDA device ordinal and its own stream (a cudaStream_t). */
 int ssde_device(const ssde_handle* h);
 void* ssde_stream(const ssde_handle* h);

@@ -29,8 +29,10 @@ def _collect(rep, kre, lib):
     sass = rd[1:]
     tmp = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, capture_output=True)
-    cubin = [os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-    dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout.splitlines()
+    dis = []
+    for f in sorted(os.listdir(tmp)):
+        if f.endswith(".cubin"):
+            dis += subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, f)], capture_output=True, text=True).stdout.splitlines()
     funcs = {}
     cur, curline = None, None
     for l in dis:

@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libsmoothsde_b200.so")
+LIB_PATH = os.path.join(HERE, "lib", "libsmoothsde_b200" + os.environ.get("SSDE_LIB_SUFFIX", "") + ".so")
 
 c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)
@@ -84,7 +84,7 @@ EXPORTS = ["ssde_create", "ssde_create_packed", "ssde_destroy", "ssde_n_par", "s
            "ssde_shard_elem_doubles", "ssde_eval_stage",
            "ssde_hvp", "ssde_hvp_device", "ssde_hess_cols_device",
            "ssde_laplace_create", "ssde_laplace_destroy", "ssde_laplace_eval", "ssde_laplace_hessian_bb",
-           "ssde_laplace_error", "ssde_device", "ssde_stream"]
+           "ssde_laplace_error", "ssde_device", "ssde_stream", "ssde_debug_stats"]
 
 
 def load():
@@ -160,6 +160,8 @@ def load():
     lib.ssde_laplace_hessian_bb.restype = C.c_int
     lib.ssde_laplace_error.argtypes = [vp]
     lib.ssde_laplace_error.restype = C.c_char_p
+    lib.ssde_debug_stats.argtypes = [vp, C.POINTER(C.c_uint64), C.c_int]
+    lib.ssde_debug_stats.restype = C.c_int
     lib.ssde_device.argtypes = [vp]
     lib.ssde_device.restype = C.c_int
     lib.ssde_stream.argtypes = [vp]

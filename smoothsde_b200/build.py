@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
-LIB = os.path.join(LIBDIR, "libsmoothsde_b200.so")
+LIB = os.path.join(LIBDIR, "libsmoothsde_b200" + os.environ.get("SSDE_LIB_SUFFIX", "") + ".so")   # suffix: diagnostics builds
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -45,7 +45,8 @@ def build(force=False, verbose=False):
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources() + LINK_FLAGS
+    extra = os.environ.get("SSDE_NVCC_EXTRA", "").split()      # e.g. -DSSDE_STATS for the diagnostics build
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources() + LINK_FLAGS
     subprocess.check_call(cmd)
     return LIB
 

@@ -130,6 +130,9 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(CtcrwArgs<ND, R> a)
         __syncthreads();
         const int tile = sm.ticket[par];
         if (tile >= a.ntiles) break;
+#ifdef SSDE_STATS
+        long long tc0 = clock64(), tc1 = 0, tc2 = 0, tc3 = 0;
+#endif
         const int64_t q = (int64_t)tile * NWARP + warp;
         const int64_t base = q * WT + lane;
         const int64_t row0 = q * WT + (int64_t)lane * LC;
@@ -180,7 +183,13 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(CtcrwArgs<ND, R> a)
         if (lane == 31) store_elem(sm.wagg[par][warp], inc);
         Elem exc = shfl_up_elem(inc, 1);
         if (lane == 0) exc = fwd_identity<ND, R>();
+#ifdef SSDE_STATS
+        tc1 = clock64();
+#endif
         __syncthreads();
+#ifdef SSDE_STATS
+        tc2 = clock64();
+#endif
         // (3) the last warp composes and publishes the tile aggregate while warp 0 looks back over
         //     the earlier tiles; warp 0 then publishes the inclusive prefix and the tile start state
         if (warp == NWARP - 1) {
@@ -207,6 +216,9 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(CtcrwArgs<ND, R> a)
         }
         __syncthreads();
         if (warp == 0 && lane == 0) publish_incl<Ops>(a.fdesc, tile, fwd_combine<ND>(pre, load_elem<Elem>(sm.tagg[par])));
+#ifdef SSDE_STATS
+        tc3 = clock64();
+#endif
         if (a.summary) continue;
         // (4) exact start state of this thread, checkpoint, plain filter re-run
         St s = load_state<ND, R>(sm.misc[par]);
@@ -261,6 +273,15 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(CtcrwArgs<ND, R> a)
         }
         const double llk = warp_sum(value(-0.5 * ((double)ND * (slog + log(fprod)) + quad)));
         if (lane == 0) a.tile_llk[q] = llk;              // one partial per warp-tile
+#ifdef SSDE_STATS
+        if (lane == 0) {                                 // per-warp phase cycles: 4 + 4*warp-class (warp 0 / others)
+            unsigned long long* st_ = a.fdesc.stats + 4 + (warp == 0 ? 0 : 4);
+            atomicAdd(st_ + 0, (unsigned long long)(tc1 - tc0));        // phase 1-2 (elements + warp scan)
+            atomicAdd(st_ + 1, (unsigned long long)(tc2 - tc1));        // first barrier
+            atomicAdd(st_ + 2, (unsigned long long)(tc3 - tc2));        // aggregate / look-back / second barrier
+            atomicAdd(st_ + 3, (unsigned long long)(clock64() - tc3));  // phase 4 (re-run)
+        }
+#endif
     }
 }
 

@@ -69,6 +69,7 @@ struct ssde_handle {
     DevBuf par, theta, grad_theta, wg, ckpt, tile_llk, tile_gh, block_llk, part, out, sb;
     DevBuf f_status, f_agg, f_incl, b_status, b_agg, b_incl, counters;   // counters: ticket_f, ticket_b, error
     DevBuf aest;
+    DevBuf stats;                    // diagnostics build (SSDE_STATS) only
     DevBuf s_in, g_in;               // incoming state / adjoint of a time shard (2 n_dim + 3 doubles each)
     bool have_s_in = false, have_g_in = false;
     // tangent (Hessian-vector) pass: Dual-sized copies of the work buffers, allocated on first use
@@ -585,6 +586,8 @@ int finish_setup(ssde_handle* h) {
     if ((rc = dev_alloc<int>(h->mu_zero, 1, err))) return rc;
     CUDA_TRY(cudaMemset(h->mu_zero.p, 0, sizeof(int)));
     if (!h->mu_cols.p && (rc = dev_alloc<int32_t>(h->mu_cols, 1, err))) return rc;
+    if ((rc = dev_alloc<unsigned long long>(h->stats, 32, err))) return rc;
+    CUDA_TRY(cudaMemset(h->stats.p, 0, 32 * sizeof(unsigned long long)));
     if ((rc = dev_alloc<unsigned>(h->counters, 4, err))) return rc;
     CUDA_TRY(cudaMemset(h->counters.p, 0, 4 * sizeof(unsigned)));
     CUDA_TRY(cudaMallocHost(&h->h_pinned, sizeof(double) * (2 * (size_t)h->npar + 4)));
@@ -676,6 +679,10 @@ CtcrwArgs<ND, R> ctcrw_args(ssde_handle* h, const double* d_par, const double* d
     unsigned* cnt = h->counters.as<unsigned>();
     a.fdesc = {h->f_status.as<unsigned>(), (TAN ? h->t_f_agg : h->f_agg).as<double>(), (TAN ? h->t_f_incl : h->f_incl).as<double>(), cnt + 0, cnt + 2, h->epoch};
     a.bdesc = {h->b_status.as<unsigned>(), (TAN ? h->t_b_agg : h->b_agg).as<double>(), (TAN ? h->t_b_incl : h->b_incl).as<double>(), cnt + 1, cnt + 2, h->epoch};
+#ifdef SSDE_STATS
+    a.fdesc.stats = h->stats.as<unsigned long long>();
+    a.bdesc.stats = h->stats.as<unsigned long long>() + 16;
+#endif
     a.ntiles = h->ntiles_f;
     a.summary = 0;
     return a;
@@ -940,6 +947,20 @@ void ssde_destroy(ssde_handle* h) {
 }
 
 int ssde_n_par(const ssde_handle* h) { return h ? h->npar : -1; }
+int ssde_debug_stats(ssde_handle* h, uint64_t out[32], int reset) {
+    if (!h || !out) return SSDE_ERR_BAD_ARG;
+    std::string& err = h->err;
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(out, h->stats.p, 32 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    if (reset) CUDA_TRY(cudaMemset(h->stats.p, 0, 32 * sizeof(uint64_t)));
+#ifdef SSDE_STATS
+    return SSDE_OK;
+#else
+    err = "library was built without SSDE_STATS";
+    return SSDE_ERR_UNSUPPORTED;
+#endif
+}
 int ssde_device(const ssde_handle* h) { return h ? h->device : -1; }
 void* ssde_stream(const ssde_handle* h) { return h ? (void*)h->stream : nullptr; }
 
