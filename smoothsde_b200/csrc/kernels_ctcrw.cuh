@@ -193,9 +193,9 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(CtcrwArgs<ND, R> a)
         // (3) the last warp composes and publishes the tile aggregate while warp 0 looks back over
         //     the earlier tiles; warp 0 then publishes the inclusive prefix and the tile start state
         if (warp == NWARP - 1) {
-            Elem tagg = load_elem<Elem>(sm.wagg[par][0]);
+            Elem tagg = load_elem<Elem>(sm.wagg[par][NWARP - 1]);
 #pragma unroll 1
-            for (int ww = 1; ww < NWARP; ++ww) tagg = fwd_combine<ND>(tagg, load_elem<Elem>(sm.wagg[par][ww]));
+            for (int ww = NWARP - 2; ww >= 0 && !Ops::is_const(tagg); --ww) tagg = fwd_combine<ND>(load_elem<Elem>(sm.wagg[par][ww]), tagg);
             if (lane == 0) { publish_agg<Ops>(a.fdesc, tile, tagg); store_elem(sm.tagg[par], tagg); }
         }
         Elem pre;
@@ -221,9 +221,14 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(CtcrwArgs<ND, R> a)
 #endif
         if (a.summary) continue;
         // (4) exact start state of this thread, checkpoint, plain filter re-run
+        // warp aggregates in front of this warp, starting at the nearest constant map (warp-uniform)
         St s = load_state<ND, R>(sm.misc[par]);
+        {
+            int w0 = warp - 1;
+            while (w0 > 0 && !Ops::is_const(load_elem<Elem>(sm.wagg[par][w0]))) --w0;
 #pragma unroll 1
-        for (int ww = 0; ww < warp; ++ww) s = fwd_apply<ND>(load_elem<Elem>(sm.wagg[par][ww]), s);
+            for (int ww = max(w0, 0); ww < warp; ++ww) s = fwd_apply<ND>(load_elem<Elem>(sm.wagg[par][ww]), s);
+        }
         s = fwd_apply<ND>(exc, s);
         const int64_t chunk = q * 32 + lane;
         {
@@ -426,9 +431,10 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_bwd_kernel(CtcrwArgs<ND, R> a)
         //     the LATER tiles; warp 0 then publishes the inclusive suffix and the adjoint entering
         //     the tile end
         if (warp == NWARP - 1) {
-            Elem tagg = load_elem<Elem>(sm.wagg[par][NWARP - 1]);
+            // the adjoint flows from later rows to earlier ones: start with the EARLIEST warp
+            Elem tagg = load_elem<Elem>(sm.wagg[par][0]);
 #pragma unroll 1
-            for (int ww = NWARP - 2; ww >= 0; --ww) tagg = bwd_combine<ND>(load_elem<Elem>(sm.wagg[par][ww]), tagg);
+            for (int ww = 1; ww < NWARP && !Ops::is_const(tagg); ++ww) tagg = bwd_combine<ND>(tagg, load_elem<Elem>(sm.wagg[par][ww]));
             if (lane == 0) { publish_agg<Ops>(a.bdesc, ticket, tagg); store_elem(sm.tagg[par], tagg); }
         }
         Elem suf;
@@ -447,8 +453,12 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_bwd_kernel(CtcrwArgs<ND, R> a)
         if (a.summary) continue;
         // (4) adjoint entering this thread's last row, then the reverse sweep over its rows
         Ad g = load_adj<ND, R>(sm.misc[par]);
+        {
+            int w1 = warp + 1;
+            while (w1 < NWARP - 1 && !Ops::is_const(load_elem<Elem>(sm.wagg[par][w1]))) ++w1;
 #pragma unroll 1
-        for (int ww = NWARP - 1; ww > warp; --ww) g = bwd_apply<ND>(load_elem<Elem>(sm.wagg[par][ww]), g);
+            for (int ww = min(w1, NWARP - 1); ww > warp; --ww) g = bwd_apply<ND>(load_elem<Elem>(sm.wagg[par][ww]), g);
+        }
         g = bwd_apply<ND>(exc, g);
         R gh = 0.0;
         nx = load_row<ND, R>(a, base + (LC - 1) * 32, (uint8_t)(fl >> (8 * (LC - 1))) != 0xff);
