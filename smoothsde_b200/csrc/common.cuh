@@ -236,6 +236,7 @@ __device__ __forceinline__ typename Ops::Elem lookback(const ScanDesc& d, int t)
     using Elem = typename Ops::Elem;
     const int lane = threadIdx.x & 31;
     Elem acc = Ops::identity();
+    bool have = false;                                     // acc still is the identity: no need to join
     int base = t - 1;
 #ifdef SSDE_STATS
     const long long c0 = clock64();
@@ -285,7 +286,8 @@ __device__ __forceinline__ typename Ops::Elem lookback(const ScanDesc& d, int t)
             if (lane + o < 32) e = Ops::join(f, e);
         }
         e = shfl_idx_elem(e, 0);
-        acc = Ops::join(e, acc);
+        acc = have ? Ops::join(e, acc) : e;
+        have = true;
         if (first < 32) break;
         base -= 32;
     }

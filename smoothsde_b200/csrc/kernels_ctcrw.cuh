@@ -101,6 +101,7 @@ struct FwdSmem {
     R th[NT / 32][TH_CACHE];
     uint64_t bar[NT / 32];
     int ticket[2];
+    int early[2];                    // the tile aggregate was published before the barrier
 };
 
 template <int ND, int NT, int MINB, class R = double>
@@ -142,16 +143,26 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(CtcrwArgs<ND, R> a)
 
         // (1) thread element over its LC rows
         Elem E = fwd_identity<ND, R>();
+        // dt and the observations of a row are fetched one row ahead of their use
+        double dt_nx = ((uint8_t)fl != 0xff) ? a.dt[base] : 1.0, y_nx[ND];
+#pragma unroll
+        for (int d = 0; d < ND; ++d) y_nx[d] = ((uint8_t)fl != 0xff) ? a.obs[(size_t)d * a.X.n_pad + base] : 0.0;
 #pragma unroll 1
         for (int k = 0; k < LC; ++k) {
             const int64_t pos = base + k * 32;
             const uint8_t f = (uint8_t)(fl >> (8 * k));
             const bool live = f != 0xff;
             const bool step = live && !(f & ROW_START);
-            const double dtv = live ? a.dt[pos] : 1.0;
+            const double dtv = dt_nx;
             double y[ND];
 #pragma unroll
-            for (int d = 0; d < ND; ++d) y[d] = step ? a.obs[(size_t)d * a.X.n_pad + pos] : 0.0;
+            for (int d = 0; d < ND; ++d) y[d] = y_nx[d];
+            if (k + 1 < LC) {
+                const bool live1 = (uint8_t)(fl >> (8 * (k + 1))) != 0xff;
+                dt_nx = live1 ? a.dt[pos + 32] : 1.0;
+#pragma unroll
+                for (int d = 0; d < ND; ++d) y_nx[d] = live1 ? a.obs[(size_t)d * a.X.n_pad + pos + 32] : 0.0;
+            }
             R eta[NP];
             if (w.staged) {
                 stage_wait(st);
@@ -180,7 +191,16 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(CtcrwArgs<ND, R> a)
             Elem f = shfl_up_elem(inc, o);
             if (lane >= o) inc = fwd_combine<ND>(f, inc);
         }
-        if (lane == 31) store_elem(sm.wagg[par][warp], inc);
+        if (lane == 31) {
+            store_elem(sm.wagg[par][warp], inc);
+            if (warp == NWARP - 1) {
+                // the last warp's rows alone usually form a constant map already: then they ARE the
+                // tile aggregate and later tiles need not wait for this CTA's barrier
+                const bool c = Ops::is_const(inc);
+                sm.early[par] = c ? 1 : 0;
+                if (c) { publish_agg<Ops>(a.fdesc, tile, inc); store_elem(sm.tagg[par], inc); }
+            }
+        }
         Elem exc = shfl_up_elem(inc, 1);
         if (lane == 0) exc = fwd_identity<ND, R>();
 #ifdef SSDE_STATS
@@ -192,7 +212,7 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(CtcrwArgs<ND, R> a)
 #endif
         // (3) the last warp composes and publishes the tile aggregate while warp 0 looks back over
         //     the earlier tiles; warp 0 then publishes the inclusive prefix and the tile start state
-        if (warp == NWARP - 1) {
+        if (warp == NWARP - 1 && !sm.early[par]) {
             Elem tagg = load_elem<Elem>(sm.wagg[par][NWARP - 1]);
 #pragma unroll 1
             for (int ww = NWARP - 2; ww >= 0 && !Ops::is_const(tagg); --ww) tagg = fwd_combine<ND>(load_elem<Elem>(sm.wagg[par][ww]), tagg);
@@ -215,7 +235,12 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(CtcrwArgs<ND, R> a)
             }
         }
         __syncthreads();
-        if (warp == 0 && lane == 0) publish_incl<Ops>(a.fdesc, tile, fwd_combine<ND>(pre, load_elem<Elem>(sm.tagg[par])));
+        if (warp == 0 && lane == 0) {
+            // a constant-map aggregate already serves as the inclusive prefix (status code 3); the
+            // summary pass of a time shard reads the last tile's inclusive element from f_incl
+            const Elem tagg = load_elem<Elem>(sm.tagg[par]);
+            if (a.summary || !Ops::is_const(tagg)) publish_incl<Ops>(a.fdesc, tile, fwd_combine<ND>(pre, tagg));
+        }
 #ifdef SSDE_STATS
         tc3 = clock64();
 #endif
@@ -244,22 +269,30 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(CtcrwArgs<ND, R> a)
         // sum_i log F_i is taken as the log of a running product (one log per chunk instead of
         // one per row); the product is folded into `slog` whenever it leaves a safe range.
         R quad = 0.0, fprod = 1.0, slog = 0.0;
+        dt_nx = ((uint8_t)fl != 0xff) ? a.dt[base] : 1.0;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) y_nx[d] = ((uint8_t)fl != 0xff) ? a.obs[(size_t)d * a.X.n_pad + base] : 0.0;
 #pragma unroll 1
         for (int k = 0; k < LC; ++k) {
             const uint8_t f = (uint8_t)(fl >> (8 * k));
             if (f == 0xff) break;
             const int64_t pos = base + k * 32;
-            const double dtv = a.dt[pos];
+            const double dtv = dt_nx;
+            double y[ND];
+#pragma unroll
+            for (int d = 0; d < ND; ++d) y[d] = y_nx[d];
+            if (k + 1 < LC && (uint8_t)(fl >> (8 * (k + 1))) != 0xff) {
+                dt_nx = a.dt[pos + 32];
+#pragma unroll
+                for (int d = 0; d < ND; ++d) y_nx[d] = a.obs[(size_t)d * a.X.n_pad + pos + 32];
+            }
             if (f & ROW_START) {
                 s = track_start_state<ND>(a, dtv);
             } else {
                 R mu[ND];
-                double y[ND];
 #pragma unroll
                 for (int d = 0; d < ND; ++d) mu[d] = 0.0;
                 if (!mu0) row_eta_prefix<ND>(w, k, a.theta, mu);
-#pragma unroll
-                for (int d = 0; d < ND; ++d) y[d] = a.obs[(size_t)d * a.X.n_pad + pos];
                 StepParT<R> sp;
                 sp.T12 = sm.W[k][0][tid]; sp.e = sm.W[k][1][tid];
                 sp.Q.a = sm.W[k][2][tid]; sp.Q.b = sm.W[k][3][tid]; sp.Q.c = sm.W[k][4][tid];
@@ -316,6 +349,7 @@ struct BwdSmem {
     R th[NT / 32][TH_CACHE];
     R sgrad[SGRAD];
     int ticket[2];
+    int early[2];
 };
 
 // per-row inputs of the adjoint sweep, fetched one row ahead
@@ -423,14 +457,21 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_bwd_kernel(CtcrwArgs<ND, R> a)
             Elem f = shfl_down_elem(inc, o);
             if (lane + o < 32) inc = bwd_combine<ND>(inc, f);
         }
-        if (lane == 0) store_elem(sm.wagg[par][warp], inc);
+        if (lane == 0) {
+            store_elem(sm.wagg[par][warp], inc);
+            if (warp == 0) {                     // the earliest rows decide (adjoint flows backwards in time)
+                const bool c = Ops::is_const(inc);
+                sm.early[par] = c ? 1 : 0;
+                if (c) { publish_agg<Ops>(a.bdesc, ticket, inc); store_elem(sm.tagg[par], inc); }
+            }
+        }
         Elem exc = shfl_down_elem(inc, 1);
         if (lane == 31) exc = bwd_identity<ND, R>();
         __syncthreads();
         // (3) the last warp composes and publishes the tile aggregate while warp 0 looks back over
         //     the LATER tiles; warp 0 then publishes the inclusive suffix and the adjoint entering
         //     the tile end
-        if (warp == NWARP - 1) {
+        if (warp == NWARP - 1 && !sm.early[par]) {
             // the adjoint flows from later rows to earlier ones: start with the EARLIEST warp
             Elem tagg = load_elem<Elem>(sm.wagg[par][0]);
 #pragma unroll 1
@@ -449,7 +490,10 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_bwd_kernel(CtcrwArgs<ND, R> a)
             }
         }
         __syncthreads();
-        if (warp == 0 && lane == 0) publish_incl<Ops>(a.bdesc, ticket, bwd_combine<ND>(load_elem<Elem>(sm.tagg[par]), suf));
+        if (warp == 0 && lane == 0) {
+            const Elem tagg = load_elem<Elem>(sm.tagg[par]);
+            if (a.summary || !Ops::is_const(tagg)) publish_incl<Ops>(a.bdesc, ticket, bwd_combine<ND>(tagg, suf));
+        }
         if (a.summary) continue;
         // (4) adjoint entering this thread's last row, then the reverse sweep over its rows
         Ad g = load_adj<ND, R>(sm.misc[par]);
