@@ -31,3 +31,5 @@ for nm, o in (("fwd", 0), ("bwd", 16)):
     wo = s[o + 8:o + 12] / (3 * ntile)
     print(f"  warp 0 : phase1-2 {w0[0]:.0f}  barrier1 {w0[1]:.0f}  agg/look-back/barrier2 {w0[2]:.0f}  phase4 {w0[3]:.0f}  cycles per tile")
     print(f"  warps1-3: phase1-2 {wo[0]:.0f}  barrier1 {wo[1]:.0f}  agg/look-back/barrier2 {wo[2]:.0f}  phase4 {wo[3]:.0f}")
+    if nm == "bwd":
+        print(f"  X'eta_bar scatter: warp 0 {s[o + 12] / ntile:.0f}  warps1-3 {s[o + 13] / (3 * ntile):.0f}")

@@ -400,6 +400,9 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_bwd_kernel(CtcrwArgs<ND, R> a)
         const int ticket = sm.ticket[par];
         if (ticket >= a.ntiles) break;
         const int tile = a.ntiles - 1 - ticket;           // reverse time order
+#ifdef SSDE_STATS
+        long long tc0 = clock64(), tc1 = 0, tc2 = 0, tc3 = 0;
+#endif
         const int64_t q = (int64_t)tile * NWARP + warp;
         const int64_t base = q * WT + lane;
         const int64_t chunk = q * 32 + lane;
@@ -467,7 +470,13 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_bwd_kernel(CtcrwArgs<ND, R> a)
         }
         Elem exc = shfl_down_elem(inc, 1);
         if (lane == 31) exc = bwd_identity<ND, R>();
+#ifdef SSDE_STATS
+        tc1 = clock64();
+#endif
         __syncthreads();
+#ifdef SSDE_STATS
+        tc2 = clock64();
+#endif
         // (3) the last warp composes and publishes the tile aggregate while warp 0 looks back over
         //     the LATER tiles; warp 0 then publishes the inclusive suffix and the adjoint entering
         //     the tile end
@@ -494,6 +503,9 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_bwd_kernel(CtcrwArgs<ND, R> a)
             const Elem tagg = load_elem<Elem>(sm.tagg[par]);
             if (a.summary || !Ops::is_const(tagg)) publish_incl<Ops>(a.bdesc, ticket, bwd_combine<ND>(tagg, suf));
         }
+#ifdef SSDE_STATS
+        tc3 = clock64();
+#endif
         if (a.summary) continue;
         // (4) adjoint entering this thread's last row, then the reverse sweep over its rows
         Ad g = load_adj<ND, R>(sm.misc[par]);
@@ -547,6 +559,9 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_bwd_kernel(CtcrwArgs<ND, R> a)
 #pragma unroll
             for (int j = 0; j < NP; ++j) sm.Rs[k][j][tid] = gp[j];
         }
+#ifdef SSDE_STATS
+        const long long tc35 = clock64();
+#endif
         // (5) grad_theta += X' eta_bar for this warp-tile
         if (w.uniform && w.S <= TCAP) {
             scatter_warptile_transposed<NP, R>(w, gacc, [&](int k, int p) { return sm.Rs[k][p][tid]; },
@@ -554,7 +569,20 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_bwd_kernel(CtcrwArgs<ND, R> a)
         } else {
             scatter_warptile<NP, R>(w, gacc, [&](int k, int p) { return sm.Rs[k][p][tid]; });
         }
+#ifdef SSDE_STATS
+        const long long tc4 = clock64();
+#endif
         gh = warp_sum(gh);
+#ifdef SSDE_STATS
+        if (lane == 0) {
+            unsigned long long* st_ = a.bdesc.stats + 4 + (warp == 0 ? 0 : 4);
+            atomicAdd(st_ + 0, (unsigned long long)(tc1 - tc0));
+            atomicAdd(st_ + 1, (unsigned long long)(tc2 - tc1));
+            atomicAdd(st_ + 2, (unsigned long long)(tc3 - tc2));
+            atomicAdd(st_ + 3, (unsigned long long)(tc35 - tc3));
+            atomicAdd(a.bdesc.stats + 12 + (warp == 0 ? 0 : 1), (unsigned long long)(tc4 - tc35));
+        }
+#endif
         if (lane == 0) {                                 // one partial per warp-tile
             a.tile_gh[q] = value(gh);
             if constexpr (!std::is_same<R, double>::value) a.tile_gh[a.X.n_pad / WT + q] = gh.d;
