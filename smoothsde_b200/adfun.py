@@ -145,6 +145,61 @@ class ADFun:
         self._remember(v, p)
         return self.reduce_grad(g, self._active)
 
+    def _reduce_hess(self, H_full, idx):
+        """Hessian w.r.t. the free groups `idx` from the full-vector Hessian (tied entries add up)."""
+        ok = np.flatnonzero(self._group >= 0)
+        pos = {g: k for k, g in enumerate(idx)}
+        A = np.zeros((len(idx), self._full0.size))
+        for i in ok:
+            k = pos.get(self._group[i])
+            if k is not None:
+                A[k, i] = 1.0
+        return A @ H_full @ A.T
+
+    def he(self, x=None):
+        """obj$he(x): exact Hessian of the objective w.r.t. obj$par (joint objects only, as in TMB;
+        used by edf_conditional, R/sde.R:1363)."""
+        if self._laplace is not None:
+            raise NotImplementedError("Hessian is not yet implemented for models with random effects (TMB says the same)")
+        x = self.par if x is None else x
+        p = self.full_from(x)
+        _, _, H = self.engine.hessian(p)
+        self.env.last_par = p.copy()
+        return self._reduce_hess(H, self._active)
+
+    def sdreport(self, x=None, step=1e-4):
+        """What SDE$fit() takes from TMB::sdreport(obj, getJointPrecision = TRUE) (R/sde.R:702-719,
+        :886-887): par.fixed, par.random, cov.fixed and the joint precision of (fixed, random) in
+        the order of the full free parameter vector.  Without random effects the joint precision is
+        the exact Hessian.  With random effects (TMB's formula): H_f = Hessian of the Laplace
+        marginal (central differences of its gradient, like optimHess), H_bb and G = H_b,theta from
+        the exact joint Hessian at (theta, b_hat):  Q = [[H_f + G' H_bb^-1 G, G'], [G, H_bb]]."""
+        x = np.asarray(self.par if x is None else x, dtype=float)
+        if self._laplace is None:
+            H = self.he(x)
+            return {"par_fixed": x.copy(), "par_random": np.zeros(0), "cov_fixed": np.linalg.inv(H),
+                    "jointPrecision": H, "names": list(self.names), "order": self._active.copy()}
+        f, _ = self._laplace.fn_gr(x)
+        p = self.env.last_par.copy()                          # (theta, b_hat)
+        nt = x.size
+        Hf = np.empty((nt, nt))
+        for j in range(nt):
+            h = step * max(1.0, abs(x[j]))
+            e = np.zeros(nt)
+            e[j] = h
+            Hf[:, j] = (self._laplace.fn_gr(x + e)[1] - self._laplace.fn_gr(x - e)[1]) / (2 * h)
+        Hf = 0.5 * (Hf + Hf.T)
+        self._laplace.fn_gr(x)                                # leave b_hat / last_par at the optimum
+        _, _, H = self.engine.hessian(p)
+        free = np.concatenate([self._active, self._rand])
+        Hj = self._reduce_hess(H, free)
+        Hbb, G = Hj[nt:, nt:], Hj[nt:, :nt]
+        Q = np.block([[Hf + G.T @ np.linalg.solve(Hbb, G), G.T], [G, Hbb]])
+        order = np.argsort(free, kind="stable")               # full free-parameter order (fixed / random interleaved)
+        return {"par_fixed": x.copy(), "par_random": p[self._rand].copy(), "cov_fixed": np.linalg.inv(Hf),
+                "jointPrecision": Q[np.ix_(order, order)], "names": list(self.names_full[free][order]),
+                "order": free[order], "value": f}
+
     def report(self, par_full=None):
         """REPORT()ed quantities at `par_full` (default: the last evaluated parameters)."""
         if self.data["type"] != "CTCRW":

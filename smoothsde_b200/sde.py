@@ -178,7 +178,7 @@ class SDE:
         self._tmb_obj_joint = self._adfun_factory(dat_joint, tmb_par, map=map, random=None, device=self._device)
 
     # ---- SDE$fit(), R/sde.R:683-720: optim(par, fn, gr, method = "BFGS")
-    def fit(self, silent=True, map=None, gtol=1e-5, maxiter=200):
+    def fit(self, silent=True, map=None, gtol=1e-5, maxiter=200, sdreport=False):
         from scipy.optimize import minimize
         if self._tmb_obj is None:
             self.setup(silent=silent, map=map)
@@ -195,6 +195,8 @@ class SDE:
             off, size = lay["log_lambda"]
             self.update_lambda(np.exp(p[off:off + size]))
         self._par_all = p.copy()
+        if sdreport:                                   # R/sde.R:702-704: sdreport(obj, getJointPrecision = TRUE)
+            self._rep = obj.sdreport(res.x)
         return res
 
     # ---- logLik.SDE, R/utility.R:115-123: -tmb_obj_joint$fn(par_all)

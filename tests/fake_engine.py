@@ -53,6 +53,10 @@ class OracleEngine:
             hv[:, j] = (4 * d2 - d1) / 3
         return v, g, (hv[:, 0] if dirs.ndim == 1 else hv)
 
+    def hessian(self, par):
+        v, g = self.eval(par, 1)
+        return v, g, self.co.hessian(np.asarray(par, dtype=float))
+
     def report(self, n, n_dim):
         return self.co.aest(self._last)
 

@@ -191,3 +191,28 @@ def test_laplace_gradient_matches_differences_of_the_marginal():
         e = np.zeros(x.size); e[j] = 1e-4
         fd[j] = (obj.fn(x + e) - obj.fn(x - e)) / 2e-4
     assert np.max(np.abs(g - fd)) <= 2e-5 * max(1.0, np.max(np.abs(fd))), (g, fd)
+
+
+def test_he_and_sdreport_follow_tmb():
+    """obj$he on the joint object honours `map`; sdreport's joint precision has TMB's block form and
+    its fixed-effect block inverts to the marginal covariance (Schur complement identity)."""
+    from smoothsde_b200 import synth
+    dat, par, info = synth.make_problem("OU", 2, 60, n_dim=1, seed=12, k=5, re_id=False)
+    p_fe, n_s = info["p_fe"], info["n_s"]
+    pars = {"coeff_fe": par[:p_fe], "log_lambda": par[p_fe:p_fe + n_s], "coeff_re": par[p_fe + n_s:]}
+    joint = oracle_adfun(dat, pars, map={"coeff_fe": [0, 1, None]})
+    H = joint.he(joint.par)
+    full = OracleEngine(dat).hessian(par)[2]
+    keep = np.delete(np.arange(par.size), 2)
+    assert np.allclose(H, full[np.ix_(keep, keep)], rtol=1e-9, atol=1e-9)
+    obj = oracle_adfun(dat, pars, random="coeff_re")
+    from scipy.optimize import minimize
+    res = minimize(obj.fn, obj.par, jac=obj.gr, method="BFGS", options={"gtol": 1e-6})
+    sd = obj.sdreport(res.x)
+    nt, nb = res.x.size, sd["par_random"].size
+    Q = sd["jointPrecision"]
+    assert Q.shape == (nt + nb, nt + nb) and np.allclose(Q, Q.T)
+    assert sd["names"] == ["coeff_fe"] * p_fe + ["log_lambda"] * n_s + ["coeff_re"] * nb
+    cov = np.linalg.inv(Q)
+    assert np.allclose(cov[:nt, :nt], sd["cov_fixed"], rtol=1e-6, atol=1e-10)       # marginal covariance of the fixed effects
+    assert np.all(np.linalg.eigvalsh(Q) > 0)

@@ -91,3 +91,23 @@ def test_fit_to_convergence_matches_oracle_driven_fit():
     assert np.max(np.abs(gpu.coeff_re() - cpu.coeff_re())) <= 1e-6
     assert np.max(np.abs(np.log(gpu.lambda_()) - np.log(cpu.lambda_()))) <= 1e-5
     assert abs(gpu.logLik() - cpu.logLik()) <= 1e-7 * max(1.0, abs(cpu.logLik()))
+
+
+def test_he_and_sdreport_match_oracle_driven_objects():
+    dat, par, info = synth.make_problem("CTCRW", 2, 150, n_dim=2, seed=190, k=5, missing_frac=0.05)
+    pars = split(dat, par, info)
+    m = {"coeff_fe": [None, None, 2, 3]}
+    j_gpu, j_cpu = ADFun(dat, pars, map=m), oracle_adfun(dat, pars, map=m)
+    H1, H2 = j_gpu.he(j_gpu.par), j_cpu.he(j_cpu.par)
+    assert np.max(np.abs(H1 - H2)) <= 1e-6 * np.max(np.abs(H2))
+    o_gpu, o_cpu = ADFun(dat, pars, map=m, random="coeff_re"), oracle_adfun(dat, pars, map=m, random="coeff_re")
+    x = o_gpu.par + 0.01
+    s1, s2 = o_gpu.sdreport(x), o_cpu.sdreport(x)
+    assert s1["names"] == s2["names"]
+    assert np.max(np.abs(s1["par_random"] - s2["par_random"])) <= 1e-7
+    Q1, Q2 = s1["jointPrecision"], s2["jointPrecision"]
+    assert np.max(np.abs(Q1 - Q2)) <= 2e-4 * np.max(np.abs(Q2))           # both sides difference the marginal gradient
+    nb = s1["par_random"].size
+    assert np.max(np.abs(Q1[-nb:, -nb:] - Q2[-nb:, -nb:])) <= 1e-6 * np.max(np.abs(Q2))   # exact blocks
+    for o in (j_gpu, o_gpu):
+        o.close()
