@@ -33,10 +33,13 @@ extern "C" {
 
 typedef struct ssde_handle ssde_handle;
 
-/* DATA_STRING(type) of src/smoothSDE.cpp:11-25.  BM_t, CIR, BM_SSM, OU_SSM, ESEAL_SSM are not
- * built (ssde_create returns SSDE_ERR_UNSUPPORTED; the reference says error("Unknown SDE type")
- * only for names outside its list, smoothSDE.cpp:25 -> SSDE_ERR_UNKNOWN_TYPE here). */
-enum ssde_model { SSDE_BM = 0, SSDE_OU = 1, SSDE_CTCRW = 2 };
+/* DATA_STRING(type) of src/smoothSDE.cpp:11-25.  BM_t, CIR, ESEAL_SSM are not built (the host
+ * layer answers SSDE_ERR_UNSUPPORTED; the reference says error("Unknown SDE type") only for names
+ * outside its list, smoothSDE.cpp:25 -> SSDE_ERR_UNKNOWN_TYPE here).
+ * BM_SSM / OU_SSM (nllk_bm_ssm.hpp, nllk_ou_ssm.hpp): a0 is [n_ID x n_dim] (first observation of
+ * each track, R/sde.R:549-550), P0 [n_dim x n_dim] must be a multiple of the identity (default
+ * diag(10), R/sde.R:553); parameter vector as for CTCRW. */
+enum ssde_model { SSDE_BM = 0, SSDE_OU = 1, SSDE_CTCRW = 2, SSDE_BM_SSM = 3, SSDE_OU_SSM = 4 };
 
 enum ssde_status {
     SSDE_OK = 0,
@@ -77,9 +80,10 @@ typedef struct {
     int32_t n_smooth;         /* length(ncol_re) (1 with ncol_re[0] = 0 when there are no smooths) */
     const int32_t* ncol_re;   /* [n_smooth] */
     int32_t include_penalty;  /* only honoured for BM/OU, as in the reference (nllk_sde.hpp:91) */
-    int32_t n_ID;             /* CTCRW: rows of a0 (tracks starting on this shard) */
-    const double* a0;         /* CTCRW: [n_ID x 2*n_dim] column-major, (x, 0, y, 0, ...) R/sde.R:574-580 */
-    const double* P0;         /* CTCRW: [2*n_dim x 2*n_dim] column-major, R/sde.R:582-588 */
+    int32_t n_ID;             /* Kalman models: rows of a0 (tracks starting on this shard) */
+    const double* a0;         /* CTCRW: [n_ID x 2*n_dim] column-major, (x, 0, y, 0, ...) R/sde.R:574-580;
+                                 BM_SSM / OU_SSM: [n_ID x n_dim] */
+    const double* P0;         /* CTCRW: [2*n_dim x 2*n_dim] column-major, R/sde.R:582-588; SSM: [n_dim x n_dim] */
     const double* H_array;    /* CTCRW: NULL or array(0) for H = sigma_obs^2 I; user H not built yet */
     int64_t H_len;
     int32_t device;           /* CUDA device ordinal */

@@ -107,8 +107,58 @@ def known_ctcrw(dat, par):
     return -llk + O.penalty_kalman(dat, p["log_lambda"], p["coeff_re"])
 
 
+def known_ssm(dat, par):
+    """OU_SSM / BM_SSM: one dense multivariate-normal density per track and dimension.  The state of
+    a track's second row has prior N(a0, P0); x_{i+1} = t_i x_i + c_i + N(0, q_i); y_i = x_i + N(0, h)."""
+    p = O.split_par(dat, np.asarray(par, float))
+    pm = _par_mat(dat, p)
+    ID, t, obs = np.asarray(dat["ID"]), np.asarray(dat["times"], float), np.asarray(dat["obs"], float)
+    a0, P0 = np.asarray(dat["a0"], float), np.asarray(dat["P0"], float)
+    n, d = obs.shape
+    h = math.exp(2 * float(p["log_sigma_obs"]))
+    starts = np.r_[0, np.nonzero(ID[1:] != ID[:-1])[0] + 1, n]
+    llk = 0.0
+    for k in range(starts.size - 1):
+        s, e = starts[k], starts[k + 1]
+        rows = np.arange(s + 1, e)
+        q = rows.size
+        if q == 0:
+            continue
+        tt, qq, cc = np.ones(q), np.zeros(q), np.zeros((q, d))
+        for j in range(1, q):
+            i = rows[j - 1]
+            dti = t[i + 1] - t[i]
+            if dat["type"] == "OU_SSM":
+                tau, kappa = math.exp(pm[i, d]), math.exp(pm[i, d + 1])
+                tt[j], qq[j] = math.exp(-dti / tau), kappa * (1 - math.exp(-2 * dti / tau))
+                cc[j] = (1 - tt[j]) * pm[i, :d]
+            else:
+                tt[j], qq[j] = 1.0, math.exp(2 * pm[i, d]) * dti
+                cc[j] = pm[i, :d] * dti
+        seen = np.nonzero(~np.isnan(obs[rows, 0]))[0]
+        if seen.size == 0:
+            continue
+        for dim in range(d):
+            mean = np.zeros(q)
+            cov = np.zeros((q, q))
+            mean[0], cov[0, 0] = a0[k, dim], P0[dim, dim]
+            for j in range(1, q):
+                mean[j] = tt[j] * mean[j - 1] + cc[j, dim]
+                cov[j, :j] = tt[j] * cov[j - 1, :j]
+                cov[:j, j] = cov[j, :j]
+                cov[j, j] = tt[j] ** 2 * cov[j - 1, j - 1] + qq[j]
+            Cy = cov[np.ix_(seen, seen)] + h * np.eye(seen.size)
+            llk += multivariate_normal(mean[seen], Cy, allow_singular=False).logpdf(obs[rows[seen], dim])
+        llk += 0.5 * seen.size * d * math.log(2 * math.pi)      # constant the templates omit
+    return -llk + O.penalty_kalman(dat, p["log_lambda"], p["coeff_re"])
+
+
 def known_answer(dat, par):
-    return known_ctcrw(dat, par) if dat["type"] == "CTCRW" else known_sde(dat, par)
+    if dat["type"] == "CTCRW":
+        return known_ctcrw(dat, par)
+    if dat["type"] in ("OU_SSM", "BM_SSM"):
+        return known_ssm(dat, par)
+    return known_sde(dat, par)
 
 
 # --------------------------------------------------------------------------------------------

@@ -46,6 +46,8 @@ class COracle:
     def __init__(self, dat, nthreads=1):
         self.dat = dat
         self.type = dat["type"]
+        if self.type not in ("BM", "OU", "CTCRW"):
+            raise NotImplementedError("the C oracle covers BM, OU and CTCRW (use oracle_np for BM_SSM / OU_SSM)")
         self.nthreads = int(nthreads)
         obs = np.asarray(dat["obs"], dtype=float)
         self.n, self.d = obs.shape

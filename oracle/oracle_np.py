@@ -27,6 +27,7 @@ import math
 import numpy as np
 
 LOG_SQRT_2PI = 0.5 * math.log(2.0 * math.pi)
+KALMAN_TYPES = ("CTCRW", "OU_SSM", "BM_SSM")
 
 
 def _re(x):
@@ -226,6 +227,111 @@ def nllk_ctcrw(dat, log_sigma_obs, coeff_fe, log_lambda, coeff_re, return_aest=F
 
 
 # --------------------------------------------------------------------------------------------
+# nllk_ou_ssm / nllk_bm_ssm: the same Kalman loop with an n_dim-state filter
+# (nllk_ou_ssm.hpp:73-249, nllk_bm_ssm.hpp:40-211)
+# --------------------------------------------------------------------------------------------
+def makeT_ou_ssm(tau, dt, n_dim, dtype):
+    """nllk_ou_ssm.hpp:30-38"""
+    return np.eye(n_dim, dtype=dtype) * np.exp(-dt / tau)
+
+
+def makeB_ou_ssm(tau, dt, n_dim, dtype):
+    """nllk_ou_ssm.hpp:45-53"""
+    return np.eye(n_dim, dtype=dtype) * (1 - np.exp(-dt / tau))
+
+
+def makeQ_ou_ssm(tau, kappa, dt, n_dim, dtype):
+    """nllk_ou_ssm.hpp:61-69"""
+    return np.eye(n_dim, dtype=dtype) * (kappa * (1 - np.exp(-2 * dt / tau)))
+
+
+def makeQ_bm_ssm(sigma, dt, n_dim, dtype):
+    """nllk_bm_ssm.hpp:27-36"""
+    return np.eye(n_dim, dtype=dtype) * (sigma * sigma * dt)
+
+
+def _nllk_ssm(dat, log_sigma_obs, coeff_fe, log_lambda, coeff_re, model, return_aest=False):
+    """OU_SSM: nllk_ou_ssm.hpp:101-249; BM_SSM: nllk_bm_ssm.hpp:62-211 (line numbers of OU_SSM below)."""
+    ID = np.asarray(dat["ID"])
+    times = np.asarray(dat["times"], dtype=float)
+    obs = np.asarray(dat["obs"], dtype=float)
+    a0 = np.asarray(dat["a0"], dtype=float)
+    P0 = np.asarray(dat["P0"], dtype=float)
+    H_array = dat.get("H_array", None)
+    n, n_dim = obs.shape
+    coeff_fe, coeff_re, log_lambda = np.asarray(coeff_fe), np.asarray(coeff_re), np.asarray(log_lambda)
+    dtype = np.result_type(coeff_fe.dtype, coeff_re.dtype, np.asarray(log_sigma_obs).dtype, log_lambda.dtype, np.float64)
+    dtimes = np.empty(n)                          # :97-100
+    dtimes[:n - 1] = times[1:] - times[:-1]
+    dtimes[n - 1] = 1.0
+    sigma_obs = np.exp(log_sigma_obs)             # :106-107
+    par_mat = linear_predictor(dat, coeff_fe, coeff_re)    # :113-119
+    mu = par_mat[:, 0:n_dim]                      # :122
+    if model == "OU_SSM":
+        tau = np.exp(par_mat[:, n_dim])           # :123
+        kappa = np.exp(par_mat[:, n_dim + 1])     # :124
+    else:
+        sigma = np.exp(par_mat[:, n_dim])         # nllk_bm_ssm.hpp:90
+    Z = np.eye(n_dim)                             # :130-131
+    H = np.eye(n_dim, dtype=dtype) * (sigma_obs * sigma_obs)   # :132, makeH :15-23
+    aest = a0[0].astype(dtype)                    # :150-154
+    Pest = P0.astype(dtype)
+    k = 1
+    llk = 0.0
+    aest_all = np.zeros((n, n_dim), dtype=dtype)
+    aest_all[0] = aest
+    for i in range(1, n):                         # :163
+        if ID[i] != ID[i - 1]:                    # :164-168
+            aest = a0[k].astype(dtype)
+            k += 1
+            Pest = P0.astype(dtype)
+        else:
+            if H_array is not None and np.size(H_array) > 1:      # :171-173
+                H = np.asarray(H_array)[:, :, i].astype(dtype)
+            if model == "OU_SSM":
+                T = makeT_ou_ssm(tau[i], dtimes[i], n_dim, dtype)             # :174
+                B = makeB_ou_ssm(tau[i], dtimes[i], n_dim, dtype)             # :175
+                Q = makeQ_ou_ssm(tau[i], kappa[i], dtimes[i], n_dim, dtype)   # :176
+                drift = B @ mu[i]                                             # :177
+            else:
+                T = np.eye(n_dim, dtype=dtype)                                # nllk_bm_ssm.hpp:100-101
+                Q = makeQ_bm_ssm(sigma[i], dtimes[i], n_dim, dtype)           # nllk_bm_ssm.hpp:139
+                drift = mu[i] * dtimes[i]                                     # nllk_bm_ssm.hpp:140
+            if _isna(obs[i, 0]):                  # :179-182
+                aest = T @ aest + drift
+                Pest = T @ Pest @ T.T + Q
+            else:
+                u = obs[i] - Z @ aest             # :185-186
+                F = Z @ Pest @ Z.T + H            # :189
+                detF = det_small(F)               # detF = exp(atomic::logdet(F)) :190 (analytic form, so that
+                                                  # complex-step derivatives pass through it)
+                if _re(detF) <= 0:                # :192-194 (keeps B*mu, unlike CTCRW)
+                    aest = T @ aest + drift
+                    Pest = T @ Pest @ T.T + Q
+                else:
+                    Finv = np.linalg.inv(F)
+                    uFu = np.sum(u * (Finv.T @ u))            # :197-199
+                    llk = llk - (np.log(detF) + uFu) / 2      # :200
+                    K = T @ Pest @ Z.T @ Finv                 # :202
+                    aest = T @ aest + K @ u + drift           # :204
+                    L = T - K @ Z                             # :206
+                    Pest = T @ Pest @ L.T + Q                 # :207
+        aest_all[i] = aest                        # :212
+    nllk = -llk + penalty_kalman(dat, log_lambda, coeff_re)   # :220-246 (identical to nllk_ctcrw's)
+    if return_aest:
+        return nllk, aest_all
+    return nllk
+
+
+def nllk_ou_ssm(dat, log_sigma_obs, coeff_fe, log_lambda, coeff_re, return_aest=False):
+    return _nllk_ssm(dat, log_sigma_obs, coeff_fe, log_lambda, coeff_re, "OU_SSM", return_aest)
+
+
+def nllk_bm_ssm(dat, log_sigma_obs, coeff_fe, log_lambda, coeff_re, return_aest=False):
+    return _nllk_ssm(dat, log_sigma_obs, coeff_fe, log_lambda, coeff_re, "BM_SSM", return_aest)
+
+
+# --------------------------------------------------------------------------------------------
 # tr_dens / nllk_sde, tr_dens.hpp:18-75 and nllk_sde.hpp:15-127  (BM and OU only)
 # --------------------------------------------------------------------------------------------
 def dnorm_log(x, mean, sd):
@@ -286,7 +392,7 @@ def split_par(dat, par):
     n_s = ncol_re.size if ncol_re[0] > 0 else 1
     o = 0
     out = {}
-    if dat["type"] == "CTCRW":
+    if dat["type"] in KALMAN_TYPES:
         out["log_sigma_obs"] = par[0]
         o = 1
     out["coeff_fe"] = par[o:o + p_fe]; o += p_fe
@@ -303,6 +409,8 @@ def nllk(dat, par):
         return nllk_sde(dat, p["coeff_fe"], p["log_lambda"], p["coeff_re"], t)
     if t == "CTCRW":
         return nllk_ctcrw(dat, p["log_sigma_obs"], p["coeff_fe"], p["log_lambda"], p["coeff_re"])
+    if t in ("OU_SSM", "BM_SSM"):
+        return _nllk_ssm(dat, p["log_sigma_obs"], p["coeff_fe"], p["log_lambda"], p["coeff_re"], t)
     raise ValueError("Unknown SDE type")         # smoothSDE.cpp:25
 
 

@@ -12,9 +12,10 @@ c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)
 c_int64_p = C.POINTER(C.c_int64)
 
-SSDE_BM, SSDE_OU, SSDE_CTCRW = 0, 1, 2
-MODEL_CODES = {"BM": SSDE_BM, "OU": SSDE_OU, "CTCRW": SSDE_CTCRW}
-KNOWN_UNBUILT = ("BM_t", "CIR", "BM_SSM", "OU_SSM", "ESEAL_SSM")
+SSDE_BM, SSDE_OU, SSDE_CTCRW, SSDE_BM_SSM, SSDE_OU_SSM = 0, 1, 2, 3, 4
+MODEL_CODES = {"BM": SSDE_BM, "OU": SSDE_OU, "CTCRW": SSDE_CTCRW, "BM_SSM": SSDE_BM_SSM, "OU_SSM": SSDE_OU_SSM}
+KALMAN_TYPES = ("CTCRW", "BM_SSM", "OU_SSM")
+KNOWN_UNBUILT = ("BM_t", "CIR", "ESEAL_SSM")
 
 SHARD_CONT_PREV, SHARD_CONT_NEXT, SHARD_NO_PENALTY = 1, 2, 4
 

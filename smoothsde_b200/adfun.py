@@ -202,13 +202,13 @@ class ADFun:
 
     def report(self, par_full=None):
         """REPORT()ed quantities at `par_full` (default: the last evaluated parameters)."""
-        if self.data["type"] != "CTCRW":
+        if self.data["type"] not in ("CTCRW", "BM_SSM", "OU_SSM"):
             return {}
         if par_full is not None:
             self.joint(np.asarray(par_full, dtype=float), order=0)
         obs = np.asarray(self.data["obs"])
         n, d = (obs.shape[0], 1) if obs.ndim == 1 else obs.shape
-        return {"aest_all": self.engine.report(n, d)}
+        return {"aest_all": self.engine.report(n, d, 2 * d if self.data["type"] == "CTCRW" else d)}
 
     def close(self):
         self.engine.close()

@@ -6,7 +6,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#include "ctcrw_math.cuh"
+#include "models.cuh"
 
 namespace ssde {
 
@@ -77,34 +77,26 @@ __device__ __forceinline__ E load_elem_cg(const double* src) {
 // Time-ordered composition traits.  join(far, near): `near` covers tiles closer (in processing
 // order) to the current one.  Forward scan processes tiles in time order, so far = earlier in
 // time; the adjoint scan processes tiles in reverse time, so far = later in time.
-// An element whose linear part has decayed below CONST_MAP_TOL acts as a constant map: what
-// comes before it cannot change the result by more than that factor (40+ orders of magnitude
-// below fp64 rounding), so a look-back may stop there as if it had found an inclusive prefix.
-// With observations on most rows the filter forgets its initial condition within a few hundred
-// rows (A underflows to exactly 0), which makes almost every tile aggregate a constant map.
-constexpr double CONST_MAP_TOL = 1e-60;
-__device__ __forceinline__ bool tiny(double x) { return fabs(x) <= CONST_MAP_TOL; }
-__device__ __forceinline__ bool tiny(const Dual& x) { return fabs(x.v) <= CONST_MAP_TOL && fabs(x.d) <= CONST_MAP_TOL; }
-template <class R>
-__device__ __forceinline__ bool tiny(const Mat2T<R>& m) { return tiny(m.m11) && tiny(m.m12) && tiny(m.m21) && tiny(m.m22); }
-
-template <int ND, class R = double>
+// An element whose linear part has decayed below CONST_MAP_TOL (models.cuh) acts as a constant
+// map: what comes before it cannot change the result by more than that factor (40+ orders of
+// magnitude below fp64 rounding), so a look-back may stop there as if it had found an inclusive
+// prefix.  With observations on most rows the filter forgets its initial condition within a few
+// hundred rows (A underflows to exactly 0), which makes almost every tile aggregate a constant map.
+template <class M>
 struct FwdOps {
-    using Elem = FwdElem<ND, R>;
-    static __device__ __forceinline__ Elem identity() { return fwd_identity<ND, R>(); }
-    static __device__ __forceinline__ Elem join(const Elem& far, const Elem& near) {
-        return fwd_combine<ND, R>(far, near);
-    }
-    static __device__ __forceinline__ bool is_const(const Elem& e) { return tiny(e.A); }
+    using Elem = typename M::FwdElem;
+    static __device__ __forceinline__ Elem identity() { return M::fwd_identity(); }
+    static __device__ __forceinline__ Elem join(const Elem& far, const Elem& near) { return M::fwd_combine(far, near); }
+    static __device__ __forceinline__ bool is_const(const Elem& e) { return M::fwd_is_const(e); }
 };
-template <int ND, class R = double>
+template <class M>
 struct BwdOps {
-    using Elem = BwdElem<ND, R>;
-    static __device__ __forceinline__ Elem identity() { return bwd_identity<ND, R>(); }
+    using Elem = typename M::BwdElem;
+    static __device__ __forceinline__ Elem identity() { return M::bwd_identity(); }
     static __device__ __forceinline__ Elem join(const Elem& far, const Elem& near) {
-        return bwd_combine<ND, R>(near, far);  // near = earlier rows (E1), far = later rows (E2)
+        return M::bwd_combine(near, far);      // near = earlier rows (E1), far = later rows (E2)
     }
-    static __device__ __forceinline__ bool is_const(const Elem& e) { return tiny(e.L); }
+    static __device__ __forceinline__ bool is_const(const Elem& e) { return M::bwd_is_const(e); }
 };
 
 // ---------------------------------------------------------------------------------------------

@@ -17,34 +17,37 @@
 #pragma once
 
 #include "design.cuh"
+#include "models.cuh"
 
 namespace ssde {
 
-template <int ND, class R = double>
-struct CtcrwArgs {
+// M = model traits (models.cuh): CtcrwModel / OuSsmModel / BmSsmModel <n_dim, scalar type>
+template <class R = double>
+struct KalmanArgs {
     DesignV2 X;
     Theta theta;               // [coeff_fe | coeff_re] (+ direction for the tangent pass)
     const double* obs;         // ND planes of n_pad doubles, permuted (design.cuh), NA replaced by 0
     const double* dt;          // [n_pad] permuted
     const uint8_t* flags;      // [n_pad] permuted, 0xff beyond the end
     const int64_t* track_starts;   // [n_tracks] sorted rows flagged ROW_START
-    const double* a0;          // [n_tracks, 2*ND]
+    const double* a0;          // [n_tracks, M::SD]
     int n_tracks;
     Sym2 P0;
     const double* par;         // device parameter vector; par[0] = log_sigma_obs
     const double* par_dot;     // R = Dual: direction in the parameter vector (else nullptr)
-    const R* s_in;             // optional incoming state (2*ND + 3 scalars) for a continued shard
-    const R* g_in;             // optional incoming adjoint (2*ND + 3 scalars)
+    const R* s_in;             // optional incoming state (M::FS scalars) for a continued shard
+    const R* g_in;             // optional incoming adjoint (M::FS scalars)
     const int* mu_zero;        // device flag: every mu_d predictor is exactly 0 at these parameters
-    R* wg;                     // [3, n_pad] permuted: tau, e = exp(-dt/tau), s2 of every row (forward -> adjoint)
-    R* ckpt;                   // [(2*ND+3), nchunks] start state of every thread chunk
+    R* wg;                     // [M::NW, n_pad] permuted: transformed parameters of every row (CTCRW: tau,
+                               // e = exp(-dt/tau), s2), forward -> adjoint
+    R* ckpt;                   // [M::FS, nchunks] start state of every thread chunk
     int64_t nchunks;           // n_pad / LC
     double* tile_llk;          // [n_pad / WT] one partial log-likelihood per warp-tile
     double* tile_gh;           // [n_pad / WT] one partial d nllk / d h per warp-tile; R = Dual: the
                                // tangents follow at tile_gh[n_pad / WT + q]
     double* grad_theta;        // [p_theta] (R = Dual: [2 p_theta], tangents second), accumulated with atomics
     int p_theta;
-    double* aest;              // optional [n, 2*ND]: REPORT(aest_all), nllk_ctcrw.hpp:246-249
+    double* aest;              // optional [n, M::SD]: REPORT(aest_all), nllk_ctcrw.hpp:246-249
     ScanDesc fdesc, bdesc;
     int ntiles;
     int summary;               // 1: stop after the tile prefixes are published (time-sharded runs only
@@ -53,29 +56,15 @@ struct CtcrwArgs {
 
 // Start state of the track whose first row carries track index `idx` (stored, as a double, in
 // the otherwise unused dt slot of track-start rows).
-template <int ND, class R>
-__device__ __forceinline__ State<ND, R> track_start_state(const CtcrwArgs<ND, R>& a, double idx) {
-    State<ND, R> s;
-    const double* p = a.a0 + (size_t)idx * 2 * ND;
-#pragma unroll
-    for (int d = 0; d < ND; ++d) s.a[d] = {p[2 * d], p[2 * d + 1]};
-    s.P = {a.P0.a, a.P0.b, a.P0.c};
-    return s;
+template <class M>
+__device__ __forceinline__ typename M::State track_start_state(const KalmanArgs<typename M::R>& a, double idx) {
+    return M::start_state(a.a0 + (size_t)idx * M::SD, a.P0);
 }
 
 // h = sigma_obs^2 = exp(2 log_sigma_obs), nllk_ctcrw.hpp:136,167
-template <int ND, class R>
-__device__ __forceinline__ R obs_variance(const CtcrwArgs<ND, R>& a) {
+template <class R>
+__device__ __forceinline__ R obs_variance(const KalmanArgs<R>& a) {
     return exp(2.0 * ScalarOf<R>::make(a.par[0], a.par_dot ? a.par_dot[0] : 0.0));
-}
-
-template <int ND, class R>
-__device__ __forceinline__ State<ND, R> load_state(const R* p) {
-    State<ND, R> s;
-#pragma unroll
-    for (int d = 0; d < ND; ++d) s.a[d] = {p[2 * d], p[2 * d + 1]};
-    s.P = {p[2 * ND], p[2 * ND + 1], p[2 * ND + 2]};
-    return s;
 }
 
 // the 8 row flags of this lane's chunk, packed (0xff = row beyond the end)
@@ -89,9 +78,10 @@ __device__ __forceinline__ unsigned long long load_flags8(const uint8_t* __restr
 // ---------------------------------------------------------------------------------------------
 // forward kernel
 // ---------------------------------------------------------------------------------------------
-template <int ND, int NT, class R = double>
+template <class M, int NT>
 struct FwdSmem {
-    static constexpr int NC = 5;                 // T12, e, Qa, Qb, Qc
+    using R = typename M::R;
+    static constexpr int NC = M::NC;             // step quantities per row (CTCRW: T12, e, Qa, Qb, Qc)
     static constexpr int ES = 24 * ScalarOf<R>::NDBL;
     R W[LC][NC][NT];
     double stage[NT / 32][STAGE_DBL];
@@ -104,14 +94,16 @@ struct FwdSmem {
     int early[2];                    // the tile aggregate was published before the barrier
 };
 
-template <int ND, int NT, int MINB, class R = double>
-__global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(CtcrwArgs<ND, R> a) {
-    using SM = FwdSmem<ND, NT, R>;
-    using Ops = FwdOps<ND, R>;
-    using Elem = FwdElem<ND, R>;
-    using St = State<ND, R>;
+template <class M, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(KalmanArgs<typename M::R> a) {
+    using R = typename M::R;
+    using SM = FwdSmem<M, NT>;
+    using Ops = FwdOps<M>;
+    using Elem = typename M::FwdElem;
+    using St = typename M::State;
+    constexpr int ND = M::ND;
     constexpr int NWARP = NT / 32;
-    constexpr int NP = ND + 2;
+    constexpr int NP = M::NP;
     static_assert(Elem::NDBL <= SM::ES, "element too large for the shared staging area");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SM& sm = *reinterpret_cast<SM*>(smem_raw);
@@ -142,7 +134,7 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(CtcrwArgs<ND, R> a)
         const unsigned long long fl = load_flags8(a.flags, base);
 
         // (1) thread element over its LC rows
-        Elem E = fwd_identity<ND, R>();
+        Elem E = M::fwd_identity();
         // dt and the observations of a row are fetched one row ahead of their use
         double dt_nx = ((uint8_t)fl != 0xff) ? a.dt[base] : 1.0, y_nx[ND];
 #pragma unroll
@@ -173,15 +165,13 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(CtcrwArgs<ND, R> a)
                 row_eta<NP>(w, k, a.theta, eta);
             }
             if (step) {
-                R tau, e, s2;
-                transform_row(eta[ND], eta[ND + 1], dtv, tau, e, s2);
-                a.wg[pos] = tau; a.wg[a.X.n_pad + pos] = e; a.wg[2 * a.X.n_pad + pos] = s2;
-                const StepParT<R> sp = make_step(tau, e, s2, dtv);
-                sm.W[k][0][tid] = sp.T12; sm.W[k][1][tid] = sp.e;
-                sm.W[k][2][tid] = sp.Q.a; sm.W[k][3][tid] = sp.Q.b; sm.W[k][4][tid] = sp.Q.c;
-                fwd_append<ND>(E, sp, y, eta, (f & ROW_OBS) != 0, h);
+                const typename M::RowPar rp = M::transform(eta, dtv);
+                M::store_rowpar(rp, [&](int c) -> R& { return a.wg[(size_t)c * a.X.n_pad + pos]; });
+                const typename M::Step sp = M::make_step(rp, dtv);
+                M::store_step(sp, [&](int c) -> R& { return sm.W[k][c][tid]; });
+                M::fwd_append(E, sp, y, eta, (f & ROW_OBS) != 0, h);
             } else if (live) {
-                fwd_append_start<ND>(E, track_start_state<ND>(a, dtv));
+                M::fwd_append_start(E, track_start_state<M>(a, dtv));
             }
         }
         // (2) warp inclusive scan (lower lanes = earlier rows)
@@ -189,7 +179,7 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(CtcrwArgs<ND, R> a)
 #pragma unroll 1
         for (int o = 1; o < 32; o <<= 1) {
             Elem f = shfl_up_elem(inc, o);
-            if (lane >= o) inc = fwd_combine<ND>(f, inc);
+            if (lane >= o) inc = M::fwd_combine(f, inc);
         }
         if (lane == 31) {
             store_elem(sm.wagg[par][warp], inc);
@@ -202,7 +192,7 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(CtcrwArgs<ND, R> a)
             }
         }
         Elem exc = shfl_up_elem(inc, 1);
-        if (lane == 0) exc = fwd_identity<ND, R>();
+        if (lane == 0) exc = M::fwd_identity();
 #ifdef SSDE_STATS
         tc1 = clock64();
 #endif
@@ -215,7 +205,7 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(CtcrwArgs<ND, R> a)
         if (warp == NWARP - 1 && !sm.early[par]) {
             Elem tagg = load_elem<Elem>(sm.wagg[par][NWARP - 1]);
 #pragma unroll 1
-            for (int ww = NWARP - 2; ww >= 0 && !Ops::is_const(tagg); --ww) tagg = fwd_combine<ND>(load_elem<Elem>(sm.wagg[par][ww]), tagg);
+            for (int ww = NWARP - 2; ww >= 0 && !Ops::is_const(tagg); --ww) tagg = M::fwd_combine(load_elem<Elem>(sm.wagg[par][ww]), tagg);
             if (lane == 0) { publish_agg<Ops>(a.fdesc, tile, tagg); store_elem(sm.tagg[par], tagg); }
         }
         Elem pre;
@@ -223,15 +213,9 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(CtcrwArgs<ND, R> a)
             pre = lookback<Ops>(a.fdesc, tile);
             if (lane == 0) {
                 // state at the first row of the tile
-                St s0;
-                if (a.s_in) s0 = load_state<ND, R>(a.s_in);
-                else { s0.P = {a.P0.a, a.P0.b, a.P0.c};
-#pragma unroll
-                    for (int d = 0; d < ND; ++d) s0.a[d] = {0.0, 0.0}; }
-                const St st0 = fwd_apply<ND>(pre, s0);
-#pragma unroll
-                for (int d = 0; d < ND; ++d) { sm.misc[par][2 * d] = st0.a[d].x; sm.misc[par][2 * d + 1] = st0.a[d].y; }
-                sm.misc[par][2 * ND] = st0.P.a; sm.misc[par][2 * ND + 1] = st0.P.b; sm.misc[par][2 * ND + 2] = st0.P.c;
+                const St s0 = a.s_in ? M::load_state([&](int i) { return a.s_in[i]; }) : M::zero_state(a.P0);
+                const St st0 = M::fwd_apply(pre, s0);
+                M::store_state(st0, [&](int i) -> R& { return sm.misc[par][i]; });
             }
         }
         __syncthreads();
@@ -239,7 +223,7 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(CtcrwArgs<ND, R> a)
             // a constant-map aggregate already serves as the inclusive prefix (status code 3); the
             // summary pass of a time shard reads the last tile's inclusive element from f_incl
             const Elem tagg = load_elem<Elem>(sm.tagg[par]);
-            if (a.summary || !Ops::is_const(tagg)) publish_incl<Ops>(a.fdesc, tile, fwd_combine<ND>(pre, tagg));
+            if (a.summary || !Ops::is_const(tagg)) publish_incl<Ops>(a.fdesc, tile, M::fwd_combine(pre, tagg));
         }
 #ifdef SSDE_STATS
         tc3 = clock64();
@@ -247,25 +231,16 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(CtcrwArgs<ND, R> a)
         if (a.summary) continue;
         // (4) exact start state of this thread, checkpoint, plain filter re-run
         // warp aggregates in front of this warp, starting at the nearest constant map (warp-uniform)
-        St s = load_state<ND, R>(sm.misc[par]);
+        St s = M::load_state([&](int i) { return sm.misc[par][i]; });
         {
             int w0 = warp - 1;
             while (w0 > 0 && !Ops::is_const(load_elem<Elem>(sm.wagg[par][w0]))) --w0;
 #pragma unroll 1
-            for (int ww = max(w0, 0); ww < warp; ++ww) s = fwd_apply<ND>(load_elem<Elem>(sm.wagg[par][ww]), s);
+            for (int ww = max(w0, 0); ww < warp; ++ww) s = M::fwd_apply(load_elem<Elem>(sm.wagg[par][ww]), s);
         }
-        s = fwd_apply<ND>(exc, s);
+        s = M::fwd_apply(exc, s);
         const int64_t chunk = q * 32 + lane;
-        {
-#pragma unroll
-            for (int d = 0; d < ND; ++d) {
-                a.ckpt[(size_t)(2 * d) * a.nchunks + chunk] = s.a[d].x;
-                a.ckpt[(size_t)(2 * d + 1) * a.nchunks + chunk] = s.a[d].y;
-            }
-            a.ckpt[(size_t)(2 * ND) * a.nchunks + chunk] = s.P.a;
-            a.ckpt[(size_t)(2 * ND + 1) * a.nchunks + chunk] = s.P.b;
-            a.ckpt[(size_t)(2 * ND + 2) * a.nchunks + chunk] = s.P.c;
-        }
+        M::store_state(s, [&](int i) -> R& { return a.ckpt[(size_t)i * a.nchunks + chunk]; });
         // sum_i log F_i is taken as the log of a running product (one log per chunk instead of
         // one per row); the product is folded into `slog` whenever it leaves a safe range.
         R quad = 0.0, fprod = 1.0, slog = 0.0;
@@ -287,26 +262,21 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(CtcrwArgs<ND, R> a)
                 for (int d = 0; d < ND; ++d) y_nx[d] = a.obs[(size_t)d * a.X.n_pad + pos + 32];
             }
             if (f & ROW_START) {
-                s = track_start_state<ND>(a, dtv);
+                s = track_start_state<M>(a, dtv);
             } else {
                 R mu[ND];
 #pragma unroll
                 for (int d = 0; d < ND; ++d) mu[d] = 0.0;
                 if (!mu0) row_eta_prefix<ND>(w, k, a.theta, mu);
-                StepParT<R> sp;
-                sp.T12 = sm.W[k][0][tid]; sp.e = sm.W[k][1][tid];
-                sp.Q.a = sm.W[k][2][tid]; sp.Q.b = sm.W[k][3][tid]; sp.Q.c = sm.W[k][4][tid];
-                sp.B1 = dtv - sp.T12; sp.B2 = 1.0 - sp.e;      // makeB_ctcrw, :87-88
+                const typename M::Step sp = M::load_step([&](int c) { return sm.W[k][c][tid]; }, dtv);
                 R F, qd;
-                fwd_step_q<ND, false>(s, sp, y, mu, (f & ROW_OBS) != 0, h, nullptr, F, qd);
+                M::template fwd_step<false>(s, sp, y, mu, (f & ROW_OBS) != 0, h, nullptr, F, qd);
                 quad += qd;
                 fprod *= F;
                 if (!(value(fprod) > 1e-150 && value(fprod) < 1e150)) { slog += log(fprod); fprod = 1.0; }
             }
             if (a.aest) {
-                double* o = a.aest + (size_t)(row0 + k) * (2 * ND);
-#pragma unroll
-                for (int d = 0; d < ND; ++d) { o[2 * d] = value(s.a[d].x); o[2 * d + 1] = value(s.a[d].y); }
+                M::store_mean(s, a.aest + (size_t)(row0 + k) * M::SD);
             }
         }
         const double llk = warp_sum(value(-0.5 * ((double)ND * (slog + log(fprod)) + quad)));
@@ -326,23 +296,16 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(CtcrwArgs<ND, R> a)
 // ---------------------------------------------------------------------------------------------
 // adjoint kernel
 // ---------------------------------------------------------------------------------------------
-template <int ND, class R>
-__device__ __forceinline__ Adj<ND, R> load_adj(const R* p) {
-    Adj<ND, R> g;
-#pragma unroll
-    for (int d = 0; d < ND; ++d) g.a[d] = {p[2 * d], p[2 * d + 1]};
-    g.P = {p[2 * ND], p[2 * ND + 1], p[2 * ND + 2]};
-    return g;
-}
-
 constexpr int SGRAD = 256;         // per-CTA gradient accumulators (doubles) when p_theta fits
 
-template <int ND, int NT, class R = double>
+template <class M, int NT>
 struct BwdSmem {
-    static constexpr int FS = 2 * ND + 3;        // forward state before the row
+    using R = typename M::R;
+    // per row: the forward state before the row (M::FS scalars), later overwritten by eta_bar
+    // (slots 0..NP-1) and by the transposed-product scratch (slots NP..RS-1)
+    static constexpr int RS = (M::FS > M::NP + 3) ? M::FS : M::NP + 3;
     static constexpr int ES = 16 * ScalarOf<R>::NDBL;
-    R Rs[LC][FS][NT];                // states; overwritten by eta_bar (slots 0..NP-1) and by the
-                                     // transposed-product scratch (slots NP..FS-1) once consumed
+    R Rs[LC][RS][NT];
     double wagg[2][NT / 32][ES];
     double tagg[2][ES];
     R misc[2][16];
@@ -353,37 +316,36 @@ struct BwdSmem {
 };
 
 // per-row inputs of the adjoint sweep, fetched one row ahead
-template <int ND, class R>
+template <class M>
 struct RowIn {
-    R tau, e, s2;
-    double dt, y[ND];
+    typename M::RowPar rp;
+    double dt, y[M::ND];
 };
-template <int ND, class R>
-__device__ __forceinline__ RowIn<ND, R> load_row(const CtcrwArgs<ND, R>& a, int64_t pos, bool live) {
-    RowIn<ND, R> r;
+template <class M>
+__device__ __forceinline__ RowIn<M> load_row(const KalmanArgs<typename M::R>& a, int64_t pos, bool live) {
+    RowIn<M> r;
     const int64_t np = a.X.n_pad;
     r.dt = live ? a.dt[pos] : 1.0;
-    r.tau = live ? a.wg[pos] : R(1.0);
-    r.e = live ? a.wg[np + pos] : R(0.0);
-    r.s2 = live ? a.wg[2 * np + pos] : R(0.0);
+    r.rp = live ? M::load_rowpar([&](int c) { return a.wg[(size_t)c * np + pos]; }) : M::dead_rowpar();
 #pragma unroll
-    for (int d = 0; d < ND; ++d) r.y[d] = live ? a.obs[(size_t)d * np + pos] : 0.0;
+    for (int d = 0; d < M::ND; ++d) r.y[d] = live ? a.obs[(size_t)d * np + pos] : 0.0;
     return r;
 }
 
-template <int ND, int NT, int MINB, class R = double>
-__global__ void __launch_bounds__(NT, MINB) ctcrw_bwd_kernel(CtcrwArgs<ND, R> a) {
-    using SM = BwdSmem<ND, NT, R>;
-    using Ops = BwdOps<ND, R>;
-    using Elem = BwdElem<ND, R>;
-    using St = State<ND, R>;
-    using Ad = Adj<ND, R>;
+template <class M, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) ctcrw_bwd_kernel(KalmanArgs<typename M::R> a) {
+    using R = typename M::R;
+    using SM = BwdSmem<M, NT>;
+    using Ops = BwdOps<M>;
+    using Elem = typename M::BwdElem;
+    using St = typename M::State;
+    using Ad = typename M::Adj;
+    constexpr int ND = M::ND;
     constexpr int NWARP = NT / 32;
-    constexpr int NP = ND + 2;
-    constexpr int FS = SM::FS;
-    constexpr int TCAP = (FS - NP) * LC;          // slots whose scratch fits in the freed state slots
+    constexpr int NP = M::NP;
+    constexpr int FS = SM::RS;
+    constexpr int TCAP = (FS - NP) * LC;          // slots whose scratch fits in the spare row slots
     static_assert(Elem::NDBL <= SM::ES, "element too large for the shared staging area");
-    static_assert(FS >= NP, "eta_bar reuses the state slots");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     SM& sm = *reinterpret_cast<SM*>(smem_raw);
 
@@ -411,46 +373,31 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_bwd_kernel(CtcrwArgs<ND, R> a)
 
         // (1) recompute the forward states of this thread's rows from its checkpoint and compose
         //     the rows' adjoint elements (in time order)
-        St s;
-#pragma unroll
-        for (int d = 0; d < ND; ++d) {
-            s.a[d].x = a.ckpt[(size_t)(2 * d) * a.nchunks + chunk];
-            s.a[d].y = a.ckpt[(size_t)(2 * d + 1) * a.nchunks + chunk];
-        }
-        s.P.a = a.ckpt[(size_t)(2 * ND) * a.nchunks + chunk];
-        s.P.b = a.ckpt[(size_t)(2 * ND + 1) * a.nchunks + chunk];
-        s.P.c = a.ckpt[(size_t)(2 * ND + 2) * a.nchunks + chunk];
-        Elem E = bwd_identity<ND, R>();
-        RowIn<ND, R> nx = load_row<ND, R>(a, base, (uint8_t)fl != 0xff);
+        St s = M::load_state([&](int i) { return a.ckpt[(size_t)i * a.nchunks + chunk]; });
+        Elem E = M::bwd_identity();
+        RowIn<M> nx = load_row<M>(a, base, (uint8_t)fl != 0xff);
 #pragma unroll 1
         for (int k = 0; k < LC; ++k) {
             const uint8_t f = (uint8_t)(fl >> (8 * k));
             const bool live = f != 0xff;
             const bool step = live && !(f & ROW_START);
-            const RowIn<ND, R> r = nx;
-            if (k + 1 < LC) nx = load_row<ND, R>(a, base + (k + 1) * 32, (uint8_t)(fl >> (8 * (k + 1))) != 0xff);
+            const RowIn<M> r = nx;
+            if (k + 1 < LC) nx = load_row<M>(a, base + (k + 1) * 32, (uint8_t)(fl >> (8 * (k + 1))) != 0xff);
             // state BEFORE row k
-#pragma unroll
-            for (int d = 0; d < ND; ++d) {
-                sm.Rs[k][2 * d][tid] = s.a[d].x;
-                sm.Rs[k][2 * d + 1][tid] = s.a[d].y;
-            }
-            sm.Rs[k][2 * ND][tid] = s.P.a;
-            sm.Rs[k][2 * ND + 1][tid] = s.P.b;
-            sm.Rs[k][2 * ND + 2][tid] = s.P.c;
+            M::store_state(s, [&](int i) -> R& { return sm.Rs[k][i][tid]; });
             if (step) {
                 R mu[ND];
 #pragma unroll
                 for (int d = 0; d < ND; ++d) mu[d] = 0.0;
                 if (!mu0) row_eta_prefix<ND>(w, k, a.theta, mu);
-                const StepParT<R> sp = make_step(r.tau, r.e, r.s2, r.dt);
-                StepAux<ND, R> ax;
+                const typename M::Step sp = M::make_step(r.rp, r.dt);
+                typename M::Aux ax;
                 R F, qd;
-                fwd_step_q<ND, true>(s, sp, r.y, mu, (f & ROW_OBS) != 0, h, &ax, F, qd);
-                E = bwd_combine<ND>(E, bwd_row_elem<ND>(sp, ax, (f & ROW_OBS) != 0, (f & ROW_LAST) != 0));
+                M::template fwd_step<true>(s, sp, r.y, mu, (f & ROW_OBS) != 0, h, &ax, F, qd);
+                E = M::bwd_combine(E, M::bwd_row_elem(sp, ax, (f & ROW_OBS) != 0, (f & ROW_LAST) != 0));
             } else if (live) {
-                s = track_start_state<ND>(a, r.dt);
-                E = bwd_combine<ND>(E, bwd_const<ND>(adj_zero<ND, R>()));
+                s = track_start_state<M>(a, r.dt);
+                E = M::bwd_combine(E, M::bwd_const(M::adj_zero()));
             }
         }
         // (2) warp inclusive SUFFIX scan (higher lanes = later rows)
@@ -458,7 +405,7 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_bwd_kernel(CtcrwArgs<ND, R> a)
 #pragma unroll 1
         for (int o = 1; o < 32; o <<= 1) {
             Elem f = shfl_down_elem(inc, o);
-            if (lane + o < 32) inc = bwd_combine<ND>(inc, f);
+            if (lane + o < 32) inc = M::bwd_combine(inc, f);
         }
         if (lane == 0) {
             store_elem(sm.wagg[par][warp], inc);
@@ -469,7 +416,7 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_bwd_kernel(CtcrwArgs<ND, R> a)
             }
         }
         Elem exc = shfl_down_elem(inc, 1);
-        if (lane == 31) exc = bwd_identity<ND, R>();
+        if (lane == 31) exc = M::bwd_identity();
 #ifdef SSDE_STATS
         tc1 = clock64();
 #endif
@@ -484,75 +431,65 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_bwd_kernel(CtcrwArgs<ND, R> a)
             // the adjoint flows from later rows to earlier ones: start with the EARLIEST warp
             Elem tagg = load_elem<Elem>(sm.wagg[par][0]);
 #pragma unroll 1
-            for (int ww = 1; ww < NWARP && !Ops::is_const(tagg); ++ww) tagg = bwd_combine<ND>(tagg, load_elem<Elem>(sm.wagg[par][ww]));
+            for (int ww = 1; ww < NWARP && !Ops::is_const(tagg); ++ww) tagg = M::bwd_combine(tagg, load_elem<Elem>(sm.wagg[par][ww]));
             if (lane == 0) { publish_agg<Ops>(a.bdesc, ticket, tagg); store_elem(sm.tagg[par], tagg); }
         }
         Elem suf;
         if (warp == 0) {
             suf = lookback<Ops>(a.bdesc, ticket);
             if (lane == 0) {
-                Ad g0 = a.g_in ? load_adj<ND, R>(a.g_in) : adj_zero<ND, R>();
-                const Ad gt = bwd_apply<ND>(suf, g0);
-#pragma unroll
-                for (int d = 0; d < ND; ++d) { sm.misc[par][2 * d] = gt.a[d].x; sm.misc[par][2 * d + 1] = gt.a[d].y; }
-                sm.misc[par][2 * ND] = gt.P.a; sm.misc[par][2 * ND + 1] = gt.P.b; sm.misc[par][2 * ND + 2] = gt.P.c;
+                const Ad g0 = a.g_in ? M::load_adj([&](int i) { return a.g_in[i]; }) : M::adj_zero();
+                const Ad gt = M::bwd_apply(suf, g0);
+                M::store_adj(gt, [&](int i) -> R& { return sm.misc[par][i]; });
             }
         }
         __syncthreads();
         if (warp == 0 && lane == 0) {
             const Elem tagg = load_elem<Elem>(sm.tagg[par]);
-            if (a.summary || !Ops::is_const(tagg)) publish_incl<Ops>(a.bdesc, ticket, bwd_combine<ND>(tagg, suf));
+            if (a.summary || !Ops::is_const(tagg)) publish_incl<Ops>(a.bdesc, ticket, M::bwd_combine(tagg, suf));
         }
 #ifdef SSDE_STATS
         tc3 = clock64();
 #endif
         if (a.summary) continue;
         // (4) adjoint entering this thread's last row, then the reverse sweep over its rows
-        Ad g = load_adj<ND, R>(sm.misc[par]);
+        Ad g = M::load_adj([&](int i) { return sm.misc[par][i]; });
         {
             int w1 = warp + 1;
             while (w1 < NWARP - 1 && !Ops::is_const(load_elem<Elem>(sm.wagg[par][w1]))) ++w1;
 #pragma unroll 1
-            for (int ww = min(w1, NWARP - 1); ww > warp; --ww) g = bwd_apply<ND>(load_elem<Elem>(sm.wagg[par][ww]), g);
+            for (int ww = min(w1, NWARP - 1); ww > warp; --ww) g = M::bwd_apply(load_elem<Elem>(sm.wagg[par][ww]), g);
         }
-        g = bwd_apply<ND>(exc, g);
+        g = M::bwd_apply(exc, g);
         R gh = 0.0;
-        nx = load_row<ND, R>(a, base + (LC - 1) * 32, (uint8_t)(fl >> (8 * (LC - 1))) != 0xff);
+        nx = load_row<M>(a, base + (LC - 1) * 32, (uint8_t)(fl >> (8 * (LC - 1))) != 0xff);
 #pragma unroll 1
         for (int k = LC - 1; k >= 0; --k) {
             const uint8_t f = (uint8_t)(fl >> (8 * k));
-            const RowIn<ND, R> r = nx;
-            if (k > 0) nx = load_row<ND, R>(a, base + (k - 1) * 32, (uint8_t)(fl >> (8 * (k - 1))) != 0xff);
+            const RowIn<M> r = nx;
+            if (k > 0) nx = load_row<M>(a, base + (k - 1) * 32, (uint8_t)(fl >> (8 * (k - 1))) != 0xff);
             R gp[NP];
 #pragma unroll
             for (int j = 0; j < NP; ++j) gp[j] = 0.0;
             if (f != 0xff) {
                 if (f & ROW_START) {
-                    g = adj_zero<ND, R>();
+                    g = M::adj_zero();
                 } else {
                     R mu[ND];
 #pragma unroll
                     for (int d = 0; d < ND; ++d) mu[d] = 0.0;
                     if (!mu0) row_eta_prefix<ND>(w, k, a.theta, mu);
-                    St sk;
-#pragma unroll
-                    for (int d = 0; d < ND; ++d) {
-                        sk.a[d].x = sm.Rs[k][2 * d][tid];
-                        sk.a[d].y = sm.Rs[k][2 * d + 1][tid];
-                    }
-                    sk.P.a = sm.Rs[k][2 * ND][tid];
-                    sk.P.b = sm.Rs[k][2 * ND + 1][tid];
-                    sk.P.c = sm.Rs[k][2 * ND + 2][tid];
-                    const StepParT<R> sp = make_step(r.tau, r.e, r.s2, r.dt);
+                    St sk = M::load_state([&](int i) { return sm.Rs[k][i][tid]; });
+                    const typename M::Step sp = M::make_step(r.rp, r.dt);
                     const bool has = (f & ROW_OBS) != 0, cut = (f & ROW_LAST) != 0;
-                    StepAux<ND, R> ax;
+                    typename M::Aux ax;
                     R F, qd;
-                    fwd_step_q<ND, true>(sk, sp, r.y, mu, has, h, &ax, F, qd);
-                    const Ad gin = cut ? adj_zero<ND, R>() : g;
+                    M::template fwd_step<true>(sk, sp, r.y, mu, has, h, &ax, F, qd);
+                    const Ad gin = cut ? M::adj_zero() : g;
                     R g_h;
-                    row_param_grad<ND>(gin, sp, ax, mu, r.tau, r.e, r.s2, r.dt, has, gp, gp[ND], gp[ND + 1], g_h);
+                    M::row_param_grad(gin, sp, ax, mu, r.rp, r.dt, has, gp, g_h);
                     gh += g_h;
-                    g = bwd_apply<ND>(bwd_row_elem<ND>(sp, ax, has, cut), g);
+                    g = M::bwd_apply(M::bwd_row_elem(sp, ax, has, cut), g);
                 }
             }
             // eta_bar of this row replaces its (consumed) forward state
@@ -598,34 +535,28 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_bwd_kernel(CtcrwArgs<ND, R> a)
 // time-sharded runs: composite elements of the shards (gathered from all ranks) -> incoming
 // state / adjoint of shard `me`.  One thread.
 // ---------------------------------------------------------------------------------------------
-template <int ND, class R = double>
+template <class M>
 __global__ void shard_state_kernel(const double* __restrict__ elems, int n_shards, int me, Sym2 P0,
-                                   R* __restrict__ s_out) {
-    using Elem = FwdElem<ND, R>;
+                                   typename M::R* __restrict__ s_out) {
+    using R = typename M::R;
+    using Elem = typename M::FwdElem;
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    Elem acc = fwd_identity<ND, R>();
-    for (int i = 0; i < me && i < n_shards; ++i) acc = fwd_combine<ND>(acc, load_elem<Elem>(elems + (size_t)i * Elem::NDBL));
-    State<ND, R> s0;
-    s0.P = {P0.a, P0.b, P0.c};
-#pragma unroll
-    for (int d = 0; d < ND; ++d) s0.a[d] = {0.0, 0.0};
-    const State<ND, R> s = fwd_apply<ND>(acc, s0);    // shard 0 begins with a track start: s0 is irrelevant
-#pragma unroll
-    for (int d = 0; d < ND; ++d) { s_out[2 * d] = s.a[d].x; s_out[2 * d + 1] = s.a[d].y; }
-    s_out[2 * ND] = s.P.a; s_out[2 * ND + 1] = s.P.b; s_out[2 * ND + 2] = s.P.c;
+    Elem acc = M::fwd_identity();
+    for (int i = 0; i < me && i < n_shards; ++i) acc = M::fwd_combine(acc, load_elem<Elem>(elems + (size_t)i * Elem::NDBL));
+    const typename M::State s = M::fwd_apply(acc, M::zero_state(P0));   // shard 0 begins with a track start: the input is irrelevant
+    M::store_state(s, [&](int i) -> R& { return s_out[i]; });
 }
 
-template <int ND, class R = double>
+template <class M>
 __global__ void shard_adjoint_kernel(const double* __restrict__ elems, int n_shards, int me,
-                                     R* __restrict__ g_out) {
-    using Elem = BwdElem<ND, R>;
+                                     typename M::R* __restrict__ g_out) {
+    using R = typename M::R;
+    using Elem = typename M::BwdElem;
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    Elem acc = bwd_identity<ND, R>();
-    for (int i = n_shards - 1; i > me; --i) acc = bwd_combine<ND>(load_elem<Elem>(elems + (size_t)i * Elem::NDBL), acc);
-    const Adj<ND, R> g = bwd_apply<ND>(acc, adj_zero<ND, R>());
-#pragma unroll
-    for (int d = 0; d < ND; ++d) { g_out[2 * d] = g.a[d].x; g_out[2 * d + 1] = g.a[d].y; }
-    g_out[2 * ND] = g.P.a; g_out[2 * ND + 1] = g.P.b; g_out[2 * ND + 2] = g.P.c;
+    Elem acc = M::bwd_identity();
+    for (int i = n_shards - 1; i > me; --i) acc = M::bwd_combine(load_elem<Elem>(elems + (size_t)i * Elem::NDBL), acc);
+    const typename M::Adj g = M::bwd_apply(acc, M::adj_zero());
+    M::store_adj(g, [&](int i) -> R& { return g_out[i]; });
 }
 
 }  // namespace ssde

@@ -1,0 +1,290 @@
+// Model traits: everything the scan kernels (kernels_ctcrw.cuh) need to know about a Kalman
+// model -- the reference's three filter templates share one loop skeleton
+// (nllk_ctcrw.hpp:195-247, nllk_ou_ssm.hpp:163-213, nllk_bm_ssm.hpp:127-175) and differ only in
+// the state dimension and in makeT / makeQ / makeB:
+//   CtcrwModel  2 states per dimension (position, velocity)   ctcrw_math.cuh
+//   OuSsmModel  1 state per dimension, T = exp(-dt/tau)       ssm1_math.cuh
+//   BmSsmModel  1 state per dimension, T = 1, drift mu dt     ssm1_math.cuh
+// A traits class M<ND, R> provides the element types and algebra, the natural-scale transform of
+// a linear-predictor row, packing of states / step quantities into arrays (accessor `at(i)`
+// returns a reference to the i-th scalar), and the closed-form gradient of one row.
+#pragma once
+
+#include "ctcrw_math.cuh"
+#include "ssm1_math.cuh"
+
+namespace ssde {
+
+constexpr double CONST_MAP_TOL = 1e-60;     // see FwdOps / is_const in common.cuh
+SSDE_HD bool tiny(double x) { return fabs(x) <= CONST_MAP_TOL; }
+SSDE_HD bool tiny(const Dual& x) { return fabs(x.v) <= CONST_MAP_TOL && fabs(x.d) <= CONST_MAP_TOL; }
+template <class R>
+SSDE_HD bool tiny(const Mat2T<R>& m) { return tiny(m.m11) && tiny(m.m12) && tiny(m.m21) && tiny(m.m22); }
+
+// ---------------------------------------------------------------------------------------------
+template <int ND_, class R_>
+struct CtcrwModel {
+    static constexpr int ND = ND_;
+    using R = R_;
+    static constexpr int NP = ND + 2;        // SDE parameters per row: mu_1..mu_d, tau, nu
+    static constexpr int SD = 2 * ND;        // state means per row (columns of a0 / aest_all)
+    static constexpr int FS = 2 * ND + 3;    // scalars of a State / Adj
+    static constexpr int NW = 3;             // transformed parameters kept for the adjoint kernel
+    static constexpr int NC = 5;             // step quantities cached in shared memory
+    using State = ssde::State<ND, R>;
+    using Adj = ssde::Adj<ND, R>;
+    using FwdElem = ssde::FwdElem<ND, R>;
+    using BwdElem = ssde::BwdElem<ND, R>;
+    using Step = StepParT<R>;
+    using Aux = StepAux<ND, R>;
+    struct RowPar { R tau, e, s2; };
+
+    static SSDE_HD RowPar transform(const R* eta, double dt) {
+        RowPar r;
+        transform_row(eta[ND], eta[ND + 1], dt, r.tau, r.e, r.s2);
+        return r;
+    }
+    static SSDE_HD RowPar dead_rowpar() { return RowPar{R(1.0), R(0.0), R(0.0)}; }
+    template <class F> static SSDE_HD void store_rowpar(const RowPar& r, F at) { at(0) = r.tau; at(1) = r.e; at(2) = r.s2; }
+    template <class F> static SSDE_HD RowPar load_rowpar(F at) { return RowPar{at(0), at(1), at(2)}; }
+    static SSDE_HD Step make_step(const RowPar& r, double dt) { return ssde::make_step(r.tau, r.e, r.s2, dt); }
+    template <class F> static SSDE_HD void store_step(const Step& sp, F at) {
+        at(0) = sp.T12; at(1) = sp.e; at(2) = sp.Q.a; at(3) = sp.Q.b; at(4) = sp.Q.c;
+    }
+    template <class F> static SSDE_HD Step load_step(F at, double dt) {
+        Step sp;
+        sp.T12 = at(0); sp.e = at(1); sp.Q.a = at(2); sp.Q.b = at(3); sp.Q.c = at(4);
+        sp.B1 = dt - sp.T12; sp.B2 = 1.0 - sp.e;          // makeB_ctcrw, nllk_ctcrw.hpp:87-88
+        return sp;
+    }
+    // a0 row = (x, 0, y, 0, ...) R/sde.R:574-580; P0 = shared 2x2 block
+    static SSDE_HD State start_state(const double* a0row, const Sym2& P0) {
+        State s;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) s.a[d] = {a0row[2 * d], a0row[2 * d + 1]};
+        s.P = {P0.a, P0.b, P0.c};
+        return s;
+    }
+    static SSDE_HD State zero_state(const Sym2& P0) {
+        State s;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) s.a[d] = {0.0, 0.0};
+        s.P = {P0.a, P0.b, P0.c};
+        return s;
+    }
+    template <class F> static SSDE_HD void store_state(const State& s, F at) {
+#pragma unroll
+        for (int d = 0; d < ND; ++d) { at(2 * d) = s.a[d].x; at(2 * d + 1) = s.a[d].y; }
+        at(2 * ND) = s.P.a; at(2 * ND + 1) = s.P.b; at(2 * ND + 2) = s.P.c;
+    }
+    template <class F> static SSDE_HD State load_state(F at) {
+        State s;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) s.a[d] = {at(2 * d), at(2 * d + 1)};
+        s.P = {at(2 * ND), at(2 * ND + 1), at(2 * ND + 2)};
+        return s;
+    }
+    template <class F> static SSDE_HD void store_adj(const Adj& g, F at) {
+#pragma unroll
+        for (int d = 0; d < ND; ++d) { at(2 * d) = g.a[d].x; at(2 * d + 1) = g.a[d].y; }
+        at(2 * ND) = g.P.a; at(2 * ND + 1) = g.P.b; at(2 * ND + 2) = g.P.c;
+    }
+    template <class F> static SSDE_HD Adj load_adj(F at) {
+        Adj g;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) g.a[d] = {at(2 * d), at(2 * d + 1)};
+        g.P = {at(2 * ND), at(2 * ND + 1), at(2 * ND + 2)};
+        return g;
+    }
+    static SSDE_HD void store_mean(const State& s, double* o) {
+#pragma unroll
+        for (int d = 0; d < ND; ++d) { o[2 * d] = value(s.a[d].x); o[2 * d + 1] = value(s.a[d].y); }
+    }
+    // forward
+    static SSDE_HD FwdElem fwd_identity() { return ssde::fwd_identity<ND, R>(); }
+    static SSDE_HD void fwd_append(FwdElem& E, const Step& sp, const double* y, const R* mu, bool has, const R& h) { ssde::fwd_append<ND>(E, sp, y, mu, has, h); }
+    static SSDE_HD void fwd_append_start(FwdElem& E, const State& s0) { ssde::fwd_append_start<ND>(E, s0); }
+    static SSDE_HD FwdElem fwd_combine(const FwdElem& a, const FwdElem& b) { return ssde::fwd_combine<ND>(a, b); }
+    static SSDE_HD State fwd_apply(const FwdElem& E, const State& s) { return ssde::fwd_apply<ND>(E, s); }
+    static SSDE_HD bool fwd_is_const(const FwdElem& E) { return tiny(E.A); }
+    template <bool AUX>
+    static SSDE_HD void fwd_step(State& s, const Step& sp, const double* y, const R* mu, bool has, const R& h, Aux* aux, R& F, R& qd) {
+        ssde::fwd_step_q<ND, AUX>(s, sp, y, mu, has, h, aux, F, qd);
+    }
+    // adjoint
+    static SSDE_HD Adj adj_zero() { return ssde::adj_zero<ND, R>(); }
+    static SSDE_HD BwdElem bwd_identity() { return ssde::bwd_identity<ND, R>(); }
+    static SSDE_HD BwdElem bwd_const(const Adj& g) { return ssde::bwd_const<ND>(g); }
+    static SSDE_HD BwdElem bwd_row_elem(const Step& sp, const Aux& ax, bool has, bool cut) { return ssde::bwd_row_elem<ND>(sp, ax, has, cut); }
+    static SSDE_HD BwdElem bwd_combine(const BwdElem& a, const BwdElem& b) { return ssde::bwd_combine<ND>(a, b); }
+    static SSDE_HD Adj bwd_apply(const BwdElem& E, const Adj& g) { return ssde::bwd_apply<ND>(E, g); }
+    static SSDE_HD bool bwd_is_const(const BwdElem& E) { return tiny(E.L); }
+    // gp[NP] = d nllk / d eta of this row
+    static SSDE_HD void row_param_grad(const Adj& g, const Step& sp, const Aux& ax, const R* mu, const RowPar& rp, double dt,
+                                       bool has, R* gp, R& g_h) {
+        ssde::row_param_grad<ND>(g, sp, ax, mu, rp.tau, rp.e, rp.s2, dt, has, gp, gp[ND], gp[ND + 1], g_h);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// shared part of the one-state-per-dimension models
+template <int ND_, class R_>
+struct Ssm1Base {
+    static constexpr int ND = ND_;
+    using R = R_;
+    static constexpr int SD = ND;
+    static constexpr int FS = ND + 1;
+    using State = State1<ND, R>;
+    using Adj = Adj1<ND, R>;
+    using FwdElem = FwdElem1<ND, R>;
+    using BwdElem = BwdElem1<ND, R>;
+    using Step = Step1<R>;
+    using Aux = StepAux1<ND, R>;
+
+    // a0 row = first observation (R/sde.R:549-550); P0 = c I
+    static SSDE_HD State start_state(const double* a0row, const Sym2& P0) {
+        State s;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) s.a[d] = a0row[d];
+        s.p = P0.a;
+        return s;
+    }
+    static SSDE_HD State zero_state(const Sym2& P0) {
+        State s;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) s.a[d] = 0.0;
+        s.p = P0.a;
+        return s;
+    }
+    template <class F> static SSDE_HD void store_state(const State& s, F at) {
+#pragma unroll
+        for (int d = 0; d < ND; ++d) at(d) = s.a[d];
+        at(ND) = s.p;
+    }
+    template <class F> static SSDE_HD State load_state(F at) {
+        State s;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) s.a[d] = at(d);
+        s.p = at(ND);
+        return s;
+    }
+    template <class F> static SSDE_HD void store_adj(const Adj& g, F at) {
+#pragma unroll
+        for (int d = 0; d < ND; ++d) at(d) = g.a[d];
+        at(ND) = g.p;
+    }
+    template <class F> static SSDE_HD Adj load_adj(F at) {
+        Adj g;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) g.a[d] = at(d);
+        g.p = at(ND);
+        return g;
+    }
+    static SSDE_HD void store_mean(const State& s, double* o) {
+#pragma unroll
+        for (int d = 0; d < ND; ++d) o[d] = value(s.a[d]);
+    }
+    static SSDE_HD FwdElem fwd_identity() { return fwd_identity1<ND, R>(); }
+    static SSDE_HD void fwd_append(FwdElem& E, const Step& sp, const double* y, const R* mu, bool has, const R& h) { fwd_append1<ND>(E, sp, y, mu, has, h); }
+    static SSDE_HD void fwd_append_start(FwdElem& E, const State& s0) { fwd_append_start1<ND>(E, s0); }
+    static SSDE_HD FwdElem fwd_combine(const FwdElem& a, const FwdElem& b) { return fwd_combine1<ND>(a, b); }
+    static SSDE_HD State fwd_apply(const FwdElem& E, const State& s) { return fwd_apply1<ND>(E, s); }
+    static SSDE_HD bool fwd_is_const(const FwdElem& E) { return tiny(E.A); }
+    template <bool AUX>
+    static SSDE_HD void fwd_step(State& s, const Step& sp, const double* y, const R* mu, bool has, const R& h, Aux* aux, R& F, R& qd) {
+        fwd_step1<ND, AUX>(s, sp, y, mu, has, h, aux, F, qd);
+    }
+    static SSDE_HD Adj adj_zero() { return adj_zero1<ND, R>(); }
+    static SSDE_HD BwdElem bwd_identity() { return bwd_identity1<ND, R>(); }
+    static SSDE_HD BwdElem bwd_const(const Adj& g) { return bwd_const1<ND>(g); }
+    static SSDE_HD BwdElem bwd_row_elem(const Step& sp, const Aux& ax, bool has, bool cut) { return bwd_row_elem1<ND>(sp, ax, has, cut); }
+    static SSDE_HD BwdElem bwd_combine(const BwdElem& a, const BwdElem& b) { return bwd_combine1<ND>(a, b); }
+    static SSDE_HD Adj bwd_apply(const BwdElem& E, const Adj& g) { return bwd_apply1<ND>(E, g); }
+    static SSDE_HD bool bwd_is_const(const BwdElem& E) { return tiny(E.L); }
+};
+
+// OU + measurement error, nllk_ou_ssm.hpp: mu_d, tau = exp(eta_tau), kappa = exp(eta_kappa) (:122-124)
+template <int ND_, class R_>
+struct OuSsmModel : Ssm1Base<ND_, R_> {
+    using B = Ssm1Base<ND_, R_>;
+    using R = R_;
+    static constexpr int ND = ND_;
+    static constexpr int NP = ND + 2;
+    static constexpr int NW = 3;
+    static constexpr int NC = 2;
+    struct RowPar { R tau, e, kappa; };
+    static SSDE_HD RowPar transform(const R* eta, double dt) {
+        RowPar r;
+        r.tau = exp(eta[ND]);
+        r.kappa = exp(eta[ND + 1]);
+        r.e = exp(-dt / r.tau);                              // makeT_ou_ssm :35
+        return r;
+    }
+    static SSDE_HD RowPar dead_rowpar() { return RowPar{R(1.0), R(0.0), R(0.0)}; }
+    template <class F> static SSDE_HD void store_rowpar(const RowPar& r, F at) { at(0) = r.tau; at(1) = r.e; at(2) = r.kappa; }
+    template <class F> static SSDE_HD RowPar load_rowpar(F at) { return RowPar{at(0), at(1), at(2)}; }
+    static SSDE_HD typename B::Step make_step(const RowPar& r, double dt) {
+        typename B::Step sp;
+        sp.t = r.e;
+        sp.cm = 1.0 - r.e;                                   // makeB_ou_ssm :50
+        sp.q = r.kappa * (1.0 - exp(-2.0 * dt / r.tau));     // makeQ_ou_ssm :66 (its own exp, as in the reference)
+        return sp;
+    }
+    template <class F> static SSDE_HD void store_step(const typename B::Step& sp, F at) { at(0) = sp.t; at(1) = sp.q; }
+    template <class F> static SSDE_HD typename B::Step load_step(F at, double) {
+        typename B::Step sp;
+        sp.t = at(0); sp.q = at(1); sp.cm = 1.0 - sp.t;
+        return sp;
+    }
+    static SSDE_HD void row_param_grad(const typename B::Adj& g, const typename B::Step& sp, const typename B::Aux& ax, const R* mu,
+                                       const RowPar& rp, double dt, bool has, R* gp, R& g_h) {
+        R tbar, qbar, cmbar;
+        step_adjoint1<ND>(g, sp, ax, mu, has, tbar, qbar, cmbar, gp, g_h);
+        // t = e, cm = 1 - e, q = kappa (1 - e2), e = exp(-dt/tau), e2 = exp(-2 dt/tau), tau = exp(eta_tau)
+        const R e2 = 1.0 - sp.q / rp.kappa;
+        const R ebar = tbar - cmbar;
+        const R r_ = dt / rp.tau;
+        gp[ND] = ebar * rp.e * r_ - qbar * rp.kappa * e2 * (2.0 * r_);
+        gp[ND + 1] = qbar * sp.q;
+    }
+};
+
+// BM + measurement error, nllk_bm_ssm.hpp: mu_d, sigma = exp(eta_sigma) (:89-90)
+template <int ND_, class R_>
+struct BmSsmModel : Ssm1Base<ND_, R_> {
+    using B = Ssm1Base<ND_, R_>;
+    using R = R_;
+    static constexpr int ND = ND_;
+    static constexpr int NP = ND + 1;
+    static constexpr int NW = 1;
+    static constexpr int NC = 1;
+    struct RowPar { R s2; };
+    static SSDE_HD RowPar transform(const R* eta, double) {
+        const R sigma = exp(eta[ND]);
+        return RowPar{sigma * sigma};
+    }
+    static SSDE_HD RowPar dead_rowpar() { return RowPar{R(0.0)}; }
+    template <class F> static SSDE_HD void store_rowpar(const RowPar& r, F at) { at(0) = r.s2; }
+    template <class F> static SSDE_HD RowPar load_rowpar(F at) { return RowPar{at(0)}; }
+    static SSDE_HD typename B::Step make_step(const RowPar& r, double dt) {
+        typename B::Step sp;
+        sp.t = 1.0;                                          // T = I, nllk_bm_ssm.hpp:100-101
+        sp.cm = dt;                                          // drift = mu * dt, :140
+        sp.q = r.s2 * dt;                                    // makeQ_bm_ssm :32
+        return sp;
+    }
+    template <class F> static SSDE_HD void store_step(const typename B::Step& sp, F at) { at(0) = sp.q; }
+    template <class F> static SSDE_HD typename B::Step load_step(F at, double dt) {
+        typename B::Step sp;
+        sp.t = 1.0; sp.cm = dt; sp.q = at(0);
+        return sp;
+    }
+    static SSDE_HD void row_param_grad(const typename B::Adj& g, const typename B::Step& sp, const typename B::Aux& ax, const R* mu,
+                                       const RowPar&, double, bool has, R* gp, R& g_h) {
+        R tbar, qbar, cmbar;
+        step_adjoint1<ND>(g, sp, ax, mu, has, tbar, qbar, cmbar, gp, g_h);
+        gp[ND] = 2.0 * qbar * sp.q;                          // q = exp(2 eta_sigma) dt
+    }
+};
+
+}  // namespace ssde

@@ -44,6 +44,12 @@ struct DevBuf {
 
 }  // namespace
 
+namespace {
+inline bool is_kalman(int model) { return model == SSDE_CTCRW || model == SSDE_OU_SSM || model == SSDE_BM_SSM; }
+inline int sde_par_count(int model, int n_dim) { return (model == SSDE_BM || model == SSDE_BM_SSM) ? n_dim + 1 : n_dim + 2; }
+inline int state_means(int model, int n_dim) { return model == SSDE_CTCRW ? 2 * n_dim : n_dim; }   // columns of a0 / aest_all
+}  // namespace
+
 struct ssde_handle {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -81,6 +87,7 @@ struct ssde_handle {
     int ntiles_f = 0, ntiles_b = 0, grid_lp = 0, grid_f = 0, grid_b = 0;
     int64_t ntiles_lp = 0;
     int64_t nchunks = 0;
+    int fs = 0, fwd_elem = 0, bwd_elem = 0;      // Kalman models: scalars of a state, doubles of the scan elements
     int last_launches = 0;
     bool timed = false;
     // optional per-kernel timing (ssde_set_profile): event k is recorded before kernel k
@@ -499,7 +506,7 @@ int setup_penalty(ssde_handle* h, const ssde_triplet& S, int n_smooth, const int
         }
         rp[h->p_re] = (uint32_t)cols.size();
         // additive constants of nllk_sde's penalty (nllk_sde.hpp:109-116)
-        if (h->model != SSDE_CTCRW) {
+        if (!is_kalman(h->model)) {
             double cst = 0.0;
             for (int i = 0; i < n_smooth; ++i) {
                 const int m = ncol_re[i], o = off[i];
@@ -547,12 +554,24 @@ int max_grid(K kernel, int nt, size_t smem, int num_sms, std::string& err, int& 
     return SSDE_OK;
 }
 
-template <int ND>
+// Calls fn(M{}) with the traits class (models.cuh) of the handle's Kalman model and dimension.
+template <class R, class Fn>
+int with_kalman_model(const ssde_handle* h, Fn&& fn) {
+    const int nd = h->n_dim;
+    switch (h->model) {
+        case SSDE_CTCRW: return nd == 1 ? fn(CtcrwModel<1, R>{}) : fn(CtcrwModel<2, R>{});
+        case SSDE_OU_SSM: return nd == 1 ? fn(OuSsmModel<1, R>{}) : fn(OuSsmModel<2, R>{});
+        case SSDE_BM_SSM: return nd == 1 ? fn(BmSsmModel<1, R>{}) : (nd == 2 ? fn(BmSsmModel<2, R>{}) : fn(BmSsmModel<3, R>{}));
+    }
+    return SSDE_ERR_UNSUPPORTED;
+}
+
+template <class M>
 int ctcrw_grids(ssde_handle* h) {
     std::string& err = h->err;
     int rc;
-    if ((rc = max_grid(ctcrw_fwd_kernel<ND, FWD_NT, FWD_MINB>, FWD_NT, sizeof(FwdSmem<ND, FWD_NT>), h->num_sms, err, h->grid_f))) return rc;
-    if ((rc = max_grid(ctcrw_bwd_kernel<ND, BWD_NT, BWD_MINB>, BWD_NT, sizeof(BwdSmem<ND, BWD_NT>), h->num_sms, err, h->grid_b))) return rc;
+    if ((rc = max_grid(ctcrw_fwd_kernel<M, FWD_NT, FWD_MINB>, FWD_NT, sizeof(FwdSmem<M, FWD_NT>), h->num_sms, err, h->grid_f))) return rc;
+    if ((rc = max_grid(ctcrw_bwd_kernel<M, BWD_NT, BWD_MINB>, BWD_NT, sizeof(BwdSmem<M, BWD_NT>), h->num_sms, err, h->grid_b))) return rc;
     return SSDE_OK;
 }
 
@@ -573,8 +592,8 @@ int finish_setup(ssde_handle* h) {
     CUDA_TRY(cudaEventCreate(&h->ev0));
     CUDA_TRY(cudaEventCreate(&h->ev1));
     const int p = h->p_fe + h->p_re;
-    h->o_sig = (h->model == SSDE_CTCRW) ? 0 : -1;
-    h->o_fe = (h->model == SSDE_CTCRW) ? 1 : 0;
+    h->o_sig = is_kalman(h->model) ? 0 : -1;
+    h->o_fe = is_kalman(h->model) ? 1 : 0;
     h->o_ll = h->o_fe + h->p_fe;
     h->o_re = h->o_ll + h->n_s;
     h->npar = h->o_re + h->p_re;
@@ -591,29 +610,31 @@ int finish_setup(ssde_handle* h) {
     if ((rc = dev_alloc<unsigned>(h->counters, 4, err))) return rc;
     CUDA_TRY(cudaMemset(h->counters.p, 0, 4 * sizeof(unsigned)));
     CUDA_TRY(cudaMallocHost(&h->h_pinned, sizeof(double) * (2 * (size_t)h->npar + 4)));
-    if (h->model == SSDE_CTCRW) {
-        const int nd = h->n_dim;
+    if (is_kalman(h->model)) {
         h->ntiles_f = (int)(h->n_pad / (FWD_NT * LC));
         h->ntiles_b = (int)(h->n_pad / (BWD_NT * LC));
         h->nchunks = h->n_pad / LC;
-        if ((rc = dev_alloc<double>(h->ckpt, (size_t)h->nchunks * (2 * nd + 3), err))) return rc;
-        if ((rc = dev_alloc<double>(h->wg, (size_t)h->n_pad * 3, err))) return rc;
-        if ((rc = dev_alloc<double>(h->s_in, 2 * nd + 3, err))) return rc;
-        if ((rc = dev_alloc<double>(h->g_in, 2 * nd + 3, err))) return rc;
+        rc = with_kalman_model<double>(h, [&](auto m) -> int {
+            using M = decltype(m);
+            int rc;
+            h->fs = M::FS; h->fwd_elem = M::FwdElem::NDBL; h->bwd_elem = M::BwdElem::NDBL;
+            if ((rc = dev_alloc<double>(h->ckpt, (size_t)h->nchunks * M::FS, err))) return rc;
+            if ((rc = dev_alloc<double>(h->wg, (size_t)h->n_pad * M::NW, err))) return rc;
+            if ((rc = dev_alloc<double>(h->s_in, M::FS, err))) return rc;
+            if ((rc = dev_alloc<double>(h->g_in, M::FS, err))) return rc;
+            if ((rc = dev_alloc<double>(h->f_agg, (size_t)h->ntiles_f * M::FwdElem::NDBL, err))) return rc;
+            if ((rc = dev_alloc<double>(h->f_incl, (size_t)h->ntiles_f * M::FwdElem::NDBL, err))) return rc;
+            if ((rc = dev_alloc<double>(h->b_agg, (size_t)h->ntiles_b * M::BwdElem::NDBL, err))) return rc;
+            if ((rc = dev_alloc<double>(h->b_incl, (size_t)h->ntiles_b * M::BwdElem::NDBL, err))) return rc;
+            return ctcrw_grids<M>(h);
+        });
+        if (rc) return rc;
         if ((rc = dev_alloc<double>(h->tile_llk, h->n_pad / WT, err))) return rc;
         if ((rc = dev_alloc<double>(h->tile_gh, h->n_pad / WT, err))) return rc;
         if ((rc = dev_alloc<unsigned>(h->f_status, h->ntiles_f, err))) return rc;
         if ((rc = dev_alloc<unsigned>(h->b_status, h->ntiles_b, err))) return rc;
         CUDA_TRY(cudaMemset(h->f_status.p, 0, sizeof(unsigned) * std::max(h->ntiles_f, 1)));
         CUDA_TRY(cudaMemset(h->b_status.p, 0, sizeof(unsigned) * std::max(h->ntiles_b, 1)));
-        const size_t fe = (nd == 1) ? FwdElem<1>::NDBL : FwdElem<2>::NDBL;
-        const size_t be = (nd == 1) ? BwdElem<1>::NDBL : BwdElem<2>::NDBL;
-        if ((rc = dev_alloc<double>(h->f_agg, (size_t)h->ntiles_f * fe, err))) return rc;
-        if ((rc = dev_alloc<double>(h->f_incl, (size_t)h->ntiles_f * fe, err))) return rc;
-        if ((rc = dev_alloc<double>(h->b_agg, (size_t)h->ntiles_b * be, err))) return rc;
-        if ((rc = dev_alloc<double>(h->b_incl, (size_t)h->ntiles_b * be, err))) return rc;
-        if (nd == 1) rc = ctcrw_grids<1>(h); else rc = ctcrw_grids<2>(h);
-        if (rc) return rc;
         h->grid_f = std::min(h->grid_f, std::max(h->ntiles_f, 1));
         h->grid_b = std::min(h->grid_b, std::max(h->ntiles_b, 1));
     } else {
@@ -656,10 +677,10 @@ DesignV2 design_of(const ssde_handle* h) {
 
 constexpr int TAN_MINB = 1;             // resident CTAs per SM the tangent kernels are compiled for
 
-template <int ND, class R>
-CtcrwArgs<ND, R> ctcrw_args(ssde_handle* h, const double* d_par, const double* d_dir, double* aest) {
+template <class R>
+KalmanArgs<R> ctcrw_args(ssde_handle* h, const double* d_par, const double* d_dir, double* aest) {
     constexpr bool TAN = !std::is_same<R, double>::value;
-    CtcrwArgs<ND, R> a;
+    KalmanArgs<R> a;
     a.X = design_of(h);
     a.theta = Theta{h->theta.as<double>(), TAN ? h->t_theta_dot.as<double>() : nullptr};
     a.obs = h->obs.as<double>(); a.dt = h->dt.as<double>(); a.flags = h->flags.as<uint8_t>();
@@ -698,33 +719,35 @@ int new_scan_epoch(ssde_handle* h, cudaStream_t st) {
     return SSDE_OK;
 }
 
-template <int ND, class R>
+template <class M>
 int launch_ctcrw_fwd(ssde_handle* h, const double* d_par, const double* d_dir, cudaStream_t st, double* aest, bool summary) {
+    using R = typename M::R;
     constexpr bool TAN = !std::is_same<R, double>::value;
     std::string& err = h->err;
     int rc = new_scan_epoch(h, st);
     if (rc) return rc;
-    CtcrwArgs<ND, R> a = ctcrw_args<ND, R>(h, d_par, d_dir, aest);
+    KalmanArgs<R> a = ctcrw_args<R>(h, d_par, d_dir, aest);
     a.summary = summary ? 1 : 0;
     mark(h, st, TAN ? "ctcrw_fwd_tangent" : (summary ? "ctcrw_fwd_summary" : "ctcrw_fwd"));
-    if constexpr (TAN) ctcrw_fwd_kernel<ND, FWD_NT, TAN_MINB, R><<<h->grid_f2, FWD_NT, sizeof(FwdSmem<ND, FWD_NT, R>), st>>>(a);
-    else ctcrw_fwd_kernel<ND, FWD_NT, FWD_MINB, R><<<h->grid_f, FWD_NT, sizeof(FwdSmem<ND, FWD_NT, R>), st>>>(a);
+    if constexpr (TAN) ctcrw_fwd_kernel<M, FWD_NT, TAN_MINB><<<h->grid_f2, FWD_NT, sizeof(FwdSmem<M, FWD_NT>), st>>>(a);
+    else ctcrw_fwd_kernel<M, FWD_NT, FWD_MINB><<<h->grid_f, FWD_NT, sizeof(FwdSmem<M, FWD_NT>), st>>>(a);
     CUDA_TRY(cudaGetLastError());
     return SSDE_OK;
 }
 
-template <int ND, class R>
+template <class M>
 int launch_ctcrw_bwd(ssde_handle* h, const double* d_par, const double* d_dir, cudaStream_t st, bool summary) {
+    using R = typename M::R;
     constexpr bool TAN = !std::is_same<R, double>::value;
     std::string& err = h->err;
     int rc = new_scan_epoch(h, st);
     if (rc) return rc;
-    CtcrwArgs<ND, R> a = ctcrw_args<ND, R>(h, d_par, d_dir, nullptr);
+    KalmanArgs<R> a = ctcrw_args<R>(h, d_par, d_dir, nullptr);
     a.ntiles = h->ntiles_b;
     a.summary = summary ? 1 : 0;
     mark(h, st, TAN ? "ctcrw_bwd_tangent" : (summary ? "ctcrw_bwd_summary" : "ctcrw_bwd"));
-    if constexpr (TAN) ctcrw_bwd_kernel<ND, BWD_NT, TAN_MINB, R><<<h->grid_b2, BWD_NT, sizeof(BwdSmem<ND, BWD_NT, R>), st>>>(a);
-    else ctcrw_bwd_kernel<ND, BWD_NT, BWD_MINB, R><<<h->grid_b, BWD_NT, sizeof(BwdSmem<ND, BWD_NT, R>), st>>>(a);
+    if constexpr (TAN) ctcrw_bwd_kernel<M, BWD_NT, TAN_MINB><<<h->grid_b2, BWD_NT, sizeof(BwdSmem<M, BWD_NT>), st>>>(a);
+    else ctcrw_bwd_kernel<M, BWD_NT, BWD_MINB><<<h->grid_b, BWD_NT, sizeof(BwdSmem<M, BWD_NT>), st>>>(a);
     CUDA_TRY(cudaGetLastError());
     return SSDE_OK;
 }
@@ -740,12 +763,12 @@ int launch_reduce(ssde_handle* h, int order, bool tan, cudaStream_t st) {
     return SSDE_OK;
 }
 
-template <int ND, class R>
+template <class M>
 int launch_ctcrw(ssde_handle* h, const double* d_par, const double* d_dir, int order, cudaStream_t st, double* aest) {
     int rc;
-    if ((rc = launch_ctcrw_fwd<ND, R>(h, d_par, d_dir, st, aest, false))) return rc;
-    if (order >= 1 && (rc = launch_ctcrw_bwd<ND, R>(h, d_par, d_dir, st, false))) return rc;
-    return launch_reduce(h, order, !std::is_same<R, double>::value, st);
+    if ((rc = launch_ctcrw_fwd<M>(h, d_par, d_dir, st, aest, false))) return rc;
+    if (order >= 1 && (rc = launch_ctcrw_bwd<M>(h, d_par, d_dir, st, false))) return rc;
+    return launch_reduce(h, order, !std::is_same<typename M::R, double>::value, st);
 }
 
 template <int MODEL, int ND, class R>
@@ -788,7 +811,7 @@ int eval_prologue(ssde_handle* h, const double* d_par, const double* d_dir, int 
 int eval_epilogue(ssde_handle* h, const double* d_par, const double* d_dir, int order, double* d_out, double* d_hv, cudaStream_t st) {
     std::string& err = h->err;
     FinArgs f{};
-    if (h->model == SSDE_CTCRW) {
+    if (is_kalman(h->model)) {
         f.part_llk = h->part.as<double>(); f.n_part = RED_BLOCKS;
         f.tile_gh = (order >= 1) ? h->part.as<double>() + RED_BLOCKS : nullptr; f.n_gh = RED_BLOCKS;
         f.tile_gh_dot = h->part.as<double>() + 2 * RED_BLOCKS;
@@ -804,7 +827,7 @@ int eval_epilogue(ssde_handle* h, const double* d_par, const double* d_dir, int 
     f.o_sig = h->o_sig; f.o_fe = h->o_fe; f.o_ll = h->o_ll; f.o_re = h->o_re;
     f.penalty = 0;
     if (h->has_smooth && h->add_penalty) {
-        if (h->model == SSDE_CTCRW) f.penalty = 1;                       // ignores include_penalty
+        if (is_kalman(h->model)) f.penalty = 1;                          // ignores include_penalty
         else if (h->include_penalty) f.penalty = 2;
     }
     f.pen_const = h->pen_const;
@@ -822,8 +845,8 @@ int eval_epilogue(ssde_handle* h, const double* d_par, const double* d_dir, int 
 
 template <class R>
 int launch_model(ssde_handle* h, const double* d_par, const double* d_dir, int order, cudaStream_t st, double* aest) {
-    if (h->model == SSDE_CTCRW)
-        return (h->n_dim == 1) ? launch_ctcrw<1, R>(h, d_par, d_dir, order, st, aest) : launch_ctcrw<2, R>(h, d_par, d_dir, order, st, aest);
+    if (is_kalman(h->model))
+        return with_kalman_model<R>(h, [&](auto m) -> int { return launch_ctcrw<decltype(m)>(h, d_par, d_dir, order, st, aest); });
     if (h->model == SSDE_BM) {
         if (h->n_dim == 1) return launch_sde<MODEL_BM, 1, R>(h, order, st);
         if (h->n_dim == 2) return launch_sde<MODEL_BM, 2, R>(h, order, st);
@@ -849,12 +872,12 @@ int run_eval(ssde_handle* h, const double* d_par, int order, double* d_out, cuda
 }
 
 // ---- tangent pass -------------------------------------------------------------------------------
-template <int ND>
+template <class M>
 int ctcrw_tan_grids(ssde_handle* h) {
     std::string& err = h->err;
     int rc;
-    if ((rc = max_grid(ctcrw_fwd_kernel<ND, FWD_NT, TAN_MINB, Dual>, FWD_NT, sizeof(FwdSmem<ND, FWD_NT, Dual>), h->num_sms, err, h->grid_f2))) return rc;
-    if ((rc = max_grid(ctcrw_bwd_kernel<ND, BWD_NT, TAN_MINB, Dual>, BWD_NT, sizeof(BwdSmem<ND, BWD_NT, Dual>), h->num_sms, err, h->grid_b2))) return rc;
+    if ((rc = max_grid(ctcrw_fwd_kernel<M, FWD_NT, TAN_MINB>, FWD_NT, sizeof(FwdSmem<M, FWD_NT>), h->num_sms, err, h->grid_f2))) return rc;
+    if ((rc = max_grid(ctcrw_bwd_kernel<M, BWD_NT, TAN_MINB>, BWD_NT, sizeof(BwdSmem<M, BWD_NT>), h->num_sms, err, h->grid_b2))) return rc;
     return SSDE_OK;
 }
 template <int MODEL, int ND>
@@ -877,19 +900,20 @@ int tangent_setup(ssde_handle* h) {
     if ((rc = dev_alloc<double>(h->t_theta_dot, p, err))) return rc;
     if ((rc = dev_alloc<double>(h->t_grad_theta, 2 * (size_t)p, err))) return rc;
     if ((rc = dev_alloc<double>(h->t_out, 2 * (size_t)h->npar + 2, err))) return rc;
-    if (h->model == SSDE_CTCRW) {
-        const int nd = h->n_dim;
-        if ((rc = dev_alloc<double>(h->t_ckpt, 2 * (size_t)h->nchunks * (2 * nd + 3), err))) return rc;
-        if ((rc = dev_alloc<double>(h->t_wg, 2 * (size_t)h->n_pad * 3, err))) return rc;
-        if ((rc = dev_alloc<double>(h->t_tile_gh, 2 * (size_t)(h->n_pad / WT), err))) return rc;
-        const size_t fe = (nd == 1) ? FwdElem<1, Dual>::NDBL : FwdElem<2, Dual>::NDBL;
-        const size_t be = (nd == 1) ? BwdElem<1, Dual>::NDBL : BwdElem<2, Dual>::NDBL;
-        if ((rc = dev_alloc<double>(h->t_f_agg, (size_t)h->ntiles_f * fe, err))) return rc;
-        if ((rc = dev_alloc<double>(h->t_f_incl, (size_t)h->ntiles_f * fe, err))) return rc;
-        if ((rc = dev_alloc<double>(h->t_b_agg, (size_t)h->ntiles_b * be, err))) return rc;
-        if ((rc = dev_alloc<double>(h->t_b_incl, (size_t)h->ntiles_b * be, err))) return rc;
-        rc = (nd == 1) ? ctcrw_tan_grids<1>(h) : ctcrw_tan_grids<2>(h);
+    if (is_kalman(h->model)) {
+        rc = with_kalman_model<Dual>(h, [&](auto m) -> int {
+            using M = decltype(m);
+            int rc;
+            if ((rc = dev_alloc<double>(h->t_ckpt, 2 * (size_t)h->nchunks * M::FS, err))) return rc;
+            if ((rc = dev_alloc<double>(h->t_wg, 2 * (size_t)h->n_pad * M::NW, err))) return rc;
+            if ((rc = dev_alloc<double>(h->t_f_agg, (size_t)h->ntiles_f * M::FwdElem::NDBL, err))) return rc;
+            if ((rc = dev_alloc<double>(h->t_f_incl, (size_t)h->ntiles_f * M::FwdElem::NDBL, err))) return rc;
+            if ((rc = dev_alloc<double>(h->t_b_agg, (size_t)h->ntiles_b * M::BwdElem::NDBL, err))) return rc;
+            if ((rc = dev_alloc<double>(h->t_b_incl, (size_t)h->ntiles_b * M::BwdElem::NDBL, err))) return rc;
+            return ctcrw_tan_grids<M>(h);
+        });
         if (rc) return rc;
+        if ((rc = dev_alloc<double>(h->t_tile_gh, 2 * (size_t)(h->n_pad / WT), err))) return rc;
         h->grid_f2 = std::min(h->grid_f2, std::max(h->ntiles_f, 1));
         h->grid_b2 = std::min(h->grid_b2, std::max(h->ntiles_b, 1));
     } else {
@@ -920,10 +944,10 @@ int run_hvp(ssde_handle* h, const double* d_par, const double* d_dir, double* d_
 }
 
 int check_common(int model, int n_dim, std::string& err) {
-    if (model < 0 || model > 2) { err = "Unknown SDE type"; return SSDE_ERR_UNKNOWN_TYPE; }
-    const int n_par = (model == SSDE_BM) ? n_dim + 1 : n_dim + 2;
-    if (n_dim < 1 || n_par > 4 || (model == SSDE_CTCRW && n_dim > 2)) {
-        err = "n_dim not supported for this model (n_par <= 4; CTCRW n_dim <= 2)";
+    if (model < 0 || model > 4) { err = "Unknown SDE type"; return SSDE_ERR_UNKNOWN_TYPE; }
+    const int n_par = sde_par_count(model, n_dim);
+    if (n_dim < 1 || n_par > 4) {
+        err = "n_dim not supported for this model (n_par <= 4: BM, BM_SSM n_dim <= 3; OU, OU_SSM, CTCRW n_dim <= 2)";
         return SSDE_ERR_UNSUPPORTED;
     }
     return SSDE_OK;
@@ -987,7 +1011,7 @@ int ssde_pack_host(const ssde_desc* d, ssde_host_pack* out) {
     std::memset(out, 0, sizeof(*out));
     int rc = check_common(d->model, d->n_dim, err);
     if (rc) return rc;
-    const int n_par = (d->model == SSDE_BM) ? d->n_dim + 1 : d->n_dim + 2;
+    const int n_par = sde_par_count(d->model, d->n_dim);
     if (d->n < 1 || d->X_fe.nrow != n_par * d->n || d->X_re.nrow != n_par * d->n) { err = "X_fe / X_re must have n_par * n rows"; return SSDE_ERR_BAD_ARG; }
     Packed pk;
     if ((rc = pack_design(*d, n_par, pk, err))) return rc;
@@ -1020,13 +1044,13 @@ int ssde_create(const ssde_desc* d, ssde_handle** out) {
     int rc = check_common(d->model, d->n_dim, err);
     if (rc) return rc;
     const int nd = d->n_dim;
-    const int n_par = (d->model == SSDE_BM) ? nd + 1 : nd + 2;
+    const int n_par = sde_par_count(d->model, nd);
     const int64_t n = d->n;
     if (n < 1 || !d->ID || !d->times || !d->obs) { err = "ID, times and obs are required"; return SSDE_ERR_BAD_ARG; }
     if (d->X_fe.nrow != n_par * n || d->X_re.nrow != n_par * n) { err = "X_fe / X_re must have n_par * n rows"; return SSDE_ERR_BAD_ARG; }
     if (d->H_array && d->H_len > 1) { err = "user-supplied H_array (coupled filter) is not built yet"; return SSDE_ERR_UNSUPPORTED; }
-    if (d->model != SSDE_CTCRW && (d->shard_flags & (SSDE_SHARD_CONT_PREV | SSDE_SHARD_CONT_NEXT))) {
-        err = "BM / OU shards must hold whole tracks (time-sharding exists for CTCRW only)";
+    if (!is_kalman(d->model) && (d->shard_flags & (SSDE_SHARD_CONT_PREV | SSDE_SHARD_CONT_NEXT))) {
+        err = "BM / OU shards must hold whole tracks (time-sharding exists for the Kalman models only)";
         return SSDE_ERR_UNSUPPORTED;
     }
     if (cudaSetDevice(d->device) != cudaSuccess) { err = "cudaSetDevice failed: no usable CUDA device (there is no CPU fallback)"; return SSDE_ERR_CUDA; }
@@ -1055,31 +1079,43 @@ int ssde_create(const ssde_desc* d, ssde_handle** out) {
             if (std::isnan(y)) f |= (uint8_t)(ROW_NA0 << k);
             else obs[(size_t)k * n_pad + pos] = y;
         }
-        if (d->model == SSDE_CTCRW) {
+        if (is_kalman(d->model)) {
             f &= (uint8_t)0x07;                                    // NA bits unused
-            if (!std::isnan(d->obs[i])) f |= ROW_OBS;              // column 0 only, nllk_ctcrw.hpp:214
+            if (!std::isnan(d->obs[i])) f |= ROW_OBS;              // column 0 only, nllk_ctcrw.hpp:214, nllk_ou_ssm.hpp:182
         }
         flags[pos] = f;
         if (!last) dt[pos] = ((i == n - 1) ? d->t_next : d->times[i + 1]) - d->times[i];
-        // CTCRW never uses the dt of a track-start row: it carries the track index instead
-        if (start && d->model == SSDE_CTCRW) dt[pos] = (double)starts.size();
+        // the Kalman models never use the dt of a track-start row: it carries the track index instead
+        if (start && is_kalman(d->model)) dt[pos] = (double)starts.size();
         if (start) starts.push_back(i);
     }
-    if (d->model == SSDE_CTCRW) {
-        if (!d->a0 || !d->P0) { err = "CTCRW needs a0 and P0"; return fail(SSDE_ERR_BAD_ARG); }
+    if (is_kalman(d->model)) {
+        if (!d->a0 || !d->P0) { err = "the Kalman models need a0 and P0"; return fail(SSDE_ERR_BAD_ARG); }
         if (d->n_ID != (int)starts.size()) { err = "nrow(a0) != number of tracks starting on this shard"; return fail(SSDE_ERR_BAD_ARG); }
-        const int m = 2 * nd;
-        const double p11 = d->P0[0], p12 = d->P0[(size_t)1 * m + 0], p22 = d->P0[(size_t)1 * m + 1];
-        for (int r = 0; r < m; ++r)
-            for (int c = 0; c < m; ++c) {
-                double want = 0.0;
-                if (r / 2 == c / 2) want = (r % 2 == 0 && c % 2 == 0) ? p11 : ((r % 2 == 1 && c % 2 == 1) ? p22 : p12);
-                if (d->P0[(size_t)c * m + r] != want) {
-                    err = "P0 must be block-diagonal with identical 2x2 blocks (coupled filter not built yet)";
-                    return fail(SSDE_ERR_UNSUPPORTED);
+        const int m = state_means(d->model, nd);
+        if (d->model == SSDE_CTCRW) {
+            const double p11 = d->P0[0], p12 = d->P0[(size_t)1 * m + 0], p22 = d->P0[(size_t)1 * m + 1];
+            for (int r = 0; r < m; ++r)
+                for (int c = 0; c < m; ++c) {
+                    double want = 0.0;
+                    if (r / 2 == c / 2) want = (r % 2 == 0 && c % 2 == 0) ? p11 : ((r % 2 == 1 && c % 2 == 1) ? p22 : p12);
+                    if (d->P0[(size_t)c * m + r] != want) {
+                        err = "P0 must be block-diagonal with identical 2x2 blocks (coupled filter not built yet)";
+                        return fail(SSDE_ERR_UNSUPPORTED);
+                    }
                 }
-            }
-        h->P0 = {p11, p12, p22};
+            h->P0 = {p11, p12, p22};
+        } else {
+            // BM_SSM / OU_SSM: P0 = c I (default diag(rep(10, n_dim)), R/sde.R:553)
+            const double c0 = d->P0[0];
+            for (int r = 0; r < m; ++r)
+                for (int c = 0; c < m; ++c)
+                    if (d->P0[(size_t)c * m + r] != (r == c ? c0 : 0.0)) {
+                        err = "P0 must be a multiple of the identity (coupled filter not built yet)";
+                        return fail(SSDE_ERR_UNSUPPORTED);
+                    }
+            h->P0 = {c0, 0.0, c0};
+        }
         std::vector<double> a0((size_t)starts.size() * m);
         for (size_t k = 0; k < starts.size(); ++k)
             for (int c = 0; c < m; ++c) a0[k * m + c] = d->a0[(size_t)c * starts.size() + k];
@@ -1089,7 +1125,7 @@ int ssde_create(const ssde_desc* d, ssde_handle** out) {
     Packed pk;
     if ((rc = pack_design(*d, n_par, pk, h->err))) return fail(rc);
     h->nnz = (int64_t)pk.col.size();
-    if (d->model == SSDE_CTCRW) {
+    if (is_kalman(d->model)) {
         std::vector<int32_t> mc;
         for (int64_t r = 0; r < n; ++r) {
             uint32_t rp = pk.rowptr[r];
@@ -1127,7 +1163,7 @@ int ssde_create_packed(const ssde_packed_desc* d, ssde_handle** out) {
     *out = nullptr;
     int rc = check_common(d->model, d->n_dim, err);
     if (rc) return rc;
-    const int n_par = (d->model == SSDE_BM) ? d->n_dim + 1 : d->n_dim + 2;
+    const int n_par = sde_par_count(d->model, d->n_dim);
     if (d->n_par != n_par) { err = "n_par does not match model / n_dim"; return SSDE_ERR_BAD_ARG; }
     if (d->n < 1 || d->n_pad != ssde_padded_rows(d->n)) { err = "n_pad must be ssde_padded_rows(n)"; return SSDE_ERR_BAD_ARG; }
     if (!d->d_desc || !d->d_val || !d->d_col || !d->d_obs || !d->d_dt || !d->d_flags) { err = "null device array"; return SSDE_ERR_BAD_ARG; }
@@ -1149,9 +1185,9 @@ int ssde_create_packed(const ssde_packed_desc* d, ssde_handle** out) {
     }
     std::vector<int64_t> starts(d->track_starts, d->track_starts + d->n_ID);
     if ((rc = dev_upload(h->track_starts, starts, h->err))) return fail(rc);
-    if (d->model == SSDE_CTCRW) {
-        if (!d->a0) { err = "CTCRW needs a0"; return fail(SSDE_ERR_BAD_ARG); }
-        std::vector<double> a0(d->a0, d->a0 + (size_t)d->n_ID * 2 * d->n_dim);
+    if (is_kalman(d->model)) {
+        if (!d->a0) { err = "the Kalman models need a0"; return fail(SSDE_ERR_BAD_ARG); }
+        std::vector<double> a0(d->a0, d->a0 + (size_t)d->n_ID * state_means(d->model, d->n_dim));
         if ((rc = dev_upload(h->a0, a0, h->err))) return fail(rc);
     }
     if ((rc = setup_penalty(h, d->S, d->n_smooth, d->ncol_re, h->err))) return fail(rc);
@@ -1174,19 +1210,17 @@ int ssde_eval_device(ssde_handle* h, const double* d_par, int order, double* d_o
 }
 
 int ssde_shard_elem_doubles(const ssde_handle* h, int which) {
-    if (!h || h->model != SSDE_CTCRW) return -1;
-    if (which == 0) return h->n_dim == 1 ? FwdElem<1>::NDBL : FwdElem<2>::NDBL;
-    return h->n_dim == 1 ? BwdElem<1>::NDBL : BwdElem<2>::NDBL;
+    if (!h || !is_kalman(h->model)) return -1;
+    return which == 0 ? h->fwd_elem : h->bwd_elem;
 }
 
 int ssde_eval_stage(ssde_handle* h, const double* d_par, int stage, const double* d_elems, int n_shards,
                     int my_shard, double* d_out, void* stream) {
     if (!h || !d_par) return SSDE_ERR_BAD_ARG;
     std::string& err = h->err;
-    if (h->model != SSDE_CTCRW) { err = "time-sharded evaluation exists for CTCRW only"; return SSDE_ERR_UNSUPPORTED; }
+    if (!is_kalman(h->model)) { err = "time-sharded evaluation exists for the Kalman models only"; return SSDE_ERR_UNSUPPORTED; }
     CUDA_TRY(cudaSetDevice(h->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
-    const int nd = h->n_dim;
     const size_t fe = (size_t)ssde_shard_elem_doubles(h, 0), be = (size_t)ssde_shard_elem_doubles(h, 1);
     int rc = SSDE_OK;
     if (stage == 0) {
@@ -1195,31 +1229,35 @@ int ssde_eval_stage(ssde_handle* h, const double* d_par, int stage, const double
         h->last_launches = 0; h->pcount = 0;
         h->have_s_in = h->have_g_in = false;
         if ((rc = eval_prologue(h, d_par, nullptr, 1, st))) return rc;
-        rc = (nd == 1) ? launch_ctcrw_fwd<1, double>(h, d_par, nullptr, st, nullptr, true) : launch_ctcrw_fwd<2, double>(h, d_par, nullptr, st, nullptr, true);
+        rc = with_kalman_model<double>(h, [&](auto m) -> int { return launch_ctcrw_fwd<decltype(m)>(h, d_par, nullptr, st, nullptr, true); });
         if (rc) return rc;
         CUDA_TRY(cudaMemcpyAsync(d_out, h->f_incl.as<double>() + (size_t)(h->ntiles_f - 1) * fe, fe * sizeof(double),
                                  cudaMemcpyDeviceToDevice, st));
     } else if (stage == 1) {
         // gathered forward elements -> incoming state; forward pass; adjoint summary -> d_out[be]
         if (!d_elems || !d_out || my_shard < 0 || my_shard >= n_shards) return SSDE_ERR_BAD_ARG;
-        if (nd == 1) shard_state_kernel<1><<<1, 32, 0, st>>>(d_elems, n_shards, my_shard, h->P0, h->s_in.as<double>());
-        else shard_state_kernel<2><<<1, 32, 0, st>>>(d_elems, n_shards, my_shard, h->P0, h->s_in.as<double>());
-        ++h->last_launches;
-        h->have_s_in = true;
-        rc = (nd == 1) ? launch_ctcrw_fwd<1, double>(h, d_par, nullptr, st, nullptr, false) : launch_ctcrw_fwd<2, double>(h, d_par, nullptr, st, nullptr, false);
-        if (rc) return rc;
-        rc = (nd == 1) ? launch_ctcrw_bwd<1, double>(h, d_par, nullptr, st, true) : launch_ctcrw_bwd<2, double>(h, d_par, nullptr, st, true);
+        rc = with_kalman_model<double>(h, [&](auto m) -> int {
+            using M = decltype(m);
+            shard_state_kernel<M><<<1, 32, 0, st>>>(d_elems, n_shards, my_shard, h->P0, h->s_in.as<double>());
+            ++h->last_launches;
+            h->have_s_in = true;
+            int rc = launch_ctcrw_fwd<M>(h, d_par, nullptr, st, nullptr, false);
+            if (rc) return rc;
+            return launch_ctcrw_bwd<M>(h, d_par, nullptr, st, true);
+        });
         if (rc) return rc;
         CUDA_TRY(cudaMemcpyAsync(d_out, h->b_incl.as<double>() + (size_t)(h->ntiles_b - 1) * be, be * sizeof(double),
                                  cudaMemcpyDeviceToDevice, st));
     } else if (stage == 2) {
         // gathered adjoint elements -> incoming adjoint; adjoint pass; finalize -> d_out[1 + n_par + 1]
         if (!d_elems || !d_out || my_shard < 0 || my_shard >= n_shards) return SSDE_ERR_BAD_ARG;
-        if (nd == 1) shard_adjoint_kernel<1><<<1, 32, 0, st>>>(d_elems, n_shards, my_shard, h->g_in.as<double>());
-        else shard_adjoint_kernel<2><<<1, 32, 0, st>>>(d_elems, n_shards, my_shard, h->g_in.as<double>());
-        ++h->last_launches;
-        h->have_g_in = true;
-        rc = (nd == 1) ? launch_ctcrw_bwd<1, double>(h, d_par, nullptr, st, false) : launch_ctcrw_bwd<2, double>(h, d_par, nullptr, st, false);
+        rc = with_kalman_model<double>(h, [&](auto m) -> int {
+            using M = decltype(m);
+            shard_adjoint_kernel<M><<<1, 32, 0, st>>>(d_elems, n_shards, my_shard, h->g_in.as<double>());
+            ++h->last_launches;
+            h->have_g_in = true;
+            return launch_ctcrw_bwd<M>(h, d_par, nullptr, st, false);
+        });
         if (rc) return rc;
         if ((rc = launch_reduce(h, 1, false, st))) return rc;
         if ((rc = eval_epilogue(h, d_par, nullptr, 1, d_out, nullptr, st))) return rc;
@@ -1355,9 +1393,9 @@ int ssde_eval(ssde_handle* h, const double* par, int order, double* nllk, double
 int ssde_report(ssde_handle* h, double* aest_all) {
     if (!h || !aest_all) return SSDE_ERR_BAD_ARG;
     std::string& err = h->err;
-    if (h->model != SSDE_CTCRW) { err = "REPORT(aest_all) exists for CTCRW only"; return SSDE_ERR_UNSUPPORTED; }
+    if (!is_kalman(h->model)) { err = "REPORT(aest_all) exists for the Kalman models only"; return SSDE_ERR_UNSUPPORTED; }
     CUDA_TRY(cudaSetDevice(h->device));
-    const int m = 2 * h->n_dim;
+    const int m = state_means(h->model, h->n_dim);
     if (!h->aest.p) { int rc = dev_alloc<double>(h->aest, (size_t)h->n_pad * m, err); if (rc) return rc; }
     int rc = run_eval(h, h->par.as<double>(), 0, h->out.as<double>(), h->stream, h->aest.as<double>());
     if (rc) return rc;

@@ -67,8 +67,8 @@ def make_desc(dat, device=0, shard_flags=0, t_next=0.0):
     d.n_smooth = ncol_re.size
     d.ncol_re = ncol_re.ctypes.data_as(L.c_int32_p)
     d.include_penalty = int(dat.get("include_penalty", 1))
-    if dat["type"] == "CTCRW":
-        a0 = np.asfortranarray(np.asarray(dat["a0"], dtype=np.float64).reshape(-1, 2 * nd))
+    if dat["type"] in L.KALMAN_TYPES:
+        a0 = np.asfortranarray(np.asarray(dat["a0"], dtype=np.float64).reshape(-1, 2 * nd if dat["type"] == "CTCRW" else nd))
         P0 = np.asfortranarray(np.asarray(dat["P0"], dtype=np.float64))
         keep += [a0, P0]
         d.n_ID = a0.shape[0]
@@ -212,9 +212,10 @@ class Engine:
     def check(self):
         self._check(self._lib.ssde_check(self._h))
 
-    def report(self, n, n_dim):
-        """REPORT(aest_all) at the parameters of the last eval()."""
-        out = np.zeros((n, 2 * n_dim), order="F")
+    def report(self, n, n_dim, state_dim=None):
+        """REPORT(aest_all) at the parameters of the last eval(); state_dim = columns of aest_all
+        (2 n_dim for CTCRW, the default; n_dim for BM_SSM / OU_SSM)."""
+        out = np.zeros((n, state_dim or 2 * n_dim), order="F")
         self._check(self._lib.ssde_report(self._h, out.ctypes.data_as(L.c_double_p)))
         return np.ascontiguousarray(out)
 

@@ -23,8 +23,10 @@ _LINKS = {
     "BM": lambda d: [("mu", None)] * d + [("sigma", "log")],
     "OU": lambda d: [("mu", None)] * d + [("tau", "log"), ("kappa", "log")],
     "CTCRW": lambda d: [("mu", None)] * d + [("tau", "log"), ("nu", "log")],
+    "BM_SSM": lambda d: [("mu", None)] * d + [("sigma", "log")],                       # R/sde.R:60-63
+    "OU_SSM": lambda d: [("mu", None)] * d + [("tau", "log"), ("kappa", "log")],       # R/sde.R:68-71
 }
-_KNOWN_UNBUILT = ("BM_t", "CIR", "BM_SSM", "OU_SSM", "ESEAL_SSM")
+_KNOWN_UNBUILT = ("BM_t", "CIR", "ESEAL_SSM")
 
 
 def _par_names(type_, n_dim):
@@ -150,6 +152,16 @@ class SDE:
         tmb_dat = {"type": self._type, "ID": (codes + 1).astype(float), "times": np.asarray(self._data["time"], float),
                    "obs": self.obs(), "X_fe": m.X_fe, "X_re": X_re, "S": S, "ncol_re": ncol_re,
                    "include_penalty": 1}
+        if self._type in ("BM_SSM", "OU_SSM"):                                  # R/sde.R:542-568
+            ID = tmb_dat["ID"]
+            i0 = np.r_[0, np.nonzero(ID[:-1] != ID[1:])[0] + 1]
+            tmb_dat["a0"] = tmb_dat["obs"][i0].copy()                           # first observation of each track
+            P0 = self._other_data.get("P0")
+            tmb_dat["P0"] = 10.0 * np.eye(len(self._response)) if P0 is None else np.asarray(P0, float)
+            tmb_par = OrderedDict([("log_sigma_obs", np.zeros(1))] + list(tmb_par.items()))
+            if self._other_data.get("H") is not None:
+                tmb_dat["H_array"] = np.asarray(self._other_data["H"], float)
+                map["log_sigma_obs"] = [None]
         if self._type == "CTCRW":                                               # R/sde.R:569-598
             n_dim = len(self._response)
             ID = tmb_dat["ID"]

@@ -32,7 +32,7 @@ from . import _lib as L
 def n_sde_par(dat):
     obs = np.asarray(dat["obs"])
     nd = 1 if obs.ndim == 1 else obs.shape[1]
-    return nd + 1 if dat["type"] == "BM" else nd + 2
+    return nd + 1 if dat["type"] in ("BM", "BM_SSM") else nd + 2
 
 
 def track_bounds(ID):
@@ -79,7 +79,7 @@ def shard_rows(dat, lo, hi):
         sub[nm] = sp.vstack([X[j * n + lo:j * n + hi] for j in range(n_par)], format="csr")
     cont_prev = lo > 0 and ID[lo - 1] == ID[lo]
     cont_next = hi < n and ID[hi] == ID[hi - 1]
-    if dat["type"] == "CTCRW":
+    if dat["type"] in L.KALMAN_TYPES:
         b = track_bounds(ID)[:-1]
         a0 = np.asarray(dat["a0"], dtype=float).reshape(b.size, -1)
         sub["a0"] = a0[(b >= lo) & (b < hi)]
@@ -261,8 +261,8 @@ class TimeShardedEngine:
 
     def __init__(self, dat, comm=None, device=0, devices=None, engine_factory=None):
         import torch
-        if dat["type"] != "CTCRW":
-            raise L.EngineError(3, "time sharding exists for CTCRW only")
+        if dat["type"] not in L.KALMAN_TYPES:
+            raise L.EngineError(3, "time sharding exists for the Kalman models only")
         if track_bounds(dat["ID"]).size != 2:
             raise ValueError("TimeShardedEngine takes ONE track; use TrackShardedEngine for many")
         n = np.asarray(dat["ID"]).size

@@ -26,17 +26,23 @@ def make_problem(model, n_tracks, n_steps, seed=20260101, irregular=None, missin
                  k=10, re_id=None, sigma_obs=0.1, n_dim=None):
     """Build one synthetic problem.
 
-    model: "BM" | "OU" | "CTCRW".  Formulas follow SURVEY.md 8(d):
+    model: "BM" | "OU" | "CTCRW" | "BM_SSM" | "OU_SSM" (the last two: BM / OU paths observed with
+    measurement error sigma_obs; a0 = first observation, P0 = diag(10), R/sde.R:547-557).
+    Formulas follow SURVEY.md 8(d):
       BM     mu, sigma ~ s(time, k)                          (C1)
       OU     mu, tau ~ s(time, k) [+ s(ID, bs="re")], kappa ~ 1   (C2)
       CTCRW  mu1 = mu2 = 0 fixed, tau, nu ~ s(time, k)       (C3/C4)
     Returns (dat, par, info).
     """
     rng = np.random.default_rng(seed)
+    ssm = model in ("BM_SSM", "OU_SSM")
+    out_type = model
+    if ssm:
+        model = model[:2]
     if irregular is None:
-        irregular = model == "CTCRW"
+        irregular = model == "CTCRW" or ssm
     if re_id is None:
-        re_id = model == "OU" and n_tracks > 1
+        re_id = model == "OU" and n_tracks > 1 and not ssm
     if n_dim is None:
         n_dim = 2 if model == "CTCRW" else 1
     T, m = n_tracks, n_steps
@@ -74,6 +80,8 @@ def make_problem(model, n_tracks, n_steps, seed=20260101, irregular=None, missin
         beta0 = [0.0] * n_dim + [0.0, 0.0]
     else:
         raise ValueError("Unknown SDE type")
+    if ssm:
+        z = z + sigma_obs * rng.standard_normal(z.shape)
     obs = z.reshape(n, n_dim).copy()
     if missing_frac > 0:
         miss = rng.random(n) < missing_frac
@@ -82,7 +90,7 @@ def make_problem(model, n_tracks, n_steps, seed=20260101, irregular=None, missin
 
     des = _design.make_design(formulas, data, n)
     dat = {
-        "type": model, "ID": ID.astype(float), "times": tflat, "obs": obs,
+        "type": out_type, "ID": ID.astype(float), "times": tflat, "obs": obs,
         "X_fe": des.X_fe, "X_re": des.X_re, "S": des.S, "ncol_re": des.ncol_re,
         "include_penalty": 1,
     }
@@ -93,6 +101,9 @@ def make_problem(model, n_tracks, n_steps, seed=20260101, irregular=None, missin
             a0[:, 2 * d] = obs[i0, d]
         dat["a0"] = a0
         dat["P0"] = np.diag(np.tile([1.0, 10.0], n_dim))
+    if ssm:
+        dat["a0"] = obs[np.arange(0, n, m)].copy()
+        dat["P0"] = 10.0 * np.eye(n_dim)
 
     # parameter vector for parity checks: beta at the link of the true means, b ~ N(0, 0.1^2),
     # log lambda = 0, log sigma_obs = log 0.1 (seed + 1)
@@ -102,7 +113,7 @@ def make_problem(model, n_tracks, n_steps, seed=20260101, irregular=None, missin
     assert coeff_fe.size == p_fe, (coeff_fe.size, p_fe)
     coeff_re = 0.1 * prng.standard_normal(p_re)
     log_lambda = np.zeros(des.ncol_re.size)
-    pieces = ([np.array([np.log(sigma_obs)])] if model == "CTCRW" else []) + \
+    pieces = ([np.array([np.log(sigma_obs)])] if (model == "CTCRW" or ssm) else []) + \
         [coeff_fe, log_lambda, coeff_re]
     par = np.concatenate(pieces)
     info = {"design": des, "formulas": formulas, "n": n, "n_dim": n_dim, "n_tracks": T,

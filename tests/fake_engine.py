@@ -57,7 +57,7 @@ class OracleEngine:
         v, g = self.eval(par, 1)
         return v, g, self.co.hessian(np.asarray(par, dtype=float))
 
-    def report(self, n, n_dim):
+    def report(self, n, n_dim, state_dim=None):
         return self.co.aest(self._last)
 
     def close(self):

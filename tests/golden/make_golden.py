@@ -36,7 +36,10 @@ CASES = [
     ("bm_d2_3x50", "BM", 3, 50, 0.1, 2, 105, None),
     ("ou_d1_4x60", "OU", 4, 60, 0.1, 1, 106, None),
     ("ou_d2_2x80", "OU", 2, 80, 0.0, 2, 107, None),
+    ("ou_ssm_d2_2x50", "OU_SSM", 2, 50, 0.1, 2, 108, [0.3, -0.2]),
+    ("bm_ssm_d1_3x40", "BM_SSM", 3, 40, 0.1, 1, 109, [0.25]),
 ]
+ONLY = sys.argv[1:]          # optional: names of the fixtures to (re)generate
 
 
 def pack(dat, par, nllk, grad, extra):
@@ -48,7 +51,7 @@ def pack(dat, par, nllk, grad, extra):
         M = sp.coo_matrix(dat[nm])
         out[nm + "_i"], out[nm + "_j"], out[nm + "_x"] = M.row.astype(np.int32), M.col.astype(np.int32), M.data
         out[nm + "_shape"] = np.array(M.shape)
-    if dat["type"] == "CTCRW":
+    if dat["type"] in ("CTCRW", "OU_SSM", "BM_SSM"):
         out["a0"], out["P0"] = dat["a0"], dat["P0"]
     out.update(extra)
     return out
@@ -56,7 +59,10 @@ def pack(dat, par, nllk, grad, extra):
 
 def main():
     for name, model, T, m, miss, nd, seed, mu in CASES:
-        dat, par, info = synth.make_problem(model, T, m, missing_frac=miss, n_dim=nd, seed=seed)
+        if ONLY and name not in ONLY:
+            continue
+        dat, par, info = synth.make_problem(model, T, m, missing_frac=miss, n_dim=nd, seed=seed,
+                                            **({"k": 5} if model.endswith("_SSM") else {}))
         par = par.copy()
         if mu is not None:
             par[1:1 + nd] = mu
@@ -65,7 +71,7 @@ def main():
         # independent known answers
         ka = KA.known_answer(dat, par)
         assert abs(ka - v) <= 1e-12 * abs(v), (name, ka, v)
-        mp = KA.nllk_mpmath(dat, par) if info["n"] <= 200 else None
+        mp = KA.nllk_mpmath(dat, par) if (info["n"] <= 200 and not model.endswith("_SSM")) else None
         if mp is not None:
             assert abs(mp - v) <= 1e-12 * abs(v), (name, mp, v)
         extra = {"known_answer": np.array(ka)}
@@ -74,6 +80,13 @@ def main():
         if model == "CTCRW":
             p = O.split_par(dat, par)
             extra["aest_all"] = O.nllk_ctcrw(dat, **p, return_aest=True)[1]
+        if model.endswith("_SSM"):
+            p = O.split_par(dat, par)
+            extra["aest_all"] = O._nllk_ssm(dat, **p, model=model, return_aest=True)[1]
+            extra["hess"] = O.hess_complex_fd(dat, par)      # the C oracle does not cover these models
+            np.savez_compressed(os.path.join(HERE, name + ".npz"), **pack(dat, par, v, g, extra))
+            print(f"{name}: n={info['n']} npar={par.size} nllk={v:.15g} known={ka:.15g}")
+            continue
         # joint Hessian (obj$he): Richardson differences of the C oracle's analytic gradient; on the
         # smallest cases cross-checked against complex-step + differences of the numpy restatement
         Hc = oracle_c.COracle(dat).hessian(par)

@@ -18,7 +18,7 @@ def load(name):
            "ncol_re": z["ncol_re"], "include_penalty": int(z["include_penalty"])}
     for nm in ("X_fe", "X_re", "S"):
         dat[nm] = sp.csr_matrix((z[nm + "_x"], (z[nm + "_i"], z[nm + "_j"])), shape=tuple(z[nm + "_shape"]))
-    if dat["type"] == "CTCRW":
+    if dat["type"] in ("CTCRW", "OU_SSM", "BM_SSM"):
         dat["a0"], dat["P0"] = z["a0"], z["P0"]
     out = {"par": z["par"], "nllk": float(z["nllk"]), "grad": z["grad"],
            "known_answer": float(z["known_answer"])}

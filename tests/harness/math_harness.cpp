@@ -7,7 +7,7 @@
 #include <cstring>
 #include <vector>
 
-#include "../../smoothsde_b200/csrc/ctcrw_math.cuh"
+#include "../../smoothsde_b200/csrc/models.cuh"
 
 using namespace ssde;
 
@@ -17,24 +17,27 @@ template <class R> static R mk(double v, double d);
 template <> double mk<double>(double v, double) { return v; }
 template <> Dual mk<Dual>(double v, double d) { return Dual(v, d); }
 
-template <int ND, class R>
+template <class M>
 struct Row {
-    StepParT<R> sp;
-    double y[ND], dt;
-    R mu[ND], tau, e, s2;
+    typename M::Step sp;
+    typename M::RowPar rp;
+    double y[M::ND], dt;
+    typename M::R mu[M::ND];
     bool start, last, obs;
     int track;
 };
 
 // eta_dot: direction in linear-predictor space (same shape as eta), nullptr for R = double
-template <int ND, class R>
-static std::vector<Row<ND, R>> build_rows(int64_t n, const uint8_t* flags, const double* y,
-                                          const double* dt, const double* eta, const double* eta_dot) {
-    std::vector<Row<ND, R>> rows(n);
+template <class M>
+static std::vector<Row<M>> build_rows(int64_t n, const uint8_t* flags, const double* y,
+                                      const double* dt, const double* eta, const double* eta_dot) {
+    using R = typename M::R;
+    constexpr int ND = M::ND, NP = M::NP;
+    std::vector<Row<M>> rows(n);
     int track = -1;
     for (int64_t i = 0; i < n; ++i) {
-        Row<ND, R>& r = rows[i];
-        auto E = [&](int c) { return mk<R>(eta[i * (ND + 2) + c], eta_dot ? eta_dot[i * (ND + 2) + c] : 0.0); };
+        Row<M>& r = rows[i];
+        auto E = [&](int c) { return mk<R>(eta[i * NP + c], eta_dot ? eta_dot[i * NP + c] : 0.0); };
         r.start = flags[i] & FLAG_START;
         r.last = flags[i] & FLAG_LAST;
         r.obs = flags[i] & FLAG_OBS;
@@ -42,174 +45,197 @@ static std::vector<Row<ND, R>> build_rows(int64_t n, const uint8_t* flags, const
         r.track = track;
         for (int d = 0; d < ND; ++d) { r.y[d] = y[i * ND + d]; r.mu[d] = E(d); }
         r.dt = dt[i];
-        transform_row(E(ND), E(ND + 1), r.dt, r.tau, r.e, r.s2);
-        r.sp = make_step(r.tau, r.e, r.s2, r.dt);
+        R er[NP];
+        for (int c = 0; c < NP; ++c) er[c] = E(c);
+        r.rp = M::transform(er, r.dt);
+        r.sp = M::make_step(r.rp, r.dt);
     }
     return rows;
 }
 
-template <int ND, class R>
-static State<ND, R> start_state(const double* a0, const double* P0, int track) {
-    State<ND, R> s;
-    for (int d = 0; d < ND; ++d) s.a[d] = {a0[track * 2 * ND + 2 * d], a0[track * 2 * ND + 2 * d + 1]};
-    s.P = {P0[0], P0[1], P0[2]};
-    return s;
+template <class M>
+static typename M::State start_state(const double* a0, const double* P0, int track) {
+    return M::start_state(a0 + (size_t)track * M::SD, Sym2{P0[0], P0[1], P0[2]});
 }
 
 // mode 0: plain sequential filter + sequential adjoint.
 // mode 1: emulated chunked scan (lc rows per thread, nt threads per tile).
-template <int ND, class R>
+template <class M>
 static int run(int mode, int64_t n, const uint8_t* flags, const double* y, const double* dt,
-               const double* eta, const double* eta_dot, const double* a0, const double* P0, R h, int lc, int nt,
+               const double* eta, const double* eta_dot, const double* a0, const double* P0, typename M::R h, int lc, int nt,
                double* out_llk, double* eta_bar, double* eta_bar_dot, double* out_gh, double* aest) {
-    auto rows = build_rows<ND, R>(n, flags, y, dt, eta, eta_dot);
-    std::vector<State<ND, R>> pre(n);       // predicted state of each row (state BEFORE the row)
+    using R = typename M::R;
+    constexpr int ND = M::ND, NP = M::NP;
+    auto rows = build_rows<M>(n, flags, y, dt, eta, eta_dot);
+    auto step_llk = [&](typename M::State& s, const Row<M>& r, typename M::Aux* ax) -> R {
+        R F, quad;
+        if (ax) M::template fwd_step<true>(s, r.sp, r.y, r.mu, r.obs, h, ax, F, quad);
+        else M::template fwd_step<false>(s, r.sp, r.y, r.mu, r.obs, h, nullptr, F, quad);
+        return r.obs ? R(-0.5 * ((double)ND * log(F) + quad)) : R(0.0);
+    };
+    std::vector<typename M::State> pre(n);       // predicted state of each row (state BEFORE the row)
     R llk = 0.0;
     if (mode == 0) {
-        State<ND, R> s = start_state<ND, R>(a0, P0, 0);
+        typename M::State s = start_state<M>(a0, P0, 0);
         for (int64_t i = 0; i < n; ++i) {
             pre[i] = s;
-            if (rows[i].start) { s = start_state<ND, R>(a0, P0, rows[i].track); continue; }
-            llk += fwd_step<ND, false>(s, rows[i].sp, rows[i].y, rows[i].mu, rows[i].obs, h, nullptr);
+            if (rows[i].start) { s = start_state<M>(a0, P0, rows[i].track); continue; }
+            llk += step_llk(s, rows[i], nullptr);
         }
     } else {
         const int64_t chunk = lc, tile = (int64_t)lc * nt;
         const int64_t nchunks = (n + chunk - 1) / chunk;
-        std::vector<FwdElem<ND, R>> agg(nchunks);
+        std::vector<typename M::FwdElem> agg(nchunks);
         for (int64_t c = 0; c < nchunks; ++c) {
-            FwdElem<ND, R> E = fwd_identity<ND, R>();
+            typename M::FwdElem E = M::fwd_identity();
             for (int64_t i = c * chunk; i < (c + 1) * chunk && i < n; ++i) {
-                if (rows[i].start) fwd_append_start<ND>(E, start_state<ND, R>(a0, P0, rows[i].track));
-                else fwd_append<ND>(E, rows[i].sp, rows[i].y, rows[i].mu, rows[i].obs, h);
+                if (rows[i].start) M::fwd_append_start(E, start_state<M>(a0, P0, rows[i].track));
+                else M::fwd_append(E, rows[i].sp, rows[i].y, rows[i].mu, rows[i].obs, h);
             }
             agg[c] = E;
         }
         // tile-level: exclusive prefix of chunk aggregates inside a tile via fwd_combine, tile
         // prefixes chained across tiles (what the look-back computes)
-        FwdElem<ND, R> tile_prefix = fwd_identity<ND, R>();
-        State<ND, R> s_in = start_state<ND, R>(a0, P0, 0);   // irrelevant: row 0 is a start row
+        typename M::FwdElem tile_prefix = M::fwd_identity();
+        typename M::State s_in = start_state<M>(a0, P0, 0);   // irrelevant: row 0 is a start row
         for (int64_t t0 = 0; t0 < n; t0 += tile) {
-            FwdElem<ND, R> run_ = fwd_identity<ND, R>();
-            const State<ND, R> s_tile = fwd_apply<ND>(tile_prefix, s_in);
+            typename M::FwdElem run_ = M::fwd_identity();
+            const typename M::State s_tile = M::fwd_apply(tile_prefix, s_in);
             for (int64_t c = t0 / chunk; c < (t0 + tile) / chunk && c < nchunks; ++c) {
-                State<ND, R> s = fwd_apply<ND>(run_, s_tile);
+                typename M::State s = M::fwd_apply(run_, s_tile);
                 for (int64_t i = c * chunk; i < (c + 1) * chunk && i < n; ++i) {
                     pre[i] = s;
-                    if (rows[i].start) { s = start_state<ND, R>(a0, P0, rows[i].track); continue; }
-                    llk += fwd_step<ND, false>(s, rows[i].sp, rows[i].y, rows[i].mu, rows[i].obs, h,
-                                               nullptr);
+                    if (rows[i].start) { s = start_state<M>(a0, P0, rows[i].track); continue; }
+                    llk += step_llk(s, rows[i], nullptr);
                 }
-                run_ = fwd_combine<ND>(run_, agg[c]);
+                run_ = M::fwd_combine(run_, agg[c]);
             }
-            tile_prefix = fwd_combine<ND>(tile_prefix, run_);
+            tile_prefix = M::fwd_combine(tile_prefix, run_);
         }
     }
     out_llk[0] = value(llk); out_llk[1] = tangent(llk);
     if (aest) {
         // REPORT(aest_all): row i holds the state AFTER iteration i (nllk_ctcrw.hpp:246)
         for (int64_t i = 0; i < n; ++i) {
-            State<ND, R> s = pre[i];
-            if (rows[i].start) s = start_state<ND, R>(a0, P0, rows[i].track);
-            else fwd_step<ND, false>(s, rows[i].sp, rows[i].y, rows[i].mu, rows[i].obs, h, nullptr);
-            for (int d = 0; d < ND; ++d) { aest[i * 2 * ND + 2 * d] = value(s.a[d].x); aest[i * 2 * ND + 2 * d + 1] = value(s.a[d].y); }
+            typename M::State s = pre[i];
+            if (rows[i].start) s = start_state<M>(a0, P0, rows[i].track);
+            else step_llk(s, rows[i], nullptr);
+            M::store_mean(s, aest + i * M::SD);
         }
     }
     if (!eta_bar) return 0;
 
     // ---- adjoint ----
     R gh = 0.0;
-    std::memset(eta_bar, 0, sizeof(double) * n * (ND + 2));
-    if (eta_bar_dot) std::memset(eta_bar_dot, 0, sizeof(double) * n * (ND + 2));
+    std::memset(eta_bar, 0, sizeof(double) * n * NP);
+    if (eta_bar_dot) std::memset(eta_bar_dot, 0, sizeof(double) * n * NP);
     auto put = [&](int64_t i, int c, const R& g) {
-        eta_bar[i * (ND + 2) + c] = value(g);
-        if (eta_bar_dot) eta_bar_dot[i * (ND + 2) + c] = tangent(g);
+        eta_bar[i * NP + c] = value(g);
+        if (eta_bar_dot) eta_bar_dot[i * NP + c] = tangent(g);
     };
-    auto row_back = [&](int64_t i, Adj<ND, R>& g) {
-        const Row<ND, R>& r = rows[i];
-        if (r.start) { g = adj_zero<ND, R>(); return; }
-        State<ND, R> s = pre[i];
-        StepAux<ND, R> ax;
-        fwd_step<ND, true>(s, r.sp, r.y, r.mu, r.obs, h, &ax);
-        const Adj<ND, R> gin = r.last ? adj_zero<ND, R>() : g;
-        R gmu[ND], gt, gn, g_h;
-        row_param_grad<ND>(gin, r.sp, ax, r.mu, r.tau, r.e, r.s2, r.dt, r.obs, gmu, gt, gn, g_h);
-        for (int d = 0; d < ND; ++d) put(i, d, gmu[d]);
-        put(i, ND, gt);
-        put(i, ND + 1, gn);
+    auto row_back = [&](int64_t i, typename M::Adj& g) {
+        const Row<M>& r = rows[i];
+        if (r.start) { g = M::adj_zero(); return; }
+        typename M::State s = pre[i];
+        typename M::Aux ax;
+        step_llk(s, r, &ax);
+        const typename M::Adj gin = r.last ? M::adj_zero() : g;
+        R gp[NP], g_h;
+        for (int c = 0; c < NP; ++c) gp[c] = 0.0;
+        M::row_param_grad(gin, r.sp, ax, r.mu, r.rp, r.dt, r.obs, gp, g_h);
+        for (int c = 0; c < NP; ++c) put(i, c, gp[c]);
         gh += g_h;
-        g = bwd_apply<ND>(bwd_row_elem<ND>(r.sp, ax, r.obs, r.last), g);
+        g = M::bwd_apply(M::bwd_row_elem(r.sp, ax, r.obs, r.last), g);
     };
     if (mode == 0) {
-        Adj<ND, R> g = adj_zero<ND, R>();
+        typename M::Adj g = M::adj_zero();
         for (int64_t i = n - 1; i >= 0; --i) row_back(i, g);
     } else {
         const int64_t chunk = lc, tile = (int64_t)lc * nt;
         const int64_t nchunks = (n + chunk - 1) / chunk;
-        std::vector<BwdElem<ND, R>> agg(nchunks);
+        std::vector<typename M::BwdElem> agg(nchunks);
         for (int64_t c = 0; c < nchunks; ++c) {
-            BwdElem<ND, R> E = bwd_identity<ND, R>();
+            typename M::BwdElem E = M::bwd_identity();
             for (int64_t i = c * chunk; i < (c + 1) * chunk && i < n; ++i) {
-                const Row<ND, R>& r = rows[i];
-                BwdElem<ND, R> el;
-                if (r.start) el = bwd_const<ND>(adj_zero<ND, R>());
+                const Row<M>& r = rows[i];
+                typename M::BwdElem el;
+                if (r.start) el = M::bwd_const(M::adj_zero());
                 else {
-                    State<ND, R> s = pre[i];
-                    StepAux<ND, R> ax;
-                    fwd_step<ND, true>(s, r.sp, r.y, r.mu, r.obs, h, &ax);
-                    el = bwd_row_elem<ND>(r.sp, ax, r.obs, r.last);
+                    typename M::State s = pre[i];
+                    typename M::Aux ax;
+                    step_llk(s, r, &ax);
+                    el = M::bwd_row_elem(r.sp, ax, r.obs, r.last);
                 }
-                E = bwd_combine<ND>(E, el);
+                E = M::bwd_combine(E, el);
             }
             agg[c] = E;
         }
-        BwdElem<ND, R> suffix = bwd_identity<ND, R>();    // composite of all rows after the current tile
-        const Adj<ND, R> g_end = adj_zero<ND, R>();
+        typename M::BwdElem suffix = M::bwd_identity();    // composite of all rows after the current tile
+        const typename M::Adj g_end = M::adj_zero();
         const int64_t ntiles = (n + tile - 1) / tile;
         for (int64_t t = ntiles - 1; t >= 0; --t) {
             const int64_t t0 = t * tile;
-            BwdElem<ND, R> run_ = bwd_identity<ND, R>();  // composite of later chunks inside this tile
-            const Adj<ND, R> g_tile = bwd_apply<ND>(suffix, g_end);
+            typename M::BwdElem run_ = M::bwd_identity();  // composite of later chunks inside this tile
+            const typename M::Adj g_tile = M::bwd_apply(suffix, g_end);
             int64_t c_hi = (t0 + tile) / chunk; if (c_hi > nchunks) c_hi = nchunks;
             for (int64_t c = c_hi - 1; c >= t0 / chunk; --c) {
-                Adj<ND, R> g = bwd_apply<ND>(run_, g_tile);
+                typename M::Adj g = M::bwd_apply(run_, g_tile);
                 int64_t i_hi = (c + 1) * chunk; if (i_hi > n) i_hi = n;
                 for (int64_t i = i_hi - 1; i >= c * chunk; --i) row_back(i, g);
-                run_ = bwd_combine<ND>(agg[c], run_);
+                run_ = M::bwd_combine(agg[c], run_);
             }
-            suffix = bwd_combine<ND>(run_, suffix);
+            suffix = M::bwd_combine(run_, suffix);
         }
     }
     out_gh[0] = value(gh); out_gh[1] = tangent(gh);
     return 0;
 }
 
+// model: 0 = CTCRW, 1 = OU_SSM, 2 = BM_SSM
+template <class R, class Fn>
+static int with_model(int model, int nd, Fn fn) {
+    if (model == 0) { if (nd == 1) return fn(CtcrwModel<1, R>{}); if (nd == 2) return fn(CtcrwModel<2, R>{}); if (nd == 3) return fn(CtcrwModel<3, R>{}); }
+    if (model == 1) { if (nd == 1) return fn(OuSsmModel<1, R>{}); if (nd == 2) return fn(OuSsmModel<2, R>{}); }
+    if (model == 2) { if (nd == 1) return fn(BmSsmModel<1, R>{}); if (nd == 2) return fn(BmSsmModel<2, R>{}); if (nd == 3) return fn(BmSsmModel<3, R>{}); }
+    return 1;
+}
+
 // out_llk[2] = (llk, d llk); out_gh[2] = (d nllk / d h, its tangent).  eta_dot == nullptr: plain doubles.
-extern "C" int harness_ctcrw(int nd, int mode, int64_t n, const uint8_t* flags, const double* y,
-                             const double* dt, const double* eta, const double* a0,
-                             const double* P0, double h, int lc, int nt, double* out_llk,
-                             double* eta_bar, double* out_gh, double* aest) {
+extern "C" int harness_kalman(int model, int nd, int mode, int64_t n, const uint8_t* flags, const double* y,
+                              const double* dt, const double* eta, const double* a0,
+                              const double* P0, double h, int lc, int nt, double* out_llk,
+                              double* eta_bar, double* out_gh, double* aest) {
     double llk2[2] = {0, 0}, gh2[2] = {0, 0};
-    int rc = 1;
-    switch (nd) {
-        case 1: rc = run<1, double>(mode, n, flags, y, dt, eta, nullptr, a0, P0, h, lc, nt, llk2, eta_bar, nullptr, gh2, aest); break;
-        case 2: rc = run<2, double>(mode, n, flags, y, dt, eta, nullptr, a0, P0, h, lc, nt, llk2, eta_bar, nullptr, gh2, aest); break;
-        case 3: rc = run<3, double>(mode, n, flags, y, dt, eta, nullptr, a0, P0, h, lc, nt, llk2, eta_bar, nullptr, gh2, aest); break;
-    }
+    int rc = with_model<double>(model, nd, [&](auto m) {
+        return run<decltype(m)>(mode, n, flags, y, dt, eta, nullptr, a0, P0, h, lc, nt, llk2, eta_bar, nullptr, gh2, aest);
+    });
     *out_llk = llk2[0];
     if (out_gh) *out_gh = gh2[0];
     return rc;
 }
+extern "C" int harness_ctcrw(int nd, int mode, int64_t n, const uint8_t* flags, const double* y,
+                             const double* dt, const double* eta, const double* a0,
+                             const double* P0, double h, int lc, int nt, double* out_llk,
+                             double* eta_bar, double* out_gh, double* aest) {
+    return harness_kalman(0, nd, mode, n, flags, y, dt, eta, a0, P0, h, lc, nt, out_llk, eta_bar, out_gh, aest);
+}
 
 // Tangent (Dual) run of the same algebra: direction (eta_dot, h_dot).
+extern "C" int harness_kalman_tangent(int model, int nd, int mode, int64_t n, const uint8_t* flags, const double* y,
+                                      const double* dt, const double* eta, const double* eta_dot,
+                                      const double* a0, const double* P0, double h, double h_dot, int lc,
+                                      int nt, double* out_llk2, double* eta_bar, double* eta_bar_dot,
+                                      double* out_gh2) {
+    const Dual hh(h, h_dot);
+    return with_model<Dual>(model, nd, [&](auto m) {
+        return run<decltype(m)>(mode, n, flags, y, dt, eta, eta_dot, a0, P0, hh, lc, nt, out_llk2, eta_bar, eta_bar_dot, out_gh2, nullptr);
+    });
+}
 extern "C" int harness_ctcrw_tangent(int nd, int mode, int64_t n, const uint8_t* flags, const double* y,
                                      const double* dt, const double* eta, const double* eta_dot,
                                      const double* a0, const double* P0, double h, double h_dot, int lc,
                                      int nt, double* out_llk2, double* eta_bar, double* eta_bar_dot,
                                      double* out_gh2) {
-    const Dual hh(h, h_dot);
-    switch (nd) {
-        case 1: return run<1, Dual>(mode, n, flags, y, dt, eta, eta_dot, a0, P0, hh, lc, nt, out_llk2, eta_bar, eta_bar_dot, out_gh2, nullptr);
-        case 2: return run<2, Dual>(mode, n, flags, y, dt, eta, eta_dot, a0, P0, hh, lc, nt, out_llk2, eta_bar, eta_bar_dot, out_gh2, nullptr);
-    }
-    return 1;
+    return harness_kalman_tangent(0, nd, mode, n, flags, y, dt, eta, eta_dot, a0, P0, h, h_dot, lc, nt, out_llk2, eta_bar,
+                                  eta_bar_dot, out_gh2);
 }

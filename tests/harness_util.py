@@ -20,9 +20,9 @@ def build_harness():
     out_dir = os.path.join(HERE, "harness", "_build")
     os.makedirs(out_dir, exist_ok=True)
     out = os.path.join(out_dir, "libmath_harness.so")
-    hdrs = [os.path.join(ROOT, "smoothsde_b200", "csrc", f) for f in ("ctcrw_math.cuh", "dual.cuh")]
+    hdrs = [os.path.join(ROOT, "smoothsde_b200", "csrc", f) for f in ("ctcrw_math.cuh", "dual.cuh", "ssm1_math.cuh", "models.cuh")]
     if (not os.path.exists(out)) or os.path.getmtime(out) < max([os.path.getmtime(src)] + [os.path.getmtime(f) for f in hdrs]):
-        subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-x", "c++", "-o", out, src])
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++", "-o", out, src])
     return ctypes.CDLL(out)
 
 
@@ -95,3 +95,31 @@ def harness_ctcrw_tangent(lib, dat, eta, eta_dot, log_sigma_obs, lso_dot, mode, 
     g_lso = 2 * h * gh2[0]
     g_lso_dot = 2 * (h_dot * gh2[0] + h * gh2[1])
     return llk2, (eb, ebd), (g_lso, g_lso_dot)
+
+
+MODEL_IDS = {"CTCRW": 0, "OU_SSM": 1, "BM_SSM": 2}
+
+
+def harness_kalman(lib, dat, eta, log_sigma_obs, mode, lc=8, nt=128):
+    """Any Kalman model through the host-compiled traits (models.cuh): (llk, eta_bar, d nllk / d log_sigma_obs)."""
+    obs = np.asarray(dat["obs"], dtype=float)
+    n, nd = obs.shape
+    flags = row_flags(dat["ID"], obs)
+    dt = ctcrw_dt(dat["times"], flags)
+    eta = np.ascontiguousarray(eta, dtype=float)
+    y = np.ascontiguousarray(np.nan_to_num(obs))
+    a0 = np.ascontiguousarray(dat["a0"], dtype=float)
+    P0 = np.asarray(dat["P0"], dtype=float)
+    P0s = np.array([P0[0, 0], P0[0, 1] if P0.shape[0] > 1 else 0.0, P0[1, 1] if P0.shape[0] > 1 else P0[0, 0]])
+    if dat["type"] != "CTCRW":
+        P0s = np.array([P0[0, 0], 0.0, P0[0, 0]])
+    h = float(np.exp(2 * log_sigma_obs))
+    llk = ctypes.c_double()
+    gh = ctypes.c_double()
+    eb = np.zeros(eta.shape)
+    rc = lib.harness_kalman(MODEL_IDS[dat["type"]], nd, mode, ctypes.c_int64(n),
+                            flags.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), _P(y), _P(dt),
+                            _P(eta), _P(a0), _P(P0s), ctypes.c_double(h), lc, nt,
+                            ctypes.byref(llk), _P(eb), ctypes.byref(gh), None)
+    assert rc == 0
+    return llk.value, eb, gh.value * 2 * h

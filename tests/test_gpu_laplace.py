@@ -18,7 +18,7 @@ pytestmark = pytest.mark.gpu
 
 def split(dat, par, info):
     p_fe, n_s = info["p_fe"], info["n_s"]
-    o = 1 if dat["type"] == "CTCRW" else 0
+    o = 1 if dat["type"] in ("CTCRW", "OU_SSM", "BM_SSM") else 0
     d = {}
     if o:
         d["log_sigma_obs"] = par[:1]
@@ -111,3 +111,23 @@ def test_he_and_sdreport_match_oracle_driven_objects():
     assert np.max(np.abs(Q1[-nb:, -nb:] - Q2[-nb:, -nb:])) <= 1e-6 * np.max(np.abs(Q2))   # exact blocks
     for o in (j_gpu, o_gpu):
         o.close()
+
+
+def test_ou_ssm_fit_recovers_the_measurement_error():
+    """SDE$new(type = "OU_SSM")$fit(): Laplace marginal of the one-state Kalman model, end to end."""
+    rng = np.random.default_rng(11)
+    T, m = 4, 300
+    t = simulate.make_times(T, m, rng, irregular=True)
+    z = simulate.simulate_ou(t, np.full_like(t, 1.0), np.full_like(t, 2.0), np.full_like(t, 1.5), rng)
+    y = z + 0.2 * rng.standard_normal(z.shape)
+    d = {"ID": np.repeat(np.arange(T), m), "time": t.ravel(), "Z": y.ravel()}
+    sde = SDE(formulas={"mu": "~ 1", "tau": "~ s(time, k = 5, bs = 'cs')", "kappa": "~ 1"}, data=d, type="OU_SSM",
+              response="Z", par0=[0.5, 1.0, 1.0])
+    r = sde.fit(gtol=1e-6)
+    assert np.isfinite(r.fun)
+    sig = float(np.exp(sde._par_all[0]))
+    assert 0.1 < sig < 0.4, sig                                  # simulated with sigma_obs = 0.2
+    assert abs(sde.coeff_fe()[0] - 1.0) < 0.5                    # mu
+    x = sde.tmb_obj().par
+    g = sde.tmb_obj().gr(r.x)
+    assert np.max(np.abs(g)) < 1e-3 * max(1.0, abs(r.fun))

@@ -29,15 +29,19 @@ CASES = [
     ("BM", 3, 80, 0.1, 2),
     ("OU", 4, 90, 0.1, 1),
     ("OU", 2, 120, 0.0, 2),
+    ("OU_SSM", 3, 90, 0.1, 2),       # one-state-per-dimension Kalman models (nllk_ou_ssm.hpp, nllk_bm_ssm.hpp)
+    ("OU_SSM", 1, 1500, 0.05, 1),    # several scan tiles
+    ("BM_SSM", 4, 70, 0.2, 2),
+    ("BM_SSM", 2, 1300, 0.0, 3),
 ]
 
 
 @pytest.mark.parametrize("model,T,m,miss,nd", CASES)
 def test_nllk_and_gradient_match_oracle(model, T, m, miss, nd):
     dat, par, info = synth.make_problem(model, T, m, missing_frac=miss, n_dim=nd, seed=7 + T + m)
-    if model == "CTCRW":
+    if model in ("CTCRW", "OU_SSM", "BM_SSM"):
         par = par.copy()
-        par[1:1 + nd] = [0.3, -0.2][:nd]          # exercise B*mu
+        par[1:1 + nd] = [0.3, -0.2, 0.1][:nd]     # exercise B*mu
     ref = O.nllk(dat, par)
     eng = Engine.from_data(dat)
     v0, _ = eng.eval(par, order=0)
@@ -50,6 +54,22 @@ def test_nllk_and_gradient_match_oracle(model, T, m, miss, nd):
     v2, g2 = eng.eval(par, order=1)
     assert abs(v2 - v) <= 1e-13 * abs(v)
     assert grad_err(g2, g) <= 1e-12
+    eng.close()
+
+
+@pytest.mark.parametrize("model,nd", [("OU_SSM", 2), ("BM_SSM", 1)])
+def test_report_aest_ssm_matches_oracle(model, nd):
+    dat, par, info = synth.make_problem(model, 3, 60, missing_frac=0.1, n_dim=nd, seed=8)
+    par = par.copy()
+    par[1:1 + nd] = [0.3, -0.2][:nd]
+    p = O.split_par(dat, par)
+    _, aest_ref = O._nllk_ssm(dat, **p, model=model, return_aest=True)
+    eng = Engine.from_data(dat)
+    eng.eval(par, order=0)
+    aest = eng.report(dat["obs"].shape[0], nd, nd)
+    ID = dat["ID"]
+    last = np.r_[ID[1:] != ID[:-1], True]
+    assert np.max(np.abs(aest[~last] - aest_ref[~last])) < 1e-9
     eng.close()
 
 

@@ -46,6 +46,20 @@ def test_time_shards_on_one_gpu_match_oracle(m, nd, nshard):
     eng.close()
 
 
+@pytest.mark.parametrize("model,nd", [("OU_SSM", 2), ("BM_SSM", 1)])
+def test_time_shards_ssm_match_single_handle(model, nd):
+    dat, par, _ = synth.make_problem(model, 1, 4000, missing_frac=0.05, n_dim=nd, seed=21)
+    par = par.copy()
+    par[1:1 + nd] = [0.3, -0.2][:nd]
+    e1 = Engine.from_data(dat)
+    ref_v, ref_g = e1.eval(par, 1)
+    eng = S.TimeShardedEngine(dat, devices=[0, 0, 0])
+    v, g = eng.eval(par)
+    assert abs(v - ref_v) <= 1e-11 * max(abs(ref_v), 1.0), (v, ref_v)
+    assert grad_err(g, ref_g) <= 1e-9
+    eng.close(); e1.close()
+
+
 def test_track_shards_solo_is_the_plain_engine():
     dat, par, _ = synth.make_problem("CTCRW", 6, 300, missing_frac=0.1, n_dim=2, seed=3)
     e1 = Engine.from_data(dat)
