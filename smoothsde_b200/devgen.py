@@ -230,8 +230,80 @@ def make_ctcrw_device(n_tracks, n_steps, seed=20260103, device=0, k=10, sigma_ob
     par = np.concatenate([[math.log(sigma_obs)], np.zeros(p_fe), np.zeros(2), 0.1 * prng.standard_normal(p_re)])
     info = {"n": n, "n_dim": nd, "nnz": n * nnz_row, "p_fe": p_fe, "p_re": p_re, "n_s": 2,
             "n_par": nd + 2, "n_tracks": n_id, "n_pad": n_pad, "tensors": dict(obs=obs, dt=dt, flags=flags, times=tflat),
-            "S": S, "a0": a0, "track_starts": track_starts, "knots": (lo, hi), "Zc": Zc}
+            "S": S, "a0": a0, "track_starts": track_starts, "knots": (lo, hi), "Zc": Zc,
+            "packed": dict(desc=desc, col=col, val=val, obs_p=obs_p, dt_p=dt_p, flags_p=flags_p, lc=lc, wt=wt, nnz_row=nnz_row)}
     return eng, par, info
+
+
+def slab_views(info, eng, cuts, device=0):
+    """Engines over contiguous row ranges [cuts[r], cuts[r+1]) of a problem built by
+    make_ctcrw_device, WITHOUT copying: every slab handle points into the same device arrays
+    (ssde_create_packed).  Cuts must be multiples of the padding unit (1024 rows).  A cut inside a
+    track gives time shards (SSDE_SHARD_CONT_PREV / CONT_NEXT), a cut at a track boundary gives
+    track shards; the penalty stays with slab 0.  Used to check at BASELINE.json's full sizes that
+    N shards reproduce the single-handle result."""
+    import torch
+    t = info["packed"]
+    n, n_pad = info["n"], info["n_pad"]
+    lc, wt, nnz_row = t["lc"], t["wt"], t["nnz_row"]
+    starts_all = np.asarray(info["track_starts"], dtype=np.int64)
+    a0_all = np.asarray(info["a0"], dtype=np.float64)
+    flags_nat = info["tensors"]["flags"]
+    out = []
+    for r in range(len(cuts) - 1):
+        lo, hi = int(cuts[r]), int(cuts[r + 1])
+        assert lo % 1024 == 0 and (hi % 1024 == 0 or hi == n), "slab boundaries must be multiples of 1024 rows"
+        m = hi - lo
+        m_pad = int(L.load().ssde_padded_rows(m))
+        assert lo + m_pad <= n_pad
+        keep = list(eng._keep)
+        pd = L.PackedDesc()
+        pd.model, pd.n_dim, pd.n_par = L.SSDE_CTCRW, info["n_dim"], info["n_par"]
+        pd.n, pd.n_pad, pd.nnz = m, m_pad, m * nnz_row
+        pd.d_desc = t["desc"].data_ptr() + (lo // wt) * 24
+        pd.d_col, pd.d_val = t["col"].data_ptr(), t["val"].data_ptr()      # val_off in the descriptors is absolute
+        # per-row arrays: obs planes are n_pad apart in the full problem, the engine expects them
+        # m_pad apart -> gather the planes of the slab (a copy of 16 B/row; everything else is a view)
+        obs_p = torch.stack([t["obs_p"][d, lo:lo + m_pad] for d in range(info["n_dim"])]).contiguous()
+        # track index carried by the dt slot of track-start rows must be slab-local
+        sel = (starts_all >= lo) & (starts_all < hi)
+        ts = starts_all[sel] - lo
+        dt_p = t["dt_p"][lo:lo + m_pad]
+        if sel.any() and int(np.flatnonzero(sel)[0]) != 0:
+            dt_p = dt_p.clone()
+            nat = permute_index(torch.as_tensor(ts, device=dt_p.device), lc)
+            dt_p[nat] = torch.arange(ts.size, dtype=torch.float64, device=dt_p.device)
+        keep += [obs_p, dt_p]
+        pd.d_obs, pd.d_dt = obs_p.data_ptr(), dt_p.data_ptr()
+        pd.d_flags = t["flags_p"].data_ptr() + lo
+        pd.p_fe, pd.p_re = info["p_fe"], info["p_re"]
+        pd.S = _as_triplet(info["S"], keep)
+        ncol_re = np.array([info["p_re"] // 2, info["p_re"] // 2], dtype=np.int32)
+        keep.append(ncol_re)
+        pd.n_smooth, pd.ncol_re, pd.include_penalty = 2, ncol_re.ctypes.data_as(L.c_int32_p), 1
+        a0 = np.ascontiguousarray(a0_all[sel]) if sel.any() else np.zeros((1, a0_all.shape[1]))
+        tsc = np.ascontiguousarray(ts) if sel.any() else np.zeros(1, dtype=np.int64)
+        keep += [a0, tsc]
+        pd.n_ID = int(sel.sum())
+        pd.track_starts, pd.a0 = tsc.ctypes.data_as(L.c_int64_p), a0.ctypes.data_as(L.c_double_p)
+        pd.P0[0], pd.P0[1], pd.P0[2] = 1.0, 0.0, 10.0
+        pd.device = device
+        f_lo = int(flags_nat[lo]) if lo < n else 1
+        f_hi = int(flags_nat[hi - 1])
+        pd.shard_flags = (0 if (f_lo & 1) else L.SHARD_CONT_PREV) | (0 if (f_hi & 2) else L.SHARD_CONT_NEXT) | (L.SHARD_NO_PENALTY if r > 0 else 0)
+        mu_cols = np.array([0, 1], dtype=np.int32)
+        keep.append(mu_cols)
+        pd.mu_cols, pd.n_mu_cols = mu_cols.ctypes.data_as(L.c_int32_p), 2
+        out.append(Engine.from_packed(pd, keep))
+    return out
+
+
+def permute_index(rows, lc):
+    """natural row index -> position in the warp-tile order (see permute_rows)."""
+    wt = 32 * lc
+    q = rows // wt
+    r = rows - q * wt
+    return q * wt + (r % lc) * 32 + r // lc
 
 
 def alg_bytes_per_obs(n_dim, n_par, nnz_per_obs):

@@ -286,6 +286,18 @@ class TimeShardedEngine:
         self.n_par, self.layout = self.shards[0][0].n_par, self.shards[0][0].layout
         self.world = world
 
+    @classmethod
+    def from_engines(cls, engines, devices):
+        """Adopt already-built shard engines (in time order), all driven from this process."""
+        import torch
+        self = cls.__new__(cls)
+        self.local, self.comm, self.world = True, SoloComm(), len(engines)
+        self.shards = [(e, r, len(engines)) for r, e in enumerate(engines)]
+        self.devs = [torch.device("cuda", d) for d in devices]
+        self.streams = [torch.cuda.Stream(device=d) for d in self.devs]
+        self.n_par, self.layout = engines[0].n_par, engines[0].layout
+        return self
+
     def _gather(self, ts):
         import torch
         if not self.local:
