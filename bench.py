@@ -40,6 +40,9 @@ def parse():
     ap.add_argument("--cpu-tracks", type=int, default=64)
     ap.add_argument("--cpu-track-steps", type=int, default=10000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="tracks", choices=["tracks", "single"],
+                    help="tracks: BASELINE configs[2] (default, the headline); single: configs[3], ONE track of "
+                         "tracks*track_steps rows, sharded along time over the ranks")
     return ap.parse_args()
 
 
@@ -166,10 +169,22 @@ def main():
             dist.all_reduce(t, op={"min": dist.ReduceOp.MIN, "max": dist.ReduceOp.MAX, "sum": dist.ReduceOp.SUM}[op])
         return t
 
-    tracks_local = args.tracks // world
-    eng, par, info = devgen.make_ctcrw_device(
-        tracks_local, args.track_steps, seed=20260103, device=local, rank=rank, world=world,
-        dist_reduce=dist_reduce, shard_flags=(_lib.SHARD_NO_PENALTY if rank > 0 else 0))
+    single = args.workload == "single"
+    ts = None
+    if single:
+        from smoothsde_b200 import sharded
+        n_all = args.tracks * args.track_steps
+        assert n_all % (world * 128) == 0
+        eng, par, info = devgen.make_ctcrw_device(
+            1, n_all // world, seed=20260104, device=local, rank=rank, world=world, sim_tracks=128,
+            dist_reduce=dist_reduce, shard_flags=(_lib.SHARD_NO_PENALTY if rank > 0 else 0), time_shard=world > 1)
+        if world > 1:
+            ts = sharded.TimeShardedEngine.from_engine_distributed(eng, sharded.DistComm(), local)
+    else:
+        tracks_local = args.tracks // world
+        eng, par, info = devgen.make_ctcrw_device(
+            tracks_local, args.track_steps, seed=20260103, device=local, rank=rank, world=world,
+            dist_reduce=dist_reduce, shard_flags=(_lib.SHARD_NO_PENALTY if rank > 0 else 0))
     n_local = info["n"]
     n_total = n_local * world
     npar = eng.n_par
@@ -179,12 +194,15 @@ def main():
     out_host = torch.zeros(npar + 2, dtype=torch.float64).pin_memory()
     # a non-default torch stream: the C ABI treats a NULL stream as "the handle's own stream",
     # and torch.cuda.Event only sees work on torch's current stream
-    tstream = torch.cuda.Stream(device=dev)
+    tstream = ts.streams[0] if ts is not None else torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(tstream)
     stream = tstream.cuda_stream
     assert stream != 0
 
     def step_device():
+        if ts is not None:                 # one track cut along time: 3 stages, 2 all-gathers + 1 all-reduce
+            out_dev.copy_(ts.eval_device(par_dev))
+            return
         eng.eval_device(par_dev.data_ptr(), out_dev.data_ptr(), 1, stream)
         if world > 1:
             dist.all_reduce(out_dev[:npar + 1])
@@ -222,7 +240,10 @@ def main():
     eng.set_profile(True)
     ksum, kcount = {}, 0
     for _ in range(min(args.steps, 10)):
-        eng.eval_device(par_dev.data_ptr(), out_dev.data_ptr(), 1, stream)
+        if ts is not None:
+            ts.eval_device(par_dev)        # events between the stages also see the waits for the collectives
+        else:
+            eng.eval_device(par_dev.data_ptr(), out_dev.data_ptr(), 1, stream)
         torch.cuda.synchronize()
         for nm, ms in eng.last_kernel_times():
             ksum[nm] = ksum.get(nm, 0.0) + ms
@@ -238,6 +259,9 @@ def main():
     if world == 1:
         for _ in range(args.steps):
             v, g = eng.eval(par, order=1)           # ssde_eval: H2D par, kernels, D2H nllk+grad, sync
+    elif ts is not None:
+        for _ in range(args.steps):
+            v, g = ts.eval(par)                     # H2D par, 3 stages + collectives, D2H nllk+grad, sync
     else:
         for _ in range(args.steps):
             par_dev.copy_(par_host, non_blocking=True)
@@ -263,7 +287,7 @@ def main():
     b_pass = 12 * nnz_row + 8 * info["n_par"]
     b_kernel = {"ctcrw_fwd": (8 * info["n_dim"] + 8 + 4) + b_pass, "ctcrw_bwd": b_pass}
     dev_ms = sum(kernels.values())
-    dom = max(kernels, key=kernels.get) if kernels else None
+    dom = max((k for k in kernels if k in b_kernel), key=kernels.get)
     achieved = b_kernel[dom] * n_local / (kernels[dom] * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
@@ -288,9 +312,13 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"CTCRW d=2, {args.tracks} tracks x {args.track_steps} irregular steps "
-                               f"(n={n_total}), tau,nu ~ s(time,k=10), mu fixed 0 (BASELINE configs[2])",
-                   "sharding": f"tracks split over {world} rank(s), one NCCL all-reduce of {npar + 1} doubles per evaluation",
+        "config": {"workload": (f"CTCRW d=2, ONE track of {n_total} irregular steps, tau,nu ~ s(time,k=10), mu fixed 0 "
+                                f"(BASELINE configs[3])" if single else
+                                f"CTCRW d=2, {args.tracks} tracks x {args.track_steps} irregular steps "
+                                f"(n={n_total}), tau,nu ~ s(time,k=10), mu fixed 0 (BASELINE configs[2])"),
+                   "sharding": (f"track cut along time over {world} rank(s): 2 NCCL all-gathers of one scan element + 1 all-reduce "
+                                f"of {npar + 2} doubles per evaluation" if single else
+                                f"tracks split over {world} rank(s), one NCCL all-reduce of {npar + 1} doubles per evaluation"),
                    "l2": "inputs per GPU (>= 3 GB) are far larger than the 126 MB L2; no flush needed"},
         "clocks": clk,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

@@ -233,10 +233,14 @@ void* ssde_stream(const ssde_handle* h);
  * associative scans, so each shard is summarised by one composite element; the host gathers the
  * elements of all shards between the stages (two all-gathers of < 1 KB and the final all-reduce
  * per evaluation).  Everything is asynchronous on `stream`, all pointers are device pointers:
- *   stage 0: forward summary pass;             d_out[ssde_shard_elem_doubles(h, 0)] = this shard's element
+ *   stage 0: forward summary pass over the TAIL of the shard (its last 4096 rows);
+ *            d_out[ssde_shard_elem_doubles(h, 0)] = composite element + constant-map flag (last double)
+ *   stage 3: the same over the WHOLE shard -- needed only when some shard's flag of stage 0 is 0,
+ *            i.e. its tail does not make the filter forget what came before (long observation gaps)
  *   stage 1: d_elems = forward elements of all n_shards shards (shard-major); computes the incoming
- *            state, runs the forward pass and the adjoint summary pass;
- *            d_out[ssde_shard_elem_doubles(h, 1)] = this shard's adjoint element
+ *            state, runs the forward pass and the adjoint summary pass over the HEAD of the shard;
+ *            d_out[ssde_shard_elem_doubles(h, 1)] = this shard's adjoint element + flag
+ *   stage 4: the adjoint summary over the whole shard (fallback as stage 3)
  *   stage 2: d_elems = adjoint elements of all shards; computes the incoming adjoint, runs the
  *            adjoint pass;  d_out[1 + n_par + 1] = partial nllk, gradient, status (as ssde_eval_device)
  */

@@ -223,8 +223,10 @@ __device__ __forceinline__ void publish_incl(const ScanDesc& d, int t, const typ
 // before ticket `t` (identity for t == 0).  Lane l inspects tile base - l; the window is consumed
 // as soon as every tile up to the nearest one that already knows its inclusive prefix has at
 // least published its aggregate -- tiles farther away are never waited for.
+// `lo`: first ticket of this launch (tickets below it count as the identity prefix; a tail-only
+// summary pass starts in the middle of the tile sequence).
 template <class Ops>
-__device__ __forceinline__ typename Ops::Elem lookback(const ScanDesc& d, int t) {
+__device__ __forceinline__ typename Ops::Elem lookback(const ScanDesc& d, int t, int lo = 0) {
     using Elem = typename Ops::Elem;
     const int lane = threadIdx.x & 31;
     Elem acc = Ops::identity();
@@ -237,7 +239,7 @@ __device__ __forceinline__ typename Ops::Elem lookback(const ScanDesc& d, int t)
                  __device__ ~Fin() { if (lane == 0) { atomicAdd(d.stats + 0, 1ull); atomicAdd(d.stats + 1, w); atomicAdd(d.stats + 2, s);
                                                        atomicAdd(d.stats + 3, (unsigned long long)(clock64() - c0)); } } } fin{d, c0, n_win, n_spin, lane};
 #endif
-    while (base >= 0) {
+    while (base >= lo) {
         const int idx = base - lane;
         unsigned spins = 0;
 #ifdef SSDE_STATS
@@ -246,8 +248,8 @@ __device__ __forceinline__ typename Ops::Elem lookback(const ScanDesc& d, int t)
         int first;                                         // nearest lane holding an inclusive prefix
         unsigned code;
         while (true) {
-            code = 2u;                                     // virtual tile -1: identity prefix
-            if (idx >= 0) {
+            code = 2u;                                     // virtual tile lo - 1: identity prefix
+            if (idx >= lo) {
                 const unsigned st = ld_status(d.status + idx);
                 code = ((st >> 2) == d.epoch) ? (st & 3u) : 0u;
             }
@@ -266,7 +268,7 @@ __device__ __forceinline__ typename Ops::Elem lookback(const ScanDesc& d, int t)
             __nanosleep(20);
         }
         Elem e = Ops::identity();
-        if (idx >= 0) {
+        if (idx >= lo) {
             if (lane < first || (lane == first && code == 3u)) e = load_elem_cg<Elem>(d.agg + (size_t)idx * Elem::NDBL);
             else if (lane == first) e = load_elem_cg<Elem>(d.incl + (size_t)idx * Elem::NDBL);
         }

@@ -52,6 +52,7 @@ struct KalmanArgs {
     int ntiles;
     int summary;               // 1: stop after the tile prefixes are published (time-sharded runs only
                                // need the composite element of the whole shard = last inclusive prefix)
+    int tile_lo;               // first ticket of this launch (> 0: summary over the tail of the shard only)
 };
 
 // Start state of the track whose first row carries track index `idx` (stored, as a double, in
@@ -119,7 +120,7 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(KalmanArgs<typename
     // look-back of every later tile).
     for (int it = 0;; ++it) {
         const int par = it & 1;
-        if (tid == 0) sm.ticket[par] = (int)atomicAdd(a.fdesc.ticket, 1u);
+        if (tid == 0) sm.ticket[par] = a.tile_lo + (int)atomicAdd(a.fdesc.ticket, 1u);
         __syncthreads();
         const int tile = sm.ticket[par];
         if (tile >= a.ntiles) break;
@@ -210,7 +211,7 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(KalmanArgs<typename
         }
         Elem pre;
         if (warp == 0) {
-            pre = lookback<Ops>(a.fdesc, tile);
+            pre = lookback<Ops>(a.fdesc, tile, a.tile_lo);
             if (lane == 0) {
                 // state at the first row of the tile
                 const St s0 = a.s_in ? M::load_state([&](int i) { return a.s_in[i]; }) : M::zero_state(a.P0);
@@ -357,7 +358,7 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_bwd_kernel(KalmanArgs<typename
 
     for (int it = 0;; ++it) {
         const int par = it & 1;
-        if (tid == 0) sm.ticket[par] = (int)atomicAdd(a.bdesc.ticket, 1u);
+        if (tid == 0) sm.ticket[par] = a.tile_lo + (int)atomicAdd(a.bdesc.ticket, 1u);
         __syncthreads();
         const int ticket = sm.ticket[par];
         if (ticket >= a.ntiles) break;
@@ -436,7 +437,7 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_bwd_kernel(KalmanArgs<typename
         }
         Elem suf;
         if (warp == 0) {
-            suf = lookback<Ops>(a.bdesc, ticket);
+            suf = lookback<Ops>(a.bdesc, ticket, a.tile_lo);
             if (lane == 0) {
                 const Ad g0 = a.g_in ? M::load_adj([&](int i) { return a.g_in[i]; }) : M::adj_zero();
                 const Ad gt = M::bwd_apply(suf, g0);
@@ -535,6 +536,18 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_bwd_kernel(KalmanArgs<typename
 // time-sharded runs: composite elements of the shards (gathered from all ranks) -> incoming
 // state / adjoint of shard `me`.  One thread.
 // ---------------------------------------------------------------------------------------------
+// Shard element handed to the other ranks: the inclusive prefix of the shard's last ticket plus
+// one double that says whether it is a constant map.  A summary pass over the TAIL of a shard is
+// the shard's exact composite element iff that flag is set (nothing before the tail matters);
+// otherwise the host repeats the pass over the whole shard.
+template <class Elem, class Ops>
+__global__ void shard_elem_kernel(const double* __restrict__ incl_last, double* __restrict__ out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const Elem e = load_elem<Elem>(incl_last);
+    store_elem(out, e);
+    out[Elem::NDBL] = Ops::is_const(e) ? 1.0 : 0.0;
+}
+
 template <class M>
 __global__ void shard_state_kernel(const double* __restrict__ elems, int n_shards, int me, Sym2 P0,
                                    typename M::R* __restrict__ s_out) {
@@ -542,7 +555,7 @@ __global__ void shard_state_kernel(const double* __restrict__ elems, int n_shard
     using Elem = typename M::FwdElem;
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     Elem acc = M::fwd_identity();
-    for (int i = 0; i < me && i < n_shards; ++i) acc = M::fwd_combine(acc, load_elem<Elem>(elems + (size_t)i * Elem::NDBL));
+    for (int i = 0; i < me && i < n_shards; ++i) acc = M::fwd_combine(acc, load_elem<Elem>(elems + (size_t)i * (Elem::NDBL + 1)));
     const typename M::State s = M::fwd_apply(acc, M::zero_state(P0));   // shard 0 begins with a track start: the input is irrelevant
     M::store_state(s, [&](int i) -> R& { return s_out[i]; });
 }
@@ -554,7 +567,7 @@ __global__ void shard_adjoint_kernel(const double* __restrict__ elems, int n_sha
     using Elem = typename M::BwdElem;
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     Elem acc = M::bwd_identity();
-    for (int i = n_shards - 1; i > me; --i) acc = M::bwd_combine(load_elem<Elem>(elems + (size_t)i * Elem::NDBL), acc);
+    for (int i = n_shards - 1; i > me; --i) acc = M::bwd_combine(load_elem<Elem>(elems + (size_t)i * (Elem::NDBL + 1)), acc);
     const typename M::Adj g = M::bwd_apply(acc, M::adj_zero());
     M::store_adj(g, [&](int i) -> R& { return g_out[i]; });
 }

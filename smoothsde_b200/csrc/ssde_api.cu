@@ -706,6 +706,7 @@ KalmanArgs<R> ctcrw_args(ssde_handle* h, const double* d_par, const double* d_di
 #endif
     a.ntiles = h->ntiles_f;
     a.summary = 0;
+    a.tile_lo = 0;
     return a;
 }
 
@@ -719,8 +720,11 @@ int new_scan_epoch(ssde_handle* h, cudaStream_t st) {
     return SSDE_OK;
 }
 
+constexpr int TAIL_TILES = 4;           // tiles of a tail-only summary pass (4096 rows)
+
 template <class M>
-int launch_ctcrw_fwd(ssde_handle* h, const double* d_par, const double* d_dir, cudaStream_t st, double* aest, bool summary) {
+int launch_ctcrw_fwd(ssde_handle* h, const double* d_par, const double* d_dir, cudaStream_t st, double* aest, bool summary,
+                     bool tail = false) {
     using R = typename M::R;
     constexpr bool TAN = !std::is_same<R, double>::value;
     std::string& err = h->err;
@@ -728,7 +732,8 @@ int launch_ctcrw_fwd(ssde_handle* h, const double* d_par, const double* d_dir, c
     if (rc) return rc;
     KalmanArgs<R> a = ctcrw_args<R>(h, d_par, d_dir, aest);
     a.summary = summary ? 1 : 0;
-    mark(h, st, TAN ? "ctcrw_fwd_tangent" : (summary ? "ctcrw_fwd_summary" : "ctcrw_fwd"));
+    a.tile_lo = (summary && tail) ? std::max(h->ntiles_f - TAIL_TILES, 0) : 0;
+    mark(h, st, TAN ? "ctcrw_fwd_tangent" : (summary ? (tail ? "ctcrw_fwd_tail" : "ctcrw_fwd_summary") : "ctcrw_fwd"));
     if constexpr (TAN) ctcrw_fwd_kernel<M, FWD_NT, TAN_MINB><<<h->grid_f2, FWD_NT, sizeof(FwdSmem<M, FWD_NT>), st>>>(a);
     else ctcrw_fwd_kernel<M, FWD_NT, FWD_MINB><<<h->grid_f, FWD_NT, sizeof(FwdSmem<M, FWD_NT>), st>>>(a);
     CUDA_TRY(cudaGetLastError());
@@ -736,7 +741,7 @@ int launch_ctcrw_fwd(ssde_handle* h, const double* d_par, const double* d_dir, c
 }
 
 template <class M>
-int launch_ctcrw_bwd(ssde_handle* h, const double* d_par, const double* d_dir, cudaStream_t st, bool summary) {
+int launch_ctcrw_bwd(ssde_handle* h, const double* d_par, const double* d_dir, cudaStream_t st, bool summary, bool tail = false) {
     using R = typename M::R;
     constexpr bool TAN = !std::is_same<R, double>::value;
     std::string& err = h->err;
@@ -745,7 +750,8 @@ int launch_ctcrw_bwd(ssde_handle* h, const double* d_par, const double* d_dir, c
     KalmanArgs<R> a = ctcrw_args<R>(h, d_par, d_dir, nullptr);
     a.ntiles = h->ntiles_b;
     a.summary = summary ? 1 : 0;
-    mark(h, st, TAN ? "ctcrw_bwd_tangent" : (summary ? "ctcrw_bwd_summary" : "ctcrw_bwd"));
+    a.tile_lo = (summary && tail) ? std::max(h->ntiles_b - TAIL_TILES, 0) : 0;
+    mark(h, st, TAN ? "ctcrw_bwd_tangent" : (summary ? (tail ? "ctcrw_bwd_tail" : "ctcrw_bwd_summary") : "ctcrw_bwd"));
     if constexpr (TAN) ctcrw_bwd_kernel<M, BWD_NT, TAN_MINB><<<h->grid_b2, BWD_NT, sizeof(BwdSmem<M, BWD_NT>), st>>>(a);
     else ctcrw_bwd_kernel<M, BWD_NT, BWD_MINB><<<h->grid_b, BWD_NT, sizeof(BwdSmem<M, BWD_NT>), st>>>(a);
     CUDA_TRY(cudaGetLastError());
@@ -1211,7 +1217,7 @@ int ssde_eval_device(ssde_handle* h, const double* d_par, int order, double* d_o
 
 int ssde_shard_elem_doubles(const ssde_handle* h, int which) {
     if (!h || !is_kalman(h->model)) return -1;
-    return which == 0 ? h->fwd_elem : h->bwd_elem;
+    return (which == 0 ? h->fwd_elem : h->bwd_elem) + 1;      // + the constant-map flag
 }
 
 int ssde_eval_stage(ssde_handle* h, const double* d_par, int stage, const double* d_elems, int n_shards,
@@ -1221,33 +1227,43 @@ int ssde_eval_stage(ssde_handle* h, const double* d_par, int stage, const double
     if (!is_kalman(h->model)) { err = "time-sharded evaluation exists for the Kalman models only"; return SSDE_ERR_UNSUPPORTED; }
     CUDA_TRY(cudaSetDevice(h->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
-    const size_t fe = (size_t)ssde_shard_elem_doubles(h, 0), be = (size_t)ssde_shard_elem_doubles(h, 1);
+    const size_t fe = (size_t)h->fwd_elem, be = (size_t)h->bwd_elem;
     int rc = SSDE_OK;
-    if (stage == 0) {
-        // parameters -> theta; forward summary; composite element of the shard -> d_out[fe]
+    if (stage == 0 || stage == 3) {
+        // parameters -> theta; forward summary (stage 0: tail of the shard only; stage 3: the whole
+        // shard); composite element of the shard + constant-map flag -> d_out[fe + 1]
         if (!d_out) return SSDE_ERR_BAD_ARG;
         h->last_launches = 0; h->pcount = 0;
         h->have_s_in = h->have_g_in = false;
         if ((rc = eval_prologue(h, d_par, nullptr, 1, st))) return rc;
-        rc = with_kalman_model<double>(h, [&](auto m) -> int { return launch_ctcrw_fwd<decltype(m)>(h, d_par, nullptr, st, nullptr, true); });
-        if (rc) return rc;
-        CUDA_TRY(cudaMemcpyAsync(d_out, h->f_incl.as<double>() + (size_t)(h->ntiles_f - 1) * fe, fe * sizeof(double),
-                                 cudaMemcpyDeviceToDevice, st));
-    } else if (stage == 1) {
-        // gathered forward elements -> incoming state; forward pass; adjoint summary -> d_out[be]
-        if (!d_elems || !d_out || my_shard < 0 || my_shard >= n_shards) return SSDE_ERR_BAD_ARG;
         rc = with_kalman_model<double>(h, [&](auto m) -> int {
             using M = decltype(m);
-            shard_state_kernel<M><<<1, 32, 0, st>>>(d_elems, n_shards, my_shard, h->P0, h->s_in.as<double>());
-            ++h->last_launches;
-            h->have_s_in = true;
-            int rc = launch_ctcrw_fwd<M>(h, d_par, nullptr, st, nullptr, false);
+            int rc = launch_ctcrw_fwd<M>(h, d_par, nullptr, st, nullptr, true, stage == 0);
             if (rc) return rc;
-            return launch_ctcrw_bwd<M>(h, d_par, nullptr, st, true);
+            shard_elem_kernel<typename M::FwdElem, FwdOps<M>><<<1, 32, 0, st>>>(h->f_incl.as<double>() + (size_t)(h->ntiles_f - 1) * fe, d_out);
+            ++h->last_launches;
+            return SSDE_OK;
         });
         if (rc) return rc;
-        CUDA_TRY(cudaMemcpyAsync(d_out, h->b_incl.as<double>() + (size_t)(h->ntiles_b - 1) * be, be * sizeof(double),
-                                 cudaMemcpyDeviceToDevice, st));
+    } else if (stage == 1 || stage == 4) {
+        // stage 1: gathered forward elements -> incoming state; forward pass; adjoint summary over the
+        // head of the shard -> d_out[be + 1].  stage 4: the adjoint summary again, over the whole shard.
+        if (!d_out || (stage == 1 && (!d_elems || my_shard < 0 || my_shard >= n_shards))) return SSDE_ERR_BAD_ARG;
+        rc = with_kalman_model<double>(h, [&](auto m) -> int {
+            using M = decltype(m);
+            int rc;
+            if (stage == 1) {
+                shard_state_kernel<M><<<1, 32, 0, st>>>(d_elems, n_shards, my_shard, h->P0, h->s_in.as<double>());
+                ++h->last_launches;
+                h->have_s_in = true;
+                if ((rc = launch_ctcrw_fwd<M>(h, d_par, nullptr, st, nullptr, false))) return rc;
+            }
+            if ((rc = launch_ctcrw_bwd<M>(h, d_par, nullptr, st, true, stage == 1))) return rc;
+            shard_elem_kernel<typename M::BwdElem, BwdOps<M>><<<1, 32, 0, st>>>(h->b_incl.as<double>() + (size_t)(h->ntiles_b - 1) * be, d_out);
+            ++h->last_launches;
+            return SSDE_OK;
+        });
+        if (rc) return rc;
     } else if (stage == 2) {
         // gathered adjoint elements -> incoming adjoint; adjoint pass; finalize -> d_out[1 + n_par + 1]
         if (!d_elems || !d_out || my_shard < 0 || my_shard >= n_shards) return SSDE_ERR_BAD_ARG;
@@ -1262,7 +1278,7 @@ int ssde_eval_stage(ssde_handle* h, const double* d_par, int stage, const double
         if ((rc = launch_reduce(h, 1, false, st))) return rc;
         if ((rc = eval_epilogue(h, d_par, nullptr, 1, d_out, nullptr, st))) return rc;
     } else {
-        err = "stage must be 0, 1 or 2";
+        err = "stage must be 0 .. 4";
         return SSDE_ERR_BAD_ARG;
     }
     CUDA_TRY(cudaGetLastError());

@@ -73,7 +73,7 @@ def permute_rows(x, n_pad, lc, fill):
 
 def make_ctcrw_device(n_tracks, n_steps, seed=20260103, device=0, k=10, sigma_obs=0.1,
                       irregular=True, rank=0, world=1, sim_tracks=None, dist_reduce=None,
-                      shard_flags=0):
+                      shard_flags=0, time_shard=False):
     """Build the rows of `n_tracks` tracks x `n_steps` steps on `device` (this rank's shard).
 
     sim_tracks: simulate only this many distinct tracks x (n_tracks*n_steps/sim_tracks) ... used
@@ -81,6 +81,9 @@ def make_ctcrw_device(n_tracks, n_steps, seed=20260103, device=0, k=10, sigma_ob
     segments that are stitched together (positions made continuous).
     dist_reduce(tensor, op) -> tensor: optional all-reduce across ranks so that every shard uses
     the same knots and sum-to-zero constraint.
+    time_shard: (with sim_tracks) this rank holds slab `rank` of `world` of ONE track of
+    world * n_steps rows: its times follow the previous slab's, only rank 0 has the track start,
+    only the last rank the track end (SSDE_SHARD_CONT_PREV / CONT_NEXT are set accordingly).
     Returns (engine, par, info)."""
     import torch
     dev = torch.device("cuda", device)
@@ -105,6 +108,10 @@ def make_ctcrw_device(n_tracks, n_steps, seed=20260103, device=0, k=10, sigma_ob
         ends = times[:, -1] + 1.0
         off = torch.cumsum(ends, 0) - ends
         times = times + off[:, None]
+    slab_t = 2.0 * n + 4.0 * T          # upper bound of a slab's time span (increments are < 2)
+    if time_shard:
+        assert single
+        times = times + rank * slab_t
     s = (times - times.min()) / (times.max() - times.min()) if single else times / times[:, -1:]
     tau = torch.exp(0.5 * torch.sin(2 * math.pi * s))
     nu = torch.exp(0.3 * torch.cos(2 * math.pi * s))
@@ -124,7 +131,19 @@ def make_ctcrw_device(n_tracks, n_steps, seed=20260103, device=0, k=10, sigma_ob
     dt = torch.ones(n, dtype=torch.float64, device=dev)
     dt[:-1] = tflat[1:] - tflat[:-1]
     flags = torch.full((n,), 4, dtype=torch.uint8, device=dev)
-    if single:
+    if single and time_shard:
+        first_slab, last_slab = rank == 0, rank == world - 1
+        track_starts = np.array([0] if first_slab else [], dtype=np.int64)
+        if first_slab:
+            flags[0] |= 1
+        if last_slab:
+            flags[-1] |= 2
+            dt[-1] = 1.0
+        else:
+            dt[-1] = (rank + 1) * slab_t - tflat[-1]          # first time of the next slab
+        n_id = 1 if first_slab else 0
+        shard_flags |= (0 if first_slab else L.SHARD_CONT_PREV) | (0 if last_slab else L.SHARD_CONT_NEXT)
+    elif single:
         track_starts = np.array([0], dtype=np.int64)
         flags[0] |= 1
         flags[-1] |= 2
@@ -138,11 +157,12 @@ def make_ctcrw_device(n_tracks, n_steps, seed=20260103, device=0, k=10, sigma_ob
         track_starts = np.arange(0, n, m, dtype=np.int64)
         n_id = T
     # CTCRW never uses the dt of a track-start row: it carries the track index (row of a0)
-    dt[torch.as_tensor(track_starts, device=dev)] = torch.arange(n_id, dtype=torch.float64, device=dev)
-    a0 = np.zeros((n_id, 2 * nd))
-    first_obs = obs[torch.as_tensor(track_starts, device=dev)].cpu().numpy()
-    for d in range(nd):
-        a0[:, 2 * d] = first_obs[:, d]
+    a0 = np.zeros((max(n_id, 1), 2 * nd))
+    if n_id:
+        dt[torch.as_tensor(track_starts, device=dev)] = torch.arange(n_id, dtype=torch.float64, device=dev)
+        first_obs = obs[torch.as_tensor(track_starts, device=dev)].cpu().numpy()
+        for d in range(nd):
+            a0[:n_id, 2 * d] = first_obs[:, d]
 
     # spline design: knots over the global time range, sum-to-zero constraint from global means
     lo, hi = tflat.min().reshape(1), tflat.max().reshape(1)
@@ -211,7 +231,7 @@ def make_ctcrw_device(n_tracks, n_steps, seed=20260103, device=0, k=10, sigma_ob
     pd.ncol_re = ncol_re.ctypes.data_as(L.c_int32_p)
     pd.include_penalty = 1
     pd.n_ID = n_id
-    ts = np.ascontiguousarray(track_starts)
+    ts = np.ascontiguousarray(track_starts if n_id else np.zeros(1, dtype=np.int64))
     a0c = np.ascontiguousarray(a0)
     keep += [ts, a0c]
     pd.track_starts = ts.ctypes.data_as(L.c_int64_p)

@@ -229,29 +229,44 @@ class TrackShardedEngine:
 # one long track: shard along time (CTCRW)
 # --------------------------------------------------------------------------------------------
 def _stage_driver(shards, par_tensors, gather, reduce_, streams):
-    """The three stages of ssde_eval_stage for a list of local shards (one per rank in the
-    distributed case).  gather(list of per-shard tensors) -> list of gathered tensors, one per
-    local shard; reduce_(list of out tensors) sums them in place across all shards."""
+    """The stages of ssde_eval_stage for a list of local shards (one per rank in the distributed
+    case).  gather(list of per-shard tensors) -> list of gathered tensors, one per local shard;
+    reduce_(list of out tensors) sums them in place across all shards.
+
+    Summary passes first run over the TAIL of each shard only (stage 0 / the summary part of stage
+    1): with observations the filter forgets, so the last few thousand rows of a shard almost
+    always are its exact composite scan element.  Every element carries a constant-map flag; if
+    any shard's flag is unset (long gaps without observations), the pass is repeated over whole
+    shards (stages 3 / 4).  Reading the flags is the only host synchronisation of an evaluation."""
     import torch
-    e0, e1, outs = [], [], []
-    for (eng, me, nsh), par, st in zip(shards, par_tensors, streams):
-        with torch.cuda.stream(st):
-            t = torch.empty(eng.shard_elem_doubles(0), dtype=torch.float64, device=par.device)
-            eng.eval_stage(0, par.data_ptr(), t.data_ptr(), stream_ptr=st.cuda_stream)
-        e0.append(t)
-    g0 = gather(e0)
-    for (eng, me, nsh), par, st, g in zip(shards, par_tensors, streams, g0):
-        with torch.cuda.stream(st):
-            t = torch.empty(eng.shard_elem_doubles(1), dtype=torch.float64, device=par.device)
-            eng.eval_stage(1, par.data_ptr(), t.data_ptr(), g.data_ptr(), nsh, me, stream_ptr=st.cuda_stream)
-        e1.append(t)
-    g1 = gather(e1)
-    for (eng, me, nsh), par, st, g in zip(shards, par_tensors, streams, g1):
-        with torch.cuda.stream(st):
-            t = torch.empty(eng.n_par + 2, dtype=torch.float64, device=par.device)
-            eng.eval_stage(2, par.data_ptr(), t.data_ptr(), g.data_ptr(), nsh, me, stream_ptr=st.cuda_stream)
-        outs.append(t)
-    return reduce_(outs)
+
+    def run(stage, which, gathered=None):
+        outs = []
+        for i, ((eng, me, nsh), par, st) in enumerate(zip(shards, par_tensors, streams)):
+            with torch.cuda.stream(st):
+                t = torch.empty(eng.shard_elem_doubles(which) if which is not None else eng.n_par + 2,
+                                dtype=torch.float64, device=par.device)
+                g = gathered[i] if gathered is not None else None
+                eng.eval_stage(stage, par.data_ptr(), t.data_ptr(), g.data_ptr() if g is not None else 0, nsh, me,
+                               stream_ptr=st.cuda_stream)
+            outs.append(t)
+        return outs
+
+    def all_const(g, which):
+        # every rank reads the same gathered flags, so all ranks take the same branch; the copy is
+        # ordered after the gather on the shard's stream
+        k = shards[0][0].shard_elem_doubles(which)
+        with torch.cuda.stream(streams[0]):
+            flags = g[0][k - 1::k].cpu()
+        return bool((flags > 0.5).all())
+
+    g0 = gather(run(0, 0))
+    if not all_const(g0, 0):
+        g0 = gather(run(3, 0))
+    g1 = gather(run(1, 1, g0))
+    if not all_const(g1, 1):
+        g1 = gather(run(4, 1))
+    return reduce_(run(2, None, g1))
 
 
 class TimeShardedEngine:
@@ -317,6 +332,29 @@ class TimeShardedEngine:
         for st in self.streams:
             st.synchronize()
         return sum(o.cpu() for o in outs).numpy()
+
+    @classmethod
+    def from_engine_distributed(cls, engine, comm, device):
+        """This rank's time slab (already built, e.g. by devgen) + a torch.distributed group."""
+        import torch
+        self = cls.__new__(cls)
+        self.local, self.comm, self.world = False, comm, comm.world
+        self.shards = [(engine, comm.rank, comm.world)]
+        self.devs = [torch.device("cuda", device)]
+        self.streams = [torch.cuda.Stream(device=self.devs[0])]
+        self.n_par, self.layout = engine.n_par, engine.layout
+        return self
+
+    def eval_device(self, par_dev):
+        """Distributed use, no host synchronisation: par_dev is a device tensor; returns the device
+        tensor [nllk, gradient, status] (all-reduced), ordered on self.streams[0]."""
+        import torch
+
+        def reduce_(outs):
+            with torch.cuda.stream(self.streams[0]):
+                self.comm.all_reduce_sum(outs[0])
+            return outs[0]
+        return _stage_driver(self.shards, [par_dev], self._gather, reduce_, self.streams)
 
     def eval(self, par, order=1):
         """(nllk, grad); the stage protocol always computes the gradient."""
