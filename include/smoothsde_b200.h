@@ -37,8 +37,12 @@ typedef struct ssde_handle ssde_handle;
  * layer answers SSDE_ERR_UNSUPPORTED; the reference says error("Unknown SDE type") only for names
  * outside its list, smoothSDE.cpp:25 -> SSDE_ERR_UNKNOWN_TYPE here).
  * BM_SSM / OU_SSM (nllk_bm_ssm.hpp, nllk_ou_ssm.hpp): a0 is [n_ID x n_dim] (first observation of
- * each track, R/sde.R:549-550), P0 [n_dim x n_dim] must be a multiple of the identity (default
- * diag(10), R/sde.R:553); parameter vector as for CTCRW. */
+ * each track, R/sde.R:549-550), P0 [n_dim x n_dim] (default diag(10), R/sde.R:553); parameter
+ * vector as for CTCRW.
+ * Kalman models: with H = sigma_obs^2 I and a P0 of the default shape (CTCRW: block-diagonal with
+ * identical 2x2 blocks; SSM: c I) the dimensions decouple and the fast kernels run; a user H_array
+ * (nllk_ctcrw.hpp:203-205) or any other symmetric P0 selects the coupled filter (full N x N
+ * covariance recursion, same scan kernels with matrix-valued elements). */
 enum ssde_model { SSDE_BM = 0, SSDE_OU = 1, SSDE_CTCRW = 2, SSDE_BM_SSM = 3, SSDE_OU_SSM = 4 };
 
 enum ssde_status {
@@ -84,8 +88,10 @@ typedef struct {
     const double* a0;         /* CTCRW: [n_ID x 2*n_dim] column-major, (x, 0, y, 0, ...) R/sde.R:574-580;
                                  BM_SSM / OU_SSM: [n_ID x n_dim] */
     const double* P0;         /* CTCRW: [2*n_dim x 2*n_dim] column-major, R/sde.R:582-588; SSM: [n_dim x n_dim] */
-    const double* H_array;    /* CTCRW: NULL or array(0) for H = sigma_obs^2 I; user H not built yet */
-    int64_t H_len;
+    const double* H_array;    /* Kalman models: NULL or array(0) (H_len <= 1) for H = sigma_obs^2 I, else the user's
+                                 measurement covariances [n_dim x n_dim x n] column-major (R/sde.R:593-598); the
+                                 objective then does not depend on log_sigma_obs (its gradient entry is 0) */
+    int64_t H_len;            /* length(H_array): n_dim * n_dim * n, or <= 1 */
     int32_t device;           /* CUDA device ordinal */
     int32_t shard_flags;      /* enum ssde_shard_flags */
     double t_next;            /* time of the next shard's first row (only with CONT_NEXT) */

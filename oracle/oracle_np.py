@@ -359,8 +359,39 @@ def tr_dens(Z1, Z0, dtimes, par, type_):
     return res
 
 
-def nllk_sde(dat, coeff_fe, log_lambda, coeff_re, type_=None):
+def has_decay(dat):
+    """t_decay.size() > 1, nllk_sde.hpp:49 (R passes t_decay = 0 when there is no decay term, R/sde.R:645)."""
+    t = dat.get("t_decay")
+    return t is not None and np.size(t) > 1
+
+
+def n_decay(dat):
+    """length(log_decay) = length(unique(ind_decay)), R/sde.R:177,506."""
+    return int(np.unique(np.asarray(dat["ind_decay"])).size) if has_decay(dat) else 0
+
+
+def decayed_X_re(dat, log_decay):
+    """nllk_sde.hpp:47-59: X_re_copy = X_re with column col_decay(i) multiplied, row by row, by
+    exp(-exp(log_decay(ind_decay(i))) * t_decay); col_decay / ind_decay are 1-based."""
+    import scipy.sparse as sp
+    X = sp.csc_matrix(dat["X_re"]).astype(np.asarray(log_decay).dtype)
+    decay_rate = np.exp(np.asarray(log_decay))                    # :47
+    t_decay = np.asarray(dat["t_decay"], dtype=float)
+    X = sp.lil_matrix(X)
+    Xc = sp.csc_matrix(dat["X_re"])
+    for i_col, i_ind in zip(np.atleast_1d(dat["col_decay"]), np.atleast_1d(dat["ind_decay"])):
+        c, k = int(i_col) - 1, int(i_ind) - 1                     # :51-52
+        decay = np.exp(-decay_rate[k] * t_decay)                  # :53
+        col = Xc[:, c]
+        rows = col.indices
+        X[rows, c] = (np.asarray(col.data) * decay[rows]).reshape(-1, 1)      # :54-56
+    return sp.csr_matrix(X)
+
+
+def nllk_sde(dat, coeff_fe, log_lambda, coeff_re, type_=None, log_decay=None):
     type_ = type_ or dat["type"]
+    if has_decay(dat):
+        dat = dict(dat, X_re=decayed_X_re(dat, log_decay))
     ID = np.asarray(dat["ID"])
     times = np.asarray(dat["times"], dtype=float)
     obs = np.asarray(dat["obs"], dtype=float)
@@ -383,8 +414,8 @@ def nllk_sde(dat, coeff_fe, log_lambda, coeff_re, type_=None):
 def split_par(dat, par):
     """Flat joint parameter vector -> named pieces.
     CTCRW: [log_sigma_obs, coeff_fe, log_lambda, coeff_re]  (nllk_ctcrw.hpp:135-140)
-    BM/OU: [coeff_fe, log_lambda, coeff_re]  (nllk_sde.hpp:42-45; log_decay is mapped off
-    whenever no decay term exists, R/sde.R:648, and decay terms are out of scope)."""
+    BM/OU: [coeff_fe, log_lambda, (log_decay,) coeff_re]  (nllk_sde.hpp:42-45; log_decay is mapped
+    off whenever no decay term exists, R/sde.R:648, and then absent from the flat vector)."""
     par = np.asarray(par)
     p_fe = dat["X_fe"].shape[1]
     p_re = dat["X_re"].shape[1]
@@ -397,6 +428,9 @@ def split_par(dat, par):
         o = 1
     out["coeff_fe"] = par[o:o + p_fe]; o += p_fe
     out["log_lambda"] = par[o:o + n_s]; o += n_s
+    if dat["type"] not in KALMAN_TYPES and has_decay(dat):
+        nd_ = n_decay(dat)
+        out["log_decay"] = par[o:o + nd_]; o += nd_
     out["coeff_re"] = par[o:o + p_re]; o += p_re
     assert o == par.size, (o, par.size)
     return out
@@ -406,7 +440,7 @@ def nllk(dat, par):
     p = split_par(dat, par)
     t = dat["type"]
     if t in ("BM", "OU"):
-        return nllk_sde(dat, p["coeff_fe"], p["log_lambda"], p["coeff_re"], t)
+        return nllk_sde(dat, p["coeff_fe"], p["log_lambda"], p["coeff_re"], t, log_decay=p.get("log_decay"))
     if t == "CTCRW":
         return nllk_ctcrw(dat, p["log_sigma_obs"], p["coeff_fe"], p["log_lambda"], p["coeff_re"])
     if t in ("OU_SSM", "BM_SSM"):

@@ -490,6 +490,28 @@ SSDE_HD Adj<ND, R> bwd_apply(const BwdElem<ND, R>& E, const Adj<ND, R>& g) {
     return r;
 }
 
+// Chain rule from the adjoints of the step quantities (T12, T22 = e, B1, B2, Q11, Q12, Q22; Q12b
+// counts both off-diagonal entries) to the linear predictors eta_tau, eta_nu.
+template <class R>
+SSDE_HD void ctcrw_chain(const R& T12b, const R& T22b, const R& B1b, const R& B2b, const R& Q11b, const R& Q12b,
+                         const R& Q22b, const R& tau, const R& e, const R& s2, double dt, R& g_tau, R& g_nu) {
+    const R om = 1.0 - e, ome2 = 1.0 - e * e;
+    const R q1 = dt - 2.0 * tau * om + 0.5 * tau * ome2;
+    const R st = s2 * tau;
+    const R taub = (T12b - B1b) * om
+                        + Q11b * (2.0 * st * q1 + st * tau * (0.5 * ome2 - 2.0 * om))
+                        + Q12b * (st * om * om)
+                        + Q22b * (0.5 * s2 * ome2);
+    const R eb = (B1b - T12b) * tau + T22b - B2b
+                      + Q11b * (st * tau * tau * (2.0 - e))
+                      - Q12b * (st * tau * om)
+                      - Q22b * (st * e);
+    const R s2b = Q11b * (tau * tau * q1) + Q12b * (0.5 * tau * tau * om * om)
+                       + Q22b * (0.5 * tau * ome2);
+    g_tau = taub * tau + eb * e * dt / tau - s2b * s2;
+    g_nu = 2.0 * s2b * s2;
+}
+
 // Gradient of one row w.r.t. its linear predictors, given the adjoint `g` of the state this row
 // PREDICTS (row i+1's predicted state), the row's transformed parameters and its forward
 // intermediates.  Outputs: gmu[d] = d nllk / d eta_mu_d,  g_tau = d/d eta_tau,  g_nu = d/d eta_nu,
@@ -510,22 +532,8 @@ SSDE_HD void row_param_grad(const Adj<ND, R>& g, const StepParT<R>& sp, const St
     }
     T12b += 2.0 * (g.P.a * ax.tp12 + g.P.b * ax.tp22);
     T22b += 2.0 * (g.P.b * ax.tp12 + g.P.c * ax.tp22);
-    const R om = 1.0 - e, ome2 = 1.0 - e * e;
-    const R q1 = dt - 2.0 * tau * om + 0.5 * tau * ome2;
     const R Q11b = g.P.a, Q12b = 2.0 * g.P.b, Q22b = g.P.c;
-    const R st = s2 * tau;
-    const R taub = (T12b - B1b) * om
-                        + Q11b * (2.0 * st * q1 + st * tau * (0.5 * ome2 - 2.0 * om))
-                        + Q12b * (st * om * om)
-                        + Q22b * (0.5 * s2 * ome2);
-    const R eb = (B1b - T12b) * tau + T22b - B2b
-                      + Q11b * (st * tau * tau * (2.0 - e))
-                      - Q12b * (st * tau * om)
-                      - Q22b * (st * e);
-    const R s2b = Q11b * (tau * tau * q1) + Q12b * (0.5 * tau * tau * om * om)
-                       + Q22b * (0.5 * tau * ome2);
-    g_tau = taub * tau + eb * e * dt / tau - s2b * s2;
-    g_nu = 2.0 * s2b * s2;
+    ctcrw_chain(T12b, T22b, B1b, B2b, Q11b, Q12b, Q22b, tau, e, s2, dt, g_tau, g_nu);
     // update part (only h): hbar = G' Pf_bar G - sum_d w_d (af_bar_d' G) + Fl,
     // with af_bar_d = T' abar+_d and Pf_bar = T' Pbar+ T.
     g_h = 0.0;

@@ -32,7 +32,9 @@ struct KalmanArgs {
     const int64_t* track_starts;   // [n_tracks] sorted rows flagged ROW_START
     const double* a0;          // [n_tracks, M::SD]
     int n_tracks;
-    Sym2 P0;
+    PriorCov P0;
+    const double* Hrow;        // coupled models with a user H_array: [ND(ND+1)/2, n_pad] permuted planes of the
+                               // packed upper triangle of H_array[, , i] (else nullptr: H = sigma_obs^2 I)
     const double* par;         // device parameter vector; par[0] = log_sigma_obs
     const double* par_dot;     // R = Dual: direction in the parameter vector (else nullptr)
     const R* s_in;             // optional incoming state (M::FS scalars) for a continued shard
@@ -83,7 +85,7 @@ template <class M, int NT>
 struct FwdSmem {
     using R = typename M::R;
     static constexpr int NC = M::NC;             // step quantities per row (CTCRW: T12, e, Qa, Qb, Qc)
-    static constexpr int ES = 24 * ScalarOf<R>::NDBL;
+    static constexpr int ES = (M::FwdElem::NDBL > 24 * ScalarOf<R>::NDBL) ? M::FwdElem::NDBL : 24 * ScalarOf<R>::NDBL;
     R W[LC][NC][NT];
     double stage[NT / 32][STAGE_DBL];
     double wagg[2][NT / 32][ES];     // shared scratch is double-buffered by tile parity: the only
@@ -170,7 +172,7 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(KalmanArgs<typename
                 M::store_rowpar(rp, [&](int c) -> R& { return a.wg[(size_t)c * a.X.n_pad + pos]; });
                 const typename M::Step sp = M::make_step(rp, dtv);
                 M::store_step(sp, [&](int c) -> R& { return sm.W[k][c][tid]; });
-                M::fwd_append(E, sp, y, eta, (f & ROW_OBS) != 0, h);
+                M::fwd_append(E, sp, y, eta, (f & ROW_OBS) != 0, M::row_h(h, a.Hrow, a.X.n_pad, pos));
             } else if (live) {
                 M::fwd_append_start(E, track_start_state<M>(a, dtv));
             }
@@ -271,7 +273,7 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(KalmanArgs<typename
                 if (!mu0) row_eta_prefix<ND>(w, k, a.theta, mu);
                 const typename M::Step sp = M::load_step([&](int c) { return sm.W[k][c][tid]; }, dtv);
                 R F, qd;
-                M::template fwd_step<false>(s, sp, y, mu, (f & ROW_OBS) != 0, h, nullptr, F, qd);
+                M::template fwd_step<false>(s, sp, y, mu, (f & ROW_OBS) != 0, M::row_h(h, a.Hrow, a.X.n_pad, pos), nullptr, F, qd);
                 quad += qd;
                 fprod *= F;
                 if (!(value(fprod) > 1e-150 && value(fprod) < 1e150)) { slog += log(fprod); fprod = 1.0; }
@@ -280,7 +282,7 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(KalmanArgs<typename
                 M::store_mean(s, a.aest + (size_t)(row0 + k) * M::SD);
             }
         }
-        const double llk = warp_sum(value(-0.5 * ((double)ND * (slog + log(fprod)) + quad)));
+        const double llk = warp_sum(value(-0.5 * ((double)M::LOGF_MULT * (slog + log(fprod)) + quad)));
         if (lane == 0) a.tile_llk[q] = llk;              // one partial per warp-tile
 #ifdef SSDE_STATS
         if (lane == 0) {                                 // per-warp phase cycles: 4 + 4*warp-class (warp 0 / others)
@@ -305,7 +307,7 @@ struct BwdSmem {
     // per row: the forward state before the row (M::FS scalars), later overwritten by eta_bar
     // (slots 0..NP-1) and by the transposed-product scratch (slots NP..RS-1)
     static constexpr int RS = (M::FS > M::NP + 3) ? M::FS : M::NP + 3;
-    static constexpr int ES = 16 * ScalarOf<R>::NDBL;
+    static constexpr int ES = (M::BwdElem::NDBL > 16 * ScalarOf<R>::NDBL) ? M::BwdElem::NDBL : 16 * ScalarOf<R>::NDBL;
     R Rs[LC][RS][NT];
     double wagg[2][NT / 32][ES];
     double tagg[2][ES];
@@ -394,7 +396,7 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_bwd_kernel(KalmanArgs<typename
                 const typename M::Step sp = M::make_step(r.rp, r.dt);
                 typename M::Aux ax;
                 R F, qd;
-                M::template fwd_step<true>(s, sp, r.y, mu, (f & ROW_OBS) != 0, h, &ax, F, qd);
+                M::template fwd_step<true>(s, sp, r.y, mu, (f & ROW_OBS) != 0, M::row_h(h, a.Hrow, a.X.n_pad, base + k * 32), &ax, F, qd);
                 E = M::bwd_combine(E, M::bwd_row_elem(sp, ax, (f & ROW_OBS) != 0, (f & ROW_LAST) != 0));
             } else if (live) {
                 s = track_start_state<M>(a, r.dt);
@@ -485,10 +487,11 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_bwd_kernel(KalmanArgs<typename
                     const bool has = (f & ROW_OBS) != 0, cut = (f & ROW_LAST) != 0;
                     typename M::Aux ax;
                     R F, qd;
-                    M::template fwd_step<true>(sk, sp, r.y, mu, has, h, &ax, F, qd);
+                    const typename M::Hc hr = M::row_h(h, a.Hrow, a.X.n_pad, base + k * 32);
+                    M::template fwd_step<true>(sk, sp, r.y, mu, has, hr, &ax, F, qd);
                     const Ad gin = cut ? M::adj_zero() : g;
                     R g_h;
-                    M::row_param_grad(gin, sp, ax, mu, r.rp, r.dt, has, gp, g_h);
+                    M::row_param_grad(gin, sp, ax, mu, r.rp, r.dt, has, hr, gp, g_h);
                     gh += g_h;
                     g = M::bwd_apply(M::bwd_row_elem(sp, ax, has, cut), g);
                 }
@@ -549,7 +552,7 @@ __global__ void shard_elem_kernel(const double* __restrict__ incl_last, double* 
 }
 
 template <class M>
-__global__ void shard_state_kernel(const double* __restrict__ elems, int n_shards, int me, Sym2 P0,
+__global__ void shard_state_kernel(const double* __restrict__ elems, int n_shards, int me, PriorCov P0,
                                    typename M::R* __restrict__ s_out) {
     using R = typename M::R;
     using Elem = typename M::FwdElem;

@@ -20,8 +20,7 @@ namespace {
 
 thread_local std::string g_create_error;
 
-constexpr int FWD_NT = 128, FWD_MINB = 3;
-constexpr int BWD_NT = 128, BWD_MINB = 3;
+constexpr int FWD_NT = KNT_DEFAULT, BWD_NT = KNT_DEFAULT;   // decoupled models; the coupled ones use M::KNT = 64
 constexpr int PAD_ROWS = 1024;          // n_pad is a multiple of the largest tile (FWD_NT * LC)
 static_assert(PAD_ROWS % (FWD_NT * LC) == 0 && PAD_ROWS % (BWD_NT * LC) == 0 && PAD_ROWS % (SDE_NT * LC) == 0, "tiles must divide the padding unit");
 constexpr int RED_BLOCKS = 64;          // partial sums of the per-tile outputs
@@ -63,7 +62,9 @@ struct ssde_handle {
     int include_penalty = 1;
     int shard_flags = 0;
     int num_sms = 148;
-    Sym2 P0{1.0, 0.0, 10.0};
+    PriorCov P0{{1.0, 0.0, 10.0}, {0.0}};
+    bool dense = false;              // coupled filter (user H_array or a P0 that is not of the default shape)
+    DevBuf Hrow;                     // permuted planes of the packed H_array rows (dense && user H only)
     // design + data
     DevBuf desc, col, val, obs, dt, flags, track_starts, a0;
     DevBuf mu_cols, mu_zero;         // theta entries that feed the mu_d predictors; device flag "all of them are 0"
@@ -559,9 +560,15 @@ template <class R, class Fn>
 int with_kalman_model(const ssde_handle* h, Fn&& fn) {
     const int nd = h->n_dim;
     switch (h->model) {
-        case SSDE_CTCRW: return nd == 1 ? fn(CtcrwModel<1, R>{}) : fn(CtcrwModel<2, R>{});
-        case SSDE_OU_SSM: return nd == 1 ? fn(OuSsmModel<1, R>{}) : fn(OuSsmModel<2, R>{});
-        case SSDE_BM_SSM: return nd == 1 ? fn(BmSsmModel<1, R>{}) : (nd == 2 ? fn(BmSsmModel<2, R>{}) : fn(BmSsmModel<3, R>{}));
+        case SSDE_CTCRW:
+            if (h->dense) return nd == 1 ? fn(DenseModel<CtcrwModel<1, R>>{}) : fn(DenseModel<CtcrwModel<2, R>>{});
+            return nd == 1 ? fn(CtcrwModel<1, R>{}) : fn(CtcrwModel<2, R>{});
+        case SSDE_OU_SSM:
+            if (h->dense) return nd == 1 ? fn(DenseModel<OuSsmModel<1, R>>{}) : fn(DenseModel<OuSsmModel<2, R>>{});
+            return nd == 1 ? fn(OuSsmModel<1, R>{}) : fn(OuSsmModel<2, R>{});
+        case SSDE_BM_SSM:
+            if (h->dense) return nd == 1 ? fn(DenseModel<BmSsmModel<1, R>>{}) : (nd == 2 ? fn(DenseModel<BmSsmModel<2, R>>{}) : fn(DenseModel<BmSsmModel<3, R>>{}));
+            return nd == 1 ? fn(BmSsmModel<1, R>{}) : (nd == 2 ? fn(BmSsmModel<2, R>{}) : fn(BmSsmModel<3, R>{}));
     }
     return SSDE_ERR_UNSUPPORTED;
 }
@@ -570,8 +577,8 @@ template <class M>
 int ctcrw_grids(ssde_handle* h) {
     std::string& err = h->err;
     int rc;
-    if ((rc = max_grid(ctcrw_fwd_kernel<M, FWD_NT, FWD_MINB>, FWD_NT, sizeof(FwdSmem<M, FWD_NT>), h->num_sms, err, h->grid_f))) return rc;
-    if ((rc = max_grid(ctcrw_bwd_kernel<M, BWD_NT, BWD_MINB>, BWD_NT, sizeof(BwdSmem<M, BWD_NT>), h->num_sms, err, h->grid_b))) return rc;
+    if ((rc = max_grid(ctcrw_fwd_kernel<M, M::KNT, M::MINB>, M::KNT, sizeof(FwdSmem<M, M::KNT>), h->num_sms, err, h->grid_f))) return rc;
+    if ((rc = max_grid(ctcrw_bwd_kernel<M, M::KNT, M::MINB>, M::KNT, sizeof(BwdSmem<M, M::KNT>), h->num_sms, err, h->grid_b))) return rc;
     return SSDE_OK;
 }
 
@@ -611,12 +618,11 @@ int finish_setup(ssde_handle* h) {
     CUDA_TRY(cudaMemset(h->counters.p, 0, 4 * sizeof(unsigned)));
     CUDA_TRY(cudaMallocHost(&h->h_pinned, sizeof(double) * (2 * (size_t)h->npar + 4)));
     if (is_kalman(h->model)) {
-        h->ntiles_f = (int)(h->n_pad / (FWD_NT * LC));
-        h->ntiles_b = (int)(h->n_pad / (BWD_NT * LC));
         h->nchunks = h->n_pad / LC;
         rc = with_kalman_model<double>(h, [&](auto m) -> int {
             using M = decltype(m);
             int rc;
+            h->ntiles_f = h->ntiles_b = (int)(h->n_pad / (M::KNT * LC));
             h->fs = M::FS; h->fwd_elem = M::FwdElem::NDBL; h->bwd_elem = M::BwdElem::NDBL;
             if ((rc = dev_alloc<double>(h->ckpt, (size_t)h->nchunks * M::FS, err))) return rc;
             if ((rc = dev_alloc<double>(h->wg, (size_t)h->n_pad * M::NW, err))) return rc;
@@ -685,7 +691,7 @@ KalmanArgs<R> ctcrw_args(ssde_handle* h, const double* d_par, const double* d_di
     a.theta = Theta{h->theta.as<double>(), TAN ? h->t_theta_dot.as<double>() : nullptr};
     a.obs = h->obs.as<double>(); a.dt = h->dt.as<double>(); a.flags = h->flags.as<uint8_t>();
     a.track_starts = h->track_starts.as<int64_t>(); a.a0 = h->a0.as<double>(); a.n_tracks = h->n_tracks;
-    a.P0 = h->P0; a.par = d_par; a.par_dot = TAN ? d_dir : nullptr;
+    a.P0 = h->P0; a.Hrow = h->Hrow.as<double>(); a.par = d_par; a.par_dot = TAN ? d_dir : nullptr;
     a.s_in = h->have_s_in ? h->s_in.as<R>() : nullptr;
     a.g_in = h->have_g_in ? h->g_in.as<R>() : nullptr;
     a.mu_zero = h->mu_zero.as<int>();
@@ -734,8 +740,8 @@ int launch_ctcrw_fwd(ssde_handle* h, const double* d_par, const double* d_dir, c
     a.summary = summary ? 1 : 0;
     a.tile_lo = (summary && tail) ? std::max(h->ntiles_f - TAIL_TILES, 0) : 0;
     mark(h, st, TAN ? "ctcrw_fwd_tangent" : (summary ? (tail ? "ctcrw_fwd_tail" : "ctcrw_fwd_summary") : "ctcrw_fwd"));
-    if constexpr (TAN) ctcrw_fwd_kernel<M, FWD_NT, TAN_MINB><<<h->grid_f2, FWD_NT, sizeof(FwdSmem<M, FWD_NT>), st>>>(a);
-    else ctcrw_fwd_kernel<M, FWD_NT, FWD_MINB><<<h->grid_f, FWD_NT, sizeof(FwdSmem<M, FWD_NT>), st>>>(a);
+    if constexpr (TAN) ctcrw_fwd_kernel<M, M::KNT, TAN_MINB><<<h->grid_f2, M::KNT, sizeof(FwdSmem<M, M::KNT>), st>>>(a);
+    else ctcrw_fwd_kernel<M, M::KNT, M::MINB><<<h->grid_f, M::KNT, sizeof(FwdSmem<M, M::KNT>), st>>>(a);
     CUDA_TRY(cudaGetLastError());
     return SSDE_OK;
 }
@@ -752,8 +758,8 @@ int launch_ctcrw_bwd(ssde_handle* h, const double* d_par, const double* d_dir, c
     a.summary = summary ? 1 : 0;
     a.tile_lo = (summary && tail) ? std::max(h->ntiles_b - TAIL_TILES, 0) : 0;
     mark(h, st, TAN ? "ctcrw_bwd_tangent" : (summary ? (tail ? "ctcrw_bwd_tail" : "ctcrw_bwd_summary") : "ctcrw_bwd"));
-    if constexpr (TAN) ctcrw_bwd_kernel<M, BWD_NT, TAN_MINB><<<h->grid_b2, BWD_NT, sizeof(BwdSmem<M, BWD_NT>), st>>>(a);
-    else ctcrw_bwd_kernel<M, BWD_NT, BWD_MINB><<<h->grid_b, BWD_NT, sizeof(BwdSmem<M, BWD_NT>), st>>>(a);
+    if constexpr (TAN) ctcrw_bwd_kernel<M, M::KNT, TAN_MINB><<<h->grid_b2, M::KNT, sizeof(BwdSmem<M, M::KNT>), st>>>(a);
+    else ctcrw_bwd_kernel<M, M::KNT, M::MINB><<<h->grid_b, M::KNT, sizeof(BwdSmem<M, M::KNT>), st>>>(a);
     CUDA_TRY(cudaGetLastError());
     return SSDE_OK;
 }
@@ -882,8 +888,8 @@ template <class M>
 int ctcrw_tan_grids(ssde_handle* h) {
     std::string& err = h->err;
     int rc;
-    if ((rc = max_grid(ctcrw_fwd_kernel<M, FWD_NT, TAN_MINB>, FWD_NT, sizeof(FwdSmem<M, FWD_NT>), h->num_sms, err, h->grid_f2))) return rc;
-    if ((rc = max_grid(ctcrw_bwd_kernel<M, BWD_NT, TAN_MINB>, BWD_NT, sizeof(BwdSmem<M, BWD_NT>), h->num_sms, err, h->grid_b2))) return rc;
+    if ((rc = max_grid(ctcrw_fwd_kernel<M, M::KNT, TAN_MINB>, M::KNT, sizeof(FwdSmem<M, M::KNT>), h->num_sms, err, h->grid_f2))) return rc;
+    if ((rc = max_grid(ctcrw_bwd_kernel<M, M::KNT, TAN_MINB>, M::KNT, sizeof(BwdSmem<M, M::KNT>), h->num_sms, err, h->grid_b2))) return rc;
     return SSDE_OK;
 }
 template <int MODEL, int ND>
@@ -1054,7 +1060,9 @@ int ssde_create(const ssde_desc* d, ssde_handle** out) {
     const int64_t n = d->n;
     if (n < 1 || !d->ID || !d->times || !d->obs) { err = "ID, times and obs are required"; return SSDE_ERR_BAD_ARG; }
     if (d->X_fe.nrow != n_par * n || d->X_re.nrow != n_par * n) { err = "X_fe / X_re must have n_par * n rows"; return SSDE_ERR_BAD_ARG; }
-    if (d->H_array && d->H_len > 1) { err = "user-supplied H_array (coupled filter) is not built yet"; return SSDE_ERR_UNSUPPORTED; }
+    const bool user_H = d->H_array && d->H_len > 1;            // H_array.size() > 1, nllk_ctcrw.hpp:203
+    if (user_H && !is_kalman(d->model)) { err = "H_array exists for the Kalman models only"; return SSDE_ERR_BAD_ARG; }
+    if (user_H && d->H_len != (int64_t)d->n_dim * d->n_dim * d->n) { err = "H_array must be n_dim x n_dim x n"; return SSDE_ERR_BAD_ARG; }
     if (!is_kalman(d->model) && (d->shard_flags & (SSDE_SHARD_CONT_PREV | SSDE_SHARD_CONT_NEXT))) {
         err = "BM / OU shards must hold whole tracks (time-sharding exists for the Kalman models only)";
         return SSDE_ERR_UNSUPPORTED;
@@ -1099,28 +1107,43 @@ int ssde_create(const ssde_desc* d, ssde_handle** out) {
         if (!d->a0 || !d->P0) { err = "the Kalman models need a0 and P0"; return fail(SSDE_ERR_BAD_ARG); }
         if (d->n_ID != (int)starts.size()) { err = "nrow(a0) != number of tracks starting on this shard"; return fail(SSDE_ERR_BAD_ARG); }
         const int m = state_means(d->model, nd);
+        // default-shaped P0 (CTCRW: block-diagonal with identical 2x2 blocks, R/sde.R:584; SSM: c I,
+        // R/sde.R:553) and H = sigma_obs^2 I: the dimensions decouple.  Anything else runs the
+        // coupled filter (dense_math.cuh).
+        bool shaped = true;
         if (d->model == SSDE_CTCRW) {
             const double p11 = d->P0[0], p12 = d->P0[(size_t)1 * m + 0], p22 = d->P0[(size_t)1 * m + 1];
             for (int r = 0; r < m; ++r)
                 for (int c = 0; c < m; ++c) {
                     double want = 0.0;
                     if (r / 2 == c / 2) want = (r % 2 == 0 && c % 2 == 0) ? p11 : ((r % 2 == 1 && c % 2 == 1) ? p22 : p12);
-                    if (d->P0[(size_t)c * m + r] != want) {
-                        err = "P0 must be block-diagonal with identical 2x2 blocks (coupled filter not built yet)";
-                        return fail(SSDE_ERR_UNSUPPORTED);
-                    }
+                    if (d->P0[(size_t)c * m + r] != want) shaped = false;
                 }
-            h->P0 = {p11, p12, p22};
+            h->P0.blk = {p11, p12, p22};
         } else {
-            // BM_SSM / OU_SSM: P0 = c I (default diag(rep(10, n_dim)), R/sde.R:553)
             const double c0 = d->P0[0];
             for (int r = 0; r < m; ++r)
                 for (int c = 0; c < m; ++c)
-                    if (d->P0[(size_t)c * m + r] != (r == c ? c0 : 0.0)) {
-                        err = "P0 must be a multiple of the identity (coupled filter not built yet)";
-                        return fail(SSDE_ERR_UNSUPPORTED);
-                    }
-            h->P0 = {c0, 0.0, c0};
+                    if (d->P0[(size_t)c * m + r] != (r == c ? c0 : 0.0)) shaped = false;
+            h->P0.blk = {c0, 0.0, c0};
+        }
+        for (int r = 0; r < m; ++r)
+            for (int c = r; c < m; ++c) {
+                if (d->P0[(size_t)c * m + r] != d->P0[(size_t)r * m + c]) { err = "P0 must be symmetric"; return fail(SSDE_ERR_BAD_ARG); }
+                h->P0.dense[r * m - r * (r - 1) / 2 + (c - r)] = d->P0[(size_t)c * m + r];
+            }
+        h->dense = user_H || !shaped;
+        if (user_H) {
+            // H_array[, , i] is column-major n_dim x n_dim; keep the packed upper triangle as permuted planes
+            const int nh = nd * (nd + 1) / 2;
+            std::vector<double> Hp((size_t)n_pad * nh, 0.0);
+            for (int64_t i = 0; i < n; ++i) {
+                const double* Hi = d->H_array + (size_t)i * nd * nd;
+                int k = 0;
+                for (int r = 0; r < nd; ++r)
+                    for (int c = r; c < nd; ++c, ++k) Hp[(size_t)k * n_pad + row_pos(i)] = 0.5 * (Hi[(size_t)c * nd + r] + Hi[(size_t)r * nd + c]);
+            }
+            if ((rc = dev_upload(h->Hrow, Hp, h->err))) return fail(rc);
         }
         std::vector<double> a0((size_t)starts.size() * m);
         for (size_t k = 0; k < starts.size(); ++k)
@@ -1183,7 +1206,7 @@ int ssde_create_packed(const ssde_packed_desc* d, ssde_handle** out) {
     h->desc.p = (void*)d->d_desc; h->col.p = (void*)d->d_col; h->val.p = (void*)d->d_val;
     h->obs.p = (void*)d->d_obs; h->dt.p = (void*)d->d_dt; h->flags.p = (void*)d->d_flags;
     h->n_tracks = d->n_ID;
-    h->P0 = {d->P0[0], d->P0[1], d->P0[2]};
+    h->P0.blk = {d->P0[0], d->P0[1], d->P0[2]};
     if (d->mu_cols && d->n_mu_cols >= 0) {
         std::vector<int32_t> mc(d->mu_cols, d->mu_cols + d->n_mu_cols);
         h->n_mu_cols = d->n_mu_cols;

@@ -83,6 +83,9 @@ def shard_rows(dat, lo, hi):
         b = track_bounds(ID)[:-1]
         a0 = np.asarray(dat["a0"], dtype=float).reshape(b.size, -1)
         sub["a0"] = a0[(b >= lo) & (b < hi)]
+        H = dat.get("H_array")
+        if H is not None and np.size(H) > 1:         # user measurement covariances follow their rows
+            sub["H_array"] = np.asarray(H, dtype=float)[:, :, lo:hi]
     t_next = float(np.asarray(dat["times"])[hi]) if cont_next else 0.0
     return sub, bool(cont_prev), bool(cont_next), t_next
 

@@ -54,24 +54,33 @@ static std::vector<Row<M>> build_rows(int64_t n, const uint8_t* flags, const dou
 }
 
 template <class M>
-static typename M::State start_state(const double* a0, const double* P0, int track) {
-    return M::start_state(a0 + (size_t)track * M::SD, Sym2{P0[0], P0[1], P0[2]});
+static typename M::State start_state(const double* a0, const PriorCov& P0, int track) {
+    return M::start_state(a0 + (size_t)track * M::SD, P0);
+}
+static PriorCov prior_blk(const double* P0) {
+    PriorCov pc{};
+    pc.blk = Sym2{P0[0], P0[1], P0[2]};
+    return pc;
 }
 
 // mode 0: plain sequential filter + sequential adjoint.
 // mode 1: emulated chunked scan (lc rows per thread, nt threads per tile).
 template <class M>
 static int run(int mode, int64_t n, const uint8_t* flags, const double* y, const double* dt,
-               const double* eta, const double* eta_dot, const double* a0, const double* P0, typename M::R h, int lc, int nt,
-               double* out_llk, double* eta_bar, double* eta_bar_dot, double* out_gh, double* aest) {
+               const double* eta, const double* eta_dot, const double* a0, const PriorCov& P0, typename M::R h, int lc, int nt,
+               double* out_llk, double* eta_bar, double* eta_bar_dot, double* out_gh, double* aest,
+               const double* Hplanes = nullptr) {
     using R = typename M::R;
     constexpr int ND = M::ND, NP = M::NP;
     auto rows = build_rows<M>(n, flags, y, dt, eta, eta_dot);
+    // measurement covariance of row i (Hplanes: [ND(ND+1)/2][n] packed upper triangles, coupled models only)
+    auto hrow = [&](int64_t i) { return M::row_h(h, Hplanes, (size_t)n, i); };
     auto step_llk = [&](typename M::State& s, const Row<M>& r, typename M::Aux* ax) -> R {
         R F, quad;
-        if (ax) M::template fwd_step<true>(s, r.sp, r.y, r.mu, r.obs, h, ax, F, quad);
-        else M::template fwd_step<false>(s, r.sp, r.y, r.mu, r.obs, h, nullptr, F, quad);
-        return r.obs ? R(-0.5 * ((double)ND * log(F) + quad)) : R(0.0);
+        const int64_t i = &r - rows.data();
+        if (ax) M::template fwd_step<true>(s, r.sp, r.y, r.mu, r.obs, hrow(i), ax, F, quad);
+        else M::template fwd_step<false>(s, r.sp, r.y, r.mu, r.obs, hrow(i), nullptr, F, quad);
+        return r.obs ? R(-0.5 * ((double)M::LOGF_MULT * log(F) + quad)) : R(0.0);
     };
     std::vector<typename M::State> pre(n);       // predicted state of each row (state BEFORE the row)
     R llk = 0.0;
@@ -90,7 +99,7 @@ static int run(int mode, int64_t n, const uint8_t* flags, const double* y, const
             typename M::FwdElem E = M::fwd_identity();
             for (int64_t i = c * chunk; i < (c + 1) * chunk && i < n; ++i) {
                 if (rows[i].start) M::fwd_append_start(E, start_state<M>(a0, P0, rows[i].track));
-                else M::fwd_append(E, rows[i].sp, rows[i].y, rows[i].mu, rows[i].obs, h);
+                else M::fwd_append(E, rows[i].sp, rows[i].y, rows[i].mu, rows[i].obs, hrow(i));
             }
             agg[c] = E;
         }
@@ -142,7 +151,7 @@ static int run(int mode, int64_t n, const uint8_t* flags, const double* y, const
         const typename M::Adj gin = r.last ? M::adj_zero() : g;
         R gp[NP], g_h;
         for (int c = 0; c < NP; ++c) gp[c] = 0.0;
-        M::row_param_grad(gin, r.sp, ax, r.mu, r.rp, r.dt, r.obs, gp, g_h);
+        M::row_param_grad(gin, r.sp, ax, r.mu, r.rp, r.dt, r.obs, hrow(i), gp, g_h);
         for (int c = 0; c < NP; ++c) put(i, c, gp[c]);
         gh += g_h;
         g = M::bwd_apply(M::bwd_row_elem(r.sp, ax, r.obs, r.last), g);
@@ -207,7 +216,7 @@ extern "C" int harness_kalman(int model, int nd, int mode, int64_t n, const uint
                               double* eta_bar, double* out_gh, double* aest) {
     double llk2[2] = {0, 0}, gh2[2] = {0, 0};
     int rc = with_model<double>(model, nd, [&](auto m) {
-        return run<decltype(m)>(mode, n, flags, y, dt, eta, nullptr, a0, P0, h, lc, nt, llk2, eta_bar, nullptr, gh2, aest);
+        return run<decltype(m)>(mode, n, flags, y, dt, eta, nullptr, a0, prior_blk(P0), h, lc, nt, llk2, eta_bar, nullptr, gh2, aest);
     });
     *out_llk = llk2[0];
     if (out_gh) *out_gh = gh2[0];
@@ -228,7 +237,7 @@ extern "C" int harness_kalman_tangent(int model, int nd, int mode, int64_t n, co
                                       double* out_gh2) {
     const Dual hh(h, h_dot);
     return with_model<Dual>(model, nd, [&](auto m) {
-        return run<decltype(m)>(mode, n, flags, y, dt, eta, eta_dot, a0, P0, hh, lc, nt, out_llk2, eta_bar, eta_bar_dot, out_gh2, nullptr);
+        return run<decltype(m)>(mode, n, flags, y, dt, eta, eta_dot, a0, prior_blk(P0), hh, lc, nt, out_llk2, eta_bar, eta_bar_dot, out_gh2, nullptr);
     });
 }
 extern "C" int harness_ctcrw_tangent(int nd, int mode, int64_t n, const uint8_t* flags, const double* y,
@@ -238,4 +247,35 @@ extern "C" int harness_ctcrw_tangent(int nd, int mode, int64_t n, const uint8_t*
                                      double* out_gh2) {
     return harness_kalman_tangent(0, nd, mode, n, flags, y, dt, eta, eta_dot, a0, P0, h, h_dot, lc, nt, out_llk2, eta_bar,
                                   eta_bar_dot, out_gh2);
+}
+
+// Coupled filter (DenseModel, dense_math.cuh): P0 is the full SD x SD matrix (row-major, symmetric),
+// Hplanes == nullptr -> H = h I, else [ND(ND+1)/2][n] packed upper triangles of the rows' H.
+template <class R, class Fn>
+static int with_dense_model(int model, int nd, Fn fn) {
+    if (model == 0) { if (nd == 1) return fn(DenseModel<CtcrwModel<1, R>>{}); if (nd == 2) return fn(DenseModel<CtcrwModel<2, R>>{}); }
+    if (model == 1) { if (nd == 1) return fn(DenseModel<OuSsmModel<1, R>>{}); if (nd == 2) return fn(DenseModel<OuSsmModel<2, R>>{}); }
+    if (model == 2) { if (nd == 1) return fn(DenseModel<BmSsmModel<1, R>>{}); if (nd == 2) return fn(DenseModel<BmSsmModel<2, R>>{}); if (nd == 3) return fn(DenseModel<BmSsmModel<3, R>>{}); }
+    return 1;
+}
+static PriorCov prior_dense(const double* P0, int m) {
+    PriorCov pc{};
+    for (int r = 0; r < m; ++r)
+        for (int c = r; c < m; ++c) pc.dense[r * m - r * (r - 1) / 2 + (c - r)] = P0[r * m + c];
+    return pc;
+}
+extern "C" int harness_dense(int model, int nd, int mode, int64_t n, const uint8_t* flags, const double* y,
+                             const double* dt, const double* eta, const double* eta_dot, const double* a0,
+                             const double* P0, int m, const double* Hplanes, double h, double h_dot, int lc, int nt,
+                             double* out_llk2, double* eta_bar, double* eta_bar_dot, double* out_gh2, double* aest) {
+    const PriorCov pc = prior_dense(P0, m);
+    if (eta_dot) {
+        const Dual hh(h, h_dot);
+        return with_dense_model<Dual>(model, nd, [&](auto mm) {
+            return run<decltype(mm)>(mode, n, flags, y, dt, eta, eta_dot, a0, pc, hh, lc, nt, out_llk2, eta_bar, eta_bar_dot, out_gh2, aest, Hplanes);
+        });
+    }
+    return with_dense_model<double>(model, nd, [&](auto mm) {
+        return run<decltype(mm)>(mode, n, flags, y, dt, eta, nullptr, a0, pc, h, lc, nt, out_llk2, eta_bar, nullptr, out_gh2, aest, Hplanes);
+    });
 }

@@ -20,7 +20,7 @@ def build_harness():
     out_dir = os.path.join(HERE, "harness", "_build")
     os.makedirs(out_dir, exist_ok=True)
     out = os.path.join(out_dir, "libmath_harness.so")
-    hdrs = [os.path.join(ROOT, "smoothsde_b200", "csrc", f) for f in ("ctcrw_math.cuh", "dual.cuh", "ssm1_math.cuh", "models.cuh")]
+    hdrs = [os.path.join(ROOT, "smoothsde_b200", "csrc", f) for f in ("ctcrw_math.cuh", "dual.cuh", "ssm1_math.cuh", "models.cuh", "dense_math.cuh")]
     if (not os.path.exists(out)) or os.path.getmtime(out) < max([os.path.getmtime(src)] + [os.path.getmtime(f) for f in hdrs]):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++", "-o", out, src])
     return ctypes.CDLL(out)
@@ -123,3 +123,44 @@ def harness_kalman(lib, dat, eta, log_sigma_obs, mode, lc=8, nt=128):
                             ctypes.byref(llk), _P(eb), ctypes.byref(gh), None)
     assert rc == 0
     return llk.value, eb, gh.value * 2 * h
+
+
+def pack_H_planes(H_array):
+    """H_array [d, d, n] -> [d(d+1)/2, n] planes of the packed upper triangles (row-major order)."""
+    Ha = np.asarray(H_array, dtype=float)
+    d = Ha.shape[0]
+    return np.ascontiguousarray(np.stack([0.5 * (Ha[r, c] + Ha[c, r]) for r in range(d) for c in range(r, d)]))
+
+
+def harness_dense(lib, dat, eta, log_sigma_obs, mode, lc=8, nt=64, eta_dot=None, lso_dot=0.0, want_aest=False):
+    """Coupled filter (DenseModel in models.cuh) through the host-compiled algebra.  Uses dat["P0"]
+    as a full matrix and dat.get("H_array").  Returns (llk, eta_bar, d nllk / d log_sigma_obs, aest)
+    or, with eta_dot, ((llk, dllk), (eta_bar, eta_bar_dot), (g_lso, g_lso_dot))."""
+    obs = np.asarray(dat["obs"], dtype=float)
+    n, nd = obs.shape
+    flags = row_flags(dat["ID"], obs)
+    dt = ctcrw_dt(dat["times"], flags)
+    eta = np.ascontiguousarray(eta, dtype=float)
+    y = np.ascontiguousarray(np.nan_to_num(obs))
+    a0 = np.ascontiguousarray(dat["a0"], dtype=float)
+    P0 = np.ascontiguousarray(dat["P0"], dtype=float)
+    m = P0.shape[0]
+    Hp = None
+    if dat.get("H_array") is not None and np.size(dat["H_array"]) > 1:
+        Hp = pack_H_planes(dat["H_array"])
+    h = float(np.exp(2 * log_sigma_obs))
+    h_dot = 2 * h * lso_dot
+    llk2, gh2 = np.zeros(2), np.zeros(2)
+    eb = np.zeros(eta.shape)
+    ebd = np.zeros(eta.shape) if eta_dot is not None else None
+    aest = np.zeros((n, m)) if want_aest else None
+    ed = np.ascontiguousarray(eta_dot, dtype=float) if eta_dot is not None else None
+    rc = lib.harness_dense(MODEL_IDS[dat["type"]], nd, mode, ctypes.c_int64(n),
+                           flags.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), _P(y), _P(dt), _P(eta),
+                           _P(ed) if ed is not None else None, _P(a0), _P(P0), m, _P(Hp) if Hp is not None else None,
+                           ctypes.c_double(h), ctypes.c_double(h_dot), lc, nt, _P(llk2), _P(eb),
+                           _P(ebd) if ebd is not None else None, _P(gh2), _P(aest) if want_aest else None)
+    assert rc == 0
+    if eta_dot is None:
+        return llk2[0], eb, gh2[0] * 2 * h, aest
+    return llk2, (eb, ebd), (2 * h * gh2[0], 2 * (h_dot * gh2[0] + h * gh2[1]))
