@@ -95,6 +95,14 @@ typedef struct {
     int32_t device;           /* CUDA device ordinal */
     int32_t shard_flags;      /* enum ssde_shard_flags */
     double t_next;            /* time of the next shard's first row (only with CONT_NEXT) */
+    /* decay terms of nllk_sde (BM / OU), nllk_sde.hpp:31-33,47-59, R/sde.R:162-177,636-648: column
+     * col_decay[i] (1-based) of X_re is multiplied, row by row, by exp(-exp(log_decay[ind_decay[i]]) * t_decay).
+     * t_decay = NULL or t_decay_len <= 1: no decay term (R passes t_decay = 0 and maps log_decay off). */
+    const double* t_decay;    /* [n_par * n], one entry per row of X_re */
+    int64_t t_decay_len;
+    const int32_t* col_decay; /* [n_col_decay] */
+    const int32_t* ind_decay; /* [n_col_decay], values 1 .. n_decay (n_decay <= 16) */
+    int32_t n_col_decay;
 } ssde_desc;
 
 /* Zero-copy variant for data that already lives on the GPU in the engine's native "warp-tile
@@ -160,11 +168,14 @@ void ssde_destroy(ssde_handle* h);
 /* Length of the joint parameter vector and its layout (PARAMETER order of the templates):
  *   CTCRW : log_sigma_obs, coeff_fe[p_fe], log_lambda[n_smooth], coeff_re[p_re]
  *           (nllk_ctcrw.hpp:135-140)
- *   BM/OU : coeff_fe[p_fe], log_lambda[n_smooth], coeff_re[p_re]
- *           (nllk_sde.hpp:42-45; log_decay is mapped off without decay terms, R/sde.R:648)
- * offsets[4] = {log_sigma_obs (or -1), coeff_fe, log_lambda, coeff_re}. */
+ *   BM/OU : coeff_fe[p_fe], log_lambda[n_smooth], log_decay[n_decay], coeff_re[p_re]
+ *           (nllk_sde.hpp:42-45; without decay terms log_decay is mapped off, R/sde.R:648, and
+ *           n_decay = 0)
+ * offsets[4] = {log_sigma_obs (or -1), coeff_fe, log_lambda, coeff_re};
+ * ssde_decay_layout: offset (or -1) and length of log_decay. */
 int ssde_n_par(const ssde_handle* h);
 int ssde_par_layout(const ssde_handle* h, int32_t offsets[4], int32_t sizes[4]);
+int ssde_decay_layout(const ssde_handle* h, int32_t* offset, int32_t* size);
 
 /* One objective evaluation with HOST buffers (what obj$fn / obj$gr / obj$he do through
  * EvalADFunObject and the MakeADHessObject2 tape).

@@ -3,9 +3,11 @@
 # The Python mirror of this file (smoothsde_b200/adfun.py) is what the automated tests exercise.
 MakeADFun_b200 <- function(data, parameters, map = list(), random = NULL, device = 0L, ...) {
     ptr <- .Call("ssde_make", data, as.integer(device))
-    lay <- .Call("ssde_layout", ptr)                  # offsets[4], sizes[4]
-    full <- unlist(parameters[c("log_sigma_obs", "coeff_fe", "log_lambda", "coeff_re")])
-    names(full) <- rep(c("log_sigma_obs", "coeff_fe", "log_lambda", "coeff_re"), lay[5:8])
+    lay <- .Call("ssde_layout", ptr)                  # offsets[5], sizes[5]
+    pnames <- c("log_sigma_obs", "coeff_fe", "log_lambda", "log_decay", "coeff_re")
+    # log_decay is in the list for BM/OU (R/sde.R:504-507) but only enters the vector with decay terms
+    full <- unlist(lapply(seq_along(pnames), function(k) if(lay[5 + k] > 0) parameters[[pnames[k]]] else NULL))
+    names(full) <- rep(pnames, lay[6:10])
     # map: factor(NA) fixes an entry, equal levels tie entries together (TMB semantics)
     group <- seq_along(full)
     for(nm in names(map)) {

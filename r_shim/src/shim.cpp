@@ -45,6 +45,8 @@ int model_of(const char* type) {
     if (!strcmp(type, "BM")) return SSDE_BM;
     if (!strcmp(type, "OU")) return SSDE_OU;
     if (!strcmp(type, "CTCRW")) return SSDE_CTCRW;
+    if (!strcmp(type, "BM_SSM")) return SSDE_BM_SSM;
+    if (!strcmp(type, "OU_SSM")) return SSDE_OU_SSM;
     return -1;          // ssde_create answers SSDE_ERR_UNKNOWN_TYPE: "Unknown SDE type" (smoothSDE.cpp:25)
 }
 
@@ -81,10 +83,18 @@ SEXP ssde_make(SEXP data, SEXP device) {
         SEXP H = list_get(data, "H_array");
         if (H != R_NilValue && Rf_xlength(H) > 1) { d.H_array = REAL(H); d.H_len = Rf_xlength(H); }
     }
+    // decay terms (nllk_sde.hpp:31-33): R passes t_decay = col_decay = ind_decay = 0 when there are none (R/sde.R:645-647)
+    SEXP td = list_get(data, "t_decay");
+    SEXP cd = PROTECT(Rf_coerceVector(td != R_NilValue ? list_get(data, "col_decay") : Rf_ScalarInteger(0), INTSXP));
+    SEXP id_ = PROTECT(Rf_coerceVector(td != R_NilValue ? list_get(data, "ind_decay") : Rf_ScalarInteger(0), INTSXP));
+    if (td != R_NilValue && Rf_xlength(td) > 1) {
+        d.t_decay = REAL(td); d.t_decay_len = Rf_xlength(td);
+        d.col_decay = INTEGER(cd); d.ind_decay = INTEGER(id_); d.n_col_decay = (int32_t)Rf_xlength(cd);
+    }
     d.device = Rf_asInteger(device);
     ssde_handle* h = NULL;
     int rc = ssde_create(&d, &h);
-    UNPROTECT(2);
+    UNPROTECT(4);
     if (rc != SSDE_OK) Rf_error("smoothsde_b200: %s", ssde_create_error());
     SEXP ptr = PROTECT(R_MakeExternalPtr(h, R_NilValue, R_NilValue));
     R_RegisterCFinalizerEx(ptr, finalizer, TRUE);
@@ -113,11 +123,17 @@ SEXP ssde_fn_gr(SEXP ptr, SEXP par, SEXP order) {
     return out;
 }
 
-// offsets / sizes of log_sigma_obs, coeff_fe, log_lambda, coeff_re in the full vector
+// offsets[5] / sizes[5] of log_sigma_obs, coeff_fe, log_lambda, log_decay, coeff_re in the full
+// vector (the PARAMETER order of the templates, nllk_ctcrw.hpp:135-140 / nllk_sde.hpp:42-45)
 SEXP ssde_layout(SEXP ptr) {
     ssde_handle* h = (ssde_handle*)R_ExternalPtrAddr(ptr);
-    SEXP out = PROTECT(Rf_allocVector(INTSXP, 8));
-    ssde_par_layout(h, INTEGER(out), INTEGER(out) + 4);
+    SEXP out = PROTECT(Rf_allocVector(INTSXP, 10));
+    int32_t off[4], siz[4], od = -1, nd = 0;
+    ssde_par_layout(h, off, siz);
+    ssde_decay_layout(h, &od, &nd);
+    int* o = INTEGER(out);
+    o[0] = off[0]; o[1] = off[1]; o[2] = off[2]; o[3] = od; o[4] = off[3];
+    o[5] = siz[0]; o[6] = siz[1]; o[7] = siz[2]; o[8] = nd; o[9] = siz[3];
     UNPROTECT(1);
     return out;
 }

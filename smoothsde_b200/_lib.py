@@ -34,7 +34,9 @@ class Desc(C.Structure):
                 ("n_smooth", C.c_int32), ("ncol_re", c_int32_p), ("include_penalty", C.c_int32),
                 ("n_ID", C.c_int32), ("a0", c_double_p), ("P0", c_double_p),
                 ("H_array", c_double_p), ("H_len", C.c_int64),
-                ("device", C.c_int32), ("shard_flags", C.c_int32), ("t_next", C.c_double)]
+                ("device", C.c_int32), ("shard_flags", C.c_int32), ("t_next", C.c_double),
+                ("t_decay", c_double_p), ("t_decay_len", C.c_int64), ("col_decay", c_int32_p),
+                ("ind_decay", c_int32_p), ("n_col_decay", C.c_int32)]
 
 
 class WtDesc(C.Structure):
@@ -77,7 +79,7 @@ class EngineError(RuntimeError):
 _lib = None
 
 # every symbol include/smoothsde_b200.h declares
-EXPORTS = ["ssde_create", "ssde_create_packed", "ssde_destroy", "ssde_n_par", "ssde_par_layout",
+EXPORTS = ["ssde_create", "ssde_create_packed", "ssde_destroy", "ssde_n_par", "ssde_par_layout", "ssde_decay_layout",
            "ssde_eval", "ssde_eval_device", "ssde_check", "ssde_report", "ssde_last_eval_ms",
            "ssde_last_eval_launches", "ssde_set_profile", "ssde_last_kernel_times", "ssde_last_error", "ssde_create_error", "ssde_version",
            "ssde_padded_rows", "ssde_layout_info", "ssde_pack_host", "ssde_pack_free",
@@ -109,6 +111,8 @@ def load():
     lib.ssde_n_par.restype = C.c_int
     lib.ssde_par_layout.argtypes = [vp, c_int32_p, c_int32_p]
     lib.ssde_par_layout.restype = C.c_int
+    lib.ssde_decay_layout.argtypes = [vp, c_int32_p, c_int32_p]
+    lib.ssde_decay_layout.restype = C.c_int
     lib.ssde_eval.argtypes = [vp, c_double_p, C.c_int, c_double_p, c_double_p, c_double_p]
     lib.ssde_eval.restype = C.c_int
     lib.ssde_eval_device.argtypes = [vp, vp, C.c_int, vp, vp]

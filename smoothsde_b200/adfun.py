@@ -42,11 +42,11 @@ class ADFun:
         full = np.zeros(self.engine.n_par)
         names = np.empty(self.engine.n_par, dtype=object)
         for nm in PAR_ORDER:
-            if nm == "log_decay":
+            if nm == "log_decay" and nm not in layout:
                 # exists in the list for BM/OU (R/sde.R:504-507) but is mapped off without decay
-                # terms (R/sde.R:648); decay models are out of scope
+                # terms (R/sde.R:648): it is then absent from the engine's vector
                 if nm in parameters and nm in map and not _all_na(map[nm]):
-                    raise NotImplementedError("decay terms (log_decay) are not built")
+                    raise ValueError("log_decay is free but the data list has no decay term (t_decay)")
                 continue
             if nm not in layout:
                 continue
@@ -59,7 +59,7 @@ class ADFun:
         # ---- map: group id per entry (-1 = fixed)
         group = np.arange(full.size)
         for nm, codes in map.items():
-            if nm == "log_decay" or nm not in layout:
+            if nm not in layout:
                 continue
             off, size = layout[nm]
             codes = np.atleast_1d(np.asarray(codes, dtype=object))

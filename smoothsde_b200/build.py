@@ -20,6 +20,10 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",
 ]
+# SSDE_FAST_BUILD=1: optimise the kernels of a translation unit in parallel (1.5 min instead of 4).
+# Development only -- the split changes register allocation of the two hot kernels and measured
+# 4 % slower on the B200 (12.9 vs 12.45 ms / 1.024e8 rows), so release builds stay single-unit.
+FAST_FLAGS = ["--split-compile", "0", "--threads", "0"]
 LINK_FLAGS = ["-lcusolver"]          # dense Cholesky of the random-effect Hessian block (ssde_laplace.cu)
 
 
@@ -46,6 +50,8 @@ def build(force=False, verbose=False):
     os.makedirs(LIBDIR, exist_ok=True)
     nvcc = os.environ.get("NVCC", "nvcc")
     extra = os.environ.get("SSDE_NVCC_EXTRA", "").split()      # e.g. -DSSDE_STATS for the diagnostics build
+    if os.environ.get("SSDE_FAST_BUILD"):
+        extra = FAST_FLAGS + extra
     cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources() + LINK_FLAGS
     subprocess.check_call(cmd)
     return LIB

@@ -34,6 +34,46 @@ struct SdeSmem {
     double red[8];
 };
 
+// Transition log-density of one row (observation i -> i+1 with the parameters of row i) and its
+// derivatives w.r.t. the row's linear predictors: llk += sum over dimensions with both endpoints
+// observed (tr_dens.hpp:31), eb[p] += d nllk / d eta_p.  `na` bit d: dimension d is NA at either
+// endpoint; z(d, 0 / 1) = observation of dimension d at row i / i+1.
+template <int MODEL, int ND, class R, class ZF>
+__device__ __forceinline__ void sde_row(const R* eta, double d_t, unsigned na, ZF z, R& llk, R* eb) {
+    if (MODEL == MODEL_BM) {
+        // mean = z0 + mu dt, sd = exp(eta_s) sqrt(dt)   (tr_dens.hpp:35-36)
+        const R sd = exp(eta[ND]) * sqrt(d_t);
+        const R isd = 1.0 / sd, lsd = log(sd);
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+            if ((na >> d) & 1) continue;      // tr_dens.hpp:31
+            const double z0 = z(d, 0), z1 = z(d, 1);
+            const R res = (z1 - (z0 + eta[d] * d_t)) * isd;
+            llk += -LOG_SQRT_2PI - lsd - 0.5 * res * res;
+            eb[d] = -res * d_t * isd;
+            eb[ND] += 1.0 - res * res;
+        }
+    } else {
+        // mean = mu + exp(-dt/tau)(z0 - mu), sd = sqrt(kappa (1 - exp(-2 dt/tau)))
+        const R tau = exp(eta[ND]), kappa = exp(eta[ND + 1]);
+        const R ph = exp(-d_t / tau);
+        const R var = kappa * (1.0 - exp(-2.0 * d_t / tau));     // tr_dens.hpp:50-51
+        const R sd = sqrt(var), isd = 1.0 / sd, lsd = log(sd);
+        const R dph = ph * d_t / tau;                  // d ph / d eta_tau
+        const R dlv = -2.0 * kappa * ph * dph / var;   // d log var / d eta_tau
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+            if ((na >> d) & 1) continue;
+            const double z0 = z(d, 0), z1 = z(d, 1);
+            const R res = (z1 - (eta[d] + ph * (z0 - eta[d]))) * isd;
+            llk += -LOG_SQRT_2PI - lsd - 0.5 * res * res;
+            eb[d] = -res * (1.0 - ph) * isd;
+            eb[ND] += 0.5 * dlv * (1.0 - res * res) - res * isd * dph * (z0 - eta[d]);
+            eb[ND + 1] += 0.5 * (1.0 - res * res);
+        }
+    }
+}
+
 template <int MODEL, int ND, class R = double>
 __global__ void __launch_bounds__(SDE_NT) sde_fused_kernel(SdeArgs a) {
     constexpr int NP = (MODEL == MODEL_BM) ? ND + 1 : ND + 2;
@@ -63,38 +103,8 @@ __global__ void __launch_bounds__(SDE_NT) sde_fused_kernel(SdeArgs a) {
                 R eta[NP];
                 row_eta<NP>(w, k, a.theta, eta);
                 const double d_t = a.dt[pos];
-                if (MODEL == MODEL_BM) {
-                    // mean = z0 + mu dt, sd = exp(eta_s) sqrt(dt)   (tr_dens.hpp:35-36)
-                    const R sd = exp(eta[ND]) * sqrt(d_t);
-                    const R isd = 1.0 / sd, lsd = log(sd);
-#pragma unroll
-                    for (int d = 0; d < ND; ++d) {
-                        if (((f0 | f1) >> (3 + d)) & 1) continue;      // tr_dens.hpp:31
-                        const double z0 = a.obs[(size_t)d * a.X.n_pad + pos], z1 = a.obs[(size_t)d * a.X.n_pad + npos];
-                        const R res = (z1 - (z0 + eta[d] * d_t)) * isd;
-                        llk += -LOG_SQRT_2PI - lsd - 0.5 * res * res;
-                        eb[d] = -res * d_t * isd;
-                        eb[ND] += 1.0 - res * res;
-                    }
-                } else {
-                    // mean = mu + exp(-dt/tau)(z0 - mu), sd = sqrt(kappa (1 - exp(-2 dt/tau)))
-                    const R tau = exp(eta[ND]), kappa = exp(eta[ND + 1]);
-                    const R ph = exp(-d_t / tau);
-                    const R var = kappa * (1.0 - exp(-2.0 * d_t / tau));     // tr_dens.hpp:50-51
-                    const R sd = sqrt(var), isd = 1.0 / sd, lsd = log(sd);
-                    const R dph = ph * d_t / tau;                  // d ph / d eta_tau
-                    const R dlv = -2.0 * kappa * ph * dph / var;   // d log var / d eta_tau
-#pragma unroll
-                    for (int d = 0; d < ND; ++d) {
-                        if (((f0 | f1) >> (3 + d)) & 1) continue;
-                        const double z0 = a.obs[(size_t)d * a.X.n_pad + pos], z1 = a.obs[(size_t)d * a.X.n_pad + npos];
-                        const R res = (z1 - (eta[d] + ph * (z0 - eta[d]))) * isd;
-                        llk += -LOG_SQRT_2PI - lsd - 0.5 * res * res;
-                        eb[d] = -res * (1.0 - ph) * isd;
-                        eb[ND] += 0.5 * dlv * (1.0 - res * res) - res * isd * dph * (z0 - eta[d]);
-                        eb[ND + 1] += 0.5 * (1.0 - res * res);
-                    }
-                }
+                sde_row<MODEL, ND>(eta, d_t, (unsigned)((f0 | f1) >> 3),
+                                   [&](int d, int nx) { return a.obs[(size_t)d * a.X.n_pad + (nx ? npos : pos)]; }, llk, eb);
             }
             if (a.want_grad) {
 #pragma unroll
@@ -108,6 +118,110 @@ __global__ void __launch_bounds__(SDE_NT) sde_fused_kernel(SdeArgs a) {
         grad_flush(gacc, SDE_NT);
     }
     const double bl = block_sum<SDE_NT>(value(llk), sm.red);
+    if (threadIdx.x == 0) a.block_llk[blockIdx.x] = bl;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Decay models (nllk_sde.hpp:47-59): column c of X_re listed in col_decay is multiplied, row by
+// row, by exp(-rho_k t_decay(row)), rho_k = exp(log_decay(ind_decay)), before the linear
+// predictor is formed -- the design then depends on a parameter, so the values cannot be
+// pre-scaled.  Same pass as sde_fused_kernel with the factor applied per nonzero; the transposed
+// product and d nllk / d log_decay_k = sum eta_bar * x * theta_c * fac * (-rho_k t) are
+// accumulated with atomics (decay models are small: R/sde.R:162-177 builds them for single
+// experiments, not for the 1e8-row workloads).
+// ---------------------------------------------------------------------------------------------
+struct DecayArgs {
+    const double* t_decay;     // [n_par, n_pad] permuted planes of other_data$t_decay
+    const int32_t* dec_of_col; // [p_theta]: decay index of a theta column, or -1
+    const double* par;         // joint parameter vector (log_decay at o_dec)
+    const double* par_dot;     // tangent pass: direction
+    int o_dec, n_dec;
+    double* grad_decay;        // [n_dec] (R = Dual: [2 n_dec], tangents second)
+};
+
+template <class R>
+__device__ __forceinline__ void atomic_add_r(double* base, int i, int stride, const R& v) {
+    atomicAdd(base + i, value(v));
+    if constexpr (!std::is_same<R, double>::value) atomicAdd(base + stride + i, v.d);
+}
+
+template <int MODEL, int ND, class R = double>
+__global__ void __launch_bounds__(SDE_NT) sde_decay_kernel(SdeArgs a, DecayArgs dc) {
+    constexpr int NP = (MODEL == MODEL_BM) ? ND + 1 : ND + 2;
+    constexpr int NWARP = SDE_NT / 32;
+    constexpr int MAXDEC = 16;
+    __shared__ double red[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    R rho[MAXDEC];
+#pragma unroll
+    for (int k = 0; k < MAXDEC; ++k)
+        rho[k] = (k < dc.n_dec) ? exp(ScalarOf<R>::make(dc.par[dc.o_dec + k], dc.par_dot ? dc.par_dot[dc.o_dec + k] : 0.0)) : R(0.0);
+    auto rho_of = [&](int k) {
+        R r = 0.0;
+#pragma unroll
+        for (int j = 0; j < MAXDEC; ++j) if (j == k) r = rho[j];
+        return r;
+    };
+    R llk = 0.0;
+    for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        const int64_t q = tile * NWARP + warp;
+        const int64_t base = q * WT + lane;
+        const int64_t row0 = q * WT + (int64_t)lane * LC;
+        const WtDesc d = a.X.desc[q];
+        const int S = slots_of(d.kmax);
+        const bool uniform = (d.flags & WT_UNIFORM) != 0;
+        const double* vals = a.X.val + d.val_off + lane;
+        const uint32_t* cols = a.X.col + d.col_off + (uniform ? 0 : lane);
+#pragma unroll 1
+        for (int k = 0; k < LC; ++k) {
+            const int64_t pos = base + k * 32;
+            const uint8_t f0 = a.flags[pos];
+            if (f0 == 0xff || (f0 & ROW_LAST)) continue;        // ID(i) == ID(i+1), nllk_sde.hpp:79
+            const int64_t npos = (k < LC - 1) ? pos + 32 : row_pos(row0 + k + 1);
+            const uint8_t f1 = a.flags[npos];
+            // nonzero j of parameter p: value, column, decay factor
+            auto each = [&](auto&& fn) {
+                int j = 0;
+#pragma unroll
+                for (int p = 0; p < NP; ++p) {
+                    const int kp = (int)((d.kmax >> (8 * p)) & 255u);
+                    for (int jj = 0; jj < kp; ++jj, ++j) {
+                        const double x = vals[(size_t)(k * S + j) * 32];
+                        const uint32_t c = uniform ? cols[j] : cols[(size_t)(k * S + j) * 32];
+                        const int dk = dc.dec_of_col[c];
+                        R fac = 1.0, dfac = 0.0;                 // factor and d factor / d log_decay
+                        if (dk >= 0) {
+                            const double t = dc.t_decay[(size_t)p * a.X.n_pad + pos];
+                            const R r = rho_of(dk);
+                            fac = exp(-r * t);                   // nllk_sde.hpp:53
+                            dfac = -r * t * fac;
+                        }
+                        fn(p, x, c, dk, fac, dfac);
+                    }
+                }
+            };
+            R eta[NP], eb[NP];
+#pragma unroll
+            for (int p = 0; p < NP; ++p) { eta[p] = 0.0; eb[p] = 0.0; }
+            each([&](int p, double x, uint32_t c, int, const R& fac, const R&) {
+#pragma unroll
+                for (int pp = 0; pp < NP; ++pp) if (pp == p) eta[pp] += x * (theta_at<R>(a.theta, c) * fac);
+            });
+            sde_row<MODEL, ND>(eta, a.dt[pos], (unsigned)((f0 | f1) >> 3),
+                               [&](int dd, int nx) { return a.obs[(size_t)dd * a.X.n_pad + (nx ? npos : pos)]; }, llk, eb);
+            if (a.want_grad) {
+                each([&](int p, double x, uint32_t c, int dk, const R& fac, const R& dfac) {
+                    R e = 0.0;
+#pragma unroll
+                    for (int pp = 0; pp < NP; ++pp) if (pp == p) e = eb[pp];
+                    if (x == 0.0) return;
+                    atomic_add_r<R>(a.grad_theta, (int)c, a.p_theta, e * (x * fac));
+                    if (dk >= 0) atomic_add_r<R>(dc.grad_decay, dk, dc.n_dec, e * (x * (theta_at<R>(a.theta, c) * dfac)));
+                });
+            }
+        }
+    }
+    const double bl = block_sum<SDE_NT>(value(llk), red);
     if (threadIdx.x == 0) a.block_llk[blockIdx.x] = bl;
 }
 

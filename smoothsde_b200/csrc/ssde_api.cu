@@ -58,6 +58,8 @@ struct ssde_handle {
     int n_tracks = 0;
     int p_fe = 0, p_re = 0, n_s = 0, npar = 0;
     int o_sig = -1, o_fe = 0, o_ll = 0, o_re = 0;
+    int o_dec = -1, n_dec = 0;       // BM/OU decay models: log_decay[n_dec] sits between log_lambda and coeff_re (nllk_sde.hpp:42-45)
+    DevBuf t_decay, dec_of_col, grad_decay;
     bool has_smooth = false, add_penalty = true, penalty_consts = false;
     int include_penalty = 1;
     int shard_flags = 0;
@@ -163,6 +165,8 @@ struct FinArgs {
     const int32_t* sm_off;    // [n_s + 1] offsets of the smooth blocks in coeff_re
     double* sb;               // [2 p_re] scratch: S b (as R)
     int p_fe, p_re, n_s, npar, o_sig, o_fe, o_ll, o_re;
+    int o_dec, n_dec;         // decay models: gradient entries of log_decay from grad_decay ([2 n_dec] in a tangent pass)
+    const double* grad_decay;
     int penalty;              // 0 none, 1 Kalman form (nllk_ctcrw.hpp:254-280), 2 nllk_sde form
     double pen_const;         // sum_i [Sn_i/2 log(2 pi) - 1/2 log det S_i]  (nllk_sde.hpp:114-116)
     int want_grad;
@@ -243,6 +247,8 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinArgs a) {
             const R g = ScalarOf<R>::make(a.grad_theta[i], TAN ? a.grad_theta[p + i] : 0.0);
             put(i < a.p_fe ? a.o_fe + i : a.o_re + (i - a.p_fe), g);
         }
+        for (int i = tid; i < a.n_dec; i += blockDim.x)
+            put(a.o_dec + i, ScalarOf<R>::make(a.grad_decay[i], TAN ? a.grad_decay[a.n_dec + i] : 0.0));
     }
     __syncthreads();
     if (a.penalty) {
@@ -602,11 +608,13 @@ int finish_setup(ssde_handle* h) {
     h->o_sig = is_kalman(h->model) ? 0 : -1;
     h->o_fe = is_kalman(h->model) ? 1 : 0;
     h->o_ll = h->o_fe + h->p_fe;
-    h->o_re = h->o_ll + h->n_s;
+    h->o_dec = h->n_dec > 0 ? h->o_ll + h->n_s : -1;
+    h->o_re = h->o_ll + h->n_s + h->n_dec;
     h->npar = h->o_re + h->p_re;
     if ((rc = dev_alloc<double>(h->par, h->npar, err))) return rc;
     if ((rc = dev_alloc<double>(h->theta, p, err))) return rc;
     if ((rc = dev_alloc<double>(h->grad_theta, p, err))) return rc;
+    if ((rc = dev_alloc<double>(h->grad_decay, 2 * (size_t)std::max(h->n_dec, 1), err))) return rc;
     if ((rc = dev_alloc<double>(h->out, h->npar + 2, err))) return rc;
     if ((rc = dev_alloc<double>(h->part, 3 * RED_BLOCKS, err))) return rc;
     if ((rc = dev_alloc<int>(h->mu_zero, 1, err))) return rc;
@@ -784,7 +792,7 @@ int launch_ctcrw(ssde_handle* h, const double* d_par, const double* d_dir, int o
 }
 
 template <int MODEL, int ND, class R>
-int launch_sde(ssde_handle* h, int order, cudaStream_t st) {
+int launch_sde(ssde_handle* h, const double* d_par, const double* d_dir, int order, cudaStream_t st) {
     constexpr bool TAN = !std::is_same<R, double>::value;
     std::string& err = h->err;
     constexpr int NP = (MODEL == MODEL_BM) ? ND + 1 : ND + 2;
@@ -796,6 +804,14 @@ int launch_sde(ssde_handle* h, int order, cudaStream_t st) {
     a.grad_theta = TAN ? h->t_grad_theta.as<double>() : h->grad_theta.as<double>(); a.p_theta = h->p_fe + h->p_re;
     a.block_llk = h->block_llk.as<double>();
     a.ntiles = h->ntiles_lp;
+    if (h->n_dec > 0) {
+        DecayArgs dc{h->t_decay.as<double>(), h->dec_of_col.as<int32_t>(), d_par, TAN ? d_dir : nullptr, h->o_dec, h->n_dec,
+                     h->grad_decay.as<double>()};
+        mark(h, st, TAN ? "sde_decay_tangent" : "sde_decay");
+        sde_decay_kernel<MODEL, ND, R><<<TAN ? h->grid_lp2 : h->grid_lp, SDE_NT, 0, st>>>(a, dc);
+        CUDA_TRY(cudaGetLastError());
+        return SSDE_OK;
+    }
     mark(h, st, TAN ? "sde_fused_tangent" : "sde_fused");
     sde_fused_kernel<MODEL, ND, R><<<TAN ? h->grid_lp2 : h->grid_lp, SDE_NT, sizeof(SdeSmem<NP, R>), st>>>(a);
     CUDA_TRY(cudaGetLastError());
@@ -810,6 +826,7 @@ int eval_prologue(ssde_handle* h, const double* d_par, const double* d_dir, int 
     if (order >= 1) {
         if (d_dir) CUDA_TRY(cudaMemsetAsync(h->t_grad_theta.p, 0, sizeof(double) * 2 * std::max(p, 1), st));
         else CUDA_TRY(cudaMemsetAsync(h->grad_theta.p, 0, sizeof(double) * std::max(p, 1), st));
+        if (h->n_dec > 0) CUDA_TRY(cudaMemsetAsync(h->grad_decay.p, 0, sizeof(double) * 2 * h->n_dec, st));
     }
     mark(h, st, "gather_theta");
     gather_theta_kernel<<<std::max((p + 255) / 256, 1), 256, 0, st>>>(d_par, h->theta.as<double>(), d_dir,
@@ -837,6 +854,7 @@ int eval_epilogue(ssde_handle* h, const double* d_par, const double* d_dir, int 
     f.sm_off = h->sm_off.as<int32_t>(); f.sb = h->sb.as<double>();
     f.p_fe = h->p_fe; f.p_re = h->p_re; f.n_s = h->n_s; f.npar = h->npar;
     f.o_sig = h->o_sig; f.o_fe = h->o_fe; f.o_ll = h->o_ll; f.o_re = h->o_re;
+    f.o_dec = h->o_dec; f.n_dec = h->n_dec; f.grad_decay = h->grad_decay.as<double>();
     f.penalty = 0;
     if (h->has_smooth && h->add_penalty) {
         if (is_kalman(h->model)) f.penalty = 1;                          // ignores include_penalty
@@ -860,11 +878,11 @@ int launch_model(ssde_handle* h, const double* d_par, const double* d_dir, int o
     if (is_kalman(h->model))
         return with_kalman_model<R>(h, [&](auto m) -> int { return launch_ctcrw<decltype(m)>(h, d_par, d_dir, order, st, aest); });
     if (h->model == SSDE_BM) {
-        if (h->n_dim == 1) return launch_sde<MODEL_BM, 1, R>(h, order, st);
-        if (h->n_dim == 2) return launch_sde<MODEL_BM, 2, R>(h, order, st);
-        return launch_sde<MODEL_BM, 3, R>(h, order, st);
+        if (h->n_dim == 1) return launch_sde<MODEL_BM, 1, R>(h, d_par, d_dir, order, st);
+        if (h->n_dim == 2) return launch_sde<MODEL_BM, 2, R>(h, d_par, d_dir, order, st);
+        return launch_sde<MODEL_BM, 3, R>(h, d_par, d_dir, order, st);
     }
-    return (h->n_dim == 1) ? launch_sde<MODEL_OU, 1, R>(h, order, st) : launch_sde<MODEL_OU, 2, R>(h, order, st);
+    return (h->n_dim == 1) ? launch_sde<MODEL_OU, 1, R>(h, d_par, d_dir, order, st) : launch_sde<MODEL_OU, 2, R>(h, d_par, d_dir, order, st);
 }
 
 int run_eval(ssde_handle* h, const double* d_par, int order, double* d_out, cudaStream_t st, double* aest) {
@@ -1004,6 +1022,12 @@ int ssde_par_layout(const ssde_handle* h, int32_t offsets[4], int32_t sizes[4]) 
     if (!h) return SSDE_ERR_BAD_ARG;
     offsets[0] = h->o_sig; offsets[1] = h->o_fe; offsets[2] = h->o_ll; offsets[3] = h->o_re;
     sizes[0] = (h->o_sig >= 0) ? 1 : 0; sizes[1] = h->p_fe; sizes[2] = h->n_s; sizes[3] = h->p_re;
+    return SSDE_OK;
+}
+
+int ssde_decay_layout(const ssde_handle* h, int32_t* offset, int32_t* size) {
+    if (!h || !offset || !size) return SSDE_ERR_BAD_ARG;
+    *offset = h->o_dec; *size = h->n_dec;
     return SSDE_OK;
 }
 
@@ -1151,6 +1175,27 @@ int ssde_create(const ssde_desc* d, ssde_handle** out) {
         if ((rc = dev_upload(h->a0, a0, h->err))) return fail(rc);
     }
     h->n_tracks = (int)starts.size();
+    if (d->t_decay && d->t_decay_len > 1) {
+        // decay terms, nllk_sde.hpp:47-59 / R/sde.R:162-177: t_decay has one entry per row of X_re
+        if (is_kalman(d->model)) { err = "decay terms exist for nllk_sde models (BM, OU) only"; return fail(SSDE_ERR_BAD_ARG); }
+        if (d->t_decay_len != (int64_t)n_par * n) { err = "t_decay must have n_par * n entries (R/sde.R:170)"; return fail(SSDE_ERR_BAD_ARG); }
+        if (d->n_col_decay < 1 || !d->col_decay || !d->ind_decay) { err = "col_decay / ind_decay missing"; return fail(SSDE_ERR_BAD_ARG); }
+        std::vector<int32_t> doc((size_t)h->p_fe + h->p_re, -1);
+        int kmax = 0;
+        for (int i = 0; i < d->n_col_decay; ++i) {
+            const int c = d->col_decay[i], k = d->ind_decay[i];            // 1-based, nllk_sde.hpp:51-52
+            if (c < 1 || c > h->p_re) { err = "'col_decay' should be between 1 and ncol(X_re) (R/sde.R:637-639)"; return fail(SSDE_ERR_BAD_ARG); }
+            if (k < 1 || k > 16) { err = "ind_decay must be in 1..16"; return fail(SSDE_ERR_UNSUPPORTED); }
+            doc[(size_t)h->p_fe + c - 1] = k - 1;
+            kmax = std::max(kmax, k);
+        }
+        h->n_dec = kmax;
+        std::vector<double> td((size_t)n_pad * n_par, 0.0);
+        for (int p = 0; p < n_par; ++p)
+            for (int64_t i = 0; i < n; ++i) td[(size_t)p * n_pad + row_pos(i)] = d->t_decay[(size_t)p * n + i];
+        if ((rc = dev_upload(h->t_decay, td, h->err))) return fail(rc);
+        if ((rc = dev_upload(h->dec_of_col, doc, h->err))) return fail(rc);
+    }
     Packed pk;
     if ((rc = pack_design(*d, n_par, pk, h->err))) return fail(rc);
     h->nnz = (int64_t)pk.col.size();

@@ -80,6 +80,19 @@ def make_desc(dat, device=0, shard_flags=0, t_next=0.0):
             keep.append(H)
             d.H_array = H.ctypes.data_as(L.c_double_p)
             d.H_len = H.size
+    td = dat.get("t_decay")
+    if td is not None and np.size(td) > 1:                  # decay terms, nllk_sde.hpp:31-33,47-59
+        td = np.ascontiguousarray(td, dtype=np.float64)
+        cd = np.ascontiguousarray(np.atleast_1d(dat["col_decay"]), dtype=np.int32)
+        idc = np.ascontiguousarray(np.atleast_1d(dat["ind_decay"]), dtype=np.int32)
+        if cd.size != idc.size:
+            raise ValueError("Check length of 'other_data$ind_decay' and 'other_data$col_decay'")     # R/sde.R:174-176
+        keep += [td, cd, idc]
+        d.t_decay = td.ctypes.data_as(L.c_double_p)
+        d.t_decay_len = td.size
+        d.col_decay = cd.ctypes.data_as(L.c_int32_p)
+        d.ind_decay = idc.ctypes.data_as(L.c_int32_p)
+        d.n_col_decay = cd.size
     d.device = device
     d.shard_flags = shard_flags
     d.t_next = float(t_next)
@@ -118,6 +131,10 @@ class Engine:
         lib.ssde_par_layout(handle, off, siz)
         names = ("log_sigma_obs", "coeff_fe", "log_lambda", "coeff_re")
         self.layout = {nm: (int(off[k]), int(siz[k])) for k, nm in enumerate(names) if siz[k] > 0 or k > 0}
+        od, nd = C.c_int32(), C.c_int32()
+        lib.ssde_decay_layout(handle, C.byref(od), C.byref(nd))
+        if nd.value > 0:                                    # BM/OU decay models only (nllk_sde.hpp:44)
+            self.layout["log_decay"] = (od.value, nd.value)
         self._grad = np.zeros(self.n_par)
         self._nllk = C.c_double()
 

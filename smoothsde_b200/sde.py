@@ -80,8 +80,6 @@ class SDE:
             raise ValueError("'data' should have a time column")
         self._data = data
         self._other_data = dict(other_data or {})
-        if "t_decay" in self._other_data:
-            raise NotImplementedError("decay models are not built")
         self._device = device
         self._adfun_factory = adfun_factory or ADFun
         self._mats = _design.make_design(formulas, data, n)                     # make_mat, R/sde.R:378-455
@@ -99,6 +97,36 @@ class SDE:
                 self._coeff_fe[i0[k]] = np.log(par0[k]) if link == "log" else par0[k]
         self._tmb_obj = self._tmb_obj_joint = None
         self._out = None
+        # ---- decay terms, R/sde.R:162-180
+        od = self._other_data
+        if od.get("t_decay") is not None:
+            if od.get("col_decay") is None:                                     # R/sde.R:165-169
+                term = od["decay_term"]
+                od["col_decay"] = np.array([i + 1 for i, nm in enumerate(m.names_re) if nm[:len(term)] == term])
+            if np.size(od["t_decay"]) != len(formulas) * n:                     # R/sde.R:170-173
+                raise ValueError("'other_data$t_decay' should be of length (number of parameters) x (number of data)")
+            if np.size(od["col_decay"]) != np.size(od["ind_decay"]):            # R/sde.R:174-176
+                raise ValueError("Check length of 'other_data$ind_decay' and 'other_data$col_decay'")
+            self._rho = np.ones(np.unique(np.asarray(od["ind_decay"])).size)    # R/sde.R:177
+        else:
+            self._rho = np.ones(1)
+
+    def rho(self): return self._rho
+    def update_rho(self, v): self._rho = np.atleast_1d(np.asarray(v, dtype=float)).copy()      # R/sde.R:358-360
+    def other_data(self): return self._other_data
+
+    def X_re_decay(self):
+        """X_re with the decaying columns multiplied by exp(-rho * t_decay), R/sde.R:303-326."""
+        od = self._other_data
+        if od.get("t_decay") is None:
+            raise ValueError("This model has no decaying terms")               # R/sde.R:322
+        X = sp.lil_matrix(sp.csc_matrix(self._mats.X_re, dtype=float))
+        Xc = sp.csc_matrix(self._mats.X_re)
+        t = np.asarray(od["t_decay"], dtype=float)
+        for col, ind in zip(np.atleast_1d(od["col_decay"]), np.atleast_1d(od["ind_decay"])):
+            c = Xc[:, int(col) - 1]
+            X[c.indices, int(col) - 1] = (c.data * np.exp(-self._rho[int(ind) - 1] * t[c.indices])).reshape(-1, 1)
+        return sp.csr_matrix(X)
 
     # ---- accessors / mutators (R/sde.R:186-360)
     def formulas(self): return self._formulas
@@ -134,7 +162,8 @@ class SDE:
         n = len(self._data["time"])
         map = dict(map or {})
         has_re = m.S is not None and m.X_re.shape[1] > 0
-        tmb_par = OrderedDict(coeff_fe=self._coeff_fe.copy(), log_lambda=np.zeros(1), coeff_re=np.zeros(1))
+        tmb_par = OrderedDict(coeff_fe=self._coeff_fe.copy(), log_lambda=np.zeros(1), log_decay=np.log(self._rho),
+                              coeff_re=np.zeros(1))                             # R/sde.R:504-507
         random = None
         if not has_re:                                                          # R/sde.R:511-518
             map["coeff_re"] = [None]
@@ -176,6 +205,19 @@ class SDE:
             if self._other_data.get("H") is not None:
                 tmb_dat["H_array"] = np.asarray(self._other_data["H"], float)
                 map["log_sigma_obs"] = [None]
+        if self._type in ("BM", "OU"):                                          # R/sde.R:635-649
+            od = self._other_data
+            if od.get("t_decay") is not None:
+                if np.any(np.asarray(od["col_decay"]) > len(m.names_re)):
+                    raise ValueError(f"'col_decay' should be between 1 and {len(m.names_re)}")
+                tmb_dat["t_decay"] = np.asarray(od["t_decay"], float)
+                tmb_dat["col_decay"] = np.asarray(od["col_decay"], np.int64)
+                tmb_dat["ind_decay"] = np.asarray(od["ind_decay"], np.int64)
+            else:
+                tmb_dat["t_decay"], tmb_dat["col_decay"], tmb_dat["ind_decay"] = np.zeros(1), np.zeros(1, int), np.zeros(1, int)
+                map["log_decay"] = [None]
+        else:
+            tmb_par.pop("log_decay")                                            # R/sde.R:650-653
         if self._fixpar:                                                        # R/sde.R:621-632
             cmap = list(range(m.X_fe.shape[1]))
             for i in self.ind_fixcoeff():
@@ -206,6 +248,9 @@ class SDE:
             self.update_coeff_re(p[off:off + size])
             off, size = lay["log_lambda"]
             self.update_lambda(np.exp(p[off:off + size]))
+        if "log_decay" in lay:                                                  # R/sde.R:715-719
+            off, size = lay["log_decay"]
+            self.update_rho(np.exp(p[off:off + size]))
         self._par_all = p.copy()
         if sdreport:                                   # R/sde.R:702-704: sdreport(obj, getJointPrecision = TRUE)
             self._rep = obj.sdreport(res.x)

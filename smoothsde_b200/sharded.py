@@ -72,7 +72,11 @@ def shard_rows(dat, lo, hi):
     obs = np.asarray(dat["obs"], dtype=float)
     if obs.ndim == 1:
         obs = obs[:, None]
-    sub = {k: v for k, v in dat.items() if k not in ("ID", "times", "obs", "X_fe", "X_re", "a0", "H_array")}
+    sub = {k: v for k, v in dat.items() if k not in ("ID", "times", "obs", "X_fe", "X_re", "a0", "H_array", "t_decay")}
+    td = dat.get("t_decay")
+    if td is not None and np.size(td) > 1:           # one entry per row of X_re: follows the rows of every block
+        td = np.asarray(td, dtype=float)
+        sub["t_decay"] = np.concatenate([td[j * n + lo:j * n + hi] for j in range(n_par)])
     sub["ID"], sub["times"], sub["obs"] = ID[lo:hi], np.asarray(dat["times"])[lo:hi], obs[lo:hi]
     for nm in ("X_fe", "X_re"):
         X = sp.csr_matrix(dat[nm])

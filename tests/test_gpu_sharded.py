@@ -66,7 +66,9 @@ def test_track_shards_solo_is_the_plain_engine():
     e2 = S.TrackShardedEngine(dat, device=0)
     v1, g1 = e1.eval(par, 1)
     v2, g2 = e2.eval(par, 1)
-    assert v1 == v2 and np.array_equal(g1, g2)
+    # same kernels on the same rows; the transposed design product is accumulated with atomics, so
+    # the gradients agree to rounding, not bitwise
+    assert v1 == v2 and np.max(np.abs(g1 - g2)) <= 1e-12 * np.max(np.abs(g1))
     d = np.linspace(-1, 1, par.size)
     _, _, h1 = e1.hvp(par, d)
     _, _, h2 = e2.hvp(par, d)
