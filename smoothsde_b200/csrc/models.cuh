@@ -25,7 +25,13 @@ struct PriorCov {
 };
 
 // Kernel geometry of the decoupled models (threads per CTA, CTAs per SM the kernels are compiled for)
-constexpr int KNT_DEFAULT = 128, MINB_DEFAULT = 3;
+#ifndef SSDE_KNT
+#define SSDE_KNT 128
+#endif
+#ifndef SSDE_MINB
+#define SSDE_MINB 3
+#endif
+constexpr int KNT_DEFAULT = SSDE_KNT, MINB_DEFAULT = SSDE_MINB;
 
 constexpr double CONST_MAP_TOL = 1e-60;     // see FwdOps / is_const in common.cuh
 SSDE_HD bool tiny(double x) { return fabs(x) <= CONST_MAP_TOL; }

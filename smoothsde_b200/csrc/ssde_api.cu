@@ -565,6 +565,11 @@ int max_grid(K kernel, int nt, size_t smem, int num_sms, std::string& err, int& 
 template <class R, class Fn>
 int with_kalman_model(const ssde_handle* h, Fn&& fn) {
     const int nd = h->n_dim;
+#ifdef SSDE_MINIMAL
+    // kernel-tuning build (scripts/tune_build.sh): only the benchmark's instantiation, seconds to compile
+    if constexpr (std::is_same<R, double>::value) { if (h->model == SSDE_CTCRW && nd == 2 && !h->dense) return fn(CtcrwModel<2, R>{}); }
+    return SSDE_ERR_UNSUPPORTED;
+#else
     switch (h->model) {
         case SSDE_CTCRW:
             if (h->dense) return nd == 1 ? fn(DenseModel<CtcrwModel<1, R>>{}) : fn(DenseModel<CtcrwModel<2, R>>{});
@@ -577,6 +582,7 @@ int with_kalman_model(const ssde_handle* h, Fn&& fn) {
             return nd == 1 ? fn(BmSsmModel<1, R>{}) : (nd == 2 ? fn(BmSsmModel<2, R>{}) : fn(BmSsmModel<3, R>{}));
     }
     return SSDE_ERR_UNSUPPORTED;
+#endif
 }
 
 template <class M>
