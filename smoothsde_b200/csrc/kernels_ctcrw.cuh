@@ -19,6 +19,19 @@
 #include "design.cuh"
 #include "models.cuh"
 
+// L2 prefetch hints (cp.async.bulk.prefetch.L2), measured on the B200 at 1024 x 1e5 rows
+// (scripts/gpu_tune.sh): forward 2 = the design values of row-steps k+2, k+3 are requested while
+// the TMA copy of row-step k+1 is issued, so that copy is an L2 hit (6.42 -> 6.23 ms); 1 = the
+// whole warp-tile block at once (6.28 ms).  Adjoint 1 = the warp-tile's design block is requested
+// when the reverse sweep starts, ~12 k cycles before the transposed product streams it
+// (5.93 -> 5.63 ms); 2 = at the start of the tile: too early, L2 thrashes (6.69 ms).
+#ifndef SSDE_BWD_PREFETCH
+#define SSDE_BWD_PREFETCH 1
+#endif
+#ifndef SSDE_FWD_PREFETCH
+#define SSDE_FWD_PREFETCH 2
+#endif
+
 namespace ssde {
 
 // M = model traits (models.cuh): CtcrwModel / OuSsmModel / BmSsmModel <n_dim, scalar type>
@@ -133,7 +146,14 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(KalmanArgs<typename
         const int64_t base = q * WT + lane;
         const int64_t row0 = q * WT + (int64_t)lane * LC;
         const WtViewT<R> w = open_warptile<R>(a.X, q, a.theta, sm.th[warp], true);
-        if (w.staged && lane == 0) stage_issue(w, st, 0);
+        if (w.staged && lane == 0) {
+            stage_issue(w, st, 0);
+#if SSDE_FWD_PREFETCH == 1
+            prefetch_l2(w.blk + (size_t)w.S * 32, (unsigned)((LC - 1) * w.S * 32 * 8));
+#elif SSDE_FWD_PREFETCH == 2
+            prefetch_l2(w.blk + (size_t)w.S * 32, (unsigned)(2 * w.S * 32 * 8));
+#endif
+        }
         const unsigned long long fl = load_flags8(a.flags, base);
 
         // (1) thread element over its LC rows
@@ -163,7 +183,12 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(KalmanArgs<typename
                 stage_wait(st);
                 row_eta_staged<NP>(w, st, eta);
                 __syncwarp();
-                if (lane == 0 && k + 1 < LC) stage_issue(w, st, k + 1);
+                if (lane == 0 && k + 1 < LC) {
+                    stage_issue(w, st, k + 1);
+#if SSDE_FWD_PREFETCH == 2
+                    if (k + 3 < LC) prefetch_l2(w.blk + (size_t)(k + 3) * w.S * 32, (unsigned)(w.S * 32 * 8));
+#endif
+                }
             } else if (step) {
                 row_eta<NP>(w, k, a.theta, eta);
             }
@@ -373,6 +398,9 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_bwd_kernel(KalmanArgs<typename
         const int64_t chunk = q * 32 + lane;
         const WtViewT<R> w = open_warptile<R>(a.X, q, a.theta, sm.th[warp], !mu0);
         const unsigned long long fl = load_flags8(a.flags, base);
+#if SSDE_BWD_PREFETCH == 2
+        if (lane == 0 && !a.summary) prefetch_l2(w.blk, (unsigned)(LC * w.S * 32 * 8));
+#endif
 
         // (1) recompute the forward states of this thread's rows from its checkpoint and compose
         //     the rows' adjoint elements (in time order)
@@ -455,6 +483,11 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_bwd_kernel(KalmanArgs<typename
         tc3 = clock64();
 #endif
         if (a.summary) continue;
+#if SSDE_BWD_PREFETCH == 1
+        // the transposed design product at the end of the tile streams LC x S x 32 values of this
+        // warp-tile from HBM: ask for them now so that they wait in L2 when the sweep is done
+        if (lane == 0) prefetch_l2(w.blk, (unsigned)(LC * w.S * 32 * 8));
+#endif
         // (4) adjoint entering this thread's last row, then the reverse sweep over its rows
         Ad g = M::load_adj([&](int i) { return sm.misc[par][i]; });
         {
