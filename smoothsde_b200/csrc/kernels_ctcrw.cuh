@@ -31,6 +31,11 @@
 #ifndef SSDE_FWD_PREFETCH
 #define SSDE_FWD_PREFETCH 2
 #endif
+// 1: at the start of a tile every warp asks for its 2 KB of each per-row plane (dt, obs, and in
+// the adjoint kernel tau / e / s2) in L2
+#ifndef SSDE_PLANE_PREFETCH
+#define SSDE_PLANE_PREFETCH 1
+#endif
 
 namespace ssde {
 
@@ -89,6 +94,35 @@ __device__ __forceinline__ unsigned long long load_flags8(const uint8_t* __restr
 #pragma unroll
     for (int k = 0; k < LC; ++k) fl |= (unsigned long long)flags[base + k * 32] << (8 * k);
     return fl;
+}
+
+// Per-plane pointers to this lane's first row of a warp-tile: row k of the lane is element k * 32
+// of every plane, so a row costs one offset and one load per plane (no 64-bit index arithmetic
+// per load).  `prefetch`: lanes 0 .. planes-1 ask for the warp-tile's 2 KB of their plane in L2, so
+// that only the first of the LC row fetches pays the HBM latency.
+template <class M>
+struct RowPlanes {
+    const typename M::R* wg[M::NW];
+    const double* dt;
+    const double* obs[M::ND];
+};
+template <class M>
+__device__ __forceinline__ RowPlanes<M> open_planes(const KalmanArgs<typename M::R>& a, int64_t base, bool with_wg, bool prefetch) {
+    RowPlanes<M> p;
+    const int64_t np = a.X.n_pad;
+#pragma unroll
+    for (int c = 0; c < M::NW; ++c) p.wg[c] = a.wg + (size_t)c * np + base;
+    p.dt = a.dt + base;
+#pragma unroll
+    for (int d = 0; d < M::ND; ++d) p.obs[d] = a.obs + (size_t)d * np + base;
+    if (prefetch) {
+        const int lane = threadIdx.x & 31;
+        const int64_t q0 = base - lane;                       // first element of the warp-tile in every plane
+        if (lane == 0) prefetch_l2(a.dt + q0, WT * 8);
+        else if (lane <= M::ND) prefetch_l2(a.obs + (size_t)(lane - 1) * np + q0, WT * 8);
+        else if (with_wg && lane <= M::ND + M::NW) prefetch_l2(a.wg + (size_t)(lane - 1 - M::ND) * np + q0, WT * (unsigned)sizeof(typename M::R));
+    }
+    return p;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -159,9 +193,10 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(KalmanArgs<typename
         // (1) thread element over its LC rows
         Elem E = M::fwd_identity();
         // dt and the observations of a row are fetched one row ahead of their use
-        double dt_nx = ((uint8_t)fl != 0xff) ? a.dt[base] : 1.0, y_nx[ND];
+        const RowPlanes<M> pl = open_planes<M>(a, base, false, SSDE_PLANE_PREFETCH != 0);
+        double dt_nx = ((uint8_t)fl != 0xff) ? pl.dt[0] : 1.0, y_nx[ND];
 #pragma unroll
-        for (int d = 0; d < ND; ++d) y_nx[d] = ((uint8_t)fl != 0xff) ? a.obs[(size_t)d * a.X.n_pad + base] : 0.0;
+        for (int d = 0; d < ND; ++d) y_nx[d] = ((uint8_t)fl != 0xff) ? pl.obs[d][0] : 0.0;
 #pragma unroll 1
         for (int k = 0; k < LC; ++k) {
             const int64_t pos = base + k * 32;
@@ -174,9 +209,9 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(KalmanArgs<typename
             for (int d = 0; d < ND; ++d) y[d] = y_nx[d];
             if (k + 1 < LC) {
                 const bool live1 = (uint8_t)(fl >> (8 * (k + 1))) != 0xff;
-                dt_nx = live1 ? a.dt[pos + 32] : 1.0;
+                dt_nx = live1 ? pl.dt[(k + 1) * 32] : 1.0;
 #pragma unroll
-                for (int d = 0; d < ND; ++d) y_nx[d] = live1 ? a.obs[(size_t)d * a.X.n_pad + pos + 32] : 0.0;
+                for (int d = 0; d < ND; ++d) y_nx[d] = live1 ? pl.obs[d][(k + 1) * 32] : 0.0;
             }
             R eta[NP];
             if (w.staged) {
@@ -194,7 +229,7 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(KalmanArgs<typename
             }
             if (step) {
                 const typename M::RowPar rp = M::transform(eta, dtv);
-                M::store_rowpar(rp, [&](int c) -> R& { return a.wg[(size_t)c * a.X.n_pad + pos]; });
+                M::store_rowpar(rp, [&](int c) -> R& { return const_cast<R&>(pl.wg[c][k * 32]); });
                 const typename M::Step sp = M::make_step(rp, dtv);
                 M::store_step(sp, [&](int c) -> R& { return sm.W[k][c][tid]; });
                 M::fwd_append(E, sp, y, eta, (f & ROW_OBS) != 0, M::row_h(h, a.Hrow, a.X.n_pad, pos));
@@ -272,9 +307,9 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(KalmanArgs<typename
         // sum_i log F_i is taken as the log of a running product (one log per chunk instead of
         // one per row); the product is folded into `slog` whenever it leaves a safe range.
         R quad = 0.0, fprod = 1.0, slog = 0.0;
-        dt_nx = ((uint8_t)fl != 0xff) ? a.dt[base] : 1.0;
+        dt_nx = ((uint8_t)fl != 0xff) ? pl.dt[0] : 1.0;
 #pragma unroll
-        for (int d = 0; d < ND; ++d) y_nx[d] = ((uint8_t)fl != 0xff) ? a.obs[(size_t)d * a.X.n_pad + base] : 0.0;
+        for (int d = 0; d < ND; ++d) y_nx[d] = ((uint8_t)fl != 0xff) ? pl.obs[d][0] : 0.0;
 #pragma unroll 1
         for (int k = 0; k < LC; ++k) {
             const uint8_t f = (uint8_t)(fl >> (8 * k));
@@ -285,9 +320,9 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(KalmanArgs<typename
 #pragma unroll
             for (int d = 0; d < ND; ++d) y[d] = y_nx[d];
             if (k + 1 < LC && (uint8_t)(fl >> (8 * (k + 1))) != 0xff) {
-                dt_nx = a.dt[pos + 32];
+                dt_nx = pl.dt[(k + 1) * 32];
 #pragma unroll
-                for (int d = 0; d < ND; ++d) y_nx[d] = a.obs[(size_t)d * a.X.n_pad + pos + 32];
+                for (int d = 0; d < ND; ++d) y_nx[d] = pl.obs[d][(k + 1) * 32];
             }
             if (f & ROW_START) {
                 s = track_start_state<M>(a, dtv);
@@ -350,13 +385,13 @@ struct RowIn {
     double dt, y[M::ND];
 };
 template <class M>
-__device__ __forceinline__ RowIn<M> load_row(const KalmanArgs<typename M::R>& a, int64_t pos, bool live) {
+__device__ __forceinline__ RowIn<M> load_row(const RowPlanes<M>& p, int k, bool live) {
     RowIn<M> r;
-    const int64_t np = a.X.n_pad;
-    r.dt = live ? a.dt[pos] : 1.0;
-    r.rp = live ? M::load_rowpar([&](int c) { return a.wg[(size_t)c * np + pos]; }) : M::dead_rowpar();
+    const int o = k * 32;
+    r.dt = live ? p.dt[o] : 1.0;
+    r.rp = live ? M::load_rowpar([&](int c) { return p.wg[c][o]; }) : M::dead_rowpar();
 #pragma unroll
-    for (int d = 0; d < M::ND; ++d) r.y[d] = live ? a.obs[(size_t)d * np + pos] : 0.0;
+    for (int d = 0; d < M::ND; ++d) r.y[d] = live ? p.obs[d][o] : 0.0;
     return r;
 }
 
@@ -406,14 +441,15 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_bwd_kernel(KalmanArgs<typename
         //     the rows' adjoint elements (in time order)
         St s = M::load_state([&](int i) { return a.ckpt[(size_t)i * a.nchunks + chunk]; });
         Elem E = M::bwd_identity();
-        RowIn<M> nx = load_row<M>(a, base, (uint8_t)fl != 0xff);
+        const RowPlanes<M> pl = open_planes<M>(a, base, true, SSDE_PLANE_PREFETCH != 0);
+        RowIn<M> nx = load_row<M>(pl, 0, (uint8_t)fl != 0xff);
 #pragma unroll 1
         for (int k = 0; k < LC; ++k) {
             const uint8_t f = (uint8_t)(fl >> (8 * k));
             const bool live = f != 0xff;
             const bool step = live && !(f & ROW_START);
             const RowIn<M> r = nx;
-            if (k + 1 < LC) nx = load_row<M>(a, base + (k + 1) * 32, (uint8_t)(fl >> (8 * (k + 1))) != 0xff);
+            if (k + 1 < LC) nx = load_row<M>(pl, k + 1, (uint8_t)(fl >> (8 * (k + 1))) != 0xff);
             // state BEFORE row k
             M::store_state(s, [&](int i) -> R& { return sm.Rs[k][i][tid]; });
             if (step) {
@@ -498,12 +534,12 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_bwd_kernel(KalmanArgs<typename
         }
         g = M::bwd_apply(exc, g);
         R gh = 0.0;
-        nx = load_row<M>(a, base + (LC - 1) * 32, (uint8_t)(fl >> (8 * (LC - 1))) != 0xff);
+        nx = load_row<M>(pl, LC - 1, (uint8_t)(fl >> (8 * (LC - 1))) != 0xff);
 #pragma unroll 1
         for (int k = LC - 1; k >= 0; --k) {
             const uint8_t f = (uint8_t)(fl >> (8 * k));
             const RowIn<M> r = nx;
-            if (k > 0) nx = load_row<M>(a, base + (k - 1) * 32, (uint8_t)(fl >> (8 * (k - 1))) != 0xff);
+            if (k > 0) nx = load_row<M>(pl, k - 1, (uint8_t)(fl >> (8 * (k - 1))) != 0xff);
             R gp[NP];
 #pragma unroll
             for (int j = 0; j < NP; ++j) gp[j] = 0.0;
