@@ -36,6 +36,9 @@
 #ifndef SSDE_PLANE_PREFETCH
 #define SSDE_PLANE_PREFETCH 1
 #endif
+#ifndef SSDE_FWD_RESTAGE
+#define SSDE_FWD_RESTAGE 1
+#endif
 
 namespace ssde {
 
@@ -237,6 +240,21 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(KalmanArgs<typename
                 M::fwd_append_start(E, track_start_state<M>(a, dtv));
             }
         }
+#if SSDE_FWD_RESTAGE
+        // The staging buffer is idle until the next tile: bring the warp-tile's dt / obs planes
+        // (2 KB each, contiguous) into it with bulk copies that land during the scan and the
+        // look-back, so that the re-run (4) reads them from shared memory instead of L2.
+        const bool restage = w.staged && !a.summary && (1 + ND) * WT <= STAGE_DBL;
+        if (restage && lane == 0) {
+            fence_proxy_async();
+            mbar_expect_tx(st.bar, (unsigned)((1 + ND) * WT * 8));
+            tma_load_1d(st.buf, a.dt + q * WT, WT * 8, st.bar);
+#pragma unroll
+            for (int d = 0; d < ND; ++d) tma_load_1d(st.buf + (1 + d) * WT, a.obs + (size_t)d * a.X.n_pad + q * WT, WT * 8, st.bar);
+        }
+#else
+        constexpr bool restage = false;
+#endif
         // (2) warp inclusive scan (lower lanes = earlier rows)
         Elem inc = E;
 #pragma unroll 1
@@ -307,22 +325,32 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(KalmanArgs<typename
         // sum_i log F_i is taken as the log of a running product (one log per chunk instead of
         // one per row); the product is folded into `slog` whenever it leaves a safe range.
         R quad = 0.0, fprod = 1.0, slog = 0.0;
-        dt_nx = ((uint8_t)fl != 0xff) ? pl.dt[0] : 1.0;
+        if (restage) {
+            stage_wait(st);
+        } else {
+            dt_nx = ((uint8_t)fl != 0xff) ? pl.dt[0] : 1.0;
 #pragma unroll
-        for (int d = 0; d < ND; ++d) y_nx[d] = ((uint8_t)fl != 0xff) ? pl.obs[d][0] : 0.0;
+            for (int d = 0; d < ND; ++d) y_nx[d] = ((uint8_t)fl != 0xff) ? pl.obs[d][0] : 0.0;
+        }
 #pragma unroll 1
         for (int k = 0; k < LC; ++k) {
             const uint8_t f = (uint8_t)(fl >> (8 * k));
             if (f == 0xff) break;
             const int64_t pos = base + k * 32;
-            const double dtv = dt_nx;
-            double y[ND];
+            double dtv, y[ND];
+            if (restage) {
+                dtv = st.buf[k * 32 + lane];
 #pragma unroll
-            for (int d = 0; d < ND; ++d) y[d] = y_nx[d];
-            if (k + 1 < LC && (uint8_t)(fl >> (8 * (k + 1))) != 0xff) {
-                dt_nx = pl.dt[(k + 1) * 32];
+                for (int d = 0; d < ND; ++d) y[d] = st.buf[(1 + d) * WT + k * 32 + lane];
+            } else {
+                dtv = dt_nx;
 #pragma unroll
-                for (int d = 0; d < ND; ++d) y_nx[d] = pl.obs[d][(k + 1) * 32];
+                for (int d = 0; d < ND; ++d) y[d] = y_nx[d];
+                if (k + 1 < LC && (uint8_t)(fl >> (8 * (k + 1))) != 0xff) {
+                    dt_nx = pl.dt[(k + 1) * 32];
+#pragma unroll
+                    for (int d = 0; d < ND; ++d) y_nx[d] = pl.obs[d][(k + 1) * 32];
+                }
             }
             if (f & ROW_START) {
                 s = track_start_state<M>(a, dtv);
