@@ -100,7 +100,12 @@ def known_ctcrw(dat, par):
         for a, ja in enumerate(seen):
             for b_, jb in enumerate(seen):
                 Cy[a * d:(a + 1) * d, b_ * d:(b_ + 1) * d] = Z @ cov[ja, jb] @ Z.T
-        Cy += h * np.eye(seen.size * d)
+        H_array = dat.get("H_array")
+        if H_array is not None and np.size(H_array) > 1:        # user measurement covariances, nllk_ctcrw.hpp:203-205
+            for a, ja in enumerate(seen):
+                Cy[a * d:(a + 1) * d, a * d:(a + 1) * d] += np.asarray(H_array, float)[:, :, rows[ja]]
+        else:
+            Cy += h * np.eye(seen.size * d)
         y = obs[rows[seen]].ravel()
         llk += multivariate_normal(my, Cy, allow_singular=False).logpdf(y)
         llk += 0.5 * seen.size * d * math.log(2 * math.pi)      # constant the template omits

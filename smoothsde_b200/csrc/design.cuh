@@ -293,8 +293,12 @@ __device__ __forceinline__ bool nonzero(const Dual& x) { return x.v != 0.0 || x.
 // Uniform warp-tile: per-lane partial sums over the LC rows go to a per-warp scratch T(j, lane)
 // in shared memory (accessor `T`), then lane j adds up row j of T -- no shuffles, one atomic per
 // slot.  The caller guarantees that T has room for w.S slots.
+#ifndef SSDE_SCATTER_BATCH
+#define SSDE_SCATTER_BATCH 4
+#endif
 template <int NP, class R, class EB, class TA>
 __device__ __forceinline__ void scatter_warptile_transposed(const WtViewT<R>& w, const GradAccT<R>& g, EB eb, TA T) {
+    constexpr int SB = SSDE_SCATTER_BATCH;
     const int lane = threadIdx.x & 31;
     const size_t ks = (size_t)w.S * 32;
     const double* vj = w.v;
@@ -306,27 +310,27 @@ __device__ __forceinline__ void scatter_warptile_transposed(const WtViewT<R>& w,
         R e[LC];
 #pragma unroll
         for (int k = 0; k < LC; ++k) e[k] = eb(k, p);
-        // 4 slots x LC rows = 32 independent loads in flight per batch
+        // SB slots x LC rows independent loads in flight per batch
 #pragma unroll 1
-        for (int i = 0; i < kp; i += 4) {
-            double v[4][LC];
+        for (int i = 0; i < kp; i += SB) {
+            double v[SB][LC];
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
+            for (int u = 0; u < SB; ++u)
 #pragma unroll
                 for (int k = 0; k < LC; ++k) v[u][k] = (i + u < kp) ? __ldg(vj + u * 32 + k * ks) : 0.0;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < SB; ++u) {
                 R acc = 0.0;
 #pragma unroll
                 for (int k = 0; k < LC; ++k) acc = fmad(v[u][k], e[k], acc);
                 if (i + u < kp) T(j + u, lane) = acc;
             }
-            vj += 128;
-            j += 4;
+            vj += SB * 32;
+            j += SB;
         }
-        // slots were advanced in steps of 4: step back to the first slot of the next parameter
+        // slots were advanced in steps of SB: step back to the first slot of the next parameter
         {
-            const int over = (4 - (kp & 3)) & 3;
+            const int over = (SB - kp % SB) % SB;
             vj -= over * 32;
             j -= over;
         }

@@ -39,6 +39,13 @@ CASES = [
     ("ou_ssm_d2_2x50", "OU_SSM", 2, 50, 0.1, 2, 108, [0.3, -0.2]),
     ("bm_ssm_d1_3x40", "BM_SSM", 3, 40, 0.1, 1, 109, [0.25]),
 ]
+# user H_array / general P0 (coupled filter) and decay terms: problems from tests/test_dense.py, tests/test_decay.py
+FEATURE_CASES = [
+    ("ctcrw_d2_userH_2x40", "dense", ("CTCRW", 2, 40, 2, 0.1, 111, True, True)),
+    ("ou_ssm_d2_userH_2x40", "dense", ("OU_SSM", 2, 40, 2, 0.1, 112, True, False)),
+    ("ou_d1_decay_3x50", "decay", ("OU", 3, 50, 1, 113)),
+    ("bm_d2_decay_2x60", "decay", ("BM", 2, 60, 2, 114)),
+]
 ONLY = sys.argv[1:]          # optional: names of the fixtures to (re)generate
 
 
@@ -53,8 +60,40 @@ def pack(dat, par, nllk, grad, extra):
         out[nm + "_shape"] = np.array(M.shape)
     if dat["type"] in ("CTCRW", "OU_SSM", "BM_SSM"):
         out["a0"], out["P0"] = dat["a0"], dat["P0"]
+    for nm in ("H_array", "t_decay", "col_decay", "ind_decay"):
+        if dat.get(nm) is not None:
+            out[nm] = np.asarray(dat[nm])
     out.update(extra)
     return out
+
+
+def feature_cases():
+    """Fixtures of the coupled filter (user H_array / P0) and of the decay terms.  Known answers:
+    one dense multivariate normal per track (CTCRW), the objective of the pre-scaled design (decay)."""
+    import warnings
+    sys.path.insert(0, os.path.dirname(HERE))
+    from test_dense import dense_problem
+    from test_decay import decay_problem
+    for name, kind, args in FEATURE_CASES:
+        if ONLY and name not in ONLY:
+            continue
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            if kind == "dense":
+                dat, par = dense_problem(*args)
+                ka = KA.known_ctcrw(dat, par) if dat["type"] == "CTCRW" else O.nllk(dat, par)
+            else:
+                dat, par, _ = decay_problem(*args)
+                p = O.split_par(dat, par)
+                plain = {k: v for k, v in dat.items() if k not in ("t_decay", "col_decay", "ind_decay")}
+                plain["X_re"] = O.decayed_X_re(dat, p["log_decay"])
+                ka = O.nllk(plain, np.r_[p["coeff_fe"], p["log_lambda"], p["coeff_re"]])
+            v = O.nllk(dat, par)
+            assert abs(ka - v) <= 1e-11 * abs(v), (name, ka, v)
+            g = O.grad_complex_step(dat, par)
+            extra = {"known_answer": np.array(ka), "hess": O.hess_complex_fd(dat, par)}
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **pack(dat, par, v, g, extra))
+        print(f"{name}: n={dat['obs'].shape[0]} npar={par.size} nllk={v:.15g} known={ka:.15g}")
 
 
 def main():
@@ -101,3 +140,4 @@ def main():
 
 if __name__ == "__main__":
     main()
+    feature_cases()

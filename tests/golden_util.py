@@ -12,6 +12,11 @@ def names():
     return sorted(os.path.splitext(os.path.basename(f))[0] for f in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
 
 
+def c_oracle_covers(dat):
+    """The C oracle restates the default-shaped models only (no user H_array, no decay terms)."""
+    return dat.get("H_array") is None and dat.get("t_decay") is None
+
+
 def load(name):
     z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
     dat = {"type": str(z["type"]), "ID": z["ID"], "times": z["times"], "obs": z["obs"],
@@ -20,6 +25,9 @@ def load(name):
         dat[nm] = sp.csr_matrix((z[nm + "_x"], (z[nm + "_i"], z[nm + "_j"])), shape=tuple(z[nm + "_shape"]))
     if dat["type"] in ("CTCRW", "OU_SSM", "BM_SSM"):
         dat["a0"], dat["P0"] = z["a0"], z["P0"]
+    for nm in ("H_array", "t_decay", "col_decay", "ind_decay"):      # coupled filter / decay fixtures
+        if nm in z:
+            dat[nm] = z[nm]
     out = {"par": z["par"], "nllk": float(z["nllk"]), "grad": z["grad"],
            "known_answer": float(z["known_answer"])}
     if "nllk_mpmath" in z:

@@ -112,3 +112,15 @@ def test_dense_tangent_matches_finite_differences(harness, model, T, m, nd, user
         assert abs(llk2[1] - dd) <= 1e-8 * max(abs(dd), 1.0)
         assert np.max(np.abs(ebd - ebd_fd)) <= 5e-7 * max(np.max(np.abs(ebd_fd)), 1.0)
         assert abs(g_lso_dot - gsd_fd) <= 5e-7 * max(abs(gsd_fd), 1.0)
+
+
+@pytest.mark.parametrize("nd,user_H,user_P0", [(2, True, True), (2, True, False), (1, True, True), (2, False, True)])
+def test_oracle_with_user_H_and_P0_matches_dense_mvn(nd, user_H, user_P0):
+    """Pins the oracle's H_array / general-P0 branches without any recursion: one multivariate
+    normal density per track (oracle/known_answers.py)."""
+    from oracle import known_answers as KA
+    dat, par = dense_problem("CTCRW", 2, 25, nd, 0.15, 61, user_H, user_P0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        v = O.nllk(dat, par)
+    assert abs(KA.known_ctcrw(dat, par) - v) <= 1e-10 * abs(v)

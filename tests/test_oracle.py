@@ -37,7 +37,7 @@ def test_numpy_oracle_reproduces_golden(name):
         assert abs(gold["nllk_mpmath"] - gold["nllk"]) <= 1e-12 * abs(gold["nllk"])
 
 
-@pytest.mark.parametrize("name", [n for n in G.names() if "_ssm_" not in n])     # the C oracle covers BM, OU, CTCRW
+@pytest.mark.parametrize("name", [n for n in G.names() if "_ssm_" not in n and "_userH_" not in n and "_decay_" not in n])     # the C oracle covers default-shaped BM, OU, CTCRW
 def test_c_oracle_reproduces_golden(name):
     dat, gold = G.load(name)
     for threads in (1, 2):
