@@ -17,7 +17,8 @@ def decay_problem(model, T, m, nd, seed, n_dec=2):
     n_par = dat["X_fe"].shape[0] // n
     t = np.asarray(dat["times"], float)
     ID = np.asarray(dat["ID"])
-    t0 = np.array([t[ID == i][0] for i in ID])
+    first = np.r_[True, ID[1:] != ID[:-1]]
+    t0 = t[np.maximum.accumulate(np.where(first, np.arange(n), 0))]     # time of the track's first row
     dat["t_decay"] = np.tile((t - t0) * 0.02, n_par) * np.repeat(1.0 + 0.1 * np.arange(n_par), n)
     p_re = dat["X_re"].shape[1]
     cols = np.arange(1, min(p_re, 6) + 1)
