@@ -151,7 +151,13 @@ __global__ void __launch_bounds__(SDE_NT) sde_decay_kernel(SdeArgs a, DecayArgs 
     constexpr int NWARP = SDE_NT / 32;
     constexpr int MAXDEC = 16;
     __shared__ double red[8];
+    __shared__ R sgrad[SDE_SGRAD];     // per-CTA accumulators of d nllk / d theta (when p_theta fits)
+    __shared__ R sdec[MAXDEC];         // ... and of d nllk / d log_decay
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    GradAccT<R> gacc{(a.p_theta <= SDE_SGRAD) ? sgrad : nullptr, a.grad_theta, a.p_theta};
+    for (int i = tid; i < SDE_SGRAD; i += SDE_NT) sgrad[i] = 0.0;
+    if (tid < MAXDEC) sdec[tid] = 0.0;
+    __syncthreads();
     R rho[MAXDEC];
 #pragma unroll
     for (int k = 0; k < MAXDEC; ++k)
@@ -176,10 +182,9 @@ __global__ void __launch_bounds__(SDE_NT) sde_decay_kernel(SdeArgs a, DecayArgs 
         for (int k = 0; k < LC; ++k) {
             const int64_t pos = base + k * 32;
             const uint8_t f0 = a.flags[pos];
-            if (f0 == 0xff || (f0 & ROW_LAST)) continue;        // ID(i) == ID(i+1), nllk_sde.hpp:79
+            const bool live = f0 != 0xff && !(f0 & ROW_LAST);      // ID(i) == ID(i+1), nllk_sde.hpp:79
             const int64_t npos = (k < LC - 1) ? pos + 32 : row_pos(row0 + k + 1);
-            const uint8_t f1 = a.flags[npos];
-            // nonzero j of parameter p: value, column, decay factor
+            // nonzero j of parameter p: value, column, decay factor (all lanes walk the same slots)
             auto each = [&](auto&& fn) {
                 int j = 0;
 #pragma unroll
@@ -207,19 +212,40 @@ __global__ void __launch_bounds__(SDE_NT) sde_decay_kernel(SdeArgs a, DecayArgs 
 #pragma unroll
                 for (int pp = 0; pp < NP; ++pp) if (pp == p) eta[pp] += x * (theta_at<R>(a.theta, c) * fac);
             });
-            sde_row<MODEL, ND>(eta, a.dt[pos], (unsigned)((f0 | f1) >> 3),
-                               [&](int dd, int nx) { return a.obs[(size_t)dd * a.X.n_pad + (nx ? npos : pos)]; }, llk, eb);
+            if (live) {
+                const uint8_t f1 = a.flags[npos];
+                sde_row<MODEL, ND>(eta, a.dt[pos], (unsigned)((f0 | f1) >> 3),
+                                   [&](int dd, int nx) { return a.obs[(size_t)dd * a.X.n_pad + (nx ? npos : pos)]; }, llk, eb);
+            }
             if (a.want_grad) {
                 each([&](int p, double x, uint32_t c, int dk, const R& fac, const R& dfac) {
                     R e = 0.0;
 #pragma unroll
                     for (int pp = 0; pp < NP; ++pp) if (pp == p) e = eb[pp];
-                    if (x == 0.0) return;
-                    atomic_add_r<R>(a.grad_theta, (int)c, a.p_theta, e * (x * fac));
-                    if (dk >= 0) atomic_add_r<R>(dc.grad_decay, dk, dc.n_dec, e * (x * (theta_at<R>(a.theta, c) * dfac)));
+                    R gt = e * (x * fac);
+                    R gd = (dk >= 0) ? R(e * (x * (theta_at<R>(a.theta, c) * dfac))) : R(0.0);
+                    if (uniform) {
+                        // every lane holds the same column: one shared-memory atomic per warp
+                        gt = warp_sum(gt);
+                        if (lane == 0 && nonzero(gt)) grad_add(gacc, c, gt);
+                        if (dk >= 0) {                           // dk is warp-uniform here
+                            gd = warp_sum(gd);
+                            if (lane == 0) { atomicAdd(&reinterpret_cast<double*>(&sdec[dk])[0], value(gd));
+                                             if constexpr (!std::is_same<R, double>::value) atomicAdd(&sdec[dk].d, gd.d); }
+                        }
+                    } else {
+                        if (nonzero(gt)) grad_add(gacc, c, gt);
+                        if (dk >= 0 && nonzero(gd)) { atomicAdd(&reinterpret_cast<double*>(&sdec[dk])[0], value(gd));
+                                                      if constexpr (!std::is_same<R, double>::value) atomicAdd(&sdec[dk].d, gd.d); }
+                    }
                 });
             }
         }
+    }
+    __syncthreads();
+    if (a.want_grad) {
+        grad_flush(gacc, SDE_NT);
+        if (tid < dc.n_dec) atomic_add_r<R>(dc.grad_decay, tid, dc.n_dec, sdec[tid]);
     }
     const double bl = block_sum<SDE_NT>(value(llk), red);
     if (threadIdx.x == 0) a.block_llk[blockIdx.x] = bl;
