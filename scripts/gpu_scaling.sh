@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-T=r45
+T=${1:-scale}
 run() { # N workload
   timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $1 --master-addr 127.0.0.1 --master-port $((29600 + $1 + ${3:-0})) bench.py --gpus $1 --workload $2 --steps 20 --warmup 3 > gpurun_out/${T}_$2_$1.log 2>&1
   python - gpurun_out/${T}_$2_$1.log $1 $2 <<'PY'
