@@ -52,6 +52,6 @@ MakeADFun_b200 <- function(data, parameters, map = list(), random = NULL, device
              A <- matrix(0, length(active), length(ok)); A[cbind(k, seq_along(ok))] <- 1
              A %*% H[ok, ok] %*% t(A)
          },
-         report = function(...) list(aest_all = .Call("ssde_aest", ptr, nrow(data$obs), ncol(data$obs))),
+         report = function(...) list(aest_all = .Call("ssde_aest", ptr, nrow(data$obs), ncol(data$a0))),
          env = env, ptr = ptr)
 }

@@ -139,9 +139,10 @@ SEXP ssde_layout(SEXP ptr) {
 }
 
 // REPORT(aest_all) (nllk_ctcrw.hpp:249) at the parameters of the last evaluation
-SEXP ssde_aest(SEXP ptr, SEXP n, SEXP n_dim) {
+// n_state = columns of aest_all: 2 * n_dim for CTCRW, n_dim for BM_SSM / OU_SSM (= ncol(a0))
+SEXP ssde_aest(SEXP ptr, SEXP n, SEXP n_state) {
     ssde_handle* h = (ssde_handle*)R_ExternalPtrAddr(ptr);
-    SEXP out = PROTECT(Rf_allocMatrix(REALSXP, Rf_asInteger(n), 2 * Rf_asInteger(n_dim)));
+    SEXP out = PROTECT(Rf_allocMatrix(REALSXP, Rf_asInteger(n), Rf_asInteger(n_state)));
     int rc = ssde_report(h, REAL(out));
     UNPROTECT(1);
     if (rc != SSDE_OK) Rf_error("smoothsde_b200: %s", ssde_last_error(h));

@@ -112,3 +112,29 @@ def test_parameter_layout_of_synthetic_problems():
     assert par.size == 1 + info["p_fe"] + info["n_s"] + info["p_re"] == 1 + 4 + 2 + 18
     dat, par, info = synth.make_problem("OU", 3, 30, n_dim=1)
     assert info["p_fe"] == 3 and info["p_re"] == 2 * (9 + 3) and info["n_s"] == 4
+
+
+def test_r_shim_type_checks_against_the_c_abi():
+    """The R shim cannot be built here (no R): compile it for syntax and types against stub
+    declarations of the R API it uses (tests/harness/r_stub) and the real include/smoothsde_b200.h,
+    and check that every routine it registers is defined and that it only calls exported symbols."""
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    stub = os.path.join(root, "tests", "harness", "r_stub")
+    inc = os.path.join(root, "include")
+    shim = os.path.join(root, "r_shim", "src", "shim.cpp")
+    init = os.path.join(root, "r_shim", "src", "init.c")
+    subprocess.check_call(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-Werror", "-I" + stub, "-I" + inc, shim])
+    subprocess.check_call(["gcc", "-fsyntax-only", "-Wall", "-Werror", "-I" + stub, init])
+    src = open(shim).read()
+    registered = re.findall(r'\{"(ssde_\w+)",\s*\(DL_FUNC\)', open(init).read())
+    defined = set(re.findall(r"^SEXP (ssde_\w+)\(", src, flags=re.M))
+    assert registered and set(registered) <= defined
+    from smoothsde_b200 import _lib as L
+    called = set(re.findall(r"\b(ssde_\w+)\(", src)) - defined
+    called -= {"ssde_handle", "ssde_laplace", "ssde_desc", "ssde_triplet"}
+    assert called <= set(L.EXPORTS), called - set(L.EXPORTS)
+    # the R adapter only .Call()s registered routines
+    rsrc = open(os.path.join(root, "r_shim", "R", "adfun.R")).read()
+    assert set(re.findall(r'\.Call\("(\w+)"', rsrc)) <= set(registered)
