@@ -162,3 +162,25 @@ def test_sde_host_layer_with_user_H_maps_log_sigma_obs_off():
     g_ref = obj.reduce_grad(oracle(tmb_dat, full)[1], obj._active)
     assert grad_err(obj.gr(par), g_ref) <= GRAD_RTOL
     obj.close()
+
+
+def test_coupled_laplace_gradient_matches_differences_of_its_value():
+    """The Laplace marginal over coeff_re (inner Newton with exact H_bb from tangent passes of the
+    coupled kernels, third-derivative differences for its gradient) on a model with a user H_array:
+    log_sigma_obs is mapped off as the reference does (R/sde.R:593-595)."""
+    from smoothsde_b200.adfun import ADFun
+    from test_gpu_laplace import split
+    from smoothsde_b200 import synth
+    dat, par, info = synth.make_problem("CTCRW", 3, 120, n_dim=2, seed=78, k=5, missing_frac=0.1)
+    rng = np.random.default_rng(5)
+    A = rng.normal(size=(info["n"], 2, 2)) * 0.2
+    dat["H_array"] = np.ascontiguousarray((A @ A.transpose(0, 2, 1) + 0.02 * np.eye(2)).transpose(1, 2, 0))
+    obj = ADFun(dat, split(dat, par, info), map={"coeff_fe": [None, None, 2, 3], "log_sigma_obs": [None]}, random="coeff_re")
+    x = obj.par + 0.03 * np.arange(obj.par.size)
+    f, g = obj._laplace.fn_gr(x)
+    fd = np.empty(x.size)
+    for j in range(x.size):
+        e = np.zeros(x.size); e[j] = 1e-4
+        fd[j] = (obj.fn(x + e) - obj.fn(x - e)) / 2e-4
+    assert np.max(np.abs(g - fd)) <= 1e-6 * max(1.0, np.max(np.abs(fd))), (g, fd)
+    obj.close()
