@@ -119,3 +119,24 @@ def test_two_process_gloo_all_reduce_matches_single_process():
         assert abs(v - ref_v) <= 1e-12 * abs(ref_v)
         assert np.max(np.abs(g - ref_g)) <= 1e-10 * max(1.0, np.max(np.abs(ref_g)))
         assert np.max(np.abs(hv - ref_hv)) <= 1e-6 * max(1.0, np.max(np.abs(ref_hv)))
+
+
+def test_shard_rows_carries_user_H_and_decay_times():
+    """Per-row extras follow their rows: H_array[, , lo:hi] (nllk_ctcrw.hpp:203-205) and the
+    matching entries of every parameter block of t_decay (nllk_sde.hpp:53)."""
+    dat, par, info = synth.make_problem("CTCRW", 4, 30, n_dim=2, seed=2, k=5)
+    n = info["n"]
+    dat["H_array"] = np.arange(4 * n, dtype=float).reshape(2, 2, n)
+    (lo0, hi0), (lo1, hi1) = S.split_tracks(dat["ID"], 2)
+    sub, cp, cn, _ = S.shard_rows(dat, lo1, hi1)
+    assert not cp and not cn and np.array_equal(sub["H_array"], dat["H_array"][:, :, lo1:hi1])
+    assert sub["a0"].shape[0] == np.unique(np.asarray(dat["ID"])[lo1:hi1]).size
+    dat2, par2, info2 = synth.make_problem("OU", 4, 30, n_dim=1, seed=2, k=5)
+    n2, n_par = info2["n"], 3
+    dat2["t_decay"] = np.arange(n_par * n2, dtype=float)
+    dat2["col_decay"], dat2["ind_decay"] = np.array([1, 2]), np.array([1, 1])
+    lo, hi = S.split_tracks(dat2["ID"], 2)[1]
+    sub2, _, _, _ = S.shard_rows(dat2, lo, hi)
+    want = np.concatenate([dat2["t_decay"][j * n2 + lo:j * n2 + hi] for j in range(n_par)])
+    assert np.array_equal(sub2["t_decay"], want) and sub2["X_re"].shape[0] == n_par * (hi - lo)
+    assert list(sub2["col_decay"]) == [1, 2]
