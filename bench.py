@@ -280,7 +280,7 @@ def main():
     else:
         peak = 6650.0; peak_src = "fallback (B200_PROFILING.md)"
     # B_alg = (8d + 8 + 4) + 2 [12 nnz/n + 8 n_par] = 620 B/obs per evaluation.  Per
-    # launch (DESIGN.md 4.3): the forward kernel owns the data term and one design pass
+    # launch (DESIGN.md 4.7): the forward kernel owns the data term and one design pass
     # (28 + 296 = 324 B/obs), the adjoint kernel the second design pass (296 B/obs).
     nnz_row = info["nnz"] / n_local
     b_alg = devgen.alg_bytes_per_obs(info["n_dim"], info["n_par"], nnz_row)
