@@ -40,6 +40,10 @@ CASES = [
     ("BM_SSM", 2, 300, 3, 0.2, True, False),
     ("BM_SSM", 2, 700, 2, 0.1, False, True),
     ("OU_SSM", 2, 300, 1, 0.1, True, False),       # n_dim = 1: a scalar h_i per row
+    ("CTCRW", 1, 2, 2, 0.0, True, False),          # a single transition-free track (two rows)
+    ("CTCRW", 7, 301, 2, 0.5, True, True),         # half of the rows missing
+    ("CTCRW", 2, 512, 2, 0.02, True, False),       # track boundary exactly on a tile boundary (64 threads x 8 rows)
+    ("BM_SSM", 30, 4, 3, 0.2, True, True),         # many tiny tracks, three coupled dimensions
 ]
 
 
