@@ -21,6 +21,7 @@ MakeADFun_b200 <- function(data, parameters, map = list(), random = NULL, device
     active <- free[!is_random[free]]                  # what optim sees (obj$par); random effects are integrated out
     env <- new.env()
     env$last.par <- full; env$last.par.best <- full; env$value.best <- Inf
+    env$active <- active; env$random <- which(is_random & !is.na(group))   # positions in the full vector (TMB: env$random)
     scatter <- function(x) {
         p <- env$last.par                             # keeps coeff_re of the last inner optimum (warm start)
         ok <- !is.na(group) & !is_random
@@ -54,4 +55,52 @@ MakeADFun_b200 <- function(data, parameters, map = list(), random = NULL, device
          },
          report = function(...) list(aest_all = .Call("ssde_aest", ptr, nrow(data$obs), ncol(data$a0))),
          env = env, ptr = ptr)
+}
+
+# What SDE$fit() takes from TMB::sdreport(obj, getJointPrecision = TRUE) (R/sde.R:702-719, :871-887,
+# :1323, :1360-1366): par.fixed, par.random, cov.fixed and jointPrecision (rows / columns named by
+# parameter, in the order of the full free parameter vector).  Same formulas as the Python mirror
+# (smoothsde_b200/adfun.py: ADFun.sdreport, checked in tests/test_gpu_laplace.py):
+#   no random effects: jointPrecision = exact joint Hessian (obj$he);
+#   random effects:    H_f = Hessian of the Laplace marginal (central differences of its gradient,
+#                      like optimHess), H_bb and G = H_{b,theta} from the exact joint Hessian at
+#                      (theta, b_hat):  Q = [[H_f + G' H_bb^-1 G, G'], [G, H_bb]]   (TMB's formula).
+# `obj` must come from MakeADFun_b200; `obj_joint` is the companion object without `random`
+# (SDE$setup() builds both, R/sde.R:656-669).
+sdreport_b200 <- function(obj, obj_joint = NULL, par.fixed = obj$env$last.par.best[obj$env$active], step = 1e-4) {
+    x <- par.fixed
+    nms <- names(obj$par)
+    if(length(obj$env$random) == 0) {
+        H <- obj$he(x)
+        dimnames(H) <- list(nms, nms)
+        return(structure(list(par.fixed = x, par.random = numeric(0), cov.fixed = solve(H),
+                              jointPrecision = H, value = obj$fn(x)), class = "sdreport_b200"))
+    }
+    if(is.null(obj_joint)) stop("sdreport_b200: the joint object (random = NULL) is needed for the joint precision")
+    nt <- length(x)
+    Hf <- matrix(0, nt, nt)
+    for(j in seq_len(nt)) {
+        h <- step * max(1, abs(x[j]))
+        e <- replace(numeric(nt), j, h)
+        Hf[, j] <- (as.numeric(obj$gr(x + e)) - as.numeric(obj$gr(x - e))) / (2 * h)
+    }
+    Hf <- (Hf + t(Hf)) / 2
+    f <- obj$fn(x)                                    # leaves (theta, b_hat) in env$last.par
+    p <- obj$env$last.par
+    free <- obj_joint$env$active                      # every free entry of the full vector, in vector order
+    H <- obj_joint$he(p[free])
+    is_rand <- free %in% obj$env$random
+    Hbb <- H[is_rand, is_rand, drop = FALSE]
+    G <- H[is_rand, !is_rand, drop = FALSE]
+    Q <- H
+    Q[!is_rand, !is_rand] <- Hf + t(G) %*% solve(Hbb, G)
+    dimnames(Q) <- list(names(p)[free], names(p)[free])
+    structure(list(par.fixed = x, par.random = p[obj$env$random], cov.fixed = solve(Hf),
+                   jointPrecision = Q, value = f), class = "sdreport_b200")
+}
+
+# as.list(rep, "Estimate") (R/sde.R:707): estimates split by parameter name
+as.list.sdreport_b200 <- function(x, what = "Estimate", ...) {
+    est <- c(x$par.fixed, x$par.random)
+    split(unname(est), factor(names(est), levels = unique(names(est))))
 }
