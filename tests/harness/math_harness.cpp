@@ -5,6 +5,7 @@
 // Nothing in the product path links or loads this file.
 #include <cstdint>
 #include <cstring>
+#include <type_traits>
 #include <vector>
 
 #include "../../smoothsde_b200/csrc/models.cuh"
@@ -278,4 +279,21 @@ extern "C" int harness_dense(int model, int nd, int mode, int64_t n, const uint8
     return with_dense_model<double>(model, nd, [&](auto mm) {
         return run<decltype(mm)>(mode, n, flags, y, dt, eta, nullptr, a0, pc, h, lc, nt, out_llk2, eta_bar, nullptr, out_gh2, aest, Hplanes);
     });
+}
+
+// dense_math.cuh helpers on their own: pivoted inverse of a general N x N matrix (row-major in / out)
+extern "C" int harness_inv_general(int n, const double* X, double* Xi) {
+    auto run_n = [&](auto tag) {
+        constexpr int N = decltype(tag)::value;
+        double a[N][N], b[N][N];
+        for (int i = 0; i < N; ++i) for (int j = 0; j < N; ++j) a[i][j] = X[i * N + j];
+        inv_general<N>(a, b);
+        for (int i = 0; i < N; ++i) for (int j = 0; j < N; ++j) Xi[i * N + j] = b[i][j];
+        return 0;
+    };
+    if (n == 1) return run_n(std::integral_constant<int, 1>{});
+    if (n == 2) return run_n(std::integral_constant<int, 2>{});
+    if (n == 3) return run_n(std::integral_constant<int, 3>{});
+    if (n == 4) return run_n(std::integral_constant<int, 4>{});
+    return 1;
 }

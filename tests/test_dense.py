@@ -124,3 +124,24 @@ def test_oracle_with_user_H_and_P0_matches_dense_mvn(nd, user_H, user_P0):
         warnings.simplefilter("ignore")
         v = O.nllk(dat, par)
     assert abs(KA.known_ctcrw(dat, par) - v) <= 1e-10 * abs(v)
+
+
+def test_pivoted_inverse_handles_vanishing_leading_minors(harness):
+    """(I + C J) of the scan combine has positive eigenvalues but is not symmetric: with
+    C = [[1, 3], [3, 10]], J = [[1, -3], [-3, 10]] its (1, 1) entry is 1 + 1 - 9 = -7, and leading
+    minors can vanish altogether -- elimination without row exchanges would divide by zero."""
+    import ctypes
+    rng = np.random.default_rng(0)
+    mats = [np.array([[0.0, 1.0], [1.0, 0.0]]), np.array([[0.0, 2.0, 0.0], [0.0, 0.0, 3.0], [4.0, 0.0, 0.0]]),
+            np.eye(2) + np.array([[1.0, 3.0], [3.0, 10.0]]) @ np.array([[1.0, -3.0], [-3.0, 10.0]])]
+    for n in (1, 2, 3, 4):
+        for _ in range(20):
+            A, B = rng.normal(size=(n, n)), rng.normal(size=(n, n))
+            mats.append(np.eye(n) + (A @ A.T) @ (B @ B.T))
+    P = ctypes.POINTER(ctypes.c_double)
+    for X in mats:
+        X = np.ascontiguousarray(X, float)
+        Xi = np.zeros_like(X)
+        assert harness.harness_inv_general(X.shape[0], X.ctypes.data_as(P), Xi.ctypes.data_as(P)) == 0
+        ref = np.linalg.inv(X)
+        assert np.max(np.abs(Xi - ref)) <= 1e-12 * np.linalg.cond(X) * np.max(np.abs(ref))
