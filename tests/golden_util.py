@@ -36,4 +36,8 @@ def load(name):
         out["hess"] = z["hess"]
     if "aest_all" in z:
         out["aest_all"] = z["aest_all"]
+    # outputs of the reference's own objective (tests/golden/make_ref_golden.py)
+    for nm in ("ref_nllk", "ref_grad", "ref_hess", "ref_aest_all"):
+        if nm in z:
+            out[nm] = float(z[nm]) if nm == "ref_nllk" else z[nm]
     return dat, out
