@@ -37,17 +37,33 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--tracks", type=int, default=1024)
     ap.add_argument("--track-steps", type=int, default=100000)
-    ap.add_argument("--cpu-tracks", type=int, default=64)
-    ap.add_argument("--cpu-track-steps", type=int, default=10000)
+    ap.add_argument("--cpu-tracks", type=int, default=128)
+    ap.add_argument("--cpu-track-steps", type=int, default=8192)
+    ap.add_argument("--cpu-b1-tracks", type=int, default=8, help="tracks of the CPU sample timed on ONE thread (B1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="tracks", choices=["tracks", "single"],
-                    help="tracks: BASELINE configs[2] (default, the headline); single: configs[3], ONE track of "
-                         "tracks*track_steps rows, sharded along time over the ranks")
+    ap.add_argument("--workload", default="both", choices=["both", "tracks", "single"],
+                    help="tracks: BASELINE configs[2] (the headline line); single: configs[3], ONE track of "
+                         "tracks*track_steps rows, sharded along time over the ranks; both (default): the headline "
+                         "line carries the time-sharded measurement under the key `single`")
+    ap.add_argument("--write-n1", action="store_true",
+                    help="(1 GPU) store this run's nllk as the N = 1 value that multi-GPU runs are checked against")
     return ap.parse_args()
 
 
+def host_cores():
+    """Cores this process may run on -- NOT omp_get_max_threads(): torch.distributed.run exports
+    OMP_NUM_THREADS=1, which must not shrink the CPU baseline."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 # ------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port (dense 2d x 2d Kalman recursion + hand adjoint, OpenMP over tracks)
+# CPU arm.  kind "reference": the reference's own objective (/root/reference/src/smoothSDE.cpp +
+# src/nllk/*.hpp, unmodified, compiled against oracle/tmb_shim/TMB.hpp into oracle/_ref), value +
+# gradient by one reverse sweep of the AD tape per track, tracks spread over a thread pool.
+# kind "port" (reported beside it): oracle/oracle_c.c, our C restatement with a hand-written adjoint.
 # ------------------------------------------------------------------------------------------------
 def cpu_problem(args):
     from smoothsde_b200 import synth
@@ -56,21 +72,57 @@ def cpu_problem(args):
     return dat, par, info
 
 
-def cpu_time_evals(args, steps, warmup):
-    """Returns (obs*eval/s, cores, sample description)."""
-    from oracle import oracle_c
-    dat, par, info = cpu_problem(args)
-    cores = min(oracle_c.max_threads(), os.cpu_count() or 1)
-    co = oracle_c.COracle(dat, nthreads=cores)
-    for _ in range(max(warmup, 1)):
-        co.eval(par, True)
+def _time_evals(fn, steps, warmup):
+    for _ in range(warmup):
+        fn()
     t0 = time.perf_counter()
     for _ in range(steps):
-        co.eval(par, True)
-    dt = time.perf_counter() - t0
-    sample = (f"{args.cpu_tracks} tracks x {args.cpu_track_steps} steps CTCRW d=2 (n={info['n']}), "
-              f"same formulas as the GPU workload, {steps} nllk+gradient evaluations")
-    return info["n"] * steps / dt, cores, sample, dt / steps * 1e3
+        fn()
+    return (time.perf_counter() - t0) / steps
+
+
+def cpu_time_evals(args, steps, warmup):
+    """Times nllk + gradient evaluations of a bounded sample of the GPU workload on the host cores.
+    Returns the cpu_baseline object (value = all-core figure of the preferred kind)."""
+    from oracle import oracle_c, oracle_ref
+    from smoothsde_b200 import sharded
+    dat, par, info = cpu_problem(args)
+    n = info["n"]
+    cores = host_cores()
+    b1_tracks = max(1, min(args.cpu_b1_tracks, args.cpu_tracks))
+    n1 = b1_tracks * args.cpu_track_steps
+    sub1 = sharded.shard_rows(dat, 0, n1)[0]
+    sample = (f"{args.cpu_tracks} tracks x {args.cpu_track_steps} irregular steps CTCRW d=2 (n={n}), same formulas and "
+              f"generator as the GPU workload; {steps} nllk+gradient evaluations after {warmup} warm-up; one-thread "
+              f"figure on the first {b1_tracks} tracks (n={n1})")
+    out = {"unit": UNIT, "cores": cores, "sample": sample, "rows": n, "steps": steps, "warmup": warmup}
+    co = oracle_c.COracle(dat, nthreads=cores)
+    s_port = _time_evals(lambda: co.eval(par, True), steps, warmup)
+    co1 = oracle_c.COracle(sub1, nthreads=1)
+    s_port1 = _time_evals(lambda: co1.eval(par, True), max(1, steps // 4), 1)
+    port = {"value": n / s_port, "ms_per_step": s_port * 1e3, "cores": cores,
+            "one_thread": {"value": n1 / s_port1, "rows": n1},
+            "what": "oracle/oracle_c.c: C restatement of nllk_ctcrw.hpp with a hand-written adjoint, OpenMP over tracks"}
+    if oracle_ref.available():
+        P = oracle_ref.RefOracleParallel(dat, cores)
+        s_ref = _time_evals(lambda: P.eval(par, True), steps, warmup)
+        v_ref, g_ref = P.eval(par, True)
+        P.close()
+        P1 = oracle_ref.RefOracleParallel(sub1, 1)
+        s_ref1 = _time_evals(lambda: P1.eval(par, True), max(1, steps // 4), 1)
+        P1.close()
+        v_port, g_port = co.eval(par, True)
+        out.update(value=n / s_ref, ms_per_step=s_ref * 1e3, kind="reference",
+                   one_thread={"value": n1 / s_ref1, "rows": n1, "cores": 1},
+                   what="the reference's own objective (src/smoothSDE.cpp + src/nllk/nllk_ctcrw.hpp, unmodified) "
+                        "compiled against oracle/tmb_shim/TMB.hpp (g++ -O2): eager containers + a reverse-mode AD tape "
+                        "re-recorded every evaluation, one track per task on a thread pool. TMB proper (CppAD/TMBad tape "
+                        "replay, Eigen) is not installed in this image; per-row arithmetic is the reference's.",
+                   port=port, port_agrees=abs(v_port - v_ref) / abs(v_ref))
+    else:
+        out.update(value=port["value"], ms_per_step=port["ms_per_step"], kind="port", one_thread=port["one_thread"],
+                   what=port["what"])
+    return out
 
 
 def run_reference(args):
@@ -78,17 +130,17 @@ def run_reference(args):
     if rank != 0:
         return
     steps = max(1, min(args.steps, 20))
-    val, cores, sample, ms = cpu_time_evals(args, steps, min(args.warmup, 2))
+    warmup = max(1, min(args.warmup, 3))
+    cb = cpu_time_evals(args, steps, warmup)
     line = {
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": steps, "warmup": min(args.warmup, 2), "ms_per_step": ms, "higher_is_better": True,
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "CTCRW d=2, tau,nu ~ s(time,k=10), bounded sample of BASELINE configs[2]",
-                   "sample": sample},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-                         "note": "C restatement of src/nllk/nllk_ctcrw.hpp with a hand-written adjoint; "
-                                 "TMB itself cannot be built in this image (no R/TMB/Eigen)"},
-        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": {"workload": "CTCRW d=2, tau,nu ~ s(time,k=10), mu fixed 0: bounded sample of BASELINE configs[2] "
+                               "(per-row cost does not depend on the number of rows)",
+                   "sample": cb["sample"]},
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
 
@@ -143,58 +195,48 @@ class Clocks:
 
 
 # ------------------------------------------------------------------------------------------------
-def main():
-    args = parse()
-    if args.impl == "reference":
-        run_reference(args)
-        return
+N1_FILE = os.path.join(ROOT, "profiles", "bench_nllk_n1.json")
+
+
+def measure(kind, args, ctx):
+    """One workload on this rank's GPU: build on the device, warm up, time `steps` evaluations
+    device-resident (CUDA events, max over ranks) and end to end through the public host-buffer
+    call.  kind: "tracks" (BASELINE configs[2], sharded by track ID) | "single" (configs[3], one
+    track sharded along time)."""
     import numpy as np
     import torch
     import torch.distributed as dist
-    from smoothsde_b200 import devgen, _lib
+    from smoothsde_b200 import devgen, _lib, sharded
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    assert args.tracks % world == 0, "tracks must divide by the number of ranks"
-
-    def dist_reduce(t, op):
-        if world > 1:
-            dist.all_reduce(t, op={"min": dist.ReduceOp.MIN, "max": dist.ReduceOp.MAX, "sum": dist.ReduceOp.SUM}[op])
-        return t
-
-    single = args.workload == "single"
-    ts = None
+    rank, world, local, dev, dist_reduce = ctx["rank"], ctx["world"], ctx["local"], ctx["dev"], ctx["dist_reduce"]
+    single = kind == "single"
+    ts = tse = None
+    comm = sharded.DistComm() if world > 1 else None
     if single:
-        from smoothsde_b200 import sharded
         n_all = args.tracks * args.track_steps
-        assert n_all % (world * 128) == 0
+        segs = 1024                     # the track is simulated as 1024 stitched segments for every world size
+        assert segs % world == 0 and n_all % segs == 0
         eng, par, info = devgen.make_ctcrw_device(
-            1, n_all // world, seed=20260104, device=local, rank=rank, world=world, sim_tracks=128,
-            dist_reduce=dist_reduce, shard_flags=(_lib.SHARD_NO_PENALTY if rank > 0 else 0), time_shard=world > 1)
+            1, n_all // world, seed=20260104, device=local, rank=rank, world=world, sim_tracks=segs // world,
+            dist_reduce=dist_reduce, dist_gather=ctx["dist_gather"],
+            shard_flags=(_lib.SHARD_NO_PENALTY if rank > 0 else 0), time_shard=world > 1)
         if world > 1:
-            ts = sharded.TimeShardedEngine.from_engine_distributed(eng, sharded.DistComm(), local)
+            ts = sharded.TimeShardedEngine.from_engine_distributed(eng, comm, local)
     else:
         tracks_local = args.tracks // world
         eng, par, info = devgen.make_ctcrw_device(
             tracks_local, args.track_steps, seed=20260103, device=local, rank=rank, world=world,
             dist_reduce=dist_reduce, shard_flags=(_lib.SHARD_NO_PENALTY if rank > 0 else 0))
+        if world > 1:
+            tse = sharded.TrackShardedEngine.from_engine(eng, comm, local)
     n_local = info["n"]
     n_total = n_local * world
     npar = eng.n_par
     par_dev = torch.as_tensor(par, device=dev)
     out_dev = torch.zeros(npar + 2, dtype=torch.float64, device=dev)
-    par_host = torch.as_tensor(par).pin_memory()
-    out_host = torch.zeros(npar + 2, dtype=torch.float64).pin_memory()
     # a non-default torch stream: the C ABI treats a NULL stream as "the handle's own stream",
     # and torch.cuda.Event only sees work on torch's current stream
-    tstream = ts.streams[0] if ts is not None else torch.cuda.Stream(device=dev)
+    tstream = ts.streams[0] if ts is not None else (tse.stream if tse is not None else torch.cuda.Stream(device=dev))
     torch.cuda.set_stream(tstream)
     stream = tstream.cuda_stream
     assert stream != 0
@@ -215,14 +257,15 @@ def main():
     for _ in range(max(args.warmup, 3)):
         step_device()
     barrier()
-    # sanity: finite objective, no device-side failure
-    eng.check()
+    eng.check()                            # no device-side failure
     first = out_dev.cpu().numpy().copy()
     assert np.isfinite(first[:npar + 1]).all(), "non-finite nllk / gradient"
 
     # ---- device-resident throughput (inputs already in HBM, results stay in HBM) ----
     clocks = Clocks(local)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if ts is not None:
+        ts.fallbacks = [0, 0]
     barrier()
     clocks.start()
     ev0.record()
@@ -235,6 +278,7 @@ def main():
     dist_reduce(ms_total, "max")
     ms_step = float(ms_total) / args.steps
     value = n_total / (ms_step * 1e-3)
+    fallbacks = list(ts.fallbacks) if ts is not None else [0, 0]
 
     # ---- per-kernel device times (CUDA events in front of every kernel, same stream) ----
     eng.set_profile(True)
@@ -252,28 +296,87 @@ def main():
     kernels = {nm: v / kcount for nm, v in ksum.items()}
     launches_per_step = eng.last_eval_launches
 
-    # ---- end to end through the public call with HOST buffers ----
+    # ---- end to end through the repo's public call with HOST buffers: Engine.eval (ssde_eval) on one
+    #      GPU, TrackShardedEngine.eval / TimeShardedEngine.eval on several: H2D of the parameter
+    #      vector, kernels (+ collectives), D2H of [nllk, gradient], host synchronisation, every step
     h2d, d2h = 8 * npar, 8 * (npar + 1)
+    api = eng if world == 1 else (ts if ts is not None else tse)
+    v = g = None
     barrier()
     t0 = time.perf_counter()
-    if world == 1:
-        for _ in range(args.steps):
-            v, g = eng.eval(par, order=1)           # ssde_eval: H2D par, kernels, D2H nllk+grad, sync
-    elif ts is not None:
-        for _ in range(args.steps):
-            v, g = ts.eval(par)                     # H2D par, 3 stages + collectives, D2H nllk+grad, sync
-    else:
-        for _ in range(args.steps):
-            par_dev.copy_(par_host, non_blocking=True)
-            step_device()
-            out_host.copy_(out_dev, non_blocking=True)
-            torch.cuda.synchronize()
+    for _ in range(args.steps):
+        v, g = api.eval(par, order=1)
     barrier()
     e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     dist_reduce(e2e_s, "max")
     e2e_value = n_total * args.steps / float(e2e_s)
+    assert abs(v - first[0]) <= 1e-12 * abs(first[0]), "host-buffer call and device-resident call disagree"
 
-    # ---- roofline ----
+    # ---- the same data set at every N: nllk against the stored 1-GPU value ----
+    key = f"{kind}:{args.tracks}x{args.track_steps}"
+    stored = json.load(open(N1_FILE)) if os.path.exists(N1_FILE) else {}
+    parity = None
+    if key in stored:
+        parity = abs(float(first[0]) - stored[key]["nllk"]) / abs(stored[key]["nllk"])
+        gs = np.asarray(stored[key]["grad"])
+        gerr = float(np.max(np.abs(first[1:npar + 1] - gs) / np.maximum(np.abs(gs), 1e-3 * np.abs(gs).max())))
+        assert parity <= 1e-10 and gerr <= 1e-7, f"{world}-GPU result differs from the stored 1-GPU result: {parity:.3e} / {gerr:.3e}"
+        parity = {"nllk_rel": parity, "grad_rel": gerr}
+    if args.write_n1 and world == 1 and rank == 0:
+        stored[key] = {"nllk": float(first[0]), "grad": [float(x) for x in first[1:npar + 1]],
+                       "par": [float(x) for x in par]}
+        json.dump(stored, open(N1_FILE, "w"), indent=1)
+
+    res = dict(kind=kind, eng=eng, info=info, n_local=n_local, n_total=n_total, npar=npar, ms_step=ms_step, value=value,
+               clk=clk, kernels=kernels, launches_per_step=launches_per_step, e2e_value=e2e_value, h2d=h2d, d2h=d2h,
+               nllk=float(first[0]), parity=parity, fallbacks=fallbacks, launch_info=eng.launch_info())
+    return res
+
+
+def release(res):
+    import torch
+    res["eng"].close()
+    res.pop("eng")
+    res.pop("info")
+    torch.cuda.empty_cache()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    import torch
+    import torch.distributed as dist
+    from smoothsde_b200 import devgen
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert args.tracks % world == 0, "tracks must divide by the number of ranks"
+
+    def dist_reduce(t, op):
+        if world > 1:
+            dist.all_reduce(t, op={"min": dist.ReduceOp.MIN, "max": dist.ReduceOp.MAX, "sum": dist.ReduceOp.SUM}[op])
+        return t
+
+    def dist_gather(t):
+        out = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, t.contiguous())
+        return out
+
+    ctx = dict(rank=rank, world=world, local=local, dev=dev, dist_reduce=dist_reduce, dist_gather=dist_gather)
+    head_kind = "single" if args.workload == "single" else "tracks"
+    r = measure(head_kind, args, ctx)
+    info, n_local, npar, kernels = r["info"], r["n_local"], r["npar"], r["kernels"]
+
+    # ---- roofline of the dominant kernel ----
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak = float(json.load(open(peaks_path))["hbm_gbs"]); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
@@ -289,17 +392,21 @@ def main():
     dev_ms = sum(kernels.values())
     dom = max((k for k in kernels if k in b_kernel), key=kernels.get)
     achieved = b_kernel[dom] * n_local / (kernels[dom] * 1e-3) / 1e9
-    traffic = None
+    traffic = dram_frac = None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath):                     # dram bytes of one launch from the committed ncu capture
         tj = json.load(open(tpath))
         k = tj["kernels"].get(dom)
         if k:
             traffic = (k["dram_bytes_read"] + k["dram_bytes_write"]) / tj["rows"] * n_local
+            dram_frac = traffic / (kernels[dom] * 1e-3) / 1e9 / peak
     ach_eval = b_alg * n_local / (dev_ms * 1e-3) / 1e9
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": traffic, "peak_source": peak_src, "kernel": dom,
+        "traffic": traffic, "dram_frac": dram_frac, "peak_source": peak_src, "kernel": dom,
+        "note": "frac = ALGORITHMIC bytes (SURVEY 8(d) CSR accounting) / launch time / peak; dram_frac = DRAM bytes "
+                "actually moved (ncu capture of this kernel, scaled by rows) / launch time / peak -- the packed layout "
+                "stores fewer bytes than the CSR accounting, so dram_frac is the memory system's real utilisation",
         "alg_bytes_per_launch": b_kernel[dom] * n_local, "launch_ms": kernels[dom],
         "traffic_source": "profiles/ncu_traffic.json (ncu --set full capture of this workload, scaled by rows per GPU)",
         "kernels_ms": kernels, "dominant_share": kernels[dom] / dev_ms,
@@ -307,10 +414,11 @@ def main():
         "evaluation": {"alg_bytes_per_obs": b_alg, "achieved": ach_eval, "frac": ach_eval / peak,
                        "note": "whole evaluation: 620 B/obs (SURVEY 8(d)) x rows on this GPU / summed kernel time"},
     }
-
+    single = head_kind == "single"
+    n_total = r["n_total"]
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+        "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": r["ms_step"], "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": (f"CTCRW d=2, ONE track of {n_total} irregular steps, tau,nu ~ s(time,k=10), mu fixed 0 "
                                 f"(BASELINE configs[3])" if single else
@@ -319,17 +427,39 @@ def main():
                    "sharding": (f"track cut along time over {world} rank(s): 2 NCCL all-gathers of one scan element + 1 all-reduce "
                                 f"of {npar + 2} doubles per evaluation" if single else
                                 f"tracks split over {world} rank(s), one NCCL all-reduce of {npar + 1} doubles per evaluation"),
+                   "same_data_at_every_n": "random draws are seeded per group of 64 tracks (devgen.GroupedRNG), so 1/2/4/8 "
+                                           "GPUs evaluate the identical data set; parity_vs_n1 checks nllk/gradient against "
+                                           "the stored 1-GPU result (profiles/bench_nllk_n1.json)",
                    "l2": "inputs per GPU (>= 3 GB) are far larger than the 126 MB L2; no flush needed"},
-        "clocks": clk,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-        "gpu_launches": launches_per_step * args.steps,
+        "clocks": r["clk"],
+        "e2e": {"value": r["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"],
+                "call": "Engine.eval (ssde_eval)" if world == 1 else ("TimeShardedEngine.eval" if single else "TrackShardedEngine.eval")},
+        "gpu_launches": r["launches_per_step"] * args.steps,
         "roofline": roofline,
-        "nllk": float(first[0]),
-        "launch_info": eng.launch_info(),
+        "nllk": r["nllk"],
+        "parity_vs_n1": r["parity"],
+        "launch_info": r["launch_info"],
     }
+    release(r)
+    if args.workload == "both":
+        # BASELINE configs[3]: ONE track of the same total length, sharded along time
+        r2 = measure("single", args, ctx)
+        k2 = r2["kernels"]
+        line["single"] = {
+            "workload": f"CTCRW d=2, ONE track of {r2['n_total']} irregular steps (BASELINE configs[3]), time-sharded over {world} rank(s)",
+            "ms_per_step": r2["ms_step"], "value": r2["value"], "unit": UNIT,
+            "e2e": {"value": r2["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": r2["h2d"], "d2h_bytes_per_step": r2["d2h"],
+                    "call": "Engine.eval (ssde_eval)" if world == 1 else "TimeShardedEngine.eval"},
+            "collectives_per_eval": ({"all_gather": 2, "all_reduce": 1} if world > 1 else {}),
+            "full_shard_fallbacks": {"forward_stage3": r2["fallbacks"][0], "adjoint_stage4": r2["fallbacks"][1],
+                                     "of_evaluations": args.steps},
+            "kernels_ms": k2, "gpu_launches": r2["launches_per_step"] * args.steps, "nllk": r2["nllk"],
+            "parity_vs_n1": r2["parity"], "clocks": r2["clk"],
+        }
+        line["gpu_launches"] += r2["launches_per_step"] * args.steps
+        release(r2)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        val, cores, sample, ms = cpu_time_evals(args, 5, 1)
-        line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        line["cpu_baseline"] = cpu_time_evals(args, 3, 1)
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

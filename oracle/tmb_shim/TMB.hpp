@@ -352,8 +352,7 @@ struct matrix {
             for (int j = 0; j < n; j++) { a(c, j) = a(c, j) * piv; inv(c, j) = inv(c, j) * piv; }
             for (int r = 0; r < n; r++) {
                 if (r == c) continue;
-                T f = a(r, c);
-                if (asDouble(f) == 0.0) continue;
+                T f = a(r, c);      // no zero-skipping: a zero-VALUED entry can still be an AD variable
                 for (int j = 0; j < n; j++) { a(r, j) = a(r, j) - f * a(c, j); inv(r, j) = inv(r, j) - f * inv(c, j); }
             }
         }

@@ -39,14 +39,12 @@ def _bspline_torch(x, k, lo, hi):
     return B
 
 
-def simulate_ctcrw_device(times, tau, nu, gen, device):
+def simulate_ctcrw_device(times, tau, nu, e1, e2, device):
     """Exact-transition CTCRW simulation (R/sde.R:1448-1478), one thread per track, by the
-    library's own simulator kernel (ssde_simulate_ctcrw).  times/tau/nu: [T, m] contiguous.
-    Returns z [T, m] for one dimension (mu = 0, start at 0)."""
+    library's own simulator kernel (ssde_simulate_ctcrw).  times/tau/nu and the standard normal
+    draws e1/e2: [T, m] contiguous.  Returns z [T, m] for one dimension (mu = 0, start at 0)."""
     import torch
     T, m = times.shape
-    e1 = torch.randn((T, m), dtype=torch.float64, device=times.device, generator=gen)
-    e2 = torch.randn((T, m), dtype=torch.float64, device=times.device, generator=gen)
     z = torch.zeros((T, m), dtype=torch.float64, device=times.device)
     lib = L.load()
     torch.cuda.synchronize(times.device)
@@ -71,24 +69,51 @@ def permute_rows(x, n_pad, lc, fill):
     return x.contiguous().reshape((n_pad,) + rest)
 
 
+RNG_GROUPS = 16
+
+
+class GroupedRNG:
+    """Random draws that do not depend on how the tracks are spread over ranks: the `total` tracks
+    (or track segments) are cut into RNG_GROUPS groups of consecutive tracks, every group has its
+    own generator seeded by (seed, global group index), and a rank draws for the groups it holds.
+    So bench.py evaluates the SAME data set at 1, 2, 4 and 8 GPUs."""
+
+    def __init__(self, seed, total, local, rank, dev):
+        import torch
+        self.g = total // RNG_GROUPS if total % RNG_GROUPS == 0 else 1
+        if local % self.g != 0:
+            raise ValueError(f"{local} tracks per rank is not a multiple of the RNG group size {self.g}")
+        first = rank * local // self.g
+        self.gens = []
+        for gid in range(first, first + local // self.g):
+            gen = torch.Generator(device=dev)
+            gen.manual_seed(int(seed) * 1000003 + gid)
+            self.gens.append(gen)
+        self.dev = dev
+
+    def draw(self, kind, m):
+        import torch
+        f = torch.rand if kind == "uniform" else torch.randn
+        return torch.cat([f((self.g, m), dtype=torch.float64, device=self.dev, generator=gen) for gen in self.gens], dim=0)
+
+
 def make_ctcrw_device(n_tracks, n_steps, seed=20260103, device=0, k=10, sigma_obs=0.1,
                       irregular=True, rank=0, world=1, sim_tracks=None, dist_reduce=None,
-                      shard_flags=0, time_shard=False):
-    """Build the rows of `n_tracks` tracks x `n_steps` steps on `device` (this rank's shard).
+                      shard_flags=0, time_shard=False, dist_gather=None):
+    """Build the rows of `n_tracks` tracks x `n_steps` steps on `device` (this rank's shard of
+    `world * n_tracks` tracks; the data set does not depend on `world`, see GroupedRNG).
 
-    sim_tracks: simulate only this many distinct tracks x (n_tracks*n_steps/sim_tracks) ... used
-    for the single-long-track configuration, where the track is simulated as `sim_tracks`
-    segments that are stitched together (positions made continuous).
-    dist_reduce(tensor, op) -> tensor: optional all-reduce across ranks so that every shard uses
-    the same knots and sum-to-zero constraint.
+    sim_tracks: the single-long-track configuration -- the track (n_steps rows on this rank) is
+    simulated as `sim_tracks` segments per rank that are stitched together (times and positions
+    made continuous, across ranks too when time_shard is set).
+    dist_reduce(tensor, op) -> tensor: all-reduce across ranks so that every shard uses the same
+    knots and sum-to-zero constraint.  dist_gather(tensor) -> [world, numel] tensor (time_shard).
     time_shard: (with sim_tracks) this rank holds slab `rank` of `world` of ONE track of
     world * n_steps rows: its times follow the previous slab's, only rank 0 has the track start,
     only the last rank the track end (SSDE_SHARD_CONT_PREV / CONT_NEXT are set accordingly).
     Returns (engine, par, info)."""
     import torch
     dev = torch.device("cuda", device)
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(seed + 1000 * rank)
     nd = 2
     T, m = n_tracks, n_steps
     single = sim_tracks is not None
@@ -97,32 +122,48 @@ def make_ctcrw_device(n_tracks, n_steps, seed=20260103, device=0, k=10, sigma_ob
         T, m = sim_tracks, n_steps // sim_tracks
         assert T * m == n_steps
     n = T * m
+    nslab = world if (time_shard or not single) else 1
+    rng = GroupedRNG(seed, T * nslab, T, rank if nslab > 1 else 0, dev)
     if irregular:
-        inc = 0.2 + 1.8 * torch.rand((T, m), dtype=torch.float64, device=dev, generator=gen)
+        inc = 0.2 + 1.8 * rng.draw("uniform", m)
         inc[:, 0] = 0.0
         times = torch.cumsum(inc, dim=1)
         del inc
     else:
         times = torch.arange(m, dtype=torch.float64, device=dev).repeat(T, 1)
+
+    def seg_offsets(x):
+        """exclusive prefix sum of the per-segment quantity x over ALL segments of the track, in
+        global segment order; the cumsum runs over the same full vector on every rank, so the
+        offsets are bit-identical for every world size"""
+        if time_shard and world > 1:
+            allx = dist_gather(x.contiguous()).reshape(-1)
+            o = torch.cumsum(allx, 0) - allx
+            nxt.append(o[(rank + 1) * T] if rank < world - 1 else None)
+            return o[rank * T:(rank + 1) * T]
+        return torch.cumsum(x, 0) - x
+
+    nxt = []            # [0]: time at which the next slab starts (time shards)
+
     if single:      # consecutive segments of one track: shift times so they increase overall
-        ends = times[:, -1] + 1.0
-        off = torch.cumsum(ends, 0) - ends
-        times = times + off[:, None]
-    slab_t = 2.0 * n + 4.0 * T          # upper bound of a slab's time span (increments are < 2)
-    if time_shard:
-        assert single
-        times = times + rank * slab_t
-    s = (times - times.min()) / (times.max() - times.min()) if single else times / times[:, -1:]
+        times = times + seg_offsets(times[:, -1] + 1.0)[:, None]
+        tmin, tmax = times.min().reshape(1), times.max().reshape(1)
+        if time_shard and dist_reduce is not None:
+            tmin, tmax = dist_reduce(tmin, "min"), dist_reduce(tmax, "max")
+        s = (times - tmin) / (tmax - tmin)
+    else:
+        s = times / times[:, -1:]
     tau = torch.exp(0.5 * torch.sin(2 * math.pi * s))
     nu = torch.exp(0.3 * torch.cos(2 * math.pi * s))
     del s
     obs = torch.empty((n, nd), dtype=torch.float64, device=dev)
     for d in range(nd):
-        z = simulate_ctcrw_device(times.contiguous(), tau.contiguous(), nu.contiguous(), gen, device)
+        e1, e2 = rng.draw("normal", m), rng.draw("normal", m)
+        z = simulate_ctcrw_device(times.contiguous(), tau.contiguous(), nu.contiguous(), e1, e2, device)
+        del e1, e2
         if single:
-            ends = z[:, -1]
-            z = z + (torch.cumsum(ends, 0) - ends)[:, None]
-        z = z + sigma_obs * torch.randn(z.shape, dtype=torch.float64, device=dev, generator=gen)
+            z = z + seg_offsets(z[:, -1].clone())[:, None]
+        z = z + sigma_obs * rng.draw("normal", m)
         obs[:, d] = z.reshape(-1)
         del z
     del tau, nu
@@ -140,7 +181,7 @@ def make_ctcrw_device(n_tracks, n_steps, seed=20260103, device=0, k=10, sigma_ob
             flags[-1] |= 2
             dt[-1] = 1.0
         else:
-            dt[-1] = (rank + 1) * slab_t - tflat[-1]          # first time of the next slab
+            dt[-1] = nxt[0] - tflat[-1]          # first time of the next slab (= what the unsharded track has there)
         n_id = 1 if first_slab else 0
         shard_flags |= (0 if first_slab else L.SHARD_CONT_PREV) | (0 if last_slab else L.SHARD_CONT_NEXT)
     elif single:

@@ -43,17 +43,24 @@ def track_bounds(ID):
 
 
 def split_tracks(ID, world):
-    """Contiguous groups of whole tracks, balanced by row count: [(lo, hi)] * world (a group may
-    be empty when there are fewer tracks than ranks)."""
+    """Contiguous groups of whole tracks, balanced by row count: [(lo, hi)] * world.  With at least
+    as many tracks as ranks every rank gets at least one track (cut r is the track boundary nearest
+    to r/world of the rows among those that leave one track for every rank before and after it);
+    with fewer tracks than ranks the trailing groups are empty -- every rank sees the same ID
+    vector, so every rank can raise the same error (TrackShardedEngine)."""
     b = track_bounds(ID)
-    n = int(b[-1])
-    cuts = [0]
+    n, nt = int(b[-1]), b.size - 1
+    if nt < world:
+        cuts = [int(b[min(r, nt)]) for r in range(world + 1)]
+        return [(cuts[r], cuts[r + 1]) for r in range(world)]
+    idx = [0]                                   # indices into b
     for r in range(1, world):
+        lo, hi = idx[-1] + 1, nt - (world - r)  # leave >= 1 track for this group and for each later one
         target = n * r / world
-        j = int(np.argmin(np.abs(b - target)))
-        cuts.append(max(int(b[j]), cuts[-1]))
-    cuts.append(n)
-    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+        j = lo + int(np.argmin(np.abs(b[lo:hi + 1] - target)))
+        idx.append(j)
+    idx.append(nt)
+    return [(int(b[idx[r]]), int(b[idx[r + 1]])) for r in range(world)]
 
 
 def split_time(n, world):
@@ -146,15 +153,32 @@ class TrackShardedEngine:
         import torch
         self.comm = comm if comm is not None else SoloComm()
         rank, world = self.comm.rank, self.comm.world
-        self.lo, self.hi = split_tracks(dat["ID"], world)[rank]
-        if self.hi <= self.lo:
-            raise ValueError(f"rank {rank} of {world} got no track: use at most as many ranks as tracks")
+        groups = split_tracks(dat["ID"], world)
+        if any(hi <= lo for lo, hi in groups):
+            # raised on EVERY rank (all see the same ID vector): no rank is left waiting in a collective
+            raise ValueError(f"{track_bounds(dat['ID']).size - 1} track(s) cannot be spread over {world} ranks: "
+                             "use at most as many ranks as tracks")
+        self.lo, self.hi = groups[rank]
         sub, cp, cn, _ = shard_rows(dat, self.lo, self.hi)
         assert not cp and not cn
         flags = L.SHARD_NO_PENALTY if rank > 0 else 0
         self.device = device
         factory = engine_factory or _default_factory
         self.engine = factory(sub, 0 if device is None else device, flags, 0.0)
+        self._init_buffers(device)
+
+    @classmethod
+    def from_engine(cls, engine, comm, device):
+        """Adopt this rank's already-built shard (e.g. from devgen, whose 1e8-row problems never
+        exist as a host data list); rank > 0 must have been built with SSDE_SHARD_NO_PENALTY."""
+        self = cls.__new__(cls)
+        self.comm, self.device, self.engine = comm, device, engine
+        self.lo = self.hi = None
+        self._init_buffers(device)
+        return self
+
+    def _init_buffers(self, device):
+        import torch
         self.n_par, self.layout = self.engine.n_par, self.engine.layout
         self.on_device = device is not None and hasattr(self.engine, "eval_device")
         if self.on_device:
@@ -235,7 +259,7 @@ class TrackShardedEngine:
 # --------------------------------------------------------------------------------------------
 # one long track: shard along time (CTCRW)
 # --------------------------------------------------------------------------------------------
-def _stage_driver(shards, par_tensors, gather, reduce_, streams):
+def _stage_driver(shards, par_tensors, gather, reduce_, streams, fallbacks=None):
     """The stages of ssde_eval_stage for a list of local shards (one per rank in the distributed
     case).  gather(list of per-shard tensors) -> list of gathered tensors, one per local shard;
     reduce_(list of out tensors) sums them in place across all shards.
@@ -270,9 +294,13 @@ def _stage_driver(shards, par_tensors, gather, reduce_, streams):
     g0 = gather(run(0, 0))
     if not all_const(g0, 0):
         g0 = gather(run(3, 0))
+        if fallbacks is not None:
+            fallbacks[0] += 1
     g1 = gather(run(1, 1, g0))
     if not all_const(g1, 1):
         g1 = gather(run(4, 1))
+        if fallbacks is not None:
+            fallbacks[1] += 1
     return reduce_(run(2, None, g1))
 
 
@@ -280,6 +308,8 @@ class TimeShardedEngine:
     """One CTCRW track cut along time.  Distributed use: one slab per rank (``comm`` = DistComm).
     Single-process use: ``devices`` = list of CUDA ordinals (repeats allowed), all slabs driven
     from this process, elements exchanged with device-to-device copies."""
+
+    fallbacks = None        # set to [0, 0] to count whole-shard summary passes [forward stage 3, adjoint stage 4]
 
     def __init__(self, dat, comm=None, device=0, devices=None, engine_factory=None):
         import torch
@@ -361,7 +391,7 @@ class TimeShardedEngine:
             with torch.cuda.stream(self.streams[0]):
                 self.comm.all_reduce_sum(outs[0])
             return outs[0]
-        return _stage_driver(self.shards, [par_dev], self._gather, reduce_, self.streams)
+        return _stage_driver(self.shards, [par_dev], self._gather, reduce_, self.streams, self.fallbacks)
 
     def eval(self, par, order=1):
         """(nllk, grad); the stage protocol always computes the gradient."""
@@ -371,7 +401,7 @@ class TimeShardedEngine:
         for dv, st in zip(self.devs, self.streams):
             with torch.cuda.stream(st):
                 pts.append(torch.as_tensor(par).to(dv))
-        out = _stage_driver(self.shards, pts, self._gather, self._reduce, self.streams)
+        out = _stage_driver(self.shards, pts, self._gather, self._reduce, self.streams, self.fallbacks)
         if out[self.n_par + 1] != 0.0:
             raise L.EngineError(5, "device-side failure on some shard")
         return float(out[0]), (out[1:self.n_par + 1].copy() if order >= 1 else None)
