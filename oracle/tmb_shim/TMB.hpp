@@ -56,6 +56,8 @@ inline Dual& operator+=(Dual& a, Dual b) { a = a + b; return a; }
 inline Dual exp(Dual a) { double e = std::exp(a.v); return Dual(e, e * a.d); }
 inline Dual log(Dual a) { return Dual(std::log(a.v), a.d / a.v); }
 inline Dual sqrt(Dual a) { double s = std::sqrt(a.v); return Dual(s, 0.5 * a.d / s); }
+inline bool is_zero(double x) { return x == 0.0; }
+inline bool is_zero(Dual x) { return x.v == 0.0 && x.d == 0.0; }
 inline double value_of(double x) { return x; }
 inline double value_of(Dual x) { return x.v; }
 
@@ -164,6 +166,12 @@ inline void reverse(const Var<B>& y, std::vector<B>& adj) {
     for (size_t k = y.i; k > 0; --k) {
         const auto& n = t.nodes[k];
         const B w = adj[k];
+        // "absolute zero" multiply, as CppAD's azmul in its reverse sweeps: an operation the result
+        // does not depend on (w == 0) contributes nothing even if its partial is inf / NaN.  The
+        // reference needs it: the prediction at a track's last row uses the cross-track dt
+        // (nllk_ctcrw.hpp:126-129,206-208; negative when the next track's clock restarts, so
+        // exp(-beta dt) overflows) and is then discarded at the ID change (:196-200).
+        if (is_zero(w)) continue;
         adj[n.a] += n.da * w;
         adj[n.b] += n.db * w;
     }

@@ -128,3 +128,18 @@ def test_unknown_type_raises_like_the_reference():
     dat, par, info = synth.make_problem("BM", 1, 20, n_dim=1, seed=2)
     with pytest.raises(RuntimeError, match="Unknown SDE type"):       # smoothSDE.cpp:25
         oracle_ref.RefOracle(dict(dat, type="XYZ")).nllk(par)
+
+
+def test_long_tracks_with_restarting_clocks():
+    """Thousands of rows per track, several tracks whose clocks restart at 0: the reference's
+    discarded cross-track prediction overflows (negative dt) and must not poison the reverse sweep;
+    the 2-D filter's zero-valued cross-covariances are still AD variables."""
+    from oracle import oracle_c
+    dat, par, info = synth.make_problem("CTCRW", 3, 2500, missing_frac=0.05, n_dim=2, seed=3003)
+    par = par.copy()
+    par[1:3] = [0.3, -0.2]
+    rv, rg = oracle_ref.RefOracle(dat).eval(par)
+    cv, cg = oracle_c.COracle(dat).eval(par, True)
+    assert np.isfinite(rg).all()
+    assert abs(rv - cv) <= 1e-13 * abs(cv)
+    assert gerr(rg, cg) <= 1e-10
