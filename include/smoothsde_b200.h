@@ -240,6 +240,10 @@ const char* ssde_laplace_error(const ssde_laplace* w);
 /* Diagnostics (libraries built with -DSSDE_STATS only, else SSDE_ERR_UNSUPPORTED): look-back and
  * per-phase cycle counters of the scan kernels, [0..15] forward, [16..31] adjoint. */
 int ssde_debug_stats(ssde_handle* h, uint64_t out[32], int reset);
+/* Diagnostics: the look-back of the scan kernels stops at an aggregate whose linear part has decayed
+ * below `tol` (default 1e-60: the filter has forgotten its initial condition, csrc/models.cuh).
+ * tol < 0 switches that shortcut off for every handle on `device`, so tests can compare both paths. */
+int ssde_debug_const_map_tol(int device, double tol);
 
 /* The handle's CUDA device ordinal and its own stream (a cudaStream_t). */
 int ssde_device(const ssde_handle* h);

@@ -70,6 +70,38 @@ class COracle:
         self.par_bar = np.zeros(X.shape[0])
         self.gth = np.zeros(X.shape[1])
 
+    @classmethod
+    def from_csr(cls, type_, ID, times, obs, rowptr, col, val, p_fe, p_re, S, ncol_re, a0=None, P0=None,
+                 nthreads=1, include_penalty=1):
+        """Problems too large for a scipy triplet list (the device-built 1e7-row shapes): the
+        stacked design [X_fe | X_re] is given directly as CSR arrays over n_par * n rows."""
+        self = cls.__new__(cls)
+        self.type = type_
+        self.nthreads = int(nthreads)
+        self.obs = np.asfortranarray(np.asarray(obs, dtype=float))
+        self.n, self.d = self.obs.shape
+        self.ID = np.ascontiguousarray(ID, dtype=float)
+        self.times = np.ascontiguousarray(times, dtype=float)
+        self.rowptr = np.ascontiguousarray(rowptr, dtype=np.int64)
+        self.col = np.ascontiguousarray(col, dtype=np.int32)
+        self.val = np.ascontiguousarray(val, dtype=np.float64)
+        self.p_fe, self.p_re = int(p_fe), int(p_re)
+        nrow = self.rowptr.size - 1
+        self.n_par = nrow // self.n
+
+        class _Shape:                      # eval() only needs X.shape
+            shape = (nrow, self.p_fe + self.p_re)
+        self.X = _Shape()
+        self.dat = {"type": type_, "X_fe": sp.csr_matrix((nrow, self.p_fe)), "X_re": sp.csr_matrix((nrow, self.p_re)),
+                    "S": S, "ncol_re": ncol_re, "include_penalty": include_penalty}
+        if type_ == "CTCRW":
+            self.a0 = np.asfortranarray(np.asarray(a0, dtype=float))
+            self.P0 = np.asfortranarray(np.asarray(P0, dtype=float))
+        self.par_vec = np.zeros(nrow)
+        self.par_bar = np.zeros(nrow)
+        self.gth = np.zeros(self.p_fe + self.p_re)
+        return self
+
     def eval(self, par, want_grad=True):
         L = lib()
         p = O.split_par(self.dat, np.asarray(par, dtype=float))

@@ -36,7 +36,7 @@ MakeADFun_b200 <- function(data, parameters, map = list(), random = NULL, device
             out <- .Call("ssde_laplace_fn_gr", lap, p, as.integer(order))
             p <- out$par
         }
-        env$last.par <- p
+        if(is.finite(out$value)) env$last.par <- p     # a diverged inner optimum must not become the next warm start
         if(is.finite(out$value) && out$value < env$value.best) { env$value.best <- out$value; env$last.par.best <- p }
         out
     }

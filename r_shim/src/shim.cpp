@@ -188,8 +188,20 @@ SEXP ssde_laplace_fn_gr(SEXP lap, SEXP par, SEXP order) {
     SEXP val = PROTECT(Rf_allocVector(REALSXP, 1));
     SEXP grad = PROTECT(Rf_allocVector(REALSXP, ord >= 1 ? np : 0));
     SEXP p = PROTECT(Rf_duplicate(par));
+    // outputs are defined on EVERY path: ssde_laplace_eval writes *value only when it gets that far
+    // and never writes the gradient on an error path
+    REAL(val)[0] = R_PosInf;
+    for (int i = 0; i < (ord >= 1 ? np : 0); ++i) REAL(grad)[i] = NA_REAL;
     int rc = ssde_laplace_eval(w, REAL(p), ord, REAL(val), ord >= 1 ? REAL(grad) : NULL, NULL);
-    if (rc != SSDE_OK && rc != SSDE_ERR_NUMERIC) { UNPROTECT(4); Rf_error("smoothsde_b200: %s", ssde_laplace_error(w)); }
+    // the only failure an optimiser may step away from: H_bb not positive definite at the inner
+    // optimum (value = Inf, as TMB's inner problem reports); anything else is an error
+    const bool not_pd = rc == SSDE_ERR_NUMERIC && strstr(ssde_laplace_error(w), "not positive definite at the inner optimum") != NULL;
+    if (rc != SSDE_OK && !not_pd) { UNPROTECT(4); Rf_error("smoothsde_b200: %s", ssde_laplace_error(w)); }
+    if (rc != SSDE_OK) {                           // not_pd: Inf value, NA gradient, starting coeff_re kept
+        REAL(val)[0] = R_PosInf;
+        for (int i = 0; i < (ord >= 1 ? np : 0); ++i) REAL(grad)[i] = NA_REAL;
+        memcpy(REAL(p), REAL(par), sizeof(double) * (size_t)np);
+    }
     SET_VECTOR_ELT(out, 0, val);
     SET_VECTOR_ELT(out, 1, grad);
     SET_VECTOR_ELT(out, 2, p);

@@ -191,7 +191,7 @@ struct ScanDesc {
     double* agg;           // [ntiles * NDBL]
     double* incl;          // [ntiles * NDBL]
     unsigned* ticket;      // dynamic tile counter (zeroed by the host before every launch)
-    unsigned* error;       // set to non-zero if a spin-wait times out
+    unsigned* error;       // bit 0: a spin-wait timed out; bit 1: innovation variance F <= 0 (forward re-run)
     unsigned epoch;
 #ifdef SSDE_STATS
     unsigned long long* stats;   // diagnostics build only: [0] look-backs, [1] windows, [2] spins, [3] cycles
@@ -262,7 +262,7 @@ __device__ __forceinline__ typename Ops::Elem lookback(const ScanDesc& d, int t,
             ++n_spin;
 #endif
             if (++spins > (1u << 22)) {                    // ~seconds: give up instead of hanging
-                if (lane == 0) atomicExch(d.error, 1u);
+                if (lane == 0) atomicOr(d.error, 1u);
                 return acc;
             }
             __nanosleep(20);

@@ -325,6 +325,7 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(KalmanArgs<typename
         // sum_i log F_i is taken as the log of a running product (one log per chunk instead of
         // one per row); the product is folded into `slog` whenever it leaves a safe range.
         R quad = 0.0, fprod = 1.0, slog = 0.0;
+        bool bad_f = false;
         if (restage) {
             stage_wait(st);
         } else {
@@ -364,6 +365,7 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(KalmanArgs<typename
                 M::template fwd_step<false>(s, sp, y, mu, (f & ROW_OBS) != 0, M::row_h(h, a.Hrow, a.X.n_pad, pos), nullptr, F, qd);
                 quad += qd;
                 fprod *= F;
+                bad_f |= value(F) <= 0.0;          // the reference's detF <= 0 branch (nllk_ctcrw.hpp:226-228) is not built: flag it
                 if (!(value(fprod) > 1e-150 && value(fprod) < 1e150)) { slog += log(fprod); fprod = 1.0; }
             }
             if (a.aest) {
@@ -372,6 +374,7 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(KalmanArgs<typename
         }
         const double llk = warp_sum(value(-0.5 * ((double)M::LOGF_MULT * (slog + log(fprod)) + quad)));
         if (lane == 0) a.tile_llk[q] = llk;              // one partial per warp-tile
+        if (bad_f) atomicOr(a.fdesc.error, 2u);
 #ifdef SSDE_STATS
         if (lane == 0) {                                 // per-warp phase cycles: 4 + 4*warp-class (warp 0 / others)
             unsigned long long* st_ = a.fdesc.stats + 4 + (warp == 0 ? 0 : 4);

@@ -34,8 +34,20 @@ struct PriorCov {
 constexpr int KNT_DEFAULT = SSDE_KNT, MINB_DEFAULT = SSDE_MINB;
 
 constexpr double CONST_MAP_TOL = 1e-60;     // see FwdOps / is_const in common.cuh
-SSDE_HD bool tiny(double x) { return fabs(x) <= CONST_MAP_TOL; }
-SSDE_HD bool tiny(const Dual& x) { return fabs(x.v) <= CONST_MAP_TOL && fabs(x.d) <= CONST_MAP_TOL; }
+// The device reads the threshold from constant memory so that tests can switch the constant-map
+// shortcut off (ssde_debug_const_map_tol(device, -1)) and compare both paths on the same data.
+#ifdef __CUDACC__
+__constant__ double c_const_map_tol = CONST_MAP_TOL;
+#endif
+SSDE_HD double const_map_tol() {
+#ifdef __CUDA_ARCH__
+    return c_const_map_tol;
+#else
+    return CONST_MAP_TOL;
+#endif
+}
+SSDE_HD bool tiny(double x) { return fabs(x) <= const_map_tol(); }
+SSDE_HD bool tiny(const Dual& x) { const double t = const_map_tol(); return fabs(x.v) <= t && fabs(x.d) <= t; }
 template <class R>
 SSDE_HD bool tiny(const Mat2T<R>& m) { return tiny(m.m11) && tiny(m.m12) && tiny(m.m21) && tiny(m.m22); }
 

@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -979,6 +980,31 @@ int run_hvp(ssde_handle* h, const double* d_par, const double* d_dir, double* d_
     return eval_epilogue(h, d_par, d_dir, 1, d_out, d_hv, st);
 }
 
+// No C++ exception may cross the C ABI (include/smoothsde_b200.h): std::vector / std::sort of the
+// host-side packing can throw std::bad_alloc on a 1e8-row design.
+template <class Fn>
+int guarded(std::string& err, Fn&& fn) {
+    try {
+        return fn();
+    } catch (const std::bad_alloc&) {
+        err = "out of host memory";
+    } catch (const std::exception& e) {
+        err = std::string("C++ exception: ") + e.what();
+    } catch (...) {
+        err = "unknown C++ exception";
+    }
+    return SSDE_ERR_BAD_ARG;
+}
+}  // namespace
+// message for a non-zero device status word (bit 0: look-back time-out; bit 1: F <= 0).  With
+// several shards the words are summed, so any non-zero value is a failure and the bits are a hint.
+const char* device_failure(double status) {
+    const unsigned e = (unsigned)status;
+    if (e & 2u) return "device-side failure: innovation variance F <= 0 in the filter (the reference's detF <= 0 branch, "
+                       "nllk_ctcrw.hpp:226-228, is not built)";
+    return "device-side failure (scan look-back timed out)";
+}
+namespace {
 int check_common(int model, int n_dim, std::string& err) {
     if (model < 0 || model > 4) { err = "Unknown SDE type"; return SSDE_ERR_UNKNOWN_TYPE; }
     const int n_par = sde_par_count(model, n_dim);
@@ -1021,6 +1047,13 @@ int ssde_debug_stats(ssde_handle* h, uint64_t out[32], int reset) {
     return SSDE_ERR_UNSUPPORTED;
 #endif
 }
+// Diagnostics: threshold below which a scan element's linear part counts as zero (models.cuh).
+// tol < 0 disables the constant-map shortcut of the look-back altogether; the default restores it.
+int ssde_debug_const_map_tol(int device, double tol) {
+    if (cudaSetDevice(device) != cudaSuccess) return SSDE_ERR_CUDA;
+    if (cudaDeviceSynchronize() != cudaSuccess) return SSDE_ERR_CUDA;
+    return cudaMemcpyToSymbol(c_const_map_tol, &tol, sizeof(double)) == cudaSuccess ? SSDE_OK : SSDE_ERR_CUDA;
+}
 int ssde_device(const ssde_handle* h) { return h ? h->device : -1; }
 void* ssde_stream(const ssde_handle* h) { return h ? (void*)h->stream : nullptr; }
 
@@ -1046,7 +1079,7 @@ int ssde_layout_info(int32_t info[4]) {
 
 // Host-only: the design of `d` in the device layout (no GPU needed).  Used by hosts that want to
 // build an ssde_packed_desc themselves and by the CPU tests of the layout.
-int ssde_pack_host(const ssde_desc* d, ssde_host_pack* out) {
+static int pack_host_impl(const ssde_desc* d, ssde_host_pack* out) {
     std::string& err = g_create_error;
     err.clear();
     if (!d || !out) { err = "null argument"; return SSDE_ERR_BAD_ARG; }
@@ -1072,13 +1105,17 @@ int ssde_pack_host(const ssde_desc* d, ssde_host_pack* out) {
     return SSDE_OK;
 }
 
+int ssde_pack_host(const ssde_desc* d, ssde_host_pack* out) {
+    return guarded(g_create_error, [&] { return pack_host_impl(d, out); });
+}
+
 void ssde_pack_free(ssde_host_pack* p) {
     if (!p) return;
     std::free(p->desc); std::free(p->val); std::free(p->col);
     std::memset(p, 0, sizeof(*p));
 }
 
-int ssde_create(const ssde_desc* d, ssde_handle** out) {
+static int create_impl(const ssde_desc* d, ssde_handle** out) {
     std::string& err = g_create_error;
     err.clear();
     if (!d || !out) { err = "null argument"; return SSDE_ERR_BAD_ARG; }
@@ -1101,12 +1138,13 @@ int ssde_create(const ssde_desc* d, ssde_handle** out) {
 
     ssde_handle* h = new (std::nothrow) ssde_handle();
     if (!h) { err = "out of memory"; return SSDE_ERR_BAD_ARG; }
+    std::unique_ptr<ssde_handle> guard(h);         // released on success; frees the handle on any error or exception
     h->device = d->device; h->model = d->model; h->n_dim = nd; h->n_par = n_par; h->n = n;
     h->n_pad = ssde_padded_rows(n);
     h->p_fe = (int)d->X_fe.ncol; h->p_re = (int)d->X_re.ncol;
     h->include_penalty = d->include_penalty; h->shard_flags = d->shard_flags;
     h->add_penalty = !(d->shard_flags & SSDE_SHARD_NO_PENALTY);
-    auto fail = [&](int code) { err = h->err.empty() ? err : h->err; delete h; return code; };
+    auto fail = [&](int code) { err = h->err.empty() ? err : h->err; return code; };
 
     // rows in the permuted order of design.cuh: flags, dt, obs planes; track starts
     const int64_t n_pad = h->n_pad;
@@ -1124,6 +1162,14 @@ int ssde_create(const ssde_desc* d, ssde_handle** out) {
             else obs[(size_t)k * n_pad + pos] = y;
         }
         if (is_kalman(d->model)) {
+            // Only column 0 is tested for NA (nllk_ctcrw.hpp:214, nllk_ou_ssm.hpp:182): a row whose
+            // column 0 is observed while another column is NA makes the reference's objective NaN
+            // (u and uFu inherit the NA, :221-234).  Reject such data instead of filtering y_k = 0.
+            if (!std::isnan(d->obs[i]) && (f & ~(uint8_t)0x07)) {
+                err = "row " + std::to_string(i) + ": obs[, 1] is observed but another column is NA; the reference's "
+                      "objective is NaN for such a row (only column 1 is tested, nllk_ctcrw.hpp:214)";
+                return fail(SSDE_ERR_BAD_ARG);
+            }
             f &= (uint8_t)0x07;                                    // NA bits unused
             if (!std::isnan(d->obs[i])) f |= ROW_OBS;              // column 0 only, nllk_ctcrw.hpp:214, nllk_ou_ssm.hpp:182
         }
@@ -1232,11 +1278,17 @@ int ssde_create(const ssde_desc* d, ssde_handle** out) {
     if ((rc = dev_upload(h->track_starts, starts, h->err))) return fail(rc);
     if ((rc = setup_penalty(h, d->S, d->n_smooth, d->ncol_re, h->err))) return fail(rc);
     if ((rc = finish_setup(h))) return fail(rc);
-    *out = h;
+    *out = guard.release();
     return SSDE_OK;
 }
 
-int ssde_create_packed(const ssde_packed_desc* d, ssde_handle** out) {
+int ssde_create(const ssde_desc* d, ssde_handle** out) {
+    const int rc = guarded(g_create_error, [&] { return create_impl(d, out); });
+    if (rc && out) *out = nullptr;
+    return rc;
+}
+
+static int create_packed_impl(const ssde_packed_desc* d, ssde_handle** out) {
     std::string& err = g_create_error;
     err.clear();
     if (!d || !out) { err = "null argument"; return SSDE_ERR_BAD_ARG; }
@@ -1250,7 +1302,8 @@ int ssde_create_packed(const ssde_packed_desc* d, ssde_handle** out) {
     if (cudaSetDevice(d->device) != cudaSuccess) { err = "cudaSetDevice failed: no usable CUDA device (there is no CPU fallback)"; return SSDE_ERR_CUDA; }
     ssde_handle* h = new (std::nothrow) ssde_handle();
     if (!h) { err = "out of memory"; return SSDE_ERR_BAD_ARG; }
-    auto fail = [&](int code) { err = h->err.empty() ? err : h->err; delete h; return code; };
+    std::unique_ptr<ssde_handle> guard(h);
+    auto fail = [&](int code) { err = h->err.empty() ? err : h->err; return code; };
     h->device = d->device; h->model = d->model; h->n_dim = d->n_dim; h->n_par = n_par; h->n = d->n; h->n_pad = d->n_pad; h->nnz = d->nnz;
     h->p_fe = d->p_fe; h->p_re = d->p_re; h->include_penalty = d->include_penalty; h->shard_flags = d->shard_flags;
     h->add_penalty = !(d->shard_flags & SSDE_SHARD_NO_PENALTY);
@@ -1272,8 +1325,14 @@ int ssde_create_packed(const ssde_packed_desc* d, ssde_handle** out) {
     }
     if ((rc = setup_penalty(h, d->S, d->n_smooth, d->ncol_re, h->err))) return fail(rc);
     if ((rc = finish_setup(h))) return fail(rc);
-    *out = h;
+    *out = guard.release();
     return SSDE_OK;
+}
+
+int ssde_create_packed(const ssde_packed_desc* d, ssde_handle** out) {
+    const int rc = guarded(g_create_error, [&] { return create_packed_impl(d, out); });
+    if (rc && out) *out = nullptr;
+    return rc;
 }
 
 int ssde_eval_device(ssde_handle* h, const double* d_par, int order, double* d_out, void* stream) {
@@ -1366,7 +1425,7 @@ int ssde_check(ssde_handle* h) {
     CUDA_TRY(cudaDeviceSynchronize());
     unsigned e = 0;
     CUDA_TRY(cudaMemcpy(&e, h->counters.as<unsigned>() + 2, sizeof(unsigned), cudaMemcpyDeviceToHost));
-    if (e) { err = "device-side failure (scan look-back timed out)"; return SSDE_ERR_NUMERIC; }
+    if (e) { err = device_failure((double)e); return SSDE_ERR_NUMERIC; }
     return SSDE_OK;
 }
 
@@ -1429,7 +1488,7 @@ int ssde_hvp(ssde_handle* h, const double* par, int n_dir, const double* dirs, d
     CUDA_TRY(cudaStreamSynchronize(st));
     if (nllk) *nllk = out[0];
     if (grad) std::memcpy(grad, out.data() + 1, sizeof(double) * np);
-    if (out[1 + np] != 0.0) { err = "device-side failure (scan look-back timed out)"; return SSDE_ERR_NUMERIC; }
+    if (out[1 + np] != 0.0) { err = device_failure(out[1 + np]); return SSDE_ERR_NUMERIC; }
     return SSDE_OK;
 }
 
@@ -1462,7 +1521,7 @@ int ssde_eval(ssde_handle* h, const double* par, int order, double* nllk, double
                 const double m = 0.5 * (hess[(size_t)j * np + i] + hess[(size_t)i * np + j]);
                 hess[(size_t)j * np + i] = hess[(size_t)i * np + j] = m;
             }
-        if (ho[1 + np] != 0.0) { err = "device-side failure (scan look-back timed out)"; return SSDE_ERR_NUMERIC; }
+        if (ho[1 + np] != 0.0) { err = device_failure(ho[1 + np]); return SSDE_ERR_NUMERIC; }
         return SSDE_OK;
     }
     h->timed = true;
@@ -1476,7 +1535,7 @@ int ssde_eval(ssde_handle* h, const double* par, int order, double* nllk, double
     CUDA_TRY(cudaStreamSynchronize(st));
     *nllk = ho[0];
     if (order >= 1) std::memcpy(grad, ho + 1, sizeof(double) * h->npar);
-    if (ho[1 + h->npar] != 0.0) { err = "device-side failure (scan look-back timed out)"; return SSDE_ERR_NUMERIC; }
+    if (ho[1 + h->npar] != 0.0) { err = device_failure(ho[1 + h->npar]); return SSDE_ERR_NUMERIC; }
     return SSDE_OK;
 }
 

@@ -22,6 +22,7 @@
 
 #include <cmath>
 #include <cstring>
+#include <memory>
 #include <new>
 #include <string>
 #include <vector>
@@ -91,7 +92,10 @@ int joint_hess_cols(ssde_laplace* w, double& v) {
     LP_TRY(ssde_hess_cols_device(w->h, w->d_par, w->o_re, nb, w->d_out, w->d_hess, w->st));
     LP_CUDA(cudaMemcpyAsync(w->out.data(), w->d_out, sizeof(double) * (np + 2), cudaMemcpyDeviceToHost, w->st));
     LP_CUDA(cudaStreamSynchronize(w->st));
-    if (w->out[np + 1] != 0.0) { w->err = "device-side failure (scan look-back timed out)"; return SSDE_ERR_NUMERIC; }
+    if (w->out[np + 1] != 0.0) {
+        w->err = ((unsigned)w->out[np + 1] & 2u) ? "device-side failure: innovation variance F <= 0 in the filter" : "device-side failure (scan look-back timed out)";
+        return SSDE_ERR_NUMERIC;
+    }
     v = w->out[0];
     std::memcpy(w->grad.data(), w->out.data() + 1, sizeof(double) * np);
     return SSDE_OK;
@@ -146,12 +150,13 @@ int hvp_at(ssde_laplace* w, const std::vector<double>& par_at, const std::vector
 
 extern "C" {
 
-int ssde_laplace_create(ssde_handle* h, const ssde_laplace_opts* opts, ssde_laplace** out) {
+static int laplace_create_impl(ssde_handle* h, const ssde_laplace_opts* opts, ssde_laplace** out) {
     if (!h || !out) return SSDE_ERR_BAD_ARG;
     *out = nullptr;
     ssde_laplace* w = new (std::nothrow) ssde_laplace();
     if (!w) return SSDE_ERR_BAD_ARG;
-    auto fail = [&](int rc) { delete w; return rc; };
+    std::unique_ptr<ssde_laplace> guard(w);        // frees the workspace on any error or exception
+    auto fail = [&](int rc) { return rc; };
     w->h = h;
     w->device = ssde_device(h);
     w->st = (cudaStream_t)ssde_stream(h);
@@ -183,8 +188,17 @@ int ssde_laplace_create(ssde_handle* h, const ssde_laplace_opts* opts, ssde_lapl
     if (cudaMalloc(&w->d_work, sizeof(double) * std::max(w->lwork, 1)) != cudaSuccess) return fail(SSDE_ERR_CUDA);
     w->par.resize(np); w->out.resize(np + 2); w->grad.resize(np);
     w->H_cols.resize((size_t)np * nb); w->L.resize((size_t)nb * nb); w->step.resize(nb); w->gb.resize(nb);
-    *out = w;
+    *out = guard.release();
     return SSDE_OK;
+}
+
+int ssde_laplace_create(ssde_handle* h, const ssde_laplace_opts* opts, ssde_laplace** out) {
+    try {                                           // no C++ exception crosses the C ABI
+        return laplace_create_impl(h, opts, out);
+    } catch (...) {
+        if (out) *out = nullptr;
+        return SSDE_ERR_BAD_ARG;
+    }
 }
 
 void ssde_laplace_destroy(ssde_laplace* w) { delete w; }

@@ -105,23 +105,37 @@ def shard_rows(dat, lo, hi):
 # communication: torch.distributed, or nothing (world = 1)
 # --------------------------------------------------------------------------------------------
 class DistComm:
-    """Thin wrapper over a torch.distributed process group (NCCL on GPUs, gloo in CPU tests)."""
+    """Thin wrapper over a torch.distributed process group: NCCL on GPUs (device tensors go straight
+    to the collective, ordered on the current stream); gloo in the CPU tests and when several ranks
+    share ONE GPU (NCCL refuses two ranks on a device) -- device tensors are then staged through the
+    host, which also orders them after the kernels of the current stream."""
 
     def __init__(self, group=None):
         import torch.distributed as dist
         self.dist, self.group = dist, group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.staged = dist.get_backend(group) != "nccl"
 
     def all_reduce_sum(self, t):
         if self.world > 1:
-            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+            if self.staged and t.is_cuda:
+                h = t.cpu()
+                self.dist.all_reduce(h, op=self.dist.ReduceOp.SUM, group=self.group)
+                t.copy_(h)
+            else:
+                self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
         return t
 
     def all_gather(self, t):
         import torch
         out = torch.empty((self.world * t.numel(),), dtype=t.dtype, device=t.device)
         if self.world > 1:
-            self.dist.all_gather_into_tensor(out, t.contiguous(), group=self.group)
+            if self.staged:
+                parts = [torch.empty(t.numel(), dtype=t.dtype) for _ in range(self.world)]
+                self.dist.all_gather(parts, t.reshape(-1).cpu().contiguous(), group=self.group)
+                out.copy_(torch.cat(parts))
+            else:
+                self.dist.all_gather_into_tensor(out, t.contiguous(), group=self.group)
         else:
             out.copy_(t.reshape(-1))
         return out

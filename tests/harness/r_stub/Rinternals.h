@@ -20,6 +20,9 @@ typedef int Rboolean;
 #define STRSXP 16
 #define VECSXP 19
 extern SEXP R_NilValue, R_NamesSymbol, R_DimSymbol;
+/* R_ext/Arith.h */
+extern double R_PosInf, R_NaReal;
+#define NA_REAL R_NaReal
 SEXP Rf_protect(SEXP);
 void Rf_unprotect(int);
 #define PROTECT(s) Rf_protect(s)

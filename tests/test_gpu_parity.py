@@ -245,3 +245,46 @@ def test_hessian_vector_products_match_oracle_differences(model, T, m, miss, nd)
         ref = (4 * d2 - d1) / 3
         assert hess_err(hv[:, c], ref) <= HESS_RTOL, (c, np.max(np.abs(hv[:, c] - ref)))
     eng.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# boundary behaviour (include/smoothsde_b200.h)
+# ---------------------------------------------------------------------------------------------
+def test_partially_missing_row_is_rejected_for_kalman_models():
+    """obs[i, 0] observed, obs[i, 1] NA: the reference's objective is NaN for such a row (only column
+    0 is tested, nllk_ctcrw.hpp:214; tests/test_ref.py::test_na_semantics_of_the_reference) -- the
+    engine refuses the data instead of silently filtering y = 0."""
+    from smoothsde_b200 import _lib
+    dat, par, info = synth.make_problem("CTCRW", 2, 30, missing_frac=0.0, n_dim=2, seed=5)
+    obs = dat["obs"].copy()
+    obs[7, 1] = np.nan
+    with pytest.raises(_lib.EngineError) as ei:
+        Engine.from_data(dict(dat, obs=obs))
+    assert ei.value.code == 2 and "another column is NA" in str(ei.value)
+    # column 0 NA, column 1 observed: the row simply counts as missing, as in the reference
+    obs = dat["obs"].copy()
+    obs[7, 0] = np.nan
+    eng = Engine.from_data(dict(dat, obs=obs))
+    v, _ = eng.eval(par, order=1)
+    ref = O.nllk(dict(dat, obs=obs), par)
+    assert abs(v - ref) <= NLLK_RTOL * abs(ref)
+    eng.close()
+
+
+def test_nonpositive_innovation_variance_sets_the_numeric_status():
+    """SSDE_ERR_NUMERIC 'F <= 0 in the filter': P0 = 0 and sigma_obs^2 underflowing to 0 give F = 0 on
+    the first filtered row; the reference would take its detF <= 0 branch (nllk_ctcrw.hpp:226-228),
+    which the engine does not build -- it must say so instead of returning a number."""
+    from smoothsde_b200 import _lib
+    dat, par, info = synth.make_problem("CTCRW", 2, 30, missing_frac=0.0, n_dim=1, seed=6)
+    dat = dict(dat, P0=np.zeros((2, 2)))
+    par = par.copy()
+    par[0] = -400.0                                   # sigma_obs^2 = exp(-800) = 0
+    eng = Engine.from_data(dat)
+    with pytest.raises(_lib.EngineError) as ei:
+        eng.eval(par, order=1)
+    assert ei.value.code == 5 and "F <= 0" in str(ei.value)
+    par[0] = np.log(0.1)
+    v, _ = eng.eval(par, order=1)                     # the handle stays usable
+    assert np.isfinite(v)
+    eng.close()

@@ -1,6 +1,6 @@
 """GPU tests of the sharded paths: a single track cut along time (three-stage scan protocol of
-ssde_eval_stage) driven from one process, track shards, and -- when the box has at least two
-GPUs -- both over NCCL with one process per GPU.  Reference numbers: the C oracle on the whole
+ssde_eval_stage) driven from one process, track shards, and both with one process per shard over
+torch.distributed (NCCL with >= 2 GPUs, gloo with both ranks on the only GPU otherwise).  Reference numbers: the C oracle on the whole
 problem."""
 import os
 import socket
@@ -87,13 +87,19 @@ def _free_port():
     return p
 
 
-def _nccl_worker(rank, world, port, q):
+def _nccl_worker(rank, world, port, q, one_gpu):
     import torch
     import torch.distributed as dist
     sys.path.insert(0, HERE)
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
-    torch.cuda.set_device(rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    dev = 0 if one_gpu else rank
+    torch.cuda.set_device(dev)
+    if one_gpu:          # NCCL refuses two ranks on one device: same processes and protocol, collectives over gloo
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    else:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    rank_dev = rank
+    rank = dev
     try:
         comm = S.DistComm()
         dat, par, _ = synth.make_problem("CTCRW", 7, 400, missing_frac=0.1, n_dim=2, seed=3)
@@ -105,22 +111,25 @@ def _nccl_worker(rank, world, port, q):
         t = S.TimeShardedEngine(dat1, comm=comm, device=rank)
         tv, tg = t.eval(par1)
         t.close()
-        q.put((rank, v, g, hv, tv, tg))
+        q.put((rank_dev, v, g, hv, tv, tg))
     finally:
         dist.barrier()
         dist.destroy_process_group()
 
 
-def test_nccl_track_and_time_shards_match_oracle():
+def test_one_process_per_shard_track_and_time_shards_match_oracle():
+    """One process per shard with torch.distributed: over NCCL with one GPU per rank when the box has
+    at least two GPUs; on a one-GPU box the same two-process protocol runs with both ranks on cuda:0
+    and the collectives over gloo (never skipped)."""
     import torch
-    world = min(torch.cuda.device_count(), 4)
-    if world < 2:
-        pytest.skip("needs at least two GPUs")
+    ngpu = torch.cuda.device_count()
+    one_gpu = ngpu < 2
+    world = 2 if one_gpu else min(ngpu, 4)
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_nccl_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_nccl_worker, args=(r, world, port, q, one_gpu)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=180) for _ in procs]
