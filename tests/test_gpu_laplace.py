@@ -131,3 +131,52 @@ def test_ou_ssm_fit_recovers_the_measurement_error():
     x = sde.tmb_obj().par
     g = sde.tmb_obj().gr(r.x)
     assert np.max(np.abs(g)) < 1e-3 * max(1.0, abs(r.fun))
+
+
+def test_laplace_marginal_equals_the_exact_gaussian_marginal():
+    """Independent known answer for the Laplace marginal: BM with mu ~ s(time), sigma ~ 1.  The joint
+    objective is quadratic in coeff_re (the drift is linear in b, nllk_sde's penalty is the exact
+    -log N(b; 0, (lambda S)^-1), nllk_sde.hpp:89-124), so the Laplace approximation is exact and
+    f(theta) = -log N(increments; dt X_fe beta, sigma^2 diag(dt) + A (lambda S)^-1 A'), A = diag(dt) X_re.
+    Value to 1e-9, gradient to 1e-6 (torch float64 autograd of the dense density)."""
+    import torch
+    from collections import OrderedDict
+    from smoothsde_b200 import design
+    rng = np.random.default_rng(123)
+    T, m = 2, 70
+    t = simulate.make_times(T, m, rng, irregular=True)
+    s = t / t[:, -1:]
+    z = simulate.simulate_bm(t, 0.4 * np.sin(2 * np.pi * s), np.full_like(t, 0.7), rng)
+    n = T * m
+    ID = np.repeat(np.arange(1, T + 1), m)
+    obs = z.reshape(n, 1).copy()
+    obs[[5, 17, 90]] = np.nan
+    des = design.make_design(OrderedDict([("mu", "~ s(time, k = 6, bs = 'cs')"), ("sigma", "~ 1")]),
+                             {"ID": ID, "time": t.ravel()}, n)
+    dat = {"type": "BM", "ID": ID.astype(float), "times": t.ravel(), "obs": obs, "X_fe": des.X_fe, "X_re": des.X_re,
+           "S": des.S, "ncol_re": des.ncol_re, "include_penalty": 1}
+    nb = des.X_re.shape[1]
+    pars = {"coeff_fe": np.array([0.1, np.log(0.6)]), "log_lambda": np.array([0.3]), "coeff_re": np.zeros(nb)}
+    obj = ADFun(dat, pars, random="coeff_re")
+    x = obj.par.copy()
+    assert x.size == 3
+    f, g = obj._laplace.fn_gr(x)
+
+    # the dense Gaussian marginal of the increments
+    tt = t.ravel()
+    i0 = np.array([i for i in range(n - 1) if ID[i] == ID[i + 1] and not np.isnan(obs[i, 0]) and not np.isnan(obs[i + 1, 0])])
+    dt = torch.tensor(tt[i0 + 1] - tt[i0])
+    y = torch.tensor(obs[i0 + 1, 0] - obs[i0, 0])
+    Xre = torch.tensor(np.asarray(des.X_re.todense())[:n][i0])           # mu block = rows 0..n-1
+    Xfe = torch.tensor(np.asarray(des.X_fe.todense())[:n][i0, 0])
+    S = torch.tensor(np.asarray(des.S.todense()))
+    th = torch.tensor(x, requires_grad=True)
+    A = dt[:, None] * Xre
+    cov = torch.diag(torch.exp(2 * th[1]) * dt) + A @ torch.linalg.inv(torch.exp(th[2]) * S) @ A.T
+    mvn = torch.distributions.MultivariateNormal(dt * Xfe * th[0], covariance_matrix=cov)
+    exact = -mvn.log_prob(y)
+    exact.backward()
+    assert abs(f - float(exact)) <= 1e-9 * abs(float(exact)), (f, float(exact))
+    ge = th.grad.numpy()
+    assert np.max(np.abs(g - ge)) <= 1e-6 * max(1.0, np.max(np.abs(ge))), (g, ge)
+    obj.close()
