@@ -299,6 +299,10 @@ int ssde_last_kernel_times(ssde_handle* h, int cap, float* ms, const char** name
 int ssde_simulate_ctcrw(int device, int64_t n_tracks, int64_t n_steps, const double* d_times,
                         const double* d_tau, const double* d_nu, const double* d_mu,
                         const double* d_e1, const double* d_e2, double* d_z, void* stream);
+/* Exact-transition OU simulator (R/sde.R:1439-1447), same conventions: z_i | z_{i-1} uses the
+ * natural-scale parameters mu, tau, kappa of row i-1; d_e are standard normal draws. */
+int ssde_simulate_ou(int device, int64_t n_tracks, int64_t n_steps, const double* d_times, const double* d_mu,
+                     const double* d_tau, const double* d_kappa, const double* d_e, double* d_z, void* stream);
 
 const char* ssde_last_error(const ssde_handle* h);
 const char* ssde_create_error(void);

@@ -83,7 +83,7 @@ EXPORTS = ["ssde_create", "ssde_create_packed", "ssde_destroy", "ssde_n_par", "s
            "ssde_eval", "ssde_eval_device", "ssde_check", "ssde_report", "ssde_last_eval_ms",
            "ssde_last_eval_launches", "ssde_set_profile", "ssde_last_kernel_times", "ssde_last_error", "ssde_create_error", "ssde_version",
            "ssde_padded_rows", "ssde_layout_info", "ssde_pack_host", "ssde_pack_free",
-           "ssde_simulate_ctcrw", "ssde_launch_info",
+           "ssde_simulate_ctcrw", "ssde_simulate_ou", "ssde_launch_info",
            "ssde_shard_elem_doubles", "ssde_eval_stage",
            "ssde_hvp", "ssde_hvp_device", "ssde_hess_cols_device",
            "ssde_laplace_create", "ssde_laplace_destroy", "ssde_laplace_eval", "ssde_laplace_hessian_bb",
@@ -144,6 +144,8 @@ def load():
     lib.ssde_pack_free.restype = None
     lib.ssde_simulate_ctcrw.argtypes = [C.c_int, C.c_int64, C.c_int64] + [vp] * 8
     lib.ssde_simulate_ctcrw.restype = C.c_int
+    lib.ssde_simulate_ou.argtypes = [C.c_int, C.c_int64, C.c_int64] + [vp] * 7
+    lib.ssde_simulate_ou.restype = C.c_int
     lib.ssde_launch_info.argtypes = [vp, c_int32_p]
     lib.ssde_launch_info.restype = C.c_int
     lib.ssde_shard_elem_doubles.argtypes = [vp, C.c_int]

@@ -36,4 +36,26 @@ __global__ void ctcrw_sim_kernel(int64_t n_tracks, int64_t m, const double* __re
     }
 }
 
+// Exact-transition OU simulator (SDE$simulate for type "OU", R/sde.R:1439-1447): one thread per
+// track, z_i ~ N(mu + exp(-dt/tau)(z_{i-1} - mu), kappa (1 - exp(-2 dt/tau))) with the parameters
+// of row i-1.
+__global__ void ou_sim_kernel(int64_t n_tracks, int64_t m, const double* __restrict__ times,
+                              const double* __restrict__ mu, const double* __restrict__ tau,
+                              const double* __restrict__ kappa, const double* __restrict__ e,
+                              double* __restrict__ z) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tracks) return;
+    const int64_t base = t * m;
+    double zc = z[base];
+    for (int64_t i = 1; i < m; ++i) {
+        const int64_t j = base + i - 1;
+        const double d = times[j + 1] - times[j];
+        const double p = exp(-d / tau[j]);
+        const double mean = p * zc + (1.0 - p) * mu[j];
+        const double sd = sqrt(kappa[j] * (1.0 - p * p));
+        zc = mean + sd * e[j + 1];
+        z[j + 1] = zc;
+    }
+}
+
 }  // namespace ssde

@@ -1570,6 +1570,19 @@ int ssde_simulate_ctcrw(int device, int64_t n_tracks, int64_t n_steps, const dou
     return SSDE_OK;
 }
 
+int ssde_simulate_ou(int device, int64_t n_tracks, int64_t n_steps, const double* d_times, const double* d_mu,
+                     const double* d_tau, const double* d_kappa, const double* d_e, double* d_z, void* stream) {
+    std::string& err = g_create_error;
+    err.clear();
+    if (n_tracks < 1 || n_steps < 1 || !d_times || !d_mu || !d_tau || !d_kappa || !d_e || !d_z) { err = "bad argument"; return SSDE_ERR_BAD_ARG; }
+    CUDA_TRY(cudaSetDevice(device));
+    const int nt = 32;
+    ou_sim_kernel<<<(unsigned)((n_tracks + nt - 1) / nt), nt, 0, (cudaStream_t)stream>>>(
+        n_tracks, n_steps, d_times, d_mu, d_tau, d_kappa, d_e, d_z);
+    CUDA_TRY(cudaGetLastError());
+    return SSDE_OK;
+}
+
 double ssde_last_eval_ms(ssde_handle* h) {
     if (!h || !h->timed) return -1.0;
     if (cudaEventSynchronize(h->ev1) != cudaSuccess) return -1.0;

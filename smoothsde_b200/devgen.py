@@ -370,3 +370,180 @@ def permute_index(rows, lc):
 def alg_bytes_per_obs(n_dim, n_par, nnz_per_obs):
     """B_alg/n = (8 d + 8 + 4) + 2 [12 nnz/n + 4*2*n_par]."""
     return (8 * n_dim + 8 + 4) + 2 * (12 * nnz_per_obs + 8 * n_par)
+
+
+# ------------------------------------------------------------------------------------------------
+# OU with a random intercept per track: BASELINE configs[1] (64 x 1e5) and the OU half of configs[4]
+# (4096 x 2.5e4)
+# ------------------------------------------------------------------------------------------------
+def make_ou_device(n_tracks, n_steps, seed=20260102, device=0, k=10, rank=0, world=1, shard_flags=0):
+    """OU, d = 1: ``mu, tau ~ s(time, k) + s(ID, bs = "re")``, ``kappa ~ 1`` for this
+    rank's `n_tracks` of `world * n_tracks` tracks x `n_steps` regular steps, built on the device in the
+    packed layout.  Columns: coeff_fe = (mu, tau, kappa intercepts); coeff_re = [mu.s(time) (k-1),
+    mu.s(ID) (all tracks), tau.s(time), tau.s(ID)] as SDE$make_mat orders them (R/sde.R:412-421);
+    S = blockdiag(S_time, I, S_time, I).  Each row has 23 nonzeros; a warp-tile that straddles two
+    tracks carries both tracks' random-intercept columns (25 slots).  Returns (engine, par, info)."""
+    import torch
+    dev = torch.device("cuda", device)
+    T, m = int(n_tracks), int(n_steps)
+    Ttot = T * world
+    g0 = rank * T                                   # global index of this rank's first track
+    n = T * m
+    assert m >= 256, "tracks shorter than a warp-tile are not handled by this generator"
+    info4 = (C.c_int32 * 4)()
+    L.load().ssde_layout_info(info4)
+    lc, wt = int(info4[0]), int(info4[1])
+    n_pad = int(L.load().ssde_padded_rows(n))
+    nq = n_pad // wt
+    km1 = k - 1
+    p_fe, p_re = 3, 2 * (km1 + Ttot)
+    c_mu_spl, c_mu_re = p_fe, p_fe + km1
+    c_tau_spl, c_tau_re = p_fe + km1 + Ttot, p_fe + 2 * km1 + Ttot
+
+    # --- truth and data -------------------------------------------------------------------------
+    gen_all = torch.Generator(device=dev)
+    gen_all.manual_seed(int(seed) * 7919 + 1)
+    u_all = 0.3 * torch.randn(Ttot, dtype=torch.float64, device=dev, generator=gen_all)     # random intercepts (all ranks draw the same)
+    v_all = 0.2 * torch.randn(Ttot, dtype=torch.float64, device=dev, generator=gen_all)
+    rng = GroupedRNG(seed, Ttot, T, rank, dev)
+    t1 = torch.arange(m, dtype=torch.float64, device=dev)
+    s = (t1 / (m - 1))[None, :]
+    mu = 2.0 * torch.sin(2 * math.pi * s) + u_all[g0:g0 + T, None]
+    tau = torch.exp(0.5 * torch.sin(2 * math.pi * s) + v_all[g0:g0 + T, None])
+    kappa = torch.full((T, m), 1.5, dtype=torch.float64, device=dev)
+    times = t1.repeat(T, 1).contiguous()
+    e = rng.draw("normal", m)
+    z = torch.zeros((T, m), dtype=torch.float64, device=dev)
+    z[:, 0] = mu[:, 0]
+    lib = L.load()
+    torch.cuda.synchronize(dev)
+    rc = lib.ssde_simulate_ou(device, T, m, times.data_ptr(), mu.contiguous().data_ptr(), tau.contiguous().data_ptr(),
+                              kappa.data_ptr(), e.data_ptr(), z.data_ptr(), None)
+    if rc != 0:
+        raise L.EngineError(rc, lib.ssde_create_error().decode())
+    torch.cuda.synchronize(dev)
+    del e, mu, tau, kappa
+    obs = z.reshape(-1)
+    dt = torch.ones(n, dtype=torch.float64, device=dev)
+    flags = torch.zeros(n, dtype=torch.uint8, device=dev)
+    first = torch.arange(0, n, m, device=dev)
+    flags[first] |= 1
+    flags[first + (m - 1)] |= 2
+
+    # --- spline block: identical for every track (regular times), sum-to-zero over one track ------
+    lo, hi = 0.0, float(m - 1)
+    B1 = _bspline_torch(t1, k, lo, hi)
+    means = B1.mean(0).cpu().numpy()
+    Zc = _design.sum_to_zero_transform(means)
+    S1 = Zc.T @ _design.second_diff_penalty(k) @ Zc + 1e-2 * np.eye(km1)
+    S1 = 0.5 * (S1 + S1.T)
+    Bz1 = B1 @ torch.as_tensor(Zc, device=dev)                  # [m, k-1]
+
+    # --- warp-tile descriptors ---------------------------------------------------------------------
+    q = torch.arange(nq, device=dev, dtype=torch.int64)
+    r_first = q * wt
+    live = r_first < n
+    r_last = torch.clamp(r_first + wt - 1, max=n - 1)
+    tr_a = torch.where(live, r_first // m, torch.zeros_like(q))
+    tr_b = torch.where(live, r_last // m, torch.zeros_like(q))
+    two = live & (tr_b > tr_a)
+    nre = torch.where(two, 2, 1)
+    S_q = torch.where(live, 2 * (1 + km1) + 2 * nre + 1, torch.zeros_like(q))
+    val_off = torch.cumsum(S_q * wt, 0) - S_q * wt
+    col_off = torch.cumsum(S_q, 0) - S_q
+    n_val, n_col = int((S_q * wt).sum()), int(S_q.sum())
+    kp = (1 + km1) + nre
+    kmax = torch.where(live, kp | (kp << 8) | (1 << 16), torch.zeros_like(q))
+    desc = torch.empty((nq, 3), dtype=torch.int64, device=dev)
+    desc[:, 0] = val_off
+    desc[:, 1] = col_off
+    desc[:, 2] = kmax | (1 << 32)                               # flags = WT_UNIFORM
+    col = torch.zeros(max(n_col, 1), dtype=torch.int32, device=dev)
+    spl = torch.arange(km1, device=dev, dtype=torch.int64)
+    for is_two in (False, True):
+        sel = torch.nonzero(live & (two == is_two)).reshape(-1)
+        if sel.numel() == 0:
+            continue
+        ga, gb = g0 + tr_a[sel], g0 + tr_b[sel]
+        ns = sel.numel()
+        one = torch.ones(ns, dtype=torch.int64, device=dev)
+        re_mu = [c_mu_re + ga] + ([c_mu_re + gb] if is_two else [])
+        re_tau = [c_tau_re + ga] + ([c_tau_re + gb] if is_two else [])
+        cols = torch.stack([0 * one] + [(c_mu_spl + j) * one for j in range(km1)] + re_mu
+                           + [1 * one] + [(c_tau_spl + j) * one for j in range(km1)] + re_tau + [2 * one], dim=1)
+        dest = col_off[sel][:, None] + torch.arange(cols.shape[1], device=dev)[None, :]
+        col[dest.reshape(-1)] = cols.reshape(-1).to(torch.int32)
+    del spl
+
+    # --- values, in chunks of warp-tiles ---------------------------------------------------------------
+    val = torch.zeros(max(n_val, 1), dtype=torch.float64, device=dev)
+    CHQ = 1 << 12
+    for q0 in range(0, nq, CHQ):
+        q1 = min(q0 + CHQ, nq)
+        rows = torch.arange(q0 * wt, q1 * wt, device=dev, dtype=torch.int64)
+        real = rows < n
+        rr = torch.clamp(rows, max=n - 1)
+        trk = rr // m
+        Bz = Bz1[rr - trk * m] * real[:, None]                   # [rows, k-1], zero on padding rows
+        onev = real.to(torch.float64)
+        for is_two in (False, True):
+            sel = torch.nonzero((live & (two == is_two))[q0:q1]).reshape(-1)
+            if sel.numel() == 0:
+                continue
+            S_here = 2 * (1 + km1) + (4 if is_two else 2) + 1
+            rsel = (sel[:, None] * wt + torch.arange(wt, device=dev)[None, :]).reshape(-1)      # rows of the selected tiles
+            V = torch.zeros((rsel.numel(), S_here), dtype=torch.float64, device=dev)
+            o = 0
+            for _p in range(2):                                # mu block, tau block
+                V[:, o] = onev[rsel]
+                V[:, o + 1:o + 1 + km1] = Bz[rsel]
+                o += 1 + km1
+                if is_two:
+                    in_a = (trk[rsel] == tr_a[q0:q1][sel].repeat_interleave(wt))
+                    V[:, o] = onev[rsel] * in_a
+                    V[:, o + 1] = onev[rsel] * (~in_a)
+                    o += 2
+                else:
+                    V[:, o] = onev[rsel]
+                    o += 1
+            V[:, o] = onev[rsel]                               # kappa intercept
+            blocks = V.reshape(sel.numel(), 32, lc, S_here).permute(0, 2, 3, 1).reshape(sel.numel(), -1)
+            dest = val_off[q0:q1][sel][:, None] + torch.arange(S_here * wt, device=dev)[None, :]
+            val[dest.reshape(-1)] = blocks.reshape(-1)
+            del V, blocks, dest
+    obs_p = permute_rows(obs.contiguous(), n_pad, lc, 0.0).reshape(1, n_pad).contiguous()
+    dt_p = permute_rows(dt, n_pad, lc, 1.0)
+    flags_p = permute_rows(flags, n_pad, lc, 255)
+
+    keep = [desc, col, val, obs_p, dt_p, flags_p]
+    pd = L.PackedDesc()
+    pd.model, pd.n_dim, pd.n_par = L.SSDE_OU, 1, 3
+    nnz = n * 23
+    pd.n, pd.n_pad, pd.nnz = n, n_pad, nnz
+    pd.d_desc, pd.d_col, pd.d_val = desc.data_ptr(), col.data_ptr(), val.data_ptr()
+    pd.d_obs, pd.d_dt, pd.d_flags = obs_p.data_ptr(), dt_p.data_ptr(), flags_p.data_ptr()
+    pd.p_fe, pd.p_re = p_fe, p_re
+    S = sp.block_diag([S1, sp.identity(Ttot), S1, sp.identity(Ttot)], format="csr")
+    pd.S = _as_triplet(S, keep)
+    ncol_re = np.array([km1, Ttot, km1, Ttot], dtype=np.int32)
+    keep.append(ncol_re)
+    pd.n_smooth = 4
+    pd.ncol_re = ncol_re.ctypes.data_as(L.c_int32_p)
+    pd.include_penalty = 1
+    pd.n_ID = T
+    ts = np.ascontiguousarray(np.arange(0, n, m, dtype=np.int64))
+    keep.append(ts)
+    pd.track_starts = ts.ctypes.data_as(L.c_int64_p)
+    pd.a0 = None
+    pd.device = device
+    pd.shard_flags = shard_flags
+    pd.mu_cols, pd.n_mu_cols = None, 0
+    torch.cuda.synchronize(dev)
+    eng = Engine.from_packed(pd, keep)
+
+    prng = np.random.default_rng(seed + 1)
+    par = np.concatenate([[0.0, 0.0, math.log(1.5)], np.zeros(4), 0.1 * prng.standard_normal(p_re)])
+    info = {"n": n, "n_dim": 1, "nnz": nnz, "p_fe": p_fe, "p_re": p_re, "n_s": 4, "n_par": 3, "n_tracks": T,
+            "n_tracks_total": Ttot, "first_track": g0, "n_pad": n_pad, "S": S, "Bz1": Bz1, "m": m, "k": k,
+            "tensors": dict(obs=obs, dt=dt, flags=flags, times=times.reshape(-1))}
+    return eng, par, info

@@ -70,3 +70,48 @@ def test_device_built_shapes_match_the_c_oracle_at_1e7_rows(T, m, seed):
     v3, g3 = eng.eval(par, order=1)             # shortcut back on: same result as before
     assert v3 == v
     eng.close()
+
+
+def test_device_built_ou_with_random_intercepts_matches_the_c_oracle_at_1e7_rows():
+    """The OU half of configs[4] / configs[1]: mu, tau ~ s(time, k = 10) + s(ID, bs = "re"), kappa ~ 1,
+    512 tracks x 25 000 steps (1.28e7 rows, p_re = 1042; warp-tiles that straddle two tracks carry both
+    tracks' random-intercept columns).  The oracle sees the natural (row, column, value) design."""
+    from smoothsde_b200 import devgen
+    T, m, k = 512, 25000, 10
+    eng, par, info = devgen.make_ou_device(T, m, seed=20260102, device=0)
+    n, p_fe, p_re = info["n"], info["p_fe"], info["p_re"]
+    rng = np.random.default_rng(2)
+    par = par.copy()
+    par[:3] = [0.2, 0.1, np.log(1.3)]
+    par[3:7] = [0.3, -0.4, 0.2, 0.5]            # log lambda
+    par[7:] = 0.2 * rng.standard_normal(p_re)
+    v, g = eng.eval(par, order=1)
+    # natural design: rows j*n + i; mu: [intercept, 9 spline, own random intercept], tau alike, kappa: [intercept]
+    Bz = info["Bz1"].cpu().numpy()                                  # [m, k-1], the same for every track
+    km1 = k - 1
+    trk = np.repeat(np.arange(T), m)
+    cnt = np.concatenate([np.full(n, 2 + km1), np.full(n, 2 + km1), np.full(n, 1)]).astype(np.int64)
+    rowptr = np.concatenate([[0], np.cumsum(cnt)])
+    spl = np.arange(km1)
+    col_mu = np.empty((n, 2 + km1), np.int32)
+    col_mu[:, 0] = 0
+    col_mu[:, 1:1 + km1] = p_fe + spl
+    col_mu[:, 1 + km1] = p_fe + km1 + trk
+    col_tau = np.empty((n, 2 + km1), np.int32)
+    col_tau[:, 0] = 1
+    col_tau[:, 1:1 + km1] = p_fe + km1 + T + spl
+    col_tau[:, 1 + km1] = p_fe + 2 * km1 + T + trk
+    vals = np.empty((n, 2 + km1))
+    vals[:, 0] = 1.0
+    vals[:, 1:1 + km1] = np.tile(Bz, (T, 1))
+    vals[:, 1 + km1] = 1.0
+    col = np.concatenate([col_mu.ravel(), col_tau.ravel(), np.full(n, 2, np.int32)])
+    data = np.concatenate([vals.ravel(), vals.ravel(), np.ones(n)])
+    ten = info["tensors"]
+    co = oracle_c.COracle.from_csr("OU", trk.astype(float) + 1, ten["times"].cpu().numpy(), ten["obs"].cpu().numpy().reshape(n, 1),
+                                   rowptr, col, data, p_fe, p_re, sp.csr_matrix(info["S"]), np.array([km1, T, km1, T]),
+                                   nthreads=len(os.sched_getaffinity(0)))
+    ref_v, ref_g = co.eval(par, True)
+    assert abs(v - ref_v) <= 1e-10 * abs(ref_v), (v, ref_v)
+    assert grad_err(g, ref_g) <= 1e-7
+    eng.close()
