@@ -24,7 +24,7 @@ NVCC_FLAGS = [
 # Development only -- the split changes register allocation of the two hot kernels and measured
 # 4 % slower on the B200 (12.9 vs 12.45 ms / 1.024e8 rows), so release builds stay single-unit.
 FAST_FLAGS = ["--split-compile", "0", "--threads", "0"]
-LINK_FLAGS = ["-lcusolver"]          # dense Cholesky of the random-effect Hessian block (ssde_laplace.cu)
+LINK_FLAGS = ["-lcusolver", "-lpthread"]          # dense Cholesky of the random-effect Hessian block (ssde_laplace.cu)
 
 
 def sources():

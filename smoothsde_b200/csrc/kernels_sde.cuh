@@ -57,7 +57,9 @@ __device__ __forceinline__ void sde_row(const R* eta, double d_t, unsigned na, Z
         // mean = mu + exp(-dt/tau)(z0 - mu), sd = sqrt(kappa (1 - exp(-2 dt/tau)))
         const R tau = exp(eta[ND]), kappa = exp(eta[ND + 1]);
         const R ph = exp(-d_t / tau);
-        const R var = kappa * (1.0 - exp(-2.0 * d_t / tau));     // tr_dens.hpp:50-51
+        // tr_dens.hpp:50-51 evaluates exp(-2 dt / tau) on its own; ph * ph differs from it by <= 1.5 ulp,
+        // far inside the 1e-10 budget, and saves a fourth exp per row
+        const R var = kappa * (1.0 - ph * ph);
         const R sd = sqrt(var), isd = 1.0 / sd, lsd = log(sd);
         const R dph = ph * d_t / tau;                  // d ph / d eta_tau
         const R dlv = -2.0 * kappa * ph * dph / var;   // d log var / d eta_tau
@@ -119,6 +121,292 @@ __global__ void __launch_bounds__(SDE_NT) sde_fused_kernel(SdeArgs a) {
     }
     const double bl = block_sum<SDE_NT>(value(llk), sm.red);
     if (threadIdx.x == 0) a.block_llk[blockIdx.x] = bl;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Streaming variant for designs whose warp-tiles are all uniform with at most SDE_SMAX slots (every
+// mgcv smooth / random-intercept design of the benchmark shapes).  One pass over HBM:
+//   * the S x 32 values of a row-step arrive by TMA bulk copy into a double-buffered per-warp
+//     staging area (the copy of row-step k+1 is in flight while the warp works on k), so a warp
+//     keeps 6-12 KB of the design stream in flight instead of a handful of 8-byte loads;
+//   * eta is formed from shared memory, the transition density and d nllk / d eta in registers, and
+//     the row's contribution to X' eta_bar is accumulated at once, per slot, in registers
+//     (acc[j] += x_j * eta_bar_p(j)) -- the design is never read a second time;
+//   * after the LC rows the 32 lanes' partial sums are added through the (now idle) staging
+//     buffer, one lane per slot, and go to per-CTA shared-memory accumulators when the column
+//     lies in a "hot" range (fixed effects and small smooth blocks, which every warp-tile
+//     touches) or straight to global memory (random intercepts: one column per track).
+// ---------------------------------------------------------------------------------------------
+constexpr int SDE_SMAX = 32;          // slots per warp-tile the streaming kernel stages
+constexpr int SDE_KPM = 12;           // ... and slots per SDE parameter (static register accumulators)
+constexpr int SDE_HOT = 512;          // per-CTA hot accumulators (doubles)
+constexpr int SDE_MAX_HOT_RANGES = 8;
+
+struct HotRanges {
+    int n;
+    int lo[SDE_MAX_HOT_RANGES], hi[SDE_MAX_HOT_RANGES], off[SDE_MAX_HOT_RANGES];
+};
+
+struct SdeStreamSmem {
+    double stage[SDE_NT / 32][2][SDE_SMAX * 32];
+    double th[SDE_NT / 32][SDE_SMAX];
+    double hot[SDE_HOT];
+    uint64_t bar[SDE_NT / 32][2];
+    double red[8];
+};
+
+// slots of one parameter in groups of four: full groups run without predicates
+#define SSDE_SLOT_GROUPS(KP, BODY)                                           \
+    _Pragma("unroll") for (int g_ = 0; g_ < SDE_KPM; g_ += 4) {              \
+        if (g_ + 4 <= (KP)) {                                                \
+            _Pragma("unroll") for (int i = g_; i < g_ + 4; ++i) { BODY; }    \
+        } else if (g_ < (KP)) {                                              \
+            _Pragma("unroll") for (int i = g_; i < g_ + 4; ++i) if (i < (KP)) { BODY; } \
+        }                                                                    \
+    }
+
+// The row arithmetic of sde_row for plain doubles with the divisions folded away (every rewrite is
+// an identity up to 1-2 ulp: 1/tau = exp(-eta_tau), 1/sd = rsqrt(var), log sd = log(var)/2,
+// d log var / d eta_tau = -2 kappa ph dph / var).  Straight-line code, so that the two rows the
+// streaming kernel works on at a time interleave in the instruction stream.
+template <int MODEL, int ND>
+__device__ __forceinline__ void sde_row_fast(const double* eta, double d_t, unsigned na, const double* z0, const double* z1,
+                                             double& llk, double* eb) {
+    if (MODEL == MODEL_BM) {
+        const double isd = exp(-eta[ND]) * rsqrt(d_t);             // sd = exp(eta_s) sqrt(dt), tr_dens.hpp:36
+        const double lsd = eta[ND] + 0.5 * log(d_t);
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+            if ((na >> d) & 1) continue;                           // tr_dens.hpp:31
+            const double res = (z1[d] - (z0[d] + eta[d] * d_t)) * isd;
+            llk += -LOG_SQRT_2PI - lsd - 0.5 * res * res;
+            eb[d] = -res * d_t * isd;
+            eb[ND] += 1.0 - res * res;
+        }
+    } else {
+        const double itau = exp(-eta[ND]), kappa = exp(eta[ND + 1]);
+        const double x = d_t * itau;
+        const double ph = exp(-x);                                 // tr_dens.hpp:49
+        const double var = kappa * (1.0 - ph * ph);                // tr_dens.hpp:50-51 (exp(-2 dt/tau) = ph^2 up to 1.5 ulp)
+        const double isd = rsqrt(var), lsd = 0.5 * log(var);
+        const double dph = ph * x;                                 // d ph / d eta_tau
+        const double dlv = -2.0 * kappa * ph * dph * isd * isd;    // d log var / d eta_tau
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+            if ((na >> d) & 1) continue;
+            const double res = (z1[d] - (eta[d] + ph * (z0[d] - eta[d]))) * isd;
+            llk += -LOG_SQRT_2PI - lsd - 0.5 * res * res;
+            eb[d] = -res * (1.0 - ph) * isd;
+            eb[ND] += 0.5 * dlv * (1.0 - res * res) - res * isd * dph * (z0[d] - eta[d]);
+            eb[ND + 1] += 0.5 * (1.0 - res * res);
+        }
+    }
+}
+
+template <int MODEL, int ND>
+__global__ void __launch_bounds__(SDE_NT, 3) sde_stream_kernel(SdeArgs a, HotRanges hr) {
+    constexpr int NP = (MODEL == MODEL_BM) ? ND + 1 : ND + 2;
+    constexpr int NWARP = SDE_NT / 32;
+    static_assert(LC % 2 == 0, "rows are processed in pairs");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    SdeStreamSmem& sm = *reinterpret_cast<SdeStreamSmem*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < SDE_HOT; i += SDE_NT) sm.hot[i] = 0.0;
+    double* buf[2] = {sm.stage[warp][0], sm.stage[warp][1]};
+    uint64_t* bar[2] = {&sm.bar[warp][0], &sm.bar[warp][1]};
+    if (lane == 0) { mbar_init(bar[0], 1); mbar_init(bar[1], 1); }
+    mbar_fence_init();
+    __syncthreads();
+    unsigned phase = 0;
+    double* th = sm.th[warp];
+    double llk = 0.0;
+    for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        const int64_t q = tile * NWARP + warp;
+        const WtDesc d = a.X.desc[q];
+        const int S = slots_of(d.kmax);
+        if (S == 0) continue;                                      // padding warp-tile
+        int kp[NP];
+#pragma unroll
+        for (int p = 0; p < NP; ++p) kp[p] = (int)((d.kmax >> (8 * p)) & 255u);
+        const double* blk = a.X.val + d.val_off;
+        const uint32_t* cols = a.X.col + d.col_off;
+        const unsigned bytes = (unsigned)S * 32u * 8u;             // one row-step
+        __syncwarp();                                              // previous warp-tile: all lanes done with th / staging
+        if (lane == 0) {
+            fence_proxy_async();
+            mbar_expect_tx(bar[0], bytes);
+            tma_load_1d(buf[0], blk, bytes, bar[0]);
+            mbar_expect_tx(bar[1], bytes);
+            tma_load_1d(buf[1], blk + (size_t)S * 32, bytes, bar[1]);
+            // the design stream runs two pairs ahead of the copies: they then hit L2
+            prefetch_l2(blk + (size_t)2 * S * 32, 4u * bytes);
+        }
+        if (lane < S) th[lane] = __ldg(a.theta.v + __ldg(cols + lane));
+        const int64_t base = q * WT + lane;
+        const int64_t row0 = q * WT + (int64_t)lane * LC;
+        double acc[NP][SDE_KPM];
+#pragma unroll
+        for (int p = 0; p < NP; ++p)
+#pragma unroll
+            for (int i = 0; i < SDE_KPM; ++i) acc[p][i] = 0.0;
+        // Per-row data: the LC flags of the chunk and the flag of the row after it are loaded up
+        // front; dt and the observations of a pair are fetched while the previous pair is worked on.
+        const double* p_dt = a.dt + base;
+        const double* p_obs[ND];
+#pragma unroll
+        for (int dd = 0; dd < ND; ++dd) p_obs[dd] = a.obs + (size_t)dd * a.X.n_pad + base;
+        const int64_t nx8 = row_pos(row0 + LC) - base;             // offset of the row after this chunk (next lane / next warp-tile)
+        const unsigned long long fl = load_flags8(a.flags, base);
+        const bool any_next = (uint8_t)(fl >> 56) != 0xff && !((uint8_t)(fl >> 56) & ROW_LAST);
+        const uint8_t f8 = any_next ? a.flags[base + nx8] : (uint8_t)0;
+        auto live_row = [&](int k) { return (uint8_t)(fl >> (8 * k)) != 0xff; };
+        // obs of rows k, k+1, k+2 (za, zb, zc) and dt of rows k, k+1 for the current pair; *_n: next pair
+        double za[ND], zb[ND], zc[ND], dta = live_row(0) ? p_dt[0] : 1.0, dtb = live_row(1) ? p_dt[32] : 1.0;
+#pragma unroll
+        for (int dd = 0; dd < ND; ++dd) {
+            za[dd] = live_row(0) ? p_obs[dd][0] : 0.0;
+            zb[dd] = live_row(1) ? p_obs[dd][32] : 0.0;
+            zc[dd] = live_row(2) ? p_obs[dd][64] : 0.0;
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (int k = 0; k < LC; k += 2) {
+            // fetch for the next pair (rows k+2, k+3): dt of both, obs of rows k+3 and k+4
+            double dta_n = 1.0, dtb_n = 1.0, zb_n[ND], zc_n[ND];
+#pragma unroll
+            for (int dd = 0; dd < ND; ++dd) { zb_n[dd] = 0.0; zc_n[dd] = 0.0; }
+            if (k + 2 < LC) {
+                if (live_row(k + 2)) dta_n = p_dt[(k + 2) * 32];
+                if (live_row(k + 3)) {
+                    dtb_n = p_dt[(k + 3) * 32];
+#pragma unroll
+                    for (int dd = 0; dd < ND; ++dd) zb_n[dd] = p_obs[dd][(k + 3) * 32];
+                }
+                if (k + 4 < LC) {
+                    if (live_row(k + 4)) {
+#pragma unroll
+                        for (int dd = 0; dd < ND; ++dd) zc_n[dd] = p_obs[dd][(k + 4) * 32];
+                    }
+                } else if (any_next) {
+#pragma unroll
+                    for (int dd = 0; dd < ND; ++dd) zc_n[dd] = p_obs[dd][nx8];
+                }
+                if (lane == 0 && k + 6 < LC) prefetch_l2(blk + (size_t)(k + 6) * S * 32, 2u * bytes);
+            }
+            const uint8_t fa = (uint8_t)(fl >> (8 * k)), fb = (uint8_t)(fl >> (8 * (k + 1)));
+            const uint8_t fc = (k + 2 < LC) ? (uint8_t)(fl >> (8 * (k + 2))) : f8;
+            const bool live_a = fa != 0xff && !(fa & ROW_LAST);    // ID(i) == ID(i+1), nllk_sde.hpp:79
+            const bool live_b = fb != 0xff && !(fb & ROW_LAST);
+            mbar_wait(bar[0], phase);
+            mbar_wait(bar[1], phase);
+            phase ^= 1u;
+            const double* va = buf[0] + lane;
+            const double* vb = buf[1] + lane;
+            double eta_a[NP], eta_b[NP], eb_a[NP], eb_b[NP];
+            {
+                int o = 0;
+#pragma unroll
+                for (int p = 0; p < NP; ++p) {
+                    const double* xa = va + o * 32;
+                    const double* xb = vb + o * 32;
+                    const double* tp = th + o;
+                    double e0 = 0.0, e1 = 0.0, g0 = 0.0, g1 = 0.0;
+                    SSDE_SLOT_GROUPS(kp[p], { const double t = tp[i];
+                                              if (i & 1) { e1 = fma(xa[i * 32], t, e1); g1 = fma(xb[i * 32], t, g1); }
+                                              else { e0 = fma(xa[i * 32], t, e0); g0 = fma(xb[i * 32], t, g0); } })
+                    eta_a[p] = e0 + e1; eta_b[p] = g0 + g1;
+                    eb_a[p] = 0.0; eb_b[p] = 0.0;
+                    o += kp[p];
+                }
+            }
+            // both rows unconditionally (a dead row has dt = 1 and zero observations: finite arithmetic,
+            // result discarded) so that the two dependency chains interleave
+            double la = 0.0, lb = 0.0;
+            sde_row_fast<MODEL, ND>(eta_a, dta, (unsigned)((fa | fb) >> 3), za, zb, la, eb_a);
+            sde_row_fast<MODEL, ND>(eta_b, dtb, (unsigned)((fb | fc) >> 3), zb, zc, lb, eb_b);
+            if (live_a) llk += la;
+            if (live_b) llk += lb;
+            if (a.want_grad) {
+                int o = 0;
+#pragma unroll
+                for (int p = 0; p < NP; ++p) {
+                    const double ea = live_a ? eb_a[p] : 0.0, eb_ = live_b ? eb_b[p] : 0.0;
+                    const double* xa = va + o * 32;
+                    const double* xb = vb + o * 32;
+                    SSDE_SLOT_GROUPS(kp[p], acc[p][i] = fma(xb[i * 32], eb_, fma(xa[i * 32], ea, acc[p][i])))
+                    o += kp[p];
+                }
+            }
+            __syncwarp();
+            if (k + 2 < LC) {
+                if (lane == 0) {
+                    fence_proxy_async();
+                    mbar_expect_tx(bar[0], bytes);
+                    tma_load_1d(buf[0], blk + (size_t)(k + 2) * S * 32, bytes, bar[0]);
+                    mbar_expect_tx(bar[1], bytes);
+                    tma_load_1d(buf[1], blk + (size_t)(k + 3) * S * 32, bytes, bar[1]);
+                }
+                dta = dta_n; dtb = dtb_n;
+#pragma unroll
+                for (int dd = 0; dd < ND; ++dd) { za[dd] = zc[dd]; zb[dd] = zb_n[dd]; zc[dd] = zc_n[dd]; }
+            }
+        }
+        if (a.want_grad) {
+            // X' eta_bar of this warp-tile: T(j, lane) in the staging buffer, lane j adds slot j
+            double* T = buf[0] + lane;
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+                SSDE_SLOT_GROUPS(kp[p], T[i * 32] = acc[p][i])
+                T += kp[p] * 32;
+            }
+            __syncwarp();
+            if (lane < S) {
+                const double* Tr = buf[0] + lane * 32;
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    s0 += Tr[(i + lane) & 31];
+                    s1 += Tr[(i + 1 + lane) & 31];
+                    s2 += Tr[(i + 2 + lane) & 31];
+                    s3 += Tr[(i + 3 + lane) & 31];
+                }
+                const double sum = (s0 + s1) + (s2 + s3);
+                const int c = (int)__ldg(cols + lane);
+                int h = -1;
+#pragma unroll
+                for (int r = 0; r < SDE_MAX_HOT_RANGES; ++r) if (r < hr.n && c >= hr.lo[r] && c < hr.hi[r]) h = hr.off[r] + (c - hr.lo[r]);
+                if (h >= 0) atomicAdd(sm.hot + h, sum);
+                else atomicAdd(a.grad_theta + c, sum);
+            }
+        }
+    }
+    __syncthreads();
+    if (a.want_grad) {
+        for (int r = 0; r < hr.n; ++r)
+            for (int i = tid; i < hr.hi[r] - hr.lo[r]; i += SDE_NT) {
+                const double x = sm.hot[hr.off[r] + i];
+                if (x != 0.0) atomicAdd(a.grad_theta + hr.lo[r] + i, x);
+            }
+    }
+    const double bl = block_sum<SDE_NT>(llk, sm.red);
+    if (threadIdx.x == 0) a.block_llk[blockIdx.x] = bl;
+}
+#undef SSDE_SLOT_GROUPS
+
+// max slots per warp-tile and "every warp-tile is uniform" (device-built designs are checked on the device)
+__global__ void design_shape_kernel(const WtDesc* __restrict__ desc, int64_t nwt, int* __restrict__ out) {
+    int smax = 0, nonuni = 0, kpmax = 0;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nwt; q += (int64_t)gridDim.x * blockDim.x) {
+        const WtDesc d = desc[q];
+        const int S = slots_of(d.kmax);
+        smax = max(smax, S);
+#pragma unroll
+        for (int p = 0; p < MAX_NP; ++p) kpmax = max(kpmax, (int)((d.kmax >> (8 * p)) & 255u));
+        if (S > 0 && !(d.flags & WT_UNIFORM)) nonuni = 1;
+    }
+    atomicMax(out + 0, smax);
+    if (nonuni) atomicOr(out + 1, 1);
+    atomicMax(out + 2, kpmax);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -7,6 +7,10 @@
 #include <cstring>
 #include <new>
 #include <memory>
+#include <thread>
+#include <chrono>
+#include <exception>
+#include <sched.h>
 #include <string>
 #include <vector>
 
@@ -86,6 +90,9 @@ struct ssde_handle {
     bool tan_ready = false;
     DevBuf t_dir, t_theta_dot, t_grad_theta, t_wg, t_ckpt, t_tile_gh, t_f_agg, t_f_incl, t_b_agg, t_b_incl, t_out, t_hess;
     int grid_f2 = 0, grid_b2 = 0, grid_lp2 = 0;
+    bool sde_stream = false;         // BM / OU: every warp-tile is uniform with <= SDE_SMAX slots -> sde_stream_kernel
+    int grid_stream = 0;
+    HotRanges hot{};                 // columns whose gradient entries get per-CTA shared-memory accumulators
     double* h_pinned = nullptr;      // pinned host staging: par in, out back
     unsigned epoch = 0;
     int ntiles_f = 0, ntiles_b = 0, grid_lp = 0, grid_f = 0, grid_b = 0;
@@ -317,56 +324,142 @@ __global__ void unit_vector_kernel(double* __restrict__ dir, int n, int j) {
 // ---------------------------------------------------------------------------------------------
 // host-side helpers
 // ---------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------
+// host-side packing of the triplet design (ssde_create): O(nnz) bucket passes + small per-row
+// sorts, spread over the host cores (a comparison sort of 1.5e8 triplets alone took ~10 s)
+// ---------------------------------------------------------------------------------------------
+struct PhaseTimer {
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    PhaseTimer() : on(std::getenv("SSDE_PACK_TIMING") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void lap(const char* what) {
+        if (!on) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[ssde pack] %-28s %.3f s\n", what, std::chrono::duration<double>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+int host_threads(int64_t work) {
+    unsigned hc = std::thread::hardware_concurrency();
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof(set), &set) == 0) hc = (unsigned)CPU_COUNT(&set);
+    int t = (int)std::min<unsigned>(std::max(hc, 1u), 32u);
+    if (work < (1 << 16)) t = 1;
+    return t;
+}
+// fn(thread, lo, hi) over [0, n) in contiguous pieces; exceptions of the workers are rethrown here
+template <class Fn>
+void parallel_ranges(int64_t n, int nthreads, Fn&& fn) {
+    if (nthreads <= 1 || n < 2) { fn(0, (int64_t)0, n); return; }
+    std::vector<std::thread> th;
+    std::vector<std::exception_ptr> ex((size_t)nthreads);
+    for (int t = 0; t < nthreads; ++t) {
+        const int64_t lo = n * t / nthreads, hi = n * (t + 1) / nthreads;
+        th.emplace_back([&, t, lo, hi] {
+            try { fn(t, lo, hi); } catch (...) { ex[(size_t)t] = std::current_exception(); }
+        });
+    }
+    for (auto& x : th) x.join();
+    for (auto& e : ex) if (e) std::rethrow_exception(e);
+}
+
+// Row-major packed design: the nonzeros of row i (all parameters, parameter-major, columns
+// ascending, duplicates summed in triplet order) start at rowptr[i]; byte p of cnt[i] = nonzeros
+// of parameter p.  Rows are NOT contiguous in col / val (the space of summed duplicates and of
+// explicit zeros stays unused), `nnz` is the number of packed nonzeros.
 struct Packed {
     std::vector<uint32_t> rowptr, cnt, col;
     std::vector<double> val;
+    int64_t nnz = 0;
 };
 
 int pack_design(const ssde_desc& d, int n_par, Packed& out, std::string& err) {
     const int64_t n = d.n;
     const ssde_triplet* mats[2] = {&d.X_fe, &d.X_re};
-    const int64_t total = d.X_fe.nnz + d.X_re.nnz;
-    struct Ent { uint64_t key; uint32_t col; double x; };
-    std::vector<Ent> ents;
-    ents.reserve(total);
-    for (int m = 0; m < 2; ++m) {
-        const ssde_triplet& T = *mats[m];
-        const uint32_t coff = (m == 0) ? 0u : (uint32_t)d.X_fe.ncol;
-        for (int64_t k = 0; k < T.nnz; ++k) {
-            const int64_t r = T.i[k], c = T.j[k];
-            if (r < 0 || r >= T.nrow || c < 0 || c >= T.ncol) { err = "design triplet index out of range"; return SSDE_ERR_BAD_ARG; }
-            if (T.x[k] == 0.0) continue;
-            const int64_t p = r / n, i = r % n;
-            ents.push_back({(uint64_t)(i * n_par + p), coff + (uint32_t)c, T.x[k]});
+    const int64_t nnz_fe = d.X_fe.nnz, total = d.X_fe.nnz + d.X_re.nnz;
+    const int nt = host_threads(total);
+    auto triplet = [&](int64_t k, int64_t& r, int64_t& c, double& x, uint32_t& coff) {
+        const ssde_triplet& T = *mats[k < nnz_fe ? 0 : 1];
+        const int64_t kk = k < nnz_fe ? k : k - nnz_fe;
+        r = T.i[kk]; c = T.j[kk]; x = T.x[kk];
+        coff = k < nnz_fe ? 0u : (uint32_t)d.X_fe.ncol;
+        return r >= 0 && r < T.nrow && c >= 0 && c < T.ncol;
+    };
+    PhaseTimer pt;
+    // (1) nonzeros per row
+    std::vector<uint32_t> fill((size_t)n, 0u);
+    std::vector<int> bad((size_t)nt, 0);
+    parallel_ranges(total, nt, [&](int t, int64_t lo, int64_t hi) {
+        for (int64_t k = lo; k < hi; ++k) {
+            int64_t r, c; double x; uint32_t coff;
+            if (!triplet(k, r, c, x, coff)) { bad[(size_t)t] = 1; return; }
+            if (x == 0.0) continue;
+            __atomic_fetch_add(&fill[(size_t)(r % n)], 1u, __ATOMIC_RELAXED);
         }
-    }
-    std::sort(ents.begin(), ents.end(), [](const Ent& a, const Ent& b) {
-        return a.key != b.key ? a.key < b.key : a.col < b.col;
     });
-    out.rowptr.assign(n + 1, 0);
-    out.cnt.assign(n, 0);
-    out.col.clear(); out.val.clear();
-    out.col.reserve(ents.size()); out.val.reserve(ents.size());
-    std::vector<uint32_t> pc(n_par);
-    size_t k = 0;
-    for (int64_t i = 0; i < n; ++i) {
-        out.rowptr[i] = (uint32_t)out.col.size();
-        std::fill(pc.begin(), pc.end(), 0u);
-        while (k < ents.size() && (int64_t)(ents[k].key / n_par) == i) {
-            const int p = (int)(ents[k].key % n_par);
-            const uint32_t c = ents[k].col;
-            double x = ents[k].x;
-            ++k;
-            while (k < ents.size() && ents[k].key == ents[k - 1].key && ents[k].col == c) { x += ents[k].x; ++k; }
-            out.col.push_back(c); out.val.push_back(x);
-            if (++pc[p] > 255u) { err = "more than 255 nonzeros for one (row, parameter)"; return SSDE_ERR_UNSUPPORTED; }
+    for (int b : bad) if (b) { err = "design triplet index out of range"; return SSDE_ERR_BAD_ARG; }
+    pt.lap("pack: count");
+    // (2) row starts
+    out.rowptr.assign((size_t)n + 1, 0u);
+    uint64_t acc = 0;
+    for (int64_t i = 0; i < n; ++i) { out.rowptr[(size_t)i] = (uint32_t)acc; acc += fill[(size_t)i]; fill[(size_t)i] = 0u; }
+    if (acc > 0xfffffff0ull) { err = "more than 2^32 nonzeros in one shard"; return SSDE_ERR_UNSUPPORTED; }
+    out.rowptr[(size_t)n] = (uint32_t)acc;
+    // (3) scatter into the rows' buckets; the triplet index travels along so that the per-row sort
+    //     (and with it the order in which duplicates are summed) does not depend on the thread count
+    struct Ent { uint32_t col, k; double x; };
+    std::vector<Ent> ents((size_t)acc);
+    std::vector<uint8_t> par((size_t)acc);
+    if (total > 0xfffffff0ll) { err = "more than 2^32 triplets in one shard"; return SSDE_ERR_UNSUPPORTED; }
+    parallel_ranges(total, nt, [&](int, int64_t lo, int64_t hi) {
+        for (int64_t k = lo; k < hi; ++k) {
+            int64_t r, c; double x; uint32_t coff;
+            triplet(k, r, c, x, coff);
+            if (x == 0.0) continue;
+            const int64_t i = r % n;
+            const uint32_t slot = out.rowptr[(size_t)i] + __atomic_fetch_add(&fill[(size_t)i], 1u, __ATOMIC_RELAXED);
+            ents[slot] = Ent{coff + (uint32_t)c, (uint32_t)k, x};
+            par[slot] = (uint8_t)(r / n);
         }
-        uint32_t w = 0;
-        for (int p = 0; p < n_par; ++p) w |= pc[p] << (8 * p);
-        out.cnt[i] = w;
-        if (out.col.size() > 0xfffffff0ull) { err = "more than 2^32 nonzeros in one shard"; return SSDE_ERR_UNSUPPORTED; }
-    }
-    out.rowptr[n] = (uint32_t)out.col.size();
+    });
+    pt.lap("pack: alloc + scatter");
+    // (4) per row: sort by (parameter, column, triplet index), sum duplicates, compact in place
+    out.cnt.assign((size_t)n, 0u);
+    out.col.assign((size_t)acc, 0u);
+    out.val.assign((size_t)acc, 0.0);
+    std::vector<int64_t> nnz_t((size_t)nt, 0);
+    std::vector<int> over((size_t)nt, 0);
+    parallel_ranges(n, nt, [&](int t, int64_t lo, int64_t hi) {
+        std::vector<uint32_t> idx;
+        for (int64_t i = lo; i < hi; ++i) {
+            const uint32_t b = out.rowptr[(size_t)i], m = fill[(size_t)i];
+            idx.resize(m);
+            for (uint32_t u = 0; u < m; ++u) idx[u] = b + u;
+            std::sort(idx.begin(), idx.end(), [&](uint32_t a_, uint32_t b_) {
+                if (par[a_] != par[b_]) return par[a_] < par[b_];
+                if (ents[a_].col != ents[b_].col) return ents[a_].col < ents[b_].col;
+                return ents[a_].k < ents[b_].k;
+            });
+            uint32_t w = 0, o = b;
+            uint32_t pc[MAX_NP] = {0, 0, 0, 0};
+            for (uint32_t u = 0; u < m;) {
+                const uint32_t e0 = idx[u];
+                double x = ents[e0].x;
+                uint32_t v = u + 1;
+                while (v < m && par[idx[v]] == par[e0] && ents[idx[v]].col == ents[e0].col) { x += ents[idx[v]].x; ++v; }
+                out.col[o] = ents[e0].col; out.val[o] = x; ++o;
+                if (++pc[par[e0]] > 255u) over[(size_t)t] = 1;
+                u = v;
+            }
+            for (int p = 0; p < n_par; ++p) w |= (pc[p] & 255u) << (8 * p);
+            out.cnt[(size_t)i] = w;
+            nnz_t[(size_t)t] += o - b;
+        }
+    });
+    for (int b : over) if (b) { err = "more than 255 nonzeros for one (row, parameter)"; return SSDE_ERR_UNSUPPORTED; }
+    out.nnz = 0;
+    for (int64_t v : nnz_t) out.nnz += v;
+    pt.lap("pack: row sort + dedupe");
     return SSDE_OK;
 }
 
@@ -379,85 +472,129 @@ struct V2Host {
 
 int build_v2(const Packed& pk, int64_t n, int64_t n_pad, int n_par, V2Host& out, std::string& err) {
     const int64_t nwt = n_pad / WT;
-    out.desc.assign(nwt, WtDesc{0, 0, 0u, WT_UNIFORM});
+    out.desc.assign((size_t)nwt, WtDesc{0, 0, 0u, WT_UNIFORM});
     out.val.clear(); out.col.clear();
-    std::vector<uint32_t> prev_cols;         // column list of the previous uniform warp-tile
-    int64_t prev_col_off = -1;
-    std::vector<std::vector<uint32_t>> U(n_par);
-    for (int64_t q = 0; q < nwt; ++q) {
-        const int64_t r0 = q * WT, r1 = std::min<int64_t>(n, r0 + WT);
-        WtDesc& d = out.desc[q];
-        d.val_off = (int64_t)out.val.size();
-        d.col_off = 0;
-        if (r0 >= r1) continue;              // padding warp-tile: no slots
-        // union of columns and max count per parameter
-        uint32_t kmax_row[MAX_NP] = {0, 0, 0, 0};
-        for (int p = 0; p < n_par; ++p) U[p].clear();
-        for (int64_t r = r0; r < r1; ++r) {
-            uint32_t rp = pk.rowptr[r];
+    const int nt = host_threads(n * 8);
+    PhaseTimer pt;
+    // (1) per warp-tile: union of columns / max count per parameter -> slots, uniform or not
+    std::vector<std::vector<uint32_t>> wcols((size_t)nwt);      // uniform warp-tiles: their column list
+    std::vector<uint64_t> wS((size_t)nwt, 0);
+    parallel_ranges(nwt, nt, [&](int, int64_t qlo, int64_t qhi) {
+        std::vector<std::vector<uint32_t>> U((size_t)n_par);
+        for (int64_t q = qlo; q < qhi; ++q) {
+            const int64_t r0 = q * WT, r1 = std::min<int64_t>(n, r0 + WT);
+            WtDesc& d = out.desc[(size_t)q];
+            if (r0 >= r1) continue;              // padding warp-tile: no slots
+            uint32_t kmax_row[MAX_NP] = {0, 0, 0, 0};
+            for (int p = 0; p < n_par; ++p) U[(size_t)p].clear();
+            for (int64_t r = r0; r < r1; ++r) {
+                uint32_t rp = pk.rowptr[(size_t)r];
+                for (int p = 0; p < n_par; ++p) {
+                    const uint32_t k = (pk.cnt[(size_t)r] >> (8 * p)) & 255u;
+                    kmax_row[p] = std::max(kmax_row[p], k);
+                    for (uint32_t j = 0; j < k; ++j) U[(size_t)p].push_back(pk.col[rp + j]);
+                    rp += k;
+                }
+            }
+            size_t s_union = 0, s_max = 0;
+            bool fits = true;
             for (int p = 0; p < n_par; ++p) {
-                const uint32_t k = (pk.cnt[r] >> (8 * p)) & 255u;
-                kmax_row[p] = std::max(kmax_row[p], k);
-                for (uint32_t j = 0; j < k; ++j) U[p].push_back(pk.col[rp + j]);
-                rp += k;
+                auto& u = U[(size_t)p];
+                std::sort(u.begin(), u.end());
+                u.erase(std::unique(u.begin(), u.end()), u.end());
+                s_union += u.size(); s_max += kmax_row[p];
+                if (u.size() > 255) fits = false;
+            }
+            const bool uniform = fits && s_union <= std::max(s_max + 4, 2 * s_max);
+            uint32_t kw = 0;
+            size_t S = 0;
+            for (int p = 0; p < n_par; ++p) {
+                const uint32_t k = uniform ? (uint32_t)U[(size_t)p].size() : kmax_row[p];
+                kw |= k << (8 * p);
+                S += k;
+            }
+            d.kmax = kw;
+            d.flags = uniform ? WT_UNIFORM : 0u;
+            wS[(size_t)q] = S;
+            if (uniform) {
+                auto& c = wcols[(size_t)q];
+                c.reserve(S);
+                for (int p = 0; p < n_par; ++p) c.insert(c.end(), U[(size_t)p].begin(), U[(size_t)p].end());
             }
         }
-        size_t s_union = 0, s_max = 0;
-        bool fits = true;
-        for (int p = 0; p < n_par; ++p) {
-            std::sort(U[p].begin(), U[p].end());
-            U[p].erase(std::unique(U[p].begin(), U[p].end()), U[p].end());
-            s_union += U[p].size(); s_max += kmax_row[p];
-            if (U[p].size() > 255) fits = false;
-        }
-        const bool uniform = fits && s_union <= std::max(s_max + 4, 2 * s_max);
-        uint32_t kw = 0;
-        size_t S = 0;
-        for (int p = 0; p < n_par; ++p) {
-            const uint32_t k = uniform ? (uint32_t)U[p].size() : kmax_row[p];
-            kw |= k << (8 * p);
-            S += k;
-        }
-        d.kmax = kw;
-        d.flags = uniform ? WT_UNIFORM : 0u;
-        out.val.resize(out.val.size() + S * WT, 0.0);
-        double* v = out.val.data() + d.val_off;
-        uint32_t* c = nullptr;
-        if (uniform) {
-            std::vector<uint32_t> cols;
-            cols.reserve(S);
-            for (int p = 0; p < n_par; ++p) cols.insert(cols.end(), U[p].begin(), U[p].end());
-            if (prev_col_off >= 0 && cols == prev_cols) {
-                d.col_off = prev_col_off;
+    });
+    pt.lap("v2: warp-tile analysis");
+    // (2) offsets; identical consecutive column lists of uniform warp-tiles are stored once
+    uint64_t nval = 0, ncol = 0;
+    std::vector<int64_t> owner((size_t)nwt, -1); // uniform warp-tiles: the warp-tile whose column list this one uses
+    int64_t prev = -1;                           // previous uniform warp-tile that owns a column list
+    for (int64_t q = 0; q < nwt; ++q) {
+        WtDesc& d = out.desc[(size_t)q];
+        d.val_off = (int64_t)nval;
+        d.col_off = 0;
+        const uint64_t S = wS[(size_t)q];
+        if (S == 0 && !(q * WT < n)) continue;
+        nval += S * WT;
+        if (d.flags & WT_UNIFORM) {
+            if (prev >= 0 && wcols[(size_t)q] == wcols[(size_t)prev]) {
+                d.col_off = out.desc[(size_t)prev].col_off;
+                std::vector<uint32_t>().swap(wcols[(size_t)q]);
+                owner[(size_t)q] = prev;
             } else {
-                d.col_off = (int64_t)out.col.size();
-                out.col.insert(out.col.end(), cols.begin(), cols.end());
-                prev_cols = cols; prev_col_off = d.col_off;
+                d.col_off = (int64_t)ncol;
+                ncol += S;
+                prev = q;
+                owner[(size_t)q] = q;
             }
         } else {
-            d.col_off = (int64_t)out.col.size();
-            out.col.resize(out.col.size() + S * WT, 0u);
-            c = out.col.data() + d.col_off;
-        }
-        for (int64_t r = r0; r < r1; ++r) {
-            const int rr = (int)(r - r0), k = rr % LC, lane = rr / LC;
-            uint32_t rp = pk.rowptr[r];
-            size_t slot0 = 0;
-            for (int p = 0; p < n_par; ++p) {
-                const uint32_t cntp = (pk.cnt[r] >> (8 * p)) & 255u;
-                for (uint32_t j = 0; j < cntp; ++j) {
-                    size_t slot;
-                    if (uniform) slot = slot0 + (std::lower_bound(U[p].begin(), U[p].end(), pk.col[rp + j]) - U[p].begin());
-                    else slot = slot0 + j;
-                    v[((size_t)k * S + slot) * 32 + lane] = pk.val[rp + j];
-                    if (c) c[((size_t)k * S + slot) * 32 + lane] = pk.col[rp + j];
-                }
-                rp += cntp;
-                slot0 += (kw >> (8 * p)) & 255u;
-            }
+            d.col_off = (int64_t)ncol;
+            ncol += S * WT;
         }
     }
-    if (out.col.empty()) out.col.push_back(0u);
+    out.val.assign((size_t)nval, 0.0);
+    out.col.assign((size_t)std::max<uint64_t>(ncol, 1), 0u);
+    pt.lap("v2: offsets + alloc");
+    // (3) fill values (and columns) of every warp-tile
+    parallel_ranges(nwt, nt, [&](int, int64_t qlo, int64_t qhi) {
+        for (int64_t q = qlo; q < qhi; ++q) {
+            const int64_t r0 = q * WT, r1 = std::min<int64_t>(n, r0 + WT);
+            if (r0 >= r1) continue;
+            const WtDesc& d = out.desc[(size_t)q];
+            const bool uniform = (d.flags & WT_UNIFORM) != 0;
+            const size_t S = (size_t)wS[(size_t)q];
+            double* v = out.val.data() + d.val_off;
+            uint32_t* c = nullptr;
+            const uint32_t* ulist = nullptr;     // this warp-tile's column list (parameter-major, ascending per parameter)
+            if (uniform) {
+                // a shared list is written to out.col by its owner -- possibly another thread -- so
+                // slots are looked up in the owner's private copy, not in out.col
+                const int64_t o = owner[(size_t)q];
+                if (o == q) std::copy(wcols[(size_t)q].begin(), wcols[(size_t)q].end(), out.col.begin() + d.col_off);
+                ulist = wcols[(size_t)o].data();
+            } else {
+                c = out.col.data() + d.col_off;
+            }
+            for (int64_t r = r0; r < r1; ++r) {
+                const int rr = (int)(r - r0), k = rr % LC, lane = rr / LC;
+                uint32_t rp = pk.rowptr[(size_t)r];
+                size_t slot0 = 0;
+                for (int p = 0; p < n_par; ++p) {
+                    const uint32_t cntp = (pk.cnt[(size_t)r] >> (8 * p)) & 255u;
+                    const size_t kp = (d.kmax >> (8 * p)) & 255u;
+                    for (uint32_t j = 0; j < cntp; ++j) {
+                        size_t slot;
+                        if (uniform) slot = slot0 + (size_t)(std::lower_bound(ulist + slot0, ulist + slot0 + kp, pk.col[rp + j]) - (ulist + slot0));
+                        else slot = slot0 + j;
+                        v[((size_t)k * S + slot) * 32 + lane] = pk.val[rp + j];
+                        if (c) c[((size_t)k * S + slot) * 32 + lane] = pk.col[rp + j];
+                    }
+                    rp += cntp;
+                    slot0 += kp;
+                }
+            }
+        }
+    });
+    pt.lap("v2: fill");
     (void)err;
     return SSDE_OK;
 }
@@ -543,6 +680,25 @@ int setup_penalty(ssde_handle* h, const ssde_triplet& S, int n_smooth, const int
             h->pen_const = cst;
         }
     }
+    // hot columns of the transposed design product: the fixed effects and every small smooth block are
+    // touched by every warp-tile, large blocks (one random intercept per track) by a few
+    h->hot.n = 0;
+    {
+        const int p_theta = h->p_fe + h->p_re;
+        int used = 0;
+        auto add = [&](int lo, int hi) {
+            if (hi <= lo || h->hot.n >= SDE_MAX_HOT_RANGES || used + (hi - lo) > SDE_HOT) return;
+            h->hot.lo[h->hot.n] = lo; h->hot.hi[h->hot.n] = hi; h->hot.off[h->hot.n] = used;
+            used += hi - lo; ++h->hot.n;
+        };
+        if (p_theta <= SDE_HOT) add(0, p_theta);
+        else {
+            add(0, std::min(h->p_fe, 128));
+            if (h->has_smooth)
+                for (int i = 0; i < n_smooth; ++i)
+                    if (ncol_re[i] <= 64) add(h->p_fe + off[i], h->p_fe + off[i + 1]);
+        }
+    }
     int rc;
     if ((rc = dev_upload(h->S_rowptr, rp, err))) return rc;
     if ((rc = dev_upload(h->S_col, cols, err))) return rc;
@@ -598,7 +754,9 @@ int ctcrw_grids(ssde_handle* h) {
 template <int MODEL, int ND>
 int sde_grid(ssde_handle* h) {
     constexpr int NP = (MODEL == MODEL_BM) ? ND + 1 : ND + 2;
-    return max_grid(sde_fused_kernel<MODEL, ND>, SDE_NT, sizeof(SdeSmem<NP>), h->num_sms, h->err, h->grid_lp);
+    int rc = max_grid(sde_fused_kernel<MODEL, ND>, SDE_NT, sizeof(SdeSmem<NP>), h->num_sms, h->err, h->grid_lp);
+    if (rc) return rc;
+    return max_grid(sde_stream_kernel<MODEL, ND>, SDE_NT, sizeof(SdeStreamSmem), h->num_sms, h->err, h->grid_stream);
 }
 
 // allocate the per-evaluation work buffers once the data are on the device
@@ -669,7 +827,17 @@ int finish_setup(ssde_handle* h) {
         }
         if (rc) return rc;
         h->grid_lp = (int)std::max<int64_t>(1, std::min<int64_t>(h->grid_lp, h->ntiles_lp));
-        if ((rc = dev_alloc<double>(h->block_llk, h->grid_lp, err))) return rc;
+        h->grid_stream = (int)std::max<int64_t>(1, std::min<int64_t>(h->grid_stream, h->ntiles_lp));
+        if ((rc = dev_alloc<double>(h->block_llk, std::max(h->grid_lp, h->grid_stream), err))) return rc;
+        // streaming kernel: only if every warp-tile of the design is uniform with <= SDE_SMAX slots
+        DevBuf shape;
+        if ((rc = dev_alloc<int>(shape, 3, err))) return rc;
+        CUDA_TRY(cudaMemset(shape.p, 0, 3 * sizeof(int)));
+        design_shape_kernel<<<std::max(1, h->num_sms), 256>>>(h->desc.as<WtDesc>(), h->n_pad / WT, shape.as<int>());
+        CUDA_TRY(cudaGetLastError());
+        int sh[3] = {0, 0, 0};
+        CUDA_TRY(cudaMemcpy(sh, shape.p, 3 * sizeof(int), cudaMemcpyDeviceToHost));
+        h->sde_stream = h->n_dec == 0 && sh[0] <= SDE_SMAX && sh[1] == 0 && sh[2] <= SDE_KPM;
     }
     return SSDE_OK;
 }
@@ -819,6 +987,14 @@ int launch_sde(ssde_handle* h, const double* d_par, const double* d_dir, int ord
         CUDA_TRY(cudaGetLastError());
         return SSDE_OK;
     }
+    if constexpr (!TAN) {
+        if (h->sde_stream) {
+            mark(h, st, "sde_stream");
+            sde_stream_kernel<MODEL, ND><<<h->grid_stream, SDE_NT, sizeof(SdeStreamSmem), st>>>(a, h->hot);
+            CUDA_TRY(cudaGetLastError());
+            return SSDE_OK;
+        }
+    }
     mark(h, st, TAN ? "sde_fused_tangent" : "sde_fused");
     sde_fused_kernel<MODEL, ND, R><<<TAN ? h->grid_lp2 : h->grid_lp, SDE_NT, sizeof(SdeSmem<NP, R>), st>>>(a);
     CUDA_TRY(cudaGetLastError());
@@ -852,7 +1028,7 @@ int eval_epilogue(ssde_handle* h, const double* d_par, const double* d_dir, int 
         f.tile_gh = (order >= 1) ? h->part.as<double>() + RED_BLOCKS : nullptr; f.n_gh = RED_BLOCKS;
         f.tile_gh_dot = h->part.as<double>() + 2 * RED_BLOCKS;
     } else {
-        f.part_llk = h->block_llk.as<double>(); f.n_part = d_dir ? h->grid_lp2 : h->grid_lp;
+        f.part_llk = h->block_llk.as<double>(); f.n_part = d_dir ? h->grid_lp2 : ((h->sde_stream && h->n_dec == 0) ? h->grid_stream : h->grid_lp);
         f.tile_gh = nullptr; f.tile_gh_dot = nullptr; f.n_gh = 0;
     }
     f.par = d_par; f.par_dot = d_dir;
@@ -1250,7 +1426,7 @@ static int create_impl(const ssde_desc* d, ssde_handle** out) {
     }
     Packed pk;
     if ((rc = pack_design(*d, n_par, pk, h->err))) return fail(rc);
-    h->nnz = (int64_t)pk.col.size();
+    h->nnz = pk.nnz;
     if (is_kalman(d->model)) {
         std::vector<int32_t> mc;
         for (int64_t r = 0; r < n; ++r) {
