@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--cpu-track-steps", type=int, default=8192)
     ap.add_argument("--cpu-b1-tracks", type=int, default=8, help="tracks of the CPU sample timed on ONE thread (B1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip the OU configurations reported under `configs`")
     ap.add_argument("--workload", default="both", choices=["both", "tracks", "single"],
                     help="tracks: BASELINE configs[2] (the headline line); single: configs[3], ONE track of "
                          "tracks*track_steps rows, sharded along time over the ranks; both (default): the headline "
@@ -313,23 +314,115 @@ def measure(kind, args, ctx):
     assert abs(v - first[0]) <= 1e-12 * abs(first[0]), "host-buffer call and device-resident call disagree"
 
     # ---- the same data set at every N: nllk against the stored 1-GPU value ----
-    key = f"{kind}:{args.tracks}x{args.track_steps}"
-    stored = json.load(open(N1_FILE)) if os.path.exists(N1_FILE) else {}
-    parity = None
-    if key in stored:
-        parity = abs(float(first[0]) - stored[key]["nllk"]) / abs(stored[key]["nllk"])
-        gs = np.asarray(stored[key]["grad"])
-        gerr = float(np.max(np.abs(first[1:npar + 1] - gs) / np.maximum(np.abs(gs), 1e-3 * np.abs(gs).max())))
-        assert parity <= 1e-10 and gerr <= 1e-7, f"{world}-GPU result differs from the stored 1-GPU result: {parity:.3e} / {gerr:.3e}"
-        parity = {"nllk_rel": parity, "grad_rel": gerr}
-    if args.write_n1 and world == 1 and rank == 0:
-        stored[key] = {"nllk": float(first[0]), "grad": [float(x) for x in first[1:npar + 1]],
-                       "par": [float(x) for x in par]}
-        json.dump(stored, open(N1_FILE, "w"), indent=1)
+    parity = n1_parity(f"{kind}:{args.tracks}x{args.track_steps}", args, world, rank, first[0], first[1:npar + 1])
 
     res = dict(kind=kind, eng=eng, info=info, n_local=n_local, n_total=n_total, npar=npar, ms_step=ms_step, value=value,
                clk=clk, kernels=kernels, launches_per_step=launches_per_step, e2e_value=e2e_value, h2d=h2d, d2h=d2h,
                nllk=float(first[0]), parity=parity, fallbacks=fallbacks, launch_info=eng.launch_info())
+    return res
+
+
+def n1_parity(key, args, world, rank, nllk, grad):
+    """nllk / gradient of this run against the stored 1-GPU result of the same data set
+    (profiles/bench_nllk_n1.json; long gradients are stored as their first 64 entries + l2 norm)."""
+    import numpy as np
+    stored = json.load(open(N1_FILE)) if os.path.exists(N1_FILE) else {}
+    grad = np.asarray(grad, dtype=float)
+    out = None
+    if key in stored:
+        st = stored[key]
+        rel = abs(float(nllk) - st["nllk"]) / abs(st["nllk"])
+        gs = np.asarray(st["grad"])
+        head = grad[:gs.size]
+        gerr = float(np.max(np.abs(head - gs) / np.maximum(np.abs(gs), 1e-3 * np.abs(gs).max())))
+        nerr = abs(float(np.linalg.norm(grad)) - st.get("grad_l2", float(np.linalg.norm(gs)))) / st.get("grad_l2", float(np.linalg.norm(gs)))
+        assert rel <= 1e-10 and gerr <= 1e-7 and nerr <= 1e-7, \
+            f"{key}: {world}-GPU result differs from the stored 1-GPU result: {rel:.3e} / {gerr:.3e} / {nerr:.3e}"
+        out = {"nllk_rel": rel, "grad_rel": gerr, "grad_l2_rel": nerr}
+    if args.write_n1 and world == 1 and rank == 0:
+        stored[key] = {"nllk": float(nllk), "grad": [float(x) for x in grad[:64]], "grad_l2": float(np.linalg.norm(grad))}
+        os.makedirs(os.path.dirname(N1_FILE), exist_ok=True)
+        json.dump(stored, open(N1_FILE, "w"), indent=1)
+    return out
+
+
+def measure_ou(name, n_tracks, n_steps, args, ctx):
+    """BM / OU fused path: OU with a random intercept per track (BASELINE configs[1] and the OU half of
+    configs[4]), tracks sharded over the ranks, one all-reduce of [nllk, gradient] per evaluation."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from smoothsde_b200 import devgen, _lib, sharded
+    rank, world, local, dev, dist_reduce = ctx["rank"], ctx["world"], ctx["local"], ctx["dev"], ctx["dist_reduce"]
+    if n_tracks % world != 0:
+        return {"skipped": f"{n_tracks} tracks do not divide over {world} ranks"}
+    eng, par, info = devgen.make_ou_device(n_tracks // world, n_steps, seed=20260102, device=local, rank=rank, world=world,
+                                           shard_flags=(_lib.SHARD_NO_PENALTY if rank > 0 else 0))
+    n_total = info["n"] * world
+    npar = eng.n_par
+    tse = sharded.TrackShardedEngine.from_engine(eng, sharded.DistComm() if world > 1 else sharded.SoloComm(), local)
+    torch.cuda.set_stream(tse.stream)
+    stream = tse.stream.cuda_stream
+    par_dev = torch.as_tensor(par, device=dev)
+    out_dev = torch.zeros(npar + 2, dtype=torch.float64, device=dev)
+
+    def step_device():
+        eng.eval_device(par_dev.data_ptr(), out_dev.data_ptr(), 1, stream)
+        if world > 1:
+            dist.all_reduce(out_dev[:npar + 1])
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    barrier()
+    eng.check()
+    first = out_dev.cpu().numpy().copy()
+    assert np.isfinite(first[:npar + 1]).all()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        step_device()
+    ev1.record()
+    barrier()
+    ms_total = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    dist_reduce(ms_total, "max")
+    ms_step = float(ms_total) / args.steps
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        v, g = tse.eval(par, order=1)
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    dist_reduce(e2e_s, "max")
+    eng.set_profile(True)
+    eng.eval_device(par_dev.data_ptr(), out_dev.data_ptr(), 1, stream)
+    torch.cuda.synchronize()
+    kernels = dict(eng.last_kernel_times())
+    eng.set_profile(False)
+    launches = eng.last_eval_launches
+    parity = n1_parity(f"{name}:{n_tracks}x{n_steps}", args, world, rank, first[0], first[1:npar + 1])
+    stored_b = 23 * 8 + 8 + 8 + 1
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.exists(peaks_path) else 6650.0
+    kmain = max(kernels, key=kernels.get)
+    res = {"workload": f"OU d=1, {n_tracks} tracks x {n_steps} steps (n={n_total}), mu,tau ~ s(time,k=10) + s(ID,bs='re'), kappa ~ 1; "
+                       f"p_re = {info['p_re']}", "ms_per_step": ms_step, "value": n_total / (ms_step * 1e-3), "unit": UNIT,
+           "e2e": {"value": n_total * args.steps / float(e2e_s), "unit": UNIT, "h2d_bytes_per_step": 8 * npar,
+                   "d2h_bytes_per_step": 8 * (npar + 1), "call": "TrackShardedEngine.eval"},
+           "kernels_ms": kernels, "gpu_launches": launches * args.steps, "nllk": float(first[0]), "parity_vs_n1": parity,
+           "roofline": {"kernel": kmain, "launch_ms": kernels[kmain], "stored_bytes_per_obs": stored_b,
+                        "alg_bytes_per_obs": devgen.alg_bytes_per_obs(1, 3, 23),
+                        "dram_frac": stored_b * info["n"] / (kernels[kmain] * 1e-3) / 1e9 / peak,
+                        "frac": devgen.alg_bytes_per_obs(1, 3, 23) * info["n"] / (kernels[kmain] * 1e-3) / 1e9 / peak,
+                        "note": "dram_frac: bytes the layout stores (design read ONCE) / launch time / measured peak; frac: SURVEY 8(d) "
+                                "CSR accounting (design read twice), > 1 because the kernel needs one pass"}}
+    eng.close()
+    torch.cuda.empty_cache()
     return res
 
 
@@ -458,6 +551,14 @@ def main():
         }
         line["gpu_launches"] += r2["launches_per_step"] * args.steps
         release(r2)
+    if args.workload == "both" and not args.no_extra_configs:
+        # the other BASELINE configs on the BM / OU path (driver-visible at every N)
+        line["configs"] = {
+            "configs[4] OU half": measure_ou("ou", 4096, 25000, args, ctx),
+            "configs[1]": measure_ou("ou", 64, 100000, args, ctx),
+        }
+        for c in line["configs"].values():
+            line["gpu_launches"] += c.get("gpu_launches", 0)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_time_evals(args, 3, 1)
     if rank == 0:

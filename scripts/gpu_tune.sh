@@ -2,7 +2,7 @@
 mkdir -p gpurun_out
 T=$1; shift
 for s in "$@"; do
-  SSDE_LIB_SUFFIX=_$s timeout 300 python bench.py --no-cpu-baseline --steps 20 > gpurun_out/${T}_$s.log 2>&1
+  SSDE_LIB_SUFFIX=_$s timeout 300 python bench.py --workload tracks --no-cpu-baseline --steps 20 > gpurun_out/${T}_$s.log 2>&1
   python - "$s" gpurun_out/${T}_$s.log <<'PY'
 import json,sys
 ls=[x for x in open(sys.argv[2]) if x.startswith('{')]

@@ -39,6 +39,10 @@
 #ifndef SSDE_FWD_RESTAGE
 #define SSDE_FWD_RESTAGE 1
 #endif
+// 1: software-pipelined row loop of the forward kernel (row k+1's transform next to row k's append)
+#ifndef SSDE_FWD_PIPE
+#define SSDE_FWD_PIPE 0
+#endif
 
 namespace ssde {
 
@@ -197,6 +201,66 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(KalmanArgs<typename
         Elem E = M::fwd_identity();
         // dt and the observations of a row are fetched one row ahead of their use
         const RowPlanes<M> pl = open_planes<M>(a, base, false, SSDE_PLANE_PREFETCH != 0);
+#if SSDE_FWD_PIPE
+        // Software pipeline: while row k is appended to the element (a chain of dependent fp64
+        // operations through E), row k+1's linear predictor, natural-scale transform and step
+        // matrices -- independent of E -- are formed in the same stretch of straight-line code, so
+        // the two dependency chains interleave (12 warps per SM cannot hide them otherwise).
+        struct RowWork { typename M::Step sp; R eta[NP]; double dtv, y[ND]; uint8_t f; };
+        auto stage_a = [&](int k, RowWork& r) {
+            const int64_t pos = base + k * 32;
+            r.f = (uint8_t)(fl >> (8 * k));
+            const bool live = r.f != 0xff;
+            const bool step = live && !(r.f & ROW_START);
+            r.dtv = live ? pl.dt[k * 32] : 1.0;
+#pragma unroll
+            for (int d = 0; d < ND; ++d) r.y[d] = live ? pl.obs[d][k * 32] : 0.0;
+#pragma unroll
+            for (int p = 0; p < NP; ++p) r.eta[p] = 0.0;
+            if (w.staged) {
+                stage_wait(st);
+                row_eta_staged<NP>(w, st, r.eta);
+                __syncwarp();
+                if (lane == 0 && k + 1 < LC) {
+                    stage_issue(w, st, k + 1);
+#if SSDE_FWD_PREFETCH == 2
+                    if (k + 3 < LC) prefetch_l2(w.blk + (size_t)(k + 3) * w.S * 32, (unsigned)(w.S * 32 * 8));
+#endif
+                }
+            } else if (step) {
+                row_eta<NP>(w, k, a.theta, r.eta);
+            }
+            // unconditional arithmetic (a dead row has eta = 0, dt = 1: finite; nothing of it is kept)
+            const typename M::RowPar rp = M::transform(r.eta, r.dtv);
+            r.sp = M::make_step(rp, r.dtv);
+            if (step) {
+                M::store_rowpar(rp, [&](int c) -> R& { return const_cast<R&>(pl.wg[c][k * 32]); });
+                M::store_step(r.sp, [&](int c) -> R& { return sm.W[k][c][tid]; });
+            }
+            (void)pos;
+        };
+        // append row k (unconditional arithmetic, the result is kept only for a filter step)
+        auto stage_b = [&](int k, const RowWork& r) {
+            const bool live = r.f != 0xff;
+            const bool step = live && !(r.f & ROW_START);
+            Elem En = E;
+            M::fwd_append(En, r.sp, r.y, r.eta, (r.f & ROW_OBS) != 0, M::row_h(h, a.Hrow, a.X.n_pad, base + k * 32));
+            if (step) E = En;
+            else if (live) M::fwd_append_start(E, track_start_state<M>(a, r.dtv));
+        };
+        double dt_nx = 1.0, y_nx[ND];                  // used again by the re-run (4)
+#pragma unroll
+        for (int d = 0; d < ND; ++d) y_nx[d] = 0.0;
+        RowWork cur, nxt;
+        stage_a(0, cur);
+#pragma unroll 1
+        for (int k = 0; k + 1 < LC; ++k) {
+            stage_a(k + 1, nxt);
+            stage_b(k, cur);
+            cur = nxt;
+        }
+        stage_b(LC - 1, cur);
+#else
         double dt_nx = ((uint8_t)fl != 0xff) ? pl.dt[0] : 1.0, y_nx[ND];
 #pragma unroll
         for (int d = 0; d < ND; ++d) y_nx[d] = ((uint8_t)fl != 0xff) ? pl.obs[d][0] : 0.0;
@@ -240,6 +304,7 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(KalmanArgs<typename
                 M::fwd_append_start(E, track_start_state<M>(a, dtv));
             }
         }
+#endif
 #if SSDE_FWD_RESTAGE
         // The staging buffer is idle until the next tile: bring the warp-tile's dt / obs planes
         // (2 KB each, contiguous) into it with bulk copies that land during the scan and the
