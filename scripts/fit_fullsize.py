@@ -24,19 +24,37 @@ def split(par, p_fe, n_s):
             "coeff_re": par[1 + p_fe + n_s:]}
 
 
-def run_fit(obj, gtol, maxiter=200):
-    calls = {"fn": 0, "gr": 0}
+class _Budget(Exception):
+    pass
 
-    def fn(x):
-        calls["fn"] += 1
-        return obj.fn(x)
 
-    def gr(x):
-        calls["gr"] += 1
-        return obj.gr(x)
-
+def run_fit(obj, gtol, maxiter=200, budget_s=None, tag=""):
+    """BFGS as optim(method = "BFGS") in R/sde.R:694-697; progress goes to stderr; stops with the best
+    point so far when the wall-clock budget is spent (reported as such)."""
+    calls = {"fn": 0, "gr": 0, "it": 0}
     t0 = time.perf_counter()
-    r = so.minimize(fn, obj.par.copy(), jac=gr, method="BFGS", options={"gtol": gtol, "maxiter": maxiter})
+    trace = []
+
+    def fg(x):
+        calls["fn"] += 1
+        calls["gr"] += 1
+        return obj.fn_gr(x)
+
+    def cb(xk):
+        calls["it"] += 1
+        el = time.perf_counter() - t0
+        trace.append((el, [float(v) for v in xk]))
+        print(f"[fit {tag}] it {calls['it']:3d}  {el:8.1f} s  fn {calls['fn']} gr {calls['gr']}  x = {np.array2string(np.asarray(xk), precision=5)}",
+              file=sys.stderr, flush=True)
+        if budget_s is not None and el > budget_s:
+            raise _Budget()
+
+    try:
+        r = so.minimize(fg, obj.par.copy(), jac=True, method="BFGS", callback=cb, options={"gtol": gtol, "maxiter": maxiter})
+    except _Budget:
+        x = np.asarray(trace[-1][1])
+        r = so.OptimizeResult(x=x, fun=obj.fn(x), jac=obj.gr(x), nit=calls["it"], success=False,
+                              message=f"stopped by the {budget_s:.0f} s wall-clock budget of this script")
     return r, time.perf_counter() - t0, calls
 
 
@@ -46,6 +64,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100000)
     ap.add_argument("--mid-tracks", type=int, default=32)
     ap.add_argument("--mid-steps", type=int, default=2000)
+    ap.add_argument("--budget", type=float, default=600.0, help="wall-clock budget of the full-size fit (s)")
     ap.add_argument("--skip-full", action="store_true")
     ap.add_argument("--skip-mid", action="store_true")
     args = ap.parse_args()
@@ -63,7 +82,7 @@ def main():
         t0 = time.perf_counter()
         f0 = obj.fn(obj.par)
         t_first = time.perf_counter() - t0
-        r, secs, calls = run_fit(obj, gtol=1e-3 * info["n"] / 1e6)     # gradient tolerance scaled with n (nllk ~ n)
+        r, secs, calls = run_fit(obj, gtol=1e-3 * info["n"] / 1e6, budget_s=args.budget, tag="full")     # gradient tolerance scaled with n (nllk ~ n)
         lap = obj._laplace
         out["full"] = {"config": f"CTCRW d=2, {args.tracks} x {args.steps} rows (n={info['n']}), tau,nu ~ s(time,k=10), mu fixed",
                        "theta_names": [str(x) for x in obj.names], "theta_hat": [float(x) for x in r.x],
@@ -85,7 +104,7 @@ def main():
         for name, make in (("gpu", lambda: ADFun(dat, pars, map=fixmu, random="coeff_re")),
                            ("oracle", lambda: oracle_adfun(dat, pars, map=fixmu, random="coeff_re"))):
             obj = make()
-            r, secs, calls = run_fit(obj, gtol=1e-6)
+            r, secs, calls = run_fit(obj, gtol=1e-6, tag=name)
             b_hat = obj.env.last_par_best[obj._rand].copy()
             res[name] = dict(x=r.x, fun=r.fun, secs=secs, nit=int(r.nit), b=b_hat, calls=calls)
             obj.close()

@@ -145,6 +145,18 @@ class ADFun:
         self._remember(v, p)
         return self.reduce_grad(g, self._active)
 
+    def fn_gr(self, x=None):
+        """(obj$fn(x), obj$gr(x)) from ONE evaluation -- what a quasi-Newton driver should call: its line
+        search needs both at every trial point, and for the Laplace object two separate calls would run
+        the inner Newton problem twice."""
+        x = self.par if x is None else x
+        if self._laplace is not None:
+            return self._laplace.fn_gr(np.asarray(x, dtype=float))
+        p = self.full_from(x)
+        v, g = self.joint(p, order=1)
+        self._remember(v, p)
+        return v, self.reduce_grad(g, self._active)
+
     def _reduce_hess(self, H_full, idx):
         """Hessian w.r.t. the free groups `idx` from the full-vector Hessian (tied entries add up)."""
         ok = np.flatnonzero(self._group >= 0)

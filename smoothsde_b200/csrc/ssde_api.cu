@@ -125,6 +125,27 @@ int dev_alloc(DevBuf& b, size_t count, std::string& err) {
     CUDA_TRY(cudaMalloc(&b.p, std::max<size_t>(count, 1) * sizeof(T)));
     return SSDE_OK;
 }
+// Uninitialised host storage for the big packing buffers: std::vector would zero-fill them on one
+// thread (page faults included) before the worker threads overwrite every entry that is ever read.
+template <class T>
+struct RawVec {
+    std::unique_ptr<T[]> p;
+    size_t n = 0;
+    void alloc(size_t count) { p.reset(new T[count > 0 ? count : 1]); n = count; }
+    T* data() { return p.get(); }
+    const T* data() const { return p.get(); }
+    size_t size() const { return n; }
+    bool empty() const { return n == 0; }
+    T& operator[](size_t i) { return p[i]; }
+    const T& operator[](size_t i) const { return p[i]; }
+};
+template <class T>
+int dev_upload(DevBuf& b, const RawVec<T>& v, std::string& err) {
+    int rc = dev_alloc<T>(b, v.size(), err);
+    if (rc) return rc;
+    if (!v.empty()) CUDA_TRY(cudaMemcpy(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return SSDE_OK;
+}
 template <class T>
 int dev_upload(DevBuf& b, const std::vector<T>& v, std::string& err) {
     int rc = dev_alloc<T>(b, v.size(), err);
@@ -368,8 +389,9 @@ void parallel_ranges(int64_t n, int nthreads, Fn&& fn) {
 // of parameter p.  Rows are NOT contiguous in col / val (the space of summed duplicates and of
 // explicit zeros stays unused), `nnz` is the number of packed nonzeros.
 struct Packed {
-    std::vector<uint32_t> rowptr, cnt, col;
-    std::vector<double> val;
+    std::vector<uint32_t> rowptr, cnt;
+    RawVec<uint32_t> col;
+    RawVec<double> val;
     int64_t nnz = 0;
 };
 
@@ -408,8 +430,10 @@ int pack_design(const ssde_desc& d, int n_par, Packed& out, std::string& err) {
     // (3) scatter into the rows' buckets; the triplet index travels along so that the per-row sort
     //     (and with it the order in which duplicates are summed) does not depend on the thread count
     struct Ent { uint32_t col, k; double x; };
-    std::vector<Ent> ents((size_t)acc);
-    std::vector<uint8_t> par((size_t)acc);
+    RawVec<Ent> ents;
+    RawVec<uint8_t> par;
+    ents.alloc((size_t)acc);
+    par.alloc((size_t)acc);
     if (total > 0xfffffff0ll) { err = "more than 2^32 triplets in one shard"; return SSDE_ERR_UNSUPPORTED; }
     parallel_ranges(total, nt, [&](int, int64_t lo, int64_t hi) {
         for (int64_t k = lo; k < hi; ++k) {
@@ -425,8 +449,8 @@ int pack_design(const ssde_desc& d, int n_par, Packed& out, std::string& err) {
     pt.lap("pack: alloc + scatter");
     // (4) per row: sort by (parameter, column, triplet index), sum duplicates, compact in place
     out.cnt.assign((size_t)n, 0u);
-    out.col.assign((size_t)acc, 0u);
-    out.val.assign((size_t)acc, 0.0);
+    out.col.alloc((size_t)acc);
+    out.val.alloc((size_t)acc);
     std::vector<int64_t> nnz_t((size_t)nt, 0);
     std::vector<int> over((size_t)nt, 0);
     parallel_ranges(n, nt, [&](int t, int64_t lo, int64_t hi) {
@@ -466,14 +490,13 @@ int pack_design(const ssde_desc& d, int n_par, Packed& out, std::string& err) {
 // Warp-tile transposed layout (design.cuh) from the row-major packed form.
 struct V2Host {
     std::vector<WtDesc> desc;
-    std::vector<double> val;
-    std::vector<uint32_t> col;
+    RawVec<double> val;
+    RawVec<uint32_t> col;
 };
 
 int build_v2(const Packed& pk, int64_t n, int64_t n_pad, int n_par, V2Host& out, std::string& err) {
     const int64_t nwt = n_pad / WT;
     out.desc.assign((size_t)nwt, WtDesc{0, 0, 0u, WT_UNIFORM});
-    out.val.clear(); out.col.clear();
     const int nt = host_threads(n * 8);
     PhaseTimer pt;
     // (1) per warp-tile: union of columns / max count per parameter -> slots, uniform or not
@@ -551,8 +574,9 @@ int build_v2(const Packed& pk, int64_t n, int64_t n_pad, int n_par, V2Host& out,
             ncol += S * WT;
         }
     }
-    out.val.assign((size_t)nval, 0.0);
-    out.col.assign((size_t)std::max<uint64_t>(ncol, 1), 0u);
+    out.val.alloc((size_t)nval);
+    out.col.alloc((size_t)std::max<uint64_t>(ncol, 1));
+    out.col[0] = 0u;
     pt.lap("v2: offsets + alloc");
     // (3) fill values (and columns) of every warp-tile
     parallel_ranges(nwt, nt, [&](int, int64_t qlo, int64_t qhi) {
@@ -563,16 +587,18 @@ int build_v2(const Packed& pk, int64_t n, int64_t n_pad, int n_par, V2Host& out,
             const bool uniform = (d.flags & WT_UNIFORM) != 0;
             const size_t S = (size_t)wS[(size_t)q];
             double* v = out.val.data() + d.val_off;
+            std::memset(v, 0, sizeof(double) * S * WT);              // explicit zeros for rows that lack a column of the union
             uint32_t* c = nullptr;
             const uint32_t* ulist = nullptr;     // this warp-tile's column list (parameter-major, ascending per parameter)
             if (uniform) {
                 // a shared list is written to out.col by its owner -- possibly another thread -- so
                 // slots are looked up in the owner's private copy, not in out.col
                 const int64_t o = owner[(size_t)q];
-                if (o == q) std::copy(wcols[(size_t)q].begin(), wcols[(size_t)q].end(), out.col.begin() + d.col_off);
+                if (o == q) std::copy(wcols[(size_t)q].begin(), wcols[(size_t)q].end(), out.col.data() + d.col_off);
                 ulist = wcols[(size_t)o].data();
             } else {
                 c = out.col.data() + d.col_off;
+                std::memset(c, 0, sizeof(uint32_t) * S * WT);
             }
             for (int64_t r = r0; r < r1; ++r) {
                 const int rr = (int)(r - r0), k = rr % LC, lane = rr / LC;

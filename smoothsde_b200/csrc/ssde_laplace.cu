@@ -232,7 +232,11 @@ int ssde_laplace_eval(ssde_laplace* w, double* par, int order, double* value, do
         for (int i = 0; i < nb; ++i) { w->gb[i] = w->grad[o + i]; gmax = std::max(gmax, std::fabs(w->gb[i])); }
         li.grad_max = gmax;
         if (!(gmax == gmax)) { w->err = "non-finite gradient in the inner problem"; return SSDE_ERR_NUMERIC; }
-        if (gmax <= w->opts.grad_tol) { converged = true; break; }
+        // absolute tolerance, or -- for objectives of 1e6 and more, whose gradient carries rounding noise
+        // far above 1e-8 -- relative to the value: max|g_b| <= 1e-12 |g| puts b_hat within ~1e-12 of the
+        // mode (H_bb scales with |g| too) and is reachable in fp64
+        const double tol_eff = std::max(w->opts.grad_tol, 1e-12 * std::fabs(v));
+        if (gmax <= tol_eff) { converged = true; break; }
         if (it == w->opts.max_newton) break;
         // Levenberg ridge until H_bb + ridge I is positive definite
         double ridge = 0.0;
@@ -249,13 +253,15 @@ int ssde_laplace_eval(ssde_laplace* w, double* par, int order, double* value, do
         std::vector<double> trial = w->par;
         double t = 1.0, vn = 0.0;
         bool ok = false;
-        for (int ls = 0; ls < 40; ++ls, t *= 0.5) {
+        // near the mode a failing search means "working precision reached": do not halve 40 times there
+        const int max_ls = (gmax <= 1e3 * tol_eff) ? 6 : 40;
+        for (int ls = 0; ls < max_ls; ++ls, t *= 0.5) {
             for (int i = 0; i < nb; ++i) trial[o + i] = w->par[o + i] - t * w->step[i];
             LP_TRY(joint_value(w, trial, vn));
             ++li.n_value;
             if (vn == vn && vn <= v - 1e-4 * t * slope + 1e-14 * std::fabs(v)) { ok = true; break; }
         }
-        if (!ok) break;                          // no descent possible at working precision
+        if (!ok) { converged = gmax <= 1e3 * tol_eff; break; }      // no descent possible at working precision
         w->par = trial;
         LP_TRY(joint_hess_cols(w, v));
         ++li.n_hess;

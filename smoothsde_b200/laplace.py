@@ -105,7 +105,8 @@ class LoopLaplace:
         for it in range(self.max_newton + 1):
             gb = g[sl]
             info["grad_max"] = float(np.max(np.abs(gb)))
-            if info["grad_max"] <= self.grad_tol:
+            tol_eff = max(self.grad_tol, 1e-12 * abs(v))       # as ssde_laplace.cu: relative for objectives >= 1e4
+            if info["grad_max"] <= tol_eff:
                 info["converged"] = 1
                 break
             if it == self.max_newton:
@@ -121,7 +122,7 @@ class LoopLaplace:
             step = np.linalg.solve(Lc.T, np.linalg.solve(Lc, gb))
             slope = float(gb @ step)
             t, ok = 1.0, False
-            for _ in range(40):
+            for _ in range(6 if info["grad_max"] <= 1e3 * tol_eff else 40):
                 q = p.copy()
                 q[sl] = p[sl] - t * step
                 vn, _ = self.engine.eval(q, order=0)
@@ -131,6 +132,7 @@ class LoopLaplace:
                     break
                 t *= 0.5
             if not ok:
+                info["converged"] = int(info["grad_max"] <= 1e3 * tol_eff)
                 break
             p = q
             v, g, Hc = self._hess_cols(p)

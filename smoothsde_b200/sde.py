@@ -237,7 +237,8 @@ class SDE:
         if self._tmb_obj is None:
             self.setup(silent=silent, map=map)
         obj = self._tmb_obj
-        res = minimize(obj.fn, obj.par, jac=obj.gr, method="BFGS", options={"gtol": gtol, "maxiter": maxiter})
+        # optim(fn, gr, method = "BFGS") in R/sde.R:694-697; value and gradient come from one evaluation
+        res = minimize(obj.fn_gr, obj.par, jac=True, method="BFGS", options={"gtol": gtol, "maxiter": maxiter})
         self._out = res
         p = obj.env.last_par_best
         lay = obj.engine.layout
