@@ -28,7 +28,7 @@ class _Budget(Exception):
     pass
 
 
-def run_fit(obj, gtol, maxiter=200, budget_s=None, tag=""):
+def run_fit(obj, gtol, maxiter=200, budget_s=None, tag="", sync=None):
     """BFGS as optim(method = "BFGS") in R/sde.R:694-697; progress goes to stderr; stops with the best
     point so far when the wall-clock budget is spent (reported as such)."""
     calls = {"fn": 0, "gr": 0, "it": 0}
@@ -44,9 +44,13 @@ def run_fit(obj, gtol, maxiter=200, budget_s=None, tag=""):
         calls["it"] += 1
         el = time.perf_counter() - t0
         trace.append((el, [float(v) for v in xk]))
-        print(f"[fit {tag}] it {calls['it']:3d}  {el:8.1f} s  fn {calls['fn']} gr {calls['gr']}  x = {np.array2string(np.asarray(xk), precision=5)}",
+        if tag is not None:
+            print(f"[fit {tag}] it {calls['it']:3d}  {el:8.1f} s  fn {calls['fn']} gr {calls['gr']}  x = {np.array2string(np.asarray(xk), precision=5)}",
               file=sys.stderr, flush=True)
-        if budget_s is not None and el > budget_s:
+        over = budget_s is not None and el > budget_s
+        if sync is not None:
+            over = sync(over)                  # every rank takes the same decision
+        if over:
             raise _Budget()
 
     try:
@@ -72,6 +76,47 @@ def main():
     from smoothsde_b200.adfun import ADFun
     out = {}
     fixmu = {"coeff_fe": [None, None, 2, 3]}                   # fixpar = c("mu1", "mu2"), R/sde.R:621-632
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        # one process per GPU (torchrun): tracks sharded over the ranks, every evaluation / Hessian-vector
+        # product all-reduced; all ranks run the same BFGS on identical numbers
+        import torch
+        import torch.distributed as dist
+        from smoothsde_b200 import _lib, sharded
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+        def dist_reduce(t, op):
+            dist.all_reduce(t, op={"min": dist.ReduceOp.MIN, "max": dist.ReduceOp.MAX, "sum": dist.ReduceOp.SUM}[op])
+            return t
+        eng, par, info = devgen.make_ctcrw_device(args.tracks // world, args.steps, seed=20260103, device=local, rank=rank,
+                                                  world=world, dist_reduce=dist_reduce,
+                                                  shard_flags=(_lib.SHARD_NO_PENALTY if rank > 0 else 0))
+        tse = sharded.TrackShardedEngine.from_engine(eng, sharded.DistComm(), local)
+        par = par.copy()
+        par[0] = np.log(0.3)
+        par[3:5] = [0.5, -0.5]
+        par[7:] = 0.0
+        obj = ADFun({"type": "CTCRW"}, split(par, info["p_fe"], info["n_s"]), map=fixmu, random="coeff_re", engine=tse)
+        t0 = time.perf_counter()
+        obj.fn(obj.par)
+        t_first = time.perf_counter() - t0
+        def sync(flag):
+            t = torch.tensor([1.0 if flag else 0.0], device=torch.device("cuda", local))
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return bool(t.item() > 0.5)
+        r, secs, calls = run_fit(obj, gtol=1e-3 * info["n"] * world / 1e6, budget_s=args.budget,
+                                 tag=f"full x{world}" if rank == 0 else None, sync=sync)
+        if rank == 0:
+            print(json.dumps({"config": f"CTCRW d=2, {args.tracks} x {args.steps} rows (n={info['n'] * world}) on {world} GPUs (track shards, "
+                                        f"LoopLaplace over all-reduced evaluations / Hessian-vector products)",
+                              "theta_hat": [float(x) for x in r.x], "sigma_obs_hat": float(np.exp(r.x[0])), "marginal_nllk": float(r.fun),
+                              "first_value_s": t_first, "fit_wall_s": secs, "bfgs_iterations": int(r.nit), "fn_gr_calls": calls["fn"],
+                              "success": bool(r.success), "message": str(r.message), "grad_inf_norm": float(np.max(np.abs(r.jac))),
+                              "s_per_call": secs / max(calls["fn"], 1)}), flush=True)
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     if not args.skip_full:
         eng, par, info = devgen.make_ctcrw_device(args.tracks, args.steps, seed=20260103, device=0)
         par = par.copy()
