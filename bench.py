@@ -151,7 +151,7 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 class Clocks:
     def __init__(self, index):
-        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.samples, self.mem_samples, self.reasons, self.max_mhz, self.max_mem_mhz = [], [], set(), None, None
         self._stop = threading.Event()
         self._thr = None
         try:
@@ -160,6 +160,7 @@ class Clocks:
             self.nv = pynvml
             self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
             self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.max_mem_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_MEM)
         except Exception:
             self.nv = None
 
@@ -170,6 +171,7 @@ class Clocks:
         while not self._stop.is_set():
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                self.mem_samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_MEM))
                 try:
                     r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
                 except Exception:
@@ -190,8 +192,9 @@ class Clocks:
         self._stop.set()
         if self._thr is not None:
             self._thr.join()
-        s = sorted(self.samples)
+        s, m = sorted(self.samples), sorted(self.mem_samples)
         return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "mem_mhz": (m[len(m) // 2] if m else None), "mem_max_mhz": self.max_mem_mhz,
                 "reasons": sorted(self.reasons), "samples": len(s)}
 
 

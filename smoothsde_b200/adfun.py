@@ -17,6 +17,7 @@ from __future__ import annotations
 
 import numpy as np
 
+from ._lib import EngineError
 from .engine import Engine
 
 PAR_ORDER = ("log_sigma_obs", "coeff_fe", "log_lambda", "log_decay", "coeff_re")
@@ -33,7 +34,7 @@ class Env:
 
 
 class ADFun:
-    def __init__(self, data, parameters, map=None, random=None, device=0, engine=None):
+    def __init__(self, data, parameters, map=None, random=None, device=0, engine=None, laplace_opts=None):
         self.data = data
         self.engine = engine if engine is not None else Engine.from_data(data, device=device)
         layout = self.engine.layout                      # name -> (offset, size) in the full vector
@@ -94,7 +95,7 @@ class ADFun:
         self._laplace = None
         if random is not None and self._rand.size:
             from .laplace import Laplace
-            self._laplace = Laplace(self)
+            self._laplace = Laplace(self, **(laplace_opts or {}))
 
     # ------------------------------------------------------------------------------------
     def full_from(self, x, b=None):
@@ -117,7 +118,14 @@ class ADFun:
         return out[idx]
 
     def joint(self, p_full, order=1):
-        v, g = self.engine.eval(p_full, order=order)
+        try:
+            v, g = self.engine.eval(p_full, order=order)
+        except EngineError as e:
+            # SSDE_ERR_NUMERIC (F <= 0 in the filter, ...) at these parameters: the objective is undefined,
+            # an optimiser must see Inf / NaN and step back, not an exception
+            if e.code != 5:
+                raise
+            v, g = np.inf, (np.full(np.asarray(p_full).size, np.nan) if order >= 1 else None)
         self.env.last_par = p_full.copy()
         return v, g
 

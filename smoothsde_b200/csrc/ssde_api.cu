@@ -11,6 +11,7 @@
 #include <chrono>
 #include <exception>
 #include <sched.h>
+#include <sys/mman.h>
 #include <string>
 #include <vector>
 
@@ -129,15 +130,32 @@ int dev_alloc(DevBuf& b, size_t count, std::string& err) {
 // thread (page faults included) before the worker threads overwrite every entry that is ever read.
 template <class T>
 struct RawVec {
-    std::unique_ptr<T[]> p;
+    struct Free { void operator()(T* q) const { std::free(q); } };
+    std::unique_ptr<T, Free> p;
     size_t n = 0;
-    void alloc(size_t count) { p.reset(new T[count > 0 ? count : 1]); n = count; }
+    // 2 MB-aligned and advised as transparent huge pages: the first touch of a multi-GB buffer by 16
+    // threads is otherwise dominated by 4 KB page faults
+    void alloc(size_t count) {
+        static_assert(std::is_trivial<T>::value, "RawVec holds plain data");
+        const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+        void* q = nullptr;
+        if (bytes >= (size_t(8) << 20)) {
+            const size_t al = size_t(2) << 20;
+            if (posix_memalign(&q, al, (bytes + al - 1) / al * al) != 0) q = nullptr;
+            if (q) madvise(q, (bytes + al - 1) / al * al, MADV_HUGEPAGE);
+        } else {
+            q = std::malloc(bytes);
+        }
+        if (!q) throw std::bad_alloc();
+        p.reset(static_cast<T*>(q));
+        n = count;
+    }
     T* data() { return p.get(); }
     const T* data() const { return p.get(); }
     size_t size() const { return n; }
     bool empty() const { return n == 0; }
-    T& operator[](size_t i) { return p[i]; }
-    const T& operator[](size_t i) const { return p[i]; }
+    T& operator[](size_t i) { return p.get()[i]; }
+    const T& operator[](size_t i) const { return p.get()[i]; }
 };
 template <class T>
 int dev_upload(DevBuf& b, const RawVec<T>& v, std::string& err) {

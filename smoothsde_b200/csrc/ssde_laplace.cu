@@ -40,6 +40,7 @@ struct ssde_laplace {
     int lwork = 0;
     std::vector<double> par, out, grad, H_cols, L, step, gb;
     ssde_laplace_opts opts{};
+    bool factor_valid = false;       // d_Hbb holds the Cholesky factor of H_bb at the mode of the previous evaluation
     std::string err;
     ~ssde_laplace() {
         cudaSetDevice(device);
@@ -82,6 +83,23 @@ int joint_value(ssde_laplace* w, const std::vector<double>& par, double& v) {
     LP_CUDA(cudaMemcpyAsync(o, w->d_out, sizeof(double), cudaMemcpyDeviceToHost, w->st));
     LP_CUDA(cudaStreamSynchronize(w->st));
     v = o[0];
+    return SSDE_OK;
+}
+
+// joint value and gradient at `par` (one plain evaluation, no tangent pass)
+int joint_grad(ssde_laplace* w, const std::vector<double>& par, double& v, std::vector<double>& g) {
+    const int np = w->np;
+    LP_CUDA(cudaMemcpyAsync(w->d_par2, par.data(), sizeof(double) * np, cudaMemcpyHostToDevice, w->st));
+    LP_TRY(ssde_eval_device(w->h, w->d_par2, 1, w->d_out, w->st));
+    std::vector<double> o(np + 2);
+    LP_CUDA(cudaMemcpyAsync(o.data(), w->d_out, sizeof(double) * (np + 2), cudaMemcpyDeviceToHost, w->st));
+    LP_CUDA(cudaStreamSynchronize(w->st));
+    if (o[np + 1] != 0.0) {
+        w->err = ((unsigned)o[np + 1] & 2u) ? "device-side failure: innovation variance F <= 0 in the filter" : "device-side failure (scan look-back timed out)";
+        return SSDE_ERR_NUMERIC;
+    }
+    v = o[0];
+    g.assign(o.begin() + 1, o.begin() + 1 + np);
     return SSDE_OK;
 }
 
@@ -221,8 +239,35 @@ int ssde_laplace_eval(ssde_laplace* w, double* par, int order, double* value, do
         if (info) *info = li;
         return SSDE_OK;
     }
-    // ---- inner problem: Newton on coeff_re with the exact H_bb, backtracking on the joint objective
+    // ---- warm start: chord iterations with the factor of the previous mode.  Between two outer
+    //      (BFGS) steps theta moves little, so H_bb^-1 of the last mode is a good preconditioner: each
+    //      iteration costs one plain evaluation instead of the n_b tangent passes of a Hessian; the
+    //      exact H_bb is then built once, at the converged mode, where the log-determinant needs it.
     double v = 0.0;
+    if (w->factor_valid) {
+        std::vector<double> g, gt, trial;
+        LP_TRY(joint_grad(w, w->par, v, g));
+        ++li.n_value;
+        for (int it = 0; it < 12; ++it) {
+            double gmax = 0.0;
+            for (int i = 0; i < nb; ++i) { w->gb[i] = g[o + i]; gmax = std::max(gmax, std::fabs(w->gb[i])); }
+            if (!(gmax == gmax) || gmax <= std::max(w->opts.grad_tol, 1e-12 * std::fabs(v))) break;
+            w->step = w->gb;
+            LP_TRY(solve_bb(w, w->step));
+            trial = w->par;
+            for (int i = 0; i < nb; ++i) trial[o + i] = w->par[o + i] - w->step[i];
+            double vt = 0.0;
+            LP_TRY(joint_grad(w, trial, vt, gt));
+            ++li.n_value;
+            double gmax_t = 0.0;
+            for (int i = 0; i < nb; ++i) gmax_t = std::max(gmax_t, std::fabs(gt[o + i]));
+            // keep the step only if it is a clear improvement; otherwise hand over to Newton
+            if (!(vt == vt) || !(gmax_t == gmax_t) || vt > v + 1e-14 * std::fabs(v) || gmax_t > 0.5 * gmax) break;
+            w->par = trial; v = vt; g.swap(gt);
+        }
+    }
+    w->factor_valid = false;
+    // ---- inner problem: Newton on coeff_re with the exact H_bb, backtracking on the joint objective
     LP_TRY(joint_hess_cols(w, v));
     li.n_hess = 1;
     int pd_info = 0;
@@ -278,6 +323,7 @@ int ssde_laplace_eval(ssde_laplace* w, double* par, int order, double* value, do
         w->err = "H_bb is not positive definite at the inner optimum";
         return SSDE_ERR_NUMERIC;
     }
+    w->factor_valid = true;                      // d_Hbb = chol(H_bb) at the mode: preconditioner of the next call
     LP_CUDA(cudaMemcpyAsync(w->L.data(), w->d_Hbb, sizeof(double) * (size_t)nb * nb, cudaMemcpyDeviceToHost, w->st));
     LP_CUDA(cudaMemcpyAsync(w->H_cols.data(), w->d_hess, sizeof(double) * (size_t)np * nb, cudaMemcpyDeviceToHost, w->st));
     LP_CUDA(cudaStreamSynchronize(w->st));

@@ -85,6 +85,17 @@ class LoopLaplace:
         self.max_newton, self.grad_tol, self.fd_step, self.richardson = max_newton, grad_tol, fd_step, richardson
         self.info = None
         self._H = None
+        self._Lc = None
+
+    def _value(self, q):
+        """joint value at a TRIAL point of a line search: a device-side numeric failure there (F <= 0 at
+        wild parameters, SSDE_ERR_NUMERIC) means "reject the trial", as a NaN would"""
+        try:
+            return self.engine.eval(q, order=0)[0]
+        except L.EngineError as e:
+            if e.code != 5:
+                raise
+            return np.inf
 
     def _hess_cols(self, p):
         E = np.zeros((p.size, self.nb))
@@ -101,6 +112,24 @@ class LoopLaplace:
             info["joint"] = v
             self.info = info
             return v, g, p
+        # warm start (as ssde_laplace.cu): chord iterations with the Cholesky factor of the previous mode --
+        # one plain evaluation each instead of the n_b tangent passes of a Hessian
+        if self._Lc is not None:
+            v, g = self.engine.eval(p, order=1)
+            info["n_value"] += 1
+            for _ in range(12):
+                gmax = float(np.max(np.abs(g[sl])))
+                if not np.isfinite(gmax) or gmax <= max(self.grad_tol, 1e-12 * abs(v)):
+                    break
+                q = p.copy()
+                q[sl] = p[sl] - np.linalg.solve(self._Lc.T, np.linalg.solve(self._Lc, g[sl]))
+                vq, gq = self.engine.eval(q, order=1)
+                info["n_value"] += 1
+                gq_max = float(np.max(np.abs(gq[sl])))
+                if not (np.isfinite(vq) and np.isfinite(gq_max)) or vq > v + 1e-14 * abs(v) or gq_max > 0.5 * gmax:
+                    break
+                p, v, g = q, vq, gq
+        self._Lc = None
         v, g, Hc = self._hess_cols(p)
         for it in range(self.max_newton + 1):
             gb = g[sl]
@@ -125,7 +154,7 @@ class LoopLaplace:
             for _ in range(6 if info["grad_max"] <= 1e3 * tol_eff else 40):
                 q = p.copy()
                 q[sl] = p[sl] - t * step
-                vn, _ = self.engine.eval(q, order=0)
+                vn = self._value(q)
                 info["n_value"] += 1
                 if np.isfinite(vn) and vn <= v - 1e-4 * t * slope + 1e-14 * abs(v):
                     ok = True
@@ -146,6 +175,7 @@ class LoopLaplace:
         except np.linalg.LinAlgError:
             self.info = info
             return np.inf, (np.full(p.size, np.nan) if order else None), p
+        self._Lc = Lc                                          # preconditioner of the next call's chord iterations
         info["logdet"] = float(2 * np.sum(np.log(np.diag(Lc))))
         val = v + 0.5 * info["logdet"] - 0.5 * nb * np.log(2 * np.pi)
         self.info = info
@@ -203,7 +233,14 @@ class Laplace:
             return c[1], c[2]
         ad = self.ad
         p0 = ad.full_from(x, self.b)                           # warm start from the previous mode
-        val, g_full, p = self.driver.eval(p0, order=order)
+        try:
+            val, g_full, p = self.driver.eval(p0, order=order)
+        except L.EngineError as e:
+            # a numeric failure of the engine at THIS theta (e.g. F <= 0 in the filter at wild parameters of a
+            # line-search trial): the objective is undefined there, report Inf like a NaN from TMB would be
+            if e.code != 5:
+                raise
+            val, g_full, p = np.inf, (np.full(p0.size, np.nan) if order >= 1 else None), p0
         if np.isfinite(val):
             self.b = p[ad._rand].copy()
         ad.env.last_par = p.copy()

@@ -216,3 +216,22 @@ def test_he_and_sdreport_follow_tmb():
     cov = np.linalg.inv(Q)
     assert np.allclose(cov[:nt, :nt], sd["cov_fixed"], rtol=1e-6, atol=1e-10)       # marginal covariance of the fixed effects
     assert np.all(np.linalg.eigvalsh(Q) > 0)
+
+
+def test_laplace_warm_start_chord_iterations_give_the_cold_start_result():
+    from smoothsde_b200 import synth
+    """The chord iterations that precondition with the factor of the previous mode must land on the same
+    mode (and the same marginal value / gradient) as a cold start with full Newton steps."""
+    from smoothsde_b200.laplace import LoopLaplace
+    dat, par, info = synth.make_problem("CTCRW", 2, 60, n_dim=1, seed=3, k=5, missing_frac=0.1)
+    warm = LoopLaplace(OracleEngine(dat))
+    f0, g0, p0 = warm.eval(par, order=1)
+    par2 = p0.copy()
+    par2[0] += 0.05                       # log_sigma_obs moves, coeff_re starts at the previous mode
+    par2[3] -= 0.03
+    f_w, g_w, p_w = warm.eval(par2, order=1)
+    assert warm.info["n_hess"] == 1       # the warm evaluation needed no Newton rebuild of H_bb
+    f_c, g_c, p_c = LoopLaplace(OracleEngine(dat)).eval(par2, order=1)
+    assert abs(f_w - f_c) <= 1e-9 * max(1.0, abs(f_c))
+    assert np.max(np.abs(p_w - p_c)) <= 1e-7
+    assert np.max(np.abs(g_w - g_c)) <= 1e-5 * max(1.0, np.max(np.abs(g_c)))

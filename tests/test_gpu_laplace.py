@@ -180,3 +180,23 @@ def test_laplace_marginal_equals_the_exact_gaussian_marginal():
     ge = th.grad.numpy()
     assert np.max(np.abs(g - ge)) <= 1e-6 * max(1.0, np.max(np.abs(ge))), (g, ge)
     obj.close()
+
+
+def test_device_laplace_warm_start_matches_cold_start():
+    """ssde_laplace_eval re-uses the Cholesky factor of the previous mode for cheap chord iterations; the
+    result must be the one a fresh workspace finds with full Newton steps."""
+    dat, par, info = synth.make_problem("CTCRW", 3, 200, n_dim=2, seed=52, k=6, missing_frac=0.05)
+    eng = Engine.from_data(dat)
+    warm = DeviceLaplace(eng)
+    f0, g0, p0 = warm.eval(par, order=1)
+    par2 = p0.copy()
+    par2[0] += 0.05
+    par2[3] -= 0.03
+    f_w, g_w, p_w = warm.eval(par2, order=1)
+    assert warm.info["converged"] == 1 and warm.info["n_hess"] == 1
+    cold = DeviceLaplace(eng)
+    f_c, g_c, p_c = cold.eval(par2, order=1)
+    assert abs(f_w - f_c) <= 1e-10 * max(1.0, abs(f_c))
+    assert np.max(np.abs(p_w - p_c)) <= 1e-8
+    assert np.max(np.abs(g_w - g_c)) <= 1e-7 * max(1.0, np.max(np.abs(g_c)))
+    warm.close(); cold.close(); eng.close()
