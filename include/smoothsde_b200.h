@@ -51,7 +51,8 @@ enum ssde_status {
     SSDE_ERR_BAD_ARG = 2,
     SSDE_ERR_UNSUPPORTED = 3,
     SSDE_ERR_CUDA = 4,
-    SSDE_ERR_NUMERIC = 5      /* F <= 0 in the filter, scan time-out, ... */
+    SSDE_ERR_NUMERIC = 5      /* device status word: innovation variance F <= 0 in the filter (bit 1), scan
+                               * look-back time-out (bit 0); Laplace: H_bb not positive definite, ... */
 };
 
 /* dgTMatrix triplets as produced by as_sparse(), R/utility.R:204-213: 0-based i, j; duplicate
@@ -273,7 +274,12 @@ int ssde_eval_stage(ssde_handle* h, const double* d_par, int stage, const double
 int ssde_check(ssde_handle* h);
 
 /* REPORT(aest_all): [n x 2*n_dim] column-major predicted-state means after each row
- * (nllk_ctcrw.hpp:192-194, :246-249) at the parameters of the last ssde_eval. */
+ * (nllk_ctcrw.hpp:192-194, :246-249) at the parameters of the last ssde_eval.
+ * One documented difference: the row that ENDS a track holds, in the reference, a prediction made
+ * with the cross-track dt = times[first row of next track] - times[last row] (:126-129, :206-208) --
+ * a value the loop discards at the ID change (:196-200) and that overflows when the next track's
+ * clock restarts; here that row is predicted with dt = 1 (the value the reference uses for the very
+ * last row, :129).  Every other row agrees with the reference to 1e-9 (tests/test_gpu_ref.py). */
 int ssde_report(ssde_handle* h, double* aest_all);
 
 /* Device time in milliseconds of the kernels of the last ssde_eval / ssde_eval_device on the
