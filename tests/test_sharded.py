@@ -140,3 +140,29 @@ def test_shard_rows_carries_user_H_and_decay_times():
     want = np.concatenate([dat2["t_decay"][j * n2 + lo:j * n2 + hi] for j in range(n_par)])
     assert np.array_equal(sub2["t_decay"], want) and sub2["X_re"].shape[0] == n_par * (hi - lo)
     assert list(sub2["col_decay"]) == [1, 2]
+
+
+def test_split_tracks_gives_every_rank_a_track_even_when_unbalanced():
+    """track sizes [100, 1, 1, 1] on 4 ranks used to leave ranks empty (which then blocked the
+    others in the first collective); with fewer tracks than ranks EVERY rank must raise."""
+    from smoothsde_b200 import sharded as S
+
+    def ids(sizes):
+        return np.repeat(np.arange(len(sizes)), sizes)
+    for sizes, world in (([100, 1, 1, 1], 4), ([1, 1, 1, 100], 4), ([50, 1, 1, 50, 3], 3), ([7] * 16, 8), ([5, 9, 2], 3)):
+        groups = S.split_tracks(ids(sizes), world)
+        assert len(groups) == world and groups[0][0] == 0 and groups[-1][1] == sum(sizes)
+        assert all(hi > lo for lo, hi in groups), (sizes, groups)
+        assert all(groups[r][1] == groups[r + 1][0] for r in range(world - 1))
+        bounds = set(np.cumsum([0] + list(sizes)).tolist())
+        assert all(lo in bounds and hi in bounds for lo, hi in groups)          # whole tracks only
+    groups = S.split_tracks(ids([5, 5]), 4)
+    assert sum(hi > lo for lo, hi in groups) == 2
+
+    class FakeComm:
+        def __init__(self, rank):
+            self.rank, self.world = rank, 4
+    dat = {"ID": ids([5, 5]).astype(float)}
+    for rank in range(4):                        # the same error on every rank, before any collective
+        with pytest.raises(ValueError, match="cannot be spread over 4 ranks"):
+            S.TrackShardedEngine(dat, comm=FakeComm(rank), device=None, engine_factory=lambda *a: None)
