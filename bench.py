@@ -3,14 +3,26 @@
 
     python bench.py --gpus 1 --steps 20 --warmup 3
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
-    python bench.py --impl reference          # CPU arm (oracle port of the TMB objective)
+    python bench.py --impl reference          # CPU arm: the reference's own templates (oracle/_ref)
 
 A "step" is one evaluation of the joint penalised nllk and its gradient (what obj$fn + obj$gr do
 in SDE$fit(), R/sde.R:694-697) over the whole synthetic data set, which is resident in HBM.
-Workload (BASELINE.json configs[2], the CTCRW 1e8-observation case the metric is quoted on):
+Headline workload (BASELINE.json configs[2], the CTCRW 1e8-observation case the metric is quoted on):
 1024 simulated tracks x 1e5 irregular steps, d = 2, tau, nu ~ s(time, k = 10), mu fixed at 0.
 With N > 1 GPUs the tracks are split across ranks (strong scaling: the total stays 1.024e8
 rows) and the packed [nllk, gradient] vector is summed with one NCCL all-reduce per evaluation.
+The data set is the SAME at every N (devgen.GroupedRNG) and the line's `parity_vs_n1` compares nllk /
+gradient with the stored 1-GPU result (profiles/bench_nllk_n1.json; `--write-n1` refreshes it).
+
+The same JSON line also carries (default `--workload both`):
+  single    BASELINE configs[3]: ONE track of 1.024e8 rows, sharded along time (2 all-gathers of a scan
+            element + 1 all-reduce per evaluation), with the count of whole-shard fallback passes;
+  configs   the BM / OU path: configs[4]'s OU half (4096 tracks x 25 000 steps, mu, tau ~ s(time) +
+            s(ID, bs = "re"), p_re = 8210) and configs[1] (64 x 1e5), tracks sharded over the ranks;
+  roofline  frac (algorithmic bytes of SURVEY 8(d) / launch time / peak) AND dram_frac (DRAM bytes the ncu
+            capture of the same kernel measured, scaled by rows / launch time / peak);
+  cpu_baseline (N = 1 only)  the reference arm on a bounded sample, all host cores and one thread, with the
+            C port beside it.
 """
 from __future__ import annotations
 
