@@ -87,24 +87,33 @@ def main():
     eng.close(); torch.cuda.empty_cache()
     if "--skip-ou" in sys.argv:
         return
-    # configs[1]: OU, mu, tau ~ s(time) + s(ID, bs = "re"), kappa ~ 1; 64 tracks x 1e5 steps (host-built design)
-    t0 = time.perf_counter()
-    dat, par, info = synth.make_problem("OU", 64, 100000, n_dim=1, seed=20260102, re_id=True)
-    t_build = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    eng = Engine.from_data(dat)
-    t_create = time.perf_counter() - t0
-    n = info["n"]
-    nnz = (dat["X_fe"].nnz + dat["X_re"].nnz) / n
-    b_alg = devgen.alg_bytes_per_obs(1, 3, nnz)
-    ms = timed(lambda: eng.eval(par, 1))
-    d = np.zeros(par.size)
-    d[-1] = 1.0
-    ms_h = timed(lambda: eng.hvp(par, d), reps=5, warm=2)
-    report("C2 OU 64 x 1e5, s(time) + s(ID, re)", n, ms, b_alg,
-           {"nnz_per_row": nnz, "p_re": int(dat["X_re"].shape[1]), "host_design_build_s": t_build, "ssde_create_s": t_create,
-            "kernel_ms_last_eval": eng.last_eval_ms, "hvp_ms_per_direction": ms_h})
-    eng.close()
+    # configs[1] and the OU half of configs[4]: OU, mu, tau ~ s(time) + s(ID, bs = "re"), kappa ~ 1, built on the device
+    for name, T, m, with_laplace in (("C2 OU 64 x 1e5, s(time) + s(ID, re)  [configs[1]]", 64, 100000, True),
+                                     ("C5 OU 4096 x 2.5e4, s(time) + s(ID, re)  [configs[4], OU half]", 4096, 25000, False)):
+        eng, par, info = devgen.make_ou_device(T, m, device=0)
+        n = info["n"]
+        b_alg = devgen.alg_bytes_per_obs(1, 3, 23)
+        ms = timed(lambda: eng.eval(par, 1))
+        d = np.zeros(par.size)
+        d[-1] = 1.0
+        ms_h = timed(lambda: eng.hvp(par, d), reps=5, warm=2)
+        extra = {"p_re": info["p_re"], "stored_bytes_per_obs": 201, "kernel_ms_last_eval": eng.last_eval_ms,
+                 "dram_frac_stored_bytes": 201 * n / (eng.last_eval_ms * 1e-3) / 1e9 / PEAK, "hvp_ms_per_direction": ms_h}
+        if with_laplace:                     # 146 random effects: the dense Laplace driver (146 tangent passes per Hessian)
+            lap = DeviceLaplace(eng)
+            t0 = time.perf_counter()
+            f, g, p = lap.eval(par, order=1)
+            extra["laplace_value_and_gradient_s"] = time.perf_counter() - t0
+            extra["laplace_info"] = lap.info
+            t0 = time.perf_counter()
+            lap.eval(p, order=1)
+            extra["laplace_warm_s"] = time.perf_counter() - t0
+            extra["laplace_warm_info"] = lap.info
+            lap.close()
+        else:
+            extra["laplace"] = "not built at this size: H_bb has arrowhead structure (18 spline coefficients + 2 x 4096 intercepts), DESIGN.md section 8"
+        report(name, n, ms, b_alg, extra)
+        eng.close(); torch.cuda.empty_cache()
 
 
 if __name__ == "__main__":
