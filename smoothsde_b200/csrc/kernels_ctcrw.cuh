@@ -43,6 +43,11 @@
 #ifndef SSDE_FWD_PIPE
 #define SSDE_FWD_PIPE 0
 #endif
+// 1: the forward kernel parks the thread's exclusive-prefix element in shared memory across the
+// look-back (instead of letting the compiler spill it) and caches tau/e/s2 instead of the step
+#ifndef SSDE_FWD_EXC_SMEM
+#define SSDE_FWD_EXC_SMEM 0
+#endif
 
 namespace ssde {
 
@@ -138,7 +143,16 @@ __device__ __forceinline__ RowPlanes<M> open_planes(const KalmanArgs<typename M:
 template <class M, int NT>
 struct FwdSmem {
     using R = typename M::R;
+#if SSDE_FWD_EXC_SMEM
+    // per row the transformed parameters (CTCRW: tau, e, s2 -- the step is rebuilt from them with ~15
+    // flops in the re-run) instead of the 5 step quantities: the 16 KB this saves hold the thread's
+    // exclusive-prefix element across the look-back, which the compiler otherwise spills to local
+    // memory (36 STL + 18 LDL.64 per thread and tile = 1.8 GB of DRAM writes per launch at 1e8 rows)
+    static constexpr int NC = M::NW;
+    double X[M::FwdElem::NDBL][NT];
+#else
     static constexpr int NC = M::NC;             // step quantities per row (CTCRW: T12, e, Qa, Qb, Qc)
+#endif
     static constexpr int ES = (M::FwdElem::NDBL > 24 * ScalarOf<R>::NDBL) ? M::FwdElem::NDBL : 24 * ScalarOf<R>::NDBL;
     R W[LC][NC][NT];
     double stage[NT / 32][STAGE_DBL];
@@ -235,7 +249,11 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(KalmanArgs<typename
             r.sp = M::make_step(rp, r.dtv);
             if (step) {
                 M::store_rowpar(rp, [&](int c) -> R& { return const_cast<R&>(pl.wg[c][k * 32]); });
+#if SSDE_FWD_EXC_SMEM
+                M::store_rowpar(rp, [&](int c) -> R& { return sm.W[k][c][tid]; });
+#else
                 M::store_step(r.sp, [&](int c) -> R& { return sm.W[k][c][tid]; });
+#endif
             }
             (void)pos;
         };
@@ -298,7 +316,11 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(KalmanArgs<typename
                 const typename M::RowPar rp = M::transform(eta, dtv);
                 M::store_rowpar(rp, [&](int c) -> R& { return const_cast<R&>(pl.wg[c][k * 32]); });
                 const typename M::Step sp = M::make_step(rp, dtv);
+#if SSDE_FWD_EXC_SMEM
+                M::store_rowpar(rp, [&](int c) -> R& { return sm.W[k][c][tid]; });
+#else
                 M::store_step(sp, [&](int c) -> R& { return sm.W[k][c][tid]; });
+#endif
                 M::fwd_append(E, sp, y, eta, (f & ROW_OBS) != 0, M::row_h(h, a.Hrow, a.X.n_pad, pos));
             } else if (live) {
                 M::fwd_append_start(E, track_start_state<M>(a, dtv));
@@ -339,6 +361,13 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(KalmanArgs<typename
         }
         Elem exc = shfl_up_elem(inc, 1);
         if (lane == 0) exc = M::fwd_identity();
+#if SSDE_FWD_EXC_SMEM
+        {
+            const double* ex = reinterpret_cast<const double*>(&exc);
+#pragma unroll
+            for (int i = 0; i < Elem::NDBL; ++i) sm.X[i][tid] = ex[i];
+        }
+#endif
 #ifdef SSDE_STATS
         tc1 = clock64();
 #endif
@@ -384,7 +413,17 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(KalmanArgs<typename
 #pragma unroll 1
             for (int ww = max(w0, 0); ww < warp; ++ww) s = M::fwd_apply(load_elem<Elem>(sm.wagg[par][ww]), s);
         }
+#if SSDE_FWD_EXC_SMEM
+        {
+            Elem ex2;
+            double* ex = reinterpret_cast<double*>(&ex2);
+#pragma unroll
+            for (int i = 0; i < Elem::NDBL; ++i) ex[i] = sm.X[i][tid];
+            s = M::fwd_apply(ex2, s);
+        }
+#else
         s = M::fwd_apply(exc, s);
+#endif
         const int64_t chunk = q * 32 + lane;
         M::store_state(s, [&](int i) -> R& { return a.ckpt[(size_t)i * a.nchunks + chunk]; });
         // sum_i log F_i is taken as the log of a running product (one log per chunk instead of
@@ -425,7 +464,11 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(KalmanArgs<typename
 #pragma unroll
                 for (int d = 0; d < ND; ++d) mu[d] = 0.0;
                 if (!mu0) row_eta_prefix<ND>(w, k, a.theta, mu);
+#if SSDE_FWD_EXC_SMEM
+                const typename M::Step sp = M::make_step(M::load_rowpar([&](int c) { return sm.W[k][c][tid]; }), dtv);
+#else
                 const typename M::Step sp = M::load_step([&](int c) { return sm.W[k][c][tid]; }, dtv);
+#endif
                 R F, qd;
                 M::template fwd_step<false>(s, sp, y, mu, (f & ROW_OBS) != 0, M::row_h(h, a.Hrow, a.X.n_pad, pos), nullptr, F, qd);
                 quad += qd;
