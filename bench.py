@@ -351,9 +351,11 @@ def n1_parity(key, args, world, rank, nllk, grad):
         head = grad[:gs.size]
         gerr = float(np.max(np.abs(head - gs) / np.maximum(np.abs(gs), 1e-3 * np.abs(gs).max())))
         nerr = abs(float(np.linalg.norm(grad)) - st.get("grad_l2", float(np.linalg.norm(gs)))) / st.get("grad_l2", float(np.linalg.norm(gs)))
-        assert rel <= 1e-10 and gerr <= 1e-7 and nerr <= 1e-7, \
-            f"{key}: {world}-GPU result differs from the stored 1-GPU result: {rel:.3e} / {gerr:.3e} / {nerr:.3e}"
-        out = {"nllk_rel": rel, "grad_rel": gerr, "grad_l2_rel": nerr}
+        ok = bool(rel <= 1e-10 and gerr <= 1e-7 and nerr <= 1e-7)
+        if not ok and rank == 0:
+            print(f"PARITY FAILURE {key}: {world}-GPU result differs from the stored 1-GPU result: "
+                  f"{rel:.3e} / {gerr:.3e} / {nerr:.3e}", file=sys.stderr, flush=True)
+        out = {"nllk_rel": rel, "grad_rel": gerr, "grad_l2_rel": nerr, "ok": ok, "tolerance": "1e-10 nllk, 1e-7 gradient"}
     if args.write_n1 and world == 1 and rank == 0:
         stored[key] = {"nllk": float(nllk), "grad": [float(x) for x in grad[:64]], "grad_l2": float(np.linalg.norm(grad))}
         os.makedirs(os.path.dirname(N1_FILE), exist_ok=True)
