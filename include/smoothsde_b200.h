@@ -206,6 +206,15 @@ int ssde_eval_device(ssde_handle* h, const double* d_par, int order, double* d_o
 int ssde_hvp(ssde_handle* h, const double* par, int n_dir, const double* dirs, double* nllk, double* grad, double* hv);
 int ssde_hvp_device(ssde_handle* h, const double* d_par, const double* d_dir, double* d_out, double* d_hv, void* stream);
 int ssde_hess_cols_device(ssde_handle* h, const double* d_par, int first, int count, double* d_out, double* d_hess, void* stream);
+/* BM / OU without decay terms (designs whose warp-tiles are uniform, <= 32 slots, <= 12 per SDE parameter):
+ * the Hessian of the penalised objective with respect to theta = [coeff_fe | coeff_re] in ONE pass over the
+ * design, H = X' W X + blockdiag(0, lambda_i S_i), with the exact NP x NP second-derivative block W_i of
+ * every row (rows are independent, nllk_sde.hpp:73-84) -- the "X_re' W X_re + S_lambda" of the Laplace inner
+ * problem.  Tangent passes (ssde_hess_cols_device) need one sweep per column, i.e. thousands for
+ * s(ID, bs = "re") with one level per track.  d_hess: [p_theta x p_theta] column-major DEVICE buffer,
+ * overwritten (this shard's part: sum over shards; the penalty is added by the shard that owns it).
+ * Asynchronous on `stream`.  SSDE_ERR_UNSUPPORTED for the Kalman models and decay models. */
+int ssde_hess_theta_device(ssde_handle* h, const double* d_par, double* d_hess, void* stream);
 
 /* Laplace-marginal objective over coeff_re: what MakeADFun(..., random = "coeff_re") evaluates
  * (R/sde.R:522-524, :656-658; TMB's inner newton() + sparse Cholesky):

@@ -85,7 +85,7 @@ EXPORTS = ["ssde_create", "ssde_create_packed", "ssde_destroy", "ssde_n_par", "s
            "ssde_padded_rows", "ssde_layout_info", "ssde_pack_host", "ssde_pack_free",
            "ssde_simulate_ctcrw", "ssde_simulate_ou", "ssde_launch_info",
            "ssde_shard_elem_doubles", "ssde_eval_stage",
-           "ssde_hvp", "ssde_hvp_device", "ssde_hess_cols_device",
+           "ssde_hvp", "ssde_hvp_device", "ssde_hess_cols_device", "ssde_hess_theta_device",
            "ssde_laplace_create", "ssde_laplace_destroy", "ssde_laplace_eval", "ssde_laplace_hessian_bb",
            "ssde_laplace_error", "ssde_device", "ssde_stream", "ssde_debug_stats",
            "ssde_debug_const_map_tol"]
@@ -170,6 +170,8 @@ def load():
     lib.ssde_laplace_error.restype = C.c_char_p
     lib.ssde_debug_stats.argtypes = [vp, C.POINTER(C.c_uint64), C.c_int]
     lib.ssde_debug_stats.restype = C.c_int
+    lib.ssde_hess_theta_device.argtypes = [vp, vp, vp, vp]
+    lib.ssde_hess_theta_device.restype = C.c_int
     lib.ssde_debug_const_map_tol.argtypes = [C.c_int, C.c_double]
     lib.ssde_debug_const_map_tol.restype = C.c_int
     lib.ssde_device.argtypes = [vp]

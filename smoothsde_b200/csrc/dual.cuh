@@ -82,4 +82,46 @@ SSDE_HD Dual sqrt(const Dual& a) { const double s = ::sqrt(a.v); return Dual(s, 
 SSDE_HD double fmad(double a, double b, double c) { return fma(a, b, c); }
 SSDE_HD Dual fmad(double a, const Dual& b, const Dual& c) { return Dual(fma(a, b.v, c.v), fma(a, b.d, c.d)); }
 
+// ---------------------------------------------------------------------------------------------
+// DualN<N>: value + N partial derivatives (forward mode along N seed directions at once).  Used by
+// the one-pass data-term Hessian of the BM / OU models (kernels_sde.cuh: sde_hess_kernel): the
+// closed-form d nllk_i / d eta of a row (sde_row) evaluated on DualN<NP> numbers seeded with the
+// unit directions of the row's NP linear predictors yields the exact NP x NP block W_i.
+// ---------------------------------------------------------------------------------------------
+template <int N>
+struct DualN {
+    double v, d[N];
+    DualN() = default;
+    SSDE_HD DualN(double v_) : v(v_) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) d[i] = 0.0;
+    }
+};
+template <int N> SSDE_HD double value(const DualN<N>& x) { return x.v; }
+#define SSDE_DN_LOOP _Pragma("unroll") for (int i = 0; i < N; ++i)
+template <int N> SSDE_HD DualN<N> operator-(const DualN<N>& a) { DualN<N> r; r.v = -a.v; SSDE_DN_LOOP r.d[i] = -a.d[i]; return r; }
+template <int N> SSDE_HD DualN<N> operator+(const DualN<N>& a, const DualN<N>& b) { DualN<N> r; r.v = a.v + b.v; SSDE_DN_LOOP r.d[i] = a.d[i] + b.d[i]; return r; }
+template <int N> SSDE_HD DualN<N> operator-(const DualN<N>& a, const DualN<N>& b) { DualN<N> r; r.v = a.v - b.v; SSDE_DN_LOOP r.d[i] = a.d[i] - b.d[i]; return r; }
+template <int N> SSDE_HD DualN<N> operator*(const DualN<N>& a, const DualN<N>& b) { DualN<N> r; r.v = a.v * b.v; SSDE_DN_LOOP r.d[i] = fma(a.v, b.d[i], a.d[i] * b.v); return r; }
+template <int N> SSDE_HD DualN<N> operator/(const DualN<N>& a, const DualN<N>& b) {
+    DualN<N> r; const double ib = 1.0 / b.v; r.v = a.v * ib; SSDE_DN_LOOP r.d[i] = (a.d[i] - r.v * b.d[i]) * ib; return r;
+}
+template <int N> SSDE_HD DualN<N> operator+(const DualN<N>& a, double b) { DualN<N> r = a; r.v += b; return r; }
+template <int N> SSDE_HD DualN<N> operator+(double a, const DualN<N>& b) { DualN<N> r = b; r.v += a; return r; }
+template <int N> SSDE_HD DualN<N> operator-(const DualN<N>& a, double b) { DualN<N> r = a; r.v -= b; return r; }
+template <int N> SSDE_HD DualN<N> operator-(double a, const DualN<N>& b) { DualN<N> r; r.v = a - b.v; SSDE_DN_LOOP r.d[i] = -b.d[i]; return r; }
+template <int N> SSDE_HD DualN<N> operator*(const DualN<N>& a, double b) { DualN<N> r; r.v = a.v * b; SSDE_DN_LOOP r.d[i] = a.d[i] * b; return r; }
+template <int N> SSDE_HD DualN<N> operator*(double a, const DualN<N>& b) { return b * a; }
+template <int N> SSDE_HD DualN<N> operator/(const DualN<N>& a, double b) { return a * (1.0 / b); }
+template <int N> SSDE_HD DualN<N> operator/(double a, const DualN<N>& b) {
+    DualN<N> r; const double ib = 1.0 / b.v; r.v = a * ib; SSDE_DN_LOOP r.d[i] = -r.v * b.d[i] * ib; return r;
+}
+template <int N> SSDE_HD DualN<N>& operator+=(DualN<N>& a, const DualN<N>& b) { a.v += b.v; SSDE_DN_LOOP a.d[i] += b.d[i]; return a; }
+template <int N> SSDE_HD DualN<N>& operator+=(DualN<N>& a, double b) { a.v += b; return a; }
+template <int N> SSDE_HD DualN<N>& operator-=(DualN<N>& a, const DualN<N>& b) { a.v -= b.v; SSDE_DN_LOOP a.d[i] -= b.d[i]; return a; }
+template <int N> SSDE_HD DualN<N> exp(const DualN<N>& a) { DualN<N> r; r.v = ::exp(a.v); SSDE_DN_LOOP r.d[i] = r.v * a.d[i]; return r; }
+template <int N> SSDE_HD DualN<N> log(const DualN<N>& a) { DualN<N> r; const double ia = 1.0 / a.v; r.v = ::log(a.v); SSDE_DN_LOOP r.d[i] = a.d[i] * ia; return r; }
+template <int N> SSDE_HD DualN<N> sqrt(const DualN<N>& a) { DualN<N> r; r.v = ::sqrt(a.v); const double h = 0.5 / r.v; SSDE_DN_LOOP r.d[i] = a.d[i] * h; return r; }
+#undef SSDE_DN_LOOP
+
 }  // namespace ssde

@@ -393,6 +393,205 @@ __global__ void __launch_bounds__(SDE_NT, 3) sde_stream_kernel(SdeArgs a, HotRan
 }
 #undef SSDE_SLOT_GROUPS
 
+// ---------------------------------------------------------------------------------------------
+// Data-term Hessian of the BM / OU models in ONE pass:  H = X' W X  with the exact NP x NP block
+// W_i = d^2 nllk_i / d eta_i d eta_i' of every row (rows are independent, nllk_sde.hpp:73-84), the
+// "X_re' W X_re" of the Laplace inner problem.  TMB builds the same matrix with its AD-of-AD sparse
+// Hessian (MakeADHessObject2, src/init.c:13); tangent passes need one sweep per column, i.e.
+// thousands for a random intercept per track (s(ID, bs = "re"), R/sde.R:412-421).
+//   * row-step staged by TMA as in sde_stream_kernel; eta per lane (= row) from shared memory;
+//   * W_i: the closed-form d nllk_i / d eta of sde_row evaluated on DualN<NP> numbers seeded with
+//     the unit directions of the row's predictors -- exact second derivatives, no hand algebra;
+//   * the row-step's values are transposed to xT[row][slot] and lane j' accumulates COLUMN j' of
+//     the warp-tile's S x S Hessian: acc[P][i] += xT[r][off_P + i] * (W_r[P][p(j')] * xT[r][j'])
+//     (broadcast reads of x_j, conflict-free reads of x_j', accumulators statically indexed);
+//   * after the LC row-steps column j' is added to per-CTA shared accumulators when both columns are
+//     hot (fixed effects, small smooth blocks) and to the dense global matrix otherwise (entries that
+//     involve a random intercept: touched by one track's warp-tiles only).
+// ---------------------------------------------------------------------------------------------
+constexpr int SDE_HESS_HOT = 48;        // hot columns with per-CTA accumulators (HOT x HOT doubles)
+
+struct HessHot {
+    int n;                               // hot columns
+    int cols[SDE_HESS_HOT];              // their theta indices
+};
+
+template <int NP>
+struct SdeHessSmem {
+    double stage[SDE_NT / 32][SDE_SMAX * 32];
+    double xT[SDE_NT / 32][32][SDE_SMAX + 1];
+    double W[SDE_NT / 32][32][NP * NP];
+    double th[SDE_NT / 32][SDE_SMAX];
+    int hidx[SDE_NT / 32][SDE_SMAX];
+    double hot[SDE_HESS_HOT * SDE_HESS_HOT];
+    uint64_t bar[SDE_NT / 32];
+};
+
+#define SSDE_SLOT_GROUPS(KP, BODY)                                           \
+    _Pragma("unroll") for (int g_ = 0; g_ < SDE_KPM; g_ += 4) {              \
+        if (g_ + 4 <= (KP)) {                                                \
+            _Pragma("unroll") for (int i = g_; i < g_ + 4; ++i) { BODY; }    \
+        } else if (g_ < (KP)) {                                              \
+            _Pragma("unroll") for (int i = g_; i < g_ + 4; ++i) if (i < (KP)) { BODY; } \
+        }                                                                    \
+    }
+
+template <int MODEL, int ND>
+__global__ void __launch_bounds__(SDE_NT, 2) sde_hess_kernel(SdeArgs a, HessHot hh, double* __restrict__ hess) {
+    constexpr int NP = (MODEL == MODEL_BM) ? ND + 1 : ND + 2;
+    constexpr int NWARP = SDE_NT / 32;
+    using DN = DualN<NP>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    SdeHessSmem<NP>& sm = *reinterpret_cast<SdeHessSmem<NP>*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < SDE_HESS_HOT * SDE_HESS_HOT; i += SDE_NT) sm.hot[i] = 0.0;
+    double* stage = sm.stage[warp];
+    uint64_t* bar = &sm.bar[warp];
+    if (lane == 0) mbar_init(bar, 1);
+    mbar_fence_init();
+    __syncthreads();
+    unsigned phase = 0;
+    double* th = sm.th[warp];
+    int* hidx = sm.hidx[warp];
+    const int64_t p = a.p_theta;
+    for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        const int64_t q = tile * NWARP + warp;
+        const WtDesc d = a.X.desc[q];
+        const int S = slots_of(d.kmax);
+        if (S == 0) continue;
+        int kp[NP], off[NP];
+        {
+            int o = 0;
+#pragma unroll
+            for (int pp = 0; pp < NP; ++pp) { kp[pp] = (int)((d.kmax >> (8 * pp)) & 255u); off[pp] = o; o += kp[pp]; }
+        }
+        const double* blk = a.X.val + d.val_off;
+        const uint32_t* cols = a.X.col + d.col_off;
+        const unsigned bytes = (unsigned)S * 32u * 8u;
+        __syncwarp();
+        if (lane == 0) {
+            fence_proxy_async();
+            mbar_expect_tx(bar, bytes);
+            tma_load_1d(stage, blk, bytes, bar);
+            prefetch_l2(blk + (size_t)S * 32, (unsigned)((LC - 1) * S * 32 * 8));
+        }
+        int my_col = 0, my_q = 0;                                   // this lane's column j' = lane: theta index, SDE parameter
+        if (lane < S) {
+            my_col = (int)__ldg(cols + lane);
+            th[lane] = __ldg(a.theta.v + my_col);
+            int h = -1;
+            for (int r = 0; r < hh.n; ++r) if (hh.cols[r] == my_col) h = r;
+            hidx[lane] = h;
+#pragma unroll
+            for (int pp = 1; pp < NP; ++pp) my_q += (lane >= off[pp]) ? 1 : 0;
+        }
+        const int64_t base = q * WT + lane;
+        const int64_t row0 = q * WT + (int64_t)lane * LC;
+        double acc[NP][SDE_KPM];
+#pragma unroll
+        for (int pp = 0; pp < NP; ++pp)
+#pragma unroll
+            for (int i = 0; i < SDE_KPM; ++i) acc[pp][i] = 0.0;
+        __syncwarp();
+#pragma unroll 1
+        for (int k = 0; k < LC; ++k) {
+            // this lane's row of the row-step
+            const int64_t pos = base + k * 32;
+            const uint8_t f0 = a.flags[pos];
+            const bool live = f0 != 0xff && !(f0 & ROW_LAST);      // ID(i) == ID(i+1), nllk_sde.hpp:79
+            const int64_t npos = (k < LC - 1) ? pos + 32 : row_pos(row0 + k + 1);
+            uint8_t f1 = 0;
+            double d_t = 1.0, z0[ND], z1[ND];
+#pragma unroll
+            for (int dd = 0; dd < ND; ++dd) { z0[dd] = 0.0; z1[dd] = 0.0; }
+            if (live) {
+                f1 = a.flags[npos];
+                d_t = a.dt[pos];
+#pragma unroll
+                for (int dd = 0; dd < ND; ++dd) {
+                    z0[dd] = a.obs[(size_t)dd * a.X.n_pad + pos];
+                    z1[dd] = a.obs[(size_t)dd * a.X.n_pad + npos];
+                }
+            }
+            mbar_wait(bar, phase);
+            phase ^= 1u;
+            const double* v = stage + lane;
+            double eta[NP];
+            {
+                const double* vp = v;
+                const double* tp = th;
+#pragma unroll
+                for (int pp = 0; pp < NP; ++pp) {
+                    double e0 = 0.0, e1 = 0.0;
+                    SSDE_SLOT_GROUPS(kp[pp], if (i & 1) e1 = fma(vp[i * 32], tp[i], e1); else e0 = fma(vp[i * 32], tp[i], e0))
+                    eta[pp] = e0 + e1;
+                    vp += kp[pp] * 32;
+                    tp += kp[pp];
+                }
+            }
+            // transpose the row-step: xT[row = lane][slot]
+            for (int j = 0; j < S; ++j) sm.xT[warp][lane][j] = v[j * 32];
+            __syncwarp();
+            if (lane == 0 && k + 1 < LC) {                         // the staging buffer is free again
+                fence_proxy_async();
+                mbar_expect_tx(bar, bytes);
+                tma_load_1d(stage, blk + (size_t)(k + 1) * S * 32, bytes, bar);
+            }
+            // exact second derivatives of the row's nllk with respect to its predictors
+            {
+                DN e[NP], eb[NP], llk(0.0);
+#pragma unroll
+                for (int pp = 0; pp < NP; ++pp) { e[pp] = DN(eta[pp]); e[pp].d[pp] = 1.0; eb[pp] = DN(0.0); }
+                if (live) sde_row<MODEL, ND, DN>(e, d_t, (unsigned)((f0 | f1) >> 3), [&](int dd, int nx) { return nx ? z1[dd] : z0[dd]; }, llk, eb);
+#pragma unroll
+                for (int pp = 0; pp < NP; ++pp)
+#pragma unroll
+                    for (int qq = 0; qq < NP; ++qq) sm.W[warp][lane][pp * NP + qq] = live ? eb[pp].d[qq] : 0.0;
+            }
+            __syncwarp();
+            // column j' = lane of the warp-tile's X' W X
+            if (lane < S) {
+#pragma unroll 2
+                for (int r = 0; r < 32; ++r) {
+                    const double* xr = sm.xT[warp][r];
+                    const double* wr = sm.W[warp][r];
+                    const double xq = xr[lane];
+#pragma unroll
+                    for (int pp = 0; pp < NP; ++pp) {
+                        const double wx = wr[pp * NP + my_q] * xq;
+                        const double* xp = xr + off[pp];
+                        SSDE_SLOT_GROUPS(kp[pp], acc[pp][i] = fma(xp[i], wx, acc[pp][i]))
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        // add column j' to the accumulators
+        if (lane < S) {
+            const int hq = hidx[lane];
+#pragma unroll
+            for (int pp = 0; pp < NP; ++pp) {
+                SSDE_SLOT_GROUPS(kp[pp], {
+                    const int j = off[pp] + i;
+                    const int hj = hidx[j];
+                    const double x = acc[pp][i];
+                    if (x != 0.0) {
+                        if (hj >= 0 && hq >= 0) atomicAdd(sm.hot + hj * SDE_HESS_HOT + hq, x);
+                        else atomicAdd(hess + (size_t)my_col * p + __ldg(cols + j), x);
+                    }
+                })
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < hh.n * hh.n; i += SDE_NT) {
+        const int r = i / hh.n, c = i % hh.n;
+        const double x = sm.hot[r * SDE_HESS_HOT + c];
+        if (x != 0.0) atomicAdd(hess + (size_t)hh.cols[c] * p + hh.cols[r], x);
+    }
+}
+#undef SSDE_SLOT_GROUPS
+
 // max slots per warp-tile and "every warp-tile is uniform" (device-built designs are checked on the device)
 __global__ void design_shape_kernel(const WtDesc* __restrict__ desc, int64_t nwt, int* __restrict__ out) {
     int smax = 0, nonuni = 0, kpmax = 0;

@@ -94,6 +94,8 @@ struct ssde_handle {
     bool sde_stream = false;         // BM / OU: every warp-tile is uniform with <= SDE_SMAX slots -> sde_stream_kernel
     int grid_stream = 0;
     HotRanges hot{};                 // columns whose gradient entries get per-CTA shared-memory accumulators
+    HessHot hess_hot{};              // ... and whose Hessian entries do (sde_hess_kernel)
+    int grid_hess = 0;
     double* h_pinned = nullptr;      // pinned host staging: par in, out back
     unsigned epoch = 0;
     int ntiles_f = 0, ntiles_b = 0, grid_lp = 0, grid_f = 0, grid_b = 0;
@@ -352,6 +354,20 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinArgs a) {
         a.out[0] = value(nllk);
         a.out[1 + a.npar] = (double)(*a.error);
     }
+}
+
+// hess[(p_fe + r), (p_fe + c)] += exp(log_lambda_i) S[r, c] for the rows r of smooth i (one thread per row of S)
+__global__ void hess_penalty_kernel(const double* __restrict__ par, int o_ll, int n_s, const int32_t* __restrict__ sm_off,
+                                    const uint32_t* __restrict__ S_rowptr, const uint32_t* __restrict__ S_col,
+                                    const double* __restrict__ S_val, int p_fe, int p_re, double* __restrict__ hess) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= p_re) return;
+    int i = 0;
+    while (i + 1 < n_s && r >= sm_off[i + 1]) ++i;
+    const double lam = exp(par[o_ll + i]);
+    const size_t p = (size_t)p_fe + p_re;
+    for (uint32_t k = S_rowptr[r]; k < S_rowptr[r + 1]; ++k)
+        atomicAdd(hess + (size_t)(p_fe + (int)S_col[k]) * p + (p_fe + r), lam * S_val[k]);
 }
 
 // dir = e_j
@@ -743,6 +759,9 @@ int setup_penalty(ssde_handle* h, const ssde_triplet& S, int n_smooth, const int
                     if (ncol_re[i] <= 64) add(h->p_fe + off[i], h->p_fe + off[i + 1]);
         }
     }
+    h->hess_hot.n = 0;
+    for (int r = 0; r < h->hot.n; ++r)
+        for (int c = h->hot.lo[r]; c < h->hot.hi[r] && h->hess_hot.n < SDE_HESS_HOT; ++c) h->hess_hot.cols[h->hess_hot.n++] = c;
     int rc;
     if ((rc = dev_upload(h->S_rowptr, rp, err))) return rc;
     if ((rc = dev_upload(h->S_col, cols, err))) return rc;
@@ -800,7 +819,8 @@ int sde_grid(ssde_handle* h) {
     constexpr int NP = (MODEL == MODEL_BM) ? ND + 1 : ND + 2;
     int rc = max_grid(sde_fused_kernel<MODEL, ND>, SDE_NT, sizeof(SdeSmem<NP>), h->num_sms, h->err, h->grid_lp);
     if (rc) return rc;
-    return max_grid(sde_stream_kernel<MODEL, ND>, SDE_NT, sizeof(SdeStreamSmem), h->num_sms, h->err, h->grid_stream);
+    if ((rc = max_grid(sde_stream_kernel<MODEL, ND>, SDE_NT, sizeof(SdeStreamSmem), h->num_sms, h->err, h->grid_stream))) return rc;
+    return max_grid(sde_hess_kernel<MODEL, ND>, SDE_NT, sizeof(SdeHessSmem<NP>), h->num_sms, h->err, h->grid_hess);
 }
 
 // allocate the per-evaluation work buffers once the data are on the device
@@ -872,6 +892,7 @@ int finish_setup(ssde_handle* h) {
         if (rc) return rc;
         h->grid_lp = (int)std::max<int64_t>(1, std::min<int64_t>(h->grid_lp, h->ntiles_lp));
         h->grid_stream = (int)std::max<int64_t>(1, std::min<int64_t>(h->grid_stream, h->ntiles_lp));
+        h->grid_hess = (int)std::max<int64_t>(1, std::min<int64_t>(h->grid_hess, h->ntiles_lp));
         if ((rc = dev_alloc<double>(h->block_llk, std::max(h->grid_lp, h->grid_stream), err))) return rc;
         // streaming kernel: only if every warp-tile of the design is uniform with <= SDE_SMAX slots
         DevBuf shape;
@@ -1680,6 +1701,51 @@ int ssde_hess_cols_device(ssde_handle* h, const double* d_par, int first, int co
     }
     h->last_launches = launches;
     if (h->timed) CUDA_TRY(cudaEventRecord(h->ev1, st));
+    return SSDE_OK;
+}
+
+int ssde_hess_theta_device(ssde_handle* h, const double* d_par, double* d_hess, void* stream) {
+    if (!h || !d_par || !d_hess) return SSDE_ERR_BAD_ARG;
+    std::string& err = h->err;
+    if (is_kalman(h->model) || h->n_dec > 0 || !h->sde_stream) {
+        err = "the one-pass X'WX Hessian exists for BM / OU without decay terms and designs with uniform warp-tiles "
+              "(<= 32 slots, <= 12 per SDE parameter); use ssde_hess_cols_device (tangent passes) otherwise";
+        return SSDE_ERR_UNSUPPORTED;
+    }
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    const int p = h->p_fe + h->p_re;
+    h->last_launches = 0;
+    h->pcount = 0;
+    int rc;
+    if ((rc = eval_prologue(h, d_par, nullptr, 0, st))) return rc;
+    CUDA_TRY(cudaMemsetAsync(d_hess, 0, sizeof(double) * (size_t)p * p, st));
+    SdeArgs a;
+    a.X = design_of(h);
+    a.theta = Theta{h->theta.as<double>(), nullptr};
+    a.obs = h->obs.as<double>(); a.dt = h->dt.as<double>(); a.flags = h->flags.as<uint8_t>();
+    a.want_grad = 0; a.grad_theta = nullptr; a.p_theta = p; a.block_llk = nullptr; a.ntiles = h->ntiles_lp;
+    mark(h, st, "sde_hess");
+    auto launch = [&](auto kern, size_t smem) {
+        kern<<<h->grid_hess, SDE_NT, smem, st>>>(a, h->hess_hot, d_hess);
+    };
+    if (h->model == SSDE_BM) {
+        if (h->n_dim == 1) launch(sde_hess_kernel<MODEL_BM, 1>, sizeof(SdeHessSmem<2>));
+        else if (h->n_dim == 2) launch(sde_hess_kernel<MODEL_BM, 2>, sizeof(SdeHessSmem<3>));
+        else launch(sde_hess_kernel<MODEL_BM, 3>, sizeof(SdeHessSmem<4>));
+    } else {
+        if (h->n_dim == 1) launch(sde_hess_kernel<MODEL_OU, 1>, sizeof(SdeHessSmem<3>));
+        else launch(sde_hess_kernel<MODEL_OU, 2>, sizeof(SdeHessSmem<4>));
+    }
+    CUDA_TRY(cudaGetLastError());
+    // smoothing penalty: lambda_i S_i on the coeff_re block (nllk_sde.hpp:118-119), added by the shard that owns it
+    if (h->has_smooth && h->add_penalty && h->include_penalty) {
+        mark(h, st, "hess_penalty");
+        hess_penalty_kernel<<<std::max((h->p_re + 127) / 128, 1), 128, 0, st>>>(
+            d_par, h->o_ll, h->n_s, h->sm_off.as<int32_t>(), h->S_rowptr.as<uint32_t>(), h->S_col.as<uint32_t>(),
+            h->S_val.as<double>(), h->p_fe, h->p_re, d_hess);
+        CUDA_TRY(cudaGetLastError());
+    }
     return SSDE_OK;
 }
 

@@ -211,6 +211,38 @@ class Engine:
                                              C.c_void_p(d_hess_ptr), C.c_void_p(stream_ptr or 0))
         self._check(rc)
 
+    def hess_theta_device(self, d_par_ptr, d_hess_ptr, stream_ptr=None):
+        """BM / OU: Hessian of the penalised objective w.r.t. theta = [coeff_fe | coeff_re] in ONE pass over the
+        design (X' W X + lambda S), into a [p_theta x p_theta] device buffer (ssde_hess_theta_device)."""
+        self._check(self._lib.ssde_hess_theta_device(self._h, C.c_void_p(d_par_ptr), C.c_void_p(d_hess_ptr), C.c_void_p(stream_ptr or 0)))
+
+    def supports_hess_theta(self):
+        """True for BM / OU handles without decay terms whose design the one-pass Hessian kernel handles."""
+        if "log_sigma_obs" in self.layout or "log_decay" in self.layout:
+            return False
+        import torch
+        dev = torch.device("cuda", self._lib.ssde_device(self._h))
+        p = self.layout["coeff_fe"][1] + self.layout["coeff_re"][1]
+        d_par = torch.zeros(self.n_par, dtype=torch.float64, device=dev)
+        H = torch.zeros((p, p), dtype=torch.float64, device=dev)
+        torch.cuda.synchronize(dev)
+        rc = self._lib.ssde_hess_theta_device(self._h, C.c_void_p(d_par.data_ptr()), C.c_void_p(H.data_ptr()), C.c_void_p(0))
+        torch.cuda.synchronize(dev)
+        return rc == 0
+
+    def hess_theta(self, par):
+        """Host convenience: the same matrix as a numpy array."""
+        import torch
+        dev = torch.device("cuda", self._lib.ssde_device(self._h))
+        p = self.layout["coeff_fe"][1] + self.layout["coeff_re"][1]
+        d_par = torch.as_tensor(np.ascontiguousarray(par, dtype=np.float64), device=dev)
+        H = torch.zeros((p, p), dtype=torch.float64, device=dev)
+        torch.cuda.synchronize(dev)
+        self.hess_theta_device(d_par.data_ptr(), H.data_ptr())
+        torch.cuda.synchronize(dev)
+        self.check()
+        return H.cpu().numpy().T.copy()              # column-major on the device
+
     def eval_device(self, d_par_ptr, d_out_ptr, order=1, stream_ptr=None):
         """Asynchronous evaluation on device buffers (raw pointers, e.g. tensor.data_ptr())."""
         rc = self._lib.ssde_eval_device(self._h, C.c_void_p(d_par_ptr), int(order),

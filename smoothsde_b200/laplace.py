@@ -212,6 +212,204 @@ class LoopLaplace:
         pass
 
 
+class OnePassLaplace:
+    """Laplace marginal of the BM / OU models with H_bb from ONE pass over the design
+    (``ssde_hess_theta_device``: X' W X + lambda S with exact per-row second-derivative blocks) instead
+    of n_b tangent passes -- what makes a random intercept per track (``s(ID, bs = "re")``,
+    R/sde.R:412-421; configs[1]: 146, configs[4]: 8210 random effects) tractable.  One engine handle on
+    one GPU; the n_b x n_b Cholesky factorisation, solves and log-determinant run on the device
+    (torch.linalg, i.e. cuSOLVER -- a plain library factorisation of the penalty block, as in
+    ssde_laplace.cu).
+
+    Value:    f(theta) = g(theta, b_hat) + 1/2 log det H_bb - n_b/2 log(2 pi), inner Newton with the exact
+              H_bb (chord iterations with the previous factor first, as DeviceLaplace).
+    Gradient: d f / d theta = g_theta(theta, b_hat)  [envelope theorem: g_b = 0 at the mode]
+                              + d/d theta [1/2 log det H_bb(theta, b_hat(theta))],
+              the second term by central differences over the non-random parameters with b_hat re-solved
+              (one or two Newton steps from the mode) -- 2 x (number of non-random parameters) Hessian
+              passes, independent of n_b, where the z_j-directional recipe of DeviceLaplace would need
+              4 n_b tangent passes."""
+
+    def __init__(self, engine, max_newton=50, grad_tol=1e-8, fd_step=1e-4):
+        import torch
+        self.engine, self._torch = engine, torch
+        self.o_re, self.nb = engine.layout["coeff_re"]
+        self.p_fe = engine.layout["coeff_fe"][1]
+        self.p = self.p_fe + self.nb
+        self.np_full = engine.n_par
+        self.dev = torch.device("cuda", engine._lib.ssde_device(engine._h))
+        self.max_newton, self.grad_tol, self.fd_step = max_newton, grad_tol, fd_step
+        self._H = torch.zeros((self.p, self.p), dtype=torch.float64, device=self.dev)
+        self._par = torch.zeros(self.np_full, dtype=torch.float64, device=self.dev)
+        self._out = torch.zeros(self.np_full + 2, dtype=torch.float64, device=self.dev)
+        self._L = None                     # Cholesky factor of H_bb at the previous mode (device)
+        self.info = None
+        # one non-default torch stream for the engine's kernels AND the torch linear algebra, so that they
+        # are ordered on the device (the C ABI treats a NULL stream as the handle's own stream)
+        self.stream = torch.cuda.Stream(device=self.dev)
+
+    # ---- device helpers -------------------------------------------------------------------------------
+    def _value_grad(self, p_host, order=1):
+        t = self._torch
+        self._par.copy_(t.as_tensor(p_host))
+        try:
+            self.engine.eval_device(self._par.data_ptr(), self._out.data_ptr(), order, self.stream.cuda_stream)
+            out = self._out.cpu().numpy()
+        except L.EngineError as e:
+            if e.code != 5:
+                raise
+            return np.inf, None
+        if out[self.np_full + 1] != 0.0:
+            return np.inf, None
+        return float(out[0]), (out[1:self.np_full + 1].copy() if order >= 1 else None)
+
+    def _factor_bb(self, p_host, ridge_scale=None):
+        """Cholesky factor (device) of H_bb at p_host; None if it is not positive definite.  With
+        `ridge_scale` (a Newton step away from the mode): Levenberg ridge until H_bb + ridge I is."""
+        t = self._torch
+        self._par.copy_(t.as_tensor(p_host))
+        self.engine.hess_theta_device(self._par.data_ptr(), self._H.data_ptr(), self.stream.cuda_stream)
+        Hbb = self._H[self.p_fe:, self.p_fe:]
+        Hs = 0.5 * (Hbb + Hbb.T)
+        Lc, info = t.linalg.cholesky_ex(Hs)
+        if int(info) == 0:
+            return Lc, 0.0
+        if ridge_scale is None:
+            return None, 0.0
+        # Away from the mode the exact W_i of badly fitted rows can make single coordinates concave (a
+        # track's random intercept of tau, say).  First repair only those: a negative diagonal entry is
+        # replaced by its absolute value; then, if needed, a global Levenberg ridge scaled to the diagonal.
+        dg = t.diagonal(Hs)
+        fix = t.where(dg < 0, -2.0 * dg, t.zeros_like(dg))
+        scale = float(dg.abs().max())
+        ridge = 0.0
+        for k in range(24):
+            Lc, info = t.linalg.cholesky_ex(Hs + t.diag(fix + ridge))
+            if int(info) == 0:
+                return Lc, max(ridge, float(fix.max()))
+            ridge = 1e-8 * scale if ridge == 0.0 else ridge * 10.0
+        return None, ridge
+
+    def _solve(self, Lc, g_b):
+        t = self._torch
+        return t.cholesky_solve(t.as_tensor(g_b, device=self.dev)[:, None], Lc)[:, 0].cpu().numpy()
+
+    def _mode(self, p, info):
+        """Inner problem from the starting point p (full vector): returns (p at the mode, value, gradient, factor)."""
+        sl = slice(self.o_re, self.o_re + self.nb)
+        v, g = self._value_grad(p)
+        info["n_value"] += 1
+        if not np.isfinite(v):
+            return p, np.inf, None, None
+        tol = lambda vv: max(self.grad_tol, 1e-12 * abs(vv))
+        if self._L is not None:                               # chord iterations with the previous factor
+            for _ in range(12):
+                gmax = float(np.max(np.abs(g[sl])))
+                if gmax <= tol(v):
+                    break
+                q = p.copy()
+                q[sl] = p[sl] - self._solve(self._L, g[sl])
+                vq, gq = self._value_grad(q)
+                info["n_value"] += 1
+                if not np.isfinite(vq) or vq > v + 1e-14 * abs(v) or float(np.max(np.abs(gq[sl]))) > 0.5 * gmax:
+                    break
+                p, v, g = q, vq, gq
+        Lc = None
+        for it in range(self.max_newton + 1):
+            gmax = float(np.max(np.abs(g[sl])))
+            info["grad_max"] = gmax
+            done = gmax <= tol(v) or it == self.max_newton
+            # at the mode the exact H_bb must be positive definite (else the Laplace value is undefined);
+            # on the way there a Levenberg ridge keeps the Newton step a descent direction
+            Lc, ridge = self._factor_bb(p, None if done else gmax)
+            info["n_hess"] += 1
+            info["ridge_max"] = max(info.get("ridge_max", 0.0), ridge)
+            if Lc is None:
+                return p, np.inf, None, None
+            if done:
+                info["converged"] = int(gmax <= tol(v))
+                break
+            step = self._solve(Lc, g[sl])
+            slope = float(g[sl] @ step)
+            t_, ok = 1.0, False
+            for _ in range(6 if gmax <= 1e3 * tol(v) else 40):
+                q = p.copy()
+                q[sl] = p[sl] - t_ * step
+                vq, gq = self._value_grad(q)
+                info["n_value"] += 1
+                if np.isfinite(vq) and vq <= v - 1e-4 * t_ * slope + 1e-14 * abs(v):
+                    ok = True
+                    break
+                t_ *= 0.5
+            if not ok:
+                info["converged"] = int(gmax <= 1e3 * tol(v))
+                if ridge != 0.0:                              # the factor in hand is of the ridged matrix
+                    Lc, _ = self._factor_bb(p, None)
+                    info["n_hess"] += 1
+                    if Lc is None:
+                        return p, np.inf, None, None
+                break
+            p, v, g = q, vq, gq
+            info["n_newton"] += 1
+        return p, v, g, Lc
+
+    def eval(self, par_full, order=1):
+        with self._torch.cuda.stream(self.stream):
+            return self._eval(par_full, order)
+
+    def _eval(self, par_full, order):
+        t = self._torch
+        p0 = np.asarray(par_full, dtype=float).copy()
+        info = dict(joint=np.nan, logdet=np.nan, grad_max=np.nan, converged=0, n_newton=0, n_hess=0, n_value=0, n_hvp=0)
+        p, v, g, Lc = self._mode(p0, info)
+        self.info = info
+        if not np.isfinite(v) or Lc is None:
+            return np.inf, (np.full(p0.size, np.nan) if order else None), p0
+        self._L = Lc
+        self._p_mode = p.copy()
+        logdet = float(2.0 * t.log(t.diagonal(Lc)).sum())
+        info["joint"], info["logdet"] = v, logdet
+        val = v + 0.5 * logdet - 0.5 * self.nb * np.log(2 * np.pi)
+        if order == 0:
+            return val, None, p
+        # gradient: envelope part + central differences of the profiled log-determinant
+        grad = g.copy()
+        sl = slice(self.o_re, self.o_re + self.nb)
+        grad[sl] = 0.0
+        outer = [i for i in range(p.size) if not (self.o_re <= i < self.o_re + self.nb)]
+        keepL = self._L
+        for k in outer:
+            h = self.fd_step * max(1.0, abs(p[k]))
+            ld = []
+            for sgn in (+1.0, -1.0):
+                q = p.copy()
+                q[k] += sgn * h
+                sub = dict(n_newton=0, n_hess=0, n_value=0, converged=0, grad_max=np.nan)
+                self._L = keepL
+                _, vq, _, Lq = self._mode(q, sub)
+                info["n_hess"] += sub["n_hess"]
+                info["n_value"] += sub["n_value"]
+                if Lq is None or not np.isfinite(vq):
+                    ld.append(np.nan)
+                else:
+                    ld.append(float(2.0 * t.log(t.diagonal(Lq)).sum()))
+            grad[k] += 0.5 * (ld[0] - ld[1]) / (2 * h)
+        self._L = keepL
+        return val, grad, p
+
+    def hessian_bb(self):
+        """H_bb at the mode of the last eval (recomputed: one pass)."""
+        t = self._torch
+        with t.cuda.stream(self.stream):
+            self._par.copy_(t.as_tensor(self._p_mode))
+            self.engine.hess_theta_device(self._par.data_ptr(), self._H.data_ptr(), self.stream.cuda_stream)
+            Hbb = self._H[self.p_fe:, self.p_fe:]
+            return (0.5 * (Hbb + Hbb.T)).cpu().numpy()
+
+    def close(self):
+        self._H = None
+
+
 class Laplace:
     """The ``fn`` / ``gr`` pair of the ``random = "coeff_re"`` object on top of an ADFun."""
 
@@ -221,8 +419,16 @@ class Laplace:
         if ad._rand.size != size:
             raise NotImplementedError("map on coeff_re together with random = 'coeff_re' is not supported")
         self.b = ad._full0[ad._rand].copy()
-        drv = DeviceLaplace if hasattr(ad.engine, "_h") else LoopLaplace
-        self.driver = drv(ad.engine, **opts)
+        eng = ad.engine
+        drv = DeviceLaplace if hasattr(eng, "_h") else LoopLaplace
+        # BM / OU on one GPU: H_bb = X' W X + lambda S from ONE pass over the design (OnePassLaplace) when the
+        # library supports it for this design; tangent passes (DeviceLaplace) otherwise
+        if hasattr(eng, "_h") and hasattr(eng, "supports_hess_theta") and eng.supports_hess_theta() and not opts.pop("tangent_hessian", False):
+            drv = OnePassLaplace
+            opts = {k: v for k, v in opts.items() if k in ("max_newton", "grad_tol", "fd_step")}
+        else:
+            opts.pop("tangent_hessian", None)
+        self.driver = drv(eng, **opts)
         self._cache = None                                     # (x, value, grad_active)
         self.last = None
 

@@ -200,3 +200,25 @@ def test_device_laplace_warm_start_matches_cold_start():
     assert np.max(np.abs(p_w - p_c)) <= 1e-8
     assert np.max(np.abs(g_w - g_c)) <= 1e-7 * max(1.0, np.max(np.abs(g_c)))
     warm.close(); cold.close(); eng.close()
+
+
+@pytest.mark.parametrize("model,T,m,nd,re_id", [("OU", 8, 300, 1, True), ("BM", 3, 400, 2, False)])
+def test_one_pass_laplace_matches_device_laplace(model, T, m, nd, re_id):
+    """OnePassLaplace (H_bb = X' W X + lambda S from one pass, profiled log-determinant differenced over the
+    outer parameters) against DeviceLaplace (H_bb from tangent passes, third-order term along z_j)."""
+    from smoothsde_b200.laplace import OnePassLaplace
+    dat, par, info = synth.make_problem(model, T, m, n_dim=nd, seed=61 + m, k=6, re_id=re_id, missing_frac=0.05)
+    par = par + 0.02 * np.arange(par.size) / par.size
+    eng = Engine.from_data(dat)
+    ref = DeviceLaplace(eng)
+    f_ref, g_ref, p_ref = ref.eval(par, order=1)
+    one = OnePassLaplace(eng)
+    f, g, p = one.eval(par, order=1)
+    assert one.info["converged"] == 1
+    assert abs(f - f_ref) <= 1e-9 * max(1.0, abs(f_ref)), (f, f_ref)
+    assert np.max(np.abs(p - p_ref)) <= 1e-7                                   # b_hat
+    scale = np.maximum(np.abs(g_ref), 1e-3 * np.max(np.abs(g_ref)))
+    assert np.max(np.abs(g - g_ref) / scale) <= 1e-5, (g, g_ref)
+    H1, H2 = one.hessian_bb(), ref.hessian_bb()
+    assert np.max(np.abs(H1 - H2)) <= 1e-9 * np.max(np.abs(H2))
+    ref.close(); one.close(); eng.close()

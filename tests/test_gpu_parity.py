@@ -288,3 +288,52 @@ def test_nonpositive_innovation_variance_sets_the_numeric_status():
     v, _ = eng.eval(par, order=1)                     # the handle stays usable
     assert np.isfinite(v)
     eng.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# one-pass data-term Hessian of the BM / OU models: X' W X + lambda S (ssde_hess_theta_device)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("model,T,m,nd,re_id,k", [("OU", 6, 300, 1, True, 10), ("OU", 3, 500, 2, False, 8), ("BM", 4, 400, 2, False, 10),
+                                                  ("BM", 2, 700, 3, False, 6), ("OU", 10, 120, 1, True, 5)])
+def test_one_pass_hessian_equals_tangent_pass_hessian(model, T, m, nd, re_id, k):
+    """H = X' W X with the exact per-row second-derivative blocks (DualN through sde_row) against the joint
+    Hessian assembled column by column from tangent passes (itself checked against the reference's
+    reverse-over-forward Hessian in tests/test_gpu_ref.py)."""
+    dat, par, info = synth.make_problem(model, T, m, missing_frac=0.1, n_dim=nd, seed=90 + T + m, re_id=re_id, k=k)
+    eng = Engine.from_data(dat)
+    _, _, H = eng.hessian(par)
+    Ht = eng.hess_theta(par)
+    o_fe, p_fe = eng.layout["coeff_fe"]
+    o_re, p_re = eng.layout["coeff_re"]
+    idx = np.r_[o_fe + np.arange(p_fe), o_re + np.arange(p_re)]
+    ref = H[np.ix_(idx, idx)]
+    assert Ht.shape == ref.shape
+    assert np.max(np.abs(Ht - Ht.T)) <= 1e-12 * np.max(np.abs(ref))
+    assert np.max(np.abs(Ht - ref)) <= 1e-10 * np.max(np.abs(ref)), np.max(np.abs(Ht - ref)) / np.max(np.abs(ref))
+    eng.close()
+
+
+def test_one_pass_hessian_on_the_device_built_ou_shape():
+    """Random intercepts per track, warp-tiles that straddle two tracks (25 slots), p_theta > the hot set."""
+    from smoothsde_b200 import devgen
+    eng, par, info = devgen.make_ou_device(12, 300, device=0)
+    rng = np.random.default_rng(5)
+    par = par.copy()
+    par[:3] = [0.2, 0.1, np.log(1.3)]
+    par[3:7] = [0.3, -0.4, 0.2, 0.5]
+    par[7:] = 0.2 * rng.standard_normal(par.size - 7)
+    _, _, H = eng.hessian(par)
+    Ht = eng.hess_theta(par)
+    o_fe, p_fe = eng.layout["coeff_fe"]
+    o_re, p_re = eng.layout["coeff_re"]
+    idx = np.r_[o_fe + np.arange(p_fe), o_re + np.arange(p_re)]
+    ref = H[np.ix_(idx, idx)]
+    assert np.max(np.abs(Ht - ref)) <= 1e-10 * np.max(np.abs(ref)), np.max(np.abs(Ht - ref)) / np.max(np.abs(ref))
+    with pytest.raises(Exception):
+        dat, p2, _ = synth.make_problem("CTCRW", 2, 50, n_dim=1, seed=1)
+        e2 = Engine.from_data(dat)
+        try:
+            e2.hess_theta(p2)                      # Kalman models: SSDE_ERR_UNSUPPORTED
+        finally:
+            e2.close()
+    eng.close()
