@@ -422,6 +422,25 @@ def measure_ou(name, n_tracks, n_steps, args, ctx):
     kernels = dict(eng.last_kernel_times())
     eng.set_profile(False)
     launches = eng.last_eval_launches
+    # the one-pass data-term Hessian X'WX + lambda S of this rank's rows (the Laplace inner problem's H_bb)
+    p_theta = info["p_fe"] + info["p_re"]
+    hess_ms = None
+    try:
+        Hbuf = torch.zeros((p_theta, p_theta), dtype=torch.float64, device=dev)
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        eng.hess_theta_device(par_dev.data_ptr(), Hbuf.data_ptr(), stream)
+        torch.cuda.synchronize()
+        h0.record()
+        for _ in range(3):
+            eng.hess_theta_device(par_dev.data_ptr(), Hbuf.data_ptr(), stream)
+        h1.record()
+        torch.cuda.synchronize()
+        hess_ms = h0.elapsed_time(h1) / 3
+        launches_h = eng.last_eval_launches
+        del Hbuf
+    except Exception as e:                       # noqa: BLE001 -- reported, not fatal for the throughput line
+        hess_ms = f"failed: {e}"
+        launches_h = 0
     parity = n1_parity(f"{name}:{n_tracks}x{n_steps}", args, world, rank, first[0], first[1:npar + 1])
     stored_b = 23 * 8 + 8 + 8 + 1
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -431,7 +450,8 @@ def measure_ou(name, n_tracks, n_steps, args, ctx):
                        f"p_re = {info['p_re']}", "ms_per_step": ms_step, "value": n_total / (ms_step * 1e-3), "unit": UNIT,
            "e2e": {"value": n_total * args.steps / float(e2e_s), "unit": UNIT, "h2d_bytes_per_step": 8 * npar,
                    "d2h_bytes_per_step": 8 * (npar + 1), "call": "TrackShardedEngine.eval"},
-           "kernels_ms": kernels, "gpu_launches": launches * args.steps, "nllk": float(first[0]), "parity_vs_n1": parity,
+           "kernels_ms": kernels, "gpu_launches": launches * args.steps + 4 * launches_h, "nllk": float(first[0]), "parity_vs_n1": parity,
+           "hessian_onepass_ms": hess_ms,
            "roofline": {"kernel": kmain, "launch_ms": kernels[kmain], "stored_bytes_per_obs": stored_b,
                         "alg_bytes_per_obs": devgen.alg_bytes_per_obs(1, 3, 23),
                         "dram_frac": stored_b * info["n"] / (kernels[kmain] * 1e-3) / 1e9 / peak,
