@@ -90,13 +90,29 @@ SSDE_HD StepParT<R> make_step(const R& tau, const R& e, const R& s2, double dt) 
 
 // Natural-scale transform of one linear-predictor row, nllk_ctcrw.hpp:152-156:
 //   tau = exp(eta_tau), nu = exp(eta_nu), sigma = 2 nu / sqrt(pi tau)  =>  s2 = 4 nu^2/(pi tau)
+// SSDE_FAST_TRANSFORM=1 (experiment, not the default): 1/tau = exp(-eta_tau) instead of a division
+// that has to wait for tau, and the branch-free exp (dual.cuh) -- three independent exponentials
+// that the compiler can interleave, then the one that needs 1/tau; every factor within ~1 ulp of
+// the expression below.  Measured on the B200 at 1.024e8 rows: forward kernel 5.59 ms against 5.37 ms
+// with the library calls (the extra live values cost 100 B more spills per thread).
+#ifndef SSDE_FAST_TRANSFORM
+#define SSDE_FAST_TRANSFORM 0
+#endif
 template <class R>
 SSDE_HD void transform_row(const R& eta_tau, const R& eta_nu, double dt, R& tau, R& e, R& s2) {
+#if SSDE_FAST_TRANSFORM
+    tau = exp_bf(eta_tau);
+    const R itau = exp_bf(-eta_tau);
+    const R nu = exp_bf(eta_nu);
+    s2 = (4.0 / 3.14159265358979323846) * nu * nu * itau;
+    e = exp_bf(-dt * itau);
+#else
     tau = exp(eta_tau);
     const R nu = exp(eta_nu);
     const R itau = 1.0 / tau;
     s2 = (4.0 / 3.14159265358979323846) * nu * nu * itau;
     e = exp(-dt * itau);
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------

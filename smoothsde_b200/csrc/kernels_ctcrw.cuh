@@ -48,6 +48,15 @@
 #ifndef SSDE_FWD_EXC_SMEM
 #define SSDE_FWD_EXC_SMEM 0
 #endif
+// 1: the forward kernel forms a row's predictors in one branch-free pass over the staged values
+// against a dense per-warp coefficient table (design.cuh, fill_theta_matrix / row_eta_dense)
+#ifndef SSDE_ETA_DENSE
+#define SSDE_ETA_DENSE 1
+#endif
+// 1: a warp keeps its theta cache when the next warp-tile uses the same column list
+#ifndef SSDE_THETA_REUSE
+#define SSDE_THETA_REUSE 1
+#endif
 
 namespace ssde {
 
@@ -160,6 +169,7 @@ struct FwdSmem {
     double tagg[2][ES];              // barrier between two tiles is the one that hands out the ticket
     R misc[2][16];
     R th[NT / 32][TH_CACHE];
+    double thm[NT / 32][STAGE_SLOTS * MAX_NP];   // dense coefficient table of the warp-tile (R = double)
     uint64_t bar[NT / 32];
     int ticket[2];
     int early[2];                    // the tile aggregate was published before the barrier
@@ -185,6 +195,8 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(KalmanArgs<typename
     WarpStage st;
     stage_init(st, sm.stage[warp], &sm.bar[warp]);
     mbar_fence_init();
+    constexpr bool DENSE_ETA = SSDE_ETA_DENSE && std::is_same<R, double>::value;
+    ThetaKey tkey;
 
     // Tickets are taken just in time (a tile reserved ahead of time by a busy CTA would stall the
     // look-back of every later tile).
@@ -200,13 +212,16 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(KalmanArgs<typename
         const int64_t q = (int64_t)tile * NWARP + warp;
         const int64_t base = q * WT + lane;
         const int64_t row0 = q * WT + (int64_t)lane * LC;
-        const WtViewT<R> w = open_warptile<R>(a.X, q, a.theta, sm.th[warp], true);
+        const WtViewT<R> w = open_warptile<R>(a.X, q, a.theta, sm.th[warp], true, SSDE_THETA_REUSE ? &tkey : nullptr);
+        if constexpr (DENSE_ETA) {
+            if (w.staged && (!SSDE_THETA_REUSE || tkey.fresh)) fill_theta_matrix(w, sm.thm[warp]);
+        }
         if (w.staged && lane == 0) {
             stage_issue(w, st, 0);
 #if SSDE_FWD_PREFETCH == 1
-            prefetch_l2(w.blk + (size_t)w.S * 32, (unsigned)((LC - 1) * w.S * 32 * 8));
+            prefetch_l2(w.blk + (size_t)w.SV * 32, (unsigned)((LC - 1) * w.SV * 32 * 8));
 #elif SSDE_FWD_PREFETCH == 2
-            prefetch_l2(w.blk + (size_t)w.S * 32, (unsigned)(2 * w.S * 32 * 8));
+            prefetch_l2(w.blk + (size_t)w.SV * 32, (unsigned)(2 * w.SV * 32 * 8));
 #endif
         }
         const unsigned long long fl = load_flags8(a.flags, base);
@@ -233,12 +248,13 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(KalmanArgs<typename
             for (int p = 0; p < NP; ++p) r.eta[p] = 0.0;
             if (w.staged) {
                 stage_wait(st);
-                row_eta_staged<NP>(w, st, r.eta);
+                if constexpr (DENSE_ETA) row_eta_dense<NP>(w, st.buf, sm.thm[warp], r.eta);
+                else row_eta_staged<NP>(w, st, r.eta);
                 __syncwarp();
                 if (lane == 0 && k + 1 < LC) {
                     stage_issue(w, st, k + 1);
 #if SSDE_FWD_PREFETCH == 2
-                    if (k + 3 < LC) prefetch_l2(w.blk + (size_t)(k + 3) * w.S * 32, (unsigned)(w.S * 32 * 8));
+                    if (k + 3 < LC) prefetch_l2(w.blk + (size_t)(k + 3) * w.SV * 32, (unsigned)(w.SV * 32 * 8));
 #endif
                 }
             } else if (step) {
@@ -301,12 +317,13 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(KalmanArgs<typename
             R eta[NP];
             if (w.staged) {
                 stage_wait(st);
-                row_eta_staged<NP>(w, st, eta);
+                if constexpr (DENSE_ETA) row_eta_dense<NP>(w, st.buf, sm.thm[warp], eta);
+                else row_eta_staged<NP>(w, st, eta);
                 __syncwarp();
                 if (lane == 0 && k + 1 < LC) {
                     stage_issue(w, st, k + 1);
 #if SSDE_FWD_PREFETCH == 2
-                    if (k + 3 < LC) prefetch_l2(w.blk + (size_t)(k + 3) * w.S * 32, (unsigned)(w.S * 32 * 8));
+                    if (k + 3 < LC) prefetch_l2(w.blk + (size_t)(k + 3) * w.SV * 32, (unsigned)(w.SV * 32 * 8));
 #endif
                 }
             } else if (step) {
@@ -573,7 +590,7 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_bwd_kernel(KalmanArgs<typename
         const WtViewT<R> w = open_warptile<R>(a.X, q, a.theta, sm.th[warp], !mu0);
         const unsigned long long fl = load_flags8(a.flags, base);
 #if SSDE_BWD_PREFETCH == 2
-        if (lane == 0 && !a.summary) prefetch_l2(w.blk, (unsigned)(LC * w.S * 32 * 8));
+        if (lane == 0 && !a.summary) prefetch_l2(w.blk, (unsigned)(LC * w.SV * 32 * 8));
 #endif
 
         // (1) recompute the forward states of this thread's rows from its checkpoint and compose
@@ -661,7 +678,7 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_bwd_kernel(KalmanArgs<typename
 #if SSDE_BWD_PREFETCH == 1
         // the transposed design product at the end of the tile streams LC x S x 32 values of this
         // warp-tile from HBM: ask for them now so that they wait in L2 when the sweep is done
-        if (lane == 0) prefetch_l2(w.blk, (unsigned)(LC * w.S * 32 * 8));
+        if (lane == 0) prefetch_l2(w.blk, (unsigned)(LC * w.SV * 32 * 8));
 #endif
         // (4) adjoint entering this thread's last row, then the reverse sweep over its rows
         Ad g = M::load_adj([&](int i) { return sm.misc[par][i]; });

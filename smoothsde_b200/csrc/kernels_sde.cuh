@@ -594,11 +594,12 @@ __global__ void __launch_bounds__(SDE_NT, 2) sde_hess_kernel(SdeArgs a, HessHot 
 
 // max slots per warp-tile and "every warp-tile is uniform" (device-built designs are checked on the device)
 __global__ void design_shape_kernel(const WtDesc* __restrict__ desc, int64_t nwt, int* __restrict__ out) {
-    int smax = 0, nonuni = 0, kpmax = 0;
+    int smax = 0, nonuni = 0, kpmax = 0, alias = 0;
     for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nwt; q += (int64_t)gridDim.x * blockDim.x) {
         const WtDesc d = desc[q];
         const int S = slots_of(d.kmax);
         smax = max(smax, S);
+        if (d.flags & WT_ALIAS_MASK) alias = 1;
 #pragma unroll
         for (int p = 0; p < MAX_NP; ++p) kpmax = max(kpmax, (int)((d.kmax >> (8 * p)) & 255u));
         if (S > 0 && !(d.flags & WT_UNIFORM)) nonuni = 1;
@@ -606,6 +607,7 @@ __global__ void design_shape_kernel(const WtDesc* __restrict__ desc, int64_t nwt
     atomicMax(out + 0, smax);
     if (nonuni) atomicOr(out + 1, 1);
     atomicMax(out + 2, kpmax);
+    if (alias) atomicOr(out + 3, 1);             // aliased parameters: the scan kernels of the Kalman models only
 }
 
 // ---------------------------------------------------------------------------------------------

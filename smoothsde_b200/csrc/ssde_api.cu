@@ -528,14 +528,19 @@ struct V2Host {
     RawVec<uint32_t> col;
 };
 
-int build_v2(const Packed& pk, int64_t n, int64_t n_pad, int n_par, V2Host& out, std::string& err) {
+// allow_alias: parameters whose value slots are identical in every row of a uniform warp-tile
+// (tau ~ s(time), nu ~ s(time)) store them once (design.cuh, alias_of) -- the scan kernels of the
+// Kalman models understand that, the nllk_sde kernels do not.
+int build_v2(const Packed& pk, int64_t n, int64_t n_pad, int n_par, bool allow_alias, V2Host& out, std::string& err) {
     const int64_t nwt = n_pad / WT;
     out.desc.assign((size_t)nwt, WtDesc{0, 0, 0u, WT_UNIFORM});
     const int nt = host_threads(n * 8);
     PhaseTimer pt;
+    if (std::getenv("SSDE_NO_ALIAS")) allow_alias = false;      // A/B runs of the two layouts
     // (1) per warp-tile: union of columns / max count per parameter -> slots, uniform or not
     std::vector<std::vector<uint32_t>> wcols((size_t)nwt);      // uniform warp-tiles: their column list
-    std::vector<uint64_t> wS((size_t)nwt, 0);
+    std::vector<uint64_t> wS((size_t)nwt, 0);                   // column slots
+    std::vector<uint64_t> wSV((size_t)nwt, 0);                  // value slots (< column slots with aliases)
     parallel_ranges(nwt, nt, [&](int, int64_t qlo, int64_t qhi) {
         std::vector<std::vector<uint32_t>> U((size_t)n_par);
         for (int64_t q = qlo; q < qhi; ++q) {
@@ -573,6 +578,33 @@ int build_v2(const Packed& pk, int64_t n, int64_t n_pad, int n_par, V2Host& out,
             d.kmax = kw;
             d.flags = uniform ? WT_UNIFORM : 0u;
             wS[(size_t)q] = S;
+            if (uniform && allow_alias) {
+                // parameter p is an alias of t < p when, in every row, both have the same number of
+                // nonzeros, with bit-identical values, at the same slot positions of their column lists
+                for (int p = 1; p < n_par; ++p) {
+                    const size_t kp = U[(size_t)p].size();
+                    if (kp == 0) continue;
+                    for (int t = 0; t < p; ++t) {
+                        if (alias_of(d.flags, t) >= 0 || U[(size_t)t].size() != kp) continue;
+                        bool same = true;
+                        for (int64_t r = r0; r < r1 && same; ++r) {
+                            const uint32_t cw = pk.cnt[(size_t)r];
+                            const uint32_t cp = (cw >> (8 * p)) & 255u, ct = (cw >> (8 * t)) & 255u;
+                            if (cp != ct) { same = false; break; }
+                            uint32_t op = pk.rowptr[(size_t)r], ot = op;
+                            for (int pp = 0; pp < p; ++pp) op += (cw >> (8 * pp)) & 255u;
+                            for (int pp = 0; pp < t; ++pp) ot += (cw >> (8 * pp)) & 255u;
+                            for (uint32_t j = 0; j < cp; ++j) {
+                                const size_t sp = (size_t)(std::lower_bound(U[(size_t)p].begin(), U[(size_t)p].end(), pk.col[op + j]) - U[(size_t)p].begin());
+                                const size_t st = (size_t)(std::lower_bound(U[(size_t)t].begin(), U[(size_t)t].end(), pk.col[ot + j]) - U[(size_t)t].begin());
+                                if (sp != st || std::memcmp(&pk.val[op + j], &pk.val[ot + j], sizeof(double)) != 0) { same = false; break; }
+                            }
+                        }
+                        if (same) { d.flags |= (uint32_t)(t + 1) << (WT_ALIAS_SHIFT + 2 * p); break; }
+                    }
+                }
+            }
+            wSV[(size_t)q] = (uint64_t)value_slots_of(d.kmax, d.flags);
             if (uniform) {
                 auto& c = wcols[(size_t)q];
                 c.reserve(S);
@@ -591,7 +623,7 @@ int build_v2(const Packed& pk, int64_t n, int64_t n_pad, int n_par, V2Host& out,
         d.col_off = 0;
         const uint64_t S = wS[(size_t)q];
         if (S == 0 && !(q * WT < n)) continue;
-        nval += S * WT;
+        nval += wSV[(size_t)q] * WT;
         if (d.flags & WT_UNIFORM) {
             if (prev >= 0 && wcols[(size_t)q] == wcols[(size_t)prev]) {
                 d.col_off = out.desc[(size_t)prev].col_off;
@@ -620,8 +652,11 @@ int build_v2(const Packed& pk, int64_t n, int64_t n_pad, int n_par, V2Host& out,
             const WtDesc& d = out.desc[(size_t)q];
             const bool uniform = (d.flags & WT_UNIFORM) != 0;
             const size_t S = (size_t)wS[(size_t)q];
+            const size_t SV = (size_t)wSV[(size_t)q];               // value slots per row (aliased parameters store none)
+            uint64_t vofs = 0;
+            value_slots_of(d.kmax, d.flags, &vofs);
             double* v = out.val.data() + d.val_off;
-            std::memset(v, 0, sizeof(double) * S * WT);              // explicit zeros for rows that lack a column of the union
+            std::memset(v, 0, sizeof(double) * SV * WT);             // explicit zeros for rows that lack a column of the union
             uint32_t* c = nullptr;
             const uint32_t* ulist = nullptr;     // this warp-tile's column list (parameter-major, ascending per parameter)
             if (uniform) {
@@ -641,12 +676,13 @@ int build_v2(const Packed& pk, int64_t n, int64_t n_pad, int n_par, V2Host& out,
                 for (int p = 0; p < n_par; ++p) {
                     const uint32_t cntp = (pk.cnt[(size_t)r] >> (8 * p)) & 255u;
                     const size_t kp = (d.kmax >> (8 * p)) & 255u;
-                    for (uint32_t j = 0; j < cntp; ++j) {
+                    const size_t vslot0 = (size_t)((vofs >> (16 * p)) & 0xffffull);
+                    for (uint32_t j = 0; j < cntp && alias_of(d.flags, p) < 0; ++j) {
                         size_t slot;
-                        if (uniform) slot = slot0 + (size_t)(std::lower_bound(ulist + slot0, ulist + slot0 + kp, pk.col[rp + j]) - (ulist + slot0));
-                        else slot = slot0 + j;
-                        v[((size_t)k * S + slot) * 32 + lane] = pk.val[rp + j];
-                        if (c) c[((size_t)k * S + slot) * 32 + lane] = pk.col[rp + j];
+                        if (uniform) slot = (size_t)(std::lower_bound(ulist + slot0, ulist + slot0 + kp, pk.col[rp + j]) - (ulist + slot0));
+                        else slot = j;
+                        v[((size_t)k * SV + vslot0 + slot) * 32 + lane] = pk.val[rp + j];
+                        if (c) c[((size_t)k * S + slot0 + slot) * 32 + lane] = pk.col[rp + j];
                     }
                     rp += cntp;
                     slot0 += kp;
@@ -896,12 +932,13 @@ int finish_setup(ssde_handle* h) {
         if ((rc = dev_alloc<double>(h->block_llk, std::max(h->grid_lp, h->grid_stream), err))) return rc;
         // streaming kernel: only if every warp-tile of the design is uniform with <= SDE_SMAX slots
         DevBuf shape;
-        if ((rc = dev_alloc<int>(shape, 3, err))) return rc;
-        CUDA_TRY(cudaMemset(shape.p, 0, 3 * sizeof(int)));
+        if ((rc = dev_alloc<int>(shape, 4, err))) return rc;
+        CUDA_TRY(cudaMemset(shape.p, 0, 4 * sizeof(int)));
         design_shape_kernel<<<std::max(1, h->num_sms), 256>>>(h->desc.as<WtDesc>(), h->n_pad / WT, shape.as<int>());
         CUDA_TRY(cudaGetLastError());
-        int sh[3] = {0, 0, 0};
-        CUDA_TRY(cudaMemcpy(sh, shape.p, 3 * sizeof(int), cudaMemcpyDeviceToHost));
+        int sh[4] = {0, 0, 0, 0};
+        CUDA_TRY(cudaMemcpy(sh, shape.p, 4 * sizeof(int), cudaMemcpyDeviceToHost));
+        if (sh[3]) { err = "descriptor flags alias parameters: supported by the Kalman models only"; return SSDE_ERR_BAD_ARG; }
         h->sde_stream = h->n_dec == 0 && sh[0] <= SDE_SMAX && sh[1] == 0 && sh[2] <= SDE_KPM;
     }
     return SSDE_OK;
@@ -1333,7 +1370,7 @@ static int pack_host_impl(const ssde_desc* d, ssde_host_pack* out) {
     if ((rc = pack_design(*d, n_par, pk, err))) return rc;
     V2Host v2;
     const int64_t n_pad = ssde_padded_rows(d->n);
-    if ((rc = build_v2(pk, d->n, n_pad, n_par, v2, err))) return rc;
+    if ((rc = build_v2(pk, d->n, n_pad, n_par, is_kalman(d->model), v2, err))) return rc;
     out->n_pad = n_pad;
     out->n_desc = (int64_t)v2.desc.size(); out->n_val = (int64_t)v2.val.size(); out->n_col = (int64_t)v2.col.size();
     out->desc = (ssde_wt_desc*)std::malloc(sizeof(WtDesc) * std::max<size_t>(v2.desc.size(), 1));
@@ -1509,7 +1546,7 @@ static int create_impl(const ssde_desc* d, ssde_handle** out) {
         if ((rc = dev_upload(h->mu_cols, mc, h->err))) return fail(rc);
     }
     V2Host v2;
-    if ((rc = build_v2(pk, n, n_pad, n_par, v2, h->err))) return fail(rc);
+    if ((rc = build_v2(pk, n, n_pad, n_par, is_kalman(d->model), v2, h->err))) return fail(rc);
     if ((rc = dev_upload(h->desc, v2.desc, h->err))) return fail(rc);
     if ((rc = dev_upload(h->col, v2.col, h->err))) return fail(rc);
     if ((rc = dev_upload(h->val, v2.val, h->err))) return fail(rc);

@@ -99,7 +99,7 @@ class GroupedRNG:
 
 def make_ctcrw_device(n_tracks, n_steps, seed=20260103, device=0, k=10, sigma_obs=0.1,
                       irregular=True, rank=0, world=1, sim_tracks=None, dist_reduce=None,
-                      shard_flags=0, time_shard=False, dist_gather=None):
+                      shard_flags=0, time_shard=False, dist_gather=None, alias=None):
     """Build the rows of `n_tracks` tracks x `n_steps` steps on `device` (this rank's shard of
     `world * n_tracks` tracks; the data set does not depend on `world`, see GroupedRNG).
 
@@ -111,8 +111,13 @@ def make_ctcrw_device(n_tracks, n_steps, seed=20260103, device=0, k=10, sigma_ob
     time_shard: (with sim_tracks) this rank holds slab `rank` of `world` of ONE track of
     world * n_steps rows: its times follow the previous slab's, only rank 0 has the track start,
     only the last rank the track end (SSDE_SHARD_CONT_PREV / CONT_NEXT are set accordingly).
+    alias: store the value slots that tau and nu (and mu1, mu2) share once per row (design.cuh
+    alias flags: 22 column slots, 11 value slots); default on, SSDE_NO_ALIAS=1 gives the plain layout.
     Returns (engine, par, info)."""
+    import os
     import torch
+    if alias is None:
+        alias = not os.environ.get("SSDE_NO_ALIAS")
     dev = torch.device("cuda", device)
     nd = 2
     T, m = n_tracks, n_steps
@@ -230,19 +235,25 @@ def make_ctcrw_device(n_tracks, n_steps, seed=20260103, device=0, k=10, sigma_ob
     lc, wt = int(info4[0]), int(info4[1])
     n_pad = int(L.load().ssde_padded_rows(n))
     nq = n_pad // wt
-    # values: [n, nnz_row] natural -> [q][k][slot][lane]
-    val = torch.zeros((n_pad, nnz_row), dtype=torch.float64, device=dev)
+    # values: [n, value slots] natural -> [q][k][slot][lane].  The two mu intercepts hold the same
+    # numbers, and so do the tau and nu blocks (same smooth of time): with `alias` a row stores
+    # 1 + k values and the descriptor flags say that mu2 reads mu1's slot and nu reads tau's.
+    nval_row = 1 + k if alias else nnz_row
+    o_tau = 1 if alias else 2
+    val = torch.zeros((n_pad, nval_row), dtype=torch.float64, device=dev)
     val[:n, 0] = 1.0
-    val[:n, 1] = 1.0
-    val[:n, 2] = 1.0
-    val[:n, 2 + k] = 1.0
+    val[:n, o_tau] = 1.0
+    if not alias:
+        val[:n, 1] = 1.0
+        val[:n, 2 + k] = 1.0
     for c0 in range(0, n, CH):
         Bz = _bspline_torch(tflat[c0:c0 + CH], k, lo, hi) @ Zt
         c1 = min(c0 + CH, n)
-        val[c0:c1, 3:2 + k] = Bz
-        val[c0:c1, 3 + k:2 + 2 * k] = Bz
+        val[c0:c1, o_tau + 1:o_tau + k] = Bz
+        if not alias:
+            val[c0:c1, 3 + k:2 + 2 * k] = Bz
         del Bz
-    val = val.reshape(nq, 32, lc, nnz_row).permute(0, 2, 3, 1).contiguous().reshape(-1)
+    val = val.reshape(nq, 32, lc, nval_row).permute(0, 2, 3, 1).contiguous().reshape(-1)
     p_fe, p_re = nd + 2, 2 * (k - 1)
     # theta = [coeff_fe (mu1, mu2, tau, nu intercepts) | coeff_re (tau spline, nu spline)];
     # every warp-tile uses the same 22 columns -> one shared column list
@@ -250,9 +261,10 @@ def make_ctcrw_device(n_tracks, n_steps, seed=20260103, device=0, k=10, sigma_ob
     col = torch.as_tensor(np.asarray(pat, dtype=np.int32), device=dev)
     kmax = 1 | (1 << 8) | (k << 16) | (k << 24)
     desc = torch.empty((nq, 3), dtype=torch.int64, device=dev)
-    desc[:, 0] = torch.arange(nq, dtype=torch.int64, device=dev) * (wt * nnz_row)
+    desc[:, 0] = torch.arange(nq, dtype=torch.int64, device=dev) * (wt * nval_row)
     desc[:, 1] = 0
-    desc[:, 2] = kmax | (1 << 32)                    # flags = WT_UNIFORM
+    wt_flags = 1 | (((1 << 10) | (3 << 14)) if alias else 0)      # WT_UNIFORM | mu2 -> mu1 | nu -> tau
+    desc[:, 2] = kmax | (wt_flags << 32)
     obs_p = torch.stack([permute_rows(obs[:, d].contiguous(), n_pad, lc, 0.0) for d in range(nd)]).contiguous()
     dt_p = permute_rows(dt, n_pad, lc, 1.0)
     flags_p = permute_rows(flags, n_pad, lc, 255)
@@ -292,7 +304,8 @@ def make_ctcrw_device(n_tracks, n_steps, seed=20260103, device=0, k=10, sigma_ob
     info = {"n": n, "n_dim": nd, "nnz": n * nnz_row, "p_fe": p_fe, "p_re": p_re, "n_s": 2,
             "n_par": nd + 2, "n_tracks": n_id, "n_pad": n_pad, "tensors": dict(obs=obs, dt=dt, flags=flags, times=tflat),
             "S": S, "a0": a0, "track_starts": track_starts, "knots": (lo, hi), "Zc": Zc,
-            "packed": dict(desc=desc, col=col, val=val, obs_p=obs_p, dt_p=dt_p, flags_p=flags_p, lc=lc, wt=wt, nnz_row=nnz_row)}
+            "packed": dict(desc=desc, col=col, val=val, obs_p=obs_p, dt_p=dt_p, flags_p=flags_p, lc=lc, wt=wt, nnz_row=nnz_row,
+                           nval_row=nval_row)}
     return eng, par, info
 
 

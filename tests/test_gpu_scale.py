@@ -23,8 +23,11 @@ def grad_err(g, g_ref):
 def host_oracle(info, T, m, k=10):
     """The device-built CTCRW problem as CSR arrays on the host (un-permuting the packed values)."""
     t = info["packed"]
-    n, n_pad, lc, nnz = info["n"], info["n_pad"], t["lc"], t["nnz_row"]
-    val = t["val"].reshape(n_pad // (32 * lc), lc, nnz, 32).permute(0, 3, 1, 2).reshape(n_pad, nnz)[:n].cpu().numpy()
+    n, n_pad, lc, nnz, nv = info["n"], info["n_pad"], t["lc"], t["nnz_row"], t["nval_row"]
+    val = t["val"].reshape(n_pad // (32 * lc), lc, nv, 32).permute(0, 3, 1, 2).reshape(n_pad, nv)[:n].cpu().numpy()
+    if nv != nnz:        # aliased layout (design.cuh): a row stores [mu intercept | tau block]; mu2 = mu1's slot, nu = tau's
+        assert nv == 1 + k and nnz == 2 + 2 * k
+        val = np.concatenate([val[:, :1], val[:, :1], val[:, 1:], val[:, 1:]], axis=1)
     p_fe, p_re = info["p_fe"], info["p_re"]
     # rows j*n + i of [X_fe | X_re]: mu1 (1 nonzero), mu2 (1), tau (k), nu (k)
     cnt = np.concatenate([np.full(n, 1), np.full(n, 1), np.full(n, k), np.full(n, k)]).astype(np.int64)
@@ -70,6 +73,26 @@ def test_device_built_shapes_match_the_c_oracle_at_1e7_rows(T, m, seed):
     v3, g3 = eng.eval(par, order=1)             # shortcut back on: same result as before
     assert v3 == v
     eng.close()
+
+
+def test_aliased_and_plain_design_layouts_agree_at_1e7_rows():
+    """tau and nu share one smooth of time: the default layout stores their values once per row (alias
+    flags, 11 of 22 doubles).  Same data, both layouts, through both kernels: the linear predictors add
+    the same products in the same order, so nllk and gradient agree to the last bits."""
+    from smoothsde_b200 import devgen
+    T, m = 128, 100000
+    res = []
+    for alias in (True, False):
+        eng, par, info = devgen.make_ctcrw_device(T, m, seed=20260107, device=0, alias=alias)
+        assert info["packed"]["nval_row"] == (11 if alias else 22)
+        par = par.copy()
+        par[1:5] = [0.3, -0.2, 0.2, -0.1]
+        res.append(eng.eval(par, order=1))
+        eng.close()
+        del eng, info
+    (v1, g1), (v0, g0) = res
+    assert abs(v1 - v0) <= 1e-13 * abs(v0), (v1, v0)
+    assert grad_err(g1, g0) <= 1e-11, (g1, g0)
 
 
 def test_device_built_ou_with_random_intercepts_matches_the_c_oracle_at_1e7_rows():

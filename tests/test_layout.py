@@ -18,6 +18,24 @@ def layout_info():
     return tuple(info)
 
 
+def alias_of(flags, p):
+    """design.cuh alias_of: bits 8+2p, 9+2p of the descriptor flags (t + 1, or 0 = own values)."""
+    return ((int(flags) >> (8 + 2 * p)) & 3) - 1
+
+
+def value_slots(kb, flags):
+    """(value slots per row, first value slot of every parameter) -- design.cuh value_slots_of."""
+    sv, off = 0, []
+    for p in range(4):
+        t = alias_of(flags, p)
+        if t >= 0:
+            off.append(off[t])
+        else:
+            off.append(sv)
+            sv += kb[p]
+    return sv, off
+
+
 def eta_from_pack(pk, n, n_par, theta):
     """Evaluate the packed design exactly the way the kernels index it."""
     LC, WT, PAD, _ = layout_info()
@@ -25,7 +43,9 @@ def eta_from_pack(pk, n, n_par, theta):
     for q, d in enumerate(pk["desc"]):
         kb = [(int(d["kmax"]) >> (8 * p)) & 255 for p in range(4)]
         S = sum(kb)
+        SV, voff = value_slots(kb, d["flags"])
         uniform = bool(d["flags"] & 1)
+        assert uniform or SV == S
         for lane in range(32):
             for k in range(LC):
                 r = q * WT + lane * LC + k
@@ -33,8 +53,8 @@ def eta_from_pack(pk, n, n_par, theta):
                     continue
                 j = 0
                 for p in range(n_par):
-                    for _ in range(kb[p]):
-                        v = pk["val"][d["val_off"] + (k * S + j) * 32 + lane]
+                    for i in range(kb[p]):
+                        v = pk["val"][d["val_off"] + (k * SV + voff[p] + i) * 32 + lane]
                         c = pk["col"][d["col_off"] + j] if uniform else pk["col"][d["col_off"] + (k * S + j) * 32 + lane]
                         eta[r, p] += v * theta[c]
                         j += 1
@@ -66,6 +86,47 @@ def test_packed_design_reproduces_linear_predictor(model, T, m, nd):
     assert np.all(pk["desc"]["flags"] & 1)
     # identical consecutive column lists are stored once
     assert pk["col"].size < 4 * pk["desc"].size * 64
+
+
+def test_parameters_with_the_same_smooth_share_their_value_slots(monkeypatch):
+    """tau ~ s(time), nu ~ s(time): identical blocks of X_re in different columns are stored once per
+    warp-tile (alias flags) for the Kalman models -- 2 x (1 + 9) + 2 column slots, 1 + 10 value slots --
+    and never for the nllk_sde models, whose kernels do not read the alias flags."""
+    dat, par, info = synth.make_problem("CTCRW", 2, 300, n_dim=2, seed=5)
+    n = info["n"]
+    pk = pack_host(dat)
+    live = pk["desc"][: (n + 255) // 256]
+    for d in live:
+        kb = [(int(d["kmax"]) >> (8 * p)) & 255 for p in range(4)]
+        assert kb == [1, 1, 10, 10]
+        assert [alias_of(d["flags"], p) for p in range(4)] == [-1, 0, -1, 2]
+        assert value_slots(kb, d["flags"])[0] == 11
+    assert pk["val"].size == 11 * 256 * live.size
+    theta = np.random.default_rng(2).normal(size=info["p_fe"] + info["p_re"])
+    ref = dense_eta(dat, theta, n, 4)
+    assert np.allclose(eta_from_pack(pk, n, 4, theta), ref, rtol=1e-13, atol=1e-13)
+    # a parameter whose block differs in one entry keeps its own values
+    Xre = sp.lil_matrix(dat["X_re"])
+    r, c = 3 * n + 17, np.flatnonzero(sp.csr_matrix(dat["X_re"])[3 * n + 17].toarray().ravel())[0]
+    Xre[r, c] = Xre[r, c] * 1.5
+    dat2 = dict(dat, X_re=sp.csr_matrix(Xre))
+    pk2 = pack_host(dat2)
+    assert alias_of(pk2["desc"][0]["flags"], 3) == -1 and alias_of(pk2["desc"][1]["flags"], 3) == 2
+    assert np.allclose(eta_from_pack(pk2, n, 4, theta), dense_eta(dat2, theta, n, 4), rtol=1e-13, atol=1e-13)
+    # SSDE_NO_ALIAS=1: the plain layout (A/B runs)
+    monkeypatch.setenv("SSDE_NO_ALIAS", "1")
+    pk3 = pack_host(dat)
+    assert not np.any(pk3["desc"]["flags"] & 0xff00) and pk3["val"].size == 22 * 256 * live.size
+    assert np.allclose(eta_from_pack(pk3, n, 4, theta), ref, rtol=1e-13, atol=1e-13)
+    monkeypatch.delenv("SSDE_NO_ALIAS")
+    # nllk_sde models: mu and tau share s(time) + s(ID) but keep their own value slots
+    dat4, _, info4 = synth.make_problem("OU", 3, 200, n_dim=1, seed=6)
+    assert not np.any(pack_host(dat4)["desc"]["flags"] & 0xff00)
+    dat5, _, info5 = synth.make_problem("OU_SSM", 2, 200, n_dim=1, seed=6)
+    pk5 = pack_host(dat5)
+    assert alias_of(pk5["desc"][0]["flags"], 1) == 0
+    th5 = np.random.default_rng(3).normal(size=info5["p_fe"] + info5["p_re"])
+    assert np.allclose(eta_from_pack(pk5, info5["n"], 3, th5), dense_eta(dat5, th5, info5["n"], 3), rtol=1e-13, atol=1e-13)
 
 
 def test_irregular_sparsity_falls_back_to_per_nonzero_columns():
