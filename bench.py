@@ -442,7 +442,7 @@ def measure_ou(name, n_tracks, n_steps, args, ctx):
         hess_ms = f"failed: {e}"
         launches_h = 0
     parity = n1_parity(f"{name}:{n_tracks}x{n_steps}", args, world, rank, first[0], first[1:npar + 1])
-    stored_b = 23 * 8 + 8 + 8 + 1
+    stored_b = info["stored_bytes_per_obs"]       # design values (mu / tau blocks stored once) + dt + obs + flag
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.exists(peaks_path) else 6650.0
     kmain = max(kernels, key=kernels.get)

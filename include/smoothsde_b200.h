@@ -118,8 +118,15 @@ typedef struct {
     int64_t col_off;          /* first column index of the warp-tile in d_col */
     uint32_t kmax;            /* byte p = slots of SDE parameter p; S = sum of the bytes */
     uint32_t flags;           /* bit0: one column list col[col_off + j] for the whole warp-tile,
-                                 else per nonzero, indexed like the values */
-} ssde_wt_desc;               /* value of slot j, row (k, l): d_val[val_off + (k*S + j)*32 + l] */
+                                 else per nonzero, indexed like the values.
+                                 bits 8+2p, 9+2p (bit0 set only): 0 = parameter p stores its own values;
+                                 t+1 = parameter p is an ALIAS of parameter t < p -- its kmax_p value slots
+                                 hold the same numbers as t's in every row (tau ~ s(time), nu ~ s(time):
+                                 one basis, two column blocks) and are not stored.  It keeps its own
+                                 column slots.  Not accepted together with decay terms. */
+} ssde_wt_desc;               /* value of slot j, row (k, l): d_val[val_off + (k*SV + j)*32 + l], SV = the
+                                 kmax bytes of the non-aliased parameters summed (= S without aliases),
+                                 value slots numbered over the non-aliased parameters in order */
 
 typedef struct {
     int32_t model, n_dim, n_par;

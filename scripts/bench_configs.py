@@ -97,8 +97,9 @@ def main():
         d = np.zeros(par.size)
         d[-1] = 1.0
         ms_h = timed(lambda: eng.hvp(par, d), reps=5, warm=2)
-        extra = {"p_re": info["p_re"], "stored_bytes_per_obs": 201, "kernel_ms_last_eval": eng.last_eval_ms,
-                 "dram_frac_stored_bytes": 201 * n / (eng.last_eval_ms * 1e-3) / 1e9 / PEAK, "hvp_ms_per_direction": ms_h}
+        sb = info["stored_bytes_per_obs"]
+        extra = {"p_re": info["p_re"], "stored_bytes_per_obs": sb, "kernel_ms_last_eval": eng.last_eval_ms,
+                 "dram_frac_stored_bytes": sb * n / (eng.last_eval_ms * 1e-3) / 1e9 / PEAK, "hvp_ms_per_direction": ms_h}
         if with_laplace:                     # 146 random effects: the dense Laplace driver (146 tangent passes per Hessian)
             lap = DeviceLaplace(eng)
             t0 = time.perf_counter()

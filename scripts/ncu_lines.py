@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Attribute executed warp instructions and stall samples of one kernel to source lines.
 
-    python scripts/ncu_lines.py <report.ncu-rep> <kernel-regex> <lib.so> [rows]
+    python scripts/ncu_lines.py <report.ncu-rep | NAME.source.csv> <kernel-regex> <lib.so> [rows]
 
 ncu's SASS page (per-instruction counters) is joined, by instruction order, with nvdisasm's
 line-info disassembly of the same cubin.  `rows` scales the counts to instructions per row.
@@ -17,10 +17,14 @@ from collections import defaultdict
 
 
 def _collect(rep, kre, lib):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass",
-                          "--kernel-name", "regex:" + kre], capture_output=True, text=True).stdout
+    if rep.endswith(".csv"):      # the SASS page dumped on the GPU box (scripts/ncu_capture.sh: NAME.source.csv)
+        raw = open(rep).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass",
+                              "--kernel-name", "regex:" + kre], capture_output=True, text=True).stdout
     lines = raw.splitlines()
-    start = next(i for i, l in enumerate(lines) if l.startswith('"Address"'))
+    kstart = next((i for i, l in enumerate(lines) if l.startswith('"Kernel Name"') and re.search(kre, l)), 0)
+    start = next(i for i, l in enumerate(lines) if i > kstart - 1 and l.startswith('"Address"'))
     end = next((i for i in range(start + 1, len(lines)) if lines[i].startswith('"Kernel Name"')), len(lines))
     kname = lines[start - 1]
     rd = list(csv.reader(io.StringIO("\n".join(lines[start:end]))))

@@ -27,5 +27,5 @@ tot = sum(k.values())
 print(json.dumps({"config": f"OU {T} x {m}, mu,tau ~ s(time,k=10) + s(ID,re), kappa ~ 1", "n": n, "p_re": info["p_re"],
                   "nllk": v, "kernels_ms": k, "ms_per_eval": tot, "obs_eval_per_s": n / tot * 1e3,
                   "alg_bytes_per_obs": devgen.alg_bytes_per_obs(1, 3, 23),
-                  "stored_bytes_per_obs": 23 * 8 + 8 + 8 + 1}))
+                  "stored_bytes_per_obs": info["stored_bytes_per_obs"]}))
 eng.close()

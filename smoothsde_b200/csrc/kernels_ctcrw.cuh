@@ -39,15 +39,6 @@
 #ifndef SSDE_FWD_RESTAGE
 #define SSDE_FWD_RESTAGE 1
 #endif
-// 1: software-pipelined row loop of the forward kernel (row k+1's transform next to row k's append)
-#ifndef SSDE_FWD_PIPE
-#define SSDE_FWD_PIPE 0
-#endif
-// 1: the forward kernel parks the thread's exclusive-prefix element in shared memory across the
-// look-back (instead of letting the compiler spill it) and caches tau/e/s2 instead of the step
-#ifndef SSDE_FWD_EXC_SMEM
-#define SSDE_FWD_EXC_SMEM 0
-#endif
 // 1: the forward kernel forms a row's predictors in one branch-free pass over the staged values
 // against a dense per-warp coefficient table (design.cuh, fill_theta_matrix / row_eta_dense)
 #ifndef SSDE_ETA_DENSE
@@ -94,6 +85,10 @@ struct KalmanArgs {
     int summary;               // 1: stop after the tile prefixes are published (time-sharded runs only
                                // need the composite element of the whole shard = last inclusive prefix)
     int tile_lo;               // first ticket of this launch (> 0: summary over the tail of the shard only)
+    int rerun;                 // forward kernel: 1 = phase (4), the filter re-run that yields the likelihood terms
+                               // (and aest); 0 = stop at the checkpoints -- the adjoint kernel, which recomputes
+                               // the forward states of every row anyway, sums the likelihood terms (llk_bwd)
+    int llk_bwd;               // adjoint kernel: 1 = write tile_llk from its forward recomputation
 };
 
 // Start state of the track whose first row carries track index `idx` (stored, as a double, in
@@ -152,16 +147,7 @@ __device__ __forceinline__ RowPlanes<M> open_planes(const KalmanArgs<typename M:
 template <class M, int NT>
 struct FwdSmem {
     using R = typename M::R;
-#if SSDE_FWD_EXC_SMEM
-    // per row the transformed parameters (CTCRW: tau, e, s2 -- the step is rebuilt from them with ~15
-    // flops in the re-run) instead of the 5 step quantities: the 16 KB this saves hold the thread's
-    // exclusive-prefix element across the look-back, which the compiler otherwise spills to local
-    // memory (36 STL + 18 LDL.64 per thread and tile = 1.8 GB of DRAM writes per launch at 1e8 rows)
-    static constexpr int NC = M::NW;
-    double X[M::FwdElem::NDBL][NT];
-#else
     static constexpr int NC = M::NC;             // step quantities per row (CTCRW: T12, e, Qa, Qb, Qc)
-#endif
     static constexpr int ES = (M::FwdElem::NDBL > 24 * ScalarOf<R>::NDBL) ? M::FwdElem::NDBL : 24 * ScalarOf<R>::NDBL;
     R W[LC][NC][NT];
     double stage[NT / 32][STAGE_DBL];
@@ -194,6 +180,8 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(KalmanArgs<typename
     const bool mu0 = *a.mu_zero != 0;
     WarpStage st;
     stage_init(st, sm.stage[warp], &sm.bar[warp]);
+    for (int i = lane; i < STAGE_DBL; i += 32) sm.stage[warp][i] = 0.0;     // row_eta_dense reads up to 3 slots past a row-step
+    __syncwarp();
     mbar_fence_init();
     constexpr bool DENSE_ETA = SSDE_ETA_DENSE && std::is_same<R, double>::value;
     ThetaKey tkey;
@@ -230,74 +218,12 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(KalmanArgs<typename
         Elem E = M::fwd_identity();
         // dt and the observations of a row are fetched one row ahead of their use
         const RowPlanes<M> pl = open_planes<M>(a, base, false, SSDE_PLANE_PREFETCH != 0);
-#if SSDE_FWD_PIPE
-        // Software pipeline: while row k is appended to the element (a chain of dependent fp64
-        // operations through E), row k+1's linear predictor, natural-scale transform and step
-        // matrices -- independent of E -- are formed in the same stretch of straight-line code, so
-        // the two dependency chains interleave (12 warps per SM cannot hide them otherwise).
-        struct RowWork { typename M::Step sp; R eta[NP]; double dtv, y[ND]; uint8_t f; };
-        auto stage_a = [&](int k, RowWork& r) {
-            const int64_t pos = base + k * 32;
-            r.f = (uint8_t)(fl >> (8 * k));
-            const bool live = r.f != 0xff;
-            const bool step = live && !(r.f & ROW_START);
-            r.dtv = live ? pl.dt[k * 32] : 1.0;
-#pragma unroll
-            for (int d = 0; d < ND; ++d) r.y[d] = live ? pl.obs[d][k * 32] : 0.0;
-#pragma unroll
-            for (int p = 0; p < NP; ++p) r.eta[p] = 0.0;
-            if (w.staged) {
-                stage_wait(st);
-                if constexpr (DENSE_ETA) row_eta_dense<NP>(w, st.buf, sm.thm[warp], r.eta);
-                else row_eta_staged<NP>(w, st, r.eta);
-                __syncwarp();
-                if (lane == 0 && k + 1 < LC) {
-                    stage_issue(w, st, k + 1);
-#if SSDE_FWD_PREFETCH == 2
-                    if (k + 3 < LC) prefetch_l2(w.blk + (size_t)(k + 3) * w.SV * 32, (unsigned)(w.SV * 32 * 8));
-#endif
-                }
-            } else if (step) {
-                row_eta<NP>(w, k, a.theta, r.eta);
-            }
-            // unconditional arithmetic (a dead row has eta = 0, dt = 1: finite; nothing of it is kept)
-            const typename M::RowPar rp = M::transform(r.eta, r.dtv);
-            r.sp = M::make_step(rp, r.dtv);
-            if (step) {
-                M::store_rowpar(rp, [&](int c) -> R& { return const_cast<R&>(pl.wg[c][k * 32]); });
-#if SSDE_FWD_EXC_SMEM
-                M::store_rowpar(rp, [&](int c) -> R& { return sm.W[k][c][tid]; });
-#else
-                M::store_step(r.sp, [&](int c) -> R& { return sm.W[k][c][tid]; });
-#endif
-            }
-            (void)pos;
-        };
-        // append row k (unconditional arithmetic, the result is kept only for a filter step)
-        auto stage_b = [&](int k, const RowWork& r) {
-            const bool live = r.f != 0xff;
-            const bool step = live && !(r.f & ROW_START);
-            Elem En = E;
-            M::fwd_append(En, r.sp, r.y, r.eta, (r.f & ROW_OBS) != 0, M::row_h(h, a.Hrow, a.X.n_pad, base + k * 32));
-            if (step) E = En;
-            else if (live) M::fwd_append_start(E, track_start_state<M>(a, r.dtv));
-        };
-        double dt_nx = 1.0, y_nx[ND];                  // used again by the re-run (4)
-#pragma unroll
-        for (int d = 0; d < ND; ++d) y_nx[d] = 0.0;
-        RowWork cur, nxt;
-        stage_a(0, cur);
-#pragma unroll 1
-        for (int k = 0; k + 1 < LC; ++k) {
-            stage_a(k + 1, nxt);
-            stage_b(k, cur);
-            cur = nxt;
-        }
-        stage_b(LC - 1, cur);
-#else
         double dt_nx = ((uint8_t)fl != 0xff) ? pl.dt[0] : 1.0, y_nx[ND];
 #pragma unroll
         for (int d = 0; d < ND; ++d) y_nx[d] = ((uint8_t)fl != 0xff) ? pl.obs[d][0] : 0.0;
+        const unsigned step_bytes = (unsigned)w.SV * 32u * 8u;      // one row-step of design values
+        const size_t step_dbl = (size_t)w.SV * 32;
+        const double* next_step = w.blk + step_dbl;                 // row-step k + 1
 #pragma unroll 1
         for (int k = 0; k < LC; ++k) {
             const int64_t pos = base + k * 32;
@@ -317,15 +243,20 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(KalmanArgs<typename
             R eta[NP];
             if (w.staged) {
                 stage_wait(st);
-                if constexpr (DENSE_ETA) row_eta_dense<NP>(w, st.buf, sm.thm[warp], eta);
-                else row_eta_staged<NP>(w, st, eta);
+                if constexpr (DENSE_ETA) {
+                    if (mu0) row_eta_dense<NP, ND>(w, st.buf, sm.thm[warp], eta);
+                    else row_eta_dense<NP, 0>(w, st.buf, sm.thm[warp], eta);
+                } else {
+                    row_eta_staged<NP>(w, st, eta);
+                }
                 __syncwarp();
                 if (lane == 0 && k + 1 < LC) {
-                    stage_issue(w, st, k + 1);
+                    stage_issue_at(st, next_step, step_bytes);
 #if SSDE_FWD_PREFETCH == 2
-                    if (k + 3 < LC) prefetch_l2(w.blk + (size_t)(k + 3) * w.SV * 32, (unsigned)(w.SV * 32 * 8));
+                    if (k + 3 < LC) prefetch_l2(next_step + 2 * step_dbl, step_bytes);
 #endif
                 }
+                next_step += step_dbl;
             } else if (step) {
                 row_eta<NP>(w, k, a.theta, eta);
             }
@@ -333,22 +264,17 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(KalmanArgs<typename
                 const typename M::RowPar rp = M::transform(eta, dtv);
                 M::store_rowpar(rp, [&](int c) -> R& { return const_cast<R&>(pl.wg[c][k * 32]); });
                 const typename M::Step sp = M::make_step(rp, dtv);
-#if SSDE_FWD_EXC_SMEM
-                M::store_rowpar(rp, [&](int c) -> R& { return sm.W[k][c][tid]; });
-#else
-                M::store_step(sp, [&](int c) -> R& { return sm.W[k][c][tid]; });
-#endif
+                if (a.rerun) M::store_step(sp, [&](int c) -> R& { return sm.W[k][c][tid]; });
                 M::fwd_append(E, sp, y, eta, (f & ROW_OBS) != 0, M::row_h(h, a.Hrow, a.X.n_pad, pos));
             } else if (live) {
                 M::fwd_append_start(E, track_start_state<M>(a, dtv));
             }
         }
-#endif
 #if SSDE_FWD_RESTAGE
         // The staging buffer is idle until the next tile: bring the warp-tile's dt / obs planes
         // (2 KB each, contiguous) into it with bulk copies that land during the scan and the
         // look-back, so that the re-run (4) reads them from shared memory instead of L2.
-        const bool restage = w.staged && !a.summary && (1 + ND) * WT <= STAGE_DBL;
+        const bool restage = w.staged && !a.summary && a.rerun && (1 + ND) * WT <= STAGE_DBL;
         if (restage && lane == 0) {
             fence_proxy_async();
             mbar_expect_tx(st.bar, (unsigned)((1 + ND) * WT * 8));
@@ -378,13 +304,6 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(KalmanArgs<typename
         }
         Elem exc = shfl_up_elem(inc, 1);
         if (lane == 0) exc = M::fwd_identity();
-#if SSDE_FWD_EXC_SMEM
-        {
-            const double* ex = reinterpret_cast<const double*>(&exc);
-#pragma unroll
-            for (int i = 0; i < Elem::NDBL; ++i) sm.X[i][tid] = ex[i];
-        }
-#endif
 #ifdef SSDE_STATS
         tc1 = clock64();
 #endif
@@ -430,19 +349,10 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(KalmanArgs<typename
 #pragma unroll 1
             for (int ww = max(w0, 0); ww < warp; ++ww) s = M::fwd_apply(load_elem<Elem>(sm.wagg[par][ww]), s);
         }
-#if SSDE_FWD_EXC_SMEM
-        {
-            Elem ex2;
-            double* ex = reinterpret_cast<double*>(&ex2);
-#pragma unroll
-            for (int i = 0; i < Elem::NDBL; ++i) ex[i] = sm.X[i][tid];
-            s = M::fwd_apply(ex2, s);
-        }
-#else
         s = M::fwd_apply(exc, s);
-#endif
         const int64_t chunk = q * 32 + lane;
         M::store_state(s, [&](int i) -> R& { return a.ckpt[(size_t)i * a.nchunks + chunk]; });
+        if (!a.rerun) continue;        // the adjoint kernel sums the likelihood terms (llk_bwd)
         // sum_i log F_i is taken as the log of a running product (one log per chunk instead of
         // one per row); the product is folded into `slog` whenever it leaves a safe range.
         R quad = 0.0, fprod = 1.0, slog = 0.0;
@@ -481,11 +391,7 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(KalmanArgs<typename
 #pragma unroll
                 for (int d = 0; d < ND; ++d) mu[d] = 0.0;
                 if (!mu0) row_eta_prefix<ND>(w, k, a.theta, mu);
-#if SSDE_FWD_EXC_SMEM
-                const typename M::Step sp = M::make_step(M::load_rowpar([&](int c) { return sm.W[k][c][tid]; }), dtv);
-#else
                 const typename M::Step sp = M::load_step([&](int c) { return sm.W[k][c][tid]; }, dtv);
-#endif
                 R F, qd;
                 M::template fwd_step<false>(s, sp, y, mu, (f & ROW_OBS) != 0, M::row_h(h, a.Hrow, a.X.n_pad, pos), nullptr, F, qd);
                 quad += qd;
@@ -599,6 +505,12 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_bwd_kernel(KalmanArgs<typename
         Elem E = M::bwd_identity();
         const RowPlanes<M> pl = open_planes<M>(a, base, true, SSDE_PLANE_PREFETCH != 0);
         RowIn<M> nx = load_row<M>(pl, 0, (uint8_t)fl != 0xff);
+        // llk_bwd: this recomputation IS the filter over the rows -- F and the quadratic form of every
+        // row come out of it, so the likelihood terms are summed here (same running-product form as the
+        // forward kernel's re-run, which is then skipped)
+        const bool want_llk = a.llk_bwd && !a.summary;
+        R quad = 0.0, fprod = 1.0, slog = 0.0;
+        bool bad_f = false;
 #pragma unroll 1
         for (int k = 0; k < LC; ++k) {
             const uint8_t f = (uint8_t)(fl >> (8 * k));
@@ -618,10 +530,21 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_bwd_kernel(KalmanArgs<typename
                 R F, qd;
                 M::template fwd_step<true>(s, sp, r.y, mu, (f & ROW_OBS) != 0, M::row_h(h, a.Hrow, a.X.n_pad, base + k * 32), &ax, F, qd);
                 E = M::bwd_combine(E, M::bwd_row_elem(sp, ax, (f & ROW_OBS) != 0, (f & ROW_LAST) != 0));
+                if (want_llk) {
+                    quad += qd;
+                    fprod *= F;
+                    bad_f |= value(F) <= 0.0;          // nllk_ctcrw.hpp:226-228 is not built: flag it
+                    if (!(value(fprod) > 1e-150 && value(fprod) < 1e150)) { slog += log(fprod); fprod = 1.0; }
+                }
             } else if (live) {
                 s = track_start_state<M>(a, r.dt);
                 E = M::bwd_combine(E, M::bwd_const(M::adj_zero()));
             }
+        }
+        if (want_llk) {
+            const double llk = warp_sum(value(-0.5 * ((double)M::LOGF_MULT * (slog + log(fprod)) + quad)));
+            if (lane == 0) a.tile_llk[q] = llk;              // one partial per warp-tile
+            if (bad_f) atomicOr(a.bdesc.error, 2u);
         }
         // (2) warp inclusive SUFFIX scan (higher lanes = later rows)
         Elem inc = E;

@@ -223,23 +223,25 @@ __global__ void __launch_bounds__(SDE_NT, 3) sde_stream_kernel(SdeArgs a, HotRan
     for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
         const int64_t q = tile * NWARP + warp;
         const WtDesc d = a.X.desc[q];
-        const int S = slots_of(d.kmax);
+        const int S = slots_of(d.kmax);                            // column slots
         if (S == 0) continue;                                      // padding warp-tile
-        int kp[NP];
+        uint64_t vofs;
+        const int SV = value_slots_of(d.kmax, d.flags, &vofs);     // value slots of a row (< S when parameters share a smooth)
+        int kp[NP], vo[NP];
 #pragma unroll
-        for (int p = 0; p < NP; ++p) kp[p] = (int)((d.kmax >> (8 * p)) & 255u);
+        for (int p = 0; p < NP; ++p) { kp[p] = (int)((d.kmax >> (8 * p)) & 255u); vo[p] = (int)((vofs >> (16 * p)) & 0xffffull) * 32; }
         const double* blk = a.X.val + d.val_off;
         const uint32_t* cols = a.X.col + d.col_off;
-        const unsigned bytes = (unsigned)S * 32u * 8u;             // one row-step
+        const unsigned bytes = (unsigned)SV * 32u * 8u;            // one row-step
         __syncwarp();                                              // previous warp-tile: all lanes done with th / staging
         if (lane == 0) {
             fence_proxy_async();
             mbar_expect_tx(bar[0], bytes);
             tma_load_1d(buf[0], blk, bytes, bar[0]);
             mbar_expect_tx(bar[1], bytes);
-            tma_load_1d(buf[1], blk + (size_t)S * 32, bytes, bar[1]);
+            tma_load_1d(buf[1], blk + (size_t)SV * 32, bytes, bar[1]);
             // the design stream runs two pairs ahead of the copies: they then hit L2
-            prefetch_l2(blk + (size_t)2 * S * 32, 4u * bytes);
+            prefetch_l2(blk + (size_t)2 * SV * 32, 4u * bytes);
         }
         if (lane < S) th[lane] = __ldg(a.theta.v + __ldg(cols + lane));
         const int64_t base = q * WT + lane;
@@ -291,7 +293,7 @@ __global__ void __launch_bounds__(SDE_NT, 3) sde_stream_kernel(SdeArgs a, HotRan
 #pragma unroll
                     for (int dd = 0; dd < ND; ++dd) zc_n[dd] = p_obs[dd][nx8];
                 }
-                if (lane == 0 && k + 6 < LC) prefetch_l2(blk + (size_t)(k + 6) * S * 32, 2u * bytes);
+                if (lane == 0 && k + 6 < LC) prefetch_l2(blk + (size_t)(k + 6) * SV * 32, 2u * bytes);
             }
             const uint8_t fa = (uint8_t)(fl >> (8 * k)), fb = (uint8_t)(fl >> (8 * (k + 1)));
             const uint8_t fc = (k + 2 < LC) ? (uint8_t)(fl >> (8 * (k + 2))) : f8;
@@ -307,8 +309,8 @@ __global__ void __launch_bounds__(SDE_NT, 3) sde_stream_kernel(SdeArgs a, HotRan
                 int o = 0;
 #pragma unroll
                 for (int p = 0; p < NP; ++p) {
-                    const double* xa = va + o * 32;
-                    const double* xb = vb + o * 32;
+                    const double* xa = va + vo[p];
+                    const double* xb = vb + vo[p];
                     const double* tp = th + o;
                     double e0 = 0.0, e1 = 0.0, g0 = 0.0, g1 = 0.0;
                     SSDE_SLOT_GROUPS(kp[p], { const double t = tp[i];
@@ -331,8 +333,8 @@ __global__ void __launch_bounds__(SDE_NT, 3) sde_stream_kernel(SdeArgs a, HotRan
 #pragma unroll
                 for (int p = 0; p < NP; ++p) {
                     const double ea = live_a ? eb_a[p] : 0.0, eb_ = live_b ? eb_b[p] : 0.0;
-                    const double* xa = va + o * 32;
-                    const double* xb = vb + o * 32;
+                    const double* xa = va + vo[p];
+                    const double* xb = vb + vo[p];
                     SSDE_SLOT_GROUPS(kp[p], acc[p][i] = fma(xb[i * 32], eb_, fma(xa[i * 32], ea, acc[p][i])))
                     o += kp[p];
                 }
@@ -342,9 +344,9 @@ __global__ void __launch_bounds__(SDE_NT, 3) sde_stream_kernel(SdeArgs a, HotRan
                 if (lane == 0) {
                     fence_proxy_async();
                     mbar_expect_tx(bar[0], bytes);
-                    tma_load_1d(buf[0], blk + (size_t)(k + 2) * S * 32, bytes, bar[0]);
+                    tma_load_1d(buf[0], blk + (size_t)(k + 2) * SV * 32, bytes, bar[0]);
                     mbar_expect_tx(bar[1], bytes);
-                    tma_load_1d(buf[1], blk + (size_t)(k + 3) * S * 32, bytes, bar[1]);
+                    tma_load_1d(buf[1], blk + (size_t)(k + 3) * SV * 32, bytes, bar[1]);
                 }
                 dta = dta_n; dtb = dtb_n;
 #pragma unroll
@@ -457,23 +459,28 @@ __global__ void __launch_bounds__(SDE_NT, 2) sde_hess_kernel(SdeArgs a, HessHot 
     for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
         const int64_t q = tile * NWARP + warp;
         const WtDesc d = a.X.desc[q];
-        const int S = slots_of(d.kmax);
+        const int S = slots_of(d.kmax);                            // column slots
         if (S == 0) continue;
-        int kp[NP], off[NP];
+        uint64_t vofs;
+        const int SV = value_slots_of(d.kmax, d.flags, &vofs);     // value slots of a row (aliased parameters store none)
+        int kp[NP], off[NP], vo[NP];
         {
             int o = 0;
 #pragma unroll
-            for (int pp = 0; pp < NP; ++pp) { kp[pp] = (int)((d.kmax >> (8 * pp)) & 255u); off[pp] = o; o += kp[pp]; }
+            for (int pp = 0; pp < NP; ++pp) {
+                kp[pp] = (int)((d.kmax >> (8 * pp)) & 255u); off[pp] = o; o += kp[pp];
+                vo[pp] = (int)((vofs >> (16 * pp)) & 0xffffull);
+            }
         }
         const double* blk = a.X.val + d.val_off;
         const uint32_t* cols = a.X.col + d.col_off;
-        const unsigned bytes = (unsigned)S * 32u * 8u;
+        const unsigned bytes = (unsigned)SV * 32u * 8u;
         __syncwarp();
         if (lane == 0) {
             fence_proxy_async();
             mbar_expect_tx(bar, bytes);
             tma_load_1d(stage, blk, bytes, bar);
-            prefetch_l2(blk + (size_t)S * 32, (unsigned)((LC - 1) * S * 32 * 8));
+            prefetch_l2(blk + (size_t)SV * 32, (unsigned)((LC - 1) * SV * 32 * 8));
         }
         int my_col = 0, my_q = 0;                                   // this lane's column j' = lane: theta index, SDE parameter
         if (lane < S) {
@@ -518,24 +525,25 @@ __global__ void __launch_bounds__(SDE_NT, 2) sde_hess_kernel(SdeArgs a, HessHot 
             const double* v = stage + lane;
             double eta[NP];
             {
-                const double* vp = v;
                 const double* tp = th;
 #pragma unroll
                 for (int pp = 0; pp < NP; ++pp) {
+                    const double* vp = v + vo[pp] * 32;
                     double e0 = 0.0, e1 = 0.0;
                     SSDE_SLOT_GROUPS(kp[pp], if (i & 1) e1 = fma(vp[i * 32], tp[i], e1); else e0 = fma(vp[i * 32], tp[i], e0))
                     eta[pp] = e0 + e1;
-                    vp += kp[pp] * 32;
                     tp += kp[pp];
                 }
             }
-            // transpose the row-step: xT[row = lane][slot]
-            for (int j = 0; j < S; ++j) sm.xT[warp][lane][j] = v[j * 32];
+            // transpose the row-step: xT[row = lane][column slot] (an aliased parameter's slots are copies of its target's)
+#pragma unroll
+            for (int pp = 0; pp < NP; ++pp)
+                for (int i = 0; i < kp[pp]; ++i) sm.xT[warp][lane][off[pp] + i] = v[(vo[pp] + i) * 32];
             __syncwarp();
             if (lane == 0 && k + 1 < LC) {                         // the staging buffer is free again
                 fence_proxy_async();
                 mbar_expect_tx(bar, bytes);
-                tma_load_1d(stage, blk + (size_t)(k + 1) * S * 32, bytes, bar);
+                tma_load_1d(stage, blk + (size_t)(k + 1) * SV * 32, bytes, bar);
             }
             // exact second derivatives of the row's nllk with respect to its predictors
             {
@@ -607,7 +615,7 @@ __global__ void design_shape_kernel(const WtDesc* __restrict__ desc, int64_t nwt
     atomicMax(out + 0, smax);
     if (nonuni) atomicOr(out + 1, 1);
     atomicMax(out + 2, kpmax);
-    if (alias) atomicOr(out + 3, 1);             // aliased parameters: the scan kernels of the Kalman models only
+    if (alias) atomicOr(out + 3, 1);             // aliased parameters: not understood by sde_decay_kernel
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -529,8 +529,8 @@ struct V2Host {
 };
 
 // allow_alias: parameters whose value slots are identical in every row of a uniform warp-tile
-// (tau ~ s(time), nu ~ s(time)) store them once (design.cuh, alias_of) -- the scan kernels of the
-// Kalman models understand that, the nllk_sde kernels do not.
+// (tau ~ s(time), nu ~ s(time)) store them once (design.cuh, alias_of); every kernel but
+// sde_decay_kernel reads the alias flags, so decay models keep the plain layout.
 int build_v2(const Packed& pk, int64_t n, int64_t n_pad, int n_par, bool allow_alias, V2Host& out, std::string& err) {
     const int64_t nwt = n_pad / WT;
     out.desc.assign((size_t)nwt, WtDesc{0, 0, 0u, WT_UNIFORM});
@@ -938,7 +938,7 @@ int finish_setup(ssde_handle* h) {
         CUDA_TRY(cudaGetLastError());
         int sh[4] = {0, 0, 0, 0};
         CUDA_TRY(cudaMemcpy(sh, shape.p, 4 * sizeof(int), cudaMemcpyDeviceToHost));
-        if (sh[3]) { err = "descriptor flags alias parameters: supported by the Kalman models only"; return SSDE_ERR_BAD_ARG; }
+        if (sh[3] && h->n_dec > 0) { err = "descriptor flags alias parameters: not supported together with decay terms"; return SSDE_ERR_BAD_ARG; }
         h->sde_stream = h->n_dec == 0 && sh[0] <= SDE_SMAX && sh[1] == 0 && sh[2] <= SDE_KPM;
     }
     return SSDE_OK;
@@ -998,8 +998,16 @@ KalmanArgs<R> ctcrw_args(ssde_handle* h, const double* d_par, const double* d_di
     a.ntiles = h->ntiles_f;
     a.summary = 0;
     a.tile_lo = 0;
+    a.rerun = 1;
+    a.llk_bwd = 0;
     return a;
 }
+
+// 1 (default): an evaluation that runs the adjoint kernel takes the likelihood terms from that
+// kernel's forward recomputation and skips the forward kernel's re-run (phase 4)
+#ifndef SSDE_LLK_IN_BWD
+#define SSDE_LLK_IN_BWD 1
+#endif
 
 // the scan descriptors are keyed by an epoch so that they never need clearing; every kernel that
 // walks the tiles (full pass or summary pass) gets a fresh epoch and fresh tickets
@@ -1015,7 +1023,7 @@ constexpr int TAIL_TILES = 4;           // tiles of a tail-only summary pass (40
 
 template <class M>
 int launch_ctcrw_fwd(ssde_handle* h, const double* d_par, const double* d_dir, cudaStream_t st, double* aest, bool summary,
-                     bool tail = false) {
+                     bool tail = false, bool rerun = true) {
     using R = typename M::R;
     constexpr bool TAN = !std::is_same<R, double>::value;
     std::string& err = h->err;
@@ -1023,6 +1031,7 @@ int launch_ctcrw_fwd(ssde_handle* h, const double* d_par, const double* d_dir, c
     if (rc) return rc;
     KalmanArgs<R> a = ctcrw_args<R>(h, d_par, d_dir, aest);
     a.summary = summary ? 1 : 0;
+    a.rerun = (rerun || aest) ? 1 : 0;
     a.tile_lo = (summary && tail) ? std::max(h->ntiles_f - TAIL_TILES, 0) : 0;
     mark(h, st, TAN ? "ctcrw_fwd_tangent" : (summary ? (tail ? "ctcrw_fwd_tail" : "ctcrw_fwd_summary") : "ctcrw_fwd"));
     if constexpr (TAN) ctcrw_fwd_kernel<M, M::KNT, TAN_MINB><<<h->grid_f2, M::KNT, sizeof(FwdSmem<M, M::KNT>), st>>>(a);
@@ -1032,7 +1041,8 @@ int launch_ctcrw_fwd(ssde_handle* h, const double* d_par, const double* d_dir, c
 }
 
 template <class M>
-int launch_ctcrw_bwd(ssde_handle* h, const double* d_par, const double* d_dir, cudaStream_t st, bool summary, bool tail = false) {
+int launch_ctcrw_bwd(ssde_handle* h, const double* d_par, const double* d_dir, cudaStream_t st, bool summary, bool tail = false,
+                     bool llk = false) {
     using R = typename M::R;
     constexpr bool TAN = !std::is_same<R, double>::value;
     std::string& err = h->err;
@@ -1041,6 +1051,7 @@ int launch_ctcrw_bwd(ssde_handle* h, const double* d_par, const double* d_dir, c
     KalmanArgs<R> a = ctcrw_args<R>(h, d_par, d_dir, nullptr);
     a.ntiles = h->ntiles_b;
     a.summary = summary ? 1 : 0;
+    a.llk_bwd = llk ? 1 : 0;
     a.tile_lo = (summary && tail) ? std::max(h->ntiles_b - TAIL_TILES, 0) : 0;
     mark(h, st, TAN ? "ctcrw_bwd_tangent" : (summary ? (tail ? "ctcrw_bwd_tail" : "ctcrw_bwd_summary") : "ctcrw_bwd"));
     if constexpr (TAN) ctcrw_bwd_kernel<M, M::KNT, TAN_MINB><<<h->grid_b2, M::KNT, sizeof(BwdSmem<M, M::KNT>), st>>>(a);
@@ -1063,8 +1074,9 @@ int launch_reduce(ssde_handle* h, int order, bool tan, cudaStream_t st) {
 template <class M>
 int launch_ctcrw(ssde_handle* h, const double* d_par, const double* d_dir, int order, cudaStream_t st, double* aest) {
     int rc;
-    if ((rc = launch_ctcrw_fwd<M>(h, d_par, d_dir, st, aest, false))) return rc;
-    if (order >= 1 && (rc = launch_ctcrw_bwd<M>(h, d_par, d_dir, st, false))) return rc;
+    const bool llk_bwd = SSDE_LLK_IN_BWD && order >= 1 && !aest;
+    if ((rc = launch_ctcrw_fwd<M>(h, d_par, d_dir, st, aest, false, false, !llk_bwd))) return rc;
+    if (order >= 1 && (rc = launch_ctcrw_bwd<M>(h, d_par, d_dir, st, false, false, llk_bwd))) return rc;
     return launch_reduce(h, order, !std::is_same<typename M::R, double>::value, st);
 }
 
@@ -1370,7 +1382,7 @@ static int pack_host_impl(const ssde_desc* d, ssde_host_pack* out) {
     if ((rc = pack_design(*d, n_par, pk, err))) return rc;
     V2Host v2;
     const int64_t n_pad = ssde_padded_rows(d->n);
-    if ((rc = build_v2(pk, d->n, n_pad, n_par, is_kalman(d->model), v2, err))) return rc;
+    if ((rc = build_v2(pk, d->n, n_pad, n_par, !(d->t_decay && d->t_decay_len > 1), v2, err))) return rc;
     out->n_pad = n_pad;
     out->n_desc = (int64_t)v2.desc.size(); out->n_val = (int64_t)v2.val.size(); out->n_col = (int64_t)v2.col.size();
     out->desc = (ssde_wt_desc*)std::malloc(sizeof(WtDesc) * std::max<size_t>(v2.desc.size(), 1));
@@ -1546,7 +1558,7 @@ static int create_impl(const ssde_desc* d, ssde_handle** out) {
         if ((rc = dev_upload(h->mu_cols, mc, h->err))) return fail(rc);
     }
     V2Host v2;
-    if ((rc = build_v2(pk, n, n_pad, n_par, is_kalman(d->model), v2, h->err))) return fail(rc);
+    if ((rc = build_v2(pk, n, n_pad, n_par, h->n_dec == 0, v2, h->err))) return fail(rc);
     if ((rc = dev_upload(h->desc, v2.desc, h->err))) return fail(rc);
     if ((rc = dev_upload(h->col, v2.col, h->err))) return fail(rc);
     if ((rc = dev_upload(h->val, v2.val, h->err))) return fail(rc);
@@ -1667,7 +1679,8 @@ int ssde_eval_stage(ssde_handle* h, const double* d_par, int stage, const double
                 shard_state_kernel<M><<<1, 32, 0, st>>>(d_elems, n_shards, my_shard, h->P0, h->s_in.as<double>());
                 ++h->last_launches;
                 h->have_s_in = true;
-                if ((rc = launch_ctcrw_fwd<M>(h, d_par, nullptr, st, nullptr, false))) return rc;
+                // the adjoint pass of stage 2 always follows: it sums the likelihood terms
+                if ((rc = launch_ctcrw_fwd<M>(h, d_par, nullptr, st, nullptr, false, false, !SSDE_LLK_IN_BWD))) return rc;
             }
             if ((rc = launch_ctcrw_bwd<M>(h, d_par, nullptr, st, true, stage == 1))) return rc;
             shard_elem_kernel<typename M::BwdElem, BwdOps<M>><<<1, 32, 0, st>>>(h->b_incl.as<double>() + (size_t)(h->ntiles_b - 1) * be, d_out);
@@ -1683,7 +1696,7 @@ int ssde_eval_stage(ssde_handle* h, const double* d_par, int stage, const double
             shard_adjoint_kernel<M><<<1, 32, 0, st>>>(d_elems, n_shards, my_shard, h->g_in.as<double>());
             ++h->last_launches;
             h->have_g_in = true;
-            return launch_ctcrw_bwd<M>(h, d_par, nullptr, st, false);
+            return launch_ctcrw_bwd<M>(h, d_par, nullptr, st, false, false, SSDE_LLK_IN_BWD != 0);
         });
         if (rc) return rc;
         if ((rc = launch_reduce(h, 1, false, st))) return rc;

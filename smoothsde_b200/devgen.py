@@ -389,14 +389,19 @@ def alg_bytes_per_obs(n_dim, n_par, nnz_per_obs):
 # OU with a random intercept per track: BASELINE configs[1] (64 x 1e5) and the OU half of configs[4]
 # (4096 x 2.5e4)
 # ------------------------------------------------------------------------------------------------
-def make_ou_device(n_tracks, n_steps, seed=20260102, device=0, k=10, rank=0, world=1, shard_flags=0):
+def make_ou_device(n_tracks, n_steps, seed=20260102, device=0, k=10, rank=0, world=1, shard_flags=0, alias=None):
     """OU, d = 1: ``mu, tau ~ s(time, k) + s(ID, bs = "re")``, ``kappa ~ 1`` for this
     rank's `n_tracks` of `world * n_tracks` tracks x `n_steps` regular steps, built on the device in the
     packed layout.  Columns: coeff_fe = (mu, tau, kappa intercepts); coeff_re = [mu.s(time) (k-1),
     mu.s(ID) (all tracks), tau.s(time), tau.s(ID)] as SDE$make_mat orders them (R/sde.R:412-421);
     S = blockdiag(S_time, I, S_time, I).  Each row has 23 nonzeros; a warp-tile that straddles two
-    tracks carries both tracks' random-intercept columns (25 slots).  Returns (engine, par, info)."""
+    tracks carries both tracks' random-intercept columns (25 slots).  `alias` (default on, SSDE_NO_ALIAS=1
+    turns it off): the mu and tau blocks hold the same numbers, so a row stores them once (design.cuh alias
+    flags: 23 / 25 column slots, 12 / 13 value slots).  Returns (engine, par, info)."""
+    import os
     import torch
+    if alias is None:
+        alias = not os.environ.get("SSDE_NO_ALIAS")
     dev = torch.device("cuda", device)
     T, m = int(n_tracks), int(n_steps)
     Ttot = T * world
@@ -461,16 +466,18 @@ def make_ou_device(n_tracks, n_steps, seed=20260102, device=0, k=10, rank=0, wor
     tr_b = torch.where(live, r_last // m, torch.zeros_like(q))
     two = live & (tr_b > tr_a)
     nre = torch.where(two, 2, 1)
-    S_q = torch.where(live, 2 * (1 + km1) + 2 * nre + 1, torch.zeros_like(q))
-    val_off = torch.cumsum(S_q * wt, 0) - S_q * wt
+    S_q = torch.where(live, 2 * (1 + km1) + 2 * nre + 1, torch.zeros_like(q))               # column slots
+    SV_q = torch.where(live, (1 + km1) + nre + 1, torch.zeros_like(q)) if alias else S_q     # value slots
+    val_off = torch.cumsum(SV_q * wt, 0) - SV_q * wt
     col_off = torch.cumsum(S_q, 0) - S_q
-    n_val, n_col = int((S_q * wt).sum()), int(S_q.sum())
+    n_val, n_col = int((SV_q * wt).sum()), int(S_q.sum())
     kp = (1 + km1) + nre
     kmax = torch.where(live, kp | (kp << 8) | (1 << 16), torch.zeros_like(q))
+    wt_flags = 1 | ((1 << 10) if alias else 0)                  # WT_UNIFORM | tau's value slots = mu's
     desc = torch.empty((nq, 3), dtype=torch.int64, device=dev)
     desc[:, 0] = val_off
     desc[:, 1] = col_off
-    desc[:, 2] = kmax | (1 << 32)                               # flags = WT_UNIFORM
+    desc[:, 2] = kmax | (wt_flags << 32)
     col = torch.zeros(max(n_col, 1), dtype=torch.int32, device=dev)
     spl = torch.arange(km1, device=dev, dtype=torch.int64)
     for is_two in (False, True):
@@ -503,11 +510,12 @@ def make_ou_device(n_tracks, n_steps, seed=20260102, device=0, k=10, rank=0, wor
             sel = torch.nonzero((live & (two == is_two))[q0:q1]).reshape(-1)
             if sel.numel() == 0:
                 continue
-            S_here = 2 * (1 + km1) + (4 if is_two else 2) + 1
+            n_blk = 1 if alias else 2                          # value blocks stored: mu (= tau) or mu, tau
+            S_here = n_blk * ((1 + km1) + (2 if is_two else 1)) + 1
             rsel = (sel[:, None] * wt + torch.arange(wt, device=dev)[None, :]).reshape(-1)      # rows of the selected tiles
             V = torch.zeros((rsel.numel(), S_here), dtype=torch.float64, device=dev)
             o = 0
-            for _p in range(2):                                # mu block, tau block
+            for _p in range(n_blk):                            # mu block(, tau block)
                 V[:, o] = onev[rsel]
                 V[:, o + 1:o + 1 + km1] = Bz[rsel]
                 o += 1 + km1
@@ -558,5 +566,6 @@ def make_ou_device(n_tracks, n_steps, seed=20260102, device=0, k=10, rank=0, wor
     par = np.concatenate([[0.0, 0.0, math.log(1.5)], np.zeros(4), 0.1 * prng.standard_normal(p_re)])
     info = {"n": n, "n_dim": 1, "nnz": nnz, "p_fe": p_fe, "p_re": p_re, "n_s": 4, "n_par": 3, "n_tracks": T,
             "n_tracks_total": Ttot, "first_track": g0, "n_pad": n_pad, "S": S, "Bz1": Bz1, "m": m, "k": k,
+            "stored_bytes_per_obs": (8.0 * n_val + 17.0 * n) / n,      # design values + dt + obs + flag
             "tensors": dict(obs=obs, dt=dt, flags=flags, times=times.reshape(-1))}
     return eng, par, info

@@ -90,8 +90,8 @@ def test_packed_design_reproduces_linear_predictor(model, T, m, nd):
 
 def test_parameters_with_the_same_smooth_share_their_value_slots(monkeypatch):
     """tau ~ s(time), nu ~ s(time): identical blocks of X_re in different columns are stored once per
-    warp-tile (alias flags) for the Kalman models -- 2 x (1 + 9) + 2 column slots, 1 + 10 value slots --
-    and never for the nllk_sde models, whose kernels do not read the alias flags."""
+    warp-tile (alias flags) -- 2 x (1 + 9) + 2 column slots, 1 + 10 value slots -- except in decay
+    models, whose kernel does not read the alias flags."""
     dat, par, info = synth.make_problem("CTCRW", 2, 300, n_dim=2, seed=5)
     n = info["n"]
     pk = pack_host(dat)
@@ -119,9 +119,19 @@ def test_parameters_with_the_same_smooth_share_their_value_slots(monkeypatch):
     assert not np.any(pk3["desc"]["flags"] & 0xff00) and pk3["val"].size == 22 * 256 * live.size
     assert np.allclose(eta_from_pack(pk3, n, 4, theta), ref, rtol=1e-13, atol=1e-13)
     monkeypatch.delenv("SSDE_NO_ALIAS")
-    # nllk_sde models: mu and tau share s(time) + s(ID) but keep their own value slots
+    # OU: mu and tau share s(time) + s(ID, bs = "re"); kappa ~ 1 has its own slot
     dat4, _, info4 = synth.make_problem("OU", 3, 200, n_dim=1, seed=6)
-    assert not np.any(pack_host(dat4)["desc"]["flags"] & 0xff00)
+    pk4 = pack_host(dat4)
+    for d in pk4["desc"][: (info4["n"] + 255) // 256]:
+        kb = [(int(d["kmax"]) >> (8 * p)) & 255 for p in range(4)]
+        assert alias_of(d["flags"], 1) == 0 and alias_of(d["flags"], 2) == -1
+        assert value_slots(kb, d["flags"])[0] == kb[0] + 1
+    th4 = np.random.default_rng(4).normal(size=info4["p_fe"] + info4["p_re"])
+    assert np.allclose(eta_from_pack(pk4, info4["n"], 3, th4), dense_eta(dat4, th4, info4["n"], 3), rtol=1e-13, atol=1e-13)
+    # decay terms scale the values per parameter inside the kernel: plain layout
+    n4 = info4["n"]
+    dat6 = dict(dat4, t_decay=np.tile(np.linspace(0.0, 1.0, n4), 3), col_decay=np.array([1]), ind_decay=np.array([1]))
+    assert not np.any(pack_host(dat6)["desc"]["flags"] & 0xff00)
     dat5, _, info5 = synth.make_problem("OU_SSM", 2, 200, n_dim=1, seed=6)
     pk5 = pack_host(dat5)
     assert alias_of(pk5["desc"][0]["flags"], 1) == 0
