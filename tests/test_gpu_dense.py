@@ -54,7 +54,7 @@ def test_coupled_filter_matches_oracle(model, T, m, nd, miss, user_H, user_P0):
     eng = Engine.from_data(dat)
     v0, _ = eng.eval(par, order=0)
     v, g = eng.eval(par, order=1)
-    assert v0 == v
+    assert abs(v0 - v) <= 1e-14 * abs(v), (v0, v)           # forward re-run (order 0) vs the adjoint kernel's recomputation
     assert abs(v - ref) <= NLLK_RTOL * abs(ref), (v, ref)
     assert grad_err(g, g_ref) <= GRAD_RTOL, (g, g_ref)
     if user_H:

@@ -46,7 +46,9 @@ def test_nllk_and_gradient_match_oracle(model, T, m, miss, nd):
     eng = Engine.from_data(dat)
     v0, _ = eng.eval(par, order=0)
     v, g = eng.eval(par, order=1)
-    assert v0 == v
+    # order 0 sums the likelihood terms in the forward kernel's re-run, order 1 in the adjoint kernel's forward
+    # recomputation (the re-run is skipped): the same filter, two compilations of it -- equal to rounding
+    assert abs(v0 - v) <= 1e-14 * abs(v), (v0, v)
     assert abs(v - ref) <= NLLK_RTOL * abs(ref), (v, ref)
     g_ref = O.grad_complex_step(dat, par)
     assert grad_err(g, g_ref) <= GRAD_RTOL, (g, g_ref)
