@@ -90,29 +90,13 @@ SSDE_HD StepParT<R> make_step(const R& tau, const R& e, const R& s2, double dt) 
 
 // Natural-scale transform of one linear-predictor row, nllk_ctcrw.hpp:152-156:
 //   tau = exp(eta_tau), nu = exp(eta_nu), sigma = 2 nu / sqrt(pi tau)  =>  s2 = 4 nu^2/(pi tau)
-// SSDE_FAST_TRANSFORM=1 (experiment, not the default): 1/tau = exp(-eta_tau) instead of a division
-// that has to wait for tau, and the branch-free exp (dual.cuh) -- three independent exponentials
-// that the compiler can interleave, then the one that needs 1/tau; every factor within ~1 ulp of
-// the expression below.  Measured on the B200 at 1.024e8 rows: forward kernel 5.59 ms against 5.37 ms
-// with the library calls (the extra live values cost 100 B more spills per thread).
-#ifndef SSDE_FAST_TRANSFORM
-#define SSDE_FAST_TRANSFORM 0
-#endif
 template <class R>
 SSDE_HD void transform_row(const R& eta_tau, const R& eta_nu, double dt, R& tau, R& e, R& s2) {
-#if SSDE_FAST_TRANSFORM
-    tau = exp_bf(eta_tau);
-    const R itau = exp_bf(-eta_tau);
-    const R nu = exp_bf(eta_nu);
-    s2 = (4.0 / 3.14159265358979323846) * nu * nu * itau;
-    e = exp_bf(-dt * itau);
-#else
     tau = exp(eta_tau);
     const R nu = exp(eta_nu);
     const R itau = 1.0 / tau;
     s2 = (4.0 / 3.14159265358979323846) * nu * nu * itau;
     e = exp(-dt * itau);
-#endif
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -481,6 +465,75 @@ SSDE_HD BwdElem<ND, R> bwd_combine(const BwdElem<ND, R>& E1, const BwdElem<ND, R
         Ro.D.c -= t2 * z1.y;
     }
     return Ro;
+}
+
+// bwd_combine(E1, bwd_row_elem(...)) for one ordinary row, without the products that the row
+// element's structural zeros (z_d = (w_d, 0), D = diag(Fl, 0)) would only multiply by 0.
+template <int ND, class R>
+SSDE_HD BwdElem<ND, R> bwd_append_row(const BwdElem<ND, R>& E1, const StepParT<R>& sp, const StepAux<ND, R>& ax,
+                                      bool has_obs, bool cut) {
+    BwdElem<ND, R> Ro;
+    const Mat2T<R> L1 = E1.L;
+    if (cut) {
+        Ro.L = {0.0, 0.0, 0.0, 0.0};
+    } else {
+        const R l11 = 1.0 - ax.g1 - sp.T12 * ax.g2, l21 = -sp.e * ax.g2;       // L2 = [[l11, T12], [l21, e]]
+        Ro.L = {l11 * L1.m11 + sp.T12 * L1.m21, l11 * L1.m12 + sp.T12 * L1.m22,
+                l21 * L1.m11 + sp.e * L1.m21, l21 * L1.m12 + sp.e * L1.m22};
+    }
+    R sw2 = 0.0;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) sw2 += ax.w[d] * ax.w[d];
+    const R Fl = has_obs ? R(0.5 * ((double)ND * ax.iF - sw2)) : R(0.0);
+    const R q11 = Fl * L1.m11, q12 = Fl * L1.m12;
+    Ro.D.a = L1.m11 * q11 + E1.D.a;
+    Ro.D.b = 0.5 * (L1.m11 * q12 + L1.m12 * q11) + E1.D.b;
+    Ro.D.c = L1.m12 * q12 + E1.D.c;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+        const R w = has_obs ? ax.w[d] : R(0.0);
+        const R t1 = L1.m11 * w, t2 = L1.m12 * w;               // L1' z2 with z2 = (w, 0)
+        const Vec2T<R> z1 = E1.z[d];
+        Ro.z[d] = {t1 + z1.x, t2 + z1.y};
+        Ro.D.a -= t1 * z1.x;
+        Ro.D.b -= 0.5 * (t1 * z1.y + t2 * z1.x);
+        Ro.D.c -= t2 * z1.y;
+    }
+    return Ro;
+}
+
+// bwd_apply(bwd_row_elem(...), g) for one ordinary row, again without the structural zeros.
+template <int ND, class R>
+SSDE_HD Adj<ND, R> bwd_apply_row(const StepParT<R>& sp, const StepAux<ND, R>& ax, bool has_obs, bool cut,
+                                 const Adj<ND, R>& g) {
+    Adj<ND, R> r;
+    R sw2 = 0.0;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) sw2 += ax.w[d] * ax.w[d];
+    const R Fl = has_obs ? R(0.5 * ((double)ND * ax.iF - sw2)) : R(0.0);
+    if (cut) {                                                   // L = 0: only the row's own terms survive
+        r.P = {Fl, 0.0, 0.0};
+#pragma unroll
+        for (int d = 0; d < ND; ++d) r.a[d] = {has_obs ? R(-ax.w[d]) : R(0.0), 0.0};
+        return r;
+    }
+    const Mat2T<R> L = {1.0 - ax.g1 - sp.T12 * ax.g2, sp.T12, -sp.e * ax.g2, sp.e};
+    const Sym2T<R> P = g.P;
+    const R q11 = P.a * L.m11 + P.b * L.m21, q12 = P.a * L.m12 + P.b * L.m22;
+    const R q21 = P.b * L.m11 + P.c * L.m21, q22 = P.b * L.m12 + P.c * L.m22;
+    r.P.a = L.m11 * q11 + L.m21 * q21 + Fl;
+    r.P.b = 0.5 * ((L.m11 * q12 + L.m21 * q22) + (L.m12 * q11 + L.m22 * q21));
+    r.P.c = L.m12 * q12 + L.m22 * q22;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+        const R w = has_obs ? ax.w[d] : R(0.0);
+        const R t1 = L.m11 * g.a[d].x + L.m21 * g.a[d].y;       // L' abar+
+        const R t2 = L.m12 * g.a[d].x + L.m22 * g.a[d].y;
+        r.a[d] = {t1 - w, t2};
+        r.P.a += t1 * w;
+        r.P.b += 0.5 * (t2 * w);
+    }
+    return r;
 }
 
 // Adjoint at the start of E's range given the adjoint `g` flowing in at its end.

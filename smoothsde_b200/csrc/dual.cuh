@@ -11,7 +11,6 @@
 #pragma once
 
 #include <math.h>
-#include <string.h>
 
 #if defined(__CUDACC__)
 #define SSDE_HD __host__ __device__ __forceinline__
@@ -78,48 +77,6 @@ using ::fma;
 SSDE_HD Dual exp(const Dual& a) { const double e = ::exp(a.v); return Dual(e, e * a.d); }
 SSDE_HD Dual log(const Dual& a) { return Dual(::log(a.v), a.d / a.v); }
 SSDE_HD Dual sqrt(const Dual& a) { const double s = ::sqrt(a.v); return Dual(s, 0.5 * a.d / s); }
-
-// Branch-free exp.  The library's exp() carries a slow-path branch, which keeps the compiler from
-// interleaving the independent exponentials of a row (tau, 1/tau, nu) -- and a warp's instruction
-// stream in the scan kernels is latency-bound.  Range reduction x = n ln2 + r with the 2^52 magic
-// add, exp(r) = 1 + (r + r^2 Q(r)) with the degree-11 Taylor Q in Estrin form (dependency depth 6
-// instead of 13), scaling by 2^n in two halves so that overflow (-> inf) and gradual underflow
-// (-> denormals, 0) come out of the multiplications.  Max error < 1 ulp (tests/test_host.py).
-SSDE_HD double exp_bf(double x) {
-    const double xc = fmin(fmax(x, -1100.0), 1100.0);
-    const double MAGIC = 6755399441055744.0;                           // 1.5 * 2^52
-    const double t = fma(xc, 1.4426950408889634074, MAGIC);
-    const double n = t - MAGIC;
-    double r = fma(n, -6.93147180559945286227e-01, xc);                // ln2 rounded to double
-    r = fma(n, -2.31904681384629955842e-17, r);                        // ln2 - that
-    const double r2 = r * r, r4 = r2 * r2;
-    const double q0 = fma(1.0 / 6.0, r, 0.5);
-    const double q1 = fma(1.0 / 120.0, r, 1.0 / 24.0);
-    const double q2 = fma(1.0 / 5040.0, r, 1.0 / 720.0);
-    const double q3 = fma(1.0 / 362880.0, r, 1.0 / 40320.0);
-    const double q4 = fma(1.0 / 39916800.0, r, 1.0 / 3628800.0);
-    const double q5 = fma(1.0 / 6227020800.0, r, 1.0 / 479001600.0);
-    const double s0 = fma(q1, r2, q0), s1 = fma(q3, r2, q2), s2 = fma(q5, r2, q4);
-    const double Q = fma(fma(s2, r4, s1), r4, s0);
-    const double p = 1.0 + fma(r2, Q, r);
-#ifdef __CUDA_ARCH__
-    const int ni = __double2loint(t);
-    const int n1 = ni >> 1, n2 = ni - n1;
-    const double f1 = __hiloint2double((n1 + 1023) << 20, 0), f2 = __hiloint2double((n2 + 1023) << 20, 0);
-#else
-    unsigned long long tb;
-    memcpy(&tb, &t, 8);
-    const int ni = (int)(unsigned)(tb & 0xffffffffull);
-    const int n1 = ni >> 1, n2 = ni - n1;
-    const unsigned long long b1 = (unsigned long long)(n1 + 1023) << 52, b2 = (unsigned long long)(n2 + 1023) << 52;
-    double f1, f2;
-    memcpy(&f1, &b1, 8);
-    memcpy(&f2, &b2, 8);
-#endif
-    const double res = (p * f1) * f2;
-    return x != x ? x : res;
-}
-SSDE_HD Dual exp_bf(const Dual& a) { const double e = exp_bf(a.v); return Dual(e, e * a.d); }
 
 // c + a * b with a plain-double factor (design value times coefficient)
 SSDE_HD double fmad(double a, double b, double c) { return fma(a, b, c); }

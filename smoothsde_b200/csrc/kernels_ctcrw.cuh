@@ -36,9 +36,6 @@
 #ifndef SSDE_PLANE_PREFETCH
 #define SSDE_PLANE_PREFETCH 1
 #endif
-#ifndef SSDE_FWD_RESTAGE
-#define SSDE_FWD_RESTAGE 1
-#endif
 // 1: the forward kernel forms a row's predictors in one branch-free pass over the staged values
 // against a dense per-warp coefficient table (design.cuh, fill_theta_matrix / row_eta_dense)
 #ifndef SSDE_ETA_DENSE
@@ -47,6 +44,20 @@
 // 1: a warp keeps its theta cache when the next warp-tile uses the same column list
 #ifndef SSDE_THETA_REUSE
 #define SSDE_THETA_REUSE 1
+#endif
+// 1: the transformed parameters (tau, e, s2) that the forward kernel hands to the adjoint kernel are
+// stored row-step by row-step, [n_pad / 32][NW][32] -- one pointer and constant offsets per row --
+// instead of as NW planes of n_pad
+#ifndef SSDE_WG_INTERLEAVED
+#define SSDE_WG_INTERLEAVED 1
+#endif
+// 1: dt / obs (and in the adjoint kernel tau, e, s2) of a row are loaded without a "row exists" predicate
+#ifndef SSDE_UNCOND_ROW_LOADS
+#define SSDE_UNCOND_ROW_LOADS 1
+#endif
+// 1: a tile's flags / dt / observations are requested before the design descriptor is waited for
+#ifndef SSDE_EARLY_ROW_LOADS
+#define SSDE_EARLY_ROW_LOADS 1
 #endif
 
 namespace ssde {
@@ -121,13 +132,20 @@ struct RowPlanes {
     const typename M::R* wg[M::NW];
     const double* dt;
     const double* obs[M::ND];
+    static constexpr int WGS = SSDE_WG_INTERLEAVED ? 32 * M::NW : 32;     // wg: elements between two rows of a lane
 };
 template <class M>
 __device__ __forceinline__ RowPlanes<M> open_planes(const KalmanArgs<typename M::R>& a, int64_t base, bool with_wg, bool prefetch) {
     RowPlanes<M> p;
     const int64_t np = a.X.n_pad;
 #pragma unroll
-    for (int c = 0; c < M::NW; ++c) p.wg[c] = a.wg + (size_t)c * np + base;
+    for (int c = 0; c < M::NW; ++c) {
+#if SSDE_WG_INTERLEAVED
+        p.wg[c] = a.wg + (size_t)(base - (threadIdx.x & 31)) * M::NW + c * 32 + (threadIdx.x & 31);
+#else
+        p.wg[c] = a.wg + (size_t)c * np + base;
+#endif
+    }
     p.dt = a.dt + base;
 #pragma unroll
     for (int d = 0; d < M::ND; ++d) p.obs[d] = a.obs + (size_t)d * np + base;
@@ -136,7 +154,11 @@ __device__ __forceinline__ RowPlanes<M> open_planes(const KalmanArgs<typename M:
         const int64_t q0 = base - lane;                       // first element of the warp-tile in every plane
         if (lane == 0) prefetch_l2(a.dt + q0, WT * 8);
         else if (lane <= M::ND) prefetch_l2(a.obs + (size_t)(lane - 1) * np + q0, WT * 8);
+#if SSDE_WG_INTERLEAVED
+        else if (with_wg && lane <= M::ND + M::NW) prefetch_l2(a.wg + (size_t)q0 * M::NW + (size_t)(lane - 1 - M::ND) * WT, WT * (unsigned)sizeof(typename M::R));
+#else
         else if (with_wg && lane <= M::ND + M::NW) prefetch_l2(a.wg + (size_t)(lane - 1 - M::ND) * np + q0, WT * (unsigned)sizeof(typename M::R));
+#endif
     }
     return p;
 }
@@ -147,9 +169,7 @@ __device__ __forceinline__ RowPlanes<M> open_planes(const KalmanArgs<typename M:
 template <class M, int NT>
 struct FwdSmem {
     using R = typename M::R;
-    static constexpr int NC = M::NC;             // step quantities per row (CTCRW: T12, e, Qa, Qb, Qc)
     static constexpr int ES = (M::FwdElem::NDBL > 24 * ScalarOf<R>::NDBL) ? M::FwdElem::NDBL : 24 * ScalarOf<R>::NDBL;
-    R W[LC][NC][NT];
     double stage[NT / 32][STAGE_DBL];
     double wagg[2][NT / 32][ES];     // shared scratch is double-buffered by tile parity: the only
     double tagg[2][ES];              // barrier between two tiles is the one that hands out the ticket
@@ -200,6 +220,14 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(KalmanArgs<typename
         const int64_t q = (int64_t)tile * NWARP + warp;
         const int64_t base = q * WT + lane;
         const int64_t row0 = q * WT + (int64_t)lane * LC;
+#if SSDE_EARLY_ROW_LOADS
+        // flags, dt and observations depend on the ticket only: request them before the descriptor chain
+        const unsigned long long fl = load_flags8(a.flags, base);
+        const RowPlanes<M> pl = open_planes<M>(a, base, false, SSDE_PLANE_PREFETCH != 0);
+        double dt_nx = ((uint8_t)fl != 0xff) ? pl.dt[0] : 1.0, y_nx[ND];
+#pragma unroll
+        for (int d = 0; d < ND; ++d) y_nx[d] = ((uint8_t)fl != 0xff) ? pl.obs[d][0] : 0.0;
+#endif
         const WtViewT<R> w = open_warptile<R>(a.X, q, a.theta, sm.th[warp], true, SSDE_THETA_REUSE ? &tkey : nullptr);
         if constexpr (DENSE_ETA) {
             if (w.staged && (!SSDE_THETA_REUSE || tkey.fresh)) fill_theta_matrix(w, sm.thm[warp]);
@@ -212,15 +240,19 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(KalmanArgs<typename
             prefetch_l2(w.blk + (size_t)w.SV * 32, (unsigned)(2 * w.SV * 32 * 8));
 #endif
         }
+#if !SSDE_EARLY_ROW_LOADS
         const unsigned long long fl = load_flags8(a.flags, base);
+#endif
 
         // (1) thread element over its LC rows
         Elem E = M::fwd_identity();
         // dt and the observations of a row are fetched one row ahead of their use
+#if !SSDE_EARLY_ROW_LOADS
         const RowPlanes<M> pl = open_planes<M>(a, base, false, SSDE_PLANE_PREFETCH != 0);
         double dt_nx = ((uint8_t)fl != 0xff) ? pl.dt[0] : 1.0, y_nx[ND];
 #pragma unroll
         for (int d = 0; d < ND; ++d) y_nx[d] = ((uint8_t)fl != 0xff) ? pl.obs[d][0] : 0.0;
+#endif
         const unsigned step_bytes = (unsigned)w.SV * 32u * 8u;      // one row-step of design values
         const size_t step_dbl = (size_t)w.SV * 32;
         const double* next_step = w.blk + step_dbl;                 // row-step k + 1
@@ -235,10 +267,16 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(KalmanArgs<typename
 #pragma unroll
             for (int d = 0; d < ND; ++d) y[d] = y_nx[d];
             if (k + 1 < LC) {
+#if SSDE_UNCOND_ROW_LOADS
+                dt_nx = pl.dt[(k + 1) * 32];                 // n_pad entries exist; a padding row's values are never used
+#pragma unroll
+                for (int d = 0; d < ND; ++d) y_nx[d] = pl.obs[d][(k + 1) * 32];
+#else
                 const bool live1 = (uint8_t)(fl >> (8 * (k + 1))) != 0xff;
                 dt_nx = live1 ? pl.dt[(k + 1) * 32] : 1.0;
 #pragma unroll
                 for (int d = 0; d < ND; ++d) y_nx[d] = live1 ? pl.obs[d][(k + 1) * 32] : 0.0;
+#endif
             }
             R eta[NP];
             if (w.staged) {
@@ -262,29 +300,13 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(KalmanArgs<typename
             }
             if (step) {
                 const typename M::RowPar rp = M::transform(eta, dtv);
-                M::store_rowpar(rp, [&](int c) -> R& { return const_cast<R&>(pl.wg[c][k * 32]); });
+                M::store_rowpar(rp, [&](int c) -> R& { return const_cast<R&>(pl.wg[c][k * RowPlanes<M>::WGS]); });
                 const typename M::Step sp = M::make_step(rp, dtv);
-                if (a.rerun) M::store_step(sp, [&](int c) -> R& { return sm.W[k][c][tid]; });
                 M::fwd_append(E, sp, y, eta, (f & ROW_OBS) != 0, M::row_h(h, a.Hrow, a.X.n_pad, pos));
             } else if (live) {
                 M::fwd_append_start(E, track_start_state<M>(a, dtv));
             }
         }
-#if SSDE_FWD_RESTAGE
-        // The staging buffer is idle until the next tile: bring the warp-tile's dt / obs planes
-        // (2 KB each, contiguous) into it with bulk copies that land during the scan and the
-        // look-back, so that the re-run (4) reads them from shared memory instead of L2.
-        const bool restage = w.staged && !a.summary && a.rerun && (1 + ND) * WT <= STAGE_DBL;
-        if (restage && lane == 0) {
-            fence_proxy_async();
-            mbar_expect_tx(st.bar, (unsigned)((1 + ND) * WT * 8));
-            tma_load_1d(st.buf, a.dt + q * WT, WT * 8, st.bar);
-#pragma unroll
-            for (int d = 0; d < ND; ++d) tma_load_1d(st.buf + (1 + d) * WT, a.obs + (size_t)d * a.X.n_pad + q * WT, WT * 8, st.bar);
-        }
-#else
-        constexpr bool restage = false;
-#endif
         // (2) warp inclusive scan (lower lanes = earlier rows)
         Elem inc = E;
 #pragma unroll 1
@@ -302,8 +324,22 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(KalmanArgs<typename
                 if (c) { publish_agg<Ops>(a.fdesc, tile, inc); store_elem(sm.tagg[par], inc); }
             }
         }
-        Elem exc = shfl_up_elem(inc, 1);
-        if (lane == 0) exc = M::fwd_identity();
+        // The lane's exclusive prefix = its left neighbour's inclusive one.  The staging buffer is idle until
+        // the next tile: every lane parks `inc` there and reads lane - 1's column after the look-back -- no
+        // shuffle, and nothing for the register allocator to spill across the CTA barriers (it spilled the
+        // element to local memory: 36 STL + 18 LDL.64 per thread and tile, ~1.7 GB of DRAM writes per launch
+        // at 1e8 rows).
+        constexpr bool PARK = Elem::NDBL * 32 <= STAGE_DBL;       // the element fits the warp's staging buffer
+        Elem exc;
+        if (PARK) {
+            __syncwarp();                                          // every lane is done with the last row-step
+            const double* ex = reinterpret_cast<const double*>(&inc);
+#pragma unroll
+            for (int i = 0; i < Elem::NDBL; ++i) st.buf[i * 32 + lane] = ex[i];
+        } else {
+            exc = shfl_up_elem(inc, 1);
+            if (lane == 0) exc = M::fwd_identity();
+        }
 #ifdef SSDE_STATS
         tc1 = clock64();
 #endif
@@ -349,7 +385,17 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(KalmanArgs<typename
 #pragma unroll 1
             for (int ww = max(w0, 0); ww < warp; ++ww) s = M::fwd_apply(load_elem<Elem>(sm.wagg[par][ww]), s);
         }
-        s = M::fwd_apply(exc, s);
+        if (PARK) {
+            Elem ex2;
+            double* ex = reinterpret_cast<double*>(&ex2);
+            const int src = lane ? lane - 1 : 0;
+#pragma unroll
+            for (int i = 0; i < Elem::NDBL; ++i) ex[i] = st.buf[i * 32 + src];
+            if (lane == 0) ex2 = M::fwd_identity();
+            s = M::fwd_apply(ex2, s);
+        } else {
+            s = M::fwd_apply(exc, s);
+        }
         const int64_t chunk = q * 32 + lane;
         M::store_state(s, [&](int i) -> R& { return a.ckpt[(size_t)i * a.nchunks + chunk]; });
         if (!a.rerun) continue;        // the adjoint kernel sums the likelihood terms (llk_bwd)
@@ -357,32 +403,22 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(KalmanArgs<typename
         // one per row); the product is folded into `slog` whenever it leaves a safe range.
         R quad = 0.0, fprod = 1.0, slog = 0.0;
         bool bad_f = false;
-        if (restage) {
-            stage_wait(st);
-        } else {
-            dt_nx = ((uint8_t)fl != 0xff) ? pl.dt[0] : 1.0;
+        dt_nx = ((uint8_t)fl != 0xff) ? pl.dt[0] : 1.0;
 #pragma unroll
-            for (int d = 0; d < ND; ++d) y_nx[d] = ((uint8_t)fl != 0xff) ? pl.obs[d][0] : 0.0;
-        }
+        for (int d = 0; d < ND; ++d) y_nx[d] = ((uint8_t)fl != 0xff) ? pl.obs[d][0] : 0.0;
 #pragma unroll 1
         for (int k = 0; k < LC; ++k) {
             const uint8_t f = (uint8_t)(fl >> (8 * k));
             if (f == 0xff) break;
             const int64_t pos = base + k * 32;
-            double dtv, y[ND];
-            if (restage) {
-                dtv = st.buf[k * 32 + lane];
+            const double dtv = dt_nx;
+            double y[ND];
 #pragma unroll
-                for (int d = 0; d < ND; ++d) y[d] = st.buf[(1 + d) * WT + k * 32 + lane];
-            } else {
-                dtv = dt_nx;
+            for (int d = 0; d < ND; ++d) y[d] = y_nx[d];
+            if (k + 1 < LC && (uint8_t)(fl >> (8 * (k + 1))) != 0xff) {
+                dt_nx = pl.dt[(k + 1) * 32];
 #pragma unroll
-                for (int d = 0; d < ND; ++d) y[d] = y_nx[d];
-                if (k + 1 < LC && (uint8_t)(fl >> (8 * (k + 1))) != 0xff) {
-                    dt_nx = pl.dt[(k + 1) * 32];
-#pragma unroll
-                    for (int d = 0; d < ND; ++d) y_nx[d] = pl.obs[d][(k + 1) * 32];
-                }
+                for (int d = 0; d < ND; ++d) y_nx[d] = pl.obs[d][(k + 1) * 32];
             }
             if (f & ROW_START) {
                 s = track_start_state<M>(a, dtv);
@@ -391,7 +427,10 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(KalmanArgs<typename
 #pragma unroll
                 for (int d = 0; d < ND; ++d) mu[d] = 0.0;
                 if (!mu0) row_eta_prefix<ND>(w, k, a.theta, mu);
-                const typename M::Step sp = M::load_step([&](int c) { return sm.W[k][c][tid]; }, dtv);
+                // the row's step, rebuilt from the tau, e, s2 the row loop has just written (an L1 / L2 hit): this
+                // phase only runs when no adjoint pass follows, and a 40 KB step cache in shared memory would cost
+                // the kernel its fourth CTA per SM
+                const typename M::Step sp = M::make_step(M::load_rowpar([&](int c) { return pl.wg[c][k * RowPlanes<M>::WGS]; }), dtv);
                 R F, qd;
                 M::template fwd_step<false>(s, sp, y, mu, (f & ROW_OBS) != 0, M::row_h(h, a.Hrow, a.X.n_pad, pos), nullptr, F, qd);
                 quad += qd;
@@ -450,10 +489,20 @@ template <class M>
 __device__ __forceinline__ RowIn<M> load_row(const RowPlanes<M>& p, int k, bool live) {
     RowIn<M> r;
     const int o = k * 32;
+#if SSDE_UNCOND_ROW_LOADS
+    // every per-row array is n_pad long and nothing loaded for a row that is not a filter step is ever
+    // used (the callers branch on the row's flags), so the loads need no predicate
+    (void)live;
+    r.dt = p.dt[o];
+    r.rp = M::load_rowpar([&](int c) { return p.wg[c][k * RowPlanes<M>::WGS]; });
+#pragma unroll
+    for (int d = 0; d < M::ND; ++d) r.y[d] = p.obs[d][o];
+#else
     r.dt = live ? p.dt[o] : 1.0;
-    r.rp = live ? M::load_rowpar([&](int c) { return p.wg[c][o]; }) : M::dead_rowpar();
+    r.rp = live ? M::load_rowpar([&](int c) { return p.wg[c][k * RowPlanes<M>::WGS]; }) : M::dead_rowpar();
 #pragma unroll
     for (int d = 0; d < M::ND; ++d) r.y[d] = live ? p.obs[d][o] : 0.0;
+#endif
     return r;
 }
 
@@ -529,7 +578,7 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_bwd_kernel(KalmanArgs<typename
                 typename M::Aux ax;
                 R F, qd;
                 M::template fwd_step<true>(s, sp, r.y, mu, (f & ROW_OBS) != 0, M::row_h(h, a.Hrow, a.X.n_pad, base + k * 32), &ax, F, qd);
-                E = M::bwd_combine(E, M::bwd_row_elem(sp, ax, (f & ROW_OBS) != 0, (f & ROW_LAST) != 0));
+                E = M::bwd_append_row(E, sp, ax, (f & ROW_OBS) != 0, (f & ROW_LAST) != 0);
                 if (want_llk) {
                     quad += qd;
                     fprod *= F;
@@ -641,7 +690,7 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_bwd_kernel(KalmanArgs<typename
                     R g_h;
                     M::row_param_grad(gin, sp, ax, mu, r.rp, r.dt, has, hr, gp, g_h);
                     gh += g_h;
-                    g = M::bwd_apply(M::bwd_row_elem(sp, ax, has, cut), g);
+                    g = M::bwd_apply_row(sp, ax, has, cut, g);
                 }
             }
             // eta_bar of this row replaces its (consumed) forward state

@@ -31,7 +31,16 @@ struct PriorCov {
 #ifndef SSDE_MINB
 #define SSDE_MINB 3
 #endif
-constexpr int KNT_DEFAULT = SSDE_KNT, MINB_DEFAULT = SSDE_MINB;
+// resident CTAs per SM of the forward kernel alone (it needs little shared memory once the step cache is gone)
+#ifndef SSDE_FWD_MINB
+#define SSDE_FWD_MINB 4
+#endif
+constexpr int KNT_DEFAULT = SSDE_KNT, MINB_DEFAULT = SSDE_MINB, FMINB_DEFAULT = SSDE_FWD_MINB;
+// 1: the CTCRW adjoint kernel appends / applies a row from its step quantities (ctcrw_math.cuh:
+// bwd_append_row, bwd_apply_row) instead of building the general element and combining it
+#ifndef SSDE_BWD_ROW_SPECIAL
+#define SSDE_BWD_ROW_SPECIAL 1
+#endif
 
 constexpr double CONST_MAP_TOL = 1e-60;     // see FwdOps / is_const in common.cuh
 // The device reads the threshold from constant memory so that tests can switch the constant-map
@@ -60,9 +69,8 @@ struct CtcrwModel {
     static constexpr int SD = 2 * ND;        // state means per row (columns of a0 / aest_all)
     static constexpr int FS = 2 * ND + 3;    // scalars of a State / Adj
     static constexpr int NW = 3;             // transformed parameters kept for the adjoint kernel
-    static constexpr int NC = 5;             // step quantities cached in shared memory
     static constexpr int SPD = 2;            // states per dimension
-    static constexpr int KNT = KNT_DEFAULT, MINB = MINB_DEFAULT;
+    static constexpr int KNT = KNT_DEFAULT, MINB = MINB_DEFAULT, FMINB = FMINB_DEFAULT;
     static constexpr int LOGF_MULT = ND;     // log|F| = n_dim log F
     using Hc = R;                            // measurement covariance of a row: H = h I
     static SSDE_HD Hc row_h(const R& h, const double*, size_t, int64_t) { return h; }
@@ -83,15 +91,6 @@ struct CtcrwModel {
     template <class F> static SSDE_HD void store_rowpar(const RowPar& r, F at) { at(0) = r.tau; at(1) = r.e; at(2) = r.s2; }
     template <class F> static SSDE_HD RowPar load_rowpar(F at) { return RowPar{at(0), at(1), at(2)}; }
     static SSDE_HD Step make_step(const RowPar& r, double dt) { return ssde::make_step(r.tau, r.e, r.s2, dt); }
-    template <class F> static SSDE_HD void store_step(const Step& sp, F at) {
-        at(0) = sp.T12; at(1) = sp.e; at(2) = sp.Q.a; at(3) = sp.Q.b; at(4) = sp.Q.c;
-    }
-    template <class F> static SSDE_HD Step load_step(F at, double dt) {
-        Step sp;
-        sp.T12 = at(0); sp.e = at(1); sp.Q.a = at(2); sp.Q.b = at(3); sp.Q.c = at(4);
-        sp.B1 = dt - sp.T12; sp.B2 = 1.0 - sp.e;          // makeB_ctcrw, nllk_ctcrw.hpp:87-88
-        return sp;
-    }
     // a0 row = (x, 0, y, 0, ...) R/sde.R:574-580; P0 = shared 2x2 block
     static SSDE_HD State start_state(const double* a0row, const PriorCov& P0) {
         State s;
@@ -153,6 +152,21 @@ struct CtcrwModel {
     static SSDE_HD BwdElem bwd_row_elem(const Step& sp, const Aux& ax, bool has, bool cut) { return ssde::bwd_row_elem<ND>(sp, ax, has, cut); }
     static SSDE_HD BwdElem bwd_combine(const BwdElem& a, const BwdElem& b) { return ssde::bwd_combine<ND>(a, b); }
     static SSDE_HD Adj bwd_apply(const BwdElem& E, const Adj& g) { return ssde::bwd_apply<ND>(E, g); }
+    // one row appended to / applied from its step quantities: the row element's structural zeros are skipped
+    static SSDE_HD BwdElem bwd_append_row(const BwdElem& E, const Step& sp, const Aux& ax, bool has, bool cut) {
+#if SSDE_BWD_ROW_SPECIAL
+        return ssde::bwd_append_row<ND>(E, sp, ax, has, cut);
+#else
+        return ssde::bwd_combine<ND>(E, ssde::bwd_row_elem<ND>(sp, ax, has, cut));
+#endif
+    }
+    static SSDE_HD Adj bwd_apply_row(const Step& sp, const Aux& ax, bool has, bool cut, const Adj& g) {
+#if SSDE_BWD_ROW_SPECIAL
+        return ssde::bwd_apply_row<ND>(sp, ax, has, cut, g);
+#else
+        return ssde::bwd_apply<ND>(ssde::bwd_row_elem<ND>(sp, ax, has, cut), g);
+#endif
+    }
     static SSDE_HD bool bwd_is_const(const BwdElem& E) { return tiny(E.L); }
     // gp[NP] = d nllk / d eta of this row
     static SSDE_HD void row_param_grad(const Adj& g, const Step& sp, const Aux& ax, const R* mu, const RowPar& rp, double dt,
@@ -183,7 +197,7 @@ struct Ssm1Base {
     static constexpr int SD = ND;
     static constexpr int FS = ND + 1;
     static constexpr int SPD = 1;
-    static constexpr int KNT = KNT_DEFAULT, MINB = MINB_DEFAULT;
+    static constexpr int KNT = KNT_DEFAULT, MINB = MINB_DEFAULT, FMINB = FMINB_DEFAULT;
     static constexpr int LOGF_MULT = ND;
     using Hc = R;
     static SSDE_HD Hc row_h(const R& h, const double*, size_t, int64_t) { return h; }
@@ -253,6 +267,12 @@ struct Ssm1Base {
     static SSDE_HD BwdElem bwd_row_elem(const Step& sp, const Aux& ax, bool has, bool cut) { return bwd_row_elem1<ND>(sp, ax, has, cut); }
     static SSDE_HD BwdElem bwd_combine(const BwdElem& a, const BwdElem& b) { return bwd_combine1<ND>(a, b); }
     static SSDE_HD Adj bwd_apply(const BwdElem& E, const Adj& g) { return bwd_apply1<ND>(E, g); }
+    static SSDE_HD BwdElem bwd_append_row(const BwdElem& E, const Step& sp, const Aux& ax, bool has, bool cut) {
+        return bwd_combine1<ND>(E, bwd_row_elem1<ND>(sp, ax, has, cut));
+    }
+    static SSDE_HD Adj bwd_apply_row(const Step& sp, const Aux& ax, bool has, bool cut, const Adj& g) {
+        return bwd_apply1<ND>(bwd_row_elem1<ND>(sp, ax, has, cut), g);
+    }
     static SSDE_HD bool bwd_is_const(const BwdElem& E) { return tiny(E.L); }
     static SSDE_HD StepBlk<1, R> to_blk(const Step& sp) {
         StepBlk<1, R> k;
@@ -269,7 +289,6 @@ struct OuSsmModel : Ssm1Base<ND_, R_> {
     static constexpr int ND = ND_;
     static constexpr int NP = ND + 2;
     static constexpr int NW = 3;
-    static constexpr int NC = 2;
     struct RowPar { R tau, e, kappa; };
     static SSDE_HD RowPar transform(const R* eta, double dt) {
         RowPar r;
@@ -286,12 +305,6 @@ struct OuSsmModel : Ssm1Base<ND_, R_> {
         sp.t = r.e;
         sp.cm = 1.0 - r.e;                                   // makeB_ou_ssm :50
         sp.q = r.kappa * (1.0 - exp(-2.0 * dt / r.tau));     // makeQ_ou_ssm :66 (its own exp, as in the reference)
-        return sp;
-    }
-    template <class F> static SSDE_HD void store_step(const typename B::Step& sp, F at) { at(0) = sp.t; at(1) = sp.q; }
-    template <class F> static SSDE_HD typename B::Step load_step(F at, double) {
-        typename B::Step sp;
-        sp.t = at(0); sp.q = at(1); sp.cm = 1.0 - sp.t;
         return sp;
     }
     // t = e, cm = 1 - e, q = kappa (1 - e2), e = exp(-dt/tau), e2 = exp(-2 dt/tau), tau = exp(eta_tau)
@@ -322,7 +335,6 @@ struct BmSsmModel : Ssm1Base<ND_, R_> {
     static constexpr int ND = ND_;
     static constexpr int NP = ND + 1;
     static constexpr int NW = 1;
-    static constexpr int NC = 1;
     struct RowPar { R s2; };
     static SSDE_HD RowPar transform(const R* eta, double) {
         const R sigma = exp(eta[ND]);
@@ -336,12 +348,6 @@ struct BmSsmModel : Ssm1Base<ND_, R_> {
         sp.t = 1.0;                                          // T = I, nllk_bm_ssm.hpp:100-101
         sp.cm = dt;                                          // drift = mu * dt, :140
         sp.q = r.s2 * dt;                                    // makeQ_bm_ssm :32
-        return sp;
-    }
-    template <class F> static SSDE_HD void store_step(const typename B::Step& sp, F at) { at(0) = sp.q; }
-    template <class F> static SSDE_HD typename B::Step load_step(F at, double dt) {
-        typename B::Step sp;
-        sp.t = 1.0; sp.cm = dt; sp.q = at(0);
         return sp;
     }
     static SSDE_HD void row_param_grad(const typename B::Adj& g, const typename B::Step& sp, const typename B::Aux& ax, const R* mu,
@@ -371,8 +377,7 @@ struct DenseModel {
     static constexpr int NS = N * (N + 1) / 2;
     static constexpr int FS = N + NS;
     static constexpr int NW = Base::NW;
-    static constexpr int NC = Base::NC;
-    static constexpr int KNT = 64, MINB = 1;     // wide elements: half-size CTAs, one per SM
+    static constexpr int KNT = 64, MINB = 1, FMINB = 1;     // wide elements: half-size CTAs, one per SM
     static constexpr int LOGF_MULT = 1;          // F_out is det F
     using State = DState<N, R>;
     using Adj = DAdj<N, R>;
@@ -402,8 +407,6 @@ struct DenseModel {
     template <class F> static SSDE_HD void store_rowpar(const RowPar& r, F at) { Base::store_rowpar(r, at); }
     template <class F> static SSDE_HD RowPar load_rowpar(F at) { return Base::load_rowpar(at); }
     static SSDE_HD Step make_step(const RowPar& r, double dt) { return Base::make_step(r, dt); }
-    template <class F> static SSDE_HD void store_step(const Step& sp, F at) { Base::store_step(sp, at); }
-    template <class F> static SSDE_HD Step load_step(F at, double dt) { return Base::load_step(at, dt); }
 
     static SSDE_HD State start_state(const double* a0row, const PriorCov& P0) {
         State s;
@@ -482,6 +485,12 @@ struct DenseModel {
     }
     static SSDE_HD BwdElem bwd_combine(const BwdElem& a, const BwdElem& b) { return dbwd_combine<N>(a, b); }
     static SSDE_HD Adj bwd_apply(const BwdElem& E, const Adj& g) { return dbwd_apply<N>(E, g); }
+    static SSDE_HD BwdElem bwd_append_row(const BwdElem& E, const Step& sp, const Aux& ax, bool has, bool cut) {
+        return dbwd_combine<N>(E, bwd_row_elem(sp, ax, has, cut));
+    }
+    static SSDE_HD Adj bwd_apply_row(const Step& sp, const Aux& ax, bool has, bool cut, const Adj& g) {
+        return dbwd_apply<N>(bwd_row_elem(sp, ax, has, cut), g);
+    }
     static SSDE_HD bool bwd_is_const(const BwdElem& E) {
         bool c = true;
 #pragma unroll

@@ -845,7 +845,7 @@ template <class M>
 int ctcrw_grids(ssde_handle* h) {
     std::string& err = h->err;
     int rc;
-    if ((rc = max_grid(ctcrw_fwd_kernel<M, M::KNT, M::MINB>, M::KNT, sizeof(FwdSmem<M, M::KNT>), h->num_sms, err, h->grid_f))) return rc;
+    if ((rc = max_grid(ctcrw_fwd_kernel<M, M::KNT, M::FMINB>, M::KNT, sizeof(FwdSmem<M, M::KNT>), h->num_sms, err, h->grid_f))) return rc;
     if ((rc = max_grid(ctcrw_bwd_kernel<M, M::KNT, M::MINB>, M::KNT, sizeof(BwdSmem<M, M::KNT>), h->num_sms, err, h->grid_b))) return rc;
     return SSDE_OK;
 }
@@ -1035,7 +1035,7 @@ int launch_ctcrw_fwd(ssde_handle* h, const double* d_par, const double* d_dir, c
     a.tile_lo = (summary && tail) ? std::max(h->ntiles_f - TAIL_TILES, 0) : 0;
     mark(h, st, TAN ? "ctcrw_fwd_tangent" : (summary ? (tail ? "ctcrw_fwd_tail" : "ctcrw_fwd_summary") : "ctcrw_fwd"));
     if constexpr (TAN) ctcrw_fwd_kernel<M, M::KNT, TAN_MINB><<<h->grid_f2, M::KNT, sizeof(FwdSmem<M, M::KNT>), st>>>(a);
-    else ctcrw_fwd_kernel<M, M::KNT, M::MINB><<<h->grid_f, M::KNT, sizeof(FwdSmem<M, M::KNT>), st>>>(a);
+    else ctcrw_fwd_kernel<M, M::KNT, M::FMINB><<<h->grid_f, M::KNT, sizeof(FwdSmem<M, M::KNT>), st>>>(a);
     CUDA_TRY(cudaGetLastError());
     return SSDE_OK;
 }

@@ -155,7 +155,7 @@ static int run(int mode, int64_t n, const uint8_t* flags, const double* y, const
         M::row_param_grad(gin, r.sp, ax, r.mu, r.rp, r.dt, r.obs, hrow(i), gp, g_h);
         for (int c = 0; c < NP; ++c) put(i, c, gp[c]);
         gh += g_h;
-        g = M::bwd_apply(M::bwd_row_elem(r.sp, ax, r.obs, r.last), g);
+        g = M::bwd_apply_row(r.sp, ax, r.obs, r.last, g);         // as the adjoint kernel's sweep does
     };
     if (mode == 0) {
         typename M::Adj g = M::adj_zero();
@@ -168,15 +168,13 @@ static int run(int mode, int64_t n, const uint8_t* flags, const double* y, const
             typename M::BwdElem E = M::bwd_identity();
             for (int64_t i = c * chunk; i < (c + 1) * chunk && i < n; ++i) {
                 const Row<M>& r = rows[i];
-                typename M::BwdElem el;
-                if (r.start) el = M::bwd_const(M::adj_zero());
+                if (r.start) E = M::bwd_combine(E, M::bwd_const(M::adj_zero()));
                 else {
                     typename M::State s = pre[i];
                     typename M::Aux ax;
                     step_llk(s, r, &ax);
-                    el = M::bwd_row_elem(r.sp, ax, r.obs, r.last);
+                    E = M::bwd_append_row(E, r.sp, ax, r.obs, r.last);   // as the adjoint kernel's element phase does
                 }
-                E = M::bwd_combine(E, el);
             }
             agg[c] = E;
         }
