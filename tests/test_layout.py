@@ -139,6 +139,21 @@ def test_parameters_with_the_same_smooth_share_their_value_slots(monkeypatch):
     assert np.allclose(eta_from_pack(pk5, info5["n"], 3, th5), dense_eta(dat5, th5, info5["n"], 3), rtol=1e-13, atol=1e-13)
 
 
+def test_three_parameters_sharing_one_smooth_alias_the_first():
+    """BM, d = 2: mu1, mu2, sigma ~ s(time): parameters 1 and 2 both read parameter 0's value slots (the second
+    one is not adjacent to its target: the kernels' unpaired path)."""
+    dat, par, info = synth.make_problem("BM", 2, 300, n_dim=2, seed=9)
+    n = info["n"]
+    pk = pack_host(dat)
+    for d in pk["desc"][: (n + 255) // 256]:
+        kb = [(int(d["kmax"]) >> (8 * p)) & 255 for p in range(4)]
+        assert kb[0] == kb[1] == kb[2] and kb[3] == 0
+        assert [alias_of(d["flags"], p) for p in range(3)] == [-1, 0, 0]
+        assert value_slots(kb, d["flags"]) == (kb[0], [0, 0, 0, kb[0]])
+    theta = np.random.default_rng(5).normal(size=info["p_fe"] + info["p_re"])
+    assert np.allclose(eta_from_pack(pk, n, 3, theta), dense_eta(dat, theta, n, 3), rtol=1e-13, atol=1e-13)
+
+
 def test_irregular_sparsity_falls_back_to_per_nonzero_columns():
     rng = np.random.default_rng(3)
     n, n_par, p_re = 700, 2, 60
