@@ -45,20 +45,6 @@
 #ifndef SSDE_THETA_REUSE
 #define SSDE_THETA_REUSE 1
 #endif
-// 1: the transformed parameters (tau, e, s2) that the forward kernel hands to the adjoint kernel are
-// stored row-step by row-step, [n_pad / 32][NW][32] -- one pointer and constant offsets per row --
-// instead of as NW planes of n_pad
-#ifndef SSDE_WG_INTERLEAVED
-#define SSDE_WG_INTERLEAVED 1
-#endif
-// 1: dt / obs (and in the adjoint kernel tau, e, s2) of a row are loaded without a "row exists" predicate
-#ifndef SSDE_UNCOND_ROW_LOADS
-#define SSDE_UNCOND_ROW_LOADS 1
-#endif
-// 1: a tile's flags / dt / observations are requested before the design descriptor is waited for
-#ifndef SSDE_EARLY_ROW_LOADS
-#define SSDE_EARLY_ROW_LOADS 1
-#endif
 
 namespace ssde {
 
@@ -132,7 +118,9 @@ struct RowPlanes {
     const typename M::R* wg[M::NW];
     const double* dt;
     const double* obs[M::ND];
-    static constexpr int WGS = SSDE_WG_INTERLEAVED ? 32 * M::NW : 32;     // wg: elements between two rows of a lane
+    // tau, e, s2 (forward -> adjoint) are stored row-step by row-step, [n_pad / 32][NW][32]: one pointer and
+    // constant offsets per row
+    static constexpr int WGS = 32 * M::NW;          // wg: elements between two rows of a lane
 };
 template <class M>
 __device__ __forceinline__ RowPlanes<M> open_planes(const KalmanArgs<typename M::R>& a, int64_t base, bool with_wg, bool prefetch) {
@@ -140,11 +128,7 @@ __device__ __forceinline__ RowPlanes<M> open_planes(const KalmanArgs<typename M:
     const int64_t np = a.X.n_pad;
 #pragma unroll
     for (int c = 0; c < M::NW; ++c) {
-#if SSDE_WG_INTERLEAVED
         p.wg[c] = a.wg + (size_t)(base - (threadIdx.x & 31)) * M::NW + c * 32 + (threadIdx.x & 31);
-#else
-        p.wg[c] = a.wg + (size_t)c * np + base;
-#endif
     }
     p.dt = a.dt + base;
 #pragma unroll
@@ -154,11 +138,7 @@ __device__ __forceinline__ RowPlanes<M> open_planes(const KalmanArgs<typename M:
         const int64_t q0 = base - lane;                       // first element of the warp-tile in every plane
         if (lane == 0) prefetch_l2(a.dt + q0, WT * 8);
         else if (lane <= M::ND) prefetch_l2(a.obs + (size_t)(lane - 1) * np + q0, WT * 8);
-#if SSDE_WG_INTERLEAVED
         else if (with_wg && lane <= M::ND + M::NW) prefetch_l2(a.wg + (size_t)q0 * M::NW + (size_t)(lane - 1 - M::ND) * WT, WT * (unsigned)sizeof(typename M::R));
-#else
-        else if (with_wg && lane <= M::ND + M::NW) prefetch_l2(a.wg + (size_t)(lane - 1 - M::ND) * np + q0, WT * (unsigned)sizeof(typename M::R));
-#endif
     }
     return p;
 }
@@ -220,14 +200,12 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(KalmanArgs<typename
         const int64_t q = (int64_t)tile * NWARP + warp;
         const int64_t base = q * WT + lane;
         const int64_t row0 = q * WT + (int64_t)lane * LC;
-#if SSDE_EARLY_ROW_LOADS
         // flags, dt and observations depend on the ticket only: request them before the descriptor chain
         const unsigned long long fl = load_flags8(a.flags, base);
         const RowPlanes<M> pl = open_planes<M>(a, base, false, SSDE_PLANE_PREFETCH != 0);
         double dt_nx = ((uint8_t)fl != 0xff) ? pl.dt[0] : 1.0, y_nx[ND];
 #pragma unroll
         for (int d = 0; d < ND; ++d) y_nx[d] = ((uint8_t)fl != 0xff) ? pl.obs[d][0] : 0.0;
-#endif
         const WtViewT<R> w = open_warptile<R>(a.X, q, a.theta, sm.th[warp], true, SSDE_THETA_REUSE ? &tkey : nullptr);
         if constexpr (DENSE_ETA) {
             if (w.staged && (!SSDE_THETA_REUSE || tkey.fresh)) fill_theta_matrix(w, sm.thm[warp]);
@@ -240,19 +218,10 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(KalmanArgs<typename
             prefetch_l2(w.blk + (size_t)w.SV * 32, (unsigned)(2 * w.SV * 32 * 8));
 #endif
         }
-#if !SSDE_EARLY_ROW_LOADS
-        const unsigned long long fl = load_flags8(a.flags, base);
-#endif
 
         // (1) thread element over its LC rows
         Elem E = M::fwd_identity();
         // dt and the observations of a row are fetched one row ahead of their use
-#if !SSDE_EARLY_ROW_LOADS
-        const RowPlanes<M> pl = open_planes<M>(a, base, false, SSDE_PLANE_PREFETCH != 0);
-        double dt_nx = ((uint8_t)fl != 0xff) ? pl.dt[0] : 1.0, y_nx[ND];
-#pragma unroll
-        for (int d = 0; d < ND; ++d) y_nx[d] = ((uint8_t)fl != 0xff) ? pl.obs[d][0] : 0.0;
-#endif
         const unsigned step_bytes = (unsigned)w.SV * 32u * 8u;      // one row-step of design values
         const size_t step_dbl = (size_t)w.SV * 32;
         const double* next_step = w.blk + step_dbl;                 // row-step k + 1
@@ -267,16 +236,9 @@ __global__ void __launch_bounds__(NT, MINB) ctcrw_fwd_kernel(KalmanArgs<typename
 #pragma unroll
             for (int d = 0; d < ND; ++d) y[d] = y_nx[d];
             if (k + 1 < LC) {
-#if SSDE_UNCOND_ROW_LOADS
                 dt_nx = pl.dt[(k + 1) * 32];                 // n_pad entries exist; a padding row's values are never used
 #pragma unroll
                 for (int d = 0; d < ND; ++d) y_nx[d] = pl.obs[d][(k + 1) * 32];
-#else
-                const bool live1 = (uint8_t)(fl >> (8 * (k + 1))) != 0xff;
-                dt_nx = live1 ? pl.dt[(k + 1) * 32] : 1.0;
-#pragma unroll
-                for (int d = 0; d < ND; ++d) y_nx[d] = live1 ? pl.obs[d][(k + 1) * 32] : 0.0;
-#endif
             }
             R eta[NP];
             if (w.staged) {
@@ -489,7 +451,6 @@ template <class M>
 __device__ __forceinline__ RowIn<M> load_row(const RowPlanes<M>& p, int k, bool live) {
     RowIn<M> r;
     const int o = k * 32;
-#if SSDE_UNCOND_ROW_LOADS
     // every per-row array is n_pad long and nothing loaded for a row that is not a filter step is ever
     // used (the callers branch on the row's flags), so the loads need no predicate
     (void)live;
@@ -497,12 +458,6 @@ __device__ __forceinline__ RowIn<M> load_row(const RowPlanes<M>& p, int k, bool 
     r.rp = M::load_rowpar([&](int c) { return p.wg[c][k * RowPlanes<M>::WGS]; });
 #pragma unroll
     for (int d = 0; d < M::ND; ++d) r.y[d] = p.obs[d][o];
-#else
-    r.dt = live ? p.dt[o] : 1.0;
-    r.rp = live ? M::load_rowpar([&](int c) { return p.wg[c][k * RowPlanes<M>::WGS]; }) : M::dead_rowpar();
-#pragma unroll
-    for (int d = 0; d < M::ND; ++d) r.y[d] = live ? p.obs[d][o] : 0.0;
-#endif
     return r;
 }
 

@@ -36,11 +36,6 @@ struct PriorCov {
 #define SSDE_FWD_MINB 4
 #endif
 constexpr int KNT_DEFAULT = SSDE_KNT, MINB_DEFAULT = SSDE_MINB, FMINB_DEFAULT = SSDE_FWD_MINB;
-// 1: the CTCRW adjoint kernel appends / applies a row from its step quantities (ctcrw_math.cuh:
-// bwd_append_row, bwd_apply_row) instead of building the general element and combining it
-#ifndef SSDE_BWD_ROW_SPECIAL
-#define SSDE_BWD_ROW_SPECIAL 1
-#endif
 
 constexpr double CONST_MAP_TOL = 1e-60;     // see FwdOps / is_const in common.cuh
 // The device reads the threshold from constant memory so that tests can switch the constant-map
@@ -154,18 +149,10 @@ struct CtcrwModel {
     static SSDE_HD Adj bwd_apply(const BwdElem& E, const Adj& g) { return ssde::bwd_apply<ND>(E, g); }
     // one row appended to / applied from its step quantities: the row element's structural zeros are skipped
     static SSDE_HD BwdElem bwd_append_row(const BwdElem& E, const Step& sp, const Aux& ax, bool has, bool cut) {
-#if SSDE_BWD_ROW_SPECIAL
         return ssde::bwd_append_row<ND>(E, sp, ax, has, cut);
-#else
-        return ssde::bwd_combine<ND>(E, ssde::bwd_row_elem<ND>(sp, ax, has, cut));
-#endif
     }
     static SSDE_HD Adj bwd_apply_row(const Step& sp, const Aux& ax, bool has, bool cut, const Adj& g) {
-#if SSDE_BWD_ROW_SPECIAL
         return ssde::bwd_apply_row<ND>(sp, ax, has, cut, g);
-#else
-        return ssde::bwd_apply<ND>(ssde::bwd_row_elem<ND>(sp, ax, has, cut), g);
-#endif
     }
     static SSDE_HD bool bwd_is_const(const BwdElem& E) { return tiny(E.L); }
     // gp[NP] = d nllk / d eta of this row
