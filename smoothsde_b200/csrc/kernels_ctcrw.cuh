@@ -6,14 +6,18 @@
 // "constant map" element, so the whole stack is ONE segmented scan and the same two kernels serve
 // many short tracks, few long tracks and a single 1e8-row track.  Work decomposition (layout in
 // design.cuh): tile = NT/32 warp-tiles, tiles taken from a dynamic ticket,
-//   (1) each thread walks its LC rows: coalesced loads of the design slots -> eta -> natural
-//       scale step matrices (kept in shared memory, never in HBM) -> composes the rows into one
-//       scan element (fwd_append),
+//   (1) each thread walks its LC rows: TMA-staged design values -> eta (one pass against a dense
+//       per-warp coefficient table) -> natural-scale parameters (tau, e, s2: to HBM for the adjoint
+//       kernel) -> step matrices in registers -> composes the rows into one scan element
+//       (fwd_append),
 //   (2) warp shuffle scan + cross-warp scan of the thread elements,
 //   (3) chained look-back across tiles gives the state at the tile start,
-//   (4) each thread re-runs the plain filter over its rows from its exact start state.
+//   (4) one checkpoint per thread chunk = its exact start state; only when no adjoint pass
+//       follows (value-only evaluation, REPORT) each thread re-runs the plain filter over its rows
+//       for the likelihood terms.
 // The adjoint kernel walks the tiles in reverse with elements (L, z, D), recomputes the forward
-// states of its rows from one checkpoint per thread chunk and ends with X' eta_bar.
+// states of its rows from the checkpoints -- which yields the likelihood terms of a gradient
+// evaluation as a by-product (llk_bwd) -- and ends with X' eta_bar.
 #pragma once
 
 #include "design.cuh"
@@ -67,8 +71,8 @@ struct KalmanArgs {
     const R* s_in;             // optional incoming state (M::FS scalars) for a continued shard
     const R* g_in;             // optional incoming adjoint (M::FS scalars)
     const int* mu_zero;        // device flag: every mu_d predictor is exactly 0 at these parameters
-    R* wg;                     // [M::NW, n_pad] permuted: transformed parameters of every row (CTCRW: tau,
-                               // e = exp(-dt/tau), s2), forward -> adjoint
+    R* wg;                     // [n_pad / 32][M::NW][32]: transformed parameters of every row (CTCRW: tau,
+                               // e = exp(-dt/tau), s2), row-step-major, forward -> adjoint
     R* ckpt;                   // [M::FS, nchunks] start state of every thread chunk
     int64_t nchunks;           // n_pad / LC
     double* tile_llk;          // [n_pad / WT] one partial log-likelihood per warp-tile

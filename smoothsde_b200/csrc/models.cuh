@@ -82,7 +82,6 @@ struct CtcrwModel {
         transform_row(eta[ND], eta[ND + 1], dt, r.tau, r.e, r.s2);
         return r;
     }
-    static SSDE_HD RowPar dead_rowpar() { return RowPar{R(1.0), R(0.0), R(0.0)}; }
     template <class F> static SSDE_HD void store_rowpar(const RowPar& r, F at) { at(0) = r.tau; at(1) = r.e; at(2) = r.s2; }
     template <class F> static SSDE_HD RowPar load_rowpar(F at) { return RowPar{at(0), at(1), at(2)}; }
     static SSDE_HD Step make_step(const RowPar& r, double dt) { return ssde::make_step(r.tau, r.e, r.s2, dt); }
@@ -284,7 +283,6 @@ struct OuSsmModel : Ssm1Base<ND_, R_> {
         r.e = exp(-dt / r.tau);                              // makeT_ou_ssm :35
         return r;
     }
-    static SSDE_HD RowPar dead_rowpar() { return RowPar{R(1.0), R(0.0), R(0.0)}; }
     template <class F> static SSDE_HD void store_rowpar(const RowPar& r, F at) { at(0) = r.tau; at(1) = r.e; at(2) = r.kappa; }
     template <class F> static SSDE_HD RowPar load_rowpar(F at) { return RowPar{at(0), at(1), at(2)}; }
     static SSDE_HD typename B::Step make_step(const RowPar& r, double dt) {
@@ -327,7 +325,6 @@ struct BmSsmModel : Ssm1Base<ND_, R_> {
         const R sigma = exp(eta[ND]);
         return RowPar{sigma * sigma};
     }
-    static SSDE_HD RowPar dead_rowpar() { return RowPar{R(0.0)}; }
     template <class F> static SSDE_HD void store_rowpar(const RowPar& r, F at) { at(0) = r.s2; }
     template <class F> static SSDE_HD RowPar load_rowpar(F at) { return RowPar{at(0)}; }
     static SSDE_HD typename B::Step make_step(const RowPar& r, double dt) {
@@ -390,7 +387,6 @@ struct DenseModel {
         return H;
     }
     static SSDE_HD RowPar transform(const R* eta, double dt) { return Base::transform(eta, dt); }
-    static SSDE_HD RowPar dead_rowpar() { return Base::dead_rowpar(); }
     template <class F> static SSDE_HD void store_rowpar(const RowPar& r, F at) { Base::store_rowpar(r, at); }
     template <class F> static SSDE_HD RowPar load_rowpar(F at) { return Base::load_rowpar(at); }
     static SSDE_HD Step make_step(const RowPar& r, double dt) { return Base::make_step(r, dt); }
