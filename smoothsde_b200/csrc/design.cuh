@@ -220,7 +220,9 @@ __device__ __forceinline__ void fill_theta_matrix(const WtView& w, double* thm) 
 // SKIP: the first SKIP parameters are known to have all-zero coefficients (mu fixed at 0, the
 // kernels' mu_zero flag): their sums are not formed.  Slots are taken four at a time with constant
 // offsets; the up to three slots past SV meet zero table rows, and the staging buffer only ever
-// holds finite numbers (zeroed at kernel start, then design values / dt / observations).
+// holds finite numbers there (zeroed at kernel start, then design values or the scan elements the
+// forward kernel parks in it -- finite unless the filter itself has already overflowed, in which
+// case the evaluation is NaN either way).
 template <int NP, int SKIP>
 __device__ __forceinline__ void row_eta_dense(const WtView& w, const double* buf, const double* thm, double* eta) {
     static_assert(NP <= MAX_NP && MAX_NP == 4 && SKIP < NP, "two double2 per table row");
